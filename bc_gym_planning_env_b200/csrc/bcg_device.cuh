@@ -1,0 +1,384 @@
+// Device-side building blocks of the batched PlanEnv.step path (sm_100a).
+// Compiled with --fmad=false: every fp64 expression rounds operation by operation like the NumPy
+// reference; the few places where the reference's BLAS route fuses (np.dot in
+// utilities/path_tools.py:145) call fma() explicitly.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bcg_b200.h"
+
+#define BCG_PI 3.141592653589793
+#define BCG_TWO_PI 6.283185307179586
+#define BCG_FULL 0xffffffffu
+
+namespace bcg {
+
+// ---- scalar helpers -------------------------------------------------------------------------
+// Python/NumPy floor-mod for doubles (npy_divmod): result carries the divisor's sign.
+__device__ __forceinline__ double py_mod(double a, double b) {
+  double m = fmod(a, b);
+  if (m != 0.0) {
+    if ((b < 0.0) != (m < 0.0)) m += b;
+  } else {
+    m = copysign(0.0, b);
+  }
+  return m;
+}
+
+// normalize_angle, utilities/coordinate_transformations.py:28-36
+__device__ __forceinline__ double wrap_angle(double z) { return py_mod(z + BCG_PI, BCG_TWO_PI) - BCG_PI; }
+
+// one axis of world_to_pixel, utilities/coordinate_transformations.py:185-205 (np.round = half-even)
+__device__ __forceinline__ int world_to_pixel_1d(double w, double origin, double inv_res) {
+  double r = rint((w - origin) * inv_res);
+  r = fmin(fmax(r, -1073741824.0), 1073741824.0);  // keep later int arithmetic overflow-free
+  return (int)r;
+}
+
+__device__ __forceinline__ double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+
+// ---- Philox4x32-10 + Box-Muller (oracle/plan_env_oracle.py:philox_normals is the CPU twin) ------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// counter = (env id, step index low, block, step index high), key = seed
+__device__ __forceinline__ void philox_normals(uint64_t seed, uint64_t env, uint64_t step, uint32_t block,
+                                               double& z0, double& z1) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)env, (uint32_t)step, block, (uint32_t)(step >> 32)),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint64_t a = ((uint64_t)r.x << 21) | (r.y >> 11);
+  const uint64_t b = ((uint64_t)r.z << 21) | (r.w >> 11);
+  const double u1 = (double)(a + 1) * 0x1.0p-53;  // (0, 1]
+  const double u2 = (double)b * 0x1.0p-53;        // [0, 1)
+  const double rad = sqrt(-2.0 * log(u1));
+  double sn, cs;
+  sincos(BCG_TWO_PI * u2, &sn, &cs);
+  z0 = rad * cs;
+  z1 = rad * sn;
+}
+
+// ---- kinematics --------------------------------------------------------------------------------
+// kinematic_body_pose_motion_step, robot_models/differential_drive.py:21-40
+__device__ __forceinline__ void pose_motion_step(double& x, double& y, double& th, double v, double w, double dt) {
+  const double h = 0.5 * w * dt;
+  const double xs = h / BCG_PI;                       // np.sinc(h / pi)
+  const double ys = BCG_PI * (xs == 0.0 ? 1.0e-20 : xs);
+  const double f = v * dt * (sin(ys) / ys);
+  double sn, cs;
+  sincos(th + h, &sn, &cs);
+  x = x + f * cs;
+  y = y + f * sn;
+  th = wrap_angle(th + w * dt);
+}
+
+// kinematic_body_pose_motion_step_with_noise, robot_models/differential_drive.py:43-74.
+// Normal slots: block 0 = (angular, final rotation), block 1 first half = linear.
+__device__ __forceinline__ void noisy_pose_motion_step(double& x, double& y, double& th, double v, double w,
+                                                       const BcgParams& p, uint64_t env, uint64_t step) {
+  double n_w = 0.0, n_g = 0.0;
+  bool have0 = false;
+  double var = p.alpha[0] * (v * v) + p.alpha[1] * (w * w);
+  if (var > 0.0) {
+    double n_v, unused;
+    philox_normals(p.seed, env, step, 1u, n_v, unused);
+    v = v + sqrt(var) * n_v;
+  }
+  var = p.alpha[2] * (v * v) + p.alpha[3] * (w * w);
+  if (var > 0.0) {
+    philox_normals(p.seed, env, step, 0u, n_w, n_g);
+    have0 = true;
+    w = w + sqrt(var) * n_w;
+  }
+  var = p.alpha[4] * (v * v) + p.alpha[5] * (w * w);
+  double gamma = 0.0;
+  if (var > 0.0) {
+    if (!have0) philox_normals(p.seed, env, step, 0u, n_w, n_g);
+    gamma = sqrt(var) * n_g;
+  }
+  pose_motion_step(x, y, th, v, w, p.dt);
+  th = wrap_angle(th + gamma * p.dt);
+}
+
+// path_velocity on the two-row path the robots build, utilities/path_tools.py:298-323
+__device__ __forceinline__ void measured_velocity(double x0, double y0, double th0, double x1, double y1,
+                                                  double th1, double dt, double& v, double& w) {
+  const double dx = x1 - x0, dy = y1 - y0;
+  double sn, cs;
+  sincos(th0, &sn, &cs);
+  const double proj = cs * dx + sn * dy;
+  double sign = (proj > 0.0) ? 1.0 : ((proj < 0.0) ? -1.0 : 0.0);
+  if (sign == 0.0) {
+    const double alt = sn * dy;
+    sign = (alt > 0.0) ? 1.0 : ((alt < 0.0) ? -1.0 : 0.0);
+  }
+  const double ds = sqrt(dx * dx + dy * dy) * sign;
+  double dth = th1 - th0;
+  if (dth < -BCG_PI) dth += BCG_TWO_PI;
+  if (dth > BCG_PI) dth -= BCG_TWO_PI;
+  v = ds / dt;
+  w = dth / dt;
+}
+
+// TricycleRobot.step (robot_models/tricycle_model.py:478-538) / DiffDriveRobot.step
+// (robot_models/differential_drive.py:236-265).  s[7] = x,y,th,v,w,steer_cmd,wheel, updated in place.
+__device__ __forceinline__ void robot_step(double s[7], double u0, double u1, const BcgParams& p, uint64_t env,
+                                           uint64_t step) {
+  const double x0 = s[0], y0 = s[1], th0 = s[2];
+  double v_new, w_new;
+  if (p.robot_kind == BCG_ROBOT_TRICYCLE) {
+    const double wheel = s[6];
+    // tricycle_front_wheel_column_step :127-154
+    double delta = p.p_gain * (u1 - wheel);
+    delta = clampd(delta, -p.max_wheel_delta, p.max_wheel_delta);
+    const double new_wheel = clampd(wheel + delta, -p.max_wheel_angle, p.max_wheel_angle);
+    // tricycle_velocity_dynamic_model_step :157-188
+    double sn, cs;
+    sincos(new_wheel, &sn, &cs);
+    const double v_des = u0 * cs;
+    const double w_des = u0 * sn / p.wheel_base;
+    const double a_lin = clampd((v_des - s[3]) / p.dt, -2.0 * p.max_lin_acc, p.max_lin_acc);
+    const double a_ang = clampd((w_des - s[4]) / p.dt, -p.max_ang_acc, p.max_ang_acc);
+    v_new = s[3] + a_lin * p.dt;
+    w_new = s[4] + a_ang * p.dt;
+    if (0.0 > v_new) v_new = 0.0;
+    s[5] = wheel - u1;  // :532
+    s[6] = new_wheel;
+  } else {
+    v_new = u0;
+    w_new = u1;
+  }
+  double x = x0, y = y0, th = th0;
+  if (p.noise_on)
+    noisy_pose_motion_step(x, y, th, v_new, w_new, p, env, step);
+  else
+    pose_motion_step(x, y, th, v_new, w_new, p.dt);
+  measured_velocity(x0, y0, th0, x, y, th, p.dt, s[3], s[4]);
+  s[0] = x;
+  s[1] = y;
+  s[2] = th;
+}
+
+// _get_element_from_list_with_delay, envs/base/env.py:27-49, as a circular buffer of `d` slots.
+// q = head | len << 16.  ring rows are laid out slot-major: row(slot, comp) = slot * ncomp + comp.
+template <int NCOMP>
+__device__ __forceinline__ void delay_line(double* ring, int64_t stride, int& q, int d, double v[NCOMP]) {
+  if (d <= 0) return;
+  int head = q & 0xffff, len = q >> 16;
+  if (len < d) {
+    int slot = head + len;
+    if (slot >= d) slot -= d;
+    double front[NCOMP];
+    if (len > 0) {
+#pragma unroll
+      for (int c = 0; c < NCOMP; ++c) front[c] = ring[(int64_t)(head * NCOMP + c) * stride];
+    }
+#pragma unroll
+    for (int c = 0; c < NCOMP; ++c) ring[(int64_t)(slot * NCOMP + c) * stride] = v[c];
+    if (len > 0) {
+#pragma unroll
+      for (int c = 0; c < NCOMP; ++c) v[c] = front[c];
+    }
+    ++len;
+  } else {
+#pragma unroll
+    for (int c = 0; c < NCOMP; ++c) {
+      double* slotp = ring + (int64_t)(head * NCOMP + c) * stride;
+      const double out = *slotp;
+      *slotp = v[c];
+      v[c] = out;
+    }
+    head = (head + 1 == d) ? 0 : head + 1;
+  }
+  q = head | (len << 16);
+}
+
+// ---- footprint table lookup ----------------------------------------------------------------------
+struct FootBin {
+  int bin, xmin, ymin, nrows, width;
+};
+
+// Warp-cooperative.  Picks the angle bin whose stored rounded-vertex tuple equals
+// round_half_even(R(th) * footprint / res) (utilities/path_tools.py:140-150), i.e. the bin whose
+// cv2.fillPoly mask the reference would have rasterised for this exact angle.
+__device__ __forceinline__ FootBin find_foot_bin(const BcgFootprintLut& lut, double th, unsigned lane,
+                                                 uint32_t* status) {
+  double sn, cs;
+  sincos(th, &sn, &cs);
+  int vx = 0, vy = 0;
+  if ((int)lane < lut.n_verts) {
+    const double fx = lut.fp_pix[2 * lane], fy = lut.fp_pix[2 * lane + 1];
+    vx = (int)rint(fma(fy, -sn, fx * cs));
+    vy = (int)rint(fma(fy, cs, fx * sn));
+  }
+  double t = th;
+  if (!(t >= -BCG_PI && t < BCG_PI)) t = wrap_angle(t);
+  int lo = 0, hi = lut.n_bins;  // invariant: edges[lo] <= t < edges[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (t >= __ldg(lut.edges + mid)) lo = mid; else hi = mid;
+  }
+  int bin = lo;
+  bool found = false;
+  // the analytic edges are good to ~1e-15 rad: verify, and look at the neighbours on a miss
+  for (int probe = 0; probe < 9 && !found; ++probe) {
+    int k = lo + ((probe & 1) ? ((probe + 1) >> 1) : -(probe >> 1));
+    if (k < 0) k += lut.n_bins;
+    if (k >= lut.n_bins) k -= lut.n_bins;
+    bool ok = true;
+    if ((int)lane < lut.n_verts) {
+      const int16_t* v = lut.verts + (int64_t)k * 2 * lut.n_verts + 2 * lane;
+      ok = (v[0] == vx) && (v[1] == vy);
+    }
+    if (__all_sync(BCG_FULL, ok)) {
+      bin = k;
+      found = true;
+    }
+  }
+  if (!found && lane == 0) atomicAdd(status + BCG_STATUS_LUT_MISS, 1u);
+  const int16_t* h = lut.header + (int64_t)bin * 4;
+  FootBin fb;
+  fb.bin = bin;
+  fb.xmin = h[0];
+  fb.ymin = h[1];
+  fb.nrows = h[2];
+  fb.width = h[3];
+  return fb;
+}
+
+// 32 mask bits starting at bit `rel` of a multi-word row mask (bit b <-> column xmin + b)
+__device__ __forceinline__ uint32_t mask_bits32(const uint64_t* row, int wpr, int rel) {
+  if (rel <= -32 || rel >= wpr * 64) return 0u;
+  if (rel < 0) return (uint32_t)(__ldg(row) << (-rel));
+  const int j = rel >> 6, off = rel & 63;
+  uint64_t lo = __ldg(row + j) >> off;
+  if (off > 32 && j + 1 < wpr) lo |= __ldg(row + j + 1) << (64 - off);
+  return (uint32_t)lo;
+}
+
+// pose_collides (envs/base/env.py:464-489) on the lethal tile plane.  Warp-cooperative; returns the
+// warp-uniform verdict.  If COUNT, *pixels gets the number of in-map footprint pixels.
+template <bool COUNT>
+__device__ __forceinline__ bool collide_tiles(const BcgParams& p, const BcgBatch& b, const BcgMapDesc& m, double x,
+                                              double y, double th, unsigned lane, int* pixels) {
+  const FootBin fb = find_foot_bin(b.lut, th, lane, b.status);
+  const int px = world_to_pixel_1d(x, m.origin_x, p.inv_resolution);
+  const int py = world_to_pixel_1d(y, m.origin_y, p.inv_resolution);
+  const int X0 = px + fb.xmin, Y0 = py + fb.ymin;
+  const int X1 = X0 + fb.width - 1, Y1 = Y0 + fb.nrows - 1;
+  unsigned hit = 0;
+  int cnt = 0;
+  if (!(X1 < 0 || Y1 < 0 || X0 >= m.width || Y0 >= m.height)) {
+    const int tx0 = max(X0, 0) >> 5, tx1 = min(X1, m.width - 1) >> 5;
+    const int ty0 = max(Y0, 0) >> 4, ty1 = min(Y1, m.height - 1) >> 4;
+    const int ntx = tx1 - tx0 + 1;
+    const int items = ntx * (ty1 - ty0 + 1) * 16;
+    const uint32_t* tiles = b.tile_arena + m.tile_off;
+    const uint64_t* rows = b.lut.rows + (int64_t)fb.bin * b.lut.max_rows * b.lut.wpr;
+    for (int it = lane; it < items; it += 32) {
+      const int r = it & 15, t = it >> 4;
+      const int ty = ty0 + t / ntx, tx = tx0 + t % ntx;
+      const int Y = (ty << 4) + r;
+      const int dy = Y - Y0;
+      if (dy < 0 || dy >= fb.nrows || Y >= m.height) continue;
+      const uint32_t mbits = mask_bits32(rows + (int64_t)dy * b.lut.wpr, b.lut.wpr, (tx << 5) - X0);
+      if (mbits == 0u) continue;
+      const uint32_t word = __ldg(tiles + ((int64_t)(ty * m.tiles_x + tx) << 4) + r);
+      hit |= word & mbits;
+      if (COUNT) {
+        const int over = (tx << 5) + 32 - m.width;  // columns of this tile beyond the map
+        const uint32_t valid = over > 0 ? (0xffffffffu >> over) : 0xffffffffu;
+        cnt += __popc(mbits & valid);
+      }
+    }
+  }
+  if (COUNT) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(BCG_FULL, cnt, o);
+    *pixels = cnt;
+  }
+  return __any_sync(BCG_FULL, hit != 0u);
+}
+
+// The same verdict read straight from the uint8 costmap rows: each half-warp owns one footprint row
+// per pass, each lane one aligned 4-byte word of it.
+__device__ __forceinline__ bool collide_u8(const BcgParams& p, const BcgBatch& b, const BcgMapDesc& m, double x,
+                                           double y, double th, unsigned lane) {
+  const FootBin fb = find_foot_bin(b.lut, th, lane, b.status);
+  const int px = world_to_pixel_1d(x, m.origin_x, p.inv_resolution);
+  const int py = world_to_pixel_1d(y, m.origin_y, p.inv_resolution);
+  const int X0 = px + fb.xmin, Y0 = py + fb.ymin;
+  const int X1 = X0 + fb.width - 1;
+  unsigned hit = 0;
+  if (!(X1 < 0 || X0 >= m.width)) {
+    const int w0 = max(X0, 0) >> 2, w1 = min(X1, m.width - 1) >> 2;
+    const uint8_t* data = b.map_arena + m.data_off;
+    const uint64_t* rows = b.lut.rows + (int64_t)fb.bin * b.lut.max_rows * b.lut.wpr;
+    const int half = lane >> 4, sub = lane & 15;
+    for (int dy = half; dy < fb.nrows; dy += 2) {
+      const int Y = Y0 + dy;
+      if (Y < 0 || Y >= m.height) continue;
+      const uint32_t* rowp = reinterpret_cast<const uint32_t*>(data + (int64_t)Y * m.pitch);
+      for (int wi = w0 + sub; wi <= w1; wi += 16) {
+        const uint32_t m4 = mask_bits32(rows + (int64_t)dy * b.lut.wpr, b.lut.wpr, (wi << 2) - X0) & 0xfu;
+        if (m4 == 0u) continue;
+        const uint32_t bytes = __ldg(rowp + wi);
+        const uint32_t eq = __vcmpeq4(bytes, 0xFEFEFEFEu);                 // 0xFF where cell == 254
+        const uint32_t sel = ((m4 * 0x00204081u) & 0x01010101u) * 0xFFu;  // 0xFF where the mask is set
+        hit |= eq & sel;
+      }
+    }
+  }
+  return __any_sync(BCG_FULL, hit != 0u);
+}
+
+// ---- reward -----------------------------------------------------------------------------------------
+// find_last_reached (utilities/path_tools.py:408-448) restricted to indices >= lo:
+// max i with hypot < sp, |wrap(dth)| < ap, parallel distance >= -sp/9.  Chunks of 32 points whose
+// bounding circle is farther than sp from the pose cannot contain a reached point and are skipped.
+// Warp-cooperative; returns -1 when nothing is reached.
+__device__ __forceinline__ int last_reached_from(const BcgParams& p, const BcgBatch& b, const BcgPathDesc& pd, int lo,
+                                                 double px, double py, double pth, unsigned lane) {
+  if (lo >= pd.n) return -1;
+  const double* P = b.path_arena + pd.off;
+  const double* C = b.path_arena + pd.chunk_off;
+  const double par_thr = -p.spatial_precision / 9;
+  const int c_lo = lo >> 5, c_hi = (pd.n - 1) >> 5;
+  for (int g = c_hi >> 5; g >= (c_lo >> 5); --g) {
+    const int c = (g << 5) + lane;
+    bool near = false;
+    if (c >= c_lo && c <= c_hi) {
+      const double cx = __ldg(C + c), cy = __ldg(C + pd.chunk_pitch + c), cr = __ldg(C + 2 * pd.chunk_pitch + c);
+      near = (hypot(cx - px, cy - py) - cr) < p.spatial_precision;
+    }
+    unsigned bits = __ballot_sync(BCG_FULL, near);
+    while (bits) {
+      const int cl = 31 - __clz(bits);
+      bits &= ~(1u << cl);
+      const int i = (((g << 5) + cl) << 5) + lane;
+      bool reached = false;
+      if (i >= lo && i < pd.n) {
+        const double xi = __ldg(P + i), yi = __ldg(P + pd.pitch + i), ti = __ldg(P + 2 * pd.pitch + i);
+        const double ci = __ldg(P + 3 * pd.pitch + i), si = __ldg(P + 4 * pd.pitch + i);
+        const double dist = hypot(xi - px, yi - py);
+        const double ang = fabs(wrap_angle(pth - ti));
+        const double par = ci * (px - xi) + si * (py - yi);
+        reached = (dist < p.spatial_precision) && (ang < p.angular_precision) && (par >= par_thr);
+      }
+      const unsigned rb = __ballot_sync(BCG_FULL, reached);
+      if (rb) return (((g << 5) + cl) << 5) + (31 - __clz(rb));
+    }
+  }
+  return -1;
+}
+
+}  // namespace bcg

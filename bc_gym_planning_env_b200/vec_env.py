@@ -1,0 +1,424 @@
+"""VecPlanEnv: N independent `PlanEnv`s stepped as one batch on a B200.
+
+State lives in HBM as structure-of-arrays (fp64 rows x N, int32 rows x N; row map in
+include/bcg_b200.h), costmaps and refined paths in arenas with per-map / per-path descriptors.
+`step` is one call into the C-ABI (`bcg_step`): kinematics -> collision -> reward -> done
+(-> egocentric observation), i.e. reference envs/base/env.py:334-361 for every env at once.
+PyTorch is used for device memory, streams and (elsewhere) torch.distributed only.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from bc_gym_planning_env_b200 import _native as nat
+from bc_gym_planning_env_b200.envs.base.params import EnvParams
+from bc_gym_planning_env_b200.footprint_lut import FootprintLut
+from bc_gym_planning_env_b200.robot_models.robot_dimensions import TRICYCLE, get_dimensions_example
+from bc_gym_planning_env_b200.utilities.costmap_2d import CostMap2D
+from bc_gym_planning_env_b200.utilities.path_tools import refine_path
+
+# PlanEnv's hard-wired odometry noise (reference envs/base/env.py:226-232)
+DEFAULT_NOISE = dict(alpha1=0.0, alpha2=0.0, alpha3=1.e-2, alpha4=1.e-2, alpha5=1.e-3, alpha6=1.e-3)
+
+EGO_X_BOUNDS = (-0.5, 3.)   # reference envs/egocentric.py:113-114
+EGO_Y_BOUNDS = (-2., 2.)
+
+_LUT_CACHE = {}
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def footprint_lut_for(robot_name, resolution, footprint_scale=1.0):
+    key = (robot_name, float(resolution), float(footprint_scale))
+    if key not in _LUT_CACHE:
+        dims = get_dimensions_example(robot_name)
+        _LUT_CACHE[key] = FootprintLut(dims.footprint() * footprint_scale, resolution)
+    return _LUT_CACHE[key]
+
+
+class VecObservation(object):
+    """Batched Observation (reference envs/base/obs.py:14-23): views into the live state tensors --
+    like the reference's Observation they alias env state and change on the next step."""
+
+    def __init__(self, env):
+        self._env = env
+        sf, si = env.state_f, env.state_i
+        self.pose = sf[nat.F_DPOSE:nat.F_DPOSE + 3].t()            # [N, 3] delayed pose
+        self.robot_state = sf[nat.F_DROBOT:nat.F_DROBOT + 7].t()   # [N, 7] delayed robot state
+        self.time = sf[nat.F_TIME]
+        self.target_idx = si[nat.I_TARGET]
+        self.dt = env.params.dt
+
+    def path(self, e):
+        """Remaining path of env e (`path[target_idx:]`, reference envs/base/env.py:421-433)."""
+        return self._env.full_path(e)[int(self.target_idx[e]):]
+
+    def costmap(self, e):
+        return self._env.costmap(e)
+
+
+class VecState(object):
+    """Snapshot of k env columns (reference `State`, envs/base/env.py:52-68): fp64 rows [F, k] and
+    int32 rows [I, k].  Costmaps and paths are immutable per env, so a snapshot holds no copy of them."""
+
+    def __init__(self, f, i):
+        self.f, self.i = f, i
+
+    def clone(self):
+        return VecState(self.f.clone(), self.i.clone())
+
+
+class VecPlanEnv(object):
+    def __init__(self, costmaps, paths, params=None, n_envs=None, map_ids=None, path_ids=None,
+                 noise_parameters=DEFAULT_NOISE, seed=0, auto_reset=False, device=None, env_id_base=0,
+                 private_map_copies=False, with_ego=False, footprint_scale=1.0):
+        """
+        :param costmaps: pool of CostMap2D (uint8), one resolution
+        :param paths: pool of oriented paths, array(n, 3); refined here when params.refine_path
+        :param params EnvParams: shared by the batch
+        :param map_ids, path_ids: [n_envs] indices into the pools (default: env e uses entry e % len)
+        :param noise_parameters: dict alpha1..alpha6 or None (noise off); PlanEnv's default is on
+        :param private_map_copies: give every env its own copy of its costmap in HBM (pool replicated
+            on device) instead of sharing pool entries
+        """
+        nat.require_cuda()
+        self.params = params if params is not None else EnvParams()
+        self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+        if self.device.type != 'cuda':
+            raise nat.BcgError("VecPlanEnv runs on a CUDA device only (no CPU path)")
+        costmaps = list(costmaps)
+        paths = list(paths)
+        if not costmaps or not paths:
+            raise ValueError("need at least one costmap and one path")
+        self.n_envs = int(n_envs if n_envs is not None else max(len(costmaps), len(paths)))
+        n = self.n_envs
+        self._map_pool = costmaps
+        self._map_ids_host = (np.arange(n) % len(costmaps)) if map_ids is None else np.asarray(map_ids, dtype=np.int64)
+        self._path_ids_host = (np.arange(n) % len(paths)) if path_ids is None else np.asarray(path_ids, dtype=np.int64)
+        assert self._map_ids_host.shape == (n,) and self._path_ids_host.shape == (n,)
+        self.resolution = float(costmaps[0].get_resolution())
+        self.dims = get_dimensions_example(self.params.robot_name)
+        self.robot_kind = nat.ROBOT_TRICYCLE if self.dims.drive_type == TRICYCLE else nat.ROBOT_DIFFDRIVE
+        self.auto_reset = bool(auto_reset)
+        self.with_ego = bool(with_ego)
+        self._step_index = 0
+
+        self._c_params = self._make_params(noise_parameters, seed, env_id_base)
+        self.layout = nat.state_layout(self._c_params)
+        self._upload_maps(costmaps, private_map_copies)
+        self._upload_paths(paths)
+        self._upload_lut(footprint_lut_for(self.params.robot_name, self.resolution, footprint_scale))
+        self._alloc_state()
+        self._make_batch()
+        s = self._stream()
+        nat.check(nat.lib().bcg_build_lethal_tiles(C.byref(self._batch), 0, self._batch.n_maps, s))
+        nat.check(nat.lib().bcg_init_state(C.byref(self._c_params), C.byref(self._batch), s))
+        self.check_status()
+
+    # ---- setup -------------------------------------------------------------------------------
+    def _make_params(self, noise, seed, env_id_base):
+        p, rp, d = self.params, self.params.reward_provider_params, self.dims
+        cp = nat.BcgParams()
+        cp.dt, cp.resolution, cp.inv_resolution = p.dt, self.resolution, 1. / self.resolution
+        cp.spatial_precision, cp.angular_precision = rp.spatial_precision, rp.angular_precision
+        cp.progress_multiplier = rp.spatial_progress_multiplier
+        cp.wheel_base, cp.max_wheel_angle = d.front_wheel_from_axis, d.max_front_wheel_angle
+        cp.max_wheel_delta = d.max_front_wheel_speed * p.dt
+        cp.p_gain, cp.max_lin_acc, cp.max_ang_acc = d.front_column_model_p_gain, d.max_linear_acceleration, d.max_angular_acceleration
+        if noise is not None:
+            for k in range(6):
+                cp.alpha[k] = float(noise['alpha%d' % (k + 1)])
+        cp.noise_on = 0 if noise is None else 1
+        # egocentric crop geometry (reference envs/egocentric.py:113-119, utilities/costmap_utils.py:46-49)
+        size = np.array([EGO_X_BOUNDS[1] - EGO_X_BOUNDS[0], EGO_Y_BOUNDS[1] - EGO_Y_BOUNDS[0]])
+        wh = np.round(size * (1. / self.resolution)).astype(int)
+        cp.ego_w, cp.ego_h = int(wh[0]), int(wh[1])
+        cp.ego_x0, cp.ego_y0 = EGO_X_BOUNDS[0], EGO_Y_BOUNDS[0]
+        cp.ego_world_w = (cp.ego_x0 + self.resolution * cp.ego_w) - cp.ego_x0   # CostMap2D.world_size()
+        cp.ego_world_h = (cp.ego_y0 + self.resolution * cp.ego_h) - cp.ego_y0
+        cp.seed, cp.env_id_base = int(seed) & (2 ** 64 - 1), int(env_id_base)
+        cp.robot_kind = self.robot_kind
+        cp.delay_control, cp.delay_pose, cp.delay_state = p.control_delay, p.pose_delay, p.state_delay
+        cp.iteration_timeout = p.iteration_timeout
+        cp.auto_reset = 1 if self.auto_reset else 0
+        return cp
+
+    def _to_device(self, arr):
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+        return t.to(self.device, non_blocking=False)
+
+    def _upload_maps(self, costmaps, private_copies):
+        descs = (nat.BcgMapDesc * len(costmaps))()
+        data_off, tile_off = 0, 0
+        for k, cm in enumerate(costmaps):
+            data = cm.get_data()
+            if data.dtype != np.uint8 or data.ndim != 2:
+                raise TypeError("costmap data must be a 2-d uint8 array")
+            if float(cm.get_resolution()) != self.resolution:
+                raise ValueError("all costmaps of a batch must share one resolution")
+            h, w = data.shape
+            d = descs[k]
+            d.height, d.width, d.pitch = h, w, _round_up(w, 32)
+            d.tiles_x, d.tiles_y = d.pitch // 32, (h + 15) // 16
+            d.origin_x, d.origin_y = float(cm.get_origin()[0]), float(cm.get_origin()[1])
+            d.data_off, d.tile_off = data_off, tile_off
+            data_off += _round_up(h * d.pitch, 128)
+            tile_off += d.tiles_x * d.tiles_y * 16
+        arena = np.zeros(data_off, dtype=np.uint8)
+        for k, cm in enumerate(costmaps):
+            d = descs[k]
+            view = arena[d.data_off:d.data_off + d.height * d.pitch].reshape(d.height, d.pitch)
+            view[:, :d.width] = cm.get_data()
+        pool_bytes, pool_words = data_off, tile_off
+        map_arena = self._to_device(arena)
+        ids = self._map_ids_host
+        if private_copies:
+            # copy index = how many earlier envs use the same pool entry
+            order = np.argsort(ids, kind='stable')
+            copy_idx = np.empty(self.n_envs, dtype=np.int64)
+            sorted_ids = ids[order]
+            starts = np.r_[0, np.flatnonzero(np.diff(sorted_ids)) + 1]
+            run_start = np.repeat(starts, np.diff(np.r_[starts, len(ids)]))
+            copy_idx[order] = np.arange(len(ids)) - run_start
+            copies = int(copy_idx.max()) + 1
+            map_arena = map_arena.repeat(copies)
+            table = (nat.BcgMapDesc * self.n_envs)()
+            for e in range(self.n_envs):
+                C.memmove(C.byref(table[e]), C.byref(descs[int(ids[e])]), C.sizeof(nat.BcgMapDesc))
+                table[e].data_off += int(copy_idx[e]) * pool_bytes
+                table[e].tile_off += int(copy_idx[e]) * pool_words
+            descs = table
+            ids = np.arange(self.n_envs)
+            pool_words *= copies
+        self._map_descs_host = descs
+        self.map_arena = map_arena
+        self.tile_arena = torch.zeros(max(pool_words, 1), dtype=torch.int32, device=self.device)
+        self.map_descs = self._to_device(np.frombuffer(bytes(descs), dtype=np.uint8).copy())
+        self.map_id = self._to_device(ids.astype(np.int32))
+        self._n_maps = len(descs)
+
+    def _upload_paths(self, paths):
+        p = self.params
+        refined, descs = [], (nat.BcgPathDesc * len(paths))()
+        off = 0
+        for k, path in enumerate(paths):
+            path = np.asarray(path, dtype=np.float64)
+            if p.refine_path:
+                path = refine_path(path, p.path_delta)
+            assert path.ndim == 2 and path.shape[1] == 3
+            refined.append(np.ascontiguousarray(path))
+            d = descs[k]
+            d.n, d.pitch = len(path), _round_up(len(path), 4)
+            d.n_chunks = (d.n + 31) // 32
+            d.chunk_pitch = _round_up(d.n_chunks, 4)
+            d.off = off
+            d.chunk_off = off + 5 * d.pitch
+            off = d.chunk_off + 3 * d.chunk_pitch
+        arena = np.zeros(off, dtype=np.float64)
+        for k, path in enumerate(refined):
+            d = descs[k]
+            rows = arena[d.off:d.off + 5 * d.pitch].reshape(5, d.pitch)
+            rows[0, :d.n], rows[1, :d.n], rows[2, :d.n] = path[:, 0], path[:, 1], path[:, 2]
+            rows[3, :d.n], rows[4, :d.n] = np.cos(path[:, 2]), np.sin(path[:, 2])   # as path_tools.py:405 evaluates them
+            ch = arena[d.chunk_off:d.chunk_off + 3 * d.chunk_pitch].reshape(3, d.chunk_pitch)
+            for c in range(d.n_chunks):
+                pts = path[32 * c:32 * c + 32, :2]
+                ctr = 0.5 * (pts.min(axis=0) + pts.max(axis=0))
+                rad = np.hypot(pts[:, 0] - ctr[0], pts[:, 1] - ctr[1]).max()
+                ch[0, c], ch[1, c], ch[2, c] = ctr[0], ctr[1], rad * (1 + 1e-12) + 1e-9   # conservative bound
+        self._paths_host = refined
+        self._path_descs_host = descs
+        self.path_arena = self._to_device(arena)
+        self.path_descs = self._to_device(np.frombuffer(bytes(descs), dtype=np.uint8).copy())
+        self.path_id = self._to_device(self._path_ids_host.astype(np.int32))
+
+    def _upload_lut(self, lut):
+        self.lut = lut
+        a = lut.arrays()
+        self._lut_dev = {k: self._to_device(v.view(np.int64) if v.dtype == np.uint64 else v) for k, v in a.items()}
+
+    def _alloc_state(self):
+        n, L = self.n_envs, self.layout
+        dev = self.device
+        self.state_f = torch.zeros((L.n_frows, n), dtype=torch.float64, device=dev)
+        self.state_i = torch.zeros((L.n_irows, n), dtype=torch.int32, device=dev)
+        self.init_f = torch.zeros_like(self.state_f)
+        self.init_i = torch.zeros_like(self.state_i)
+        self._cand = torch.zeros((7, n), dtype=torch.float64, device=dev)
+        self._status = torch.zeros(nat.STATUS_WORDS, dtype=torch.int32, device=dev)
+        self._stats = torch.zeros(nat.STATS_WORDS, dtype=torch.float64, device=dev)
+        self.reward = torch.zeros(n, dtype=torch.float64, device=dev)
+        self._done_u8 = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self._hit_u8 = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.obs_vec = torch.zeros((n, 12), dtype=torch.float32, device=dev)
+        cp = self._c_params
+        if self.with_ego:
+            self.ego_image = torch.zeros((n, cp.ego_h, cp.ego_w, 1), dtype=torch.uint8, device=dev)
+            self.goal_n_state = torch.zeros((n, 9, 1), dtype=torch.float32, device=dev)
+        else:
+            self.ego_image = self.goal_n_state = None
+
+    def _make_batch(self):
+        b = nat.BcgBatch()
+        b.n_envs, b.n_frows, b.n_irows = self.n_envs, self.layout.n_frows, self.layout.n_irows
+        b.n_maps, b.n_paths = self._n_maps, len(self._paths_host)
+        b.state_f, b.state_i = self.state_f.data_ptr(), self.state_i.data_ptr()
+        b.init_f, b.init_i = self.init_f.data_ptr(), self.init_i.data_ptr()
+        b.cand = self._cand.data_ptr()
+        b.map_id, b.path_id = self.map_id.data_ptr(), self.path_id.data_ptr()
+        b.maps, b.paths = self.map_descs.data_ptr(), self.path_descs.data_ptr()
+        b.map_arena, b.tile_arena, b.path_arena = self.map_arena.data_ptr(), self.tile_arena.data_ptr(), self.path_arena.data_ptr()
+        d = self._lut_dev
+        b.lut.edges, b.lut.verts, b.lut.header = d['edges'].data_ptr(), d['verts'].data_ptr(), d['header'].data_ptr()
+        b.lut.rows, b.lut.fp_pix = d['rows'].data_ptr(), d['fp_pix'].data_ptr()
+        b.lut.n_bins, b.lut.n_verts, b.lut.max_rows, b.lut.wpr = self.lut.n_bins, self.lut.n_verts, self.lut.max_rows, self.lut.wpr
+        b.status, b.stats = self._status.data_ptr(), self._stats.data_ptr()
+        self._batch = b
+        out = nat.BcgStepOut()
+        out.reward, out.done, out.hit = self.reward.data_ptr(), self._done_u8.data_ptr(), self._hit_u8.data_ptr()
+        out.obs_vec = self.obs_vec.data_ptr()
+        if self.with_ego:
+            out.ego_image, out.goal_n_state = self.ego_image.data_ptr(), self.goal_n_state.data_ptr()
+        self._out = out
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- the env API ---------------------------------------------------------------------------
+    @property
+    def done(self):
+        return self._done_u8.view(torch.bool)
+
+    @property
+    def hit(self):
+        return self._hit_u8.view(torch.bool)
+
+    def action_bounds(self):
+        """low, high of the action Box (reference envs/base/env.py:237-240), float32."""
+        s = self.dims.max_front_wheel_speed
+        return (np.array([s / 10, -np.pi / 2]).astype(np.float32), np.array([s / 2, np.pi / 2]).astype(np.float32))
+
+    def _as_actions(self, actions):
+        if isinstance(actions, np.ndarray):
+            if actions.dtype not in (np.float32, np.float64):
+                actions = actions.astype(np.float64)
+            actions = torch.from_numpy(np.ascontiguousarray(actions)).to(self.device)
+        if actions.dtype not in (torch.float32, torch.float64):
+            actions = actions.to(torch.float64)
+        if actions.device != self.device:
+            actions = actions.to(self.device)
+        if tuple(actions.shape) != (self.n_envs, 2):
+            raise ValueError("actions must have shape (%d, 2), got %s" % (self.n_envs, tuple(actions.shape)))
+        return actions.contiguous()
+
+    def step(self, actions):
+        """One env step for every env.  actions: [N, 2] float32/float64 (tensor or ndarray).
+        Returns (VecObservation, reward fp64 [N], done bool [N], {}) -- tensors are reused buffers."""
+        a = self._as_actions(actions)
+        nat.check(nat.lib().bcg_step(C.byref(self._c_params), C.byref(self._batch), nat.ptr(a),
+                                     1 if a.dtype == torch.float64 else 0, self._step_index,
+                                     C.byref(self._out), self._stream()))
+        self._step_index += 1
+        return self.observation(), self.reward, self.done, {}
+
+    def reset(self, mask=None):
+        """PlanEnv.reset for all envs (mask None) or those with mask[e] true."""
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        nat.check(nat.lib().bcg_reset_where(C.byref(self._batch), nat.ptr(m), self._stream()))
+        return self.observation()
+
+    def observation(self):
+        return VecObservation(self)
+
+    def observe_ego(self):
+        """EgocentricCostmap.observation of the current state -> ('env' uint8 [N,H,W,1],
+        'goal_n_state' float32 [N,9,1])."""
+        if not self.with_ego:
+            cp = self._c_params
+            self.ego_image = torch.zeros((self.n_envs, cp.ego_h, cp.ego_w, 1), dtype=torch.uint8, device=self.device)
+            self.goal_n_state = torch.zeros((self.n_envs, 9, 1), dtype=torch.float32, device=self.device)
+        nat.check(nat.lib().bcg_observe_ego(C.byref(self._c_params), C.byref(self._batch), nat.ptr(self.ego_image),
+                                            nat.ptr(self.goal_n_state), self._stream()))
+        return self.ego_image, self.goal_n_state
+
+    def get_state(self, indices=None):
+        idx = self._indices(indices)
+        k = idx.numel()
+        f = torch.empty((self.layout.n_frows, k), dtype=torch.float64, device=self.device)
+        i = torch.empty((self.layout.n_irows, k), dtype=torch.int32, device=self.device)
+        nat.check(nat.lib().bcg_gather_state(C.byref(self._batch), nat.ptr(idx), k, nat.ptr(f), nat.ptr(i), self._stream()))
+        return VecState(f, i)
+
+    def set_state(self, state, indices=None, load_delayed_robot=True):
+        """Restore columns.  Like the reference (envs/base/env.py:282-285) the live robot is loaded
+        from the *delayed* robot state of the snapshot unless load_delayed_robot is False."""
+        idx = self._indices(indices)
+        k = idx.numel()
+        if tuple(state.f.shape) != (self.layout.n_frows, k) or tuple(state.i.shape) != (self.layout.n_irows, k):
+            raise ValueError("snapshot shape does not match the env layout / index count")
+        f, i = state.f.to(self.device).contiguous(), state.i.to(self.device).contiguous()
+        nat.check(nat.lib().bcg_scatter_state(C.byref(self._batch), nat.ptr(idx), k, nat.ptr(f), nat.ptr(i),
+                                              1 if load_delayed_robot else 0, self._stream()))
+
+    def _indices(self, indices):
+        if indices is None:
+            return torch.arange(self.n_envs, dtype=torch.int64, device=self.device)
+        idx = torch.as_tensor(indices, dtype=torch.int64, device=self.device).reshape(-1).contiguous()
+        if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= self.n_envs):
+            raise IndexError("env index out of range")
+        return idx
+
+    # ---- pieces of the path, individually addressable ---------------------------------------------
+    def _poses_rows(self, poses):
+        p = torch.as_tensor(poses, dtype=torch.float64, device=self.device)
+        if tuple(p.shape) != (self.n_envs, 3):
+            raise ValueError("poses must have shape (%d, 3)" % self.n_envs)
+        return p.t().contiguous()
+
+    def pose_collides(self, poses, count_pixels=False, use_u8=False):
+        """Batched `pose_collides` (reference envs/base/env.py:464-489): pose e against env e's costmap."""
+        rows = self._poses_rows(poses)
+        flags = torch.empty(self.n_envs, dtype=torch.uint8, device=self.device)
+        if use_u8:
+            nat.check(nat.lib().bcg_collision_u8(C.byref(self._c_params), C.byref(self._batch), nat.ptr(rows),
+                                                 nat.ptr(flags), self._stream()))
+            return flags.view(torch.bool)
+        pixels = torch.empty(self.n_envs, dtype=torch.int32, device=self.device) if count_pixels else None
+        nat.check(nat.lib().bcg_collision(C.byref(self._c_params), C.byref(self._batch), nat.ptr(rows), nat.ptr(flags),
+                                          nat.ptr(pixels), self._stream()))
+        return (flags.view(torch.bool), pixels) if count_pixels else flags.view(torch.bool)
+
+    # ---- bookkeeping ---------------------------------------------------------------------------
+    def check_status(self):
+        """Poll the device anomaly counters (synchronises).  Raises like the reference would."""
+        st = self._status.cpu().numpy().astype(np.int64)
+        if st[nat.STATUS_PATH_EXHAUSTED]:
+            self._status.zero_()
+            raise ValueError("Goal pose too close to initial pose")   # reference envs/base/reward.py:275-277
+        if st[nat.STATUS_LUT_MISS]:
+            raise nat.BcgError("%d footprint lookups fell outside the angle-bin table" % st[nat.STATUS_LUT_MISS])
+
+    def episode_stats(self, reset=False):
+        """Device-accumulated episode statistics as a fp64 tensor [STATS_WORDS] (see STAT_NAMES)."""
+        out = self._stats.clone()
+        if reset:
+            self._stats.zero_()
+        return out
+
+    def full_path(self, e):
+        return self._paths_host[int(self._path_ids_host[e])]
+
+    def costmap(self, e):
+        return self._map_pool[int(self._map_ids_host[e])]
+
+    def queue_rows(self, which):
+        """(first fp64 row, slots, components, int row) of a delay ring: 'control' | 'pose' | 'state'."""
+        L, p = self.layout, self.params
+        return {'control': (L.ring_control, p.control_delay, 2, nat.I_QC),
+                'pose': (L.ring_pose, p.pose_delay, 3, nat.I_QP),
+                'state': (L.ring_state, p.state_delay, 7, nat.I_QS)}[which]

@@ -1,0 +1,239 @@
+/*
+ * bcg_b200.h -- C-ABI of the B200-native batched PlanEnv.step path.
+ *
+ * The upstream reference (braincorp/bc-gym-planning-env, pure Python) has no FFI of its own; the
+ * seams this library plugs into are (paths relative to bc_gym_planning_env/ in the reference):
+ *   (i)  the env API            envs/base/env.py:278-361 (get_state/set_state/reset/step)
+ *   (ii) the native-hook seam   `brain.shining_utils.*` imports at utilities/path_tools.py:101-103,
+ *        utilities/coordinate_transformations.py:17-20,39-41,169-171, utilities/costmap_utils.py:106-107
+ * Each entry point below names the reference function(s) it replaces for a *batch* of N environments.
+ *
+ * Conventions
+ *   - plain C types only; every pointer marked "device" is a CUDA device pointer owned by the caller
+ *     (the Python host allocates them as torch tensors); the library never allocates or frees them.
+ *   - every function returns 0 on success, <0 on error; bcg_last_error() gives the message of the
+ *     last failure on the calling thread.  No C++ exception crosses the boundary.
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it.
+ *   - per-env dynamic state is structure-of-arrays: state_f[row * n_envs + env] (fp64 rows) and
+ *     state_i[row * n_envs + env] (int32 rows); row numbers come from bcg_state_layout().
+ *   - kernels never trap: out-of-map pixels are skipped exactly like envs/base/env.py:483-484 and
+ *     anomalies are counted in the device `status` words (BCG_STATUS_*), which the host polls.
+ */
+#ifndef BCG_B200_H_
+#define BCG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BCG_ABI_VERSION 1
+
+/* error codes */
+#define BCG_OK 0
+#define BCG_ERR_INVALID (-1) /* bad argument                     */
+#define BCG_ERR_CUDA (-2)    /* a CUDA runtime call failed       */
+#define BCG_ERR_NO_DEVICE (-3)
+
+/* robot kinds (robot_models/robot_drive_types.py) */
+#define BCG_ROBOT_TRICYCLE 0
+#define BCG_ROBOT_DIFFDRIVE 1
+
+/* fixed fp64 state rows; ring rows follow (see BcgStateLayout) */
+#define BCG_F_ROBOT 0    /* 7 rows: true robot x,y,th,v,w,steer_cmd,wheel   (tricycle_model.py:234-244) */
+#define BCG_F_DROBOT 7   /* 7 rows: delayed robot state = State.robot_state (env.py:386-396)            */
+#define BCG_F_DPOSE 14   /* 3 rows: delayed pose       = State.pose         (env.py:377-394)            */
+#define BCG_F_TIME 17    /* State.current_time                                                         */
+#define BCG_F_MIN_DIST 18 /* ContinuousRewardProviderState.min_spat_dist_so_far (reward.py:15)          */
+#define BCG_F_EP_RETURN 19 /* sum of rewards since the last reset (statistics only)                     */
+#define BCG_F_FIXED 20
+/* int32 state rows */
+#define BCG_I_ITER 0     /* State.current_iter                                 */
+#define BCG_I_TARGET 1   /* ContinuousRewardProviderState.target_idx            */
+#define BCG_I_COLLIDED 2 /* State.robot_collided (sticky, env.py:393)           */
+#define BCG_I_QC 3       /* control queue: head | len << 16                     */
+#define BCG_I_QP 4       /* pose queue                                          */
+#define BCG_I_QS 5       /* robot-state queue                                   */
+#define BCG_I_FIXED 6
+
+/* device status words (uint32 counters, length BCG_STATUS_WORDS) */
+#define BCG_STATUS_LUT_MISS 0     /* footprint tuple not found in the angle-bin table */
+#define BCG_STATUS_PATH_EXHAUSTED 1 /* init: "Goal pose too close to initial pose" (reward.py:275-277) */
+#define BCG_STATUS_WORDS 8
+
+/* episode statistics accumulated on device at episode end (fp64, length BCG_STATS_WORDS) */
+#define BCG_STAT_EPISODES 0
+#define BCG_STAT_RETURN 1
+#define BCG_STAT_LENGTH 2
+#define BCG_STAT_COLLIDED 3
+#define BCG_STAT_GOAL 4
+#define BCG_STAT_TIMEOUT 5
+#define BCG_STATS_WORDS 8
+
+/* Environment constants shared by the batch: EnvParams (envs/base/params.py:15-43), RewardParams
+ * (envs/base/reward.py:162-171), robot dimension table (robot_models/robot_dimensions_examples.py). */
+typedef struct BcgParams {
+  double dt;
+  double resolution;
+  double inv_resolution;      /* 1./resolution, as coordinate_transformations.py:204 computes it */
+  double spatial_precision;   /* sp */
+  double angular_precision;   /* ap */
+  double progress_multiplier; /* RewardParams.spatial_progress_multiplier */
+  double wheel_base;          /* front_wheel_from_axis */
+  double max_wheel_angle;
+  double max_wheel_delta;     /* max_front_wheel_speed * dt (tricycle_model.py:143) */
+  double p_gain;
+  double max_lin_acc;
+  double max_ang_acc;
+  double alpha[6];            /* odometry noise; used when noise_on */
+  double ego_x0, ego_y0;      /* egocentric crop origin in the robot frame (egocentric.py:113-114) */
+  double ego_world_w, ego_world_h; /* CostMap2D.world_size() of the crop (costmap_2d.py:115-121) */
+  uint64_t seed;              /* Philox key */
+  uint64_t env_id_base;       /* global id of env 0 of this shard (distinct noise streams per GPU) */
+  int32_t robot_kind;
+  int32_t noise_on;
+  int32_t delay_control, delay_pose, delay_state;
+  int32_t iteration_timeout;
+  int32_t ego_w, ego_h;       /* crop size in pixels */
+  int32_t auto_reset;         /* restore the initial state of envs that report done */
+  int32_t reserved;
+} BcgParams;
+
+/* one costmap of the arena: CostMap2D (utilities/costmap_2d.py:13-37) + its derived lethal bit-plane */
+typedef struct BcgMapDesc {
+  int64_t data_off;  /* byte offset of uint8 [H][pitch] in the map arena                      */
+  int64_t tile_off;  /* uint32 offset of the lethal tile plane in the tile arena               */
+  double origin_x, origin_y;
+  int32_t height, width, pitch;
+  int32_t tiles_x, tiles_y; /* 32 px x 16 rows per 64-byte tile                                */
+  int32_t reserved;
+} BcgMapDesc;
+
+/* one refined path: fp64 SoA rows x,y,th,cos(th),sin(th), each `pitch` long, then chunk bounds */
+typedef struct BcgPathDesc {
+  int64_t off;       /* fp64 offset of the 5 point rows in the path arena                       */
+  int64_t chunk_off; /* fp64 offset of the 3 chunk rows (cx, cy, radius), each `chunk_pitch`     */
+  int32_t n;         /* number of points                                                       */
+  int32_t pitch;
+  int32_t n_chunks;  /* ceil(n / 32)                                                           */
+  int32_t chunk_pitch;
+} BcgPathDesc;
+
+/* angle-binned footprint table replacing get_pixel_footprint (utilities/path_tools.py:122-162) */
+typedef struct BcgFootprintLut {
+  const double* edges;    /* device [n_bins + 1] ascending, edges[0] = -pi, edges[n_bins] = +pi    */
+  const int16_t* verts;   /* device [n_bins][2 * n_verts]  rounded vertices (x0,y0,x1,y1,...)       */
+  const int16_t* header;  /* device [n_bins][4] = xmin, ymin, n_rows, width (mask bounding box)     */
+  const uint64_t* rows;   /* device [n_bins][max_rows][wpr] bit i of word j <-> column xmin+64j+i   */
+  const double* fp_pix;   /* device [2 * n_verts] footprint / resolution (fx0,fy0,...)             */
+  int32_t n_bins, n_verts, max_rows, wpr;
+} BcgFootprintLut;
+
+/* everything a step touches; all pointers are device pointers */
+typedef struct BcgBatch {
+  int32_t n_envs;
+  int32_t n_frows, n_irows; /* must equal bcg_state_layout() for the params in use */
+  int32_t n_maps, n_paths;
+  int32_t reserved;
+  double* state_f;
+  int32_t* state_i;
+  double* init_f;  /* the state reset() restores (env.py:247,302) */
+  int32_t* init_i;
+  double* cand;    /* scratch [7][n_envs]: robot state proposed by the kinematic kernel */
+  const int32_t* map_id;  /* [n_envs] index into maps  */
+  const int32_t* path_id; /* [n_envs] index into paths */
+  const BcgMapDesc* maps;
+  const BcgPathDesc* paths;
+  const uint8_t* map_arena;
+  const uint32_t* tile_arena;
+  const double* path_arena;
+  BcgFootprintLut lut;
+  uint32_t* status; /* [BCG_STATUS_WORDS] */
+  double* stats;    /* [BCG_STATS_WORDS]  */
+} BcgBatch;
+
+typedef struct BcgStateLayout {
+  int32_t n_frows, n_irows;
+  int32_t ring_control; /* first fp64 row of the control ring: delay_control slots x 2 rows */
+  int32_t ring_pose;    /* delay_pose slots x 3 rows                                         */
+  int32_t ring_state;   /* delay_state slots x 7 rows                                        */
+} BcgStateLayout;
+
+/* outputs of one step; any pointer may be NULL to skip that output */
+typedef struct BcgStepOut {
+  double* reward;      /* [n] reward of this step (reward.py:214-259)                          */
+  uint8_t* done;       /* [n] env.py:407-419                                                   */
+  uint8_t* hit;        /* [n] collision verdict of this step's pose_collides (env.py:455)       */
+  uint8_t* ego_image;  /* [n][ego_h][ego_w] egocentric crop (egocentric.py:125-160 'env')        */
+  float* goal_n_state; /* [n][9] egocentric.py:152-159                                          */
+  float* obs_vec;      /* [n][12] fp32 copy of delayed pose(3), delayed robot state(7), time, target_idx */
+} BcgStepOut;
+
+/* -- library ------------------------------------------------------------------------------------ */
+int bcg_abi_version(void);
+/* copies the calling thread's last error message (NUL terminated) and returns its length */
+size_t bcg_last_error(char* buf, size_t cap);
+/* sizeof() of the ABI structs, in declaration order: 0 BcgParams, 1 BcgMapDesc, 2 BcgPathDesc,
+ * 3 BcgFootprintLut, 4 BcgBatch, 5 BcgStateLayout, 6 BcgStepOut; -1 for anything else.  Lets a
+ * binding (ctypes, cffi, ...) verify its struct mirrors before the first call. */
+int64_t bcg_sizeof(int32_t which);
+/* number of CUDA devices visible, <0 on error; makes a missing GPU a loud failure for callers */
+int bcg_device_count(void);
+/* state row map for the delays in `p` (mirrors the three queues of env.py:64-66) */
+int bcg_state_layout(const BcgParams* p, BcgStateLayout* out);
+
+/* -- setup (at reset time, not per step) ------------------------------------------------------------ */
+/* derive the lethal bit-plane (cell == 254, costmap_2d.py:21) of maps [first, first+count) */
+int bcg_build_lethal_tiles(const BcgBatch* b, int32_t first, int32_t count, void* stream);
+/* make_initial_state (env.py:179-214) + ContinuousRewardProvider.generate_initial_state
+ * (reward.py:261-288) for every env: writes init_f/init_i and copies them into state_f/state_i */
+int bcg_init_state(const BcgParams* p, const BcgBatch* b, void* stream);
+/* PlanEnv.reset (env.py:293-303) for envs with mask[e] != 0 (mask NULL = all) */
+int bcg_reset_where(const BcgBatch* b, const uint8_t* mask, void* stream);
+
+/* -- the hot path -------------------------------------------------------------------------------- */
+/* PlanEnv.step (env.py:334-361) for all envs.  actions: device [n][2] (wheel_v, wheel_angle) or
+ * (v, w) for diff-drive; action_is_f64 selects fp64 vs fp32 elements.  Launches, in order:
+ * kinematics (thread/env), collision+commit+reward (warp/env), egocentric observation (CTA/env,
+ * only if out->ego_image or out->goal_n_state is set).  step_index is the caller's global step
+ * counter: odometry noise is Philox4x32-10 keyed by p->seed at counter (env id, step_index, draw),
+ * replacing the reference's global np.random (differential_drive.py:50). */
+int bcg_step(const BcgParams* p, const BcgBatch* b, const void* actions, int32_t action_is_f64,
+             uint64_t step_index, const BcgStepOut* out, void* stream);
+
+/* the pieces, individually addressable (used by tests, ncu and the hook seam) */
+/* robot.step (tricycle_model.py:478-538 / differential_drive.py:236-265) into b->cand */
+int bcg_kinematic_step(const BcgParams* p, const BcgBatch* b, const void* actions,
+                       int32_t action_is_f64, uint64_t step_index, void* stream);
+/* pose_collides (env.py:464-489) of poses [3][n] (rows x,y,th) against each env's map, using the
+ * lethal tile plane; flags_out [n].  pixels_out (optional, [n]) = in-map footprint pixel count. */
+int bcg_collision(const BcgParams* p, const BcgBatch* b, const double* poses, uint8_t* flags_out,
+                  int32_t* pixels_out, void* stream);
+/* same verdicts read straight from the uint8 costmap rows (no derived plane) */
+int bcg_collision_u8(const BcgParams* p, const BcgBatch* b, const double* poses, uint8_t* flags_out,
+                     void* stream);
+/* EgocentricCostmap.observation (egocentric.py:125-160) from the current state */
+int bcg_observe_ego(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, float* goal_n_state,
+                    void* stream);
+
+/* -- snapshots: get_state / set_state (env.py:278-291) ------------------------------------------ */
+/* gather columns idx[0..k) of state_f/state_i into out_f [n_frows][k], out_i [n_irows][k] */
+int bcg_gather_state(const BcgBatch* b, const int64_t* idx, int32_t k, double* out_f,
+                     int32_t* out_i, void* stream);
+/* scatter columns back; load_delayed_robot != 0 applies env.py:284 (robot := delayed robot state) */
+int bcg_scatter_state(const BcgBatch* b, const int64_t* idx, int32_t k, const double* in_f,
+                      const int32_t* in_i, int32_t load_delayed_robot, void* stream);
+
+/* -- hook-seam helpers (batched forms of the brain.shining_utils.* scalars) --------------------- */
+/* world_to_pixel (coordinate_transformations.py:185-205): xy [n][2] fp64 -> int32 [n][2] */
+int bcg_world_to_pixel(const double* xy, int64_t n, double origin_x, double origin_y,
+                       double resolution, int32_t* out, void* stream);
+/* normalize_angle (coordinate_transformations.py:28-36) */
+int bcg_normalize_angle(const double* in, int64_t n, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BCG_B200_H_ */

@@ -1,0 +1,268 @@
+"""TEST INFRASTRUCTURE ONLY -- regenerates tests/golden/*.npz from the UNMODIFIED reference.
+
+    python -m oracle.gen_golden            # needs /root/reference (build container only)
+
+Every fixture stores the inputs (costmaps, coarse paths, params, actions) next to what the
+reference's own `step` / `pose_collides` / `EgocentricCostmap` produced for them, so the GPU box --
+where the reference does not exist -- can check the CUDA path and the oracle against the real thing.
+Versions that produced the committed fixtures: numpy 2.3.5, opencv-python 4.13.0, attrs 26.1.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def _ref():
+    from oracle.ref_loader import load_reference
+    load_reference()
+
+
+def _pack_envs(envs):
+    """costmaps / origins / coarse paths of a list of reference PlanEnvs -> dict of arrays."""
+    d = {"n_envs": np.int64(len(envs))}
+    for i, pe in enumerate(envs):
+        st = pe._state
+        d["costmap_%d" % i] = st.costmap.get_data().copy()
+        d["origin_%d" % i] = np.array(st.costmap.get_origin())
+        d["path_%d" % i] = np.array(st.original_path)          # already refined by make_initial_state
+    d["resolution"] = np.float64(envs[0]._state.costmap.get_resolution())
+    return d
+
+
+def _record_step(pe, obs, reward, done):
+    rs = obs.robot_state
+    rp = pe._state.reward_provider_state
+    return dict(pose=np.array(obs.pose, dtype=np.float64),
+                robot_state=np.array([rs.x, rs.y, rs.angle, rs.v, rs.w, rs.steering_motor_command, rs.wheel_angle]),
+                true_pose=np.array(pe._robot.get_pose(), dtype=np.float64),
+                reward=float(reward), done=bool(done), collided=bool(pe._state.robot_collided),
+                target_idx=int(rp.target_idx), min_dist=float(rp.min_spat_dist_so_far), time=float(obs.time),
+                path_len=len(obs.path))
+
+
+def _stack(records):
+    keys = records[0][0].keys()
+    return {k: np.array([[r[k] for r in env_recs] for env_recs in records]) for k in keys}
+
+
+def _params_json(ep, noise):
+    rp = ep.reward_provider_params
+    return json.dumps(dict(dt=ep.dt, sp=rp.spatial_precision, ap=rp.angular_precision,
+                           multiplier=rp.spatial_progress_multiplier, timeout=ep.iteration_timeout,
+                           delays=[ep.control_delay, ep.pose_delay, ep.state_delay], robot=ep.robot_name,
+                           noise=noise))
+
+
+def gen_rollouts(name, make_env, n_envs, n_steps, noise=False, sample_from_space=False):
+    from bc_gym_planning_env.envs.base.action import Action
+    from bc_gym_planning_env.envs.base import spaces
+    import bc_gym_planning_env.robot_models.differential_drive as dd
+    envs, records, actions, draws = [], [], [], []
+    if sample_from_space:
+        spaces.SPACE_LOCAL_RANDOM_STATE.seed(0)
+    for s in range(n_envs):
+        env = make_env(s)
+        pe = env._env
+        if not noise:
+            pe._robot.set_noise_parameters(None)
+        envs.append(pe)
+        rng = np.random.RandomState(1000 + s)
+        np.random.seed(77 + s)
+        env_recs, env_actions, env_draws = [], [], []
+        real_normal = np.random.normal
+        for t in range(n_steps):
+            if sample_from_space:
+                a = env.action_space.sample().command.astype(np.float32)
+            else:
+                a = rng.uniform(pe.action_space.low, pe.action_space.high).astype(np.float32)
+            step_draws = []
+
+            def recording_normal(loc, scale):   # _gaussian_noise calls np.random.normal(0, std)
+                z = real_normal(0, 1)
+                step_draws.append(z)
+                return loc + scale * z
+            dd.np.random.normal = recording_normal
+            try:
+                obs, r, d, _ = env.step(Action(command=a))
+            finally:
+                dd.np.random.normal = real_normal
+            env_recs.append(_record_step(pe, obs, r, d))
+            env_actions.append(a)
+            env_draws.append((step_draws + [np.nan] * 3)[:3])
+        records.append(env_recs)
+        actions.append(env_actions)
+        draws.append(env_draws)
+    out = _pack_envs(envs)
+    out.update({"ref_" + k: v for k, v in _stack(records).items()})
+    out["actions"] = np.array(actions, dtype=np.float32)
+    out["params"] = np.array(_params_json(envs[0]._params, noise))
+    if noise:
+        out["normal_draws"] = np.array(draws)     # [E, T, 3] in draw order; NaN = not drawn
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items() if k.startswith("ref_")})
+
+
+def gen_ego(name, n_envs, n_steps, every):
+    from bc_gym_planning_env.envs.base.action import Action
+    from bc_gym_planning_env.envs.base.params import EnvParams
+    from bc_gym_planning_env.envs.egocentric import EgocentricCostmap
+    from bc_gym_planning_env.envs.synth_turn_env import RandomAisleTurnEnv
+    envs, actions, images, vectors = [], [], [], []
+    for s in range(n_envs):
+        base = RandomAisleTurnEnv(params=EnvParams(pose_delay=1, state_delay=1), seed=100 + s)
+        base._env._robot.set_noise_parameters(None)
+        env = EgocentricCostmap(base)
+        envs.append(base._env)
+        rng = np.random.RandomState(s)
+        ea, ei, ev = [], [], []
+        for t in range(n_steps):
+            a = rng.uniform(base.action_space.low, base.action_space.high).astype(np.float32)
+            obs, _, _, _ = env.step(Action(command=a))
+            ea.append(a)
+            if t % every == every - 1:
+                ei.append(obs["env"][..., 0].copy())
+                ev.append(obs["goal_n_state"][:, 0].copy())
+        actions.append(ea)
+        images.append(ei)
+        vectors.append(ev)
+    out = _pack_envs(envs)
+    out["actions"] = np.array(actions, dtype=np.float32)
+    out["every"] = np.int64(every)
+    out["ref_ego_image"] = np.array(images)
+    out["ref_goal_n_state"] = np.array(vectors)
+    out["params"] = np.array(_params_json(envs[0]._params, False))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, out["ref_ego_image"].shape, out["ref_goal_n_state"].shape)
+
+
+def gen_collision(name, n_maps, n_poses):
+    from bc_gym_planning_env.envs.base.env import pose_collides
+    from bc_gym_planning_env.envs.synth_turn_env import RandomAisleTurnEnv
+    from bc_gym_planning_env.utilities.path_tools import get_pixel_footprint
+    envs, poses, flags, pixels = [], [], [], []
+    rng = np.random.RandomState(5)
+    for s in range(n_maps):
+        env = RandomAisleTurnEnv(seed=200 + s)
+        pe = env._env
+        envs.append(pe)
+        cm = pe._state.costmap
+        path = pe._state.original_path
+        ep, ef, epx = [], [], []
+        for k in range(n_poses):
+            if k % 4 == 0:      # anywhere, including far outside the map
+                lo = cm.get_origin() - 2.0
+                hi = cm.get_origin() + cm.world_size() + 2.0
+                xy = rng.uniform(lo, hi)
+            else:               # near the path so that walls are often touched
+                xy = path[rng.randint(len(path)), :2] + rng.normal(0, 0.5, 2)
+            th = rng.uniform(-np.pi, np.pi)
+            hit = pose_collides(xy[0], xy[1], th, pe._robot, cm)
+            kernel = get_pixel_footprint(th, pe._robot.get_footprint(), cm.get_resolution())
+            rr, cc = np.where(kernel)
+            px, py = cm.world_to_pixel(np.array([xy[0], xy[1]]))
+            rr = py + rr - kernel.shape[0] // 2
+            cc = px + cc - kernel.shape[1] // 2
+            good = (rr >= 0) & (rr < cm.get_data().shape[0]) & (cc >= 0) & (cc < cm.get_data().shape[1])
+            ep.append([xy[0], xy[1], th])
+            ef.append(hit)
+            epx.append(int(good.sum()))
+        poses.append(ep)
+        flags.append(ef)
+        pixels.append(epx)
+    out = _pack_envs(envs)
+    out["poses"] = np.array(poses)
+    out["ref_flags"] = np.array(flags)
+    out["ref_pixels"] = np.array(pixels, dtype=np.int32)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, out["poses"].shape, "hit rate %.3f" % out["ref_flags"].mean())
+
+
+def gen_kat_collision(name):
+    """The costmap + 20 golden poses of the reference's utilities/test_costmap_utils.py:251-306, with
+    the verdicts of both reference collision routines on them and on 1000 random poses."""
+    from bc_gym_planning_env.utilities.costmap_2d import CostMap2D
+    from bc_gym_planning_env.utilities.map_drawing_utils import add_wall_to_static_map
+    from bc_gym_planning_env.utilities.costmap_utils import is_robot_colliding, pose_collides
+    costmap = CostMap2D.create_empty((10, 6), 0.05, (-1, -3))
+    for x in (3.9, 1.5):
+        add_wall_to_static_map(costmap, (x, -4.), (x, -1 + 1.5))
+    add_wall_to_static_map(costmap, (5., -4.), (5. + 1, -1 + 4.5))
+    footprint = np.array([[-0.77, -0.385], [-0.77, 0.385], [0.67, 0.385], [0.67, -0.385]])
+    golden = np.array(
+        [(x, 0., 0.2) for x in range(7)] + [(x, 1.2, np.pi / 2 + 0.4) for x in range(7)] +
+        [(x, -3, 0.2) for x in range(3)] + [(x, -3.2, 0.2) for x in range(3)], dtype=np.float64)
+    rng = np.random.RandomState(11)
+    rand = rng.rand(1000, 3)
+    rand[:, :2] *= costmap.world_size() + costmap.get_origin() + np.array([1., 1.])
+    poses = np.vstack([golden, rand])
+    irc = [bool(is_robot_colliding(p, footprint, costmap.get_data(), costmap.get_origin(), 0.05)) for p in poses]
+    pc = [bool(pose_collides(p, footprint, costmap.get_data(), costmap.get_origin(), 0.05)) for p in poses]
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), costmap=costmap.get_data(), origin=np.array(costmap.get_origin()),
+                        resolution=np.float64(0.05), footprint=footprint, poses=poses,
+                        ref_is_robot_colliding=np.array(irc), ref_pose_collides=np.array(pc))
+    print(name, "is_robot_colliding first 20:", irc[:20])
+
+
+def gen_diffdrive(name, n_envs, n_steps):
+    """DiffDriveRobot.step + env.pose_collides + rollback (envs/base/env.py:442-461) -- PlanEnv itself
+    cannot host a diff-drive robot in the reference."""
+    from bc_gym_planning_env.envs.base.action import Action
+    from bc_gym_planning_env.envs.base.env import _env_step
+    from bc_gym_planning_env.envs.synth_turn_env import RandomAisleTurnEnv
+    from bc_gym_planning_env.robot_models.differential_drive import DiffDriveRobot
+    from bc_gym_planning_env.robot_models.robot_dimensions_examples import get_dimensions_example
+    envs, actions, states, hits = [], [], [], []
+    for s in range(n_envs):
+        env = RandomAisleTurnEnv(seed=300 + s)
+        pe = env._env
+        envs.append(pe)
+        robot = DiffDriveRobot(dimensions=get_dimensions_example('industrial_diffdrive_v1'))
+        p0 = pe._state.original_path[0]
+        robot.set_pose(p0[0], p0[1], p0[2])
+        rng = np.random.RandomState(s)
+        ea, es, eh = [], [], []
+        for t in range(n_steps):
+            a = np.array([rng.uniform(0.0, 0.8), rng.uniform(-1.0, 1.0)])
+            hit = _env_step(pe._state.costmap, robot, 0.05, Action(command=a))
+            st = robot.get_state()
+            ea.append(a)
+            es.append([st.x, st.y, st.angle, st.v, st.w])
+            eh.append(bool(hit))
+        actions.append(ea)
+        states.append(es)
+        hits.append(eh)
+    out = _pack_envs(envs)
+    out["actions"] = np.array(actions, dtype=np.float64)
+    out["ref_robot_state"] = np.array(states)
+    out["ref_hit"] = np.array(hits)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, out["ref_robot_state"].shape, "hits", int(out["ref_hit"].sum()))
+
+
+def main():
+    _ref()
+    os.makedirs(OUT, exist_ok=True)
+    from bc_gym_planning_env.envs.base.params import EnvParams
+    from bc_gym_planning_env.envs.mini_env import RandomMiniEnv
+    from bc_gym_planning_env.envs.synth_turn_env import RandomAisleTurnEnv
+    gen_rollouts("mini_noise_off", lambda s: RandomMiniEnv(seed=s), 12, 250, sample_from_space=True)
+    gen_rollouts("aisle_delays_211", lambda s: RandomAisleTurnEnv(
+        params=EnvParams(control_delay=2, pose_delay=1, state_delay=1, iteration_timeout=220), seed=s), 12, 300)
+    gen_rollouts("aisle_delays_120", lambda s: RandomAisleTurnEnv(
+        params=EnvParams(control_delay=1, pose_delay=2, state_delay=0), seed=50 + s), 6, 200)
+    gen_rollouts("aisle_noise_on", lambda s: RandomAisleTurnEnv(
+        params=EnvParams(control_delay=2, pose_delay=1, state_delay=1), seed=70 + s), 6, 200, noise=True)
+    gen_ego("aisle_ego", 6, 48, 6)
+    gen_collision("aisle_collision", 8, 250)
+    gen_kat_collision("kat_is_robot_colliding")
+    gen_diffdrive("diffdrive_steps", 6, 250)
+
+
+if __name__ == "__main__":
+    sys.path.insert(0, os.path.dirname(HERE))
+    main()

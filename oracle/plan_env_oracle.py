@@ -417,7 +417,7 @@ def philox4x32_10(counter, key):
 def philox_normals(seed, env_id, step, block):
     """Two N(0,1) draws for (seed; env_id, step, block): 53-bit uniforms from the four words,
     Box-Muller in fp64.  The device kernel uses the same construction (csrc/bcg_kernels.cu)."""
-    r = philox4x32_10((env_id & _M32, step & _M32, block & _M32, (env_id >> 32) & _M32),
+    r = philox4x32_10((env_id & _M32, step & _M32, block & _M32, (step >> 32) & _M32),
                       (seed & _M32, (seed >> 32) & _M32))
     u1 = (((r[0] << 21) | (r[1] >> 11)) + 1) * (2.0 ** -53)   # (0, 1]
     u2 = ((r[2] << 21) | (r[3] >> 11)) * (2.0 ** -53)         # [0, 1)
