@@ -46,8 +46,9 @@ class BcgPathDesc(C.Structure):
 class BcgFootprintLut(C.Structure):
     _fields_ = [
         ("edges", C.c_void_p), ("verts", C.c_void_p), ("header", C.c_void_p), ("rows", C.c_void_p),
-        ("fp_pix", C.c_void_p),
+        ("fp_pix", C.c_void_p), ("bucket_first", C.c_void_p), ("bucket_scale", C.c_double),
         ("n_bins", C.c_int32), ("n_verts", C.c_int32), ("max_rows", C.c_int32), ("wpr", C.c_int32),
+        ("n_buckets", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -56,7 +57,7 @@ class BcgBatch(C.Structure):
         ("n_envs", C.c_int32), ("n_frows", C.c_int32), ("n_irows", C.c_int32),
         ("n_maps", C.c_int32), ("n_paths", C.c_int32), ("reserved", C.c_int32),
         ("state_f", C.c_void_p), ("state_i", C.c_void_p), ("init_f", C.c_void_p), ("init_i", C.c_void_p),
-        ("cand", C.c_void_p), ("map_id", C.c_void_p), ("path_id", C.c_void_p),
+        ("cand", C.c_void_p), ("cand_i", C.c_void_p), ("map_id", C.c_void_p), ("path_id", C.c_void_p),
         ("maps", C.c_void_p), ("paths", C.c_void_p),
         ("map_arena", C.c_void_p), ("tile_arena", C.c_void_p), ("path_arena", C.c_void_p),
         ("lut", BcgFootprintLut),
@@ -101,6 +102,8 @@ SYMBOLS = {
     "bcg_reset_where": (C.c_int, [C.POINTER(BcgBatch), _P, _P]),
     "bcg_step": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgBatch), _P, C.c_int32, C.c_uint64,
                            C.POINTER(BcgStepOut), _P]),
+    "bcg_step_events": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgBatch), _P, C.c_int32, C.c_uint64,
+                                  C.POINTER(BcgStepOut), C.POINTER(C.c_void_p), _P]),
     "bcg_kinematic_step": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgBatch), _P, C.c_int32, C.c_uint64, _P]),
     "bcg_collision": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgBatch), _P, _P, _P, _P]),
     "bcg_collision_u8": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgBatch), _P, _P, _P]),

@@ -203,56 +203,89 @@ __device__ __forceinline__ void delay_line(double* ring, int64_t stride, int& q,
 }
 
 // ---- footprint table lookup ----------------------------------------------------------------------
-struct FootBin {
-  int bin, xmin, ymin, nrows, width;
+// What the collision kernels need to know about one pose: its pixel, its angle bin and the bin's mask
+// bounding box.  Produced per thread (kinematic / pose-prep kernels), consumed per warp.
+struct FootRef {
+  int px, py, bin;
+  int xmin, ymin, nrows, width;
 };
 
-// Warp-cooperative.  Picks the angle bin whose stored rounded-vertex tuple equals
+// Per-thread.  Picks the angle bin whose stored rounded-vertex tuple equals
 // round_half_even(R(th) * footprint / res) (utilities/path_tools.py:140-150), i.e. the bin whose
-// cv2.fillPoly mask the reference would have rasterised for this exact angle.
-__device__ __forceinline__ FootBin find_foot_bin(const BcgFootprintLut& lut, double th, unsigned lane,
-                                                 uint32_t* status) {
+// cv2.fillPoly mask the reference would have rasterised for this exact angle.  A uniform bucket table
+// gives the first candidate; the analytic bin edges are only good to ~1e-15 rad, so the tuple is
+// verified and neighbours are probed on a miss.
+__device__ __forceinline__ int find_foot_bin(const BcgFootprintLut& lut, double th, uint32_t* status) {
   double sn, cs;
   sincos(th, &sn, &cs);
-  int vx = 0, vy = 0;
-  if ((int)lane < lut.n_verts) {
-    const double fx = lut.fp_pix[2 * lane], fy = lut.fp_pix[2 * lane + 1];
-    vx = (int)rint(fma(fy, -sn, fx * cs));
-    vy = (int)rint(fma(fy, cs, fx * sn));
-  }
   double t = th;
   if (!(t >= -BCG_PI && t < BCG_PI)) t = wrap_angle(t);
-  int lo = 0, hi = lut.n_bins;  // invariant: edges[lo] <= t < edges[hi]
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (t >= __ldg(lut.edges + mid)) lo = mid; else hi = mid;
-  }
-  int bin = lo;
-  bool found = false;
-  // the analytic edges are good to ~1e-15 rad: verify, and look at the neighbours on a miss
-  for (int probe = 0; probe < 9 && !found; ++probe) {
-    int k = lo + ((probe & 1) ? ((probe + 1) >> 1) : -(probe >> 1));
-    if (k < 0) k += lut.n_bins;
-    if (k >= lut.n_bins) k -= lut.n_bins;
+  int bk = (int)((t + BCG_PI) * lut.bucket_scale);
+  bk = min(max(bk, 0), lut.n_buckets - 1);
+  int k = __ldg(lut.bucket_first + bk);
+  while (k + 1 < lut.n_bins && t >= __ldg(lut.edges + k + 1)) ++k;
+  while (k > 0 && t < __ldg(lut.edges + k)) --k;
+  for (int probe = 0; probe < 9; ++probe) {
+    int kk = k + ((probe & 1) ? ((probe + 1) >> 1) : -(probe >> 1));
+    if (kk < 0) kk += lut.n_bins;
+    if (kk >= lut.n_bins) kk -= lut.n_bins;
+    const int16_t* v = lut.verts + (int64_t)kk * 2 * lut.n_verts;
     bool ok = true;
-    if ((int)lane < lut.n_verts) {
-      const int16_t* v = lut.verts + (int64_t)k * 2 * lut.n_verts + 2 * lane;
-      ok = (v[0] == vx) && (v[1] == vy);
+    for (int i = 0; i < lut.n_verts && ok; ++i) {
+      const double fx = __ldg(lut.fp_pix + 2 * i), fy = __ldg(lut.fp_pix + 2 * i + 1);
+      const int vx = (int)rint(fma(fy, -sn, fx * cs));   // np.dot's fused form, see oracle
+      const int vy = (int)rint(fma(fy, cs, fx * sn));
+      ok = (v[2 * i] == vx) && (v[2 * i + 1] == vy);
     }
-    if (__all_sync(BCG_FULL, ok)) {
-      bin = k;
-      found = true;
-    }
+    if (ok) return kk;
   }
-  if (!found && lane == 0) atomicAdd(status + BCG_STATUS_LUT_MISS, 1u);
-  const int16_t* h = lut.header + (int64_t)bin * 4;
-  FootBin fb;
-  fb.bin = bin;
-  fb.xmin = h[0];
-  fb.ymin = h[1];
-  fb.nrows = h[2];
-  fb.width = h[3];
-  return fb;
+  atomicAdd(status + BCG_STATUS_LUT_MISS, 1u);
+  return k;
+}
+
+__device__ __forceinline__ FootRef make_foot_ref(const BcgParams& p, const BcgFootprintLut& lut, const BcgMapDesc* maps,
+                                                 int map_id, double x, double y, double th, uint32_t* status) {
+  FootRef f;
+  f.px = world_to_pixel_1d(x, __ldg(&maps[map_id].origin_x), p.inv_resolution);
+  f.py = world_to_pixel_1d(y, __ldg(&maps[map_id].origin_y), p.inv_resolution);
+  f.bin = find_foot_bin(lut, th, status);
+  const short4 h = __ldg(reinterpret_cast<const short4*>(lut.header) + f.bin);
+  f.xmin = h.x;
+  f.ymin = h.y;
+  f.nrows = h.z;
+  f.width = h.w;
+  return f;
+}
+
+// scratch int rows written by the kinematic / pose-prep kernels
+#define BCG_CI_PX 0
+#define BCG_CI_PY 1
+#define BCG_CI_BIN 2
+#define BCG_CI_HDR0 3  /* xmin | ymin << 16 */
+#define BCG_CI_HDR1 4  /* nrows | width << 16 */
+#define BCG_CI_TARGET 5
+#define BCG_CI_FLAGS 6 /* bit0 hit, bit1 goal after this step, bit2 goal before it */
+#define BCG_CI_ROWS 7
+
+__device__ __forceinline__ void store_foot_ref(int32_t* ci, int64_t N, const FootRef& f) {
+  ci[BCG_CI_PX * N] = f.px;
+  ci[BCG_CI_PY * N] = f.py;
+  ci[BCG_CI_BIN * N] = f.bin;
+  ci[BCG_CI_HDR0 * N] = (f.xmin & 0xffff) | (f.ymin << 16);
+  ci[BCG_CI_HDR1 * N] = (f.nrows & 0xffff) | (f.width << 16);
+}
+
+__device__ __forceinline__ FootRef load_foot_ref(const int32_t* ci, int64_t N) {
+  FootRef f;
+  f.px = __ldg(ci + BCG_CI_PX * N);
+  f.py = __ldg(ci + BCG_CI_PY * N);
+  f.bin = __ldg(ci + BCG_CI_BIN * N);
+  const int h0 = __ldg(ci + BCG_CI_HDR0 * N), h1 = __ldg(ci + BCG_CI_HDR1 * N);
+  f.xmin = (int)(short)(h0 & 0xffff);
+  f.ymin = h0 >> 16;
+  f.nrows = h1 & 0xffff;
+  f.width = h1 >> 16;
+  return f;
 }
 
 // 32 mask bits starting at bit `rel` of a multi-word row mask (bit b <-> column xmin + b)
@@ -268,13 +301,10 @@ __device__ __forceinline__ uint32_t mask_bits32(const uint64_t* row, int wpr, in
 // pose_collides (envs/base/env.py:464-489) on the lethal tile plane.  Warp-cooperative; returns the
 // warp-uniform verdict.  If COUNT, *pixels gets the number of in-map footprint pixels.
 template <bool COUNT>
-__device__ __forceinline__ bool collide_tiles(const BcgParams& p, const BcgBatch& b, const BcgMapDesc& m, double x,
-                                              double y, double th, unsigned lane, int* pixels) {
-  const FootBin fb = find_foot_bin(b.lut, th, lane, b.status);
-  const int px = world_to_pixel_1d(x, m.origin_x, p.inv_resolution);
-  const int py = world_to_pixel_1d(y, m.origin_y, p.inv_resolution);
-  const int X0 = px + fb.xmin, Y0 = py + fb.ymin;
-  const int X1 = X0 + fb.width - 1, Y1 = Y0 + fb.nrows - 1;
+__device__ __forceinline__ bool collide_tiles(const BcgBatch& b, const BcgMapDesc& m, const FootRef& f, unsigned lane,
+                                              int* pixels) {
+  const int X0 = f.px + f.xmin, Y0 = f.py + f.ymin;
+  const int X1 = X0 + f.width - 1, Y1 = Y0 + f.nrows - 1;
   unsigned hit = 0;
   int cnt = 0;
   if (!(X1 < 0 || Y1 < 0 || X0 >= m.width || Y0 >= m.height)) {
@@ -283,16 +313,16 @@ __device__ __forceinline__ bool collide_tiles(const BcgParams& p, const BcgBatch
     const int ntx = tx1 - tx0 + 1;
     const int items = ntx * (ty1 - ty0 + 1) * 16;
     const uint32_t* tiles = b.tile_arena + m.tile_off;
-    const uint64_t* rows = b.lut.rows + (int64_t)fb.bin * b.lut.max_rows * b.lut.wpr;
+    const uint64_t* rows = b.lut.rows + (int64_t)f.bin * b.lut.max_rows * b.lut.wpr;
     for (int it = lane; it < items; it += 32) {
       const int r = it & 15, t = it >> 4;
-      const int ty = ty0 + t / ntx, tx = tx0 + t % ntx;
+      const int tyi = t / ntx;
+      const int ty = ty0 + tyi, tx = tx0 + (t - tyi * ntx);
       const int Y = (ty << 4) + r;
       const int dy = Y - Y0;
-      if (dy < 0 || dy >= fb.nrows || Y >= m.height) continue;
-      const uint32_t mbits = mask_bits32(rows + (int64_t)dy * b.lut.wpr, b.lut.wpr, (tx << 5) - X0);
-      if (mbits == 0u) continue;
+      if (dy < 0 || dy >= f.nrows || Y >= m.height) continue;
       const uint32_t word = __ldg(tiles + ((int64_t)(ty * m.tiles_x + tx) << 4) + r);
+      const uint32_t mbits = mask_bits32(rows + (int64_t)dy * b.lut.wpr, b.lut.wpr, (tx << 5) - X0);
       hit |= word & mbits;
       if (COUNT) {
         const int over = (tx << 5) + 32 - m.width;  // columns of this tile beyond the map
@@ -311,27 +341,22 @@ __device__ __forceinline__ bool collide_tiles(const BcgParams& p, const BcgBatch
 
 // The same verdict read straight from the uint8 costmap rows: each half-warp owns one footprint row
 // per pass, each lane one aligned 4-byte word of it.
-__device__ __forceinline__ bool collide_u8(const BcgParams& p, const BcgBatch& b, const BcgMapDesc& m, double x,
-                                           double y, double th, unsigned lane) {
-  const FootBin fb = find_foot_bin(b.lut, th, lane, b.status);
-  const int px = world_to_pixel_1d(x, m.origin_x, p.inv_resolution);
-  const int py = world_to_pixel_1d(y, m.origin_y, p.inv_resolution);
-  const int X0 = px + fb.xmin, Y0 = py + fb.ymin;
-  const int X1 = X0 + fb.width - 1;
+__device__ __forceinline__ bool collide_u8(const BcgBatch& b, const BcgMapDesc& m, const FootRef& f, unsigned lane) {
+  const int X0 = f.px + f.xmin, Y0 = f.py + f.ymin;
+  const int X1 = X0 + f.width - 1;
   unsigned hit = 0;
   if (!(X1 < 0 || X0 >= m.width)) {
     const int w0 = max(X0, 0) >> 2, w1 = min(X1, m.width - 1) >> 2;
     const uint8_t* data = b.map_arena + m.data_off;
-    const uint64_t* rows = b.lut.rows + (int64_t)fb.bin * b.lut.max_rows * b.lut.wpr;
+    const uint64_t* rows = b.lut.rows + (int64_t)f.bin * b.lut.max_rows * b.lut.wpr;
     const int half = lane >> 4, sub = lane & 15;
-    for (int dy = half; dy < fb.nrows; dy += 2) {
+    for (int dy = half; dy < f.nrows; dy += 2) {
       const int Y = Y0 + dy;
       if (Y < 0 || Y >= m.height) continue;
       const uint32_t* rowp = reinterpret_cast<const uint32_t*>(data + (int64_t)Y * m.pitch);
       for (int wi = w0 + sub; wi <= w1; wi += 16) {
-        const uint32_t m4 = mask_bits32(rows + (int64_t)dy * b.lut.wpr, b.lut.wpr, (wi << 2) - X0) & 0xfu;
-        if (m4 == 0u) continue;
         const uint32_t bytes = __ldg(rowp + wi);
+        const uint32_t m4 = mask_bits32(rows + (int64_t)dy * b.lut.wpr, b.lut.wpr, (wi << 2) - X0) & 0xfu;
         const uint32_t eq = __vcmpeq4(bytes, 0xFEFEFEFEu);                 // 0xFF where cell == 254
         const uint32_t sel = ((m4 * 0x00204081u) & 0x01010101u) * 0xFFu;  // 0xFF where the mask is set
         hit |= eq & sel;

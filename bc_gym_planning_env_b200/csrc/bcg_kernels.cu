@@ -55,10 +55,12 @@ int check_batch(const BcgParams* p, const BcgBatch* b) {
   BCG_REQUIRE(p->delay_control < 4096 && p->delay_pose < 4096 && p->delay_state < 4096, "delay too large");
   const BcgStateLayout L = make_layout(*p);
   BCG_REQUIRE(b->n_frows == L.n_frows && b->n_irows == L.n_irows, "state row count does not match bcg_state_layout");
-  BCG_REQUIRE(b->state_f && b->state_i && b->init_f && b->init_i && b->cand, "null state pointers");
+  BCG_REQUIRE(b->state_f && b->state_i && b->init_f && b->init_i && b->cand && b->cand_i, "null state pointers");
   BCG_REQUIRE(b->map_id && b->path_id && b->maps && b->paths && b->map_arena && b->tile_arena && b->path_arena,
               "null arena pointers");
-  BCG_REQUIRE(b->lut.edges && b->lut.verts && b->lut.header && b->lut.rows && b->lut.fp_pix, "null footprint table");
+  BCG_REQUIRE(b->lut.edges && b->lut.verts && b->lut.header && b->lut.rows && b->lut.fp_pix && b->lut.bucket_first,
+              "null footprint table");
+  BCG_REQUIRE(b->lut.n_buckets > 0 && b->lut.bucket_scale > 0, "empty footprint bucket table");
   BCG_REQUIRE(b->lut.n_verts > 0 && b->lut.n_verts <= 32, "footprint must have 1..32 vertices");
   BCG_REQUIRE(b->lut.n_bins > 0 && b->lut.wpr > 0 && b->lut.max_rows > 0, "empty footprint table");
   BCG_REQUIRE(b->status && b->stats, "null status/stats");
@@ -67,8 +69,10 @@ int check_batch(const BcgParams* p, const BcgBatch* b) {
 
 // ---- kernels -------------------------------------------------------------------------------------
 
-// robot.step for every env: envs/base/env.py:371-373 (control delay) + robot model into b.cand.
-__global__ void __launch_bounds__(256) kin_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L,
+// robot.step for every env: envs/base/env.py:371-373 (control delay) + robot model into b.cand, plus the
+// pixel / footprint-bin reference of the proposed pose for the collision kernel.  One thread per env:
+// every load and store is a coalesced SoA row access.
+__global__ void __launch_bounds__(128) kin_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L,
                                                   const void* __restrict__ actions, const int action_is_f64,
                                                   const uint64_t step_index) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -84,139 +88,211 @@ __global__ void __launch_bounds__(256) kin_kernel(const BcgParams p, const BcgBa
     u[0] = (double)a.x;
     u[1] = (double)a.y;
   }
+  double s[7];
+#pragma unroll
+  for (int r = 0; r < 7; ++r) s[r] = b.state_f[(BCG_F_ROBOT + r) * N + e];
+  const int map_id = b.map_id[e];
   if (p.delay_control > 0) {
     int q = b.state_i[BCG_I_QC * N + e];
     delay_line<2>(b.state_f + (int64_t)L.ring_control * N + e, N, q, p.delay_control, u);
     b.state_i[BCG_I_QC * N + e] = q;
   }
-  double s[7];
-#pragma unroll
-  for (int r = 0; r < 7; ++r) s[r] = b.state_f[(BCG_F_ROBOT + r) * N + e];
   robot_step(s, u[0], u[1], p, p.env_id_base + (uint64_t)e, step_index);
 #pragma unroll
   for (int r = 0; r < 7; ++r) b.cand[r * N + e] = s[r];
+  const FootRef f = make_foot_ref(p, b.lut, b.maps, map_id, s[0], s[1], s[2], b.status);
+  store_foot_ref(b.cand_i + e, N, f);
 }
 
-// Collision + the rest of _resolve_state_transition (env.py:363-398) + reward (reward.py:214-259) +
-// done (env.py:407-419); one warp per env, scalars are computed warp-uniformly and stored by lane 0.
-__global__ void __launch_bounds__(256) commit_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L,
-                                                     const BcgStepOut out) {
+// pixel / footprint-bin reference of arbitrary poses [3][n] (stand-alone collision entry points)
+__global__ void __launch_bounds__(128) pose_prep_kernel(const BcgParams p, const BcgBatch b,
+                                                        const double* __restrict__ poses) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= b.n_envs) return;
+  const int64_t N = b.n_envs;
+  const FootRef f = make_foot_ref(p, b.lut, b.maps, b.map_id[e], poses[e], poses[N + e], poses[2 * N + e], b.status);
+  store_foot_ref(b.cand_i + e, N, f);
+}
+
+// One warp per env: footprint-vs-lethal-tile collision of the proposed pose (env.py:455), then the
+// reward of the pose the reward provider will see (reward.py:214-259).  Reads only; its few results go
+// to the scratch rows, the thread-per-env commit kernel applies them.  No store precedes a load, so all
+// of a warp's independent loads are in flight together.
+__global__ void __launch_bounds__(256, 4) collide_reward_kernel(const BcgParams p, const BcgBatch b,
+                                                                const BcgStateLayout L) {
   const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned lane = threadIdx.x & 31;
   if (e >= b.n_envs) return;
   const int64_t N = b.n_envs;
-  double* sf = b.state_f + e;
-  int32_t* si = b.state_i + e;
+  const double* sf = b.state_f + e;
+  const int32_t* si = b.state_i + e;
 
-  double c[7];
+  const FootRef f = load_foot_ref(b.cand_i + e, N);
+  const int map_id = __ldg(b.map_id + e), path_id = __ldg(b.path_id + e);
+  int target = __ldg(si + BCG_I_TARGET * N);
+  const int qp = __ldg(si + BCG_I_QP * N);
+  double min_dist = __ldg(sf + BCG_F_MIN_DIST * N);
+  double pose[3], old_pose[3], ring_front[3];
 #pragma unroll
-  for (int r = 0; r < 7; ++r) c[r] = b.cand[r * N + e];
-  const BcgMapDesc m = b.maps[b.map_id[e]];
-  const BcgPathDesc pd = b.paths[b.path_id[e]];
-
-  const bool hit = collide_tiles<false>(p, b, m, c[0], c[1], c[2], lane, nullptr);
-  if (hit) {  // env.py:458-459 + tricycle_model.py:471-476: pose restored, v = w = 0, wheel/steer kept
-    c[0] = sf[(BCG_F_ROBOT + 0) * N];
-    c[1] = sf[(BCG_F_ROBOT + 1) * N];
-    c[2] = sf[(BCG_F_ROBOT + 2) * N];
-    c[3] = 0.0;
-    c[4] = 0.0;
+  for (int r = 0; r < 3; ++r) {
+    pose[r] = __ldg(b.cand + r * N + e);
+    old_pose[r] = __ldg(sf + (BCG_F_ROBOT + r) * N);
   }
-  int iter = si[BCG_I_ITER * N];
-  int target = si[BCG_I_TARGET * N];
-  int collided = si[BCG_I_COLLIDED * N];
-  double min_dist = sf[BCG_F_MIN_DIST * N];
-  const bool done_before = (target > pd.n - 1) || (iter >= p.iteration_timeout) || (collided != 0);
-
-  // delay lines (env.py:377-389).  All lanes compute the same values; only lane 0 writes.
-  double dpose[3] = {c[0], c[1], c[2]};
-  double dstate[7];
+  const int q_head = qp & 0xffff, q_len = qp >> 16;
+  const bool from_ring = p.delay_pose > 0 && q_len > 0;   // env.py:27-49: the front of a non-empty queue
+  if (from_ring) {
 #pragma unroll
-  for (int r = 0; r < 7; ++r) dstate[r] = c[r];
-  int qp = si[BCG_I_QP * N], qs = si[BCG_I_QS * N];
-  __syncwarp();
-  if (lane == 0) {
-#pragma unroll
-    for (int r = 0; r < 7; ++r) sf[(BCG_F_ROBOT + r) * N] = c[r];
-    delay_line<3>(sf + (int64_t)L.ring_pose * N, N, qp, p.delay_pose, dpose);
-    delay_line<7>(sf + (int64_t)L.ring_state * N, N, qs, p.delay_state, dstate);
+    for (int r = 0; r < 3; ++r) ring_front[r] = __ldg(sf + (int64_t)(L.ring_pose + q_head * 3 + r) * N);
   }
-#pragma unroll
-  for (int r = 0; r < 3; ++r) dpose[r] = __shfl_sync(BCG_FULL, dpose[r], 0);
-#pragma unroll
-  for (int r = 0; r < 7; ++r) dstate[r] = __shfl_sync(BCG_FULL, dstate[r], 0);
+  const BcgMapDesc m = b.maps[map_id];
+  const BcgPathDesc pd = b.paths[path_id];
 
-  const double time = sf[BCG_F_TIME * N] + p.dt;
-  iter += 1;
-  collided |= hit ? 1 : 0;
+  const bool hit = collide_tiles<false>(b, m, f, lane, nullptr);
 
-  // reward on the *delayed* pose (reward.py:227-232 reads state.pose)
+  // the pose State.pose will hold after this step: rolled back on a hit (env.py:458-459), delayed (:377-380)
+#pragma unroll
+  for (int r = 0; r < 3; ++r) pose[r] = from_ring ? ring_front[r] : (hit ? old_pose[r] : pose[r]);
+
+  const bool goal_before = target > pd.n - 1;
   double reward = 0.0;
   const double* P = b.path_arena + pd.off;
-  if (!(target > pd.n - 1)) {
-    const int last = last_reached_from(p, b, pd, target, dpose[0], dpose[1], dpose[2], lane);
+  if (!goal_before) {
+    const int last = last_reached_from(p, b, pd, target, pose[0], pose[1], pose[2], lane);
     if (last >= target) {
       target = last + 1;
       if (target > pd.n - 1) {
         min_dist = 0.0;
       } else {
-        min_dist = hypot(__ldg(P + target) - dpose[0], __ldg(P + pd.pitch + target) - dpose[1]);
+        min_dist = hypot(__ldg(P + target) - pose[0], __ldg(P + pd.pitch + target) - pose[1]);
       }
       reward = 1.0;
     } else {
-      const double d = hypot(__ldg(P + target) - dpose[0], __ldg(P + pd.pitch + target) - dpose[1]);
+      const double d = hypot(__ldg(P + target) - pose[0], __ldg(P + pd.pitch + target) - pose[1]);
       if (d < min_dist) {
         reward = (min_dist - d) * p.progress_multiplier;
         min_dist = d;
       }
     }
   }
-  const bool goal = target > pd.n - 1;
-  const bool timed_out = iter >= p.iteration_timeout;
-  const bool done = goal || timed_out || (collided != 0);
-  const double ep_return = sf[BCG_F_EP_RETURN * N] + reward;
-  __syncwarp();  // every lane has read the old state; lane 0 (or the reset loop) may now overwrite it
-
   if (lane == 0) {
+    b.cand[7 * N + e] = reward;
+    b.cand[8 * N + e] = min_dist;
+    b.cand_i[BCG_CI_TARGET * N + e] = target;
+    b.cand_i[BCG_CI_FLAGS * N + e] = (hit ? 1 : 0) | ((target > pd.n - 1) ? 2 : 0) | (goal_before ? 4 : 0);
+  }
+}
+
+// One thread per env: the rest of _resolve_state_transition (env.py:363-398) -- rollback, pose and
+// robot-state delay lines, time/iter, sticky collision -- then done (env.py:407-419), episode statistics,
+// auto-reset (env.py:293-303) and the compact fp32 observation.  All accesses are coalesced SoA rows.
+__global__ void __launch_bounds__(128) commit_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L,
+                                                     const BcgStepOut out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = e < b.n_envs;
+  const int64_t N = b.n_envs;
+  double ev_ret = 0.0, ev_len = 0.0;
+  int ev = 0, ev_col = 0, ev_goal = 0, ev_to = 0;
+  if (active) {
+    double* sf = b.state_f + e;
+    int32_t* si = b.state_i + e;
+    double c[7];
+#pragma unroll
+    for (int r = 0; r < 7; ++r) c[r] = b.cand[r * N + e];
+    const double reward = b.cand[7 * N + e];
+    const double min_dist = b.cand[8 * N + e];
+    const int target = b.cand_i[BCG_CI_TARGET * N + e];
+    const int flags = b.cand_i[BCG_CI_FLAGS * N + e];
+    const bool hit = flags & 1, goal = flags & 2, goal_before = flags & 4;
+    int iter = si[BCG_I_ITER * N];
+    int collided = si[BCG_I_COLLIDED * N];
+    int qp = si[BCG_I_QP * N], qs = si[BCG_I_QS * N];
+    const bool done_before = goal_before || (iter >= p.iteration_timeout) || (collided != 0);
+    if (hit) {  // env.py:458-459 + tricycle_model.py:471-476: pose restored, v = w = 0, wheel/steer kept
+      c[0] = sf[(BCG_F_ROBOT + 0) * N];
+      c[1] = sf[(BCG_F_ROBOT + 1) * N];
+      c[2] = sf[(BCG_F_ROBOT + 2) * N];
+      c[3] = 0.0;
+      c[4] = 0.0;
+    }
+    double dpose[3] = {c[0], c[1], c[2]};
+    double dstate[7];
+#pragma unroll
+    for (int r = 0; r < 7; ++r) dstate[r] = c[r];
+    delay_line<3>(sf + (int64_t)L.ring_pose * N, N, qp, p.delay_pose, dpose);
+    delay_line<7>(sf + (int64_t)L.ring_state * N, N, qs, p.delay_state, dstate);
+    const double time = sf[BCG_F_TIME * N] + p.dt;
+    const double ep_return = sf[BCG_F_EP_RETURN * N] + reward;
+    iter += 1;
+    collided |= hit ? 1 : 0;
+    const bool timed_out = iter >= p.iteration_timeout;
+    const bool done = goal || timed_out || (collided != 0);
     if (out.reward) out.reward[e] = reward;
     if (out.done) out.done[e] = done ? 1 : 0;
     if (out.hit) out.hit[e] = hit ? 1 : 0;
-    if (done && !done_before) {  // episode statistics, once per episode
-      atomicAdd(b.stats + BCG_STAT_EPISODES, 1.0);
-      atomicAdd(b.stats + BCG_STAT_RETURN, ep_return);
-      atomicAdd(b.stats + BCG_STAT_LENGTH, (double)iter);
-      if (collided) atomicAdd(b.stats + BCG_STAT_COLLIDED, 1.0);
-      if (goal) atomicAdd(b.stats + BCG_STAT_GOAL, 1.0);
-      if (timed_out) atomicAdd(b.stats + BCG_STAT_TIMEOUT, 1.0);
+    if (done && !done_before) {
+      ev = 1;
+      ev_ret = ep_return;
+      ev_len = (double)iter;
+      ev_col = collided;
+      ev_goal = goal ? 1 : 0;
+      ev_to = timed_out ? 1 : 0;
+    }
+    float ov[12];
+    if (done && p.auto_reset) {
+      for (int r = 0; r < L.n_frows; ++r) sf[(int64_t)r * N] = b.init_f[(int64_t)r * N + e];
+      for (int r = 0; r < L.n_irows; ++r) si[(int64_t)r * N] = b.init_i[(int64_t)r * N + e];
+      if (out.obs_vec) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) ov[r] = (float)b.init_f[(int64_t)(BCG_F_DPOSE + r) * N + e];
+#pragma unroll
+        for (int r = 0; r < 7; ++r) ov[3 + r] = (float)b.init_f[(int64_t)(BCG_F_DROBOT + r) * N + e];
+        ov[10] = (float)b.init_f[(int64_t)BCG_F_TIME * N + e];
+        ov[11] = (float)b.init_i[(int64_t)BCG_I_TARGET * N + e];
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 7; ++r) sf[(BCG_F_ROBOT + r) * N] = c[r];
+#pragma unroll
+      for (int r = 0; r < 7; ++r) sf[(BCG_F_DROBOT + r) * N] = dstate[r];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) sf[(BCG_F_DPOSE + r) * N] = dpose[r];
+      sf[BCG_F_TIME * N] = time;
+      sf[BCG_F_MIN_DIST * N] = min_dist;
+      sf[BCG_F_EP_RETURN * N] = ep_return;
+      si[BCG_I_ITER * N] = iter;
+      si[BCG_I_TARGET * N] = target;
+      si[BCG_I_COLLIDED * N] = collided;
+      si[BCG_I_QP * N] = qp;
+      si[BCG_I_QS * N] = qs;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) ov[r] = (float)dpose[r];
+#pragma unroll
+      for (int r = 0; r < 7; ++r) ov[3 + r] = (float)dstate[r];
+      ov[10] = (float)time;
+      ov[11] = (float)target;
+    }
+    if (out.obs_vec) {
+      float4* o = reinterpret_cast<float4*>(out.obs_vec + (int64_t)e * 12);
+      o[0] = make_float4(ov[0], ov[1], ov[2], ov[3]);
+      o[1] = make_float4(ov[4], ov[5], ov[6], ov[7]);
+      o[2] = make_float4(ov[8], ov[9], ov[10], ov[11]);
     }
   }
-  if (done && p.auto_reset) {
-    // PlanEnv.reset (env.py:293-303): every row back to the stored initial state
-    for (int r = lane; r < L.n_frows; r += 32) sf[(int64_t)r * N] = b.init_f[(int64_t)r * N + e];
-    for (int r = lane; r < L.n_irows; r += 32) si[(int64_t)r * N] = b.init_i[(int64_t)r * N + e];
-  } else if (lane == 0) {
+  // episode statistics: one atomic set per warp that saw an episode end
+  if (__any_sync(BCG_FULL, ev != 0)) {
+    double v[6] = {(double)ev, ev_ret, ev_len, (double)ev_col, (double)ev_goal, (double)ev_to};
 #pragma unroll
-    for (int r = 0; r < 7; ++r) sf[(BCG_F_DROBOT + r) * N] = dstate[r];
+    for (int k = 0; k < 6; ++k) {
 #pragma unroll
-    for (int r = 0; r < 3; ++r) sf[(BCG_F_DPOSE + r) * N] = dpose[r];
-    sf[BCG_F_TIME * N] = time;
-    sf[BCG_F_MIN_DIST * N] = min_dist;
-    sf[BCG_F_EP_RETURN * N] = ep_return;
-    si[BCG_I_ITER * N] = iter;
-    si[BCG_I_TARGET * N] = target;
-    si[BCG_I_COLLIDED * N] = collided;
-    si[BCG_I_QP * N] = qp;
-    si[BCG_I_QS * N] = qs;
-  }
-  if (out.obs_vec) {
-    __syncwarp();
-    if (lane < 12) {
-      float v;
-      if (lane < 3) v = (float)sf[(BCG_F_DPOSE + lane) * N];
-      else if (lane < 10) v = (float)sf[(BCG_F_DROBOT + lane - 3) * N];
-      else if (lane == 10) v = (float)sf[BCG_F_TIME * N];
-      else v = (float)si[BCG_I_TARGET * N];
-      out.obs_vec[(int64_t)e * 12 + lane] = v;
+      for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(BCG_FULL, v[k], o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(b.stats + BCG_STAT_EPISODES, v[0]);
+      atomicAdd(b.stats + BCG_STAT_RETURN, v[1]);
+      atomicAdd(b.stats + BCG_STAT_LENGTH, v[2]);
+      atomicAdd(b.stats + BCG_STAT_COLLIDED, v[3]);
+      atomicAdd(b.stats + BCG_STAT_GOAL, v[4]);
+      atomicAdd(b.stats + BCG_STAT_TIMEOUT, v[5]);
     }
   }
 }
@@ -294,23 +370,23 @@ __global__ void __launch_bounds__(256) tiles_kernel(const BcgBatch b, const int 
   }
 }
 
-__global__ void __launch_bounds__(256) collision_kernel(const BcgParams p, const BcgBatch b,
-                                                        const double* __restrict__ poses, uint8_t* __restrict__ flags,
+// pose_collides of the poses prepared in b.cand_i; one warp per env
+__global__ void __launch_bounds__(256) collision_kernel(const BcgBatch b, uint8_t* __restrict__ flags,
                                                         int32_t* __restrict__ pixels, const int use_u8) {
   const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned lane = threadIdx.x & 31;
   if (e >= b.n_envs) return;
   const int64_t N = b.n_envs;
-  const BcgMapDesc m = b.maps[b.map_id[e]];
-  const double x = poses[e], y = poses[N + e], th = poses[2 * N + e];
+  const FootRef f = load_foot_ref(b.cand_i + e, N);
+  const BcgMapDesc m = b.maps[__ldg(b.map_id + e)];
   bool hit;
   int cnt = 0;
   if (use_u8) {
-    hit = collide_u8(p, b, m, x, y, th, lane);
+    hit = collide_u8(b, m, f, lane);
   } else if (pixels) {
-    hit = collide_tiles<true>(p, b, m, x, y, th, lane, &cnt);
+    hit = collide_tiles<true>(b, m, f, lane, &cnt);
   } else {
-    hit = collide_tiles<false>(p, b, m, x, y, th, lane, nullptr);
+    hit = collide_tiles<false>(b, m, f, lane, nullptr);
   }
   if (lane == 0) {
     flags[e] = hit ? 1 : 0;
@@ -327,92 +403,250 @@ __device__ __forceinline__ int cv_round_sat(double v) {
 }
 
 #define BCG_EGO_MAX 256
+#define BCG_EGO_THREADS 256
+#define BCG_EGO_MAX_TILE_ROWS 384
+
+struct EgoAffine {
+  double a11, a12, b1, a21, a22, b2;   // source = A * (u, v) + b, cv::warpAffine's inverted map
+};
+
+// costmap_utils.py:42-65 + the fp64 inversion cv::warpAffine applies to the float32 forward matrix
+__device__ __forceinline__ EgoAffine ego_affine(const BcgParams& p, const BcgMapDesc& m, double px, double py,
+                                                double pth) {
+  const double cx = (double)world_to_pixel_1d(px, m.origin_x, p.inv_resolution);
+  const double cy = (double)world_to_pixel_1d(py, m.origin_y, p.inv_resolution);
+  const double deg = 180 * pth / BCG_PI;
+  const double rad = deg * (BCG_PI / 180.);
+  double bsn, acs;
+  sincos(rad, &bsn, &acs);
+  const float r00 = (float)acs, r01 = (float)bsn, r02 = (float)((1 - acs) * cx - bsn * cy);
+  const float r10 = (float)(-bsn), r11 = (float)acs, r12 = (float)(bsn * cx + (1 - acs) * cy);
+  const double dsx = rint((p.ego_x0 - (m.origin_x - px)) * p.inv_resolution);
+  const double dsy = rint((p.ego_y0 - (m.origin_y - py)) * p.inv_resolution);
+  const double M0 = (double)r00, M1 = (double)r01, M2 = (double)(r02 - (float)dsx);
+  const double M3 = (double)r10, M4 = (double)r11, M5 = (double)(r12 - (float)dsy);
+  double D = M0 * M4 - M1 * M3;
+  D = (D != 0.0) ? 1. / D : 0.0;
+  EgoAffine a;
+  a.a11 = M4 * D;
+  a.a22 = M0 * D;
+  a.a12 = M1 * (-D);
+  a.a21 = M3 * (-D);
+  a.b1 = -a.a11 * M2 - a.a12 * M5;
+  a.b2 = -a.a21 * M2 - a.a22 * M5;
+  return a;
+}
+
+// goal_n_state (envs/egocentric.py:141-160) by one thread
+__device__ __forceinline__ void write_goal_n_state(const BcgParams& p, const BcgBatch& b, int e, double px, double py,
+                                                   double pth, float* __restrict__ goal_n_state) {
+  const int64_t N = b.n_envs;
+  const double* sf = b.state_f + e;
+  float* g = goal_n_state + (int64_t)e * 9;
+  const BcgPathDesc pd = b.paths[b.path_id[e]];
+  const int target = b.state_i[BCG_I_TARGET * N + e];
+  if (target > pd.n - 1) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) g[k] = 0.f;
+    return;
+  }
+  // from_global_to_egocentric (coordinate_transformations.py:341-362 -> :57-84 -> :310-328)
+  const double* P = b.path_arena + pd.off;
+  const double gx = P[target], gy = P[pd.pitch + target], gt = P[2 * pd.pitch + target];
+  double sn, cs;
+  sincos(pth, &sn, &cs);
+  const double tx = -px * cs - py * sn;
+  const double ty = px * sn - py * cs;
+  const double tt = wrap_angle(-pth);
+  double st, ct;
+  sincos(tt, &st, &ct);
+  const double ex = ct * gx - st * gy + tx;
+  const double ey = st * gx + ct * gy + ty;
+  const double ea = wrap_angle(gt + tt);
+  g[0] = (float)clampd(ex / p.ego_world_w, -1.0, 1.0);
+  g[1] = (float)clampd(ey / p.ego_world_h, -1.0, 1.0);
+  g[2] = (float)ea;
+  g[3] = (float)sf[(BCG_F_DROBOT + 0) * N];
+  g[4] = (float)sf[(BCG_F_DROBOT + 1) * N];
+  g[5] = (float)sf[(BCG_F_DROBOT + 2) * N];
+  g[6] = (float)sf[(BCG_F_DROBOT + 3) * N];
+  g[7] = (float)sf[(BCG_F_DROBOT + 4) * N];
+  g[8] = (float)sf[(BCG_F_DROBOT + 6) * N];
+}
+
+// x-extent of a convex quad within the horizontal band [ylo, yhi]; extremes lie on the boundary
+__device__ __forceinline__ void quad_band_extent(const double qx[4], const double qy[4], double ylo, double yhi,
+                                                 double& xmin, double& xmax) {
+  xmin = 1e300;
+  xmax = -1e300;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double xa = qx[k], ya = qy[k], xb = qx[(k + 1) & 3], yb = qy[(k + 1) & 3];
+    double t0 = 0.0, t1 = 1.0;
+    const double dy = yb - ya;
+    if (dy == 0.0) {
+      if (ya < ylo || ya > yhi) continue;
+    } else {
+      double ta = (ylo - ya) / dy, tb = (yhi - ya) / dy;
+      if (ta > tb) { const double t = ta; ta = tb; tb = t; }
+      t0 = fmax(ta, 0.0);
+      t1 = fmin(tb, 1.0);
+      if (t0 > t1) continue;
+    }
+    const double x0 = xa + (xb - xa) * t0, x1 = xa + (xb - xa) * t1;
+    xmin = fmin(xmin, fmin(x0, x1));
+    xmax = fmax(xmax, fmax(x0, x1));
+  }
+}
 
 // EgocentricCostmap.observation (envs/egocentric.py:125-160): extract_egocentric_costmap
 // (utilities/costmap_utils.py:25-75) = cv2.getRotationMatrix2D composed in float32 with the crop
 // shift, then cv2.warpAffine(INTER_NEAREST, borderValue=0): fp64 inverse and 10-bit fixed-point source
-// coordinates; plus the 9-vector goal_n_state (:152-159).
-__global__ void __launch_bounds__(256) ego_kernel(const BcgParams p, const BcgBatch b, uint8_t* __restrict__ image,
-                                                  float* __restrict__ goal_n_state) {
+// coordinates X = (rint(A11 u 2^10) + rint((A12 v + b1) 2^10) + 512) >> 10.
+//
+// One CTA per env, crops up to 128 px wide.  The source pixels of the crop lie in a rotated rectangle.
+// Per source row, the span of that rectangle (grown by the 0.501 px the fixed-point rounding can move a
+// sample) is staged into shared memory with coalesced 4-byte loads, zero outside the map (= borderValue);
+// the rotated gather then runs out of shared memory with no bounds checks: 7 instructions per pixel.
+// The tile pitch is 4 * odd bytes so a 90-degree gather walks distinct banks.
+__global__ void __launch_bounds__(BCG_EGO_THREADS, 5) ego_kernel(const BcgParams p, const BcgBatch b,
+                                                              uint8_t* __restrict__ image,
+                                                              float* __restrict__ goal_n_state,
+                                                              const int tile_capacity) {
+  extern __shared__ __align__(16) uint8_t tile[];
   __shared__ int adx[BCG_EGO_MAX], ady[BCG_EGO_MAX], bdx[BCG_EGO_MAX], bdy[BCG_EGO_MAX];
+  __shared__ short2 span[BCG_EGO_MAX_TILE_ROWS];
+  __shared__ EgoAffine aff_s;
+  __shared__ int box[4];
   const int e = blockIdx.x;
   const int64_t N = b.n_envs;
   const double* sf = b.state_f + e;
   const BcgMapDesc m = b.maps[b.map_id[e]];
   const double px = sf[(BCG_F_DPOSE + 0) * N], py = sf[(BCG_F_DPOSE + 1) * N], pth = sf[(BCG_F_DPOSE + 2) * N];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
 
-  if (image) {
-    // costmap_utils.py:42-65
-    const double cx = (double)world_to_pixel_1d(px, m.origin_x, p.inv_resolution);
-    const double cy = (double)world_to_pixel_1d(py, m.origin_y, p.inv_resolution);
-    const double deg = 180 * pth / BCG_PI;
-    const double rad = deg * (BCG_PI / 180.);
-    double bsn, acs;
-    sincos(rad, &bsn, &acs);
-    const float r00 = (float)acs, r01 = (float)bsn, r02 = (float)((1 - acs) * cx - bsn * cy);
-    const float r10 = (float)(-bsn), r11 = (float)acs, r12 = (float)(bsn * cx + (1 - acs) * cy);
-    const double dsx = rint((p.ego_x0 - (m.origin_x - px)) * p.inv_resolution);
-    const double dsy = rint((p.ego_y0 - (m.origin_y - py)) * p.inv_resolution);
-    const double M0 = (double)r00, M1 = (double)r01, M2 = (double)(r02 - (float)dsx);
-    const double M3 = (double)r10, M4 = (double)r11, M5 = (double)(r12 - (float)dsy);
-    // cv::warpAffine inverts the forward map in double
-    double D = M0 * M4 - M1 * M3;
-    D = (D != 0.0) ? 1. / D : 0.0;
-    const double A11 = M4 * D, A22 = M0 * D, A12 = M1 * (-D), A21 = M3 * (-D);
-    const double b1 = -A11 * M2 - A12 * M5;
-    const double b2 = -A21 * M2 - A22 * M5;
-    for (int t = threadIdx.x; t < p.ego_w; t += blockDim.x) {
-      adx[t] = cv_round_sat(A11 * t * 1024);
-      ady[t] = cv_round_sat(A21 * t * 1024);
+  if (threadIdx.x == 0) aff_s = ego_affine(p, m, px, py, pth);
+  __syncthreads();
+  const EgoAffine A = aff_s;
+  for (int t = threadIdx.x; t < p.ego_w; t += blockDim.x) {
+    adx[t] = cv_round_sat(A.a11 * t * 1024);
+    ady[t] = cv_round_sat(A.a21 * t * 1024);
+  }
+  for (int t = threadIdx.x; t < p.ego_h; t += blockDim.x) {
+    bdx[t] = cv_round_sat((A.a12 * t + A.b1) * 1024) + 512;
+    bdy[t] = cv_round_sat((A.a22 * t + A.b2) * 1024) + 512;
+  }
+  __syncthreads();
+  // source bounding box (NOT clipped to the map): X(u, v) = (adx[u] + bdx[v]) >> 10 is monotone in each
+  // table entry, so its extremes are at extreme table entries; warp 0 reduces the four tables.
+  if (warp == 0) {
+    int ax0 = 0x7fffffff, ax1 = -0x7fffffff, ay0 = 0x7fffffff, ay1 = -0x7fffffff;
+    int bx0 = 0x7fffffff, bx1 = -0x7fffffff, by0 = 0x7fffffff, by1 = -0x7fffffff;
+    for (int t = lane; t < p.ego_w; t += 32) {
+      ax0 = min(ax0, adx[t]); ax1 = max(ax1, adx[t]);
+      ay0 = min(ay0, ady[t]); ay1 = max(ay1, ady[t]);
     }
-    for (int t = threadIdx.x; t < p.ego_h; t += blockDim.x) {
-      bdx[t] = cv_round_sat((A12 * t + b1) * 1024) + 512;
-      bdy[t] = cv_round_sat((A22 * t + b2) * 1024) + 512;
+    for (int t = lane; t < p.ego_h; t += 32) {
+      bx0 = min(bx0, bdx[t]); bx1 = max(bx1, bdx[t]);
+      by0 = min(by0, bdy[t]); by1 = max(by1, bdy[t]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ax0 = min(ax0, __shfl_xor_sync(BCG_FULL, ax0, o)); ax1 = max(ax1, __shfl_xor_sync(BCG_FULL, ax1, o));
+      ay0 = min(ay0, __shfl_xor_sync(BCG_FULL, ay0, o)); ay1 = max(ay1, __shfl_xor_sync(BCG_FULL, ay1, o));
+      bx0 = min(bx0, __shfl_xor_sync(BCG_FULL, bx0, o)); bx1 = max(bx1, __shfl_xor_sync(BCG_FULL, bx1, o));
+      by0 = min(by0, __shfl_xor_sync(BCG_FULL, by0, o)); by1 = max(by1, __shfl_xor_sync(BCG_FULL, by1, o));
+    }
+    if (lane == 0) {
+      const long long lim = 1ll << 40;   // poses astronomically far from the map: keep the arithmetic sane
+      box[0] = (int)(min(max(((long long)ax0 + bx0) >> 10, -lim), lim) & ~3ll);   // left edge on a 4-byte word
+      box[1] = (int)min(max(((long long)ax1 + bx1) >> 10, -lim), lim);
+      box[2] = (int)min(max(((long long)ay0 + by0) >> 10, -lim), lim);
+      box[3] = (int)min(max(((long long)ay1 + by1) >> 10, -lim), lim);
+    }
+  }
+  __syncthreads();
+  const int X0 = box[0], Y0 = box[2];
+  const int bw = box[1] - X0 + 1, bh = box[3] - Y0 + 1;
+  const int pitch_w = ((bw + 3) >> 2) | 1;          // words per tile row, odd
+  const int pitch_b = pitch_w * 4;
+  const uint8_t* src = b.map_arena + m.data_off;
+  const int npx = p.ego_w * p.ego_h;
+  uint8_t* dst = image + (int64_t)e * npx;
+  const bool staged = p.ego_w <= 128 && bh <= BCG_EGO_MAX_TILE_ROWS && bw > 0 && bh > 0 &&
+                      (long long)pitch_b * bh <= tile_capacity &&
+                      abs(X0) < (1 << 20) && abs(Y0) < (1 << 20);
+  if (staged) {
+    // per-row span of the rotated crop rectangle, grown by the rounding slack
+    const double uw = (double)(p.ego_w - 1), vh = (double)(p.ego_h - 1);
+    const double qx[4] = {A.b1, A.a11 * uw + A.b1, A.a11 * uw + A.a12 * vh + A.b1, A.a12 * vh + A.b1};
+    const double qy[4] = {A.b2, A.a21 * uw + A.b2, A.a21 * uw + A.a22 * vh + A.b2, A.a22 * vh + A.b2};
+    for (int y = threadIdx.x; y < bh; y += blockDim.x) {
+      double xmin, xmax;
+      quad_band_extent(qx, qy, (double)(Y0 + y) - 0.51, (double)(Y0 + y) + 0.51, xmin, xmax);
+      int xs = 1, xe = 0;
+      if (xmin <= xmax) {
+        xs = max((int)floor(xmin - 0.51) - X0, 0);
+        xe = min((int)ceil(xmax + 0.51) - X0, bw - 1);
+      }
+      span[y] = make_short2((short)xs, (short)xe);
     }
     __syncthreads();
-    const uint8_t* src = b.map_arena + m.data_off;
-    const int npx = p.ego_w * p.ego_h;
-    uint8_t* dst = image + (int64_t)e * npx;
+    uint32_t* tw = reinterpret_cast<uint32_t*>(tile);
+    for (int y = warp; y < bh; y += nwarp) {
+      const short2 sp = span[y];
+      if (sp.x > sp.y) continue;
+      const int Ys = Y0 + y;
+      const bool row_in = Ys >= 0 && Ys < m.height;
+      // X0 is a multiple of 4 and the row pitch of 32, so word loads are aligned and never straddle the map edge
+      const uint32_t* srow = reinterpret_cast<const uint32_t*>(src + (int64_t)(row_in ? Ys : 0) * m.pitch);
+      for (int xw = (sp.x >> 2) + lane; xw <= (sp.y >> 2); xw += 32) {
+        const int Xs = X0 + (xw << 2);
+        uint32_t word = 0u;
+        if (row_in && Xs >= 0 && Xs < m.pitch) word = __ldg(srow + (Xs >> 2));
+        tw[y * pitch_w + xw] = word;
+      }
+    }
+    __syncthreads();
+    // gather: warp w takes crop rows w, w+8, ...; lane l takes columns l, l+32, l+64, l+96
+    int ax[4], ay[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int u = lane + 32 * k;
+      ax[k] = (u < p.ego_w) ? adx[u] : adx[0];
+      ay[k] = (u < p.ego_w) ? ady[u] : ady[0];
+    }
+    for (int v = warp; v < p.ego_h; v += nwarp) {
+      const int bx = bdx[v] - (X0 << 10), by = bdy[v] - (Y0 << 10);
+      uint8_t* drow = dst + v * p.ego_w + lane;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int Xr = (ax[k] + bx) >> 10, Yr = (ay[k] + by) >> 10;
+        const uint8_t val = tile[Yr * pitch_b + Xr];
+        if (lane + 32 * k < p.ego_w) drow[32 * k] = val;
+      }
+    }
+  } else if (image) {
+    // generic path (huge crops / poses far outside any sane range): direct, bounds-checked global gather
     for (int i = threadIdx.x; i < npx; i += blockDim.x) {
       const int v = i / p.ego_w, u = i - v * p.ego_w;
-      const int X = (adx[u] + bdx[v]) >> 10, Y = (ady[u] + bdy[v]) >> 10;
+      const long long X = ((long long)adx[u] + bdx[v]) >> 10, Y = ((long long)ady[u] + bdy[v]) >> 10;
       uint8_t val = 0;
-      if ((unsigned)X < (unsigned)m.width && (unsigned)Y < (unsigned)m.height) val = __ldg(src + (int64_t)Y * m.pitch + X);
+      if (X >= 0 && X < m.width && Y >= 0 && Y < m.height) val = __ldg(src + Y * m.pitch + X);
       dst[i] = val;
     }
   }
-  if (goal_n_state && threadIdx.x == 0) {
-    float* g = goal_n_state + (int64_t)e * 9;
-    const BcgPathDesc pd = b.paths[b.path_id[e]];
-    const int target = b.state_i[BCG_I_TARGET * N + e];
-    if (target > pd.n - 1) {
-#pragma unroll
-      for (int k = 0; k < 9; ++k) g[k] = 0.f;
-    } else {
-      // from_global_to_egocentric (coordinate_transformations.py:341-362 -> :57-84 -> :310-328)
-      const double* P = b.path_arena + pd.off;
-      const double gx = P[target], gy = P[pd.pitch + target], gt = P[2 * pd.pitch + target];
-      double sn, cs;
-      sincos(pth, &sn, &cs);
-      const double tx = -px * cs - py * sn;
-      const double ty = px * sn - py * cs;
-      const double tt = wrap_angle(-pth);
-      double st, ct;
-      sincos(tt, &st, &ct);
-      const double ex = ct * gx - st * gy + tx;
-      const double ey = st * gx + ct * gy + ty;
-      const double ea = wrap_angle(gt + tt);
-      g[0] = (float)clampd(ex / p.ego_world_w, -1.0, 1.0);
-      g[1] = (float)clampd(ey / p.ego_world_h, -1.0, 1.0);
-      g[2] = (float)ea;
-      g[3] = (float)sf[(BCG_F_DROBOT + 0) * N];
-      g[4] = (float)sf[(BCG_F_DROBOT + 1) * N];
-      g[5] = (float)sf[(BCG_F_DROBOT + 2) * N];
-      g[6] = (float)sf[(BCG_F_DROBOT + 3) * N];
-      g[7] = (float)sf[(BCG_F_DROBOT + 4) * N];
-      g[8] = (float)sf[(BCG_F_DROBOT + 6) * N];
-    }
-  }
+  if (goal_n_state && threadIdx.x == 0) write_goal_n_state(p, b, e, px, py, pth, goal_n_state);
+}
+
+// goal_n_state only (no image requested): one thread per env
+__global__ void __launch_bounds__(128) goal_kernel(const BcgParams p, const BcgBatch b, float* __restrict__ goal_n_state) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= b.n_envs) return;
+  const int64_t N = b.n_envs;
+  const double* sf = b.state_f + e;
+  write_goal_n_state(p, b, e, sf[(BCG_F_DPOSE + 0) * N], sf[(BCG_F_DPOSE + 1) * N], sf[(BCG_F_DPOSE + 2) * N],
+                     goal_n_state);
 }
 
 __global__ void __launch_bounds__(256) gather_kernel(const BcgBatch b, const int64_t* __restrict__ idx, const int k,
@@ -531,8 +765,24 @@ int bcg_kinematic_step(const BcgParams* p, const BcgBatch* b, const void* action
                        uint64_t step_index, void* stream) {
   if (int rc = check_batch(p, b)) return rc;
   BCG_REQUIRE(actions, "null actions");
-  kin_kernel<<<blocks_for(b->n_envs, 256), 256, 0, (cudaStream_t)stream>>>(*p, *b, make_layout(*p), actions,
+  kin_kernel<<<blocks_for(b->n_envs, 128), 128, 0, (cudaStream_t)stream>>>(*p, *b, make_layout(*p), actions,
                                                                           action_is_f64, step_index);
+  BCG_CHECK_CUDA(cudaGetLastError());
+  return BCG_OK;
+}
+
+static int launch_ego(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, float* goal_n_state, cudaStream_t s) {
+  BCG_REQUIRE(p->ego_w > 0 && p->ego_h > 0 && p->ego_w <= BCG_EGO_MAX && p->ego_h <= BCG_EGO_MAX,
+              "egocentric crop must be 1..256 pixels per side");
+  if (ego_image) {
+    // bounding box of the rotated crop: at most ceil(hypot(w, h)) + 2 rows of (that + 7) bytes, pitch 4 * odd
+    const int side = (int)ceil(sqrt((double)p->ego_w * p->ego_w + (double)p->ego_h * p->ego_h)) + 2;
+    int cap = side * (((side + 3) / 4) | 1) * 4;
+    if (cap > 40 * 1024) cap = 40 * 1024;   // larger crops fall back to the direct global gather per CTA
+    ego_kernel<<<b->n_envs, BCG_EGO_THREADS, cap, s>>>(*p, *b, ego_image, goal_n_state, cap);
+  } else {
+    goal_kernel<<<blocks_for(b->n_envs, 128), 128, 0, s>>>(*p, *b, goal_n_state);
+  }
   BCG_CHECK_CUDA(cudaGetLastError());
   return BCG_OK;
 }
@@ -540,24 +790,44 @@ int bcg_kinematic_step(const BcgParams* p, const BcgBatch* b, const void* action
 int bcg_observe_ego(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, float* goal_n_state, void* stream) {
   if (int rc = check_batch(p, b)) return rc;
   BCG_REQUIRE(ego_image || goal_n_state, "nothing to compute");
-  BCG_REQUIRE(p->ego_w > 0 && p->ego_h > 0 && p->ego_w <= BCG_EGO_MAX && p->ego_h <= BCG_EGO_MAX,
-              "egocentric crop must be 1..256 pixels per side");
-  ego_kernel<<<b->n_envs, ego_image ? 256 : 32, 0, (cudaStream_t)stream>>>(*p, *b, ego_image, goal_n_state);
+  return launch_ego(p, b, ego_image, goal_n_state, (cudaStream_t)stream);
+}
+
+int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, int32_t action_is_f64,
+                    uint64_t step_index, const BcgStepOut* out, void* const* events, void* stream) {
+  if (int rc = check_batch(p, b)) return rc;
+  BCG_REQUIRE(actions && out, "null actions/out");
+  const bool ego = out->ego_image || out->goal_n_state;
+  cudaStream_t s = (cudaStream_t)stream;
+  const BcgStateLayout L = make_layout(*p);
+  if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[0], s));
+  kin_kernel<<<blocks_for(b->n_envs, 128), 128, 0, s>>>(*p, *b, L, actions, action_is_f64, step_index);
   BCG_CHECK_CUDA(cudaGetLastError());
+  if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[1], s));
+  collide_reward_kernel<<<blocks_for((int64_t)b->n_envs * 32, 256), 256, 0, s>>>(*p, *b, L);
+  BCG_CHECK_CUDA(cudaGetLastError());
+  if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[2], s));
+  commit_kernel<<<blocks_for(b->n_envs, 128), 128, 0, s>>>(*p, *b, L, *out);
+  BCG_CHECK_CUDA(cudaGetLastError());
+  if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[3], s));
+  if (ego) {
+    if (int rc = launch_ego(p, b, out->ego_image, out->goal_n_state, s)) return rc;
+  }
+  if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[4], s));
   return BCG_OK;
 }
 
 int bcg_step(const BcgParams* p, const BcgBatch* b, const void* actions, int32_t action_is_f64, uint64_t step_index,
              const BcgStepOut* out, void* stream) {
-  if (int rc = check_batch(p, b)) return rc;
-  BCG_REQUIRE(actions && out, "null actions/out");
-  cudaStream_t s = (cudaStream_t)stream;
-  const BcgStateLayout L = make_layout(*p);
-  kin_kernel<<<blocks_for(b->n_envs, 256), 256, 0, s>>>(*p, *b, L, actions, action_is_f64, step_index);
+  return bcg_step_events(p, b, actions, action_is_f64, step_index, out, nullptr, stream);
+}
+
+static int launch_collision(const BcgParams* p, const BcgBatch* b, const double* poses, uint8_t* flags_out,
+                            int32_t* pixels_out, int use_u8, cudaStream_t s) {
+  pose_prep_kernel<<<blocks_for(b->n_envs, 128), 128, 0, s>>>(*p, *b, poses);
   BCG_CHECK_CUDA(cudaGetLastError());
-  commit_kernel<<<blocks_for((int64_t)b->n_envs * 32, 256), 256, 0, s>>>(*p, *b, L, *out);
+  collision_kernel<<<blocks_for((int64_t)b->n_envs * 32, 256), 256, 0, s>>>(*b, flags_out, pixels_out, use_u8);
   BCG_CHECK_CUDA(cudaGetLastError());
-  if (out->ego_image || out->goal_n_state) return bcg_observe_ego(p, b, out->ego_image, out->goal_n_state, stream);
   return BCG_OK;
 }
 
@@ -565,19 +835,13 @@ int bcg_collision(const BcgParams* p, const BcgBatch* b, const double* poses, ui
                   void* stream) {
   if (int rc = check_batch(p, b)) return rc;
   BCG_REQUIRE(poses && flags_out, "null poses/flags");
-  collision_kernel<<<blocks_for((int64_t)b->n_envs * 32, 256), 256, 0, (cudaStream_t)stream>>>(*p, *b, poses, flags_out,
-                                                                                              pixels_out, 0);
-  BCG_CHECK_CUDA(cudaGetLastError());
-  return BCG_OK;
+  return launch_collision(p, b, poses, flags_out, pixels_out, 0, (cudaStream_t)stream);
 }
 
 int bcg_collision_u8(const BcgParams* p, const BcgBatch* b, const double* poses, uint8_t* flags_out, void* stream) {
   if (int rc = check_batch(p, b)) return rc;
   BCG_REQUIRE(poses && flags_out, "null poses/flags");
-  collision_kernel<<<blocks_for((int64_t)b->n_envs * 32, 256), 256, 0, (cudaStream_t)stream>>>(*p, *b, poses, flags_out,
-                                                                                              nullptr, 1);
-  BCG_CHECK_CUDA(cudaGetLastError());
-  return BCG_OK;
+  return launch_collision(p, b, poses, flags_out, nullptr, 1, (cudaStream_t)stream);
 }
 
 int bcg_gather_state(const BcgBatch* b, const int64_t* idx, int32_t k, double* out_f, int32_t* out_i, void* stream) {

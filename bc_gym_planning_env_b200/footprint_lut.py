@@ -105,6 +105,13 @@ class FootprintLut(object):
             self.rows[k, :h] = (padded.reshape(h, self.wpr, 64) * weights).sum(axis=2, dtype=np.uint64)
             self.pixels[k] = int(m.sum())
 
+        # uniform bucket table: first candidate bin for an angle without a binary search
+        self.n_buckets = 16384
+        self.bucket_scale = self.n_buckets / (2 * np.pi)
+        lefts = -np.pi + np.arange(self.n_buckets) / self.bucket_scale
+        self.bucket_first = np.clip(np.searchsorted(self.edges, lefts, side="right") - 1, 0,
+                                    self.n_bins - 1).astype(np.int32)
+
     def bin_of(self, angle):
         """Host twin of the device lookup (used by tests and by roofline accounting)."""
         t = angle if -np.pi <= angle < np.pi else float((angle + np.pi) % (2 * np.pi) - np.pi)
@@ -125,4 +132,4 @@ class FootprintLut(object):
 
     def arrays(self):
         return dict(edges=self.edges, verts=self.verts, header=self.header, rows=self.rows,
-                    fp_pix=self.fp_pix.reshape(-1))
+                    fp_pix=self.fp_pix.reshape(-1), bucket_first=self.bucket_first)

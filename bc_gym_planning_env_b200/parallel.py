@@ -1,0 +1,86 @@
+"""Multi-GPU plumbing: one process per GPU, envs sharded by contiguous index range.
+
+Envs are independent (reference envs/base/env.py:225-249: each PlanEnv owns its robot, reward state
+and queues; the costmap is read-only during step), so stepping needs NO collective.  torch.distributed
+(NCCL over NVLink on the box, gloo in CPU tests) is used for exactly two things:
+  * all-reduce(sum) of the small episode-statistics vector, once per report interval;
+  * fan-out of `get_state` snapshots for Monte-Carlo rollouts (README.md:45-61 of the reference):
+    broadcast the snapshot columns from one rank, every rank scatters them into its own envs.
+"""
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(n_total, rank=None, world_size=None):
+    """Contiguous [lo, hi) range of global env ids owned by `rank`; sizes differ by at most one."""
+    if rank is None or world_size is None:
+        rank, world_size = world()
+    base, rem = divmod(int(n_total), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_sum_(t):
+    """In-place sum over ranks (no-op for a single process).  Returns t."""
+    if world()[1] > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def allreduce_episode_stats(env, reset=False):
+    """Whole-job episode statistics: fp64 [STATS_WORDS] summed over ranks (see _native.STAT_NAMES)."""
+    return allreduce_sum_(env.episode_stats(reset=reset))
+
+
+def broadcast_snapshot(f, i, src=0):
+    """Broadcast snapshot columns (fp64 [F, k], int32 [I, k]) from rank `src`; other ranks pass
+    tensors of the right shape to be overwritten.  Returns (f, i)."""
+    if world()[1] > 1:
+        dist.broadcast(f, src=src)
+        dist.broadcast(i, src=src)
+    return f, i
+
+
+def fan_out_columns(k_states, n_local):
+    """Which snapshot column each local env starts from when k_states start states are replicated
+    over all envs of all ranks: global env g takes state g % k_states."""
+    rank, ws = world()
+    g0 = rank * n_local
+    return (torch.arange(n_local, dtype=torch.int64) + g0) % int(k_states)
+
+
+def monte_carlo_rollouts(env, start, actions, reduce=True):
+    """Monte-Carlo evaluation of `start` states (README.md:45-61 of the reference, batched).
+
+    env: a VecPlanEnv whose envs all share the map/path of the start states they are assigned;
+    start: VecState with k columns (already identical on every rank, e.g. via broadcast_snapshot);
+    actions: [H, k, 2] fixed action sequence per start state.  Every local env e is loaded with column
+    fan_out_columns()[e] and stepped H times with its own Philox stream.
+    Returns fp64 [k, 4]: (sum of returns, collisions, goals reached, rollouts) per start state, summed
+    over ranks when reduce."""
+    from bc_gym_planning_env_b200 import _native as nat
+    k = start.f.shape[1]
+    cols = fan_out_columns(k, env.n_envs).to(env.device)
+    env.set_state(type(start)(start.f.to(env.device)[:, cols].contiguous(), start.i.to(env.device)[:, cols].contiguous()))
+    ret = torch.zeros(env.n_envs, dtype=torch.float64, device=env.device)
+    acts = actions.to(env.device)
+    for h in range(acts.shape[0]):
+        _, r, _, _ = env.step(acts[h][cols].contiguous())
+        ret += r
+    out = torch.zeros((k, 4), dtype=torch.float64, device=env.device)
+    target = env.state_i[nat.I_TARGET].to(torch.int64)
+    n_path = torch.as_tensor([len(env.full_path(e)) for e in range(env.n_envs)], device=env.device) \
+        if env.n_envs <= 4096 else None
+    collided = env.state_i[nat.I_COLLIDED].to(torch.float64)
+    out[:, 0].index_add_(0, cols, ret)
+    out[:, 1].index_add_(0, cols, collided)
+    if n_path is not None:
+        out[:, 2].index_add_(0, cols, (target > n_path - 1).to(torch.float64))
+    out[:, 3].index_add_(0, cols, torch.ones_like(ret))
+    return allreduce_sum_(out) if reduce else out

@@ -247,7 +247,8 @@ class VecPlanEnv(object):
         self.state_i = torch.zeros((L.n_irows, n), dtype=torch.int32, device=dev)
         self.init_f = torch.zeros_like(self.state_f)
         self.init_i = torch.zeros_like(self.state_i)
-        self._cand = torch.zeros((7, n), dtype=torch.float64, device=dev)
+        self._cand = torch.zeros((9, n), dtype=torch.float64, device=dev)
+        self._cand_i = torch.zeros((7, n), dtype=torch.int32, device=dev)
         self._status = torch.zeros(nat.STATUS_WORDS, dtype=torch.int32, device=dev)
         self._stats = torch.zeros(nat.STATS_WORDS, dtype=torch.float64, device=dev)
         self.reward = torch.zeros(n, dtype=torch.float64, device=dev)
@@ -267,13 +268,15 @@ class VecPlanEnv(object):
         b.n_maps, b.n_paths = self._n_maps, len(self._paths_host)
         b.state_f, b.state_i = self.state_f.data_ptr(), self.state_i.data_ptr()
         b.init_f, b.init_i = self.init_f.data_ptr(), self.init_i.data_ptr()
-        b.cand = self._cand.data_ptr()
+        b.cand, b.cand_i = self._cand.data_ptr(), self._cand_i.data_ptr()
         b.map_id, b.path_id = self.map_id.data_ptr(), self.path_id.data_ptr()
         b.maps, b.paths = self.map_descs.data_ptr(), self.path_descs.data_ptr()
         b.map_arena, b.tile_arena, b.path_arena = self.map_arena.data_ptr(), self.tile_arena.data_ptr(), self.path_arena.data_ptr()
         d = self._lut_dev
         b.lut.edges, b.lut.verts, b.lut.header = d['edges'].data_ptr(), d['verts'].data_ptr(), d['header'].data_ptr()
         b.lut.rows, b.lut.fp_pix = d['rows'].data_ptr(), d['fp_pix'].data_ptr()
+        b.lut.bucket_first, b.lut.n_buckets = d['bucket_first'].data_ptr(), self.lut.n_buckets
+        b.lut.bucket_scale = self.lut.bucket_scale
         b.lut.n_bins, b.lut.n_verts, b.lut.max_rows, b.lut.wpr = self.lut.n_bins, self.lut.n_verts, self.lut.max_rows, self.lut.wpr
         b.status, b.stats = self._status.data_ptr(), self._stats.data_ptr()
         self._batch = b
@@ -321,6 +324,17 @@ class VecPlanEnv(object):
         nat.check(nat.lib().bcg_step(C.byref(self._c_params), C.byref(self._batch), nat.ptr(a),
                                      1 if a.dtype == torch.float64 else 0, self._step_index,
                                      C.byref(self._out), self._stream()))
+        self._step_index += 1
+        return self.observation(), self.reward, self.done, {}
+
+    def step_timed(self, actions, events):
+        """`step` with five torch.cuda.Event (enable_timing=True, already recorded once so that their
+        handles exist) recorded around the four kernels; see bcg_step_events."""
+        a = self._as_actions(actions)
+        handles = (C.c_void_p * 5)(*[C.c_void_p(ev.cuda_event) for ev in events])
+        nat.check(nat.lib().bcg_step_events(C.byref(self._c_params), C.byref(self._batch), nat.ptr(a),
+                                            1 if a.dtype == torch.float64 else 0, self._step_index,
+                                            C.byref(self._out), handles, self._stream()))
         self._step_index += 1
         return self.observation(), self.reward, self.done, {}
 

@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched PlanEnv.step path (BASELINE.json configs[2]).
+
+    python bench.py --gpus N --steps K --warmup W                 # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W  # CPU reference arm (oracle port)
+
+Workload (`config.workload`): AisleTurnEnv, 65 536 envs per GPU, tricycle robot,
+EnvParams(control_delay=2, pose_delay=1, state_delay=1), PlanEnv's odometry noise on (Philox4x32-10),
+auto-reset on done, egocentric observation assembled every step.  A "step" is one `VecPlanEnv.step`
+over all envs of the rank.  Envs shard across ranks with no data-path collective ("weak" scaling:
+65 536 envs per GPU); the only collective is one all-reduce of the episode statistics at the end of
+the timed region.  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+DELAYS = (2, 1, 1)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
+    ap.add_argument("--pool", type=int, default=2048, help="distinct random aisle maps generated on the host")
+    ap.add_argument("--no-ego", action="store_true", help="skip the egocentric observation kernel (not the headline)")
+    ap.add_argument("--e2e-steps", type=int, default=50)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--ref-envs", type=int, default=16, help="reference arm: envs advanced per worker per step")
+    return ap.parse_args()
+
+
+def workload_config(args, n_envs):
+    return {
+        "workload": "AisleTurnEnv x %d envs/GPU, tricycle, control/pose/state delay %d/%d/%d, Philox odometry noise, "
+                    "auto-reset, egocentric obs %s" % (n_envs, DELAYS[0], DELAYS[1], DELAYS[2], "off" if args.no_ego else "on"),
+        "envs_per_gpu": n_envs,
+        "map_pool": args.pool,
+        "maps": "random aisle turns (RandomAisleTurnEnv distribution); pool of %d distinct maps generated on the host, "
+                "replicated on device so every env owns a private costmap copy in HBM" % args.pool,
+        "l2": "inputs larger than L2 (per-env costmaps + egocentric output are GBs per step); no explicit flush",
+    }
+
+
+def aisle_params():
+    from bc_gym_planning_env_b200.envs.base.params import EnvParams
+    return EnvParams(control_delay=DELAYS[0], pose_delay=DELAYS[1], state_delay=DELAYS[2])
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    """nvidia-smi clocks and throttle reasons sampled DURING the timed region."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc, self.path = None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 8:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    smax.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(np.max(smax)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the ONLY places bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------------
+def _oracle_envs(n, seed):
+    from oracle import plan_env_oracle as O
+    from bc_gym_planning_env_b200.envs.synth_turn_env import random_aisle_pool
+    costmaps, paths = random_aisle_pool(n, seed, aisle_params())
+    envs = []
+    for i, (cm, path) in enumerate(zip(costmaps, paths)):
+        src = (lambda env_id: (lambda step: O.philox_normal_source(0, env_id, step)))(seed + i)
+        envs.append(O.OraclePlanEnv(cm.get_data(), cm.get_origin(), cm.get_resolution(), path, delays=DELAYS,
+                                    alphas=O.DEFAULT_NOISE, normal_source=src))
+    return envs
+
+
+def _oracle_advance(envs, rng, with_ego, low, high):
+    """One env.step (+ egocentric observation) for each oracle env, auto-reset on done."""
+    from oracle import plan_env_oracle as O
+    n = 0
+    for env in envs:
+        obs, _, done, _ = env.step(rng.uniform(low, high).astype(np.float32))
+        if with_ego:
+            O.ego_costmap(env.costmap, obs["pose"], env.origin, env.resolution)
+            O.goal_n_state(obs["path"], obs["pose"], obs["robot_state"], env.resolution)
+        if done:
+            env.reset()
+        n += 1
+    return n
+
+
+def _action_bounds():
+    s = 60. * np.pi / 180.
+    return np.array([s / 10, -np.pi / 2]), np.array([s / 2, np.pi / 2])
+
+
+def cpu_baseline_sample(seconds, with_ego):
+    """Single-process oracle port on one host core for ~`seconds` s."""
+    envs = _oracle_envs(4, 900)
+    rng = np.random.RandomState(0)
+    low, high = _action_bounds()
+    _oracle_advance(envs, rng, with_ego, low, high)
+    t0 = time.perf_counter()
+    n = 0
+    while time.perf_counter() - t0 < seconds:
+        n += _oracle_advance(envs, rng, with_ego, low, high)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d env-steps of the NumPy oracle port (4 aisle envs, same delays/noise/ego settings) in %.1f s on 1 core; "
+                      "host has %d cores" % (n, dt, os.cpu_count())}
+
+
+def _ref_worker(args):
+    wid, n_envs, n_steps, warmup, with_ego = args
+    envs = _oracle_envs(n_envs, 1000 + 100 * wid)
+    rng = np.random.RandomState(wid)
+    low, high = _action_bounds()
+    for _ in range(warmup):
+        _oracle_advance(envs, rng, with_ego, low, high)
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(n_steps):
+        n += _oracle_advance(envs, rng, with_ego, low, high)
+    return n, t0, time.perf_counter()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (its oracle port; the reference
+    itself is pure Python and cannot travel to the GPU box) on all host cores.  A step = every worker
+    advances `--ref-envs` envs once."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    workers = max(1, os.cpu_count() or 1)
+    with_ego = not args.no_ego
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers) as pool:
+        res = pool.map(_ref_worker, [(w, args.ref_envs, args.steps, args.warmup, with_ego) for w in range(workers)])
+    n = sum(r[0] for r in res)
+    wall = max(r[2] for r in res) - min(r[1] for r in res)
+    value = n / wall
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, args.envs),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
+                         "sample": "%d workers x %d envs x %d steps of the NumPy oracle port" % (workers, args.ref_envs, args.steps)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# the CUDA arm
+# ------------------------------------------------------------------------------------------------
+def build_env(args, rank, device):
+    from bc_gym_planning_env_b200.envs.synth_turn_env import random_aisle_pool
+    from bc_gym_planning_env_b200.vec_env import VecPlanEnv
+    params = aisle_params()
+    costmaps, paths = random_aisle_pool(args.pool, 10000 + rank * args.pool, params)
+    env = VecPlanEnv(costmaps, paths, params, n_envs=args.envs, seed=1234, auto_reset=True, device=device,
+                     env_id_base=rank * args.envs, private_map_copies=True, with_ego=not args.no_ego)
+    return env
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from bc_gym_planning_env_b200 import _native as nat
+    from bc_gym_planning_env_b200.parallel import allreduce_episode_stats
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    nat.require_cuda()
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    env = build_env(args, rank, device)
+    n = env.n_envs
+    low, high = env.action_bounds()
+    gen = torch.Generator(device=device)
+    gen.manual_seed(4321 + rank)
+    n_sets = 8
+    lo_t, hi_t = torch.from_numpy(low).to(device), torch.from_numpy(high).to(device)
+    actions = [(lo_t + (hi_t - lo_t) * torch.rand((n, 2), generator=gen, device=device)).contiguous() for _ in range(n_sets)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(args.warmup):
+        env.step(actions[w % n_sets])
+    env.episode_stats(reset=True)
+    barrier()
+
+    # ---- timed region: K steps, inputs resident in HBM ------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    for evs in ev:
+        for e in evs:
+            e.record()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record()
+    for k in range(args.steps):
+        env.step_timed(actions[k % n_sets], ev[k])
+    stats = allreduce_episode_stats(env)      # the path's only collective
+    t_end.record()
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = t_start.elapsed_time(t_end)
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    env.check_status()
+    value = n * world * args.steps / (elapsed_ms * 1e-3)
+    kin_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    cr_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    commit_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in ev]))
+    ego_ms = float(np.mean([e[3].elapsed_time(e[4]) for e in ev]))
+
+    # ---- algorithmic bytes -----------------------------------------------------------
+    cand_pose = env._cand[:3].t().contiguous()
+    _, pixels = env.pose_collides(cand_pose, count_pixels=True)
+    coll_bytes = float(pixels.sum().item())                       # 1 B per in-map footprint pixel (uint8 costmap)
+    n_path = torch.tensor([len(env.full_path(e)) for e in range(min(n, 4096))], dtype=torch.float64)
+    remaining = float(n_path.mean().item()) - float(env.state_i[nat.I_TARGET].double().mean().item())
+    scan_bytes = 24.0 * max(remaining, 0.0) * n                  # (N - target_idx) x 24 B per env
+    cp = env._c_params
+    ego_bytes = 2.0 * cp.ego_w * cp.ego_h * n                     # gather read + image write per env
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+
+    def roof(kernel, alg_bytes, ms, note):
+        ach = alg_bytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        return {"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms, "peak_source": peak_src,
+                "note": note}
+
+    roof_commit = roof("collide_reward_kernel", coll_bytes + scan_bytes, cr_ms,
+                       "algorithmic bytes (SURVEY 8d) = in-map footprint pixels x 1 B (uint8 definition; the kernel reads "
+                       "the derived 1-bit lethal tile plane) + remaining path points x 24 B (the kernel skips path chunks "
+                       "farther than the reach radius); collision-only share: %.1f MB" % (coll_bytes / 1e6))
+    roof_ego = roof("ego_kernel", ego_bytes, ego_ms, "algorithmic bytes = 2 x ego_w x ego_h per env (gather + write)")
+    dominant = roof_ego if (not args.no_ego and ego_ms >= cr_ms) else roof_commit
+
+    # ---- stand-alone collision kernels, cold L2 (flush between launches) ----------------------------
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.int32, device=device)
+    rows = cand_pose.t().contiguous()
+
+    def time_kernel(fn, reps=5):
+        ms = []
+        for _ in range(reps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+        return float(np.median(ms))
+
+    import ctypes as C
+    flags = torch.empty(n, dtype=torch.uint8, device=device)
+    s = env._stream()
+    tiles_ms = time_kernel(lambda: nat.check(nat.lib().bcg_collision(C.byref(env._c_params), C.byref(env._batch), nat.ptr(rows), nat.ptr(flags), None, s)))
+    u8_ms = time_kernel(lambda: nat.check(nat.lib().bcg_collision_u8(C.byref(env._c_params), C.byref(env._batch), nat.ptr(rows), nat.ptr(flags), s)))
+    del flush
+
+    # ---- e2e: host actions in, host results out, every step -----------------------------------------
+    h_actions = [a.cpu().pin_memory() for a in actions]
+    d_actions = torch.empty((n, 2), dtype=torch.float32, device=device)
+    h_reward = torch.empty(n, dtype=torch.float64).pin_memory()
+    h_done = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_obs = torch.empty((n, 12), dtype=torch.float32).pin_memory()
+    h2d = h_actions[0].numel() * 4
+    d2h = h_reward.numel() * 8 + h_done.numel() + h_obs.numel() * 4
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.e2e_steps):
+        d_actions.copy_(h_actions[k % n_sets], non_blocking=True)
+        env.step(d_actions)
+        h_reward.copy_(env.reward, non_blocking=True)
+        h_done.copy_(env._done_u8, non_blocking=True)
+        h_obs.copy_(env.obs_vec, non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the caller needs the result before acting again
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = n * world * args.e2e_steps / (float(t.item()) * 1e-3)
+
+    if rank == 0:
+        cpu = cpu_baseline_sample(args.cpu_seconds, not args.no_ego) if args.gpus == 1 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, n),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "pinned-host actions in; reward f64, done u8 and the 12-float compact observation out; "
+                            "egocentric images stay in HBM for a GPU-resident policy"},
+            "gpu_launches": args.steps * (3 if args.no_ego else 4) * world,
+            "roofline": dominant,
+            "roofline_collision": roof_commit,
+            "roofline_ego": None if args.no_ego else roof_ego,
+            "kernels_ms": {"kin_kernel": kin_ms, "collide_reward_kernel": cr_ms, "commit_kernel": commit_ms, "ego_kernel": ego_ms,
+                           "collision_tiles_cold_l2": tiles_ms, "collision_u8_cold_l2": u8_ms},
+            "collision_standalone": {
+                "tiles": roof("collision_kernel (lethal tile plane), cold L2", coll_bytes, tiles_ms, "uint8-definition bytes"),
+                "u8": roof("collision_kernel (uint8 rows), cold L2", coll_bytes, u8_ms, "uint8-definition bytes"),
+            },
+            "episode_stats": {k: float(v) for k, v in zip(nat.STAT_NAMES, stats.tolist())},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -128,7 +128,10 @@ typedef struct BcgFootprintLut {
   const int16_t* header;  /* device [n_bins][4] = xmin, ymin, n_rows, width (mask bounding box)     */
   const uint64_t* rows;   /* device [n_bins][max_rows][wpr] bit i of word j <-> column xmin+64j+i   */
   const double* fp_pix;   /* device [2 * n_verts] footprint / resolution (fx0,fy0,...)             */
+  const int32_t* bucket_first; /* device [n_buckets]: bin containing the left end of uniform bucket k  */
+  double bucket_scale;    /* n_buckets / (2 pi)                                                     */
   int32_t n_bins, n_verts, max_rows, wpr;
+  int32_t n_buckets, reserved;
 } BcgFootprintLut;
 
 /* everything a step touches; all pointers are device pointers */
@@ -141,7 +144,10 @@ typedef struct BcgBatch {
   int32_t* state_i;
   double* init_f;  /* the state reset() restores (env.py:247,302) */
   int32_t* init_i;
-  double* cand;    /* scratch [7][n_envs]: robot state proposed by the kinematic kernel */
+  double* cand;    /* scratch [9][n_envs]: robot state proposed by the kinematic kernel (7 rows), then
+                      this step's reward and new min_dist from the collide/reward kernel            */
+  int32_t* cand_i; /* scratch [7][n_envs]: pixel, angle bin and mask box of the proposed pose, new
+                      target_idx, verdict flags                                                     */
   const int32_t* map_id;  /* [n_envs] index into maps  */
   const int32_t* path_id; /* [n_envs] index into paths */
   const BcgMapDesc* maps;
@@ -196,12 +202,18 @@ int bcg_reset_where(const BcgBatch* b, const uint8_t* mask, void* stream);
 /* -- the hot path -------------------------------------------------------------------------------- */
 /* PlanEnv.step (env.py:334-361) for all envs.  actions: device [n][2] (wheel_v, wheel_angle) or
  * (v, w) for diff-drive; action_is_f64 selects fp64 vs fp32 elements.  Launches, in order:
- * kinematics (thread/env), collision+commit+reward (warp/env), egocentric observation (CTA/env,
- * only if out->ego_image or out->goal_n_state is set).  step_index is the caller's global step
+ * kinematics (thread/env), collision+reward (warp/env), commit (thread/env), egocentric observation
+ * (CTA/env, only if out->ego_image or out->goal_n_state is set).  step_index is the caller's global step
  * counter: odometry noise is Philox4x32-10 keyed by p->seed at counter (env id, step_index, draw),
  * replacing the reference's global np.random (differential_drive.py:50). */
 int bcg_step(const BcgParams* p, const BcgBatch* b, const void* actions, int32_t action_is_f64,
              uint64_t step_index, const BcgStepOut* out, void* stream);
+
+/* bcg_step with per-kernel timing hooks: events[0..4] are caller-created cudaEvent_t handles (timing
+ * enabled) recorded on `stream` before the kinematic kernel and after each of the kinematic,
+ * collide/reward, commit and egocentric kernels.  events == NULL behaves exactly like bcg_step. */
+int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, int32_t action_is_f64,
+                    uint64_t step_index, const BcgStepOut* out, void* const* events, void* stream);
 
 /* the pieces, individually addressable (used by tests, ncu and the hook seam) */
 /* robot.step (tricycle_model.py:478-538 / differential_drive.py:236-265) into b->cand */
