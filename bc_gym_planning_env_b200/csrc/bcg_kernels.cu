@@ -6,6 +6,8 @@
 //                                       chunk-culled reached-index scan, reward, done, auto-reset
 //   ego_kernel      1 CTA    / env   -- cv2.warpAffine(INTER_NEAREST)-exact egocentric gather
 // No tensor cores: nothing here is a dense contraction.
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -499,33 +501,86 @@ __device__ __forceinline__ void quad_band_extent(const double qx[4], const doubl
   }
 }
 
+// ---- TMA / mbarrier primitives (sm_90+ PTX; SASS: UTMALDG, SYNCS) ------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "BCG_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra BCG_DONE;\n"
+      "bra BCG_WAIT;\n"
+      "BCG_DONE:\n"
+      "}\n" ::"r"(mbar),
+      "r"(parity)
+      : "memory");
+}
+
+// one 2-D box of a uint8 costmap -> shared memory; out-of-map elements arrive as 0
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int x, int y, uint32_t mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(tmap), "r"(x), "r"(y), "r"(mbar)
+      : "memory");
+}
+
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
 // EgocentricCostmap.observation (envs/egocentric.py:125-160): extract_egocentric_costmap
 // (utilities/costmap_utils.py:25-75) = cv2.getRotationMatrix2D composed in float32 with the crop
 // shift, then cv2.warpAffine(INTER_NEAREST, borderValue=0): fp64 inverse and 10-bit fixed-point source
 // coordinates X = (rint(A11 u 2^10) + rint((A12 v + b1) 2^10) + 512) >> 10.
 //
-// One CTA per env, crops up to 128 px wide.  The source pixels of the crop lie in a rotated rectangle.
-// Per source row, the span of that rectangle (grown by the 0.501 px the fixed-point rounding can move a
-// sample) is staged into shared memory with coalesced 4-byte loads, zero outside the map (= borderValue);
-// the rotated gather then runs out of shared memory with no bounds checks: 7 instructions per pixel.
-// The tile pitch is 4 * odd bytes so a 90-degree gather walks distinct banks.
-__global__ void __launch_bounds__(BCG_EGO_THREADS, 5) ego_kernel(const BcgParams p, const BcgBatch b,
-                                                              uint8_t* __restrict__ image,
-                                                              float* __restrict__ goal_n_state,
-                                                              const int tile_capacity) {
-  extern __shared__ __align__(16) uint8_t tile[];
+// One CTA per env.  The source pixels of the crop lie in a rotated rectangle whose bounding box is
+// staged into shared memory, zero outside the map (= borderValue); the rotated gather then runs out of
+// shared memory with no bounds checks.  Two ways to stage:
+//   * TMA (b.map_tmaps set): one thread issues ceil(rows / box_h) cp.async.bulk.tensor.2d box loads on an
+//     mbarrier; the copy engine does the address generation and the out-of-map zero fill;
+//   * plain loads: per source row only the span of the rotated rectangle (grown by the 0.501 px the
+//     fixed-point rounding can move a sample) is loaded with coalesced 4-byte words.
+// Tile pitches: 208 B for TMA boxes, 4 * odd otherwise -- both measured at < 2 shared-memory wavefronts
+// per gather averaged over crop angles.
+__global__ void __launch_bounds__(BCG_EGO_THREADS, 4) ego_kernel(const BcgParams p, const BcgBatch b,
+                                                                 uint8_t* __restrict__ image,
+                                                                 float* __restrict__ goal_n_state,
+                                                                 const int tile_capacity) {
+  extern __shared__ __align__(128) uint8_t tile_raw[];
+  // TMA destinations must be 128-byte aligned; the launch reserves the slack
+  uint8_t* const tile = tile_raw + ((128u - (smem_u32(tile_raw) & 127u)) & 127u);
   __shared__ int adx[BCG_EGO_MAX], ady[BCG_EGO_MAX], bdx[BCG_EGO_MAX], bdy[BCG_EGO_MAX];
   __shared__ short2 span[BCG_EGO_MAX_TILE_ROWS];
   __shared__ EgoAffine aff_s;
   __shared__ int box[4];
+  __shared__ __align__(8) uint64_t mbar_s;
   const int e = blockIdx.x;
   const int64_t N = b.n_envs;
   const double* sf = b.state_f + e;
-  const BcgMapDesc m = b.maps[b.map_id[e]];
+  const int map_id = b.map_id[e];
+  const BcgMapDesc m = b.maps[map_id];
   const double px = sf[(BCG_F_DPOSE + 0) * N], py = sf[(BCG_F_DPOSE + 1) * N], pth = sf[(BCG_F_DPOSE + 2) * N];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const uint32_t mbar = smem_u32(&mbar_s);
 
-  if (threadIdx.x == 0) aff_s = ego_affine(p, m, px, py, pth);
+  if (threadIdx.x == 0) {
+    aff_s = ego_affine(p, m, px, py, pth);
+    if (b.map_tmaps) mbar_init(mbar, 1);
+  }
   __syncthreads();
   const EgoAffine A = aff_s;
   for (int t = threadIdx.x; t < p.ego_w; t += blockDim.x) {
@@ -559,71 +614,104 @@ __global__ void __launch_bounds__(BCG_EGO_THREADS, 5) ego_kernel(const BcgParams
     }
     if (lane == 0) {
       const long long lim = 1ll << 40;   // poses astronomically far from the map: keep the arithmetic sane
-      box[0] = (int)(min(max(((long long)ax0 + bx0) >> 10, -lim), lim) & ~3ll);   // left edge on a 4-byte word
+      box[0] = (int)min(max(((long long)ax0 + bx0) >> 10, -lim), lim);
       box[1] = (int)min(max(((long long)ax1 + bx1) >> 10, -lim), lim);
       box[2] = (int)min(max(((long long)ay0 + by0) >> 10, -lim), lim);
       box[3] = (int)min(max(((long long)ay1 + by1) >> 10, -lim), lim);
     }
   }
   __syncthreads();
-  const int X0 = box[0], Y0 = box[2];
-  const int bw = box[1] - X0 + 1, bh = box[3] - Y0 + 1;
-  const int pitch_w = ((bw + 3) >> 2) | 1;          // words per tile row, odd
-  const int pitch_b = pitch_w * 4;
+  const int Y0 = box[2];
+  const int bh = box[3] - Y0 + 1;
+  const bool sane = p.ego_w <= 128 && box[1] >= box[0] && bh > 0 && abs(box[0]) < (1 << 20) && abs(box[1]) < (1 << 20) &&
+                    abs(Y0) < (1 << 20) && abs(box[3]) < (1 << 20);
   const uint8_t* src = b.map_arena + m.data_off;
   const int npx = p.ego_w * p.ego_h;
   uint8_t* dst = image + (int64_t)e * npx;
-  const bool staged = p.ego_w <= 128 && bh <= BCG_EGO_MAX_TILE_ROWS && bw > 0 && bh > 0 &&
-                      (long long)pitch_b * bh <= tile_capacity &&
-                      abs(X0) < (1 << 20) && abs(Y0) < (1 << 20);
+
+  int X0 = box[0], pitch_b = 0;
+  bool staged = false;
+  if (sane && b.map_tmaps) {
+    // ---- TMA staging ------------------------------------------------------------------------------
+    // the innermost start coordinate of a box must land on a 16-byte boundary (misaligned starts raise
+    // an illegal-instruction fault on sm_100a), so the window's left edge is floored to 16 pixels
+    const int X0a = box[0] & ~15;
+    const int bw = box[1] - X0a + 1;
+    const int nops = (bh + b.tmap_box_h - 1) / b.tmap_box_h;
+    const int box_bytes = b.tmap_box_w * b.tmap_box_h;
+    if (bw <= b.tmap_box_w && nops * box_bytes <= tile_capacity) {
+      staged = true;
+      X0 = X0a;
+      pitch_b = b.tmap_box_w;
+      if (threadIdx.x == 0) {
+        const uint8_t* tmap = reinterpret_cast<const uint8_t*>(b.map_tmaps) + (int64_t)map_id * 128;
+        mbar_expect_tx(mbar, (uint32_t)(nops * box_bytes));
+        const uint32_t t0 = smem_u32(tile);
+        for (int k = 0; k < nops; ++k) tma_load_2d(t0 + k * box_bytes, tmap, X0, Y0 + k * b.tmap_box_h, mbar);
+      }
+      mbar_wait(mbar, 0);
+    }
+  }
+  if (sane && !staged) {
+    // ---- plain-load staging: per-row span of the rotated crop rectangle ------------------------------------
+    X0 &= ~3;                                        // left edge on a 4-byte word
+    const int bw = box[1] - X0 + 1;
+    const int pitch_w = ((bw + 3) >> 2) | 1;          // words per tile row, odd
+    if (bh <= BCG_EGO_MAX_TILE_ROWS && (long long)pitch_w * 4 * bh <= tile_capacity) {
+      staged = true;
+      pitch_b = pitch_w * 4;
+      const double uw = (double)(p.ego_w - 1), vh = (double)(p.ego_h - 1);
+      const double qx[4] = {A.b1, A.a11 * uw + A.b1, A.a11 * uw + A.a12 * vh + A.b1, A.a12 * vh + A.b1};
+      const double qy[4] = {A.b2, A.a21 * uw + A.b2, A.a21 * uw + A.a22 * vh + A.b2, A.a22 * vh + A.b2};
+      for (int y = threadIdx.x; y < bh; y += blockDim.x) {
+        double xmin, xmax;
+        quad_band_extent(qx, qy, (double)(Y0 + y) - 0.51, (double)(Y0 + y) + 0.51, xmin, xmax);
+        int xs = 1, xe = 0;
+        if (xmin <= xmax) {
+          xs = max((int)floor(xmin - 0.51) - X0, 0);
+          xe = min((int)ceil(xmax + 0.51) - X0, bw - 1);
+        }
+        span[y] = make_short2((short)xs, (short)xe);
+      }
+      __syncthreads();
+      uint32_t* tw = reinterpret_cast<uint32_t*>(tile);
+      for (int y = warp; y < bh; y += nwarp) {
+        const short2 sp = span[y];
+        if (sp.x > sp.y) continue;
+        const int Ys = Y0 + y;
+        const bool row_in = Ys >= 0 && Ys < m.height;
+        // X0 is a multiple of 4 and the row pitch of 32: word loads are aligned and never straddle the map edge
+        const uint32_t* srow = reinterpret_cast<const uint32_t*>(src + (int64_t)(row_in ? Ys : 0) * m.pitch);
+        for (int xw = (sp.x >> 2) + lane; xw <= (sp.y >> 2); xw += 32) {
+          const int Xs = X0 + (xw << 2);
+          uint32_t word = 0u;
+          if (row_in && Xs >= 0 && Xs < m.pitch) word = __ldg(srow + (Xs >> 2));
+          tw[y * pitch_w + xw] = word;
+        }
+      }
+      __syncthreads();
+    }
+  }
   if (staged) {
-    // per-row span of the rotated crop rectangle, grown by the rounding slack
-    const double uw = (double)(p.ego_w - 1), vh = (double)(p.ego_h - 1);
-    const double qx[4] = {A.b1, A.a11 * uw + A.b1, A.a11 * uw + A.a12 * vh + A.b1, A.a12 * vh + A.b1};
-    const double qy[4] = {A.b2, A.a21 * uw + A.b2, A.a21 * uw + A.a22 * vh + A.b2, A.a22 * vh + A.b2};
-    for (int y = threadIdx.x; y < bh; y += blockDim.x) {
-      double xmin, xmax;
-      quad_band_extent(qx, qy, (double)(Y0 + y) - 0.51, (double)(Y0 + y) + 0.51, xmin, xmax);
-      int xs = 1, xe = 0;
-      if (xmin <= xmax) {
-        xs = max((int)floor(xmin - 0.51) - X0, 0);
-        xe = min((int)ceil(xmax + 0.51) - X0, bw - 1);
-      }
-      span[y] = make_short2((short)xs, (short)xe);
-    }
-    __syncthreads();
-    uint32_t* tw = reinterpret_cast<uint32_t*>(tile);
-    for (int y = warp; y < bh; y += nwarp) {
-      const short2 sp = span[y];
-      if (sp.x > sp.y) continue;
-      const int Ys = Y0 + y;
-      const bool row_in = Ys >= 0 && Ys < m.height;
-      // X0 is a multiple of 4 and the row pitch of 32, so word loads are aligned and never straddle the map edge
-      const uint32_t* srow = reinterpret_cast<const uint32_t*>(src + (int64_t)(row_in ? Ys : 0) * m.pitch);
-      for (int xw = (sp.x >> 2) + lane; xw <= (sp.y >> 2); xw += 32) {
-        const int Xs = X0 + (xw << 2);
-        uint32_t word = 0u;
-        if (row_in && Xs >= 0 && Xs < m.pitch) word = __ldg(srow + (Xs >> 2));
-        tw[y * pitch_w + xw] = word;
-      }
-    }
-    __syncthreads();
-    // gather: warp w takes crop rows w, w+8, ...; lane l takes columns l, l+32, l+64, l+96
+    // ---- gather: warp w takes crop rows w, w+8, ...; lane l takes columns l, l+32, l+64, l+96 -----------
     int ax[4], ay[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int u = lane + 32 * k;
-      ax[k] = (u < p.ego_w) ? adx[u] : adx[0];
-      ay[k] = (u < p.ego_w) ? ady[u] : ady[0];
+      const int u = min(lane + 32 * k, p.ego_w - 1);
+      ax[k] = adx[u] - (X0 << 10);
+      ay[k] = ady[u] - (Y0 << 10);
     }
-    for (int v = warp; v < p.ego_h; v += nwarp) {
-      const int bx = bdx[v] - (X0 << 10), by = bdy[v] - (Y0 << 10);
-      uint8_t* drow = dst + v * p.ego_w + lane;
+    const uint32_t tbase = smem_u32(tile);
+    const int n_full = p.ego_w >> 5;                 // column groups in which every lane is live
+    uint8_t* drow = dst + (int64_t)warp * p.ego_w + lane;
+    const int row_step = nwarp * p.ego_w;
+    for (int v = warp; v < p.ego_h; v += nwarp, drow += row_step) {
+      const int bx = bdx[v], by = bdy[v];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int Xr = (ax[k] + bx) >> 10, Yr = (ay[k] + by) >> 10;
-        const uint8_t val = tile[Yr * pitch_b + Xr];
-        if (lane + 32 * k < p.ego_w) drow[32 * k] = val;
+        const uint32_t val = lds_u8(tbase + Yr * pitch_b + Xr);
+        if (k < n_full || lane + 32 * k < p.ego_w) drow[32 * k] = (uint8_t)val;
       }
     }
   } else if (image) {
@@ -747,6 +835,37 @@ int bcg_build_lethal_tiles(const BcgBatch* b, int32_t first, int32_t count, void
   return BCG_OK;
 }
 
+int bcg_encode_map_tensor_maps(const BcgMapDesc* maps_host, int32_t n_maps, const void* map_arena_dev, int32_t box_w,
+                               int32_t box_h, void* out_host) {
+  BCG_REQUIRE(maps_host && map_arena_dev && out_host && n_maps >= 0, "null argument");
+  BCG_REQUIRE(box_w > 0 && box_w <= 256 && box_w % 16 == 0 && box_h > 0 && box_h <= 256, "bad TMA box");
+  static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    BCG_CHECK_CUDA(cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(BCG_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  }
+  CUtensorMap* out = reinterpret_cast<CUtensorMap*>(out_host);
+  static_assert(sizeof(CUtensorMap) == 128, "tensor maps are 128 bytes");
+  for (int32_t k = 0; k < n_maps; ++k) {
+    const BcgMapDesc& m = maps_host[k];
+    const cuuint64_t dims[2] = {(cuuint64_t)m.width, (cuuint64_t)m.height};
+    const cuuint64_t strides[1] = {(cuuint64_t)m.pitch};
+    const cuuint32_t boxd[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+    const cuuint32_t estr[2] = {1, 1};
+    alignas(64) CUtensorMap tm;
+    const CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                              const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(map_arena_dev)) + m.data_off, dims,
+                              strides, boxd, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(BCG_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    memcpy(out + k, &tm, sizeof(tm));
+  }
+  return BCG_OK;
+}
+
 int bcg_init_state(const BcgParams* p, const BcgBatch* b, void* stream) {
   if (int rc = check_batch(p, b)) return rc;
   init_kernel<<<blocks_for((int64_t)b->n_envs * 32, 256), 256, 0, (cudaStream_t)stream>>>(*p, *b, make_layout(*p));
@@ -777,9 +896,15 @@ static int launch_ego(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image,
   if (ego_image) {
     // bounding box of the rotated crop: at most ceil(hypot(w, h)) + 2 rows of (that + 7) bytes, pitch 4 * odd
     const int side = (int)ceil(sqrt((double)p->ego_w * p->ego_w + (double)p->ego_h * p->ego_h)) + 2;
-    int cap = side * (((side + 3) / 4) | 1) * 4;
-    if (cap > 40 * 1024) cap = 40 * 1024;   // larger crops fall back to the direct global gather per CTA
-    ego_kernel<<<b->n_envs, BCG_EGO_THREADS, cap, s>>>(*p, *b, ego_image, goal_n_state, cap);
+    int cap = (side + 1) * ((((side + 3) + 3) / 4) | 1) * 4;
+    if (b->map_tmaps) {
+      BCG_REQUIRE(b->tmap_box_w > 0 && b->tmap_box_h > 0, "tensor-map box not set");
+      const int tma_cap = ((side + b->tmap_box_h - 1) / b->tmap_box_h) * b->tmap_box_h * b->tmap_box_w;
+      if (tma_cap > cap) cap = tma_cap;
+    }
+    cap = (cap + 127) / 128 * 128;
+    if (cap > 42 * 1024) cap = 42 * 1024;   // larger crops fall back to the direct global gather per CTA
+    ego_kernel<<<b->n_envs, BCG_EGO_THREADS, cap + 128, s>>>(*p, *b, ego_image, goal_n_state, cap);
   } else {
     goal_kernel<<<blocks_for(b->n_envs, 128), 128, 0, s>>>(*p, *b, goal_n_state);
   }

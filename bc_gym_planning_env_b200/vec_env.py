@@ -74,7 +74,7 @@ class VecState(object):
 class VecPlanEnv(object):
     def __init__(self, costmaps, paths, params=None, n_envs=None, map_ids=None, path_ids=None,
                  noise_parameters=DEFAULT_NOISE, seed=0, auto_reset=False, device=None, env_id_base=0,
-                 private_map_copies=False, with_ego=False, footprint_scale=1.0):
+                 private_map_copies=False, with_ego=False, footprint_scale=1.0, use_tma=True):
         """
         :param costmaps: pool of CostMap2D (uint8), one resolution
         :param paths: pool of oriented paths, array(n, 3); refined here when params.refine_path
@@ -104,6 +104,7 @@ class VecPlanEnv(object):
         self.robot_kind = nat.ROBOT_TRICYCLE if self.dims.drive_type == TRICYCLE else nat.ROBOT_DIFFDRIVE
         self.auto_reset = bool(auto_reset)
         self.with_ego = bool(with_ego)
+        self.use_tma = bool(use_tma)
         self._step_index = 0
 
         self._c_params = self._make_params(noise_parameters, seed, env_id_base)
@@ -195,6 +196,14 @@ class VecPlanEnv(object):
             pool_words *= copies
         self._map_descs_host = descs
         self.map_arena = map_arena
+        # TMA tensor maps for the egocentric kernel's source-window staging: box 208 x 16 uint8
+        # (208 = measured best dense pitch for the rotated shared-memory gather)
+        self._tmap_box = (208, 16)
+        tm = np.zeros(len(descs) * 128, dtype=np.uint8)
+        nat.check(nat.lib().bcg_encode_map_tensor_maps(descs, len(descs), C.c_void_p(map_arena.data_ptr()),
+                                                       self._tmap_box[0], self._tmap_box[1],
+                                                       C.c_void_p(tm.ctypes.data)))
+        self.map_tmaps = self._to_device(tm)
         self.tile_arena = torch.zeros(max(pool_words, 1), dtype=torch.int32, device=self.device)
         self.map_descs = self._to_device(np.frombuffer(bytes(descs), dtype=np.uint8).copy())
         self.map_id = self._to_device(ids.astype(np.int32))
@@ -279,6 +288,8 @@ class VecPlanEnv(object):
         b.lut.bucket_scale = self.lut.bucket_scale
         b.lut.n_bins, b.lut.n_verts, b.lut.max_rows, b.lut.wpr = self.lut.n_bins, self.lut.n_verts, self.lut.max_rows, self.lut.wpr
         b.status, b.stats = self._status.data_ptr(), self._stats.data_ptr()
+        if self.use_tma:
+            b.map_tmaps, b.tmap_box_w, b.tmap_box_h = self.map_tmaps.data_ptr(), self._tmap_box[0], self._tmap_box[1]
         self._batch = b
         out = nat.BcgStepOut()
         out.reward, out.done, out.hit = self.reward.data_ptr(), self._done_u8.data_ptr(), self._hit_u8.data_ptr()
