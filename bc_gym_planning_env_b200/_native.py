@@ -61,7 +61,8 @@ class BcgBatch(C.Structure):
         ("maps", C.c_void_p), ("paths", C.c_void_p),
         ("map_arena", C.c_void_p), ("tile_arena", C.c_void_p), ("path_arena", C.c_void_p),
         ("lut", BcgFootprintLut),
-        ("map_tmaps", C.c_void_p), ("tmap_box_w", C.c_int32), ("tmap_box_h", C.c_int32),
+        ("map_tmaps", C.c_void_p), ("tmap_n_widths", C.c_int32), ("tmap_box_h", C.c_int32),
+        ("tmap_box_w", C.c_int32 * 4),
         ("status", C.c_void_p), ("stats", C.c_void_p),
     ]
 
@@ -99,7 +100,8 @@ SYMBOLS = {
     "bcg_device_count": (C.c_int, []),
     "bcg_state_layout": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgStateLayout)]),
     "bcg_build_lethal_tiles": (C.c_int, [C.POINTER(BcgBatch), C.c_int32, C.c_int32, _P]),
-    "bcg_encode_map_tensor_maps": (C.c_int, [C.POINTER(BcgMapDesc), C.c_int32, _P, C.c_int32, C.c_int32, _P]),
+    "bcg_encode_map_tensor_maps": (C.c_int, [C.POINTER(BcgMapDesc), C.c_int32, _P, C.POINTER(C.c_int32), C.c_int32,
+                                             C.c_int32, _P]),
     "bcg_init_state": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgBatch), _P]),
     "bcg_reset_where": (C.c_int, [C.POINTER(BcgBatch), _P, _P]),
     "bcg_step": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgBatch), _P, C.c_int32, C.c_uint64,

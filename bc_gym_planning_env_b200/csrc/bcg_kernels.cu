@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(BCG_EGO_THREADS, 4) ego_kernel(const BcgParams
   __shared__ int adx[BCG_EGO_MAX], ady[BCG_EGO_MAX], bdx[BCG_EGO_MAX], bdy[BCG_EGO_MAX];
   __shared__ short2 span[BCG_EGO_MAX_TILE_ROWS];
   __shared__ EgoAffine aff_s;
-  __shared__ int box[4];
+  __shared__ int box[6];   // source window x0, x1, y0, y1 (not clipped to the map); TMA width class; mode
   __shared__ __align__(8) uint64_t mbar_s;
   const int e = blockIdx.x;
   const int64_t N = b.n_envs;
@@ -576,12 +576,51 @@ __global__ void __launch_bounds__(BCG_EGO_THREADS, 4) ego_kernel(const BcgParams
   const double px = sf[(BCG_F_DPOSE + 0) * N], py = sf[(BCG_F_DPOSE + 1) * N], pth = sf[(BCG_F_DPOSE + 2) * N];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const uint32_t mbar = smem_u32(&mbar_s);
+  enum { MODE_DIRECT = 0, MODE_TMA = 1, MODE_SPANS = 2 };
 
   if (threadIdx.x == 0) {
-    aff_s = ego_affine(p, m, px, py, pth);
-    if (b.map_tmaps) mbar_init(mbar, 1);
+    const EgoAffine A0 = ego_affine(p, m, px, py, pth);
+    aff_s = A0;
+    // Source window: every sample is X = floor(x + 0.5 + d), |d| <= 2^-10, of a point x of the rotated crop
+    // rectangle, so the rectangle's corners grown by 0.51 px bound all samples.
+    const double uw = (double)(p.ego_w - 1), vh = (double)(p.ego_h - 1);
+    const double cx[4] = {A0.b1, A0.a11 * uw + A0.b1, A0.a11 * uw + A0.a12 * vh + A0.b1, A0.a12 * vh + A0.b1};
+    const double cy[4] = {A0.b2, A0.a21 * uw + A0.b2, A0.a21 * uw + A0.a22 * vh + A0.b2, A0.a22 * vh + A0.b2};
+    const double lim = 1048576.0;
+    const double xlo = fmin(fmin(cx[0], cx[1]), fmin(cx[2], cx[3])), xhi = fmax(fmax(cx[0], cx[1]), fmax(cx[2], cx[3]));
+    const double ylo = fmin(fmin(cy[0], cy[1]), fmin(cy[2], cy[3])), yhi = fmax(fmax(cy[0], cy[1]), fmax(cy[2], cy[3]));
+    const bool sane = p.ego_w <= 128 && xlo > -lim && xhi < lim && ylo > -lim && yhi < lim;   // false for NaN too
+    int mode = MODE_DIRECT, cls = 0;
+    if (sane) {
+      const int x0 = (int)floor(xlo - 0.51), x1 = (int)ceil(xhi + 0.51);
+      const int y0 = (int)floor(ylo - 0.51), y1 = (int)ceil(yhi + 0.51);
+      box[0] = x0; box[1] = x1; box[2] = y0; box[3] = y1;
+      const int bh = y1 - y0 + 1;
+      mode = MODE_SPANS;
+      if (b.map_tmaps) {
+        // the innermost start coordinate of a box must land on a 16-byte boundary (misaligned starts raise
+        // an illegal-instruction fault on sm_100a), so the window's left edge is floored to 16 pixels
+        const int x0a = x0 & ~15;
+        const int bw = x1 - x0a + 1;
+        while (cls < b.tmap_n_widths && b.tmap_box_w[cls] < bw) ++cls;
+        const int nops = (bh + b.tmap_box_h - 1) / b.tmap_box_h;
+        if (cls < b.tmap_n_widths && nops * b.tmap_box_h * b.tmap_box_w[cls] <= tile_capacity) {
+          mode = MODE_TMA;
+          box[0] = x0a;
+          const int box_bytes = b.tmap_box_w[cls] * b.tmap_box_h;
+          const uint8_t* tmap = reinterpret_cast<const uint8_t*>(b.map_tmaps) + ((int64_t)map_id * b.tmap_n_widths + cls) * 128;
+          mbar_init(mbar, 1);
+          mbar_expect_tx(mbar, (uint32_t)(nops * box_bytes));
+          const uint32_t t0 = smem_u32(tile);
+          for (int k = 0; k < nops; ++k) tma_load_2d(t0 + k * box_bytes, tmap, x0a, y0 + k * b.tmap_box_h, mbar);
+        }
+      }
+    }
+    box[4] = cls;
+    box[5] = mode;
   }
   __syncthreads();
+  // the copy engine is now filling the tile; meanwhile every thread builds the fixed-point tables
   const EgoAffine A = aff_s;
   for (int t = threadIdx.x; t < p.ego_w; t += blockDim.x) {
     adx[t] = cv_round_sat(A.a11 * t * 1024);
@@ -591,74 +630,22 @@ __global__ void __launch_bounds__(BCG_EGO_THREADS, 4) ego_kernel(const BcgParams
     bdx[t] = cv_round_sat((A.a12 * t + A.b1) * 1024) + 512;
     bdy[t] = cv_round_sat((A.a22 * t + A.b2) * 1024) + 512;
   }
-  __syncthreads();
-  // source bounding box (NOT clipped to the map): X(u, v) = (adx[u] + bdx[v]) >> 10 is monotone in each
-  // table entry, so its extremes are at extreme table entries; warp 0 reduces the four tables.
-  if (warp == 0) {
-    int ax0 = 0x7fffffff, ax1 = -0x7fffffff, ay0 = 0x7fffffff, ay1 = -0x7fffffff;
-    int bx0 = 0x7fffffff, bx1 = -0x7fffffff, by0 = 0x7fffffff, by1 = -0x7fffffff;
-    for (int t = lane; t < p.ego_w; t += 32) {
-      ax0 = min(ax0, adx[t]); ax1 = max(ax1, adx[t]);
-      ay0 = min(ay0, ady[t]); ay1 = max(ay1, ady[t]);
-    }
-    for (int t = lane; t < p.ego_h; t += 32) {
-      bx0 = min(bx0, bdx[t]); bx1 = max(bx1, bdx[t]);
-      by0 = min(by0, bdy[t]); by1 = max(by1, bdy[t]);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      ax0 = min(ax0, __shfl_xor_sync(BCG_FULL, ax0, o)); ax1 = max(ax1, __shfl_xor_sync(BCG_FULL, ax1, o));
-      ay0 = min(ay0, __shfl_xor_sync(BCG_FULL, ay0, o)); ay1 = max(ay1, __shfl_xor_sync(BCG_FULL, ay1, o));
-      bx0 = min(bx0, __shfl_xor_sync(BCG_FULL, bx0, o)); bx1 = max(bx1, __shfl_xor_sync(BCG_FULL, bx1, o));
-      by0 = min(by0, __shfl_xor_sync(BCG_FULL, by0, o)); by1 = max(by1, __shfl_xor_sync(BCG_FULL, by1, o));
-    }
-    if (lane == 0) {
-      const long long lim = 1ll << 40;   // poses astronomically far from the map: keep the arithmetic sane
-      box[0] = (int)min(max(((long long)ax0 + bx0) >> 10, -lim), lim);
-      box[1] = (int)min(max(((long long)ax1 + bx1) >> 10, -lim), lim);
-      box[2] = (int)min(max(((long long)ay0 + by0) >> 10, -lim), lim);
-      box[3] = (int)min(max(((long long)ay1 + by1) >> 10, -lim), lim);
-    }
-  }
-  __syncthreads();
+  int mode = box[5];
+  int X0 = box[0];
   const int Y0 = box[2];
   const int bh = box[3] - Y0 + 1;
-  const bool sane = p.ego_w <= 128 && box[1] >= box[0] && bh > 0 && abs(box[0]) < (1 << 20) && abs(box[1]) < (1 << 20) &&
-                    abs(Y0) < (1 << 20) && abs(box[3]) < (1 << 20);
+  int pitch_b = 0;
   const uint8_t* src = b.map_arena + m.data_off;
   const int npx = p.ego_w * p.ego_h;
   uint8_t* dst = image + (int64_t)e * npx;
-
-  int X0 = box[0], pitch_b = 0;
-  bool staged = false;
-  if (sane && b.map_tmaps) {
-    // ---- TMA staging ------------------------------------------------------------------------------
-    // the innermost start coordinate of a box must land on a 16-byte boundary (misaligned starts raise
-    // an illegal-instruction fault on sm_100a), so the window's left edge is floored to 16 pixels
-    const int X0a = box[0] & ~15;
-    const int bw = box[1] - X0a + 1;
-    const int nops = (bh + b.tmap_box_h - 1) / b.tmap_box_h;
-    const int box_bytes = b.tmap_box_w * b.tmap_box_h;
-    if (bw <= b.tmap_box_w && nops * box_bytes <= tile_capacity) {
-      staged = true;
-      X0 = X0a;
-      pitch_b = b.tmap_box_w;
-      if (threadIdx.x == 0) {
-        const uint8_t* tmap = reinterpret_cast<const uint8_t*>(b.map_tmaps) + (int64_t)map_id * 128;
-        mbar_expect_tx(mbar, (uint32_t)(nops * box_bytes));
-        const uint32_t t0 = smem_u32(tile);
-        for (int k = 0; k < nops; ++k) tma_load_2d(t0 + k * box_bytes, tmap, X0, Y0 + k * b.tmap_box_h, mbar);
-      }
-      mbar_wait(mbar, 0);
-    }
-  }
-  if (sane && !staged) {
+  if (mode == MODE_TMA) {
+    pitch_b = b.tmap_box_w[box[4]];
+  } else if (mode == MODE_SPANS) {
     // ---- plain-load staging: per-row span of the rotated crop rectangle ------------------------------------
     X0 &= ~3;                                        // left edge on a 4-byte word
     const int bw = box[1] - X0 + 1;
     const int pitch_w = ((bw + 3) >> 2) | 1;          // words per tile row, odd
     if (bh <= BCG_EGO_MAX_TILE_ROWS && (long long)pitch_w * 4 * bh <= tile_capacity) {
-      staged = true;
       pitch_b = pitch_w * 4;
       const double uw = (double)(p.ego_w - 1), vh = (double)(p.ego_h - 1);
       const double qx[4] = {A.b1, A.a11 * uw + A.b1, A.a11 * uw + A.a12 * vh + A.b1, A.a12 * vh + A.b1};
@@ -689,9 +676,13 @@ __global__ void __launch_bounds__(BCG_EGO_THREADS, 4) ego_kernel(const BcgParams
           tw[y * pitch_w + xw] = word;
         }
       }
-      __syncthreads();
+    } else {
+      mode = MODE_DIRECT;
     }
   }
+  __syncthreads();                       // tables (and the plain-load tile) are complete
+  if (mode == MODE_TMA) mbar_wait(mbar, 0);
+  const bool staged = mode != MODE_DIRECT;
   if (staged) {
     // ---- gather: warp w takes crop rows w, w+8, ...; lane l takes columns l, l+32, l+64, l+96 -----------
     int ax[4], ay[4];
@@ -835,10 +826,13 @@ int bcg_build_lethal_tiles(const BcgBatch* b, int32_t first, int32_t count, void
   return BCG_OK;
 }
 
-int bcg_encode_map_tensor_maps(const BcgMapDesc* maps_host, int32_t n_maps, const void* map_arena_dev, int32_t box_w,
-                               int32_t box_h, void* out_host) {
-  BCG_REQUIRE(maps_host && map_arena_dev && out_host && n_maps >= 0, "null argument");
-  BCG_REQUIRE(box_w > 0 && box_w <= 256 && box_w % 16 == 0 && box_h > 0 && box_h <= 256, "bad TMA box");
+int bcg_encode_map_tensor_maps(const BcgMapDesc* maps_host, int32_t n_maps, const void* map_arena_dev,
+                               const int32_t* box_w, int32_t n_widths, int32_t box_h, void* out_host) {
+  BCG_REQUIRE(maps_host && map_arena_dev && out_host && box_w && n_maps >= 0, "null argument");
+  BCG_REQUIRE(n_widths >= 1 && n_widths <= 4 && box_h > 0 && box_h <= 256, "bad TMA box");
+  for (int j = 0; j < n_widths; ++j)
+    BCG_REQUIRE(box_w[j] > 0 && box_w[j] <= 256 && box_w[j] % 16 == 0 && (j == 0 || box_w[j] > box_w[j - 1]),
+                "TMA box widths must be ascending multiples of 16, at most 256");
   static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -853,15 +847,18 @@ int bcg_encode_map_tensor_maps(const BcgMapDesc* maps_host, int32_t n_maps, cons
     const BcgMapDesc& m = maps_host[k];
     const cuuint64_t dims[2] = {(cuuint64_t)m.width, (cuuint64_t)m.height};
     const cuuint64_t strides[1] = {(cuuint64_t)m.pitch};
-    const cuuint32_t boxd[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
     const cuuint32_t estr[2] = {1, 1};
-    alignas(64) CUtensorMap tm;
-    const CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
-                              const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(map_arena_dev)) + m.data_off, dims,
-                              strides, boxd, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(BCG_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
-    memcpy(out + k, &tm, sizeof(tm));
+    for (int j = 0; j < n_widths; ++j) {
+      const cuuint32_t boxd[2] = {(cuuint32_t)box_w[j], (cuuint32_t)box_h};
+      alignas(64) CUtensorMap tm;
+      const CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                                const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(map_arena_dev)) + m.data_off, dims,
+                                strides, boxd, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS)
+        return fail(BCG_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+      memcpy(out + (int64_t)k * n_widths + j, &tm, sizeof(tm));
+    }
   }
   return BCG_OK;
 }
@@ -898,8 +895,9 @@ static int launch_ego(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image,
     const int side = (int)ceil(sqrt((double)p->ego_w * p->ego_w + (double)p->ego_h * p->ego_h)) + 2;
     int cap = (side + 1) * ((((side + 3) + 3) / 4) | 1) * 4;
     if (b->map_tmaps) {
-      BCG_REQUIRE(b->tmap_box_w > 0 && b->tmap_box_h > 0, "tensor-map box not set");
-      const int tma_cap = ((side + b->tmap_box_h - 1) / b->tmap_box_h) * b->tmap_box_h * b->tmap_box_w;
+      BCG_REQUIRE(b->tmap_n_widths >= 1 && b->tmap_n_widths <= 4 && b->tmap_box_h > 0, "tensor-map boxes not set");
+      const int rows = ((side + 1 + b->tmap_box_h - 1) / b->tmap_box_h) * b->tmap_box_h;
+      const int tma_cap = rows * b->tmap_box_w[b->tmap_n_widths - 1];
       if (tma_cap > cap) cap = tma_cap;
     }
     cap = (cap + 127) / 128 * 128;

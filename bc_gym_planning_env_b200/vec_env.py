@@ -196,12 +196,13 @@ class VecPlanEnv(object):
             pool_words *= copies
         self._map_descs_host = descs
         self.map_arena = map_arena
-        # TMA tensor maps for the egocentric kernel's source-window staging: box 208 x 16 uint8
-        # (208 = measured best dense pitch for the rotated shared-memory gather)
-        self._tmap_box = (208, 16)
-        tm = np.zeros(len(descs) * 128, dtype=np.uint8)
-        nat.check(nat.lib().bcg_encode_map_tensor_maps(descs, len(descs), C.c_void_p(map_arena.data_ptr()),
-                                                       self._tmap_box[0], self._tmap_box[1],
+        # TMA tensor maps for the egocentric kernel's source-window staging: three box-width classes
+        # (dense pitches that keep the rotated shared-memory gather under 2 wavefronts on average) x 8 rows
+        self._tmap_widths, self._tmap_box_h = (144, 176, 208), 8
+        widths = (C.c_int32 * len(self._tmap_widths))(*self._tmap_widths)
+        tm = np.zeros(len(descs) * len(self._tmap_widths) * 128, dtype=np.uint8)
+        nat.check(nat.lib().bcg_encode_map_tensor_maps(descs, len(descs), C.c_void_p(map_arena.data_ptr()), widths,
+                                                       len(self._tmap_widths), self._tmap_box_h,
                                                        C.c_void_p(tm.ctypes.data)))
         self.map_tmaps = self._to_device(tm)
         self.tile_arena = torch.zeros(max(pool_words, 1), dtype=torch.int32, device=self.device)
@@ -289,7 +290,9 @@ class VecPlanEnv(object):
         b.lut.n_bins, b.lut.n_verts, b.lut.max_rows, b.lut.wpr = self.lut.n_bins, self.lut.n_verts, self.lut.max_rows, self.lut.wpr
         b.status, b.stats = self._status.data_ptr(), self._stats.data_ptr()
         if self.use_tma:
-            b.map_tmaps, b.tmap_box_w, b.tmap_box_h = self.map_tmaps.data_ptr(), self._tmap_box[0], self._tmap_box[1]
+            b.map_tmaps, b.tmap_n_widths, b.tmap_box_h = self.map_tmaps.data_ptr(), len(self._tmap_widths), self._tmap_box_h
+            for j, w in enumerate(self._tmap_widths):
+                b.tmap_box_w[j] = w
         self._batch = b
         out = nat.BcgStepOut()
         out.reward, out.done, out.hit = self.reward.data_ptr(), self._done_u8.data_ptr(), self._hit_u8.data_ptr()

@@ -156,9 +156,12 @@ typedef struct BcgBatch {
   const uint32_t* tile_arena;
   const double* path_arena;
   BcgFootprintLut lut;
-  const void* map_tmaps; /* optional: [n_maps] 128-byte TMA tensor maps from bcg_encode_map_tensor_maps; NULL =
-                            the egocentric kernel stages its source window with plain coalesced loads       */
-  int32_t tmap_box_w, tmap_box_h; /* box the tensor maps were encoded with                                  */
+  const void* map_tmaps; /* optional: [n_maps][tmap_n_widths] 128-byte TMA tensor maps from
+                            bcg_encode_map_tensor_maps; NULL = the egocentric kernel stages its source
+                            window with plain coalesced loads                                             */
+  int32_t tmap_n_widths;  /* 1..4 box-width classes, ascending                                           */
+  int32_t tmap_box_h;     /* rows per box                                                                */
+  int32_t tmap_box_w[4];  /* box widths (multiples of 16) the tensor maps were encoded with              */
   uint32_t* status; /* [BCG_STATUS_WORDS] */
   double* stats;    /* [BCG_STATS_WORDS]  */
 } BcgBatch;
@@ -196,12 +199,13 @@ int bcg_state_layout(const BcgParams* p, BcgStateLayout* out);
 /* -- setup (at reset time, not per step) ------------------------------------------------------------ */
 /* derive the lethal bit-plane (cell == 254, costmap_2d.py:21) of maps [first, first+count) */
 int bcg_build_lethal_tiles(const BcgBatch* b, int32_t first, int32_t count, void* stream);
-/* Host-side: encode one CUtensorMap (128 B, cuTensorMapEncodeTiled) per costmap -- uint8 [H][pitch]
- * tensor, box (box_w, box_h), zero fill outside the map (= cv2.warpAffine's borderValue 0,
- * utilities/costmap_utils.py:72) -- into out_host [n_maps * 128 bytes].  The caller uploads the buffer
- * and points BcgBatch.map_tmaps at it.  box_w must be a multiple of 16 and box_w, box_h <= 256. */
+/* Host-side: encode n_widths CUtensorMaps (128 B each, cuTensorMapEncodeTiled) per costmap -- uint8
+ * [H][pitch] tensor, boxes (box_w[j], box_h), zero fill outside the map (= cv2.warpAffine's
+ * borderValue 0, utilities/costmap_utils.py:72) -- into out_host [n_maps][n_widths][128 bytes].  The
+ * caller uploads the buffer and points BcgBatch.map_tmaps at it.  Widths must be ascending multiples
+ * of 16, and widths and box_h <= 256. */
 int bcg_encode_map_tensor_maps(const BcgMapDesc* maps_host, int32_t n_maps, const void* map_arena_dev,
-                               int32_t box_w, int32_t box_h, void* out_host);
+                               const int32_t* box_w, int32_t n_widths, int32_t box_h, void* out_host);
 /* make_initial_state (env.py:179-214) + ContinuousRewardProvider.generate_initial_state
  * (reward.py:261-288) for every env: writes init_f/init_i and copies them into state_f/state_i */
 int bcg_init_state(const BcgParams* p, const BcgBatch* b, void* stream);
