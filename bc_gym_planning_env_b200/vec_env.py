@@ -31,11 +31,17 @@ def _round_up(v, m):
     return (v + m - 1) // m * m
 
 
-def footprint_lut_for(robot_name, resolution, footprint_scale=1.0):
-    key = (robot_name, float(resolution), float(footprint_scale))
+def footprint_lut_for(robot_name, resolution, footprint_scale=1.0, footprint=None):
+    """Angle-bin table of a standard robot (cached) or of an explicit footprint polygon (n, 2)."""
+    if footprint is not None:
+        footprint = np.asarray(footprint, dtype=np.float64)
+        key = ('custom', footprint.tobytes(), float(resolution), float(footprint_scale))
+    else:
+        key = (robot_name, float(resolution), float(footprint_scale))
     if key not in _LUT_CACHE:
-        dims = get_dimensions_example(robot_name)
-        _LUT_CACHE[key] = FootprintLut(dims.footprint() * footprint_scale, resolution)
+        if footprint is None:
+            footprint = get_dimensions_example(robot_name).footprint()
+        _LUT_CACHE[key] = FootprintLut(footprint * footprint_scale, resolution)
     return _LUT_CACHE[key]
 
 
@@ -74,7 +80,7 @@ class VecState(object):
 class VecPlanEnv(object):
     def __init__(self, costmaps, paths, params=None, n_envs=None, map_ids=None, path_ids=None,
                  noise_parameters=DEFAULT_NOISE, seed=0, auto_reset=False, device=None, env_id_base=0,
-                 private_map_copies=False, with_ego=False, footprint_scale=1.0, use_tma=True):
+                 private_map_copies=False, with_ego=False, footprint_scale=1.0, use_tma=True, footprint=None):
         """
         :param costmaps: pool of CostMap2D (uint8), one resolution
         :param paths: pool of oriented paths, array(n, 3); refined here when params.refine_path
@@ -83,6 +89,8 @@ class VecPlanEnv(object):
         :param noise_parameters: dict alpha1..alpha6 or None (noise off); PlanEnv's default is on
         :param private_map_copies: give every env its own copy of its costmap in HBM (pool replicated
             on device) instead of sharing pool entries
+        :param with_ego: assemble the egocentric observation inside every step
+        :param footprint: explicit footprint polygon array(n, 2) in metres (default: the robot's own)
         """
         nat.require_cuda()
         self.params = params if params is not None else EnvParams()
@@ -111,7 +119,7 @@ class VecPlanEnv(object):
         self.layout = nat.state_layout(self._c_params)
         self._upload_maps(costmaps, private_map_copies)
         self._upload_paths(paths)
-        self._upload_lut(footprint_lut_for(self.params.robot_name, self.resolution, footprint_scale))
+        self._upload_lut(footprint_lut_for(self.params.robot_name, self.resolution, footprint_scale, footprint))
         self._alloc_state()
         self._make_batch()
         s = self._stream()
