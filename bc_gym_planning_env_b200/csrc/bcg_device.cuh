@@ -26,8 +26,18 @@ __device__ __forceinline__ double py_mod(double a, double b) {
   return m;
 }
 
-// normalize_angle, utilities/coordinate_transformations.py:28-36
-__device__ __forceinline__ double wrap_angle(double z) { return py_mod(z + BCG_PI, BCG_TWO_PI) - BCG_PI; }
+// normalize_angle, utilities/coordinate_transformations.py:28-36.  For |z + pi| < 4 pi the floor-mod is
+// spelled out: a - 2 pi is exact there (Sterbenz), and a + 2 pi is the very addition NumPy's divmod
+// performs after its (exact) fmod, so the result is bit-identical to py_mod without the fmod loop.
+__device__ __forceinline__ double wrap_angle(double z) {
+  const double a = z + BCG_PI;
+  double m;
+  if (a >= 0.0 && a < BCG_TWO_PI) m = a;
+  else if (a >= BCG_TWO_PI && a < 2 * BCG_TWO_PI) m = a - BCG_TWO_PI;
+  else if (a < 0.0 && a >= -BCG_TWO_PI) m = a + BCG_TWO_PI;
+  else m = py_mod(a, BCG_TWO_PI);
+  return m - BCG_PI;
+}
 
 // one axis of world_to_pixel, utilities/coordinate_transformations.py:185-205 (np.round = half-even)
 __device__ __forceinline__ int world_to_pixel_1d(double w, double origin, double inv_res) {
@@ -298,36 +308,43 @@ __device__ __forceinline__ uint32_t mask_bits32(const uint64_t* row, int wpr, in
   return (uint32_t)lo;
 }
 
-// pose_collides (envs/base/env.py:464-489) on the lethal tile plane.  Warp-cooperative; returns the
+// bits [rel, rel + 32) of a 64-bit row mask (bit b <-> column xmin + b), rel in (-32, 64)
+__device__ __forceinline__ uint32_t mask_window32(uint64_t mk, int rel) {
+  return rel < 0 ? (uint32_t)(mk << (-rel)) : (uint32_t)(mk >> rel);
+}
+
+// pose_collides (envs/base/env.py:464-489) on the lethal tile plane.  Warp-cooperative: a lane owns one
+// footprint row (two passes cover the <= 64 rows), loads the row's mask once and walks the <= 3 tiles
+// the row crosses; 16 consecutive rows of a tile are one coalesced 64-byte read.  Returns the
 // warp-uniform verdict.  If COUNT, *pixels gets the number of in-map footprint pixels.
 template <bool COUNT>
 __device__ __forceinline__ bool collide_tiles(const BcgBatch& b, const BcgMapDesc& m, const FootRef& f, unsigned lane,
                                               int* pixels) {
   const int X0 = f.px + f.xmin, Y0 = f.py + f.ymin;
-  const int X1 = X0 + f.width - 1, Y1 = Y0 + f.nrows - 1;
+  const int X1 = X0 + f.width - 1;
   unsigned hit = 0;
   int cnt = 0;
-  if (!(X1 < 0 || Y1 < 0 || X0 >= m.width || Y0 >= m.height)) {
+  if (!(X1 < 0 || X0 >= m.width)) {
     const int tx0 = max(X0, 0) >> 5, tx1 = min(X1, m.width - 1) >> 5;
-    const int ty0 = max(Y0, 0) >> 4, ty1 = min(Y1, m.height - 1) >> 4;
-    const int ntx = tx1 - tx0 + 1;
-    const int items = ntx * (ty1 - ty0 + 1) * 16;
     const uint32_t* tiles = b.tile_arena + m.tile_off;
-    const uint64_t* rows = b.lut.rows + (int64_t)f.bin * b.lut.max_rows * b.lut.wpr;
-    for (int it = lane; it < items; it += 32) {
-      const int r = it & 15, t = it >> 4;
-      const int tyi = t / ntx;
-      const int ty = ty0 + tyi, tx = tx0 + (t - tyi * ntx);
-      const int Y = (ty << 4) + r;
-      const int dy = Y - Y0;
-      if (dy < 0 || dy >= f.nrows || Y >= m.height) continue;
-      const uint32_t word = __ldg(tiles + ((int64_t)(ty * m.tiles_x + tx) << 4) + r);
-      const uint32_t mbits = mask_bits32(rows + (int64_t)dy * b.lut.wpr, b.lut.wpr, (tx << 5) - X0);
-      hit |= word & mbits;
-      if (COUNT) {
-        const int over = (tx << 5) + 32 - m.width;  // columns of this tile beyond the map
-        const uint32_t valid = over > 0 ? (0xffffffffu >> over) : 0xffffffffu;
-        cnt += __popc(mbits & valid);
+    const int wpr = b.lut.wpr;
+    const uint64_t* rows = b.lut.rows + (int64_t)f.bin * b.lut.max_rows * wpr;
+    for (int dy = lane; dy < f.nrows; dy += 32) {
+      const int Y = Y0 + dy;
+      if (Y < 0 || Y >= m.height) continue;
+      const uint32_t* trow = tiles + (((int64_t)(Y >> 4) * m.tiles_x) << 4) + (Y & 15);
+      const uint64_t* mrow = rows + (int64_t)dy * wpr;
+      const uint64_t mk = __ldg(mrow);
+      for (int tx = tx0; tx <= tx1; ++tx) {
+        const uint32_t word = __ldg(trow + (tx << 4));
+        const int rel = (tx << 5) - X0;
+        const uint32_t mbits = (wpr == 1) ? mask_window32(mk, rel) : mask_bits32(mrow, wpr, rel);
+        hit |= word & mbits;
+        if (COUNT) {
+          const int over = (tx << 5) + 32 - m.width;  // columns of this tile beyond the map
+          const uint32_t valid = over > 0 ? (0xffffffffu >> over) : 0xffffffffu;
+          cnt += __popc(mbits & valid);
+        }
       }
     }
   }
@@ -377,13 +394,15 @@ __device__ __forceinline__ int last_reached_from(const BcgParams& p, const BcgBa
   const double* P = b.path_arena + pd.off;
   const double* C = b.path_arena + pd.chunk_off;
   const double par_thr = -p.spatial_precision / 9;
+  const double sp2 = p.spatial_precision * p.spatial_precision;
   const int c_lo = lo >> 5, c_hi = (pd.n - 1) >> 5;
   for (int g = c_hi >> 5; g >= (c_lo >> 5); --g) {
     const int c = (g << 5) + lane;
     bool near = false;
     if (c >= c_lo && c <= c_hi) {
-      const double cx = __ldg(C + c), cy = __ldg(C + pd.chunk_pitch + c), cr = __ldg(C + 2 * pd.chunk_pitch + c);
-      near = (hypot(cx - px, cy - py) - cr) < p.spatial_precision;
+      const double cx = __ldg(C + c) - px, cy = __ldg(C + pd.chunk_pitch + c) - py;
+      const double reach = p.spatial_precision + __ldg(C + 2 * pd.chunk_pitch + c);
+      near = (cx * cx + cy * cy) < reach * reach * (1.0 + 1e-12);     // conservative: never drops a reachable chunk
     }
     unsigned bits = __ballot_sync(BCG_FULL, near);
     while (bits) {
@@ -394,10 +413,15 @@ __device__ __forceinline__ int last_reached_from(const BcgParams& p, const BcgBa
       if (i >= lo && i < pd.n) {
         const double xi = __ldg(P + i), yi = __ldg(P + pd.pitch + i), ti = __ldg(P + 2 * pd.pitch + i);
         const double ci = __ldg(P + 3 * pd.pitch + i), si = __ldg(P + 4 * pd.pitch + i);
-        const double dist = hypot(xi - px, yi - py);
-        const double ang = fabs(wrap_angle(pth - ti));
-        const double par = ci * (px - xi) + si * (py - yi);
-        reached = (dist < p.spatial_precision) && (ang < p.angular_precision) && (par >= par_thr);
+        // hypot(dx, dy) < sp, decided from the squared distance unless it is within 1e-12 of the threshold
+        const double dx = xi - px, dy = yi - py, d2 = dx * dx + dy * dy;
+        bool close = d2 < sp2 * (1.0 - 1e-12);
+        if (!close && d2 <= sp2 * (1.0 + 1e-12)) close = hypot(dx, dy) < p.spatial_precision;
+        if (close) {
+          const double ang = fabs(wrap_angle(pth - ti));
+          const double par = ci * (px - xi) + si * (py - yi);
+          reached = (ang < p.angular_precision) && (par >= par_thr);
+        }
       }
       const unsigned rb = __ballot_sync(BCG_FULL, reached);
       if (rb) return (((g << 5) + cl) << 5) + (31 - __clz(rb));

@@ -372,9 +372,11 @@ __global__ void __launch_bounds__(256) tiles_kernel(const BcgBatch b, const int 
   }
 }
 
-// pose_collides of the poses prepared in b.cand_i; one warp per env
+// pose_collides of the poses prepared in b.cand_i; one warp per env.  MODE 0: lethal tile plane,
+// 1: tile plane + in-map pixel count, 2: raw uint8 rows.
+template <int MODE>
 __global__ void __launch_bounds__(256) collision_kernel(const BcgBatch b, uint8_t* __restrict__ flags,
-                                                        int32_t* __restrict__ pixels, const int use_u8) {
+                                                        int32_t* __restrict__ pixels) {
   const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned lane = threadIdx.x & 31;
   if (e >= b.n_envs) return;
@@ -383,16 +385,12 @@ __global__ void __launch_bounds__(256) collision_kernel(const BcgBatch b, uint8_
   const BcgMapDesc m = b.maps[__ldg(b.map_id + e)];
   bool hit;
   int cnt = 0;
-  if (use_u8) {
-    hit = collide_u8(b, m, f, lane);
-  } else if (pixels) {
-    hit = collide_tiles<true>(b, m, f, lane, &cnt);
-  } else {
-    hit = collide_tiles<false>(b, m, f, lane, nullptr);
-  }
+  if (MODE == 2) hit = collide_u8(b, m, f, lane);
+  else if (MODE == 1) hit = collide_tiles<true>(b, m, f, lane, &cnt);
+  else hit = collide_tiles<false>(b, m, f, lane, nullptr);
   if (lane == 0) {
     flags[e] = hit ? 1 : 0;
-    if (pixels) pixels[e] = cnt;
+    if (MODE == 1) pixels[e] = cnt;
   }
 }
 
@@ -556,7 +554,7 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
 //     fixed-point rounding can move a sample) is loaded with coalesced 4-byte words.
 // Tile pitches: 208 B for TMA boxes, 4 * odd otherwise -- both measured at < 2 shared-memory wavefronts
 // per gather averaged over crop angles.
-__global__ void __launch_bounds__(BCG_EGO_THREADS, 4) ego_kernel(const BcgParams p, const BcgBatch b,
+__global__ void __launch_bounds__(BCG_EGO_THREADS, 5) ego_kernel(const BcgParams p, const BcgBatch b,
                                                                  uint8_t* __restrict__ image,
                                                                  float* __restrict__ goal_n_state,
                                                                  const int tile_capacity) {
@@ -564,7 +562,8 @@ __global__ void __launch_bounds__(BCG_EGO_THREADS, 4) ego_kernel(const BcgParams
   // TMA destinations must be 128-byte aligned; the launch reserves the slack
   uint8_t* const tile = tile_raw + ((128u - (smem_u32(tile_raw) & 127u)) & 127u);
   __shared__ int adx[BCG_EGO_MAX], ady[BCG_EGO_MAX], bdx[BCG_EGO_MAX], bdy[BCG_EGO_MAX];
-  __shared__ short2 span[BCG_EGO_MAX_TILE_ROWS];
+  // per-row spans of the plain-load path live behind the tile (that path never needs the whole capacity)
+  short2* const span = reinterpret_cast<short2*>(tile + tile_capacity);
   __shared__ EgoAffine aff_s;
   __shared__ int box[6];   // source window x0, x1, y0, y1 (not clipped to the map); TMA width class; mode
   __shared__ __align__(8) uint64_t mbar_s;
@@ -902,7 +901,9 @@ static int launch_ego(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image,
     }
     cap = (cap + 127) / 128 * 128;
     if (cap > 42 * 1024) cap = 42 * 1024;   // larger crops fall back to the direct global gather per CTA
-    ego_kernel<<<b->n_envs, BCG_EGO_THREADS, cap + 128, s>>>(*p, *b, ego_image, goal_n_state, cap);
+    // alignment slack + the per-row spans of the plain-load path, which live behind the tile
+    const int extra = 128 + BCG_EGO_MAX_TILE_ROWS * (int)sizeof(short2);
+    ego_kernel<<<b->n_envs, BCG_EGO_THREADS, cap + extra, s>>>(*p, *b, ego_image, goal_n_state, cap);
   } else {
     goal_kernel<<<blocks_for(b->n_envs, 128), 128, 0, s>>>(*p, *b, goal_n_state);
   }
@@ -947,9 +948,14 @@ int bcg_step(const BcgParams* p, const BcgBatch* b, const void* actions, int32_t
 
 static int launch_collision(const BcgParams* p, const BcgBatch* b, const double* poses, uint8_t* flags_out,
                             int32_t* pixels_out, int use_u8, cudaStream_t s) {
-  pose_prep_kernel<<<blocks_for(b->n_envs, 128), 128, 0, s>>>(*p, *b, poses);
-  BCG_CHECK_CUDA(cudaGetLastError());
-  collision_kernel<<<blocks_for((int64_t)b->n_envs * 32, 256), 256, 0, s>>>(*b, flags_out, pixels_out, use_u8);
+  if (poses) {   // NULL: check the poses the last kinematic step proposed (their references are still in cand_i)
+    pose_prep_kernel<<<blocks_for(b->n_envs, 128), 128, 0, s>>>(*p, *b, poses);
+    BCG_CHECK_CUDA(cudaGetLastError());
+  }
+  const int grid = blocks_for((int64_t)b->n_envs * 32, 256);
+  if (use_u8) collision_kernel<2><<<grid, 256, 0, s>>>(*b, flags_out, nullptr);
+  else if (pixels_out) collision_kernel<1><<<grid, 256, 0, s>>>(*b, flags_out, pixels_out);
+  else collision_kernel<0><<<grid, 256, 0, s>>>(*b, flags_out, nullptr);
   BCG_CHECK_CUDA(cudaGetLastError());
   return BCG_OK;
 }
@@ -957,13 +963,13 @@ static int launch_collision(const BcgParams* p, const BcgBatch* b, const double*
 int bcg_collision(const BcgParams* p, const BcgBatch* b, const double* poses, uint8_t* flags_out, int32_t* pixels_out,
                   void* stream) {
   if (int rc = check_batch(p, b)) return rc;
-  BCG_REQUIRE(poses && flags_out, "null poses/flags");
+  BCG_REQUIRE(flags_out, "null flags");
   return launch_collision(p, b, poses, flags_out, pixels_out, 0, (cudaStream_t)stream);
 }
 
 int bcg_collision_u8(const BcgParams* p, const BcgBatch* b, const double* poses, uint8_t* flags_out, void* stream) {
   if (int rc = check_batch(p, b)) return rc;
-  BCG_REQUIRE(poses && flags_out, "null poses/flags");
+  BCG_REQUIRE(flags_out, "null flags");
   return launch_collision(p, b, poses, flags_out, nullptr, 1, (cudaStream_t)stream);
 }
 

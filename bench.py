@@ -332,8 +332,8 @@ def run_b200(args):
     import ctypes as C
     flags = torch.empty(n, dtype=torch.uint8, device=device)
     s = env._stream()
-    tiles_ms = time_kernel(lambda: nat.check(nat.lib().bcg_collision(C.byref(env._c_params), C.byref(env._batch), nat.ptr(rows), nat.ptr(flags), None, s)))
-    u8_ms = time_kernel(lambda: nat.check(nat.lib().bcg_collision_u8(C.byref(env._c_params), C.byref(env._batch), nat.ptr(rows), nat.ptr(flags), s)))
+    tiles_ms = time_kernel(lambda: nat.check(nat.lib().bcg_collision(C.byref(env._c_params), C.byref(env._batch), None, nat.ptr(flags), None, s)))
+    u8_ms = time_kernel(lambda: nat.check(nat.lib().bcg_collision_u8(C.byref(env._c_params), C.byref(env._batch), None, nat.ptr(flags), s)))
     del flush
 
     # ---- e2e: host actions in, host results out, every step -----------------------------------------

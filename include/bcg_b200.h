@@ -233,7 +233,9 @@ int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, 
 int bcg_kinematic_step(const BcgParams* p, const BcgBatch* b, const void* actions,
                        int32_t action_is_f64, uint64_t step_index, void* stream);
 /* pose_collides (env.py:464-489) of poses [3][n] (rows x,y,th) against each env's map, using the
- * lethal tile plane; flags_out [n].  pixels_out (optional, [n]) = in-map footprint pixel count. */
+ * lethal tile plane; flags_out [n].  pixels_out (optional, [n]) = in-map footprint pixel count.
+ * poses == NULL re-checks the poses the last bcg_kinematic_step / bcg_step proposed (only the
+ * warp-per-env collision kernel is launched -- this is the form the roofline is measured on). */
 int bcg_collision(const BcgParams* p, const BcgBatch* b, const double* poses, uint8_t* flags_out,
                   int32_t* pixels_out, void* stream);
 /* same verdicts read straight from the uint8 costmap rows (no derived plane) */
