@@ -80,7 +80,7 @@ class ClockSampler(object):
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -153,6 +153,7 @@ def _action_bounds():
 
 def cpu_baseline_sample(seconds, with_ego):
     """Single-process oracle port on one host core for ~`seconds` s."""
+    _single_threaded_math()
     envs = _oracle_envs(4, 900)
     rng = np.random.RandomState(0)
     low, high = _action_bounds()
@@ -167,13 +168,37 @@ def cpu_baseline_sample(seconds, with_ego):
                       "host has %d cores" % (n, dt, os.cpu_count())}
 
 
+def _single_threaded_math():
+    """One worker per core: keep BLAS / OpenCV from spawning their own thread pools in every worker."""
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(1)
+    except Exception:
+        pass
+    try:
+        import cv2
+        cv2.setNumThreads(0)
+    except Exception:
+        pass
+
+
+_REF_BARRIER = None
+
+
+def _ref_init(barrier):
+    global _REF_BARRIER
+    _REF_BARRIER = barrier
+
+
 def _ref_worker(args):
     wid, n_envs, n_steps, warmup, with_ego = args
+    _single_threaded_math()
     envs = _oracle_envs(n_envs, 1000 + 100 * wid)
     rng = np.random.RandomState(wid)
     low, high = _action_bounds()
     for _ in range(warmup):
         _oracle_advance(envs, rng, with_ego, low, high)
+    _REF_BARRIER.wait()                      # all workers start the timed steps together
     t0 = time.perf_counter()
     n = 0
     for _ in range(n_steps):
@@ -191,9 +216,12 @@ def run_reference(args):
     import multiprocessing as mp
     workers = max(1, os.cpu_count() or 1)
     with_ego = not args.no_ego
+    from oracle import plan_env_oracle  # noqa: F401  (import once here, not in every forked worker)
+    from bc_gym_planning_env_b200.envs import synth_turn_env  # noqa: F401
     ctx = mp.get_context("fork")
-    with ctx.Pool(workers) as pool:
-        res = pool.map(_ref_worker, [(w, args.ref_envs, args.steps, args.warmup, with_ego) for w in range(workers)])
+    barrier = ctx.Barrier(workers)
+    with ctx.Pool(workers, initializer=_ref_init, initargs=(barrier,)) as pool:
+        res = pool.map(_ref_worker, [(w, args.ref_envs, args.steps, args.warmup, with_ego) for w in range(workers)], chunksize=1)
     n = sum(r[0] for r in res)
     wall = max(r[2] for r in res) - min(r[1] for r in res)
     value = n / wall
@@ -284,6 +312,24 @@ def run_b200(args):
     cr_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
     commit_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in ev]))
     ego_ms = float(np.mean([e[3].elapsed_time(e[4]) for e in ev]))
+
+    # ---- same loop without the egocentric kernel (reported beside the headline, not instead of it) -----
+    no_ego_value = None
+    if not args.no_ego:
+        saved = (env._out.ego_image, env._out.goal_n_state)
+        env._out.ego_image, env._out.goal_n_state = None, None
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for k in range(args.steps):
+            env.step(actions[k % n_sets])
+        a1.record()
+        barrier()
+        tt = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        no_ego_value = n * world * args.steps / (float(tt.item()) * 1e-3)
+        env._out.ego_image, env._out.goal_n_state = saved
 
     # ---- algorithmic bytes -----------------------------------------------------------
     cand_pose = env._cand[:3].t().contiguous()
@@ -381,6 +427,7 @@ def run_b200(args):
                 "tiles": roof("collision_kernel (lethal tile plane), cold L2", coll_bytes, tiles_ms, "uint8-definition bytes"),
                 "u8": roof("collision_kernel (uint8 rows), cold L2", coll_bytes, u8_ms, "uint8-definition bytes"),
             },
+            "value_without_ego_obs": no_ego_value,
             "episode_stats": {k: float(v) for k, v in zip(nat.STAT_NAMES, stats.tolist())},
             "cpu_baseline": cpu,
         }
