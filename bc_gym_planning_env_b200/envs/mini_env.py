@@ -203,6 +203,39 @@ def sample_mini_env_params(gen_params, rng, batch=8):
     raise ValueError("Something went wrong, the sampling space looks empty.")
 
 
+def random_mini_pool(n, seed, gen_params=None, max_rounds=1000):
+    """n mini envs for a batch: ([CostMap2D], [coarse path]) where entry i is what RandomMiniEnv(seed=seed + i)
+    draws first.  All pending candidates of a round are collision-checked in one kernel call."""
+    if gen_params is None:
+        gen_params = RandomMiniEnvParams(env_params=EnvParams(goal_ang_dist=np.pi / 8., goal_spat_dist=0.2))
+    ep = gen_params.env_params
+    rngs = [np.random.RandomState(seed + i) for i in range(n)]
+    result = [None] * n
+    pending = list(range(n))
+    for _ in range(max_rounds):
+        if not pending:
+            break
+        built = []
+        for i in pending:
+            try:
+                built.append((i, prepare_map_and_path(sample_candidate(gen_params, rngs[i]))))
+            except SpaceSeemsEmptyError:
+                pass
+        if built:
+            costmaps = [cm for _, (cm, _) in built for _ in range(2)]
+            poses = [path[k] for _, (_, path) in built for k in range(2)]
+            hits = _poses_collide(costmaps, poses, ep).reshape(-1, 2)
+            for (i, (cm, path)), hit in zip(built, hits):
+                d = float(np.hypot(path[0, 0] - path[1, 0], path[0, 1] - path[1, 1]))
+                a = float(np.abs(_wrap(path[0, 2] - path[1, 2])))
+                if not hit.any() and not (d < ep.goal_spat_dist and a < ep.goal_ang_dist):
+                    result[i] = (cm, path)
+        pending = [i for i in pending if result[i] is None]
+    if pending:
+        raise ValueError("Something went wrong, the sampling space looks empty.")
+    return [r[0] for r in result], [r[1] for r in result]
+
+
 class MiniEnv(PlanEnv):
     def __init__(self, config, **kw):
         self._config = config
