@@ -213,12 +213,38 @@ __device__ __forceinline__ void delay_line(double* ring, int64_t stride, int& q,
 }
 
 // ---- footprint table lookup ----------------------------------------------------------------------
-// What the collision kernels need to know about one pose: its pixel, its angle bin and the bin's mask
-// bounding box.  Produced per thread (kinematic / pose-prep kernels), consumed per warp.
-struct FootRef {
-  int px, py, bin;
-  int xmin, ymin, nrows, width;
+// Work records: what the warp-per-env kernels need to know about one env, resolved by the thread-per-env
+// kernels (kinematics / pose-prep) and stored array-of-structures so that a warp gets everything with one
+// round of 16-byte loads instead of chasing map_id -> map descriptor -> tile address through memory.
+struct __align__(16) WorkCollide {   // 64 bytes
+  int64_t tile_off;                  // lethal tile plane of the env's map (uint32 offset in the tile arena)
+  int64_t data_off;                  // uint8 cells of the env's map (byte offset in the map arena)
+  int32_t tiles_x, map_pitch;
+  int32_t X0, Y0;                    // map pixel of the footprint mask's top-left corner
+  int16_t nrows, fwidth;             // mask bounding box
+  int16_t map_w, map_h;
+  int32_t bin;                       // footprint angle bin
+  int32_t path_n;
+  int64_t path_off;                  // fp64 offset of the env's path rows in the path arena
+  int32_t path_pitch, chunk_pitch;   // chunk rows start at path_off + 5 * path_pitch
 };
+
+struct __align__(16) WorkReward {    // 96 bytes
+  double cand[3];                    // pose proposed by the kinematic step
+  double old_pose[3];                // pose to fall back to on a collision (env.py:458-459)
+  double ring_front[3];              // front of the pose delay queue (valid when from_ring)
+  double min_dist;
+  int32_t target, from_ring;
+};
+
+#define BCG_WORK_BYTES 192           // WorkCollide at +0, WorkReward at +64
+
+__device__ __forceinline__ const WorkCollide* work_collide(const void* work, int e) {
+  return reinterpret_cast<const WorkCollide*>(reinterpret_cast<const uint8_t*>(work) + (int64_t)e * BCG_WORK_BYTES);
+}
+__device__ __forceinline__ const WorkReward* work_reward(const void* work, int e) {
+  return reinterpret_cast<const WorkReward*>(reinterpret_cast<const uint8_t*>(work) + (int64_t)e * BCG_WORK_BYTES + 64);
+}
 
 // Per-thread.  Picks the angle bin whose stored rounded-vertex tuple equals
 // round_half_even(R(th) * footprint / res) (utilities/path_tools.py:140-150), i.e. the bin whose
@@ -253,50 +279,34 @@ __device__ __forceinline__ int find_foot_bin(const BcgFootprintLut& lut, double 
   return k;
 }
 
-__device__ __forceinline__ FootRef make_foot_ref(const BcgParams& p, const BcgFootprintLut& lut, const BcgMapDesc* maps,
-                                                 int map_id, double x, double y, double th, uint32_t* status) {
-  FootRef f;
-  f.px = world_to_pixel_1d(x, __ldg(&maps[map_id].origin_x), p.inv_resolution);
-  f.py = world_to_pixel_1d(y, __ldg(&maps[map_id].origin_y), p.inv_resolution);
-  f.bin = find_foot_bin(lut, th, status);
-  const short4 h = __ldg(reinterpret_cast<const short4*>(lut.header) + f.bin);
-  f.xmin = h.x;
-  f.ymin = h.y;
-  f.nrows = h.z;
-  f.width = h.w;
-  return f;
+__device__ __forceinline__ WorkCollide make_work_collide(const BcgParams& p, const BcgBatch& b, int map_id, int path_id,
+                                                         double x, double y, double th) {
+  const BcgMapDesc m = b.maps[map_id];
+  const BcgPathDesc pd = b.paths[path_id];
+  WorkCollide w;
+  w.bin = find_foot_bin(b.lut, th, b.status);
+  const short4 h = __ldg(reinterpret_cast<const short4*>(b.lut.header) + w.bin);     // xmin, ymin, nrows, width
+  w.X0 = world_to_pixel_1d(x, m.origin_x, p.inv_resolution) + h.x;
+  w.Y0 = world_to_pixel_1d(y, m.origin_y, p.inv_resolution) + h.y;
+  w.nrows = h.z;
+  w.fwidth = h.w;
+  w.tile_off = m.tile_off;
+  w.data_off = m.data_off;
+  w.tiles_x = m.tiles_x;
+  w.map_pitch = m.pitch;
+  w.map_w = (int16_t)m.width;
+  w.map_h = (int16_t)m.height;
+  w.path_n = pd.n;
+  w.path_off = pd.off;
+  w.path_pitch = pd.pitch;
+  w.chunk_pitch = pd.chunk_pitch;
+  return w;
 }
 
-// scratch int rows written by the kinematic / pose-prep kernels
-#define BCG_CI_PX 0
-#define BCG_CI_PY 1
-#define BCG_CI_BIN 2
-#define BCG_CI_HDR0 3  /* xmin | ymin << 16 */
-#define BCG_CI_HDR1 4  /* nrows | width << 16 */
-#define BCG_CI_TARGET 5
-#define BCG_CI_FLAGS 6 /* bit0 hit, bit1 goal after this step, bit2 goal before it */
-#define BCG_CI_ROWS 7
-
-__device__ __forceinline__ void store_foot_ref(int32_t* ci, int64_t N, const FootRef& f) {
-  ci[BCG_CI_PX * N] = f.px;
-  ci[BCG_CI_PY * N] = f.py;
-  ci[BCG_CI_BIN * N] = f.bin;
-  ci[BCG_CI_HDR0 * N] = (f.xmin & 0xffff) | (f.ymin << 16);
-  ci[BCG_CI_HDR1 * N] = (f.nrows & 0xffff) | (f.width << 16);
-}
-
-__device__ __forceinline__ FootRef load_foot_ref(const int32_t* ci, int64_t N) {
-  FootRef f;
-  f.px = __ldg(ci + BCG_CI_PX * N);
-  f.py = __ldg(ci + BCG_CI_PY * N);
-  f.bin = __ldg(ci + BCG_CI_BIN * N);
-  const int h0 = __ldg(ci + BCG_CI_HDR0 * N), h1 = __ldg(ci + BCG_CI_HDR1 * N);
-  f.xmin = (int)(short)(h0 & 0xffff);
-  f.ymin = h0 >> 16;
-  f.nrows = h1 & 0xffff;
-  f.width = h1 >> 16;
-  return f;
-}
+// scratch int rows written by the collide/reward kernel for the commit kernel
+#define BCG_CI_TARGET 0
+#define BCG_CI_FLAGS 1 /* bit0 hit, bit1 goal after this step, bit2 goal before it */
+#define BCG_CI_ROWS 2
 
 // 32 mask bits starting at bit `rel` of a multi-word row mask (bit b <-> column xmin + b)
 __device__ __forceinline__ uint32_t mask_bits32(const uint64_t* row, int wpr, int rel) {
@@ -318,21 +328,21 @@ __device__ __forceinline__ uint32_t mask_window32(uint64_t mk, int rel) {
 // the row crosses; 16 consecutive rows of a tile are one coalesced 64-byte read.  Returns the
 // warp-uniform verdict.  If COUNT, *pixels gets the number of in-map footprint pixels.
 template <bool COUNT>
-__device__ __forceinline__ bool collide_tiles(const BcgBatch& b, const BcgMapDesc& m, const FootRef& f, unsigned lane,
-                                              int* pixels) {
-  const int X0 = f.px + f.xmin, Y0 = f.py + f.ymin;
-  const int X1 = X0 + f.width - 1;
+__device__ __forceinline__ bool collide_tiles(const BcgBatch& b, const WorkCollide& f, unsigned lane, int* pixels) {
+  const int X0 = f.X0, Y0 = f.Y0;
+  const int X1 = X0 + f.fwidth - 1;
+  const int map_w = f.map_w, map_h = f.map_h;
   unsigned hit = 0;
   int cnt = 0;
-  if (!(X1 < 0 || X0 >= m.width)) {
-    const int tx0 = max(X0, 0) >> 5, tx1 = min(X1, m.width - 1) >> 5;
-    const uint32_t* tiles = b.tile_arena + m.tile_off;
+  if (!(X1 < 0 || X0 >= map_w)) {
+    const int tx0 = max(X0, 0) >> 5, tx1 = min(X1, map_w - 1) >> 5;
+    const uint32_t* tiles = b.tile_arena + f.tile_off;
     const int wpr = b.lut.wpr;
     const uint64_t* rows = b.lut.rows + (int64_t)f.bin * b.lut.max_rows * wpr;
     for (int dy = lane; dy < f.nrows; dy += 32) {
       const int Y = Y0 + dy;
-      if (Y < 0 || Y >= m.height) continue;
-      const uint32_t* trow = tiles + (((int64_t)(Y >> 4) * m.tiles_x) << 4) + (Y & 15);
+      if (Y < 0 || Y >= map_h) continue;
+      const uint32_t* trow = tiles + (((int64_t)(Y >> 4) * f.tiles_x) << 4) + (Y & 15);
       const uint64_t* mrow = rows + (int64_t)dy * wpr;
       const uint64_t mk = __ldg(mrow);
       for (int tx = tx0; tx <= tx1; ++tx) {
@@ -341,7 +351,7 @@ __device__ __forceinline__ bool collide_tiles(const BcgBatch& b, const BcgMapDes
         const uint32_t mbits = (wpr == 1) ? mask_window32(mk, rel) : mask_bits32(mrow, wpr, rel);
         hit |= word & mbits;
         if (COUNT) {
-          const int over = (tx << 5) + 32 - m.width;  // columns of this tile beyond the map
+          const int over = (tx << 5) + 32 - map_w;  // columns of this tile beyond the map
           const uint32_t valid = over > 0 ? (0xffffffffu >> over) : 0xffffffffu;
           cnt += __popc(mbits & valid);
         }
@@ -358,19 +368,20 @@ __device__ __forceinline__ bool collide_tiles(const BcgBatch& b, const BcgMapDes
 
 // The same verdict read straight from the uint8 costmap rows: each half-warp owns one footprint row
 // per pass, each lane one aligned 4-byte word of it.
-__device__ __forceinline__ bool collide_u8(const BcgBatch& b, const BcgMapDesc& m, const FootRef& f, unsigned lane) {
-  const int X0 = f.px + f.xmin, Y0 = f.py + f.ymin;
-  const int X1 = X0 + f.width - 1;
+__device__ __forceinline__ bool collide_u8(const BcgBatch& b, const WorkCollide& f, unsigned lane) {
+  const int X0 = f.X0, Y0 = f.Y0;
+  const int X1 = X0 + f.fwidth - 1;
+  const int map_w = f.map_w, map_h = f.map_h;
   unsigned hit = 0;
-  if (!(X1 < 0 || X0 >= m.width)) {
-    const int w0 = max(X0, 0) >> 2, w1 = min(X1, m.width - 1) >> 2;
-    const uint8_t* data = b.map_arena + m.data_off;
+  if (!(X1 < 0 || X0 >= map_w)) {
+    const int w0 = max(X0, 0) >> 2, w1 = min(X1, map_w - 1) >> 2;
+    const uint8_t* data = b.map_arena + f.data_off;
     const uint64_t* rows = b.lut.rows + (int64_t)f.bin * b.lut.max_rows * b.lut.wpr;
     const int half = lane >> 4, sub = lane & 15;
     for (int dy = half; dy < f.nrows; dy += 2) {
       const int Y = Y0 + dy;
-      if (Y < 0 || Y >= m.height) continue;
-      const uint32_t* rowp = reinterpret_cast<const uint32_t*>(data + (int64_t)Y * m.pitch);
+      if (Y < 0 || Y >= map_h) continue;
+      const uint32_t* rowp = reinterpret_cast<const uint32_t*>(data + (int64_t)Y * f.map_pitch);
       for (int wi = w0 + sub; wi <= w1; wi += 16) {
         const uint32_t bytes = __ldg(rowp + wi);
         const uint32_t m4 = mask_bits32(rows + (int64_t)dy * b.lut.wpr, b.lut.wpr, (wi << 2) - X0) & 0xfu;
@@ -388,11 +399,27 @@ __device__ __forceinline__ bool collide_u8(const BcgBatch& b, const BcgMapDesc& 
 // max i with hypot < sp, |wrap(dth)| < ap, parallel distance >= -sp/9.  Chunks of 32 points whose
 // bounding circle is farther than sp from the pose cannot contain a reached point and are skipped.
 // Warp-cooperative; returns -1 when nothing is reached.
-__device__ __forceinline__ int last_reached_from(const BcgParams& p, const BcgBatch& b, const BcgPathDesc& pd, int lo,
-                                                 double px, double py, double pth, unsigned lane) {
+struct PathRef {
+  const double* P;   // 5 rows x, y, th, cos th, sin th, each `pitch` long
+  const double* C;   // 3 chunk rows cx, cy, radius, each `chunk_pitch` long
+  int n, pitch, chunk_pitch;
+};
+
+__device__ __forceinline__ PathRef path_ref(const BcgBatch& b, const BcgPathDesc& d) {
+  PathRef r;
+  r.P = b.path_arena + d.off;
+  r.C = b.path_arena + d.chunk_off;
+  r.n = d.n;
+  r.pitch = d.pitch;
+  r.chunk_pitch = d.chunk_pitch;
+  return r;
+}
+
+__device__ __forceinline__ int last_reached_from(const BcgParams& p, const PathRef& pd, int lo, double px, double py,
+                                                 double pth, unsigned lane) {
   if (lo >= pd.n) return -1;
-  const double* P = b.path_arena + pd.off;
-  const double* C = b.path_arena + pd.chunk_off;
+  const double* P = pd.P;
+  const double* C = pd.C;
   const double par_thr = -p.spatial_precision / 9;
   const double sp2 = p.spatial_precision * p.spatial_precision;
   const int c_lo = lo >> 5, c_hi = (pd.n - 1) >> 5;

@@ -57,7 +57,7 @@ int check_batch(const BcgParams* p, const BcgBatch* b) {
   BCG_REQUIRE(p->delay_control < 4096 && p->delay_pose < 4096 && p->delay_state < 4096, "delay too large");
   const BcgStateLayout L = make_layout(*p);
   BCG_REQUIRE(b->n_frows == L.n_frows && b->n_irows == L.n_irows, "state row count does not match bcg_state_layout");
-  BCG_REQUIRE(b->state_f && b->state_i && b->init_f && b->init_i && b->cand && b->cand_i, "null state pointers");
+  BCG_REQUIRE(b->state_f && b->state_i && b->init_f && b->init_i && b->cand && b->cand_i && b->work, "null state pointers");
   BCG_REQUIRE(b->map_id && b->path_id && b->maps && b->paths && b->map_arena && b->tile_arena && b->path_arena,
               "null arena pointers");
   BCG_REQUIRE(b->lut.edges && b->lut.verts && b->lut.header && b->lut.rows && b->lut.fp_pix && b->lut.bucket_first,
@@ -93,7 +93,25 @@ __global__ void __launch_bounds__(128) kin_kernel(const BcgParams p, const BcgBa
   double s[7];
 #pragma unroll
   for (int r = 0; r < 7; ++r) s[r] = b.state_f[(BCG_F_ROBOT + r) * N + e];
-  const int map_id = b.map_id[e];
+  const int map_id = b.map_id[e], path_id = b.path_id[e];
+  // inputs of the reward the warp kernel will compute (read here: coalesced rows)
+  WorkReward wr;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) wr.old_pose[r] = s[r];
+  wr.min_dist = b.state_f[BCG_F_MIN_DIST * N + e];
+  wr.target = b.state_i[BCG_I_TARGET * N + e];
+  wr.from_ring = 0;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) wr.ring_front[r] = 0.0;
+  if (p.delay_pose > 0) {
+    const int qp = b.state_i[BCG_I_QP * N + e];
+    if ((qp >> 16) > 0) {                              // env.py:27-49: the front of a non-empty queue
+      wr.from_ring = 1;
+      const int head = qp & 0xffff;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) wr.ring_front[r] = b.state_f[(int64_t)(L.ring_pose + head * 3 + r) * N + e];
+    }
+  }
   if (p.delay_control > 0) {
     int q = b.state_i[BCG_I_QC * N + e];
     delay_line<2>(b.state_f + (int64_t)L.ring_control * N + e, N, q, p.delay_control, u);
@@ -102,74 +120,71 @@ __global__ void __launch_bounds__(128) kin_kernel(const BcgParams p, const BcgBa
   robot_step(s, u[0], u[1], p, p.env_id_base + (uint64_t)e, step_index);
 #pragma unroll
   for (int r = 0; r < 7; ++r) b.cand[r * N + e] = s[r];
-  const FootRef f = make_foot_ref(p, b.lut, b.maps, map_id, s[0], s[1], s[2], b.status);
-  store_foot_ref(b.cand_i + e, N, f);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) wr.cand[r] = s[r];
+  uint8_t* rec = reinterpret_cast<uint8_t*>(b.work) + (int64_t)e * BCG_WORK_BYTES;
+  *reinterpret_cast<WorkCollide*>(rec) = make_work_collide(p, b, map_id, path_id, s[0], s[1], s[2]);
+  *reinterpret_cast<WorkReward*>(rec + 64) = wr;
 }
 
-// pixel / footprint-bin reference of arbitrary poses [3][n] (stand-alone collision entry points)
+// work records of arbitrary poses [3][n] (stand-alone collision entry points)
 __global__ void __launch_bounds__(128) pose_prep_kernel(const BcgParams p, const BcgBatch b,
                                                         const double* __restrict__ poses) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= b.n_envs) return;
   const int64_t N = b.n_envs;
-  const FootRef f = make_foot_ref(p, b.lut, b.maps, b.map_id[e], poses[e], poses[N + e], poses[2 * N + e], b.status);
-  store_foot_ref(b.cand_i + e, N, f);
+  uint8_t* rec = reinterpret_cast<uint8_t*>(b.work) + (int64_t)e * BCG_WORK_BYTES;
+  *reinterpret_cast<WorkCollide*>(rec) = make_work_collide(p, b, b.map_id[e], b.path_id[e], poses[e], poses[N + e], poses[2 * N + e]);
 }
 
 // One warp per env: footprint-vs-lethal-tile collision of the proposed pose (env.py:455), then the
 // reward of the pose the reward provider will see (reward.py:214-259).  Reads only; its few results go
 // to the scratch rows, the thread-per-env commit kernel applies them.  No store precedes a load, so all
 // of a warp's independent loads are in flight together.
-__global__ void __launch_bounds__(256, 4) collide_reward_kernel(const BcgParams p, const BcgBatch b,
-                                                                const BcgStateLayout L) {
+__global__ void __launch_bounds__(256, 5) collide_reward_kernel(const BcgParams p, const BcgBatch b) {
   const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned lane = threadIdx.x & 31;
   if (e >= b.n_envs) return;
   const int64_t N = b.n_envs;
-  const double* sf = b.state_f + e;
-  const int32_t* si = b.state_i + e;
-
-  const FootRef f = load_foot_ref(b.cand_i + e, N);
-  const int map_id = __ldg(b.map_id + e), path_id = __ldg(b.path_id + e);
-  int target = __ldg(si + BCG_I_TARGET * N);
-  const int qp = __ldg(si + BCG_I_QP * N);
-  double min_dist = __ldg(sf + BCG_F_MIN_DIST * N);
-  double pose[3], old_pose[3], ring_front[3];
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    pose[r] = __ldg(b.cand + r * N + e);
-    old_pose[r] = __ldg(sf + (BCG_F_ROBOT + r) * N);
+  // round 1: the env's two work records (a warp-uniform 160-byte read)
+  const WorkCollide wc = *work_collide(b.work, e);
+  const WorkReward wr = *work_reward(b.work, e);
+  PathRef pd;
+  pd.P = b.path_arena + wc.path_off;
+  pd.C = pd.P + 5 * (int64_t)wc.path_pitch;
+  pd.n = wc.path_n;
+  pd.pitch = wc.path_pitch;
+  pd.chunk_pitch = wc.chunk_pitch;
+  int target = wr.target;
+  double min_dist = wr.min_dist;
+  const bool goal_before = target > pd.n - 1;
+  // round 2 (issued before the collision verdict is needed): the goal point the reward most likely uses
+  double gx = 0.0, gy = 0.0;
+  if (!goal_before) {
+    gx = __ldg(pd.P + target);
+    gy = __ldg(pd.P + pd.pitch + target);
   }
-  const int q_head = qp & 0xffff, q_len = qp >> 16;
-  const bool from_ring = p.delay_pose > 0 && q_len > 0;   // env.py:27-49: the front of a non-empty queue
-  if (from_ring) {
-#pragma unroll
-    for (int r = 0; r < 3; ++r) ring_front[r] = __ldg(sf + (int64_t)(L.ring_pose + q_head * 3 + r) * N);
-  }
-  const BcgMapDesc m = b.maps[map_id];
-  const BcgPathDesc pd = b.paths[path_id];
 
-  const bool hit = collide_tiles<false>(b, m, f, lane, nullptr);
+  const bool hit = collide_tiles<false>(b, wc, lane, nullptr);
 
   // the pose State.pose will hold after this step: rolled back on a hit (env.py:458-459), delayed (:377-380)
+  double pose[3];
 #pragma unroll
-  for (int r = 0; r < 3; ++r) pose[r] = from_ring ? ring_front[r] : (hit ? old_pose[r] : pose[r]);
+  for (int r = 0; r < 3; ++r) pose[r] = wr.from_ring ? wr.ring_front[r] : (hit ? wr.old_pose[r] : wr.cand[r]);
 
-  const bool goal_before = target > pd.n - 1;
   double reward = 0.0;
-  const double* P = b.path_arena + pd.off;
   if (!goal_before) {
-    const int last = last_reached_from(p, b, pd, target, pose[0], pose[1], pose[2], lane);
+    const int last = last_reached_from(p, pd, target, pose[0], pose[1], pose[2], lane);
     if (last >= target) {
       target = last + 1;
       if (target > pd.n - 1) {
         min_dist = 0.0;
       } else {
-        min_dist = hypot(__ldg(P + target) - pose[0], __ldg(P + pd.pitch + target) - pose[1]);
+        min_dist = hypot(__ldg(pd.P + target) - pose[0], __ldg(pd.P + pd.pitch + target) - pose[1]);
       }
       reward = 1.0;
     } else {
-      const double d = hypot(__ldg(P + target) - pose[0], __ldg(P + pd.pitch + target) - pose[1]);
+      const double d = hypot(gx - pose[0], gy - pose[1]);
       if (d < min_dist) {
         reward = (min_dist - d) * p.progress_multiplier;
         min_dist = d;
@@ -305,10 +320,10 @@ __global__ void __launch_bounds__(256) init_kernel(const BcgParams p, const BcgB
   const unsigned lane = threadIdx.x & 31;
   if (e >= b.n_envs) return;
   const int64_t N = b.n_envs;
-  const BcgPathDesc pd = b.paths[b.path_id[e]];
-  const double* P = b.path_arena + pd.off;
+  const PathRef pd = path_ref(b, b.paths[b.path_id[e]]);
+  const double* P = pd.P;
   const double x0 = P[0], y0 = P[pd.pitch], t0 = P[2 * pd.pitch];
-  const int last = last_reached_from(p, b, pd, 0, x0, y0, t0, lane);
+  const int last = last_reached_from(p, pd, 0, x0, y0, t0, lane);
   int target = last + 1;
   double min_dist = 0.0;
   if (target > pd.n - 1) {
@@ -372,22 +387,20 @@ __global__ void __launch_bounds__(256) tiles_kernel(const BcgBatch b, const int 
   }
 }
 
-// pose_collides of the poses prepared in b.cand_i; one warp per env.  MODE 0: lethal tile plane,
+// pose_collides of the poses whose work records are in b.work; one warp per env.  MODE 0: lethal tile plane,
 // 1: tile plane + in-map pixel count, 2: raw uint8 rows.
 template <int MODE>
-__global__ void __launch_bounds__(256) collision_kernel(const BcgBatch b, uint8_t* __restrict__ flags,
+__global__ void __launch_bounds__(256, 6) collision_kernel(const BcgBatch b, uint8_t* __restrict__ flags,
                                                         int32_t* __restrict__ pixels) {
   const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned lane = threadIdx.x & 31;
   if (e >= b.n_envs) return;
-  const int64_t N = b.n_envs;
-  const FootRef f = load_foot_ref(b.cand_i + e, N);
-  const BcgMapDesc m = b.maps[__ldg(b.map_id + e)];
+  const WorkCollide f = *work_collide(b.work, e);
   bool hit;
   int cnt = 0;
-  if (MODE == 2) hit = collide_u8(b, m, f, lane);
-  else if (MODE == 1) hit = collide_tiles<true>(b, m, f, lane, &cnt);
-  else hit = collide_tiles<false>(b, m, f, lane, nullptr);
+  if (MODE == 2) hit = collide_u8(b, f, lane);
+  else if (MODE == 1) hit = collide_tiles<true>(b, f, lane, &cnt);
+  else hit = collide_tiles<false>(b, f, lane, nullptr);
   if (lane == 0) {
     flags[e] = hit ? 1 : 0;
     if (MODE == 1) pixels[e] = cnt;
@@ -928,7 +941,7 @@ int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, 
   kin_kernel<<<blocks_for(b->n_envs, 128), 128, 0, s>>>(*p, *b, L, actions, action_is_f64, step_index);
   BCG_CHECK_CUDA(cudaGetLastError());
   if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[1], s));
-  collide_reward_kernel<<<blocks_for((int64_t)b->n_envs * 32, 256), 256, 0, s>>>(*p, *b, L);
+  collide_reward_kernel<<<blocks_for((int64_t)b->n_envs * 32, 256), 256, 0, s>>>(*p, *b);
   BCG_CHECK_CUDA(cudaGetLastError());
   if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[2], s));
   commit_kernel<<<blocks_for(b->n_envs, 128), 128, 0, s>>>(*p, *b, L, *out);
@@ -948,7 +961,7 @@ int bcg_step(const BcgParams* p, const BcgBatch* b, const void* actions, int32_t
 
 static int launch_collision(const BcgParams* p, const BcgBatch* b, const double* poses, uint8_t* flags_out,
                             int32_t* pixels_out, int use_u8, cudaStream_t s) {
-  if (poses) {   // NULL: check the poses the last kinematic step proposed (their references are still in cand_i)
+  if (poses) {   // NULL: check the poses the last kinematic step proposed (their work records are still in b->work)
     pose_prep_kernel<<<blocks_for(b->n_envs, 128), 128, 0, s>>>(*p, *b, poses);
     BCG_CHECK_CUDA(cudaGetLastError());
   }

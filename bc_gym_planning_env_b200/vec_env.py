@@ -170,6 +170,8 @@ class VecPlanEnv(object):
                 raise ValueError("all costmaps of a batch must share one resolution")
             h, w = data.shape
             d = descs[k]
+            if h >= 32768 or w >= 32768:
+                raise ValueError("costmaps are limited to 32767 cells per side")
             d.height, d.width, d.pitch = h, w, _round_up(w, 32)
             d.tiles_x, d.tiles_y = d.pitch // 32, (h + 15) // 16
             d.origin_x, d.origin_y = float(cm.get_origin()[0]), float(cm.get_origin()[1])
@@ -266,7 +268,8 @@ class VecPlanEnv(object):
         self.init_f = torch.zeros_like(self.state_f)
         self.init_i = torch.zeros_like(self.state_i)
         self._cand = torch.zeros((9, n), dtype=torch.float64, device=dev)
-        self._cand_i = torch.zeros((7, n), dtype=torch.int32, device=dev)
+        self._cand_i = torch.zeros((2, n), dtype=torch.int32, device=dev)
+        self._work = torch.zeros((n, 192), dtype=torch.uint8, device=dev)
         self._status = torch.zeros(nat.STATUS_WORDS, dtype=torch.int32, device=dev)
         self._stats = torch.zeros(nat.STATS_WORDS, dtype=torch.float64, device=dev)
         self.reward = torch.zeros(n, dtype=torch.float64, device=dev)
@@ -286,7 +289,7 @@ class VecPlanEnv(object):
         b.n_maps, b.n_paths = self._n_maps, len(self._paths_host)
         b.state_f, b.state_i = self.state_f.data_ptr(), self.state_i.data_ptr()
         b.init_f, b.init_i = self.init_f.data_ptr(), self.init_i.data_ptr()
-        b.cand, b.cand_i = self._cand.data_ptr(), self._cand_i.data_ptr()
+        b.cand, b.cand_i, b.work = self._cand.data_ptr(), self._cand_i.data_ptr(), self._work.data_ptr()
         b.map_id, b.path_id = self.map_id.data_ptr(), self.path_id.data_ptr()
         b.maps, b.paths = self.map_descs.data_ptr(), self.path_descs.data_ptr()
         b.map_arena, b.tile_arena, b.path_arena = self.map_arena.data_ptr(), self.tile_arena.data_ptr(), self.path_arena.data_ptr()

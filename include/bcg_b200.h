@@ -146,8 +146,9 @@ typedef struct BcgBatch {
   int32_t* init_i;
   double* cand;    /* scratch [9][n_envs]: robot state proposed by the kinematic kernel (7 rows), then
                       this step's reward and new min_dist from the collide/reward kernel            */
-  int32_t* cand_i; /* scratch [7][n_envs]: pixel, angle bin and mask box of the proposed pose, new
-                      target_idx, verdict flags                                                     */
+  int32_t* cand_i; /* scratch [2][n_envs]: new target_idx and verdict flags from the collide/reward kernel */
+  void* work;      /* scratch [n_envs][192 bytes]: per-env work records (map / path / footprint references and
+                      reward inputs) written by the kinematic kernel for the warp-per-env kernels         */
   const int32_t* map_id;  /* [n_envs] index into maps  */
   const int32_t* path_id; /* [n_envs] index into paths */
   const BcgMapDesc* maps;
