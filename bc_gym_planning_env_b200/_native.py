@@ -57,7 +57,7 @@ class BcgBatch(C.Structure):
         ("n_envs", C.c_int32), ("n_frows", C.c_int32), ("n_irows", C.c_int32),
         ("n_maps", C.c_int32), ("n_paths", C.c_int32), ("reserved", C.c_int32),
         ("state_f", C.c_void_p), ("state_i", C.c_void_p), ("init_f", C.c_void_p), ("init_i", C.c_void_p),
-        ("cand", C.c_void_p), ("cand_i", C.c_void_p), ("work", C.c_void_p), ("map_id", C.c_void_p), ("path_id", C.c_void_p),
+        ("cand", C.c_void_p), ("cand_i", C.c_void_p), ("ego_work", C.c_void_p), ("work", C.c_void_p), ("map_id", C.c_void_p), ("path_id", C.c_void_p),
         ("maps", C.c_void_p), ("paths", C.c_void_p),
         ("map_arena", C.c_void_p), ("tile_arena", C.c_void_p), ("path_arena", C.c_void_p),
         ("lut", BcgFootprintLut),

@@ -199,11 +199,172 @@ __global__ void __launch_bounds__(256, 5) collide_reward_kernel(const BcgParams 
   }
 }
 
+// cv2::saturate_cast<int>(double) == cvRound with saturation
+__device__ __forceinline__ int cv_round_sat(double v) {
+  const double r = rint(v);
+  if (r >= 2147483647.0) return 2147483647;
+  if (r <= -2147483648.0) return (-2147483647 - 1);
+  return (int)r;
+}
+
+#define BCG_EGO_MAX 256
+#define BCG_EGO_THREADS 256
+#define BCG_EGO_MAX_TILE_ROWS 384
+
+struct EgoAffine {
+  double a11, a12, b1, a21, a22, b2;   // source = A * (u, v) + b, cv::warpAffine's inverted map
+};
+
+// costmap_utils.py:42-65 + the fp64 inversion cv::warpAffine applies to the float32 forward matrix
+__device__ __forceinline__ EgoAffine ego_affine(const BcgParams& p, const BcgMapDesc& m, double px, double py,
+                                                double pth) {
+  const double cx = (double)world_to_pixel_1d(px, m.origin_x, p.inv_resolution);
+  const double cy = (double)world_to_pixel_1d(py, m.origin_y, p.inv_resolution);
+  const double deg = 180 * pth / BCG_PI;
+  const double rad = deg * (BCG_PI / 180.);
+  double bsn, acs;
+  sincos(rad, &bsn, &acs);
+  const float r00 = (float)acs, r01 = (float)bsn, r02 = (float)((1 - acs) * cx - bsn * cy);
+  const float r10 = (float)(-bsn), r11 = (float)acs, r12 = (float)(bsn * cx + (1 - acs) * cy);
+  const double dsx = rint((p.ego_x0 - (m.origin_x - px)) * p.inv_resolution);
+  const double dsy = rint((p.ego_y0 - (m.origin_y - py)) * p.inv_resolution);
+  const double M0 = (double)r00, M1 = (double)r01, M2 = (double)(r02 - (float)dsx);
+  const double M3 = (double)r10, M4 = (double)r11, M5 = (double)(r12 - (float)dsy);
+  double D = M0 * M4 - M1 * M3;
+  D = (D != 0.0) ? 1. / D : 0.0;
+  EgoAffine a;
+  a.a11 = M4 * D;
+  a.a22 = M0 * D;
+  a.a12 = M1 * (-D);
+  a.a21 = M3 * (-D);
+  a.b1 = -a.a11 * M2 - a.a12 * M5;
+  a.b2 = -a.a21 * M2 - a.a22 * M5;
+  return a;
+}
+
+// goal_n_state (envs/egocentric.py:141-160) by one thread
+__device__ __forceinline__ void write_goal_n_state(const BcgParams& p, const BcgBatch& b, int e, double px, double py,
+                                                   double pth, float* __restrict__ goal_n_state) {
+  const int64_t N = b.n_envs;
+  const double* sf = b.state_f + e;
+  float* g = goal_n_state + (int64_t)e * 9;
+  const BcgPathDesc pd = b.paths[b.path_id[e]];
+  const int target = b.state_i[BCG_I_TARGET * N + e];
+  if (target > pd.n - 1) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) g[k] = 0.f;
+    return;
+  }
+  // from_global_to_egocentric (coordinate_transformations.py:341-362 -> :57-84 -> :310-328)
+  const double* P = b.path_arena + pd.off;
+  const double gx = P[target], gy = P[pd.pitch + target], gt = P[2 * pd.pitch + target];
+  double sn, cs;
+  sincos(pth, &sn, &cs);
+  const double tx = -px * cs - py * sn;
+  const double ty = px * sn - py * cs;
+  const double tt = wrap_angle(-pth);
+  double st, ct;
+  sincos(tt, &st, &ct);
+  const double ex = ct * gx - st * gy + tx;
+  const double ey = st * gx + ct * gy + ty;
+  const double ea = wrap_angle(gt + tt);
+  g[0] = (float)clampd(ex / p.ego_world_w, -1.0, 1.0);
+  g[1] = (float)clampd(ey / p.ego_world_h, -1.0, 1.0);
+  g[2] = (float)ea;
+  g[3] = (float)sf[(BCG_F_DROBOT + 0) * N];
+  g[4] = (float)sf[(BCG_F_DROBOT + 1) * N];
+  g[5] = (float)sf[(BCG_F_DROBOT + 2) * N];
+  g[6] = (float)sf[(BCG_F_DROBOT + 3) * N];
+  g[7] = (float)sf[(BCG_F_DROBOT + 4) * N];
+  g[8] = (float)sf[(BCG_F_DROBOT + 6) * N];
+}
+
+// Per-env record the egocentric kernel starts from, resolved one thread per env (commit / prep kernel):
+// the inverted affine map, the source window and how to stage it.
+struct __align__(16) EgoWork {       // 128 bytes
+  EgoAffine aff;                     // 48
+  int32_t x0, x1, y0, y1;            // source window, not clipped to the map (x0 floored to 16 px for TMA)
+  int32_t cls, mode;                 // TMA box-width class; 0 direct, 1 TMA, 2 plain-load spans
+  int64_t data_off;                  // uint8 cells of the env's map
+  int32_t map_w, map_h, map_pitch, map_id;
+  int32_t pad[8];
+};
+#define BCG_EGO_MODE_DIRECT 0
+#define BCG_EGO_MODE_TMA 1
+#define BCG_EGO_MODE_SPANS 2
+
+__device__ __forceinline__ EgoWork make_ego_work(const BcgParams& p, const BcgBatch& b, int map_id, double px, double py,
+                                                 double pth, int tile_capacity) {
+  const BcgMapDesc m = b.maps[map_id];
+  EgoWork w;
+  w.aff = ego_affine(p, m, px, py, pth);
+  w.data_off = m.data_off;
+  w.map_w = m.width;
+  w.map_h = m.height;
+  w.map_pitch = m.pitch;
+  w.map_id = map_id;
+  w.cls = 0;
+  w.mode = BCG_EGO_MODE_DIRECT;
+  w.x0 = w.x1 = w.y0 = w.y1 = 0;
+  // Source window: every sample is X = floor(x + 0.5 + d), |d| <= 2^-10, of a point x of the rotated crop
+  // rectangle, so the rectangle's corners grown by 0.51 px bound all samples.
+  const EgoAffine& A = w.aff;
+  const double uw = (double)(p.ego_w - 1), vh = (double)(p.ego_h - 1);
+  const double cx[4] = {A.b1, A.a11 * uw + A.b1, A.a11 * uw + A.a12 * vh + A.b1, A.a12 * vh + A.b1};
+  const double cy[4] = {A.b2, A.a21 * uw + A.b2, A.a21 * uw + A.a22 * vh + A.b2, A.a22 * vh + A.b2};
+  const double lim = 1048576.0;
+  const double xlo = fmin(fmin(cx[0], cx[1]), fmin(cx[2], cx[3])), xhi = fmax(fmax(cx[0], cx[1]), fmax(cx[2], cx[3]));
+  const double ylo = fmin(fmin(cy[0], cy[1]), fmin(cy[2], cy[3])), yhi = fmax(fmax(cy[0], cy[1]), fmax(cy[2], cy[3]));
+  const bool sane = p.ego_w <= 128 && xlo > -lim && xhi < lim && ylo > -lim && yhi < lim;   // false for NaN too
+  if (!sane) return w;
+  w.x0 = (int)floor(xlo - 0.51);
+  w.x1 = (int)ceil(xhi + 0.51);
+  w.y0 = (int)floor(ylo - 0.51);
+  w.y1 = (int)ceil(yhi + 0.51);
+  const int bh = w.y1 - w.y0 + 1;
+  w.mode = BCG_EGO_MODE_SPANS;
+  if (b.map_tmaps) {
+    // the innermost start coordinate of a box must land on a 16-byte boundary (misaligned starts raise
+    // an illegal-instruction fault on sm_100a), so the window's left edge is floored to 16 pixels
+    const int x0a = w.x0 & ~15;
+    const int bw = w.x1 - x0a + 1;
+    int cls = 0;
+    while (cls < b.tmap_n_widths && b.tmap_box_w[cls] < bw) ++cls;
+    const int nops = (bh + b.tmap_box_h - 1) / b.tmap_box_h;
+    if (cls < b.tmap_n_widths && nops * b.tmap_box_h * b.tmap_box_w[cls] <= tile_capacity) {
+      w.mode = BCG_EGO_MODE_TMA;
+      w.cls = cls;
+      w.x0 = x0a;
+    }
+  }
+  if (w.mode == BCG_EGO_MODE_SPANS) {
+    const int x0w = w.x0 & ~3;                        // left edge on a 4-byte word
+    const int pitch_w = ((w.x1 - x0w + 1 + 3) >> 2) | 1;
+    if (bh <= BCG_EGO_MAX_TILE_ROWS && (long long)pitch_w * 4 * bh <= tile_capacity) w.x0 = x0w;
+    else w.mode = BCG_EGO_MODE_DIRECT;
+  }
+  return w;
+}
+
+// shared-memory tile the egocentric kernel is launched with (bytes): worst-case source window of the crop
+__host__ __device__ inline int ego_tile_capacity(const BcgParams& p, const BcgBatch& b) {
+  const int side = (int)ceil(sqrt((double)p.ego_w * p.ego_w + (double)p.ego_h * p.ego_h)) + 2;
+  int cap = (side + 1) * ((((side + 3) + 3) / 4) | 1) * 4;
+  if (b.map_tmaps && b.tmap_n_widths >= 1 && b.tmap_box_h > 0) {
+    const int rows = ((side + 1 + b.tmap_box_h - 1) / b.tmap_box_h) * b.tmap_box_h;
+    const int tma_cap = rows * b.tmap_box_w[b.tmap_n_widths - 1];
+    if (tma_cap > cap) cap = tma_cap;
+  }
+  cap = (cap + 127) / 128 * 128;
+  if (cap > 42 * 1024) cap = 42 * 1024;   // larger crops fall back to the direct global gather per CTA
+  return cap;
+}
+
 // One thread per env: the rest of _resolve_state_transition (env.py:363-398) -- rollback, pose and
 // robot-state delay lines, time/iter, sticky collision -- then done (env.py:407-419), episode statistics,
 // auto-reset (env.py:293-303) and the compact fp32 observation.  All accesses are coalesced SoA rows.
 __global__ void __launch_bounds__(128) commit_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L,
-                                                     const BcgStepOut out) {
+                                                     const BcgStepOut out, const int ego_cap) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = e < b.n_envs;
   const int64_t N = b.n_envs;
@@ -293,6 +454,14 @@ __global__ void __launch_bounds__(128) commit_kernel(const BcgParams p, const Bc
       o[0] = make_float4(ov[0], ov[1], ov[2], ov[3]);
       o[1] = make_float4(ov[4], ov[5], ov[6], ov[7]);
       o[2] = make_float4(ov[8], ov[9], ov[10], ov[11]);
+    }
+    // the observation the egocentric kernel will render is that of the state just written: resolve its
+    // affine map, source window and goal vector here, one thread per env
+    if (out.ego_image || out.goal_n_state) {
+      const double opx = sf[(BCG_F_DPOSE + 0) * N], opy = sf[(BCG_F_DPOSE + 1) * N], opth = sf[(BCG_F_DPOSE + 2) * N];
+      if (out.ego_image)
+        reinterpret_cast<EgoWork*>(b.ego_work)[e] = make_ego_work(p, b, b.map_id[e], opx, opy, opth, ego_cap);
+      if (out.goal_n_state) write_goal_n_state(p, b, e, opx, opy, opth, out.goal_n_state);
     }
   }
   // episode statistics: one atomic set per warp that saw an episode end
@@ -407,86 +576,6 @@ __global__ void __launch_bounds__(256, 6) collision_kernel(const BcgBatch b, uin
   }
 }
 
-// cv2::saturate_cast<int>(double) == cvRound with saturation
-__device__ __forceinline__ int cv_round_sat(double v) {
-  const double r = rint(v);
-  if (r >= 2147483647.0) return 2147483647;
-  if (r <= -2147483648.0) return (-2147483647 - 1);
-  return (int)r;
-}
-
-#define BCG_EGO_MAX 256
-#define BCG_EGO_THREADS 256
-#define BCG_EGO_MAX_TILE_ROWS 384
-
-struct EgoAffine {
-  double a11, a12, b1, a21, a22, b2;   // source = A * (u, v) + b, cv::warpAffine's inverted map
-};
-
-// costmap_utils.py:42-65 + the fp64 inversion cv::warpAffine applies to the float32 forward matrix
-__device__ __forceinline__ EgoAffine ego_affine(const BcgParams& p, const BcgMapDesc& m, double px, double py,
-                                                double pth) {
-  const double cx = (double)world_to_pixel_1d(px, m.origin_x, p.inv_resolution);
-  const double cy = (double)world_to_pixel_1d(py, m.origin_y, p.inv_resolution);
-  const double deg = 180 * pth / BCG_PI;
-  const double rad = deg * (BCG_PI / 180.);
-  double bsn, acs;
-  sincos(rad, &bsn, &acs);
-  const float r00 = (float)acs, r01 = (float)bsn, r02 = (float)((1 - acs) * cx - bsn * cy);
-  const float r10 = (float)(-bsn), r11 = (float)acs, r12 = (float)(bsn * cx + (1 - acs) * cy);
-  const double dsx = rint((p.ego_x0 - (m.origin_x - px)) * p.inv_resolution);
-  const double dsy = rint((p.ego_y0 - (m.origin_y - py)) * p.inv_resolution);
-  const double M0 = (double)r00, M1 = (double)r01, M2 = (double)(r02 - (float)dsx);
-  const double M3 = (double)r10, M4 = (double)r11, M5 = (double)(r12 - (float)dsy);
-  double D = M0 * M4 - M1 * M3;
-  D = (D != 0.0) ? 1. / D : 0.0;
-  EgoAffine a;
-  a.a11 = M4 * D;
-  a.a22 = M0 * D;
-  a.a12 = M1 * (-D);
-  a.a21 = M3 * (-D);
-  a.b1 = -a.a11 * M2 - a.a12 * M5;
-  a.b2 = -a.a21 * M2 - a.a22 * M5;
-  return a;
-}
-
-// goal_n_state (envs/egocentric.py:141-160) by one thread
-__device__ __forceinline__ void write_goal_n_state(const BcgParams& p, const BcgBatch& b, int e, double px, double py,
-                                                   double pth, float* __restrict__ goal_n_state) {
-  const int64_t N = b.n_envs;
-  const double* sf = b.state_f + e;
-  float* g = goal_n_state + (int64_t)e * 9;
-  const BcgPathDesc pd = b.paths[b.path_id[e]];
-  const int target = b.state_i[BCG_I_TARGET * N + e];
-  if (target > pd.n - 1) {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) g[k] = 0.f;
-    return;
-  }
-  // from_global_to_egocentric (coordinate_transformations.py:341-362 -> :57-84 -> :310-328)
-  const double* P = b.path_arena + pd.off;
-  const double gx = P[target], gy = P[pd.pitch + target], gt = P[2 * pd.pitch + target];
-  double sn, cs;
-  sincos(pth, &sn, &cs);
-  const double tx = -px * cs - py * sn;
-  const double ty = px * sn - py * cs;
-  const double tt = wrap_angle(-pth);
-  double st, ct;
-  sincos(tt, &st, &ct);
-  const double ex = ct * gx - st * gy + tx;
-  const double ey = st * gx + ct * gy + ty;
-  const double ea = wrap_angle(gt + tt);
-  g[0] = (float)clampd(ex / p.ego_world_w, -1.0, 1.0);
-  g[1] = (float)clampd(ey / p.ego_world_h, -1.0, 1.0);
-  g[2] = (float)ea;
-  g[3] = (float)sf[(BCG_F_DROBOT + 0) * N];
-  g[4] = (float)sf[(BCG_F_DROBOT + 1) * N];
-  g[5] = (float)sf[(BCG_F_DROBOT + 2) * N];
-  g[6] = (float)sf[(BCG_F_DROBOT + 3) * N];
-  g[7] = (float)sf[(BCG_F_DROBOT + 4) * N];
-  g[8] = (float)sf[(BCG_F_DROBOT + 6) * N];
-}
-
 // x-extent of a convex quad within the horizontal band [ylo, yhi]; extremes lie on the boundary
 __device__ __forceinline__ void quad_band_extent(const double qx[4], const double qy[4], double ylo, double yhi,
                                                  double& xmin, double& xmax) {
@@ -558,18 +647,19 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
 // shift, then cv2.warpAffine(INTER_NEAREST, borderValue=0): fp64 inverse and 10-bit fixed-point source
 // coordinates X = (rint(A11 u 2^10) + rint((A12 v + b1) 2^10) + 512) >> 10.
 //
-// One CTA per env.  The source pixels of the crop lie in a rotated rectangle whose bounding box is
-// staged into shared memory, zero outside the map (= borderValue); the rotated gather then runs out of
-// shared memory with no bounds checks.  Two ways to stage:
-//   * TMA (b.map_tmaps set): one thread issues ceil(rows / box_h) cp.async.bulk.tensor.2d box loads on an
-//     mbarrier; the copy engine does the address generation and the out-of-map zero fill;
+// One CTA per env, starting from the env's EgoWork record (affine map + source window, resolved one
+// thread per env by the commit / prep kernel).  The source pixels of the crop lie in a rotated rectangle
+// whose bounding box is staged into shared memory, zero outside the map (= borderValue); the rotated
+// gather then runs out of shared memory with no bounds checks.  Two ways to stage:
+//   * TMA (b.map_tmaps set): thread 0 issues ceil(rows / box_h) cp.async.bulk.tensor.2d box loads on an
+//     mbarrier right away; the copy engine does the address generation and the out-of-map zero fill
+//     while the CTA builds its fixed-point tables;
 //   * plain loads: per source row only the span of the rotated rectangle (grown by the 0.501 px the
 //     fixed-point rounding can move a sample) is loaded with coalesced 4-byte words.
-// Tile pitches: 208 B for TMA boxes, 4 * odd otherwise -- both measured at < 2 shared-memory wavefronts
-// per gather averaged over crop angles.
+// Tile pitches: 144/176/208 B for TMA boxes, 4 * odd otherwise -- all measured at < 2 shared-memory
+// wavefronts per gather averaged over crop angles.
 __global__ void __launch_bounds__(BCG_EGO_THREADS, 5) ego_kernel(const BcgParams p, const BcgBatch b,
                                                                  uint8_t* __restrict__ image,
-                                                                 float* __restrict__ goal_n_state,
                                                                  const int tile_capacity) {
   extern __shared__ __align__(128) uint8_t tile_raw[];
   // TMA destinations must be 128-byte aligned; the launch reserves the slack
@@ -577,63 +667,30 @@ __global__ void __launch_bounds__(BCG_EGO_THREADS, 5) ego_kernel(const BcgParams
   __shared__ int adx[BCG_EGO_MAX], ady[BCG_EGO_MAX], bdx[BCG_EGO_MAX], bdy[BCG_EGO_MAX];
   // per-row spans of the plain-load path live behind the tile (that path never needs the whole capacity)
   short2* const span = reinterpret_cast<short2*>(tile + tile_capacity);
-  __shared__ EgoAffine aff_s;
-  __shared__ int box[6];   // source window x0, x1, y0, y1 (not clipped to the map); TMA width class; mode
   __shared__ __align__(8) uint64_t mbar_s;
   const int e = blockIdx.x;
-  const int64_t N = b.n_envs;
-  const double* sf = b.state_f + e;
-  const int map_id = b.map_id[e];
-  const BcgMapDesc m = b.maps[map_id];
-  const double px = sf[(BCG_F_DPOSE + 0) * N], py = sf[(BCG_F_DPOSE + 1) * N], pth = sf[(BCG_F_DPOSE + 2) * N];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const uint32_t mbar = smem_u32(&mbar_s);
-  enum { MODE_DIRECT = 0, MODE_TMA = 1, MODE_SPANS = 2 };
+  const EgoWork w = reinterpret_cast<const EgoWork*>(b.ego_work)[e];     // warp-uniform 128-byte read
+  const EgoAffine A = w.aff;
+  int mode = w.mode;
+  const int X0 = w.x0, Y0 = w.y0;
+  const int bh = w.y1 - Y0 + 1;
+  int pitch_b = 0;
 
-  if (threadIdx.x == 0) {
-    const EgoAffine A0 = ego_affine(p, m, px, py, pth);
-    aff_s = A0;
-    // Source window: every sample is X = floor(x + 0.5 + d), |d| <= 2^-10, of a point x of the rotated crop
-    // rectangle, so the rectangle's corners grown by 0.51 px bound all samples.
-    const double uw = (double)(p.ego_w - 1), vh = (double)(p.ego_h - 1);
-    const double cx[4] = {A0.b1, A0.a11 * uw + A0.b1, A0.a11 * uw + A0.a12 * vh + A0.b1, A0.a12 * vh + A0.b1};
-    const double cy[4] = {A0.b2, A0.a21 * uw + A0.b2, A0.a21 * uw + A0.a22 * vh + A0.b2, A0.a22 * vh + A0.b2};
-    const double lim = 1048576.0;
-    const double xlo = fmin(fmin(cx[0], cx[1]), fmin(cx[2], cx[3])), xhi = fmax(fmax(cx[0], cx[1]), fmax(cx[2], cx[3]));
-    const double ylo = fmin(fmin(cy[0], cy[1]), fmin(cy[2], cy[3])), yhi = fmax(fmax(cy[0], cy[1]), fmax(cy[2], cy[3]));
-    const bool sane = p.ego_w <= 128 && xlo > -lim && xhi < lim && ylo > -lim && yhi < lim;   // false for NaN too
-    int mode = MODE_DIRECT, cls = 0;
-    if (sane) {
-      const int x0 = (int)floor(xlo - 0.51), x1 = (int)ceil(xhi + 0.51);
-      const int y0 = (int)floor(ylo - 0.51), y1 = (int)ceil(yhi + 0.51);
-      box[0] = x0; box[1] = x1; box[2] = y0; box[3] = y1;
-      const int bh = y1 - y0 + 1;
-      mode = MODE_SPANS;
-      if (b.map_tmaps) {
-        // the innermost start coordinate of a box must land on a 16-byte boundary (misaligned starts raise
-        // an illegal-instruction fault on sm_100a), so the window's left edge is floored to 16 pixels
-        const int x0a = x0 & ~15;
-        const int bw = x1 - x0a + 1;
-        while (cls < b.tmap_n_widths && b.tmap_box_w[cls] < bw) ++cls;
-        const int nops = (bh + b.tmap_box_h - 1) / b.tmap_box_h;
-        if (cls < b.tmap_n_widths && nops * b.tmap_box_h * b.tmap_box_w[cls] <= tile_capacity) {
-          mode = MODE_TMA;
-          box[0] = x0a;
-          const int box_bytes = b.tmap_box_w[cls] * b.tmap_box_h;
-          const uint8_t* tmap = reinterpret_cast<const uint8_t*>(b.map_tmaps) + ((int64_t)map_id * b.tmap_n_widths + cls) * 128;
-          mbar_init(mbar, 1);
-          mbar_expect_tx(mbar, (uint32_t)(nops * box_bytes));
-          const uint32_t t0 = smem_u32(tile);
-          for (int k = 0; k < nops; ++k) tma_load_2d(t0 + k * box_bytes, tmap, x0a, y0 + k * b.tmap_box_h, mbar);
-        }
-      }
+  if (mode == BCG_EGO_MODE_TMA) {
+    pitch_b = b.tmap_box_w[w.cls];
+    if (threadIdx.x == 0) {
+      const int nops = (bh + b.tmap_box_h - 1) / b.tmap_box_h;
+      const int box_bytes = pitch_b * b.tmap_box_h;
+      const uint8_t* tmap = reinterpret_cast<const uint8_t*>(b.map_tmaps) + ((int64_t)w.map_id * b.tmap_n_widths + w.cls) * 128;
+      mbar_init(mbar, 1);
+      mbar_expect_tx(mbar, (uint32_t)(nops * box_bytes));
+      const uint32_t t0 = smem_u32(tile);
+      for (int k = 0; k < nops; ++k) tma_load_2d(t0 + k * box_bytes, tmap, X0, Y0 + k * b.tmap_box_h, mbar);
     }
-    box[4] = cls;
-    box[5] = mode;
   }
-  __syncthreads();
   // the copy engine is now filling the tile; meanwhile every thread builds the fixed-point tables
-  const EgoAffine A = aff_s;
   for (int t = threadIdx.x; t < p.ego_w; t += blockDim.x) {
     adx[t] = cv_round_sat(A.a11 * t * 1024);
     ady[t] = cv_round_sat(A.a21 * t * 1024);
@@ -642,60 +699,47 @@ __global__ void __launch_bounds__(BCG_EGO_THREADS, 5) ego_kernel(const BcgParams
     bdx[t] = cv_round_sat((A.a12 * t + A.b1) * 1024) + 512;
     bdy[t] = cv_round_sat((A.a22 * t + A.b2) * 1024) + 512;
   }
-  int mode = box[5];
-  int X0 = box[0];
-  const int Y0 = box[2];
-  const int bh = box[3] - Y0 + 1;
-  int pitch_b = 0;
-  const uint8_t* src = b.map_arena + m.data_off;
+  const uint8_t* src = b.map_arena + w.data_off;
   const int npx = p.ego_w * p.ego_h;
   uint8_t* dst = image + (int64_t)e * npx;
-  if (mode == MODE_TMA) {
-    pitch_b = b.tmap_box_w[box[4]];
-  } else if (mode == MODE_SPANS) {
+  if (mode == BCG_EGO_MODE_SPANS) {
     // ---- plain-load staging: per-row span of the rotated crop rectangle ------------------------------------
-    X0 &= ~3;                                        // left edge on a 4-byte word
-    const int bw = box[1] - X0 + 1;
+    const int bw = w.x1 - X0 + 1;                     // X0 is a multiple of 4 here
     const int pitch_w = ((bw + 3) >> 2) | 1;          // words per tile row, odd
-    if (bh <= BCG_EGO_MAX_TILE_ROWS && (long long)pitch_w * 4 * bh <= tile_capacity) {
-      pitch_b = pitch_w * 4;
-      const double uw = (double)(p.ego_w - 1), vh = (double)(p.ego_h - 1);
-      const double qx[4] = {A.b1, A.a11 * uw + A.b1, A.a11 * uw + A.a12 * vh + A.b1, A.a12 * vh + A.b1};
-      const double qy[4] = {A.b2, A.a21 * uw + A.b2, A.a21 * uw + A.a22 * vh + A.b2, A.a22 * vh + A.b2};
-      for (int y = threadIdx.x; y < bh; y += blockDim.x) {
-        double xmin, xmax;
-        quad_band_extent(qx, qy, (double)(Y0 + y) - 0.51, (double)(Y0 + y) + 0.51, xmin, xmax);
-        int xs = 1, xe = 0;
-        if (xmin <= xmax) {
-          xs = max((int)floor(xmin - 0.51) - X0, 0);
-          xe = min((int)ceil(xmax + 0.51) - X0, bw - 1);
-        }
-        span[y] = make_short2((short)xs, (short)xe);
+    pitch_b = pitch_w * 4;
+    const double uw = (double)(p.ego_w - 1), vh = (double)(p.ego_h - 1);
+    const double qx[4] = {A.b1, A.a11 * uw + A.b1, A.a11 * uw + A.a12 * vh + A.b1, A.a12 * vh + A.b1};
+    const double qy[4] = {A.b2, A.a21 * uw + A.b2, A.a21 * uw + A.a22 * vh + A.b2, A.a22 * vh + A.b2};
+    for (int y = threadIdx.x; y < bh; y += blockDim.x) {
+      double xmin, xmax;
+      quad_band_extent(qx, qy, (double)(Y0 + y) - 0.51, (double)(Y0 + y) + 0.51, xmin, xmax);
+      int xs = 1, xe = 0;
+      if (xmin <= xmax) {
+        xs = max((int)floor(xmin - 0.51) - X0, 0);
+        xe = min((int)ceil(xmax + 0.51) - X0, bw - 1);
       }
-      __syncthreads();
-      uint32_t* tw = reinterpret_cast<uint32_t*>(tile);
-      for (int y = warp; y < bh; y += nwarp) {
-        const short2 sp = span[y];
-        if (sp.x > sp.y) continue;
-        const int Ys = Y0 + y;
-        const bool row_in = Ys >= 0 && Ys < m.height;
-        // X0 is a multiple of 4 and the row pitch of 32: word loads are aligned and never straddle the map edge
-        const uint32_t* srow = reinterpret_cast<const uint32_t*>(src + (int64_t)(row_in ? Ys : 0) * m.pitch);
-        for (int xw = (sp.x >> 2) + lane; xw <= (sp.y >> 2); xw += 32) {
-          const int Xs = X0 + (xw << 2);
-          uint32_t word = 0u;
-          if (row_in && Xs >= 0 && Xs < m.pitch) word = __ldg(srow + (Xs >> 2));
-          tw[y * pitch_w + xw] = word;
-        }
+      span[y] = make_short2((short)xs, (short)xe);
+    }
+    __syncthreads();
+    uint32_t* tw = reinterpret_cast<uint32_t*>(tile);
+    for (int y = warp; y < bh; y += nwarp) {
+      const short2 sp = span[y];
+      if (sp.x > sp.y) continue;
+      const int Ys = Y0 + y;
+      const bool row_in = Ys >= 0 && Ys < w.map_h;
+      // X0 is a multiple of 4 and the row pitch of 32: word loads are aligned and never straddle the map edge
+      const uint32_t* srow = reinterpret_cast<const uint32_t*>(src + (int64_t)(row_in ? Ys : 0) * w.map_pitch);
+      for (int xw = (sp.x >> 2) + lane; xw <= (sp.y >> 2); xw += 32) {
+        const int Xs = X0 + (xw << 2);
+        uint32_t word = 0u;
+        if (row_in && Xs >= 0 && Xs < w.map_pitch) word = __ldg(srow + (Xs >> 2));
+        tw[y * pitch_w + xw] = word;
       }
-    } else {
-      mode = MODE_DIRECT;
     }
   }
-  __syncthreads();                       // tables (and the plain-load tile) are complete
-  if (mode == MODE_TMA) mbar_wait(mbar, 0);
-  const bool staged = mode != MODE_DIRECT;
-  if (staged) {
+  __syncthreads();                       // tables (and the plain-load tile) are complete, the mbarrier is initialised
+  if (mode == BCG_EGO_MODE_TMA) mbar_wait(mbar, 0);
+  if (mode != BCG_EGO_MODE_DIRECT) {
     // ---- gather: warp w takes crop rows w, w+8, ...; lane l takes columns l, l+32, l+64, l+96 -----------
     int ax[4], ay[4];
 #pragma unroll
@@ -717,27 +761,28 @@ __global__ void __launch_bounds__(BCG_EGO_THREADS, 5) ego_kernel(const BcgParams
         if (k < n_full || lane + 32 * k < p.ego_w) drow[32 * k] = (uint8_t)val;
       }
     }
-  } else if (image) {
+  } else {
     // generic path (huge crops / poses far outside any sane range): direct, bounds-checked global gather
     for (int i = threadIdx.x; i < npx; i += blockDim.x) {
       const int v = i / p.ego_w, u = i - v * p.ego_w;
       const long long X = ((long long)adx[u] + bdx[v]) >> 10, Y = ((long long)ady[u] + bdy[v]) >> 10;
       uint8_t val = 0;
-      if (X >= 0 && X < m.width && Y >= 0 && Y < m.height) val = __ldg(src + Y * m.pitch + X);
+      if (X >= 0 && X < w.map_w && Y >= 0 && Y < w.map_h) val = __ldg(src + Y * w.map_pitch + X);
       dst[i] = val;
     }
   }
-  if (goal_n_state && threadIdx.x == 0) write_goal_n_state(p, b, e, px, py, pth, goal_n_state);
 }
 
-// goal_n_state only (no image requested): one thread per env
-__global__ void __launch_bounds__(128) goal_kernel(const BcgParams p, const BcgBatch b, float* __restrict__ goal_n_state) {
+// EgoWork records and / or goal_n_state from the current state (stand-alone bcg_observe_ego): one thread per env
+__global__ void __launch_bounds__(128) ego_prep_kernel(const BcgParams p, const BcgBatch b, const int want_image,
+                                                       float* __restrict__ goal_n_state, const int ego_cap) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= b.n_envs) return;
   const int64_t N = b.n_envs;
   const double* sf = b.state_f + e;
-  write_goal_n_state(p, b, e, sf[(BCG_F_DPOSE + 0) * N], sf[(BCG_F_DPOSE + 1) * N], sf[(BCG_F_DPOSE + 2) * N],
-                     goal_n_state);
+  const double px = sf[(BCG_F_DPOSE + 0) * N], py = sf[(BCG_F_DPOSE + 1) * N], pth = sf[(BCG_F_DPOSE + 2) * N];
+  if (want_image) reinterpret_cast<EgoWork*>(b.ego_work)[e] = make_ego_work(p, b, b.map_id[e], px, py, pth, ego_cap);
+  if (goal_n_state) write_goal_n_state(p, b, e, px, py, pth, goal_n_state);
 }
 
 __global__ void __launch_bounds__(256) gather_kernel(const BcgBatch b, const int64_t* __restrict__ idx, const int k,
@@ -899,27 +944,20 @@ int bcg_kinematic_step(const BcgParams* p, const BcgBatch* b, const void* action
   return BCG_OK;
 }
 
-static int launch_ego(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, float* goal_n_state, cudaStream_t s) {
+static int check_ego(const BcgParams* p, const BcgBatch* b, const uint8_t* ego_image) {
   BCG_REQUIRE(p->ego_w > 0 && p->ego_h > 0 && p->ego_w <= BCG_EGO_MAX && p->ego_h <= BCG_EGO_MAX,
               "egocentric crop must be 1..256 pixels per side");
-  if (ego_image) {
-    // bounding box of the rotated crop: at most ceil(hypot(w, h)) + 2 rows of (that + 7) bytes, pitch 4 * odd
-    const int side = (int)ceil(sqrt((double)p->ego_w * p->ego_w + (double)p->ego_h * p->ego_h)) + 2;
-    int cap = (side + 1) * ((((side + 3) + 3) / 4) | 1) * 4;
-    if (b->map_tmaps) {
-      BCG_REQUIRE(b->tmap_n_widths >= 1 && b->tmap_n_widths <= 4 && b->tmap_box_h > 0, "tensor-map boxes not set");
-      const int rows = ((side + 1 + b->tmap_box_h - 1) / b->tmap_box_h) * b->tmap_box_h;
-      const int tma_cap = rows * b->tmap_box_w[b->tmap_n_widths - 1];
-      if (tma_cap > cap) cap = tma_cap;
-    }
-    cap = (cap + 127) / 128 * 128;
-    if (cap > 42 * 1024) cap = 42 * 1024;   // larger crops fall back to the direct global gather per CTA
-    // alignment slack + the per-row spans of the plain-load path, which live behind the tile
-    const int extra = 128 + BCG_EGO_MAX_TILE_ROWS * (int)sizeof(short2);
-    ego_kernel<<<b->n_envs, BCG_EGO_THREADS, cap + extra, s>>>(*p, *b, ego_image, goal_n_state, cap);
-  } else {
-    goal_kernel<<<blocks_for(b->n_envs, 128), 128, 0, s>>>(*p, *b, goal_n_state);
-  }
+  if (ego_image) BCG_REQUIRE(b->ego_work, "BcgBatch.ego_work is needed for the egocentric image");
+  if (b->map_tmaps) BCG_REQUIRE(b->tmap_n_widths >= 1 && b->tmap_n_widths <= 4 && b->tmap_box_h > 0, "tensor-map boxes not set");
+  return BCG_OK;
+}
+
+// the image kernel; the EgoWork records must already be in b->ego_work
+static int launch_ego_image(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, cudaStream_t s) {
+  const int cap = ego_tile_capacity(*p, *b);
+  // alignment slack + the per-row spans of the plain-load path, which live behind the tile
+  const int extra = 128 + BCG_EGO_MAX_TILE_ROWS * (int)sizeof(short2);
+  ego_kernel<<<b->n_envs, BCG_EGO_THREADS, cap + extra, s>>>(*p, *b, ego_image, cap);
   BCG_CHECK_CUDA(cudaGetLastError());
   return BCG_OK;
 }
@@ -927,7 +965,13 @@ static int launch_ego(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image,
 int bcg_observe_ego(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, float* goal_n_state, void* stream) {
   if (int rc = check_batch(p, b)) return rc;
   BCG_REQUIRE(ego_image || goal_n_state, "nothing to compute");
-  return launch_ego(p, b, ego_image, goal_n_state, (cudaStream_t)stream);
+  if (int rc = check_ego(p, b, ego_image)) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  ego_prep_kernel<<<blocks_for(b->n_envs, 128), 128, 0, s>>>(*p, *b, ego_image ? 1 : 0, goal_n_state,
+                                                            ego_tile_capacity(*p, *b));
+  BCG_CHECK_CUDA(cudaGetLastError());
+  if (ego_image) return launch_ego_image(p, b, ego_image, s);
+  return BCG_OK;
 }
 
 int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, int32_t action_is_f64,
@@ -935,6 +979,9 @@ int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, 
   if (int rc = check_batch(p, b)) return rc;
   BCG_REQUIRE(actions && out, "null actions/out");
   const bool ego = out->ego_image || out->goal_n_state;
+  if (ego) {
+    if (int rc = check_ego(p, b, out->ego_image)) return rc;
+  }
   cudaStream_t s = (cudaStream_t)stream;
   const BcgStateLayout L = make_layout(*p);
   if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[0], s));
@@ -944,11 +991,11 @@ int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, 
   collide_reward_kernel<<<blocks_for((int64_t)b->n_envs * 32, 256), 256, 0, s>>>(*p, *b);
   BCG_CHECK_CUDA(cudaGetLastError());
   if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[2], s));
-  commit_kernel<<<blocks_for(b->n_envs, 128), 128, 0, s>>>(*p, *b, L, *out);
+  commit_kernel<<<blocks_for(b->n_envs, 128), 128, 0, s>>>(*p, *b, L, *out, ego ? ego_tile_capacity(*p, *b) : 0);
   BCG_CHECK_CUDA(cudaGetLastError());
   if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[3], s));
-  if (ego) {
-    if (int rc = launch_ego(p, b, out->ego_image, out->goal_n_state, s)) return rc;
+  if (out->ego_image) {
+    if (int rc = launch_ego_image(p, b, out->ego_image, s)) return rc;
   }
   if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[4], s));
   return BCG_OK;

@@ -270,6 +270,7 @@ class VecPlanEnv(object):
         self._cand = torch.zeros((9, n), dtype=torch.float64, device=dev)
         self._cand_i = torch.zeros((2, n), dtype=torch.int32, device=dev)
         self._work = torch.zeros((n, 192), dtype=torch.uint8, device=dev)
+        self._ego_work = torch.zeros((n, 128), dtype=torch.uint8, device=dev)
         self._status = torch.zeros(nat.STATUS_WORDS, dtype=torch.int32, device=dev)
         self._stats = torch.zeros(nat.STATS_WORDS, dtype=torch.float64, device=dev)
         self.reward = torch.zeros(n, dtype=torch.float64, device=dev)
@@ -290,6 +291,7 @@ class VecPlanEnv(object):
         b.state_f, b.state_i = self.state_f.data_ptr(), self.state_i.data_ptr()
         b.init_f, b.init_i = self.init_f.data_ptr(), self.init_i.data_ptr()
         b.cand, b.cand_i, b.work = self._cand.data_ptr(), self._cand_i.data_ptr(), self._work.data_ptr()
+        b.ego_work = self._ego_work.data_ptr()
         b.map_id, b.path_id = self.map_id.data_ptr(), self.path_id.data_ptr()
         b.maps, b.paths = self.map_descs.data_ptr(), self.path_descs.data_ptr()
         b.map_arena, b.tile_arena, b.path_arena = self.map_arena.data_ptr(), self.tile_arena.data_ptr(), self.path_arena.data_ptr()

@@ -147,6 +147,9 @@ typedef struct BcgBatch {
   double* cand;    /* scratch [9][n_envs]: robot state proposed by the kinematic kernel (7 rows), then
                       this step's reward and new min_dist from the collide/reward kernel            */
   int32_t* cand_i; /* scratch [2][n_envs]: new target_idx and verdict flags from the collide/reward kernel */
+  void* ego_work;  /* scratch [n_envs][128 bytes]: per-env affine map + source window of the egocentric crop,
+                      written by the commit kernel (or bcg_observe_ego) for the egocentric kernel; may be
+                      NULL when no egocentric image is ever requested                                      */
   void* work;      /* scratch [n_envs][192 bytes]: per-env work records (map / path / footprint references and
                       reward inputs) written by the kinematic kernel for the warp-per-env kernels         */
   const int32_t* map_id;  /* [n_envs] index into maps  */
