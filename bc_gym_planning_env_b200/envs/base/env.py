@@ -47,6 +47,23 @@ class ContinuousRewardProviderState(object):
     def done(self):
         return self.target_idx > len(self.path) - 1
 
+    def get_reward_provider_state_type_name(self):
+        return self.reward_provider_state_type_name
+
+    def serialize(self):
+        return dict(min_spat_dist_so_far=self.min_spat_dist_so_far, path=self.path, target_idx=self.target_idx,
+                    version=self.VERSION)
+
+    @classmethod
+    def deserialize(cls, state):
+        state = dict(state)
+        assert state.pop('version') == cls.VERSION
+        return cls(**state)
+
+
+CONTINUOUS_REWARD_STATE = 'continuous_reward_state'      # reference reward_provider_examples.py
+ContinuousRewardProviderState.reward_provider_state_type_name = CONTINUOUS_REWARD_STATE
+
 
 @attr.s(eq=False)
 class State(object):
@@ -90,6 +107,39 @@ class State(object):
     def __ne__(self, other):
         return not self.__eq__(other)
 
+    # Wire format: a dict of basic types that pickles, with the reference's keys (envs/base/env.py:139-176).
+    # (The reference writes 'reward_provider_state_type_name' but reads 'reward_provider_state_name' and
+    # leaves queue items without a version; both spellings are accepted here and every item is versioned.)
+    def serialize(self):
+        return dict(
+            version=self.VERSION,
+            reward_provider_state_type_name=self.reward_provider_state.get_reward_provider_state_type_name(),
+            reward_provider_state=self.reward_provider_state.serialize(),
+            path=self.path, original_path=self.original_path, costmap=self.costmap.get_state(),
+            iter_timeout=self.iter_timeout, current_time=self.current_time, current_iter=self.current_iter,
+            robot_collided=self.robot_collided,
+            poses_queue=[np.array(p) for p in self.poses_queue],
+            robot_state_queue=[s.serialize() for s in self.robot_state_queue],
+            control_queue=[a.serialize() for a in self.control_queue],
+            pose=self.pose, robot_type_name=self.robot_state.get_robot_type_name(),
+            robot_state=self.robot_state.serialize())
+
+    @classmethod
+    def deserialize(cls, state):
+        state = dict(state)
+        assert state.pop('version') == cls.VERSION
+        name = state.pop('reward_provider_state_type_name', None) or state.pop('reward_provider_state_name', None)
+        if name != CONTINUOUS_REWARD_STATE:
+            raise AssertionError("Unknown reward provider state {}".format(name))
+        state.pop('reward_provider_state_name', None)
+        state['reward_provider_state'] = ContinuousRewardProviderState.deserialize(state['reward_provider_state'])
+        state['costmap'] = CostMap2D.from_state(state['costmap'])
+        rs_type = robot_state_type(state.pop('robot_type_name'))
+        state['robot_state'] = rs_type.deserialize(state['robot_state'])
+        state['robot_state_queue'] = [rs_type.deserialize(s) for s in state['robot_state_queue']]
+        state['control_queue'] = [Action.deserialize(a) for a in state['control_queue']]
+        return cls(**state)
+
 
 class _RobotView(object):
     """The slice of TricycleRobot's interface that scripts written for the reference poke at
@@ -126,6 +176,7 @@ class PlanEnv(object):
         :param seed int: Philox key of the noise stream (the reference uses the global np.random)
         """
         self._params = params
+        self._noise_kwargs = dict(noise_parameters=noise_parameters, seed=seed)
         self._vec = VecPlanEnv([costmap], [path], params, n_envs=1, noise_parameters=noise_parameters, seed=seed,
                                device=device)
         self._robot = _RobotView(self)
@@ -157,6 +208,28 @@ class PlanEnv(object):
         """No-op like the reference (env.py:325-332): the base env is deterministic given its noise key."""
         pass
 
+    VERSION = 1
+
+    def serialize(self):
+        """Dict of basic types, reference keys (envs/base/env.py:251-261): pickle it to checkpoint the env."""
+        state = self.get_state()
+        return dict(version=self.VERSION, state=state.serialize(), params=self._params.serialize(),
+                    path=state.original_path, costmap=state.costmap.get_state(),
+                    noise=self._noise_kwargs)             # extension: the odometry-noise setting and Philox key
+
+    @classmethod
+    def deserialize(cls, state):
+        """Rebuild an env and put it in the serialized state (envs/base/env.py:263-276).  The path in the
+        dict is the already refined one, so it is not refined again."""
+        state = dict(state)
+        assert state.pop('version') == cls.VERSION
+        params = EnvParams.deserialize(state['params'])
+        noise = state.get('noise') or dict(noise_parameters=DEFAULT_NOISE, seed=0)
+        env = cls(CostMap2D.from_state(state['costmap']), state['path'], attr.evolve(params, refine_path=False), **noise)
+        env._params = params
+        env.set_state(State.deserialize(state['state']))
+        return env
+
     def render(self, mode='human'):
         raise NotImplementedError("rendering is outside the B200 step path (reference envs/base/draw.py)")
 
@@ -165,6 +238,7 @@ class PlanEnv(object):
 
     # ---- conversions -----------------------------------------------------------------------------
     def _set_noise(self, noise_parameters):
+        self._noise_kwargs = dict(self._noise_kwargs, noise_parameters=noise_parameters)
         v = self._vec
         v._c_params.noise_on = 0 if noise_parameters is None else 1
         if noise_parameters is not None:

@@ -120,6 +120,18 @@ class Observation(object):
     robot_state = attr.ib(type=object)              # (delayed) robot state record
     VERSION = 1
 
+    def __eq__(self, other):
+        """Field-wise equality like the reference (envs/base/obs.py:99-122)."""
+        return (isinstance(other, Observation) and np.shape(self.pose) == np.shape(other.pose)
+                and bool((np.asarray(self.pose) == np.asarray(other.pose)).all())
+                and np.shape(self.path) == np.shape(other.path)
+                and bool((np.asarray(self.path) == np.asarray(other.path)).all())
+                and self.costmap == other.costmap and self.time == other.time and self.dt == other.dt
+                and self.robot_state == other.robot_state)
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
     def serialize(self):
         return dict(pose=self.pose, path=self.path, costmap=self.costmap.get_state(), time=self.time, dt=self.dt,
                     robot_state=self.robot_state.serialize(), robot_type_name=self.robot_state.get_robot_type_name(),

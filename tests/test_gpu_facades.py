@@ -87,3 +87,32 @@ def test_plan_env_raises_like_the_reference():
     cm = CostMap2D(np.zeros((50, 50), np.uint8), 0.03, np.array([0., 0.]))
     with pytest.raises(ValueError, match="Goal pose too close to initial pose"):
         PlanEnv(cm, np.array([[0.5, 0.5, 0.], [0.6, 0.5, 0.]]), EnvParams())          # reward.py:275-277
+
+
+def test_save_n_load_identity():
+    """The reference's serialization contract (scripts/env_runners/save_n_load_checks.py:16-71): serialize to a
+    dict of basic types, pickle, unpickle, deserialize -- state, observation, reward and done of the clone stay
+    equal to the original's for 100 steps."""
+    import pickle
+    from bc_gym_planning_env_b200.envs.synth_turn_env import AisleTurnEnv, AisleTurnEnvParams, TurnParams
+
+    def roundtrip(thing, the_class):
+        return the_class.deserialize(pickle.loads(pickle.dumps(thing.serialize(), protocol=pickle.HIGHEST_PROTOCOL)))
+
+    # state_delay stays 0: a State carries only the *delayed* robot state (env.py:52-68, :284), so with a state
+    # delay neither the reference nor this port can resume the true robot from a saved State
+    cfg = AisleTurnEnvParams(turn_params=TurnParams(), env_params=EnvParams(control_delay=2, pose_delay=1, state_delay=0))
+    env = AisleTurnEnv(cfg, noise_parameters=None)
+    env.reset()
+    for _ in range(7):                       # so that the queues are not empty when the env is saved
+        env.step(env.action_space.sample())
+    env_two = roundtrip(env, PlanEnv)
+    for action in [env.action_space.sample() for _ in range(100)]:
+        assert env.get_state() == env_two.get_state()
+        obs1, r1, done1, _ = env.step(action)
+        obs2, r2, done2, _ = env_two.step(action)
+        obs3 = roundtrip(obs2, Observation)
+        assert env.get_state() == env_two.get_state()
+        assert obs1 == obs2 and obs1 == obs3 and r1 == r2 and done1 == done2
+    state = env.get_state()
+    assert roundtrip(state, State) == state
