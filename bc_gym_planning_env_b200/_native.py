@@ -24,7 +24,7 @@ class BcgParams(C.Structure):
         ("robot_kind", C.c_int32), ("noise_on", C.c_int32),
         ("delay_control", C.c_int32), ("delay_pose", C.c_int32), ("delay_state", C.c_int32),
         ("iteration_timeout", C.c_int32), ("ego_w", C.c_int32), ("ego_h", C.c_int32),
-        ("auto_reset", C.c_int32), ("reserved", C.c_int32),
+        ("auto_reset", C.c_int32), ("ego_variant", C.c_int32),
     ]
 
 

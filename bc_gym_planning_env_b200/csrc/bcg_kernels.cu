@@ -257,7 +257,8 @@ __device__ __forceinline__ void write_goal_n_state(const BcgParams& p, const Bcg
   }
   // from_global_to_egocentric (coordinate_transformations.py:341-362 -> :57-84 -> :310-328)
   const double* P = b.path_arena + pd.off;
-  const double gx = P[target], gy = P[pd.pitch + target], gt = P[2 * pd.pitch + target];
+  const int gi = p.ego_variant == 1 ? pd.n - 1 : target;      // last path point vs next way point
+  const double gx = P[gi], gy = P[pd.pitch + gi], gt = P[2 * pd.pitch + gi];
   double sn, cs;
   sincos(pth, &sn, &cs);
   const double tx = -px * cs - py * sn;
@@ -268,6 +269,18 @@ __device__ __forceinline__ void write_goal_n_state(const BcgParams& p, const Bcg
   const double ex = ct * gx - st * gy + tx;
   const double ey = st * gx + ct * gy + ty;
   const double ea = wrap_angle(gt + tt);
+  if (p.ego_variant == 1) {
+    // synth_turn_env.py:412-418: goal / crop world size, scaled to unit length; then (v, w, wheel)
+    const double nx = ex / p.ego_world_w, ny = ey / p.ego_world_h;
+    const double nrm = sqrt(nx * nx + ny * ny);
+    g[0] = (float)(nx / nrm);
+    g[1] = (float)(ny / nrm);
+    g[2] = (float)sf[(BCG_F_DROBOT + 3) * N];
+    g[3] = (float)sf[(BCG_F_DROBOT + 4) * N];
+    g[4] = (float)sf[(BCG_F_DROBOT + 6) * N];
+    g[5] = g[6] = g[7] = g[8] = 0.f;
+    return;
+  }
   g[0] = (float)clampd(ex / p.ego_world_w, -1.0, 1.0);
   g[1] = (float)clampd(ey / p.ego_world_h, -1.0, 1.0);
   g[2] = (float)ea;
@@ -458,7 +471,8 @@ __global__ void __launch_bounds__(128) commit_kernel(const BcgParams p, const Bc
     // the observation the egocentric kernel will render is that of the state just written: resolve its
     // affine map, source window and goal vector here, one thread per env
     if (out.ego_image || out.goal_n_state) {
-      const double opx = sf[(BCG_F_DPOSE + 0) * N], opy = sf[(BCG_F_DPOSE + 1) * N], opth = sf[(BCG_F_DPOSE + 2) * N];
+      const int prow = p.ego_variant == 1 ? BCG_F_ROBOT : BCG_F_DPOSE;   // true robot pose vs observed (delayed) pose
+      const double opx = sf[(prow + 0) * N], opy = sf[(prow + 1) * N], opth = sf[(prow + 2) * N];
       if (out.ego_image)
         reinterpret_cast<EgoWork*>(b.ego_work)[e] = make_ego_work(p, b, b.map_id[e], opx, opy, opth, ego_cap);
       if (out.goal_n_state) write_goal_n_state(p, b, e, opx, opy, opth, out.goal_n_state);
@@ -780,7 +794,8 @@ __global__ void __launch_bounds__(128) ego_prep_kernel(const BcgParams p, const 
   if (e >= b.n_envs) return;
   const int64_t N = b.n_envs;
   const double* sf = b.state_f + e;
-  const double px = sf[(BCG_F_DPOSE + 0) * N], py = sf[(BCG_F_DPOSE + 1) * N], pth = sf[(BCG_F_DPOSE + 2) * N];
+  const int prow = p.ego_variant == 1 ? BCG_F_ROBOT : BCG_F_DPOSE;
+  const double px = sf[(prow + 0) * N], py = sf[(prow + 1) * N], pth = sf[(prow + 2) * N];
   if (want_image) reinterpret_cast<EgoWork*>(b.ego_work)[e] = make_ego_work(p, b, b.map_id[e], px, py, pth, ego_cap);
   if (goal_n_state) write_goal_n_state(p, b, e, px, py, pth, goal_n_state);
 }

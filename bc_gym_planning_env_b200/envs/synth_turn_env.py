@@ -136,6 +136,39 @@ class RandomAisleTurnEnv(object):
         self._env.set_state(state)
 
 
+class ColoredCostmapRandomAisleTurnEnv(RandomAisleTurnEnv):
+    """RandomAisleTurnEnv whose observation is the whole costmap, uint8 (H, W, 1)
+    (reference envs/synth_turn_env.py:335-377)."""
+
+    def step(self, action):
+        rich_obs, reward, done, info = super(ColoredCostmapRandomAisleTurnEnv, self).step(action)
+        return np.expand_dims(rich_obs.costmap.get_data(), -1), reward, done, info
+
+    def reset(self):
+        rich_obs = super(ColoredCostmapRandomAisleTurnEnv, self).reset()
+        return np.expand_dims(rich_obs.costmap.get_data(), -1)
+
+
+class ColoredEgoCostmapRandomAisleTurnEnv(RandomAisleTurnEnv):
+    """RandomAisleTurnEnv whose observation is {'environment': egocentric crop uint8 (133, 133, 1) about the
+    true robot pose, 'goal': float64 (5, 1)} (reference envs/synth_turn_env.py:380-451).  Crop and goal vector
+    come from the CUDA egocentric kernel (VecPlanEnv.observe_colored_ego); the goal vector is computed in fp64
+    and stored in fp32 on the device."""
+
+    def _extract_egocentric_observation(self, rich_observation):
+        from collections import OrderedDict
+        image, goal = self._env._vec.observe_colored_ego()
+        return OrderedDict((('environment', image[0].cpu().numpy()),
+                            ('goal', goal[0].cpu().numpy().astype(np.float64))))
+
+    def step(self, action):
+        rich_obs, reward, done, info = super(ColoredEgoCostmapRandomAisleTurnEnv, self).step(action)
+        return self._extract_egocentric_observation(rich_obs), reward, done, info
+
+    def reset(self):
+        return self._extract_egocentric_observation(super(ColoredEgoCostmapRandomAisleTurnEnv, self).reset())
+
+
 def random_aisle_pool(n, seed, env_params=None):
     """n random aisle turns for a batch: ([CostMap2D], [coarse path]) drawn like
     RandomAisleTurnEnv(seed=seed + i) would draw its first turn."""

@@ -376,6 +376,28 @@ class VecPlanEnv(object):
     def observation(self):
         return VecObservation(self)
 
+    def observe_colored_ego(self):
+        """ColoredEgoCostmapRandomAisleTurnEnv._extract_egocentric_observation (reference
+        envs/synth_turn_env.py:396-420) for every env: ('environment' uint8 [N,133,133,1] cropped about the TRUE
+        robot pose over x in [-0.5, 3.5], y in [-2, 2]; 'goal' float32 [N,5,1] = unit vector towards the last
+        path point in crop units, then v, w, wheel angle)."""
+        import copy
+        cp = copy.copy(self._c_params)
+        x_bounds, y_bounds = (-0.5, 3.5), (-2., 2.)
+        size = np.array([x_bounds[1] - x_bounds[0], y_bounds[1] - y_bounds[0]])
+        wh = np.round(size * (1. / self.resolution)).astype(int)
+        cp.ego_w, cp.ego_h = int(wh[0]), int(wh[1])
+        cp.ego_x0, cp.ego_y0 = x_bounds[0], y_bounds[0]
+        cp.ego_world_w = (cp.ego_x0 + self.resolution * cp.ego_w) - cp.ego_x0
+        cp.ego_world_h = (cp.ego_y0 + self.resolution * cp.ego_h) - cp.ego_y0
+        cp.ego_variant = 1
+        if getattr(self, '_colored_image', None) is None:
+            self._colored_image = torch.zeros((self.n_envs, cp.ego_h, cp.ego_w, 1), dtype=torch.uint8, device=self.device)
+            self._colored_goal = torch.zeros((self.n_envs, 9), dtype=torch.float32, device=self.device)
+        nat.check(nat.lib().bcg_observe_ego(C.byref(cp), C.byref(self._batch), nat.ptr(self._colored_image),
+                                            nat.ptr(self._colored_goal), self._stream()))
+        return self._colored_image, self._colored_goal[:, :5].unsqueeze(-1)
+
     def observe_ego(self):
         """EgocentricCostmap.observation of the current state -> ('env' uint8 [N,H,W,1],
         'goal_n_state' float32 [N,9,1])."""

@@ -98,7 +98,10 @@ typedef struct BcgParams {
   int32_t iteration_timeout;
   int32_t ego_w, ego_h;       /* crop size in pixels */
   int32_t auto_reset;         /* restore the initial state of envs that report done */
-  int32_t reserved;
+  int32_t ego_variant;        /* 0: EgocentricCostmap wrapper (egocentric.py:125-160): crop about the delayed pose,
+                                 9-vector goal_n_state.  1: ColoredEgoCostmapRandomAisleTurnEnv
+                                 (synth_turn_env.py:396-420): crop about the TRUE robot pose, goal = unit vector
+                                 towards the last path point, 5 values [gx, gy, v, w, wheel] (slots 5..8 zero) */
 } BcgParams;
 
 /* one costmap of the arena: CostMap2D (utilities/costmap_2d.py:13-37) + its derived lethal bit-plane */

@@ -140,6 +140,40 @@ def gen_ego(name, n_envs, n_steps, every):
     print(name, out["ref_ego_image"].shape, out["ref_goal_n_state"].shape)
 
 
+def gen_colored_ego(name, n_envs, n_steps, every):
+    """ColoredEgoCostmapRandomAisleTurnEnv observations (envs/synth_turn_env.py:380-451).  The class takes no
+    seed, so the instance's RandomState is seeded and its first env rebuilt through reset()."""
+    from bc_gym_planning_env.envs.base.action import Action
+    from bc_gym_planning_env.envs.synth_turn_env import ColoredEgoCostmapRandomAisleTurnEnv
+    envs, actions, images, vectors = [], [], [], []
+    for s in range(n_envs):
+        env = ColoredEgoCostmapRandomAisleTurnEnv()
+        env.seed(400 + s)
+        env.reset()
+        env._env._robot.set_noise_parameters(None)
+        envs.append(env._env)
+        rng = np.random.RandomState(s)
+        ea, ei, ev = [], [], []
+        for t in range(n_steps):
+            a = rng.uniform(env.action_space.low, env.action_space.high).astype(np.float32)
+            obs, _, done, _ = env.step(Action(command=a))
+            ea.append(a)
+            if t % every == every - 1:
+                ei.append(obs["environment"][..., 0].copy())
+                ev.append(obs["goal"][:, 0].copy())
+        actions.append(ea)
+        images.append(ei)
+        vectors.append(ev)
+    out = _pack_envs(envs)
+    out["actions"] = np.array(actions, dtype=np.float32)
+    out["every"] = np.int64(every)
+    out["ref_environment"] = np.array(images)
+    out["ref_goal"] = np.array(vectors)
+    out["params"] = np.array(_params_json(envs[0]._params, False))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, out["ref_environment"].shape, out["ref_goal"].shape)
+
+
 def gen_collision(name, n_maps, n_poses):
     from bc_gym_planning_env.envs.base.env import pose_collides
     from bc_gym_planning_env.envs.synth_turn_env import RandomAisleTurnEnv
@@ -258,6 +292,7 @@ def main():
     gen_rollouts("aisle_noise_on", lambda s: RandomAisleTurnEnv(
         params=EnvParams(control_delay=2, pose_delay=1, state_delay=1), seed=70 + s), 6, 200, noise=True)
     gen_ego("aisle_ego", 6, 48, 6)
+    gen_colored_ego("aisle_colored_ego", 4, 48, 6)
     gen_collision("aisle_collision", 8, 250)
     gen_kat_collision("kat_is_robot_colliding")
     gen_diffdrive("diffdrive_steps", 6, 250)

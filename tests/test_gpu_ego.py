@@ -41,3 +41,25 @@ def test_observe_ego_standalone_equals_step_output():
     vec_step = env.goal_n_state.clone()
     img, vec = env.observe_ego()
     assert torch.equal(img, img_step) and torch.equal(vec, vec_step)
+
+
+def test_colored_ego_variant_matches_reference():
+    """ColoredEgoCostmapRandomAisleTurnEnv (reference envs/synth_turn_env.py:380-451): 133x133 crop about the
+    TRUE robot pose, goal = unit vector to the last path point + (v, w, wheel)."""
+    d = common.load("aisle_colored_ego")
+    env = common.make_vec_env(d)                       # EnvParams(): no delays, like the reference class
+    actions = torch.from_numpy(d["actions"]).cuda()
+    every = int(d["every"])
+    k = 0
+    for t in range(actions.shape[1]):
+        env.step(actions[:, t].contiguous())
+        if t % every == every - 1:
+            image, goal = env.observe_colored_ego()
+            assert tuple(image.shape[1:]) == (133, 133, 1) and tuple(goal.shape[1:]) == (5, 1)
+            assert np.array_equal(image.cpu().numpy()[..., 0], d["ref_environment"][:, k]), t
+            np.testing.assert_allclose(goal.cpu().numpy()[..., 0], d["ref_goal"][:, k], rtol=2e-7, atol=1e-7)
+            k += 1
+    assert (d["ref_environment"] != 0).any()
+    # the wrapper-style observation is unaffected by the variant call
+    img9, vec9 = env.observe_ego()
+    assert tuple(img9.shape[1:]) == (133, 117, 1) and tuple(vec9.shape[1:]) == (9, 1)

@@ -116,3 +116,25 @@ def test_save_n_load_identity():
         assert obs1 == obs2 and obs1 == obs3 and r1 == r2 and done1 == done2
     state = env.get_state()
     assert roundtrip(state, State) == state
+
+
+def test_colored_observation_envs():
+    from bc_gym_planning_env_b200.envs.synth_turn_env import (ColoredCostmapRandomAisleTurnEnv,
+                                                             ColoredEgoCostmapRandomAisleTurnEnv)
+    d = common.load("aisle_colored_ego")
+    env = ColoredEgoCostmapRandomAisleTurnEnv(seed=None, noise_parameters=None)
+    env.seed(400)
+    obs = env.reset()                                   # same construction order as the fixture generator
+    assert obs['environment'].shape == (133, 133, 1) and obs['goal'].shape == (5, 1) and obs['goal'].dtype == np.float64
+    every, k = int(d["every"]), 0
+    for t in range(d["actions"].shape[1]):
+        obs, r, done, _ = env.step(Action(command=d["actions"][0, t]))
+        if t % every == every - 1:
+            assert np.array_equal(obs['environment'][..., 0], d["ref_environment"][0, k])
+            np.testing.assert_allclose(obs['goal'][:, 0], d["ref_goal"][0, k], rtol=2e-7, atol=1e-7)
+            k += 1
+    full = ColoredCostmapRandomAisleTurnEnv(seed=5, noise_parameters=None)
+    o = full.reset()
+    assert o.ndim == 3 and o.shape[-1] == 1 and o.dtype == np.uint8 and (o == 254).any()
+    o2, r, done, info = full.step(full.action_space.sample())
+    assert o2.shape == o.shape
