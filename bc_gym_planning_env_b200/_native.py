@@ -24,6 +24,7 @@ class BcgParams(C.Structure):
         ("robot_kind", C.c_int32), ("noise_on", C.c_int32),
         ("delay_control", C.c_int32), ("delay_pose", C.c_int32), ("delay_state", C.c_int32),
         ("iteration_timeout", C.c_int32), ("ego_w", C.c_int32), ("ego_h", C.c_int32),
+        ("reward_kind", C.c_int32), ("reserved", C.c_int32),
         ("auto_reset", C.c_int32), ("ego_variant", C.c_int32),
     ]
 
@@ -90,6 +91,7 @@ STATUS_LUT_MISS, STATUS_PATH_EXHAUSTED, STATUS_WORDS = 0, 1, 8
 STAT_NAMES = ("episodes", "return", "length", "collided", "goal", "timeout")
 STATS_WORDS = 8
 ROBOT_TRICYCLE, ROBOT_DIFFDRIVE = 0, 1
+REWARD_CONTINUOUS, REWARD_PURE_PURSUIT = 0, 1
 
 # every symbol include/bcg_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p

@@ -235,6 +235,8 @@ struct __align__(16) WorkReward {    // 96 bytes
   double ring_front[3];              // front of the pose delay queue (valid when from_ring)
   double min_dist;
   int32_t target, from_ring;
+  int32_t collided;                  // sticky collision flag before this step
+  int32_t goal_before;               // pure pursuit: was the observed pose already within 1 m of the goal
 };
 
 #define BCG_WORK_BYTES 192           // WorkCollide at +0, WorkReward at +64
@@ -455,6 +457,23 @@ __device__ __forceinline__ int last_reached_from(const BcgParams& p, const PathR
     }
   }
   return -1;
+}
+
+// ContinuousRewardPurePursuitProviderState.update_goal (envs/base/reward.py:126-137): the first way point from
+// `lo` on that is more than `radius` from the pose, else the last point.  Warp-cooperative min-index scan.
+__device__ __forceinline__ int first_beyond_radius(const PathRef& pd, int lo, double px, double py, double radius,
+                                                   unsigned lane) {
+  for (int base = lo & ~31; base < pd.n; base += 32) {
+    const int i = base + lane;
+    bool far = false;
+    if (i >= lo && i < pd.n) {
+      const double dx = __ldg(pd.P + i) - px, dy = __ldg(pd.P + pd.pitch + i) - py;
+      far = sqrt(fma(dy, dy, dx * dx)) > radius;        // np.linalg.norm of a 2-vector = sqrt(ddot), fused like the BLAS
+    }
+    const unsigned bits = __ballot_sync(BCG_FULL, far);
+    if (bits) return base + __ffs(bits) - 1;
+  }
+  return pd.n - 1;
 }
 
 }  // namespace bcg

@@ -100,6 +100,14 @@ __global__ void __launch_bounds__(128) kin_kernel(const BcgParams p, const BcgBa
   for (int r = 0; r < 3; ++r) wr.old_pose[r] = s[r];
   wr.min_dist = b.state_f[BCG_F_MIN_DIST * N + e];
   wr.target = b.state_i[BCG_I_TARGET * N + e];
+  wr.collided = b.state_i[BCG_I_COLLIDED * N + e];
+  wr.goal_before = 0;
+  if (p.reward_kind == BCG_REWARD_PURE_PURSUIT) {      // reward.py:139-149 on the pose observed before this step
+    const BcgPathDesc pdsc = b.paths[path_id];
+    const double* P = b.path_arena + pdsc.off;
+    const double gx = P[pdsc.n - 1], gy = P[pdsc.pitch + pdsc.n - 1];
+    wr.goal_before = hypot(gx - b.state_f[(BCG_F_DPOSE + 0) * N + e], gy - b.state_f[(BCG_F_DPOSE + 1) * N + e]) < 1.0;
+  }
   wr.from_ring = 0;
 #pragma unroll
   for (int r = 0; r < 3; ++r) wr.ring_front[r] = 0.0;
@@ -157,12 +165,14 @@ __global__ void __launch_bounds__(256, 5) collide_reward_kernel(const BcgParams 
   pd.chunk_pitch = wc.chunk_pitch;
   int target = wr.target;
   double min_dist = wr.min_dist;
-  const bool goal_before = target > pd.n - 1;
+  const bool pursuit = p.reward_kind == BCG_REWARD_PURE_PURSUIT;
+  const bool goal_before = pursuit ? (wr.goal_before != 0) : (target > pd.n - 1);
   // round 2 (issued before the collision verdict is needed): the goal point the reward most likely uses
   double gx = 0.0, gy = 0.0;
-  if (!goal_before) {
-    gx = __ldg(pd.P + target);
-    gy = __ldg(pd.P + pd.pitch + target);
+  if (pursuit || !goal_before) {
+    const int gi = pursuit ? pd.n - 1 : target;
+    gx = __ldg(pd.P + gi);
+    gy = __ldg(pd.P + pd.pitch + gi);
   }
 
   const bool hit = collide_tiles<false>(b, wc, lane, nullptr);
@@ -173,7 +183,17 @@ __global__ void __launch_bounds__(256, 5) collide_reward_kernel(const BcgParams 
   for (int r = 0; r < 3; ++r) pose[r] = wr.from_ring ? wr.ring_front[r] : (hit ? wr.old_pose[r] : wr.cand[r]);
 
   double reward = 0.0;
-  if (!goal_before) {
+  bool goal_after;
+  if (pursuit) {
+    // ContinuousRewardPurePursuitProvider.reward (reward.py:331-350)
+    target = first_beyond_radius(pd, target, pose[0], pose[1], 2.0, lane);
+    const double d = hypot(gx - pose[0], gy - pose[1]);
+    reward = -0.05;
+    reward += min_dist - d;
+    if (wr.collided || hit) reward -= 100;
+    min_dist = d;
+    goal_after = d < 1.0;
+  } else if (!goal_before) {
     const int last = last_reached_from(p, pd, target, pose[0], pose[1], pose[2], lane);
     if (last >= target) {
       target = last + 1;
@@ -191,11 +211,12 @@ __global__ void __launch_bounds__(256, 5) collide_reward_kernel(const BcgParams 
       }
     }
   }
+  if (!pursuit) goal_after = target > pd.n - 1;
   if (lane == 0) {
     b.cand[7 * N + e] = reward;
     b.cand[8 * N + e] = min_dist;
     b.cand_i[BCG_CI_TARGET * N + e] = target;
-    b.cand_i[BCG_CI_FLAGS * N + e] = (hit ? 1 : 0) | ((target > pd.n - 1) ? 2 : 0) | (goal_before ? 4 : 0);
+    b.cand_i[BCG_CI_FLAGS * N + e] = (hit ? 1 : 0) | (goal_after ? 2 : 0) | (goal_before ? 4 : 0);
   }
 }
 
@@ -506,13 +527,19 @@ __global__ void __launch_bounds__(256) init_kernel(const BcgParams p, const BcgB
   const PathRef pd = path_ref(b, b.paths[b.path_id[e]]);
   const double* P = pd.P;
   const double x0 = P[0], y0 = P[pd.pitch], t0 = P[2 * pd.pitch];
-  const int last = last_reached_from(p, pd, 0, x0, y0, t0, lane);
-  int target = last + 1;
+  int target;
   double min_dist = 0.0;
-  if (target > pd.n - 1) {
-    if (lane == 0) atomicAdd(b.status + BCG_STATUS_PATH_EXHAUSTED, 1u);
+  if (p.reward_kind == BCG_REWARD_PURE_PURSUIT) {        // reward.py:352-371
+    target = 1;
+    min_dist = hypot(P[pd.n - 1] - x0, P[pd.pitch + pd.n - 1] - y0);
   } else {
-    min_dist = hypot(P[target] - x0, P[pd.pitch + target] - y0);
+    const int last = last_reached_from(p, pd, 0, x0, y0, t0, lane);
+    target = last + 1;
+    if (target > pd.n - 1) {
+      if (lane == 0) atomicAdd(b.status + BCG_STATUS_PATH_EXHAUSTED, 1u);
+    } else {
+      min_dist = hypot(P[target] - x0, P[pd.pitch + target] - y0);
+    }
   }
   for (int r = lane; r < L.n_frows; r += 32) {
     double v = 0.0;

@@ -62,7 +62,32 @@ class ContinuousRewardProviderState(object):
 
 
 CONTINUOUS_REWARD_STATE = 'continuous_reward_state'      # reference reward_provider_examples.py
+CONTINUOUS_REWARD_PURE_PURSUIT_STATE = 'continuous_reward_pure_pursuit_state'
 ContinuousRewardProviderState.reward_provider_state_type_name = CONTINUOUS_REWARD_STATE
+
+
+@attr.s(eq=False)
+class ContinuousRewardPurePursuitProviderState(ContinuousRewardProviderState):
+    """reference envs/base/reward.py:78-159: the goal is always the last path point, `target_idx` is the
+    look-ahead way point and the current path is everything up to it."""
+    reward_provider_state_type_name = CONTINUOUS_REWARD_PURE_PURSUIT_STATE
+
+    def current_goal_pose(self):
+        return self.path[-1]
+
+    def current_path(self):
+        return self.path[:self.target_idx + 1]
+
+    def done(self, state=None):
+        pose = state.pose if state is not None else None
+        if pose is None:
+            raise ValueError("the pure-pursuit provider needs the env state to decide done")
+        goal = self.current_goal_pose()
+        return bool(np.hypot(goal[0] - pose[0], goal[1] - pose[1]) < 1.0)
+
+
+_REWARD_STATE_TYPES = {CONTINUOUS_REWARD_STATE: ContinuousRewardProviderState,
+                       CONTINUOUS_REWARD_PURE_PURSUIT_STATE: ContinuousRewardPurePursuitProviderState}
 
 
 @attr.s(eq=False)
@@ -129,10 +154,10 @@ class State(object):
         state = dict(state)
         assert state.pop('version') == cls.VERSION
         name = state.pop('reward_provider_state_type_name', None) or state.pop('reward_provider_state_name', None)
-        if name != CONTINUOUS_REWARD_STATE:
-            raise AssertionError("Unknown reward provider state {}".format(name))
+        if name not in _REWARD_STATE_TYPES:
+            raise Exception('No reward provider state name "{}" exists'.format(name))
         state.pop('reward_provider_state_name', None)
-        state['reward_provider_state'] = ContinuousRewardProviderState.deserialize(state['reward_provider_state'])
+        state['reward_provider_state'] = _REWARD_STATE_TYPES[name].deserialize(state['reward_provider_state'])
         state['costmap'] = CostMap2D.from_state(state['costmap'])
         rs_type = robot_state_type(state.pop('robot_type_name'))
         state['robot_state'] = rs_type.deserialize(state['robot_state'])
@@ -185,6 +210,9 @@ class PlanEnv(object):
         self.reward_range = (0.0, 1.0)
         self._costmap = costmap
         self._state_type = robot_state_type(params.robot_name)
+        self._reward_state_type = (ContinuousRewardPurePursuitProviderState
+                                   if self._vec._c_params.reward_kind == nat.REWARD_PURE_PURSUIT
+                                   else ContinuousRewardProviderState)
 
     # ---- reference API -----------------------------------------------------------------------------
     def reset(self):
@@ -249,7 +277,7 @@ class PlanEnv(object):
         v = self._vec
         f = v.state_f[:, 0].cpu().numpy()
         target = int(v.state_i[nat.I_TARGET, 0])
-        return Observation(pose=f[nat.F_DPOSE:nat.F_DPOSE + 3].copy(), path=v.full_path(0)[target:],
+        return Observation(pose=f[nat.F_DPOSE:nat.F_DPOSE + 3].copy(), path=self._reward_state_type(0.0, v.full_path(0), target).current_path(),
                            costmap=self._costmap, robot_state=self._state_type.from_row(f[nat.F_DROBOT:nat.F_DROBOT + 7]),
                            time=float(f[nat.F_TIME]), dt=self._params.dt)
 
@@ -265,9 +293,9 @@ class PlanEnv(object):
         f, i = vs.f[:, 0].cpu().numpy(), vs.i[:, 0].cpu().numpy()
         full = self._vec.full_path(0)
         target = int(i[nat.I_TARGET])
-        rps = ContinuousRewardProviderState(min_spat_dist_so_far=float(f[nat.F_MIN_DIST]), path=full.copy(), target_idx=target)
+        rps = self._reward_state_type(min_spat_dist_so_far=float(f[nat.F_MIN_DIST]), path=full.copy(), target_idx=target)
         return State(
-            reward_provider_state=rps, path=full[target:].copy(), original_path=full.copy(), costmap=self._costmap.copy(),
+            reward_provider_state=rps, path=rps.current_path().copy(), original_path=full.copy(), costmap=self._costmap.copy(),
             iter_timeout=self._params.iteration_timeout, current_time=float(f[nat.F_TIME]), current_iter=int(i[nat.I_ITER]),
             robot_collided=bool(i[nat.I_COLLIDED]),
             poses_queue=self._queue(f, i, 'pose'),

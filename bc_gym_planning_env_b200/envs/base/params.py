@@ -6,6 +6,7 @@ import numpy as np
 from bc_gym_planning_env_b200.robot_models.robot_dimensions import INDUSTRIAL_TRICYCLE_V1
 
 CONTINUOUS_REWARD = 'continuous_reward'   # reward_provider_examples.py
+CONTINUOUS_REWARD_PURE_PURSUIT = 'continuous_reward_pure_pursuit'
 
 
 @attr.s

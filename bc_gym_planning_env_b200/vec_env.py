@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from bc_gym_planning_env_b200 import _native as nat
-from bc_gym_planning_env_b200.envs.base.params import EnvParams
+from bc_gym_planning_env_b200.envs.base.params import CONTINUOUS_REWARD, CONTINUOUS_REWARD_PURE_PURSUIT, EnvParams
 from bc_gym_planning_env_b200.footprint_lut import FootprintLut
 from bc_gym_planning_env_b200.robot_models.robot_dimensions import TRICYCLE, get_dimensions_example
 from bc_gym_planning_env_b200.utilities.costmap_2d import CostMap2D
@@ -59,8 +59,11 @@ class VecObservation(object):
         self.dt = env.params.dt
 
     def path(self, e):
-        """Remaining path of env e (`path[target_idx:]`, reference envs/base/env.py:421-433)."""
-        return self._env.full_path(e)[int(self.target_idx[e]):]
+        """Observation.path of env e (reference envs/base/env.py:421-433): `path[target_idx:]`, or
+        `path[:target_idx + 1]` with the pure-pursuit reward provider (reward.py:120-124)."""
+        t = int(self.target_idx[e])
+        full = self._env.full_path(e)
+        return full[:t + 1] if self._env.params.reward_provider_name == CONTINUOUS_REWARD_PURE_PURSUIT else full[t:]
 
     def costmap(self, e):
         return self._env.costmap(e)
@@ -152,6 +155,10 @@ class VecPlanEnv(object):
         cp.robot_kind = self.robot_kind
         cp.delay_control, cp.delay_pose, cp.delay_state = p.control_delay, p.pose_delay, p.state_delay
         cp.iteration_timeout = p.iteration_timeout
+        kinds = {CONTINUOUS_REWARD: nat.REWARD_CONTINUOUS, CONTINUOUS_REWARD_PURE_PURSUIT: nat.REWARD_PURE_PURSUIT}
+        if p.reward_provider_name not in kinds:          # reward_provider_examples_factory.py:44-47
+            raise AssertionError("Unknown reward provider: {}. Should be one of {}".format(p.reward_provider_name, list(kinds)))
+        cp.reward_kind = kinds[p.reward_provider_name]
         cp.auto_reset = 1 if self.auto_reset else 0
         return cp
 

@@ -38,6 +38,10 @@ extern "C" {
 #define BCG_ERR_NO_DEVICE (-3)
 
 /* robot kinds (robot_models/robot_drive_types.py) */
+/* reward providers (envs/base/reward_provider_examples.py) */
+#define BCG_REWARD_CONTINUOUS 0
+#define BCG_REWARD_PURE_PURSUIT 1
+
 #define BCG_ROBOT_TRICYCLE 0
 #define BCG_ROBOT_DIFFDRIVE 1
 
@@ -97,6 +101,9 @@ typedef struct BcgParams {
   int32_t delay_control, delay_pose, delay_state;
   int32_t iteration_timeout;
   int32_t ego_w, ego_h;       /* crop size in pixels */
+  int32_t reward_kind;        /* 0 ContinuousRewardProvider (reward.py:173-288), 1 ContinuousRewardPurePursuitProvider
+                                 (reward.py:291-371) */
+  int32_t reserved;
   int32_t auto_reset;         /* restore the initial state of envs that report done */
   int32_t ego_variant;        /* 0: EgocentricCostmap wrapper (egocentric.py:125-160): crop about the delayed pose,
                                  9-vector goal_n_state.  1: ColoredEgoCostmapRandomAisleTurnEnv

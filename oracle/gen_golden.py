@@ -55,7 +55,7 @@ def _params_json(ep, noise):
     return json.dumps(dict(dt=ep.dt, sp=rp.spatial_precision, ap=rp.angular_precision,
                            multiplier=rp.spatial_progress_multiplier, timeout=ep.iteration_timeout,
                            delays=[ep.control_delay, ep.pose_delay, ep.state_delay], robot=ep.robot_name,
-                           noise=noise))
+                           noise=noise, reward_provider=ep.reward_provider_name))
 
 
 def gen_rollouts(name, make_env, n_envs, n_steps, noise=False, sample_from_space=False):
@@ -291,6 +291,9 @@ def main():
         params=EnvParams(control_delay=1, pose_delay=2, state_delay=0), seed=50 + s), 6, 200)
     gen_rollouts("aisle_noise_on", lambda s: RandomAisleTurnEnv(
         params=EnvParams(control_delay=2, pose_delay=1, state_delay=1), seed=70 + s), 6, 200, noise=True)
+    gen_rollouts("aisle_pure_pursuit", lambda s: RandomAisleTurnEnv(
+        params=EnvParams(control_delay=1, pose_delay=1, state_delay=1, iteration_timeout=260,
+                         reward_provider_name='continuous_reward_pure_pursuit'), seed=90 + s), 6, 300)
     gen_ego("aisle_ego", 6, 48, 6)
     gen_colored_ego("aisle_colored_ego", 4, 48, 6)
     gen_collision("aisle_collision", 8, 250)

@@ -298,6 +298,33 @@ def reward_step(pose, path, target_idx, min_dist, sp, ap, multiplier):
     return 0.0, target_idx, min_dist
 
 
+def pure_pursuit_initial_state(path):
+    """envs/base/reward.py:352-371 -- (target_idx, min_dist) of ContinuousRewardPurePursuitProvider."""
+    return 1, float(np.hypot(path[-1, 0] - path[0, 0], path[-1, 1] - path[0, 1]))
+
+
+def pure_pursuit_reward_step(pose, path, target_idx, min_dist, collided, radius=2.):
+    """envs/base/reward.py:126-137 (update_goal: first way point from target_idx on that is more than
+    `radius` away, else the last one) and :331-350 (reward = -0.05 + progress towards the LAST path point,
+    -100 while collided).  Returns (reward, target_idx, min_dist)."""
+    new_target = len(path) - 1
+    for i in range(target_idx, len(path)):
+        if np.linalg.norm(path[i, :2] - pose[:2]) > radius:
+            new_target = i
+            break
+    d = float(np.hypot(path[-1, 0] - pose[0], path[-1, 1] - pose[1]))
+    reward = -0.05
+    reward += min_dist - d
+    if collided:
+        reward -= 100
+    return float(reward), new_target, d
+
+
+def pure_pursuit_done(pose, path):
+    """envs/base/reward.py:139-149 -- within 1 m of the last path point."""
+    return bool(np.hypot(path[-1, 0] - pose[0], path[-1, 1] - pose[1]) < 1.0)
+
+
 # ----------------------------------------------------------------------------------------------
 # egocentric observation
 # ----------------------------------------------------------------------------------------------
@@ -454,7 +481,8 @@ class OraclePlanEnv(object):
 
     def __init__(self, costmap, origin, resolution, path, robot="industrial_tricycle_v1", dt=0.05,
                  sp=1.0, ap=np.pi / 2, multiplier=0.0, timeout=1200, delays=(0, 0, 0), alphas=None,
-                 normal_source=None, refine=True, path_delta=0.05, initial_wheel_angle=0.0):
+                 normal_source=None, refine=True, path_delta=0.05, initial_wheel_angle=0.0,
+                 reward_provider="continuous_reward"):
         self.costmap = np.ascontiguousarray(costmap)
         self.origin = np.asarray(origin, dtype=np.float64)
         self.resolution = float(resolution)
@@ -464,6 +492,7 @@ class OraclePlanEnv(object):
         self.delays = tuple(int(d) for d in delays)
         self.alphas = alphas
         self.normal_source = normal_source
+        self.pure_pursuit = reward_provider == "continuous_reward_pure_pursuit"
         path = np.asarray(path, dtype=np.float64)
         self.path = refine_path(path, path_delta) if refine else np.ascontiguousarray(path)
         self.reset()
@@ -476,19 +505,23 @@ class OraclePlanEnv(object):
         self.robot_state = [float(p0[0]), float(p0[1]), float(p0[2]), 0., 0., 0., 0.]
         self.delayed_robot_state = list(self.robot_state)
         self.pose = np.array(p0, dtype=np.float64)
-        self.target_idx, self.min_dist = initial_reward_state(self.path, self.sp, self.ap)
+        if self.pure_pursuit:
+            self.target_idx, self.min_dist = pure_pursuit_initial_state(self.path)
+        else:
+            self.target_idx, self.min_dist = initial_reward_state(self.path, self.sp, self.ap)
         self.time, self.iter, self.collided = 0.0, 0, False
         self.control_queue, self.pose_queue, self.state_queue = [], [], []
         return self.observation()
 
     def observation(self):
         """envs/base/env.py:421-433 -- (delayed pose, remaining path, delayed robot state, time)."""
-        return dict(pose=np.array(self.pose), path=self.path[self.target_idx:],
-                    robot_state=list(self.delayed_robot_state), time=self.time)
+        path = self.path[:self.target_idx + 1] if self.pure_pursuit else self.path[self.target_idx:]   # reward.py:120-124 / :59-64
+        return dict(pose=np.array(self.pose), path=path, robot_state=list(self.delayed_robot_state), time=self.time)
 
     def done(self):
-        """envs/base/env.py:400-419 + envs/base/reward.py:66-69."""
-        return bool(self.target_idx > len(self.path) - 1 or self.iter >= self.timeout or self.collided)
+        """envs/base/env.py:400-419 + envs/base/reward.py:66-69 (:139-149 for pure pursuit)."""
+        goal = pure_pursuit_done(self.pose, self.path) if self.pure_pursuit else self.target_idx > len(self.path) - 1
+        return bool(goal or self.iter >= self.timeout or self.collided)
 
     def step(self, cmd):
         """envs/base/env.py:334-398, 442-461.  Returns (observation, reward, done, hit_this_step)."""
@@ -515,8 +548,12 @@ class OraclePlanEnv(object):
         self.iter += 1
         self.delayed_robot_state = list(delay_line(self.state_queue, list(new), ds))
         self.collided = self.collided or hit
-        r, self.target_idx, self.min_dist = reward_step(self.pose, self.path, self.target_idx, self.min_dist,
-                                                        self.sp, self.ap, self.multiplier)
+        if self.pure_pursuit:
+            r, self.target_idx, self.min_dist = pure_pursuit_reward_step(self.pose, self.path, self.target_idx,
+                                                                         self.min_dist, self.collided)
+        else:
+            r, self.target_idx, self.min_dist = reward_step(self.pose, self.path, self.target_idx, self.min_dist,
+                                                            self.sp, self.ap, self.multiplier)
         return self.observation(), float(r), self.done(), hit
 
     # envs/base/env.py:278-291 -- deep snapshot; set_state loads the *delayed* robot state into the robot

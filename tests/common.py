@@ -33,7 +33,7 @@ def make_oracles(d, alphas=None, normal_sources=None):
         out.append(O.OraclePlanEnv(cm, origin, float(d["resolution"]), path, robot=p["robot"], dt=p["dt"], sp=p["sp"],
                                    ap=p["ap"], multiplier=p["multiplier"], timeout=p["timeout"], delays=p["delays"],
                                    alphas=alphas, normal_source=None if normal_sources is None else normal_sources[i],
-                                   refine=False))
+                                   refine=False, reward_provider=p.get("reward_provider", "continuous_reward")))
     return out
 
 
@@ -41,7 +41,7 @@ def env_params(p, **over):
     from bc_gym_planning_env_b200.envs.base.params import EnvParams, RewardParams
     kw = dict(dt=p["dt"], goal_spat_dist=p["sp"], goal_ang_dist=p["ap"], iteration_timeout=p["timeout"],
               control_delay=p["delays"][0], pose_delay=p["delays"][1], state_delay=p["delays"][2], robot_name=p["robot"],
-              refine_path=False,
+              refine_path=False, reward_provider_name=p.get("reward_provider", "continuous_reward"),
               reward_provider_params=RewardParams(spatial_precision=p["sp"], angular_precision=p["ap"],
                                                   spatial_progress_multiplier=p["multiplier"]))
     kw.update(over)

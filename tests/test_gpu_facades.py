@@ -138,3 +138,20 @@ def test_colored_observation_envs():
     assert o.ndim == 3 and o.shape[-1] == 1 and o.dtype == np.uint8 and (o == 254).any()
     o2, r, done, info = full.step(full.action_space.sample())
     assert o2.shape == o.shape
+
+
+def test_pure_pursuit_provider_through_the_facade():
+    d = common.load("aisle_pure_pursuit")
+    p = d["params"]
+    params = EnvParams(control_delay=1, pose_delay=1, state_delay=1, iteration_timeout=p["timeout"],
+                       reward_provider_name='continuous_reward_pure_pursuit')
+    env = RandomAisleTurnEnv(params=params, seed=90, noise_parameters=None)
+    for t in range(120):
+        obs, r, done, _ = env.step(Action(command=d["actions"][0, t]))
+        assert abs(r - d["ref_reward"][0, t]) < 1e-9 and done == d["ref_done"][0, t]
+        assert len(obs.path) == d["ref_path_len"][0, t]
+    state = env.get_state()
+    assert state.reward_provider_state.get_reward_provider_state_type_name() == 'continuous_reward_pure_pursuit_state'
+    assert State.deserialize(state.serialize()) == state
+    with pytest.raises(AssertionError):
+        RandomAisleTurnEnv(params=EnvParams(reward_provider_name='nope'), seed=1)

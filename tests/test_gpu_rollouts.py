@@ -31,7 +31,7 @@ def _rollout(d, **kw):
     return {k: np.swapaxes(np.array(v), 0, 1) for k, v in rec.items()}
 
 
-@pytest.mark.parametrize("name", ["mini_noise_off", "aisle_delays_211", "aisle_delays_120"])
+@pytest.mark.parametrize("name", ["mini_noise_off", "aisle_delays_211", "aisle_delays_120", "aisle_pure_pursuit"])
 def test_step_matches_reference(name):
     d = common.load(name)
     got = _rollout(d)
@@ -41,7 +41,8 @@ def test_step_matches_reference(name):
         ref = d["ref_" + k]
         np.testing.assert_allclose(got[k], ref, rtol=common.CONTRACT_RTOL, atol=common.CONTRACT_RTOL)
         np.testing.assert_allclose(got[k], ref, rtol=0, atol=common.TIGHT_ATOL, err_msg=k)
-    assert d["ref_collided"].any() and d["ref_done"].any() and (d["ref_reward"] == 1.0).any()
+    assert d["ref_collided"].any() and d["ref_done"].any()
+    assert (d["ref_reward"] == 1.0).any() or (d["ref_reward"] < -99).any()
 
 
 def test_f64_actions_and_shared_pools_agree():

@@ -22,7 +22,7 @@ def _replay(d, oracles):
             assert len(obs["path"]) == d["ref_path_len"][e, t]
 
 
-@pytest.mark.parametrize("name", ["mini_noise_off", "aisle_delays_211", "aisle_delays_120"])
+@pytest.mark.parametrize("name", ["mini_noise_off", "aisle_delays_211", "aisle_delays_120", "aisle_pure_pursuit"])
 def test_oracle_matches_reference_rollouts(name):
     d = common.load(name)
     _replay(d, common.make_oracles(d))
