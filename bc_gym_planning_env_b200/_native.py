@@ -34,6 +34,7 @@ class BcgMapDesc(C.Structure):
         ("data_off", C.c_int64), ("tile_off", C.c_int64), ("origin_x", C.c_double), ("origin_y", C.c_double),
         ("height", C.c_int32), ("width", C.c_int32), ("pitch", C.c_int32),
         ("tiles_x", C.c_int32), ("tiles_y", C.c_int32), ("reserved", C.c_int32),
+        ("cell_tile_off", C.c_int64), ("ctiles_x", C.c_int32), ("ctiles_y", C.c_int32),
     ]
 
 
@@ -64,6 +65,7 @@ class BcgBatch(C.Structure):
         ("lut", BcgFootprintLut),
         ("map_tmaps", C.c_void_p), ("tmap_n_widths", C.c_int32), ("tmap_box_h", C.c_int32),
         ("tmap_box_w", C.c_int32 * 4),
+        ("cell_tile_arena", C.c_void_p),
         ("status", C.c_void_p), ("stats", C.c_void_p),
     ]
 
@@ -102,6 +104,7 @@ SYMBOLS = {
     "bcg_device_count": (C.c_int, []),
     "bcg_state_layout": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgStateLayout)]),
     "bcg_build_lethal_tiles": (C.c_int, [C.POINTER(BcgBatch), C.c_int32, C.c_int32, _P]),
+    "bcg_build_cell_tiles": (C.c_int, [C.POINTER(BcgBatch), C.c_int32, C.c_int32, _P]),
     "bcg_encode_map_tensor_maps": (C.c_int, [C.POINTER(BcgMapDesc), C.c_int32, _P, C.POINTER(C.c_int32), C.c_int32,
                                              C.c_int32, _P]),
     "bcg_init_state": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgBatch), _P]),

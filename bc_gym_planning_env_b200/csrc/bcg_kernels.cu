@@ -323,9 +323,12 @@ struct __align__(16) EgoWork {       // 128 bytes
   int32_t map_w, map_h, map_pitch, map_id;
   int32_t pad[8];
 };
+static_assert(sizeof(EgoWork) == 128, "EgoWork records are 128 bytes");
 #define BCG_EGO_MODE_DIRECT 0
 #define BCG_EGO_MODE_TMA 1
 #define BCG_EGO_MODE_SPANS 2
+#define BCG_EGO_MODE_TILES 3
+#define BCG_EGO_WORK_BYTES 256        // stride of the per-env records in BcgBatch.ego_work (EgoWork uses the first 128)
 
 __device__ __forceinline__ EgoWork make_ego_work(const BcgParams& p, const BcgBatch& b, int map_id, double px, double py,
                                                  double pth, int tile_capacity) {
@@ -340,6 +343,7 @@ __device__ __forceinline__ EgoWork make_ego_work(const BcgParams& p, const BcgBa
   w.cls = 0;
   w.mode = BCG_EGO_MODE_DIRECT;
   w.x0 = w.x1 = w.y0 = w.y1 = 0;
+
   // Source window: every sample is X = floor(x + 0.5 + d), |d| <= 2^-10, of a point x of the rotated crop
   // rectangle, so the rectangle's corners grown by 0.51 px bound all samples.
   const EgoAffine& A = w.aff;
@@ -392,6 +396,147 @@ __host__ __device__ inline int ego_tile_capacity(const BcgParams& p, const BcgBa
   cap = (cap + 127) / 128 * 128;
   if (cap > 42 * 1024) cap = 42 * 1024;   // larger crops fall back to the direct global gather per CTA
   return cap;
+}
+
+// x-extent of a convex quad within the horizontal band [ylo, yhi]; extremes lie on the boundary
+__device__ __forceinline__ void quad_band_extent(const double qx[4], const double qy[4], double ylo, double yhi,
+                                                 double& xmin, double& xmax) {
+  xmin = 1e300;
+  xmax = -1e300;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double xa = qx[k], ya = qy[k], xb = qx[(k + 1) & 3], yb = qy[(k + 1) & 3];
+    double t0 = 0.0, t1 = 1.0;
+    const double dy = yb - ya;
+    if (dy == 0.0) {
+      if (ya < ylo || ya > yhi) continue;
+    } else {
+      double ta = (ylo - ya) / dy, tb = (yhi - ya) / dy;
+      if (ta > tb) { const double t = ta; ta = tb; tb = t; }
+      t0 = fmax(ta, 0.0);
+      t1 = fmin(tb, 1.0);
+      if (t0 > t1) continue;
+    }
+    const double x0 = xa + (xb - xa) * t0, x1 = xa + (xb - xa) * t1;
+    xmin = fmin(xmin, fmin(x0, x1));
+    xmax = fmax(xmax, fmax(x0, x1));
+  }
+}
+
+
+// Record of the persistent cell-tile egocentric kernel (ego_tiles_kernel), resolved one thread per env: the
+// inverted affine map, the tile-aligned source window and, per row of cell tiles, which tiles the rotated crop
+// rectangle touches.  Doing the clipping here (32 envs per warp) instead of in the image kernel (one env per
+// CTA) is ~50x cheaper in issued instructions.
+#define BCG_EGT_MAX_TILE_ROWS 64
+struct __align__(16) EgoTileWork {   // 256 bytes
+  EgoAffine aff;                     // 48
+  int32_t X0, Y0;                    // window origin in map pixels, multiples of (16, 8); 0 in direct mode
+  int32_t ntx, nty;                  // window size in cell tiles
+  int32_t mode, map_id;              // BCG_EGO_MODE_TILES or BCG_EGO_MODE_DIRECT
+  int32_t ctiles_x, ctiles_y;        // cell-tile grid of the env's map
+  int64_t ctile_off;                 // byte offset of the map's cell tiles in the cell-tile arena
+  int32_t pad[10];
+  uint8_t span[BCG_EGT_MAX_TILE_ROWS][2];   // first and last window tile column touched in tile row t (first > last: none)
+};
+static_assert(sizeof(EgoTileWork) == BCG_EGO_WORK_BYTES, "EgoTileWork records are 256 bytes");
+
+// shared-memory bytes of one window buffer of ego_tiles_kernel: worst-case tile-aligned window of the crop
+__host__ __device__ inline int ego_window_capacity(const BcgParams& p) {
+  const int side = (int)ceil(sqrt((double)p.ego_w * p.ego_w + (double)p.ego_h * p.ego_h)) + 2;
+  const int nty = (side + 1 + 7) / 8 + 1, ntx = (side + 1 + 15) / 16 + 1;
+  long long cap = (long long)nty * 128 * (ntx | 1);
+  if (cap > 52 * 1024) cap = 52 * 1024;     // two buffers x two CTAs per SM must fit; larger crops gather from global
+  return (int)cap;
+}
+
+__device__ __forceinline__ void write_ego_tile_record(const BcgParams& p, const BcgBatch& b, int e, int map_id, double px,
+                                                      double py, double pth, int win_capacity) {
+  const BcgMapDesc m = b.maps[map_id];
+  EgoTileWork* rec = reinterpret_cast<EgoTileWork*>(reinterpret_cast<uint8_t*>(b.ego_work) + (int64_t)e * BCG_EGO_WORK_BYTES);
+  EgoTileWork w;
+  w.aff = ego_affine(p, m, px, py, pth);
+  w.X0 = w.Y0 = w.ntx = w.nty = 0;
+  w.mode = BCG_EGO_MODE_DIRECT;
+  w.map_id = map_id;
+  w.ctiles_x = m.ctiles_x;
+  w.ctiles_y = m.ctiles_y;
+  w.ctile_off = m.cell_tile_off;
+  // every sample is X = floor(x + 0.5 + d), |d| <= 2^-10, of a point x of the rotated crop rectangle: the
+  // rectangle grown by 0.51 px bounds all samples
+  const EgoAffine& A = w.aff;
+  const double uw = (double)(p.ego_w - 1), vh = (double)(p.ego_h - 1);
+  const double qx[4] = {A.b1, A.a11 * uw + A.b1, A.a11 * uw + A.a12 * vh + A.b1, A.a12 * vh + A.b1};
+  const double qy[4] = {A.b2, A.a21 * uw + A.b2, A.a21 * uw + A.a22 * vh + A.b2, A.a22 * vh + A.b2};
+  const double lim = 1048576.0;
+  const double xlo = fmin(fmin(qx[0], qx[1]), fmin(qx[2], qx[3])), xhi = fmax(fmax(qx[0], qx[1]), fmax(qx[2], qx[3]));
+  const double ylo = fmin(fmin(qy[0], qy[1]), fmin(qy[2], qy[3])), yhi = fmax(fmax(qy[0], qy[1]), fmax(qy[2], qy[3]));
+  const bool sane = xlo > -lim && xhi < lim && ylo > -lim && yhi < lim;   // false for NaN too
+  if (sane) {
+    const int x0 = (int)floor(xlo - 0.51) & ~15, y0 = (int)floor(ylo - 0.51) & ~7;
+    const int x1 = (int)ceil(xhi + 0.51), y1 = (int)ceil(yhi + 0.51);
+    const int ntx = (x1 >> 4) - (x0 >> 4) + 1, nty = (y1 >> 3) - (y0 >> 3) + 1;
+    if (ntx <= 16 && nty <= BCG_EGT_MAX_TILE_ROWS && nty * 128 * (ntx | 1) <= win_capacity) {   // 16: one staging pass per tile row
+      w.mode = BCG_EGO_MODE_TILES;
+      w.X0 = x0;
+      w.Y0 = y0;
+      w.ntx = ntx;
+      w.nty = nty;
+    }
+  }
+  uint4* dst = reinterpret_cast<uint4*>(rec);
+  const uint4* src = reinterpret_cast<const uint4*>(&w);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) dst[k] = src[k];
+  if (w.mode == BCG_EGO_MODE_TILES) {
+    // x-extent of the crop rectangle within each row of tiles: clip its four edges against the band (no division
+    // in the loop: one inverse slope per edge)
+    const int ttx0 = w.X0 >> 4;
+    double inv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double dy = qy[(k + 1) & 3] - qy[k];
+      inv[k] = dy != 0.0 ? (qx[(k + 1) & 3] - qx[k]) / dy : 0.0;
+    }
+    for (int t = 0; t < w.nty; ++t) {
+      const double blo = (double)(w.Y0 + 8 * t) - 0.51, bhi = (double)(w.Y0 + 8 * t + 7) + 0.51;
+      double xmin = 1e300, xmax = -1e300;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const double xa = qx[k], ya = qy[k], xb = qx[(k + 1) & 3], yb = qy[(k + 1) & 3];
+        const double lo = fmax(blo, fmin(ya, yb)), hi = fmin(bhi, fmax(ya, yb));
+        if (lo <= hi) {
+          double x0, x1;
+          if (ya == yb) {
+            x0 = xa;
+            x1 = xb;
+          } else {               // clamp: the clipped points lie on the edge, rounding must not push them past its ends
+            x0 = fmin(fmax(xa + (lo - ya) * inv[k], fmin(xa, xb)), fmax(xa, xb));
+            x1 = fmin(fmax(xa + (hi - ya) * inv[k], fmin(xa, xb)), fmax(xa, xb));
+          }
+          xmin = fmin(xmin, fmin(x0, x1));
+          xmax = fmax(xmax, fmax(x0, x1));
+        }
+      }
+      int ts = 1, te = 0;
+      if (xmin <= xmax) {
+        ts = max(((int)floor(xmin - 0.51) >> 4) - ttx0, 0);
+        te = min(((int)ceil(xmax + 0.51) >> 4) - ttx0, w.ntx - 1);
+      }
+      *reinterpret_cast<uint16_t*>(rec->span[t]) = (uint16_t)(ts | (te << 8));
+    }
+  }
+}
+
+// the per-env record of whichever egocentric kernel the batch is set up for
+__device__ __forceinline__ void write_ego_record(const BcgParams& p, const BcgBatch& b, int e, int map_id, double px,
+                                                 double py, double pth, int cap) {
+  if (b.cell_tile_arena) {
+    write_ego_tile_record(p, b, e, map_id, px, py, pth, cap);
+  } else {
+    *reinterpret_cast<EgoWork*>(reinterpret_cast<uint8_t*>(b.ego_work) + (int64_t)e * BCG_EGO_WORK_BYTES) =
+        make_ego_work(p, b, map_id, px, py, pth, cap);
+  }
 }
 
 // One thread per env: the rest of _resolve_state_transition (env.py:363-398) -- rollback, pose and
@@ -495,7 +640,7 @@ __global__ void __launch_bounds__(128) commit_kernel(const BcgParams p, const Bc
       const int prow = p.ego_variant == 1 ? BCG_F_ROBOT : BCG_F_DPOSE;   // true robot pose vs observed (delayed) pose
       const double opx = sf[(prow + 0) * N], opy = sf[(prow + 1) * N], opth = sf[(prow + 2) * N];
       if (out.ego_image)
-        reinterpret_cast<EgoWork*>(b.ego_work)[e] = make_ego_work(p, b, b.map_id[e], opx, opy, opth, ego_cap);
+        write_ego_record(p, b, e, b.map_id[e], opx, opy, opth, ego_cap);
       if (out.goal_n_state) write_goal_n_state(p, b, e, opx, opy, opth, out.goal_n_state);
     }
   }
@@ -597,6 +742,23 @@ __global__ void __launch_bounds__(256) tiles_kernel(const BcgBatch b, const int 
   }
 }
 
+// cell tiles: the uint8 cells of a map as 128-byte tiles of 16 px x 8 rows (see BcgMapDesc); one thread per
+// 16-byte tile row, zero beyond the map
+__global__ void __launch_bounds__(256) cell_tiles_kernel(const BcgBatch b, const int first) {
+  const BcgMapDesc m = b.maps[first + blockIdx.y];
+  const int pieces = m.ctiles_x * m.ctiles_y * 8;
+  uint4* dst = reinterpret_cast<uint4*>(const_cast<uint8_t*>(b.cell_tile_arena) + m.cell_tile_off);
+  const uint8_t* src = b.map_arena + m.data_off;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < pieces; q += gridDim.x * blockDim.x) {
+    const int tile = q >> 3, r = q & 7;
+    const int ty = tile / m.ctiles_x, tx = tile - ty * m.ctiles_x;
+    const int y = (ty << 3) + r;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (y < m.height && (tx << 4) < m.pitch) v = *reinterpret_cast<const uint4*>(src + (int64_t)y * m.pitch + (tx << 4));
+    dst[q] = v;
+  }
+}
+
 // pose_collides of the poses whose work records are in b.work; one warp per env.  MODE 0: lethal tile plane,
 // 1: tile plane + in-map pixel count, 2: raw uint8 rows.
 template <int MODE>
@@ -614,31 +776,6 @@ __global__ void __launch_bounds__(256, 6) collision_kernel(const BcgBatch b, uin
   if (lane == 0) {
     flags[e] = hit ? 1 : 0;
     if (MODE == 1) pixels[e] = cnt;
-  }
-}
-
-// x-extent of a convex quad within the horizontal band [ylo, yhi]; extremes lie on the boundary
-__device__ __forceinline__ void quad_band_extent(const double qx[4], const double qy[4], double ylo, double yhi,
-                                                 double& xmin, double& xmax) {
-  xmin = 1e300;
-  xmax = -1e300;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const double xa = qx[k], ya = qy[k], xb = qx[(k + 1) & 3], yb = qy[(k + 1) & 3];
-    double t0 = 0.0, t1 = 1.0;
-    const double dy = yb - ya;
-    if (dy == 0.0) {
-      if (ya < ylo || ya > yhi) continue;
-    } else {
-      double ta = (ylo - ya) / dy, tb = (yhi - ya) / dy;
-      if (ta > tb) { const double t = ta; ta = tb; tb = t; }
-      t0 = fmax(ta, 0.0);
-      t1 = fmin(tb, 1.0);
-      if (t0 > t1) continue;
-    }
-    const double x0 = xa + (xb - xa) * t0, x1 = xa + (xb - xa) * t1;
-    xmin = fmin(xmin, fmin(x0, x1));
-    xmax = fmax(xmax, fmax(x0, x1));
   }
 }
 
@@ -677,6 +814,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int 
       : "memory");
 }
 
+// 16 bytes global -> shared without passing through registers (SASS: LDGSTS); src_bytes 0 writes zeros
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_group_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -712,7 +857,7 @@ __global__ void __launch_bounds__(BCG_EGO_THREADS, 5) ego_kernel(const BcgParams
   const int e = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const uint32_t mbar = smem_u32(&mbar_s);
-  const EgoWork w = reinterpret_cast<const EgoWork*>(b.ego_work)[e];     // warp-uniform 128-byte read
+  const EgoWork w = *reinterpret_cast<const EgoWork*>(reinterpret_cast<const uint8_t*>(b.ego_work) + (int64_t)e * BCG_EGO_WORK_BYTES);   // warp-uniform 128-byte read
   const EgoAffine A = w.aff;
   int mode = w.mode;
   const int X0 = w.x0, Y0 = w.y0;
@@ -814,6 +959,160 @@ __global__ void __launch_bounds__(BCG_EGO_THREADS, 5) ego_kernel(const BcgParams
   }
 }
 
+// ---- cell-tile egocentric kernel ----------------------------------------------------------------------------
+// Same observation as ego_kernel (EgocentricCostmap.observation, envs/egocentric.py:125-160 ->
+// extract_egocentric_costmap, utilities/costmap_utils.py:25-75 -> cv2.warpAffine INTER_NEAREST), half the HBM
+// traffic: the source window is staged from the cell tiles (BcgMapDesc), and only the 128-byte tiles the rotated
+// crop rectangle touches are read (the per-row tile spans come with the env's EgoTileWork record).
+// Persistent CTAs, 5 per SM for the 133 x 117 crop (one 39 KB window each), walking envs blockIdx.x, + gridDim.x, ...;
+// the CTAs of an SM overlap each other's load and gather phases.  Per env: 16-byte pieces of the tiles -> registers ->
+// the row-major shared-memory window (zeros outside the map = borderValue), fixed-point tables, barrier, rotated
+// gather out of shared memory, barrier.  Records are prefetched a few envs ahead with cp.async.
+// Measured (profiles/r1_notes.md): the L1 data pipe (byte gathers from shared memory + byte stores) bounds it,
+// not HBM; cp.async staging, TMA boxes of the tile view, double-buffered windows and L2 prefetch were all slower.
+#define BCG_EGT_THREADS 256
+#define BCG_EGT_CTAS 5
+#define BCG_EGT_MAX_W 160
+#define BCG_EGT_REC_SLOTS 8
+struct EgoTab {
+  int adx[BCG_EGT_MAX_W], ady[BCG_EGT_MAX_W];   // rint(a11 u 2^10), rint(a21 u 2^10)
+  int2 bxy[BCG_EGO_MAX];                        // rint((a12 v + b1) 2^10) + 512 - (X0 << 10), same for y
+  int pitch_b, mode, map_id, pad;
+};
+
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int NG>
+__global__ void __launch_bounds__(BCG_EGT_THREADS, BCG_EGT_CTAS) ego_tiles_kernel(const BcgParams p, const BcgBatch b,
+                                                                                  uint8_t* __restrict__ image,
+                                                                                  const int win_bytes) {
+  extern __shared__ __align__(128) uint8_t egt_smem[];
+  constexpr int NT = BCG_EGT_THREADS, NW = NT / 32;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  EgoTab& T = *reinterpret_cast<EgoTab*>(egt_smem + win_bytes);
+  uint8_t* const rec_s = egt_smem + win_bytes + sizeof(EgoTab);
+  const uint32_t win_u32 = smem_u32(egt_smem), rec_u32 = smem_u32(rec_s);
+  const uint8_t* const recs = reinterpret_cast<const uint8_t*>(b.ego_work);
+  const int n = b.n_envs, G = gridDim.x;
+  const int ego_w = p.ego_w, ego_h = p.ego_h, npx = ego_w * ego_h;
+  const int e0 = blockIdx.x;
+  if (e0 >= n) return;
+
+  // record of env `en` -> ring slot `slot` (the first 16 threads move 16 bytes each)
+  auto fetch_record = [&](int en, int slot) {
+    if (en < n && tid < 16)
+      cp_async_16(rec_u32 + slot * BCG_EGO_WORK_BYTES + tid * 16, recs + (int64_t)en * BCG_EGO_WORK_BYTES + tid * 16, 16u);
+  };
+
+  // The newest record fetch may still be in flight after a wait, so records are fetched RD envs ahead.
+  constexpr int RD = 3;
+  static_assert(RD < BCG_EGT_REC_SLOTS, "record ring too small");
+#pragma unroll
+  for (int k = 0; k < RD; ++k) fetch_record(e0 + k * G, k);
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();
+
+  int e = e0;
+  for (int it = 0; e < n; e += G, ++it) {
+    const int slot = it & (BCG_EGT_REC_SLOTS - 1);
+    fetch_record(e + RD * G, (it + RD) & (BCG_EGT_REC_SLOTS - 1));
+    cp_async_commit();
+    const EgoTileWork* r = reinterpret_cast<const EgoTileWork*>(rec_s + slot * BCG_EGO_WORK_BYTES);
+    const int mode = r->mode, X0 = r->X0, Y0 = r->Y0, ntx = r->ntx, nty = r->nty;
+    const int pitch_b = 16 * (ntx | 1);          // 16 * odd: staging writes and rotated reads spread over the banks
+    if (mode == BCG_EGO_MODE_TILES) {
+      // ---- stage: warp w moves the rows of tiles w, w + 8, ...; a lane moves row `piece` of every 4th tile ----------
+      const int ctx = r->ctiles_x, cty = r->ctiles_y;
+      const int ttx0 = X0 >> 4, tty0 = Y0 >> 3;
+      const int piece = lane & 7, sub = lane >> 3;
+      // the tile (tty0 + t, ttx0 + tx) adds ((tty0 + t) * ctx + tx) * 128 to src and (8 t pitch + 16 tx) to dst
+      const uint8_t* const src_lane = b.cell_tile_arena + r->ctile_off + piece * 16 + ((int64_t)ttx0 + sub) * 128;
+      const uint32_t dst_lane = win_u32 + piece * pitch_b + sub * 16;
+      const int lo_map = -ttx0, hi_map = ctx - 1 - ttx0;       // window tile columns that exist in the map
+      const uint32_t span_u32 = rec_u32 + slot * BCG_EGO_WORK_BYTES + 128;
+      for (int t = warp; t < nty; t += NW) {
+        const uint32_t sp = lds_u16(span_u32 + 2 * t);
+        const int ts = sp & 0xff, te = sp >> 8;
+        const int ty = tty0 + t;
+        const int lo = (unsigned)ty < (unsigned)cty ? max(ts, lo_map) : 0x7fffffff;   // rows outside the map: all zero
+        const int hi = min(te, hi_map);
+        const uint8_t* src = src_lane + ((int64_t)ty * ctx + ts) * 128;
+        const uint32_t dst = dst_lane + (uint32_t)(t * 8 * pitch_b + ts * 16);
+        uint4 val[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                        // 16 tile columns >= any span (the record writer checks)
+          const int tx = ts + sub + 4 * j;
+          val[j] = make_uint4(0u, 0u, 0u, 0u);               // zeros = borderValue
+          if (tx <= te && tx >= lo && tx <= hi) val[j] = __ldcg(reinterpret_cast<const uint4*>(src + 512 * j));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (ts + sub + 4 * j <= te) sts_v4(dst + 64 * j, val[j]);
+      }
+    }
+    // ---- fixed-point tables of the crop (cv::warpAffine: saturate_cast<int> == cvt.rni with saturation) -------------
+    {
+      const EgoAffine A = r->aff;
+      for (int t = tid; t < ego_w; t += NT) {
+        T.adx[t] = __double2int_rn(A.a11 * t * 1024);
+        T.ady[t] = __double2int_rn(A.a21 * t * 1024);
+      }
+      for (int t = tid; t < ego_h; t += NT)
+        T.bxy[t] = make_int2(__double2int_rn((A.a12 * t + A.b1) * 1024) + 512 - (X0 << 10),
+                             __double2int_rn((A.a22 * t + A.b2) * 1024) + 512 - (Y0 << 10));
+    }
+    const int map_id = r->map_id;
+    cp_async_wait_group_1();                  // the record needed next iteration has landed (the newest may not have)
+    __syncthreads();                          // window, tables and that record are visible to every warp
+    uint8_t* const dst = image + (int64_t)e * npx;
+    if (mode == BCG_EGO_MODE_TILES) {
+      // ---- gather: warp w takes crop rows w, w + 8, ...; lane l takes columns l, l + 32, ...  (NG = ceil(ego_w / 32):
+      // only the last column group can be partial) -----------------------------------------------------------------
+      int ax[NG], ay[NG];
+#pragma unroll
+      for (int k = 0; k < NG; ++k) {
+        const int u = min(lane + 32 * k, ego_w - 1);
+        ax[k] = T.adx[u];
+        ay[k] = T.ady[u];
+      }
+      const bool last_live = lane + 32 * (NG - 1) < ego_w;
+      const int64_t row_step = (int64_t)NW * ego_w;
+      uint8_t* d0 = dst + warp * ego_w + lane;
+      const int2* brow = T.bxy + warp;
+      for (int v = warp; v < ego_h; v += NW, brow += NW, d0 += row_step) {
+        const int2 b0 = brow[0];
+        uint32_t v0[NG];
+#pragma unroll
+        for (int k = 0; k < NG; ++k) v0[k] = lds_u8(win_u32 + ((ay[k] + b0.y) >> 10) * pitch_b + ((ax[k] + b0.x) >> 10));
+#pragma unroll
+        for (int k = 0; k < NG - 1; ++k) d0[32 * k] = (uint8_t)v0[k];
+        if (last_live) d0[32 * (NG - 1)] = (uint8_t)v0[NG - 1];
+      }
+    } else {
+      // crops too large for the window / poses far outside any sane range: bounds-checked global gather
+      const BcgMapDesc m = b.maps[map_id];
+      const uint8_t* src = b.map_arena + m.data_off;
+      for (int i = tid; i < npx; i += NT) {
+        const int vv = i / ego_w, u = i - vv * ego_w;
+        const int2 bb = T.bxy[vv];
+        const long long X = ((long long)T.adx[u] + bb.x) >> 10, Y = ((long long)T.ady[u] + bb.y) >> 10;
+        uint8_t val = 0;
+        if (X >= 0 && X < m.width && Y >= 0 && Y < m.height) val = __ldg(src + Y * m.pitch + X);
+        dst[i] = val;
+      }
+    }
+    __syncthreads();                          // every warp is done with the window, the tables and record `it`
+  }
+}
+
 // EgoWork records and / or goal_n_state from the current state (stand-alone bcg_observe_ego): one thread per env
 __global__ void __launch_bounds__(128) ego_prep_kernel(const BcgParams p, const BcgBatch b, const int want_image,
                                                        float* __restrict__ goal_n_state, const int ego_cap) {
@@ -823,7 +1122,7 @@ __global__ void __launch_bounds__(128) ego_prep_kernel(const BcgParams p, const 
   const double* sf = b.state_f + e;
   const int prow = p.ego_variant == 1 ? BCG_F_ROBOT : BCG_F_DPOSE;
   const double px = sf[(prow + 0) * N], py = sf[(prow + 1) * N], pth = sf[(prow + 2) * N];
-  if (want_image) reinterpret_cast<EgoWork*>(b.ego_work)[e] = make_ego_work(p, b, b.map_id[e], px, py, pth, ego_cap);
+  if (want_image) write_ego_record(p, b, e, b.map_id[e], px, py, pth, ego_cap);
   if (goal_n_state) write_goal_n_state(p, b, e, px, py, pth, goal_n_state);
 }
 
@@ -925,6 +1224,18 @@ int bcg_build_lethal_tiles(const BcgBatch* b, int32_t first, int32_t count, void
   return BCG_OK;
 }
 
+int bcg_build_cell_tiles(const BcgBatch* b, int32_t first, int32_t count, void* stream) {
+  BCG_REQUIRE(b && b->maps && b->map_arena && b->cell_tile_arena, "null map / cell-tile arena");
+  BCG_REQUIRE(first >= 0 && count >= 0 && first + count <= b->n_maps, "map range out of bounds");
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int32_t done = 0; done < count; done += 32768) {
+    const int32_t chunk = (count - done) < 32768 ? (count - done) : 32768;
+    cell_tiles_kernel<<<dim3(8, chunk), 256, 0, s>>>(*b, first + done);
+    BCG_CHECK_CUDA(cudaGetLastError());
+  }
+  return BCG_OK;
+}
+
 int bcg_encode_map_tensor_maps(const BcgMapDesc* maps_host, int32_t n_maps, const void* map_arena_dev,
                                const int32_t* box_w, int32_t n_widths, int32_t box_h, void* out_host) {
   BCG_REQUIRE(maps_host && map_arena_dev && out_host && box_w && n_maps >= 0, "null argument");
@@ -990,12 +1301,63 @@ static int check_ego(const BcgParams* p, const BcgBatch* b, const uint8_t* ego_i
   BCG_REQUIRE(p->ego_w > 0 && p->ego_h > 0 && p->ego_w <= BCG_EGO_MAX && p->ego_h <= BCG_EGO_MAX,
               "egocentric crop must be 1..256 pixels per side");
   if (ego_image) BCG_REQUIRE(b->ego_work, "BcgBatch.ego_work is needed for the egocentric image");
+  if (ego_image && b->cell_tile_arena) BCG_REQUIRE(p->ego_w <= BCG_EGT_MAX_W, "the cell-tile egocentric kernel handles crops up to 160 pixels wide");
   if (b->map_tmaps) BCG_REQUIRE(b->tmap_n_widths >= 1 && b->tmap_n_widths <= 4 && b->tmap_box_h > 0, "tensor-map boxes not set");
   return BCG_OK;
 }
 
-// the image kernel; the EgoWork records must already be in b->ego_work
+}  // extern "C"
+
+// capacity handed to the record writers: window buffer of the tile kernel, or shared-memory tile of ego_kernel
+static int ego_capacity(const BcgParams& p, const BcgBatch& b) {
+  return b.cell_tile_arena ? ego_window_capacity(p) : ego_tile_capacity(p, b);
+}
+
+static int sm_count_of_current_device(int* out) {
+  static int cached[64] = {0};
+  int dev = 0;
+  BCG_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || cached[dev] == 0) {
+    int n = 0;
+    BCG_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    if (dev >= 0 && dev < 64) cached[dev] = n;
+    *out = n;
+    return BCG_OK;
+  }
+  *out = cached[dev];
+  return BCG_OK;
+}
+
+template <int NG>
+static int launch_ego_tiles(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, cudaStream_t s) {
+  const int win = ego_window_capacity(*p);
+  const int smem = win + (int)sizeof(EgoTab) + BCG_EGT_REC_SLOTS * BCG_EGO_WORK_BYTES;
+  static int configured[64] = {0};    // per template instance and device: the attribute is per function and context
+  int dev = 0;
+  BCG_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || configured[dev] < smem) {
+    BCG_CHECK_CUDA(cudaFuncSetAttribute(ego_tiles_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (dev >= 0 && dev < 64) configured[dev] = smem;
+  }
+  int sms = 0;
+  if (int rc = sm_count_of_current_device(&sms)) return rc;
+  const int grid = b->n_envs < BCG_EGT_CTAS * sms ? b->n_envs : BCG_EGT_CTAS * sms;
+  ego_tiles_kernel<NG><<<grid, BCG_EGT_THREADS, smem, s>>>(*p, *b, ego_image, win);
+  BCG_CHECK_CUDA(cudaGetLastError());
+  return BCG_OK;
+}
+
+// the image kernel; the per-env records must already be in b->ego_work
 static int launch_ego_image(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, cudaStream_t s) {
+  if (b->cell_tile_arena) {
+    switch ((p->ego_w + 31) / 32) {
+      case 1: return launch_ego_tiles<1>(p, b, ego_image, s);
+      case 2: return launch_ego_tiles<2>(p, b, ego_image, s);
+      case 3: return launch_ego_tiles<3>(p, b, ego_image, s);
+      case 4: return launch_ego_tiles<4>(p, b, ego_image, s);
+      default: return launch_ego_tiles<5>(p, b, ego_image, s);
+    }
+  }
   const int cap = ego_tile_capacity(*p, *b);
   // alignment slack + the per-row spans of the plain-load path, which live behind the tile
   const int extra = 128 + BCG_EGO_MAX_TILE_ROWS * (int)sizeof(short2);
@@ -1004,13 +1366,15 @@ static int launch_ego_image(const BcgParams* p, const BcgBatch* b, uint8_t* ego_
   return BCG_OK;
 }
 
+extern "C" {
+
 int bcg_observe_ego(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, float* goal_n_state, void* stream) {
   if (int rc = check_batch(p, b)) return rc;
   BCG_REQUIRE(ego_image || goal_n_state, "nothing to compute");
   if (int rc = check_ego(p, b, ego_image)) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   ego_prep_kernel<<<blocks_for(b->n_envs, 128), 128, 0, s>>>(*p, *b, ego_image ? 1 : 0, goal_n_state,
-                                                            ego_tile_capacity(*p, *b));
+                                                            ego_capacity(*p, *b));
   BCG_CHECK_CUDA(cudaGetLastError());
   if (ego_image) return launch_ego_image(p, b, ego_image, s);
   return BCG_OK;
@@ -1033,7 +1397,7 @@ int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, 
   collide_reward_kernel<<<blocks_for((int64_t)b->n_envs * 32, 256), 256, 0, s>>>(*p, *b);
   BCG_CHECK_CUDA(cudaGetLastError());
   if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[2], s));
-  commit_kernel<<<blocks_for(b->n_envs, 128), 128, 0, s>>>(*p, *b, L, *out, ego ? ego_tile_capacity(*p, *b) : 0);
+  commit_kernel<<<blocks_for(b->n_envs, 128), 128, 0, s>>>(*p, *b, L, *out, ego ? ego_capacity(*p, *b) : 0);
   BCG_CHECK_CUDA(cudaGetLastError());
   if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[3], s));
   if (out->ego_image) {

@@ -83,7 +83,8 @@ class VecState(object):
 class VecPlanEnv(object):
     def __init__(self, costmaps, paths, params=None, n_envs=None, map_ids=None, path_ids=None,
                  noise_parameters=DEFAULT_NOISE, seed=0, auto_reset=False, device=None, env_id_base=0,
-                 private_map_copies=False, with_ego=False, footprint_scale=1.0, use_tma=True, footprint=None):
+                 private_map_copies=False, with_ego=False, footprint_scale=1.0, use_tma=True, footprint=None,
+                 ego_staging='tiles'):
         """
         :param costmaps: pool of CostMap2D (uint8), one resolution
         :param paths: pool of oriented paths, array(n, 3); refined here when params.refine_path
@@ -94,6 +95,9 @@ class VecPlanEnv(object):
             on device) instead of sharing pool entries
         :param with_ego: assemble the egocentric observation inside every step
         :param footprint: explicit footprint polygon array(n, 2) in metres (default: the robot's own)
+        :param ego_staging: how the egocentric kernel stages its source window: 'tiles' (default; a derived
+            copy of every costmap in 128-byte cell tiles, only the tiles the rotated window touches are read),
+            'tma' (box loads of the window's bounding box from the uint8 rows) or 'spans' (plain loads)
         """
         nat.require_cuda()
         self.params = params if params is not None else EnvParams()
@@ -115,7 +119,12 @@ class VecPlanEnv(object):
         self.robot_kind = nat.ROBOT_TRICYCLE if self.dims.drive_type == TRICYCLE else nat.ROBOT_DIFFDRIVE
         self.auto_reset = bool(auto_reset)
         self.with_ego = bool(with_ego)
-        self.use_tma = bool(use_tma)
+        if ego_staging not in ('tiles', 'tma', 'spans'):
+            raise ValueError("ego_staging must be 'tiles', 'tma' or 'spans'")
+        if not use_tma:                      # older spelling: plain loads, no derived planes for the ego kernel
+            ego_staging = 'spans'
+        self.ego_staging = ego_staging
+        self.use_tma = ego_staging == 'tma'
         self._step_index = 0
 
         self._c_params = self._make_params(noise_parameters, seed, env_id_base)
@@ -127,6 +136,8 @@ class VecPlanEnv(object):
         self._make_batch()
         s = self._stream()
         nat.check(nat.lib().bcg_build_lethal_tiles(C.byref(self._batch), 0, self._batch.n_maps, s))
+        if self.cell_tile_arena is not None:
+            nat.check(nat.lib().bcg_build_cell_tiles(C.byref(self._batch), 0, self._batch.n_maps, s))
         nat.check(nat.lib().bcg_init_state(C.byref(self._c_params), C.byref(self._batch), s))
         self.check_status()
 
@@ -168,7 +179,7 @@ class VecPlanEnv(object):
 
     def _upload_maps(self, costmaps, private_copies):
         descs = (nat.BcgMapDesc * len(costmaps))()
-        data_off, tile_off = 0, 0
+        data_off, tile_off, ctile_off = 0, 0, 0
         for k, cm in enumerate(costmaps):
             data = cm.get_data()
             if data.dtype != np.uint8 or data.ndim != 2:
@@ -182,15 +193,17 @@ class VecPlanEnv(object):
             d.height, d.width, d.pitch = h, w, _round_up(w, 32)
             d.tiles_x, d.tiles_y = d.pitch // 32, (h + 15) // 16
             d.origin_x, d.origin_y = float(cm.get_origin()[0]), float(cm.get_origin()[1])
-            d.data_off, d.tile_off = data_off, tile_off
+            d.ctiles_x, d.ctiles_y = d.pitch // 16, (h + 7) // 8
+            d.data_off, d.tile_off, d.cell_tile_off = data_off, tile_off, ctile_off
             data_off += _round_up(h * d.pitch, 128)
             tile_off += d.tiles_x * d.tiles_y * 16
+            ctile_off += d.ctiles_x * d.ctiles_y * 128
         arena = np.zeros(data_off, dtype=np.uint8)
         for k, cm in enumerate(costmaps):
             d = descs[k]
             view = arena[d.data_off:d.data_off + d.height * d.pitch].reshape(d.height, d.pitch)
             view[:, :d.width] = cm.get_data()
-        pool_bytes, pool_words = data_off, tile_off
+        pool_bytes, pool_words, pool_ctile_bytes = data_off, tile_off, ctile_off
         map_arena = self._to_device(arena)
         ids = self._map_ids_host
         if private_copies:
@@ -208,9 +221,11 @@ class VecPlanEnv(object):
                 C.memmove(C.byref(table[e]), C.byref(descs[int(ids[e])]), C.sizeof(nat.BcgMapDesc))
                 table[e].data_off += int(copy_idx[e]) * pool_bytes
                 table[e].tile_off += int(copy_idx[e]) * pool_words
+                table[e].cell_tile_off += int(copy_idx[e]) * pool_ctile_bytes
             descs = table
             ids = np.arange(self.n_envs)
             pool_words *= copies
+            pool_ctile_bytes *= copies
         self._map_descs_host = descs
         self.map_arena = map_arena
         # TMA tensor maps for the egocentric kernel's source-window staging: three box-width classes
@@ -218,11 +233,15 @@ class VecPlanEnv(object):
         self._tmap_widths, self._tmap_box_h = (144, 176, 208), 8
         widths = (C.c_int32 * len(self._tmap_widths))(*self._tmap_widths)
         tm = np.zeros(len(descs) * len(self._tmap_widths) * 128, dtype=np.uint8)
-        nat.check(nat.lib().bcg_encode_map_tensor_maps(descs, len(descs), C.c_void_p(map_arena.data_ptr()), widths,
-                                                       len(self._tmap_widths), self._tmap_box_h,
-                                                       C.c_void_p(tm.ctypes.data)))
-        self.map_tmaps = self._to_device(tm)
         self.tile_arena = torch.zeros(max(pool_words, 1), dtype=torch.int32, device=self.device)
+        self.cell_tile_arena = None
+        if self.ego_staging == 'tiles':
+            self.cell_tile_arena = torch.empty(max(pool_ctile_bytes, 128), dtype=torch.uint8, device=self.device)
+        if self.ego_staging == 'tma':
+            nat.check(nat.lib().bcg_encode_map_tensor_maps(descs, len(descs), C.c_void_p(map_arena.data_ptr()), widths,
+                                                           len(self._tmap_widths), self._tmap_box_h,
+                                                           C.c_void_p(tm.ctypes.data)))
+        self.map_tmaps = self._to_device(tm)
         self.map_descs = self._to_device(np.frombuffer(bytes(descs), dtype=np.uint8).copy())
         self.map_id = self._to_device(ids.astype(np.int32))
         self._n_maps = len(descs)
@@ -277,7 +296,7 @@ class VecPlanEnv(object):
         self._cand = torch.zeros((9, n), dtype=torch.float64, device=dev)
         self._cand_i = torch.zeros((2, n), dtype=torch.int32, device=dev)
         self._work = torch.zeros((n, 192), dtype=torch.uint8, device=dev)
-        self._ego_work = torch.zeros((n, 128), dtype=torch.uint8, device=dev)
+        self._ego_work = torch.zeros((n, 256), dtype=torch.uint8, device=dev)
         self._status = torch.zeros(nat.STATUS_WORDS, dtype=torch.int32, device=dev)
         self._stats = torch.zeros(nat.STATS_WORDS, dtype=torch.float64, device=dev)
         self.reward = torch.zeros(n, dtype=torch.float64, device=dev)
@@ -309,6 +328,8 @@ class VecPlanEnv(object):
         b.lut.bucket_scale = self.lut.bucket_scale
         b.lut.n_bins, b.lut.n_verts, b.lut.max_rows, b.lut.wpr = self.lut.n_bins, self.lut.n_verts, self.lut.max_rows, self.lut.wpr
         b.status, b.stats = self._status.data_ptr(), self._stats.data_ptr()
+        if self.cell_tile_arena is not None:
+            b.cell_tile_arena = self.cell_tile_arena.data_ptr()
         if self.use_tma:
             b.map_tmaps, b.tmap_n_widths, b.tmap_box_h = self.map_tmaps.data_ptr(), len(self._tmap_widths), self._tmap_box_h
             for j, w in enumerate(self._tmap_widths):

@@ -39,6 +39,8 @@ def parse_args():
     ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
     ap.add_argument("--pool", type=int, default=2048, help="distinct random aisle maps generated on the host")
     ap.add_argument("--no-ego", action="store_true", help="skip the egocentric observation kernel (not the headline)")
+    ap.add_argument("--ego-staging", default="tiles", choices=["tiles", "tma", "spans"],
+                    help="how the egocentric kernel stages its source window (see VecPlanEnv)")
     ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--ref-envs", type=int, default=16, help="reference arm: envs advanced per worker per step")
@@ -247,7 +249,8 @@ def build_env(args, rank, device):
     params = aisle_params()
     costmaps, paths = random_aisle_pool(args.pool, 10000 + rank * args.pool, params)
     env = VecPlanEnv(costmaps, paths, params, n_envs=args.envs, seed=1234, auto_reset=True, device=device,
-                     env_id_base=rank * args.envs, private_map_copies=True, with_ego=not args.no_ego)
+                     env_id_base=rank * args.envs, private_map_copies=True, with_ego=not args.no_ego,
+                     ego_staging=args.ego_staging)
     return env
 
 

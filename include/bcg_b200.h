@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BCG_ABI_VERSION 1
+#define BCG_ABI_VERSION 2
 
 /* error codes */
 #define BCG_OK 0
@@ -111,7 +111,10 @@ typedef struct BcgParams {
                                  towards the last path point, 5 values [gx, gy, v, w, wheel] (slots 5..8 zero) */
 } BcgParams;
 
-/* one costmap of the arena: CostMap2D (utilities/costmap_2d.py:13-37) + its derived lethal bit-plane */
+/* one costmap of the arena: CostMap2D (utilities/costmap_2d.py:13-37) + its derived planes: the lethal
+ * bit-plane (collision) and the cell tiles (the same uint8 cells re-laid out as 128-byte tiles of 16 px x 8
+ * rows, tile (ty, tx) at cell_tile_off + (ty * ctiles_x + tx) * 128, row r of a tile at + r * 16, zero
+ * beyond the map; the egocentric kernel fetches whole HBM lines of a rotated window from it) */
 typedef struct BcgMapDesc {
   int64_t data_off;  /* byte offset of uint8 [H][pitch] in the map arena                      */
   int64_t tile_off;  /* uint32 offset of the lethal tile plane in the tile arena               */
@@ -119,6 +122,8 @@ typedef struct BcgMapDesc {
   int32_t height, width, pitch;
   int32_t tiles_x, tiles_y; /* 32 px x 16 rows per 64-byte tile                                */
   int32_t reserved;
+  int64_t cell_tile_off;    /* byte offset of the map's cell tiles in the cell-tile arena (multiple of 128) */
+  int32_t ctiles_x, ctiles_y; /* 16 px x 8 rows per 128-byte cell tile: pitch / 16, ceil(height / 8)     */
 } BcgMapDesc;
 
 /* one refined path: fp64 SoA rows x,y,th,cos(th),sin(th), each `pitch` long, then chunk bounds */
@@ -157,7 +162,7 @@ typedef struct BcgBatch {
   double* cand;    /* scratch [9][n_envs]: robot state proposed by the kinematic kernel (7 rows), then
                       this step's reward and new min_dist from the collide/reward kernel            */
   int32_t* cand_i; /* scratch [2][n_envs]: new target_idx and verdict flags from the collide/reward kernel */
-  void* ego_work;  /* scratch [n_envs][128 bytes]: per-env affine map + source window of the egocentric crop,
+  void* ego_work;  /* scratch [n_envs][256 bytes]: per-env affine map + source window of the egocentric crop,
                       written by the commit kernel (or bcg_observe_ego) for the egocentric kernel; may be
                       NULL when no egocentric image is ever requested                                      */
   void* work;      /* scratch [n_envs][192 bytes]: per-env work records (map / path / footprint references and
@@ -176,6 +181,10 @@ typedef struct BcgBatch {
   int32_t tmap_n_widths;  /* 1..4 box-width classes, ascending                                           */
   int32_t tmap_box_h;     /* rows per box                                                                */
   int32_t tmap_box_w[4];  /* box widths (multiples of 16) the tensor maps were encoded with              */
+  const uint8_t* cell_tile_arena; /* optional: cell tiles of every map (bcg_build_cell_tiles); when set the
+                            egocentric kernel stages only the 128-byte tiles its rotated source window
+                            touches (16-byte cp.async pieces, zero fill outside the map) and map_tmaps is
+                            not used                                                                      */
   uint32_t* status; /* [BCG_STATUS_WORDS] */
   double* stats;    /* [BCG_STATS_WORDS]  */
 } BcgBatch;
@@ -213,6 +222,8 @@ int bcg_state_layout(const BcgParams* p, BcgStateLayout* out);
 /* -- setup (at reset time, not per step) ------------------------------------------------------------ */
 /* derive the lethal bit-plane (cell == 254, costmap_2d.py:21) of maps [first, first+count) */
 int bcg_build_lethal_tiles(const BcgBatch* b, int32_t first, int32_t count, void* stream);
+/* derive the cell tiles (see BcgMapDesc) of maps [first, first+count) from the uint8 rows */
+int bcg_build_cell_tiles(const BcgBatch* b, int32_t first, int32_t count, void* stream);
 /* Host-side: encode n_widths CUtensorMaps (128 B each, cuTensorMapEncodeTiled) per costmap -- uint8
  * [H][pitch] tensor, boxes (box_w[j], box_h), zero fill outside the map (= cv2.warpAffine's
  * borderValue 0, utilities/costmap_utils.py:72) -- into out_host [n_maps][n_widths][128 bytes].  The

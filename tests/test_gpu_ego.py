@@ -9,11 +9,11 @@ from tests import common
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("use_tma", [True, False])
-def test_ego_observation_matches_reference(use_tma):
-    """Both ways of staging the source window (TMA box loads, plain span loads) against cv2."""
+@pytest.mark.parametrize("staging", ["tiles", "tma", "spans"])
+def test_ego_observation_matches_reference(staging):
+    """All ways of staging the source window (cell tiles via cp.async, TMA box loads, plain span loads) against cv2."""
     d = common.load("aisle_ego")
-    env = common.make_vec_env(d, with_ego=True, use_tma=use_tma)
+    env = common.make_vec_env(d, with_ego=True, ego_staging=staging)
     actions = torch.from_numpy(d["actions"]).cuda()
     every = int(d["every"])
     k = 0

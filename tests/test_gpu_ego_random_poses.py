@@ -1,6 +1,6 @@
 """-m gpu: egocentric crops at arbitrary poses -- deep inside, straddling every map edge and far
 outside the map -- against the oracle's closed form of cv2.warpAffine (itself pinned against cv2 in the
-CPU suite), for both staging paths of the kernel."""
+CPU suite), for every staging path of the kernel."""
 import numpy as np
 import pytest
 import torch
@@ -12,10 +12,10 @@ from tests import common
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("use_tma", [True, False])
-def test_ego_crops_at_random_poses(use_tma):
+@pytest.mark.parametrize("staging", ["tiles", "tma", "spans"])
+def test_ego_crops_at_random_poses(staging):
     d = common.load("aisle_collision")
-    env = common.make_vec_env(d, with_ego=True, use_tma=use_tma)
+    env = common.make_vec_env(d, with_ego=True, ego_staging=staging)
     maps = common.fixture_envs(d)
     res = float(d["resolution"])
     rng = np.random.RandomState(3)
