@@ -70,6 +70,22 @@ class BcgBatch(C.Structure):
     ]
 
 
+class BcgTurnParams(C.Structure):
+    _fields_ = [
+        ("main_corridor_length", C.c_double), ("turn_corridor_length", C.c_double), ("turn_corridor_angle", C.c_double),
+        ("main_corridor_width", C.c_double), ("turn_corridor_width", C.c_double), ("margin", C.c_double),
+        ("rot_theta", C.c_double), ("flip_arnd_oy", C.c_int32), ("flip_arnd_ox", C.c_int32),
+    ]
+
+
+class BcgAisleSlots(C.Structure):
+    _fields_ = [
+        ("map_slot_bytes", C.c_int64), ("tile_slot_words", C.c_int64),
+        ("path_pitch", C.c_int32), ("chunk_pitch", C.c_int32),
+        ("gen_state", C.c_void_p), ("params_out", C.c_void_p),
+    ]
+
+
 class BcgStateLayout(C.Structure):
     _fields_ = [
         ("n_frows", C.c_int32), ("n_irows", C.c_int32),
@@ -84,12 +100,13 @@ class BcgStepOut(C.Structure):
     ]
 
 
-_STRUCTS = [BcgParams, BcgMapDesc, BcgPathDesc, BcgFootprintLut, BcgBatch, BcgStateLayout, BcgStepOut]
+_STRUCTS = [BcgParams, BcgMapDesc, BcgPathDesc, BcgFootprintLut, BcgBatch, BcgStateLayout, BcgStepOut, BcgTurnParams,
+            BcgAisleSlots]
 
 # fixed rows / words of include/bcg_b200.h
 F_ROBOT, F_DROBOT, F_DPOSE, F_TIME, F_MIN_DIST, F_EP_RETURN, F_FIXED = 0, 7, 14, 17, 18, 19, 20
 I_ITER, I_TARGET, I_COLLIDED, I_QC, I_QP, I_QS, I_FIXED = 0, 1, 2, 3, 4, 5, 6
-STATUS_LUT_MISS, STATUS_PATH_EXHAUSTED, STATUS_WORDS = 0, 1, 8
+STATUS_LUT_MISS, STATUS_PATH_EXHAUSTED, STATUS_SLOT_OVERFLOW, STATUS_WORDS = 0, 1, 2, 8
 STAT_NAMES = ("episodes", "return", "length", "collided", "goal", "timeout")
 STATS_WORDS = 8
 ROBOT_TRICYCLE, ROBOT_DIFFDRIVE = 0, 1
@@ -108,6 +125,8 @@ SYMBOLS = {
     "bcg_encode_map_tensor_maps": (C.c_int, [C.POINTER(BcgMapDesc), C.c_int32, _P, C.POINTER(C.c_int32), C.c_int32,
                                              C.c_int32, _P]),
     "bcg_init_state": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgBatch), _P]),
+    "bcg_generate_aisles": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgBatch), C.POINTER(BcgAisleSlots), _P, _P, C.c_uint64,
+                                      C.c_double, _P]),
     "bcg_reset_where": (C.c_int, [C.POINTER(BcgBatch), _P, _P]),
     "bcg_step": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgBatch), _P, C.c_int32, C.c_uint64,
                            C.POINTER(BcgStepOut), _P]),

@@ -16,6 +16,7 @@
 
 #include "bcg_b200.h"
 #include "bcg_device.cuh"
+#include "bcg_generate.cuh"
 
 using namespace bcg;
 
@@ -663,13 +664,10 @@ __global__ void __launch_bounds__(128) commit_kernel(const BcgParams p, const Bc
   }
 }
 
-// make_initial_state (env.py:179-214) + generate_initial_state (reward.py:261-288); one warp per env.
-__global__ void __launch_bounds__(256) init_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L) {
-  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const unsigned lane = threadIdx.x & 31;
-  if (e >= b.n_envs) return;
+// make_initial_state (env.py:179-214) + generate_initial_state (reward.py:261-288) of env e by one warp
+__device__ __forceinline__ void init_env_state(const BcgParams& p, const BcgBatch& b, const BcgStateLayout& L, int e,
+                                               const PathRef& pd, unsigned lane) {
   const int64_t N = b.n_envs;
-  const PathRef pd = path_ref(b, b.paths[b.path_id[e]]);
   const double* P = pd.P;
   const double x0 = P[0], y0 = P[pd.pitch], t0 = P[2 * pd.pitch];
   int target;
@@ -699,6 +697,119 @@ __global__ void __launch_bounds__(256) init_kernel(const BcgParams p, const BcgB
     const int v = (r == BCG_I_TARGET) ? target : 0;
     b.init_i[(int64_t)r * N + e] = v;
     b.state_i[(int64_t)r * N + e] = v;
+  }
+}
+
+// one warp per env
+__global__ void __launch_bounds__(256) init_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L) {
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  if (e >= b.n_envs) return;
+  init_env_state(p, b, L, e, path_ref(b, b.paths[b.path_id[e]]), lane);
+}
+
+// bcg_generate_aisles: one CTA per env (see bcg_generate.cuh)
+__global__ void __launch_bounds__(256) generate_aisles_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L,
+                                                              const BcgAisleSlots slots, const uint8_t* __restrict__ mask,
+                                                              const BcgTurnParams* __restrict__ turn_params,
+                                                              const uint64_t draw_index, const double path_delta) {
+  const int e = blockIdx.x;
+  if (mask && !mask[e]) return;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const BcgTurnParams tp = turn_params ? turn_params[e] : draw_turn_params(p.seed, p.env_id_base + (uint64_t)e, draw_index);
+  // every thread works the geometry out for itself (a few hundred flops; no broadcast, no barrier)
+  const AisleGeometry g = aisle_geometry(tp, p.inv_resolution);
+  const RefinedShape shape = refined_shape(g.way, path_delta);
+  BcgMapDesc* md = const_cast<BcgMapDesc*>(b.maps) + e;
+  BcgPathDesc* pdsc = const_cast<BcgPathDesc*>(b.paths) + e;
+  const int pitch = (g.width + 31) & ~31;
+  const int tiles_x = pitch >> 5, tiles_y = (g.height + 15) >> 4, ctiles_x = pitch >> 4, ctiles_y = (g.height + 7) >> 3;
+  const bool fits = g.width > 0 && g.height > 0 && g.width < 32768 && g.height < 32768 &&
+                    (int64_t)g.height * pitch <= slots.map_slot_bytes &&
+                    (int64_t)ctiles_x * ctiles_y * 128 <= slots.map_slot_bytes &&
+                    (int64_t)tiles_x * tiles_y * 16 <= slots.tile_slot_words && shape.n <= slots.path_pitch &&
+                    (shape.n + 31) / 32 <= slots.chunk_pitch;
+  if (!fits) {                                  // leave the env exactly as it was
+    if (tid == 0) atomicAdd(b.status + BCG_STATUS_SLOT_OVERFLOW, 1u);
+    return;
+  }
+  AisleGenState* gs = reinterpret_cast<AisleGenState*>(slots.gen_state) + e;
+  MapLayout m;
+  m.data = const_cast<uint8_t*>(b.map_arena) + md->data_off;
+  m.tiles = const_cast<uint32_t*>(b.tile_arena) + md->tile_off;
+  m.ctiles = const_cast<uint8_t*>(b.cell_tile_arena) + md->cell_tile_off;
+  // ---- erase what the slot holds (with the layout it was drawn in) -------------------------------------------
+  if (gs->valid) {
+    MapLayout old = m;
+    old.pitch = gs->pitch; old.rows = gs->rows; old.tiles_x = gs->tiles_x; old.ctiles_x = gs->ctiles_x;
+    for (int k = 0; k < 5; ++k) draw_wall(old, gs->wall[k][0], gs->wall[k][1], gs->wall[k][2], gs->wall[k][3], 0, tid, nthr);
+  }
+  __syncthreads();                              // erased pixels may be drawn again; gs is about to be rewritten
+  // ---- draw the new walls: Wall.render (envs/base/maps.py:27-42), thickness max(1, int(0.05 / res)) = 1 px -------
+  m.pitch = pitch; m.rows = g.height; m.tiles_x = tiles_x; m.ctiles_x = ctiles_x;
+  int wpx[5][4];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    wpx[k][0] = world_to_pixel_1d(g.wall[k][0], g.origin_x, p.inv_resolution);
+    wpx[k][1] = world_to_pixel_1d(g.wall[k][1], g.origin_y, p.inv_resolution);
+    wpx[k][2] = world_to_pixel_1d(g.wall[k][2], g.origin_x, p.inv_resolution);
+    wpx[k][3] = world_to_pixel_1d(g.wall[k][3], g.origin_y, p.inv_resolution);
+    draw_wall(m, wpx[k][0], wpx[k][1], wpx[k][2], wpx[k][3], 254, tid, nthr);
+  }
+  if (tid == 0) {
+    AisleGenState ns;
+    for (int k = 0; k < 5; ++k)
+      for (int c = 0; c < 4; ++c) ns.wall[k][c] = wpx[k][c];
+    ns.pitch = pitch; ns.rows = g.height; ns.tiles_x = tiles_x; ns.ctiles_x = ctiles_x;
+    ns.valid = 1;
+    for (int k = 0; k < 7; ++k) ns.pad[k] = 0;
+    *gs = ns;
+    md->origin_x = g.origin_x; md->origin_y = g.origin_y;
+    md->height = g.height; md->width = g.width; md->pitch = pitch;
+    md->tiles_x = tiles_x; md->tiles_y = tiles_y; md->ctiles_x = ctiles_x; md->ctiles_y = ctiles_y;
+    pdsc->n = shape.n;
+    pdsc->pitch = slots.path_pitch;
+    pdsc->n_chunks = (shape.n + 31) / 32;
+    pdsc->chunk_pitch = slots.chunk_pitch;
+    pdsc->chunk_off = pdsc->off + 5 * (int64_t)slots.path_pitch;
+    if (slots.params_out) slots.params_out[e] = tp;
+  }
+  // ---- refined path rows x, y, th, cos th, sin th ------------------------------------------------------------------
+  double* P = const_cast<double*>(b.path_arena) + pdsc->off;
+  const int pp = slots.path_pitch;
+  for (int i = tid; i < shape.n; i += nthr) {
+    double x, y, th, sn, cs;
+    refined_point(g.way, shape, i, x, y, th);
+    sincos(th, &sn, &cs);
+    P[i] = x; P[pp + i] = y; P[2 * pp + i] = th; P[3 * pp + i] = cs; P[4 * pp + i] = sn;
+  }
+  __syncthreads();                              // the path rows are visible to the whole CTA
+  // ---- bounding circles of 32-point chunks (conservative; see last_reached_from) ----------------------------------
+  double* Cb = P + 5 * (int64_t)pp;
+  const int warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
+  for (int c = warp; c * 32 < shape.n; c += nwarp) {
+    const int i = min(c * 32 + lane, shape.n - 1);
+    const double x = P[i], y = P[pp + i];
+    double xlo = x, xhi = x, ylo = y, yhi = y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      xlo = fmin(xlo, __shfl_xor_sync(BCG_FULL, xlo, o)); xhi = fmax(xhi, __shfl_xor_sync(BCG_FULL, xhi, o));
+      ylo = fmin(ylo, __shfl_xor_sync(BCG_FULL, ylo, o)); yhi = fmax(yhi, __shfl_xor_sync(BCG_FULL, yhi, o));
+    }
+    const double ctx = 0.5 * (xlo + xhi), cty = 0.5 * (ylo + yhi);
+    double rad = hypot(x - ctx, y - cty);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rad = fmax(rad, __shfl_xor_sync(BCG_FULL, rad, o));
+    if (lane == 0) {
+      Cb[c] = ctx; Cb[slots.chunk_pitch + c] = cty; Cb[2 * slots.chunk_pitch + c] = rad * (1 + 1e-12) + 1e-9;
+    }
+  }
+  __syncthreads();
+  // ---- initial state ----------------------------------------------------------------------------------------------
+  if (warp == 0) {
+    PathRef pr;
+    pr.P = P; pr.C = Cb; pr.n = shape.n; pr.pitch = pp; pr.chunk_pitch = slots.chunk_pitch;
+    init_env_state(p, b, L, e, pr, lane);
   }
 }
 
@@ -1191,6 +1302,8 @@ int64_t bcg_sizeof(int32_t which) {
     case 4: return sizeof(BcgBatch);
     case 5: return sizeof(BcgStateLayout);
     case 6: return sizeof(BcgStepOut);
+    case 7: return sizeof(BcgTurnParams);
+    case 8: return sizeof(BcgAisleSlots);
     default: return -1;
   }
 }
@@ -1276,6 +1389,23 @@ int bcg_encode_map_tensor_maps(const BcgMapDesc* maps_host, int32_t n_maps, cons
 int bcg_init_state(const BcgParams* p, const BcgBatch* b, void* stream) {
   if (int rc = check_batch(p, b)) return rc;
   init_kernel<<<blocks_for((int64_t)b->n_envs * 32, 256), 256, 0, (cudaStream_t)stream>>>(*p, *b, make_layout(*p));
+  BCG_CHECK_CUDA(cudaGetLastError());
+  return BCG_OK;
+}
+
+int bcg_generate_aisles(const BcgParams* p, const BcgBatch* b, const BcgAisleSlots* slots, const uint8_t* mask,
+                        const BcgTurnParams* turn_params, uint64_t draw_index, double path_delta, void* stream) {
+  if (int rc = check_batch(p, b)) return rc;
+  BCG_REQUIRE(slots && slots->gen_state, "null slots / gen_state");
+  BCG_REQUIRE(b->cell_tile_arena, "bcg_generate_aisles needs the cell-tile arena");
+  BCG_REQUIRE(!b->map_tmaps, "bcg_generate_aisles cannot re-encode TMA tensor maps; use cell-tile or plain-load staging");
+  BCG_REQUIRE(b->n_maps == b->n_envs && b->n_paths == b->n_envs, "device-generated envs own one map and one path slot each");
+  BCG_REQUIRE(slots->map_slot_bytes > 0 && slots->tile_slot_words > 0 && slots->path_pitch >= 8 && slots->path_pitch % 4 == 0 &&
+                  slots->chunk_pitch * 32 >= slots->path_pitch,
+              "bad slot sizes");
+  BCG_REQUIRE(path_delta > 0, "path_delta must be positive");
+  generate_aisles_kernel<<<b->n_envs, 256, 0, (cudaStream_t)stream>>>(*p, *b, make_layout(*p), *slots, mask, turn_params,
+                                                                     draw_index, path_delta);
   BCG_CHECK_CUDA(cudaGetLastError());
   return BCG_OK;
 }

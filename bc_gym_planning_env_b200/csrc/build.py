@@ -13,7 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 SOURCES = [os.path.join(HERE, "bcg_kernels.cu")]
-HEADERS = [os.path.join(HERE, "bcg_device.cuh"), os.path.join(ROOT, "include", "bcg_b200.h")]
+HEADERS = [os.path.join(HERE, "bcg_device.cuh"), os.path.join(HERE, "bcg_generate.cuh"),
+           os.path.join(ROOT, "include", "bcg_b200.h")]
 TARGET = os.path.join(HERE, "libbcg_b200.so")
 
 

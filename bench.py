@@ -55,6 +55,7 @@ def workload_config(args, n_envs):
         "map_pool": args.pool,
         "maps": "random aisle turns (RandomAisleTurnEnv distribution); pool of %d distinct maps generated on the host, "
                 "replicated on device so every env owns a private costmap copy in HBM" % args.pool,
+        "ego_staging": args.ego_staging,
         "l2": "inputs larger than L2 (per-env costmaps + egocentric output are GBs per step); no explicit flush",
     }
 
@@ -349,17 +350,27 @@ def run_b200(args):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
 
+    # DRAM bytes per launch of each kernel from the committed `ncu --set full` capture of this workload
+    # (profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum at 65 536 envs); null for other sizes
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if int(tj.get("envs_per_gpu", -1)) == n:
+            traffic = tj.get("dram_bytes_per_launch", {})
+
     def roof(kernel, alg_bytes, ms, note):
         ach = alg_bytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         return {"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms, "peak_source": peak_src,
-                "note": note}
+                "traffic": traffic.get(kernel.split(" ")[0]), "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms,
+                "peak_source": peak_src, "note": note}
 
     roof_commit = roof("collide_reward_kernel", coll_bytes + scan_bytes, cr_ms,
                        "algorithmic bytes (SURVEY 8d) = in-map footprint pixels x 1 B (uint8 definition; the kernel reads "
                        "the derived 1-bit lethal tile plane) + remaining path points x 24 B (the kernel skips path chunks "
                        "farther than the reach radius); collision-only share: %.1f MB" % (coll_bytes / 1e6))
-    roof_ego = roof("ego_kernel", ego_bytes, ego_ms, "algorithmic bytes = 2 x ego_w x ego_h per env (gather + write)")
+    ego_name = "ego_tiles_kernel" if args.ego_staging == "tiles" else "ego_kernel"
+    roof_ego = roof(ego_name, ego_bytes, ego_ms, "algorithmic bytes = 2 x ego_w x ego_h per env (gather + write); staging: " + args.ego_staging)
     dominant = roof_ego if (not args.no_ego and ego_ms >= cr_ms) else roof_commit
 
     # ---- stand-alone collision kernels, cold L2 (flush between launches) ----------------------------
@@ -424,7 +435,7 @@ def run_b200(args):
             "roofline": dominant,
             "roofline_collision": roof_commit,
             "roofline_ego": None if args.no_ego else roof_ego,
-            "kernels_ms": {"kin_kernel": kin_ms, "collide_reward_kernel": cr_ms, "commit_kernel": commit_ms, "ego_kernel": ego_ms,
+            "kernels_ms": {"kin_kernel": kin_ms, "collide_reward_kernel": cr_ms, "commit_kernel": commit_ms, ego_name: ego_ms,
                            "collision_tiles_cold_l2": tiles_ms, "collision_u8_cold_l2": u8_ms},
             "collision_standalone": {
                 "tiles": roof("collision_kernel (lethal tile plane), cold L2", coll_bytes, tiles_ms, "uint8-definition bytes"),

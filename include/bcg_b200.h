@@ -65,6 +65,7 @@ extern "C" {
 /* device status words (uint32 counters, length BCG_STATUS_WORDS) */
 #define BCG_STATUS_LUT_MISS 0     /* footprint tuple not found in the angle-bin table */
 #define BCG_STATUS_PATH_EXHAUSTED 1 /* init: "Goal pose too close to initial pose" (reward.py:275-277) */
+#define BCG_STATUS_SLOT_OVERFLOW 2  /* bcg_generate_aisles: a drawn map / path did not fit its slot; env left as it was */
 #define BCG_STATUS_WORDS 8
 
 /* episode statistics accumulated on device at episode end (fp64, length BCG_STATS_WORDS) */
@@ -189,6 +190,28 @@ typedef struct BcgBatch {
   double* stats;    /* [BCG_STATS_WORDS]  */
 } BcgBatch;
 
+/* TurnParams (envs/synth_turn_env.py:18-31): geometry of one aisle turn */
+typedef struct BcgTurnParams {
+  double main_corridor_length, turn_corridor_length, turn_corridor_angle;
+  double main_corridor_width, turn_corridor_width, margin, rot_theta;
+  int32_t flip_arnd_oy, flip_arnd_ox;
+} BcgTurnParams;
+
+/* Fixed-size per-env slots for environments that are (re)generated on the device (bcg_generate_aisles).
+ * Env e owns maps[e] and paths[e] (n_maps == n_paths == n_envs, map_id[e] == path_id[e] == e); the offsets in
+ * its descriptors are set once by the host (e * slot size) and never change, the generator rewrites the
+ * geometry fields (height, width, pitch, origin, tile counts, path length).  The map, cell-tile and lethal-tile
+ * slots must be zero when an env is generated for the first time. */
+typedef struct BcgAisleSlots {
+  int64_t map_slot_bytes;    /* capacity of one env's uint8 rows, and of its cell tiles           */
+  int64_t tile_slot_words;   /* capacity of one env's lethal tile plane (uint32 words)            */
+  int32_t path_pitch;        /* row pitch of one env's 5 path rows (points); multiple of 4        */
+  int32_t chunk_pitch;       /* row pitch of its 3 chunk rows; >= ceil(path_pitch / 32)           */
+  void* gen_state;           /* device scratch [n_envs][128 bytes], zero before the first call:
+                                the walls currently drawn in each slot (to erase them cheaply)     */
+  BcgTurnParams* params_out; /* optional device [n_envs]: the turn each regenerated env now has   */
+} BcgAisleSlots;
+
 typedef struct BcgStateLayout {
   int32_t n_frows, n_irows;
   int32_t ring_control; /* first fp64 row of the control ring: delay_control slots x 2 rows */
@@ -211,7 +234,7 @@ int bcg_abi_version(void);
 /* copies the calling thread's last error message (NUL terminated) and returns its length */
 size_t bcg_last_error(char* buf, size_t cap);
 /* sizeof() of the ABI structs, in declaration order: 0 BcgParams, 1 BcgMapDesc, 2 BcgPathDesc,
- * 3 BcgFootprintLut, 4 BcgBatch, 5 BcgStateLayout, 6 BcgStepOut; -1 for anything else.  Lets a
+ * 3 BcgFootprintLut, 4 BcgBatch, 5 BcgStateLayout, 6 BcgStepOut, 7 BcgTurnParams, 8 BcgAisleSlots; -1 for anything else.  Lets a
  * binding (ctypes, cffi, ...) verify its struct mirrors before the first call. */
 int64_t bcg_sizeof(int32_t which);
 /* number of CUDA devices visible, <0 on error; makes a missing GPU a loud failure for callers */
@@ -236,6 +259,16 @@ int bcg_encode_map_tensor_maps(const BcgMapDesc* maps_host, int32_t n_maps, cons
 int bcg_init_state(const BcgParams* p, const BcgBatch* b, void* stream);
 /* PlanEnv.reset (env.py:293-303) for envs with mask[e] != 0 (mask NULL = all) */
 int bcg_reset_where(const BcgBatch* b, const uint8_t* mask, void* stream);
+
+/* RandomAisleTurnEnv.reset with draw_new_turn_on_reset (envs/synth_turn_env.py:278-291) on the device, for
+ * envs with mask[e] != 0 (mask NULL = all): draw a turn (:317-332; Philox keyed (p->seed; env id, draw_index)
+ * unless `turn_params`, device [n_envs], supplies them), build its walls like cv2.line and its way points
+ * (path_and_costmap_from_config :110-192), refine the path (utilities/path_tools.py:178-240, spacing
+ * `path_delta`), derive both tile planes, and make the initial state (env.py:179-214, reward.py:261-288).
+ * The previous walls of the slot are erased pixel by pixel, so a reset costs O(wall pixels), not O(map).
+ * Not available together with TMA tensor maps (map_tmaps), which cannot be re-encoded on the device. */
+int bcg_generate_aisles(const BcgParams* p, const BcgBatch* b, const BcgAisleSlots* slots, const uint8_t* mask,
+                        const BcgTurnParams* turn_params, uint64_t draw_index, double path_delta, void* stream);
 
 /* -- the hot path -------------------------------------------------------------------------------- */
 /* PlanEnv.step (env.py:334-361) for all envs.  actions: device [n][2] (wheel_v, wheel_angle) or

@@ -16,6 +16,6 @@ for staging, variant in (("tiles", 1), ("tma", 0)):
                               "--ego-staging", staging], env=env, capture_output=True, text=True)
         try:
             d = json.loads(out.stdout.strip().splitlines()[-1])
-            print(staging, variant, "dbg", dbg, "ego_ms %.4f commit_ms %.4f step_ms %.4f" % (d["kernels_ms"]["ego_kernel"], d["kernels_ms"]["commit_kernel"], d["ms_per_step"]), flush=True)
+            print(staging, variant, "dbg", dbg, "ego_ms %.4f commit_ms %.4f step_ms %.4f" % (d["kernels_ms"].get("ego_tiles_kernel", d["kernels_ms"].get("ego_kernel")), d["kernels_ms"]["commit_kernel"], d["ms_per_step"]), flush=True)
         except Exception:
             print(staging, variant, "dbg", dbg, "failed", out.stderr[-800:], flush=True)
