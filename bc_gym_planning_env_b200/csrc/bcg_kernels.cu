@@ -1404,6 +1404,7 @@ int bcg_generate_aisles(const BcgParams* p, const BcgBatch* b, const BcgAisleSlo
                   slots->chunk_pitch * 32 >= slots->path_pitch,
               "bad slot sizes");
   BCG_REQUIRE(path_delta > 0, "path_delta must be positive");
+  BCG_REQUIRE((int)(0.05 / p->resolution) <= 1, "walls are drawn one pixel thick: resolution must be above 0.025 m");
   generate_aisles_kernel<<<b->n_envs, 256, 0, (cudaStream_t)stream>>>(*p, *b, make_layout(*p), *slots, mask, turn_params,
                                                                      draw_index, path_delta);
   BCG_CHECK_CUDA(cudaGetLastError());

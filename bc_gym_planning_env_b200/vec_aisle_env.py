@@ -1,0 +1,182 @@
+"""VecRandomAisleTurnEnv: N `RandomAisleTurnEnv`s whose worlds are drawn and rasterised on the GPU.
+
+The reference rebuilds a random aisle turn on the host at every `reset` (envs/synth_turn_env.py:278-291:
+draw TurnParams :317-332, path_and_costmap_from_config :110-192, cv2.line walls, refine_path, initial reward
+state) at about 1 k worlds/s per core.  Here `bcg_generate_aisles` does the same for any subset of the batch
+in one launch: every env owns a fixed-size slot of the map / tile / path arenas and its world is rewritten in
+place, so a 65 536-env reset storm is a single kernel instead of a minute of host work.
+Draws come from Philox4x32-10 keyed (seed; env id, draw index) instead of the reference's MT19937; explicit
+TurnParams can be supplied instead (that is how the parity tests replay the reference's own worlds).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from bc_gym_planning_env_b200 import _native as nat
+from bc_gym_planning_env_b200.envs.synth_turn_env import TurnParams
+from bc_gym_planning_env_b200.utilities.costmap_2d import CostMap2D
+from bc_gym_planning_env_b200.vec_env import DEFAULT_NOISE, VecPlanEnv, _round_up, footprint_lut_for
+
+TURN_DTYPE = np.dtype([("main_corridor_length", "<f8"), ("turn_corridor_length", "<f8"), ("turn_corridor_angle", "<f8"),
+                       ("main_corridor_width", "<f8"), ("turn_corridor_width", "<f8"), ("margin", "<f8"),
+                       ("rot_theta", "<f8"), ("flip_arnd_oy", "<i4"), ("flip_arnd_ox", "<i4")])
+assert TURN_DTYPE.itemsize == C.sizeof(nat.BcgTurnParams)
+
+
+def turn_params_array(turns):
+    """list of TurnParams (or dicts with its fields) -> structured array in the layout of BcgTurnParams"""
+    out = np.zeros(len(turns), dtype=TURN_DTYPE)
+    for k, t in enumerate(turns):
+        get = (lambda f: t[f]) if isinstance(t, dict) else (lambda f: getattr(t, f))
+        for f in TURN_DTYPE.names:
+            out[f][k] = get(f)
+    return out
+
+
+def worst_case_world(resolution, path_delta):
+    """Upper bounds (map cells incl. row padding, refined path points) over the RandomAisleTurnEnv distribution
+    (envs/synth_turn_env.py:317-332).  The extents grow with every length and width, so only the two angles are
+    searched (dense grid); 6 % head-room covers the grid spacing and the 32-cell row padding."""
+    al, rt = np.meshgrid(np.linspace(-3. / 8. * np.pi, 3. / 8. * np.pi, 201), np.linspace(0, 2 * np.pi, 721))
+    h, far, d, z = 8.0, 6.0, 1.5, 1.5
+    ta, ca = np.tan(al), np.cos(al)
+    lower, upper = -z / ca, z / ca
+    o = np.ones_like(al)
+    cx = np.stack([-d * o, 0 * o, d * o, d * o, far * o, far * o, d * o, far * o, -d * o, d * o])
+    cy = np.stack([-h * o, -h * o, -h * o, d * ta + lower, far * ta + lower, far * ta, d * ta + upper, far * ta + upper,
+                   h * o, h * o])
+    c, s = np.cos(rt), np.sin(rt)
+    X, Y = c * cx - s * cy, s * cx + c * cy
+    w = (X.max(0) - X.min(0) + 2.0) / resolution + 33
+    hh = (Y.max(0) - Y.min(0) + 2.0) / resolution + 9
+    cells = int(np.ceil((w * hh).max() * 1.06))
+    ca_min = np.cos(3. / 8. * np.pi)
+    length = (h + d * np.tan(3. / 8. * np.pi) + z / ca_min) + np.hypot(d, z / ca_min) + (far + d / ca_min)
+    return cells, int(np.ceil(length / path_delta)) + 8
+
+
+class VecRandomAisleTurnEnv(VecPlanEnv):
+    def __init__(self, n_envs, params=None, draw_new_turn_on_reset=True, seed=0, turn_params=None,
+                 noise_parameters=DEFAULT_NOISE, auto_reset=False, device=None, env_id_base=0, with_ego=False,
+                 footprint_scale=1.0, footprint=None, resolution=0.03, max_map_cells=None, max_path_points=None):
+        """
+        :param n_envs: batch size; env e draws from the Philox stream (seed; env_id_base + e, draw index)
+        :param draw_new_turn_on_reset: `reset` draws a new turn for the envs it resets (reference default)
+        :param turn_params: optional list of n_envs TurnParams for the first worlds (default: drawn on device)
+        :param max_map_cells, max_path_points: slot capacities per env (default: worst case of the distribution)
+        """
+        self._configure(params, n_envs, resolution, noise_parameters, seed, auto_reset, device, env_id_base, with_ego,
+                        'tiles')
+        if not self.params.refine_path:
+            raise ValueError("device-side generation always refines the path (EnvParams.refine_path)")
+        if max(1, int(0.05 / self.resolution)) != 1:
+            raise ValueError("device-side walls are one pixel thick: resolution must be above 0.025 m")
+        self._draw_new_turn_on_reset = bool(draw_new_turn_on_reset)
+        cells, points = worst_case_world(self.resolution, self.params.path_delta)
+        self._slot_bytes = _round_up(int(max_map_cells if max_map_cells is not None else cells), 128)
+        self._path_pitch = _round_up(int(max_path_points if max_path_points is not None else points), 4)
+        self._chunk_pitch = _round_up((self._path_pitch + 31) // 32, 4)
+        self._tile_slot_words = _round_up(self._slot_bytes // 32 + 16 * 64, 16)   # 1 bit per cell + partial-tile slack
+        self._draw_index = 0
+        self._alloc_slots()
+        self._upload_lut(footprint_lut_for(self.params.robot_name, self.resolution, footprint_scale, footprint))
+        self._alloc_state()
+        self._make_batch()
+        self.generate(turn_params=turn_params)
+        self.check_status()
+
+    # ---- slots ---------------------------------------------------------------------------------
+    def _alloc_slots(self):
+        n, dev = self.n_envs, self.device
+        descs = (nat.BcgMapDesc * n)()
+        pdescs = (nat.BcgPathDesc * n)()
+        path_slot = 5 * self._path_pitch + 3 * self._chunk_pitch
+        for e in range(n):
+            descs[e].data_off = e * self._slot_bytes
+            descs[e].cell_tile_off = e * self._slot_bytes
+            descs[e].tile_off = e * self._tile_slot_words
+            pdescs[e].off = e * path_slot
+            pdescs[e].chunk_off = e * path_slot + 5 * self._path_pitch
+            pdescs[e].pitch, pdescs[e].chunk_pitch = self._path_pitch, self._chunk_pitch
+        self.map_arena = torch.zeros(n * self._slot_bytes, dtype=torch.uint8, device=dev)
+        self.cell_tile_arena = torch.zeros(n * self._slot_bytes, dtype=torch.uint8, device=dev)
+        self.tile_arena = torch.zeros(n * self._tile_slot_words, dtype=torch.int32, device=dev)
+        self.path_arena = torch.zeros(n * path_slot, dtype=torch.float64, device=dev)
+        self.map_descs = self._to_device(np.frombuffer(bytes(descs), dtype=np.uint8).copy())
+        self.path_descs = self._to_device(np.frombuffer(bytes(pdescs), dtype=np.uint8).copy())
+        self.map_id = torch.arange(n, dtype=torch.int32, device=dev)
+        self.path_id = torch.arange(n, dtype=torch.int32, device=dev)
+        self.map_tmaps = None
+        self._n_maps = self._n_paths = n
+        self._gen_state = torch.zeros((n, 128), dtype=torch.uint8, device=dev)
+        self._turns = torch.zeros((n, TURN_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+        slots = nat.BcgAisleSlots()
+        slots.map_slot_bytes, slots.tile_slot_words = self._slot_bytes, self._tile_slot_words
+        slots.path_pitch, slots.chunk_pitch = self._path_pitch, self._chunk_pitch
+        slots.gen_state, slots.params_out = self._gen_state.data_ptr(), self._turns.data_ptr()
+        self._slots = slots
+
+    # ---- generation ------------------------------------------------------------------------------
+    def generate(self, mask=None, turn_params=None):
+        """Give the envs with mask[e] true (None: all) a new world and its initial state.
+        turn_params: list of n_envs TurnParams / structured array (TURN_DTYPE) to use instead of drawing;
+        entries of unmasked envs are ignored."""
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+            if tuple(m.shape) != (self.n_envs,):
+                raise ValueError("mask must have shape (%d,)" % self.n_envs)
+        tp = None
+        if turn_params is not None:
+            arr = turn_params if isinstance(turn_params, np.ndarray) else turn_params_array(turn_params)
+            if arr.dtype != TURN_DTYPE or arr.shape != (self.n_envs,):
+                raise ValueError("turn_params must hold one TurnParams per env")
+            tp = self._to_device(arr.view(np.uint8).reshape(self.n_envs, TURN_DTYPE.itemsize))
+        nat.check(nat.lib().bcg_generate_aisles(C.byref(self._c_params), C.byref(self._batch), C.byref(self._slots),
+                                                nat.ptr(m), nat.ptr(tp), self._draw_index, float(self.params.path_delta),
+                                                self._stream()))
+        self._draw_index += 1
+        if tp is not None:
+            torch.cuda.current_stream(self.device).synchronize()     # tp is released when this returns
+
+    def reset(self, mask=None):
+        """RandomAisleTurnEnv.reset (envs/synth_turn_env.py:278-291) for all envs (mask None) or those with
+        mask[e] true: a new turn when draw_new_turn_on_reset, the initial state either way."""
+        if not self._draw_new_turn_on_reset:
+            return super(VecRandomAisleTurnEnv, self).reset(mask)
+        self.generate(mask)
+        if self.with_ego:
+            self.observe_ego()
+        return self.observation()
+
+    # ---- accessors: the worlds live on the device ----------------------------------------------------
+    def turn_params(self, e=None):
+        """TurnParams of env e, or the structured array (TURN_DTYPE) of the whole batch."""
+        arr = self._turns.cpu().numpy().reshape(-1).view(TURN_DTYPE)
+        if e is None:
+            return arr
+        r = arr[int(e)]
+        kw = {f: float(r[f]) for f in TURN_DTYPE.names}
+        kw["flip_arnd_oy"], kw["flip_arnd_ox"] = bool(r["flip_arnd_oy"]), bool(r["flip_arnd_ox"])
+        return TurnParams(**kw)
+
+    def _map_desc(self, e):
+        sz = C.sizeof(nat.BcgMapDesc)
+        raw = self.map_descs[int(e) * sz:(int(e) + 1) * sz].cpu().numpy().tobytes()
+        return nat.BcgMapDesc.from_buffer_copy(raw)
+
+    def _path_desc(self, e):
+        sz = C.sizeof(nat.BcgPathDesc)
+        raw = self.path_descs[int(e) * sz:(int(e) + 1) * sz].cpu().numpy().tobytes()
+        return nat.BcgPathDesc.from_buffer_copy(raw)
+
+    def costmap(self, e):
+        d = self._map_desc(e)
+        rows = self.map_arena[d.data_off:d.data_off + d.height * d.pitch].view(d.height, d.pitch)[:, :d.width]
+        return CostMap2D(rows.cpu().numpy().copy(), self.resolution, np.array([d.origin_x, d.origin_y], dtype=np.float64))
+
+    def full_path(self, e):
+        d = self._path_desc(e)
+        rows = self.path_arena[d.off:d.off + 3 * d.pitch].view(3, d.pitch)[:, :d.n]
+        return np.ascontiguousarray(rows.t().cpu().numpy())

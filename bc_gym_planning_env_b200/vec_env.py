@@ -99,36 +99,17 @@ class VecPlanEnv(object):
             copy of every costmap in 128-byte cell tiles, only the tiles the rotated window touches are read),
             'tma' (box loads of the window's bounding box from the uint8 rows) or 'spans' (plain loads)
         """
-        nat.require_cuda()
-        self.params = params if params is not None else EnvParams()
-        self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
-        if self.device.type != 'cuda':
-            raise nat.BcgError("VecPlanEnv runs on a CUDA device only (no CPU path)")
         costmaps = list(costmaps)
         paths = list(paths)
         if not costmaps or not paths:
             raise ValueError("need at least one costmap and one path")
-        self.n_envs = int(n_envs if n_envs is not None else max(len(costmaps), len(paths)))
-        n = self.n_envs
+        n = int(n_envs if n_envs is not None else max(len(costmaps), len(paths)))
+        self._configure(params, n, float(costmaps[0].get_resolution()), noise_parameters, seed, auto_reset, device,
+                        env_id_base, with_ego, ego_staging if use_tma else 'spans')   # use_tma=False: older spelling
         self._map_pool = costmaps
         self._map_ids_host = (np.arange(n) % len(costmaps)) if map_ids is None else np.asarray(map_ids, dtype=np.int64)
         self._path_ids_host = (np.arange(n) % len(paths)) if path_ids is None else np.asarray(path_ids, dtype=np.int64)
         assert self._map_ids_host.shape == (n,) and self._path_ids_host.shape == (n,)
-        self.resolution = float(costmaps[0].get_resolution())
-        self.dims = get_dimensions_example(self.params.robot_name)
-        self.robot_kind = nat.ROBOT_TRICYCLE if self.dims.drive_type == TRICYCLE else nat.ROBOT_DIFFDRIVE
-        self.auto_reset = bool(auto_reset)
-        self.with_ego = bool(with_ego)
-        if ego_staging not in ('tiles', 'tma', 'spans'):
-            raise ValueError("ego_staging must be 'tiles', 'tma' or 'spans'")
-        if not use_tma:                      # older spelling: plain loads, no derived planes for the ego kernel
-            ego_staging = 'spans'
-        self.ego_staging = ego_staging
-        self.use_tma = ego_staging == 'tma'
-        self._step_index = 0
-
-        self._c_params = self._make_params(noise_parameters, seed, env_id_base)
-        self.layout = nat.state_layout(self._c_params)
         self._upload_maps(costmaps, private_map_copies)
         self._upload_paths(paths)
         self._upload_lut(footprint_lut_for(self.params.robot_name, self.resolution, footprint_scale, footprint))
@@ -140,6 +121,28 @@ class VecPlanEnv(object):
             nat.check(nat.lib().bcg_build_cell_tiles(C.byref(self._batch), 0, self._batch.n_maps, s))
         nat.check(nat.lib().bcg_init_state(C.byref(self._c_params), C.byref(self._batch), s))
         self.check_status()
+
+    def _configure(self, params, n_envs, resolution, noise_parameters, seed, auto_reset, device, env_id_base, with_ego,
+                   ego_staging):
+        """Everything that does not depend on where the maps and paths come from."""
+        nat.require_cuda()
+        self.params = params if params is not None else EnvParams()
+        self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+        if self.device.type != 'cuda':
+            raise nat.BcgError("VecPlanEnv runs on a CUDA device only (no CPU path)")
+        self.n_envs = int(n_envs)
+        self.resolution = float(resolution)
+        self.dims = get_dimensions_example(self.params.robot_name)
+        self.robot_kind = nat.ROBOT_TRICYCLE if self.dims.drive_type == TRICYCLE else nat.ROBOT_DIFFDRIVE
+        self.auto_reset = bool(auto_reset)
+        self.with_ego = bool(with_ego)
+        if ego_staging not in ('tiles', 'tma', 'spans'):
+            raise ValueError("ego_staging must be 'tiles', 'tma' or 'spans'")
+        self.ego_staging = ego_staging
+        self.use_tma = ego_staging == 'tma'
+        self._step_index = 0
+        self._c_params = self._make_params(noise_parameters, seed, env_id_base)
+        self.layout = nat.state_layout(self._c_params)
 
     # ---- setup -------------------------------------------------------------------------------
     def _make_params(self, noise, seed, env_id_base):
@@ -276,6 +279,7 @@ class VecPlanEnv(object):
                 rad = np.hypot(pts[:, 0] - ctr[0], pts[:, 1] - ctr[1]).max()
                 ch[0, c], ch[1, c], ch[2, c] = ctr[0], ctr[1], rad * (1 + 1e-12) + 1e-9   # conservative bound
         self._paths_host = refined
+        self._n_paths = len(refined)
         self._path_descs_host = descs
         self.path_arena = self._to_device(arena)
         self.path_descs = self._to_device(np.frombuffer(bytes(descs), dtype=np.uint8).copy())
@@ -313,7 +317,7 @@ class VecPlanEnv(object):
     def _make_batch(self):
         b = nat.BcgBatch()
         b.n_envs, b.n_frows, b.n_irows = self.n_envs, self.layout.n_frows, self.layout.n_irows
-        b.n_maps, b.n_paths = self._n_maps, len(self._paths_host)
+        b.n_maps, b.n_paths = self._n_maps, self._n_paths
         b.state_f, b.state_i = self.state_f.data_ptr(), self.state_i.data_ptr()
         b.init_f, b.init_i = self.init_f.data_ptr(), self.init_i.data_ptr()
         b.cand, b.cand_i, b.work = self._cand.data_ptr(), self._cand_i.data_ptr(), self._work.data_ptr()
@@ -493,6 +497,10 @@ class VecPlanEnv(object):
             raise ValueError("Goal pose too close to initial pose")   # reference envs/base/reward.py:275-277
         if st[nat.STATUS_LUT_MISS]:
             raise nat.BcgError("%d footprint lookups fell outside the angle-bin table" % st[nat.STATUS_LUT_MISS])
+        if st[nat.STATUS_SLOT_OVERFLOW]:
+            self._status.zero_()
+            raise nat.BcgError("%d generated worlds did not fit their map / path slots (envs left unchanged)"
+                               % st[nat.STATUS_SLOT_OVERFLOW])
 
     def episode_stats(self, reset=False):
         """Device-accumulated episode statistics as a fp64 tensor [STATS_WORDS] (see STAT_NAMES)."""

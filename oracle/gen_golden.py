@@ -278,6 +278,36 @@ def gen_diffdrive(name, n_envs, n_steps):
     print(name, out["ref_robot_state"].shape, "hits", int(out["ref_hit"].sum()))
 
 
+def gen_aisle_worlds(name, n_envs):
+    """Worlds the reference builds when RandomAisleTurnEnv draws a turn (synth_turn_env.py:110-192, :317-332):
+    turn params, costmap, origin, coarse way points, refined path and the initial reward state.  The last four
+    envs are reset twice so that fixtures also hold consecutive draws of one RandomState."""
+    from bc_gym_planning_env.envs.synth_turn_env import RandomAisleTurnEnv, path_and_costmap_from_config
+    from oracle.aisle_oracle import TURN_FIELDS
+    out = {"n_envs": np.int64(n_envs)}
+    turns = []
+    for s in range(n_envs):
+        env = RandomAisleTurnEnv(seed=300 + s)
+        if s >= n_envs - 4:
+            env.reset()
+            env.reset()
+        cfg = env._env._config                 # reset() rebuilds _env from a local config; env.config goes stale
+        tp = cfg.turn_params
+        turns.append([float(getattr(tp, f)) for f in TURN_FIELDS])
+        st = env._env._state
+        out["costmap_%d" % s] = st.costmap.get_data().copy()
+        out["origin_%d" % s] = np.array(st.costmap.get_origin())
+        out["coarse_%d" % s] = np.array(path_and_costmap_from_config(cfg)[0])
+        out["path_%d" % s] = np.array(st.original_path)
+        rp = st.reward_provider_state
+        out["target_idx_%d" % s] = np.int64(rp.target_idx)
+        out["min_dist_%d" % s] = np.float64(rp.min_spat_dist_so_far)
+    out["turn_params"] = np.array(turns)
+    out["resolution"] = np.float64(env._env._state.costmap.get_resolution())
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, out["turn_params"].shape, [out["costmap_%d" % s].shape for s in range(n_envs)])
+
+
 def main():
     _ref()
     os.makedirs(OUT, exist_ok=True)
@@ -299,6 +329,7 @@ def main():
     gen_collision("aisle_collision", 8, 250)
     gen_kat_collision("kat_is_robot_colliding")
     gen_diffdrive("diffdrive_steps", 6, 250)
+    gen_aisle_worlds("aisle_worlds", 16)
 
 
 if __name__ == "__main__":
