@@ -33,7 +33,7 @@ class BcgMapDesc(C.Structure):
     _fields_ = [
         ("data_off", C.c_int64), ("tile_off", C.c_int64), ("origin_x", C.c_double), ("origin_y", C.c_double),
         ("height", C.c_int32), ("width", C.c_int32), ("pitch", C.c_int32),
-        ("tiles_x", C.c_int32), ("tiles_y", C.c_int32), ("reserved", C.c_int32),
+        ("tiles_x", C.c_int32), ("tiles_y", C.c_int32), ("flags", C.c_int32),
         ("cell_tile_off", C.c_int64), ("ctiles_x", C.c_int32), ("ctiles_y", C.c_int32),
     ]
 
@@ -65,7 +65,7 @@ class BcgBatch(C.Structure):
         ("lut", BcgFootprintLut),
         ("map_tmaps", C.c_void_p), ("tmap_n_widths", C.c_int32), ("tmap_box_h", C.c_int32),
         ("tmap_box_w", C.c_int32 * 4),
-        ("cell_tile_arena", C.c_void_p),
+        ("cell_tile_arena", C.c_void_p), ("occ_tile_arena", C.c_void_p), ("ego_list", C.c_void_p),
         ("status", C.c_void_p), ("stats", C.c_void_p),
     ]
 
@@ -110,6 +110,7 @@ STATUS_LUT_MISS, STATUS_PATH_EXHAUSTED, STATUS_SLOT_OVERFLOW, STATUS_WORDS = 0, 
 STAT_NAMES = ("episodes", "return", "length", "collided", "goal", "timeout")
 STATS_WORDS = 8
 ROBOT_TRICYCLE, ROBOT_DIFFDRIVE = 0, 1
+MAP_ONLY_LETHAL = 1
 REWARD_CONTINUOUS, REWARD_PURE_PURSUIT = 0, 1
 
 # every symbol include/bcg_b200.h declares: name -> (restype, argtypes)

@@ -94,6 +94,7 @@ __device__ __forceinline__ AisleGeometry aisle_geometry(const BcgTurnParams& tp,
 struct MapLayout {
   uint8_t* data;       // uint8 rows
   uint32_t* tiles;     // lethal tile plane
+  uint32_t* occ;       // occupancy plane (same layout; may be null)
   uint8_t* ctiles;     // cell tiles
   int pitch, rows, tiles_x, ctiles_x;
 };
@@ -102,7 +103,7 @@ struct MapLayout {
 // minor axis after step j has moved ceil((2 d j - D) / (2 D)) times (clamped at 0), D/d = major/minor extent --
 // Bresenham with the initial error D - 2 d in closed form, pixel for pixel equal to cv2.line
 // (tests/test_host_logic.py::test_line_pixels_match_cv2).  Threads take pixels j = first, first + stride, ...;
-// `value` 254 draws, 0 erases; the lethal tile plane and the cell tiles are kept in step.
+// `value` 254 draws, 0 erases; the lethal and occupancy tile planes and the cell tiles are kept in step.
 __device__ __forceinline__ void draw_wall(const MapLayout& m, int x0, int y0, int x1, int y1, uint8_t value, int first,
                                           int stride) {
   if (x1 < x0) {
@@ -122,9 +123,14 @@ __device__ __forceinline__ void draw_wall(const MapLayout& m, int x0, int y0, in
     if (x < 0 || y < 0 || x >= m.pitch || y >= m.rows) continue;      // never for aisle walls (1 m margin); be safe
     m.data[(int64_t)y * m.pitch + x] = value;
     m.ctiles[(((int64_t)(y >> 3) * m.ctiles_x + (x >> 4)) << 7) + ((y & 7) << 4) + (x & 15)] = value;
-    uint32_t* word = m.tiles + (((int64_t)(y >> 4) * m.tiles_x + (x >> 5)) << 4) + (y & 15);
-    if (value == 254) atomicOr(word, 1u << (x & 31));
-    else atomicAnd(word, ~(1u << (x & 31)));
+    const int64_t widx = (((int64_t)(y >> 4) * m.tiles_x + (x >> 5)) << 4) + (y & 15);
+    if (value == 254) {
+      atomicOr(m.tiles + widx, 1u << (x & 31));
+      if (m.occ) atomicOr(m.occ + widx, 1u << (x & 31));
+    } else {
+      atomicAnd(m.tiles + widx, ~(1u << (x & 31)));
+      if (m.occ) atomicAnd(m.occ + widx, ~(1u << (x & 31)));
+    }
   }
 }
 

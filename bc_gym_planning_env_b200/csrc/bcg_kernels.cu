@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -239,7 +240,7 @@ struct EgoAffine {
 
 // costmap_utils.py:42-65 + the fp64 inversion cv::warpAffine applies to the float32 forward matrix
 __device__ __forceinline__ EgoAffine ego_affine(const BcgParams& p, const BcgMapDesc& m, double px, double py,
-                                                double pth) {
+                                                double pth, float* fwd = nullptr) {
   const double cx = (double)world_to_pixel_1d(px, m.origin_x, p.inv_resolution);
   const double cy = (double)world_to_pixel_1d(py, m.origin_y, p.inv_resolution);
   const double deg = 180 * pth / BCG_PI;
@@ -252,6 +253,10 @@ __device__ __forceinline__ EgoAffine ego_affine(const BcgParams& p, const BcgMap
   const double dsy = rint((p.ego_y0 - (m.origin_y - py)) * p.inv_resolution);
   const double M0 = (double)r00, M1 = (double)r01, M2 = (double)(r02 - (float)dsx);
   const double M3 = (double)r10, M4 = (double)r11, M5 = (double)(r12 - (float)dsy);
+  if (fwd) {                           // the float32 forward matrix itself (source pixel -> crop pixel)
+    fwd[0] = (float)M0; fwd[1] = (float)M1; fwd[2] = (float)M2;
+    fwd[3] = (float)M3; fwd[4] = (float)M4; fwd[5] = (float)M5;
+  }
   double D = M0 * M4 - M1 * M3;
   D = (D != 0.0) ? 1. / D : 0.0;
   EgoAffine a;
@@ -437,7 +442,8 @@ struct __align__(16) EgoTileWork {   // 256 bytes
   int32_t mode, map_id;              // BCG_EGO_MODE_TILES or BCG_EGO_MODE_DIRECT
   int32_t ctiles_x, ctiles_y;        // cell-tile grid of the env's map
   int64_t ctile_off;                 // byte offset of the map's cell tiles in the cell-tile arena
-  int32_t pad[10];
+  float fwd[6];                      // cv::warpAffine's forward matrix (source -> crop), for the sparse kernel
+  int32_t pad[4];
   uint8_t span[BCG_EGT_MAX_TILE_ROWS][2];   // first and last window tile column touched in tile row t (first > last: none)
 };
 static_assert(sizeof(EgoTileWork) == BCG_EGO_WORK_BYTES, "EgoTileWork records are 256 bytes");
@@ -456,10 +462,12 @@ __device__ __forceinline__ void write_ego_tile_record(const BcgParams& p, const 
   const BcgMapDesc m = b.maps[map_id];
   EgoTileWork* rec = reinterpret_cast<EgoTileWork*>(reinterpret_cast<uint8_t*>(b.ego_work) + (int64_t)e * BCG_EGO_WORK_BYTES);
   EgoTileWork w;
-  w.aff = ego_affine(p, m, px, py, pth);
+  w.aff = ego_affine(p, m, px, py, pth, w.fwd);
   w.X0 = w.Y0 = w.ntx = w.nty = 0;
   w.mode = BCG_EGO_MODE_DIRECT;
   w.map_id = map_id;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) w.pad[k] = 0;
   w.ctiles_x = m.ctiles_x;
   w.ctiles_y = m.ctiles_y;
   w.ctile_off = m.cell_tile_off;
@@ -737,6 +745,7 @@ __global__ void __launch_bounds__(256) generate_aisles_kernel(const BcgParams p,
   MapLayout m;
   m.data = const_cast<uint8_t*>(b.map_arena) + md->data_off;
   m.tiles = const_cast<uint32_t*>(b.tile_arena) + md->tile_off;
+  m.occ = b.occ_tile_arena ? const_cast<uint32_t*>(b.occ_tile_arena) + md->tile_off : nullptr;
   m.ctiles = const_cast<uint8_t*>(b.cell_tile_arena) + md->cell_tile_off;
   // ---- erase what the slot holds (with the layout it was drawn in) -------------------------------------------
   if (gs->valid) {
@@ -767,6 +776,7 @@ __global__ void __launch_bounds__(256) generate_aisles_kernel(const BcgParams p,
     md->origin_x = g.origin_x; md->origin_y = g.origin_y;
     md->height = g.height; md->width = g.width; md->pitch = pitch;
     md->tiles_x = tiles_x; md->tiles_y = tiles_y; md->ctiles_x = ctiles_x; md->ctiles_y = ctiles_y;
+    md->flags = BCG_MAP_ONLY_LETHAL;           // walls are the only occupied cells
     pdsc->n = shape.n;
     pdsc->pitch = slots.path_pitch;
     pdsc->n_chunks = (shape.n + 31) / 32;
@@ -827,12 +837,14 @@ __global__ void __launch_bounds__(256) tiles_kernel(const BcgBatch b, const int 
   const BcgMapDesc m = b.maps[first + blockIdx.y];
   const int words = m.tiles_x * m.tiles_y * 16;
   uint32_t* dst = const_cast<uint32_t*>(b.tile_arena) + m.tile_off;
+  uint32_t* occ = b.occ_tile_arena ? const_cast<uint32_t*>(b.occ_tile_arena) + m.tile_off : nullptr;
   const uint8_t* src = b.map_arena + m.data_off;
+  bool other = false;                      // a cell that is neither free (0) nor lethal (254)
   for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < words; w += gridDim.x * blockDim.x) {
     const int tile = w >> 4, r = w & 15;
     const int ty = tile / m.tiles_x, tx = tile - ty * m.tiles_x;
     const int y = (ty << 4) + r;
-    uint32_t bits = 0;
+    uint32_t bits = 0, obits = 0;
     if (y < m.height) {
       const uint4* row = reinterpret_cast<const uint4*>(src + (int64_t)y * m.pitch + (tx << 5));
 #pragma unroll
@@ -842,19 +854,28 @@ __global__ void __launch_bounds__(256) tiles_kernel(const BcgBatch b, const int 
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint32_t eq = __vcmpeq4(ws[k], 0xFEFEFEFEu) & 0x01010101u;  // bit 0 of each byte
+          const uint32_t nz = __vcmpne4(ws[k], 0u) & 0x01010101u;
           const uint32_t nib = (eq * 0x10204080u) >> 28;                    // gather to 4 bits
+          const uint32_t onib = (nz * 0x10204080u) >> 28;
           bits |= nib << (h * 16 + k * 4);
+          obits |= onib << (h * 16 + k * 4);
         }
       }
       const int over = (tx << 5) + 32 - m.width;
-      if (over > 0) bits &= (over >= 32) ? 0u : (0xffffffffu >> over);
+      if (over > 0) {
+        const uint32_t keep = (over >= 32) ? 0u : (0xffffffffu >> over);
+        bits &= keep;
+        obits &= keep;
+      }
+      other |= (obits != bits);
     }
     dst[w] = bits;
+    if (occ) occ[w] = obits;
   }
+  if (__any_sync(BCG_FULL, other) && (threadIdx.x & 31) == 0)
+    atomicAnd(&const_cast<BcgMapDesc*>(b.maps)[first + blockIdx.y].flags, ~BCG_MAP_ONLY_LETHAL);
 }
 
-// cell tiles: the uint8 cells of a map as 128-byte tiles of 16 px x 8 rows (see BcgMapDesc); one thread per
-// 16-byte tile row, zero beyond the map
 __global__ void __launch_bounds__(256) cell_tiles_kernel(const BcgBatch b, const int first) {
   const BcgMapDesc m = b.maps[first + blockIdx.y];
   const int pieces = m.ctiles_x * m.ctiles_y * 8;
@@ -1103,7 +1124,8 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, const uint4& v) {
 template <int NG>
 __global__ void __launch_bounds__(BCG_EGT_THREADS, BCG_EGT_CTAS) ego_tiles_kernel(const BcgParams p, const BcgBatch b,
                                                                                   uint8_t* __restrict__ image,
-                                                                                  const int win_bytes) {
+                                                                                  const int win_bytes,
+                                                                                  const int* __restrict__ env_list) {
   extern __shared__ __align__(128) uint8_t egt_smem[];
   constexpr int NT = BCG_EGT_THREADS, NW = NT / 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1111,15 +1133,17 @@ __global__ void __launch_bounds__(BCG_EGT_THREADS, BCG_EGT_CTAS) ego_tiles_kerne
   uint8_t* const rec_s = egt_smem + win_bytes + sizeof(EgoTab);
   const uint32_t win_u32 = smem_u32(egt_smem), rec_u32 = smem_u32(rec_s);
   const uint8_t* const recs = reinterpret_cast<const uint8_t*>(b.ego_work);
-  const int n = b.n_envs, G = gridDim.x;
+  // env_list (optional): render only the envs env_list[0 .. env_list[n_envs] - 1] (what the sparse kernel left over)
+  const int n = env_list ? env_list[b.n_envs] : b.n_envs, G = gridDim.x;
   const int ego_w = p.ego_w, ego_h = p.ego_h, npx = ego_w * ego_h;
   const int e0 = blockIdx.x;
   if (e0 >= n) return;
+  auto env_of = [&](int i) { return env_list ? env_list[i] : i; };
 
   // record of env `en` -> ring slot `slot` (the first 16 threads move 16 bytes each)
   auto fetch_record = [&](int en, int slot) {
     if (en < n && tid < 16)
-      cp_async_16(rec_u32 + slot * BCG_EGO_WORK_BYTES + tid * 16, recs + (int64_t)en * BCG_EGO_WORK_BYTES + tid * 16, 16u);
+      cp_async_16(rec_u32 + slot * BCG_EGO_WORK_BYTES + tid * 16, recs + (int64_t)env_of(en) * BCG_EGO_WORK_BYTES + tid * 16, 16u);
   };
 
   // The newest record fetch may still be in flight after a wait, so records are fetched RD envs ahead.
@@ -1183,7 +1207,7 @@ __global__ void __launch_bounds__(BCG_EGT_THREADS, BCG_EGT_CTAS) ego_tiles_kerne
     const int map_id = r->map_id;
     cp_async_wait_group_1();                  // the record needed next iteration has landed (the newest may not have)
     __syncthreads();                          // window, tables and that record are visible to every warp
-    uint8_t* const dst = image + (int64_t)e * npx;
+    uint8_t* const dst = image + (int64_t)env_of(e) * npx;
     if (mode == BCG_EGO_MODE_TILES) {
       // ---- gather: warp w takes crop rows w, w + 8, ...; lane l takes columns l, l + 32, ...  (NG = ceil(ego_w / 32):
       // only the last column group can be partial) -----------------------------------------------------------------
@@ -1222,6 +1246,204 @@ __global__ void __launch_bounds__(BCG_EGT_THREADS, BCG_EGT_CTAS) ego_tiles_kerne
     }
     __syncthreads();                          // every warp is done with the window, the tables and record `it`
   }
+}
+
+// ---- ego_sparse_kernel: scatter instead of gather ----------------------------------------------------------------
+// A costmap is mostly free space (an aisle turn: five one-pixel walls), so almost every pixel of the crop is 0.  Instead
+// of sampling all ego_w x ego_h pixels through a staged copy of the source window (ego_tiles_kernel: 463 M warp
+// instructions and 112 M shared-memory wavefronts per launch, profiles/r1b_ncu_summary.txt), one CTA per env
+//   1. zeroes a shared-memory image,
+//   2. reads the OCCUPANCY plane (1 bit per cell != 0, bcg_build_lethal_tiles) of the window -- 1/8 of the bytes -- and
+//      lists the occupied cells inside the tile spans the rotated crop touches (warp-aggregated compaction),
+//   3. maps every listed cell forward with cv::warpAffine's float32 matrix and tests the <= 4 crop pixels around the
+//      image point with the exact fixed-point inverse rule (the one the dense kernel applies to every pixel); a crop
+//      pixel samples cell (X, Y) iff that test holds, so the result is bit-identical,
+//   4. hands the image to the bulk-copy engine (cp.async.bulk.global.shared::cta) at the 16-byte phase of its global
+//      destination; < 16 head / tail bytes are stored by lanes.  Two image buffers: the store of env i overlaps env i+1.
+// Why <= 4 candidates: the sample of pixel (u, v) is X = floor(x + 1/2 + d), |d| <= 2^-10, with (x, y) = A (u, v) + b and A
+// a rotation, so the pixels sampling (X, Y) lie within 0.501 (|cos| + |sin|) <= 0.709 of the forward image of (X, Y).
+// Envs whose window holds more than BCG_EGS_LIST occupied cells (filled regions of real costmaps), or whose record is
+// in direct mode, are appended to ego_list and rendered by the dense kernel right after.
+#define BCG_EGS_THREADS 256
+#define BCG_EGS_CTAS 5
+#define BCG_EGS_LIST 2048
+struct EgoSparseTab {
+  int2 adxy[BCG_EGT_MAX_W];                     // (rint(a11 u 2^10), rint(a21 u 2^10))
+  int2 bxy[BCG_EGO_MAX];                        // rint((a12 v + b1) 2^10) + 512 - (X0 << 10), same for y
+  uint32_t list[BCG_EGS_LIST];                  // occupied window cells: y_rel << 16 | x_rel
+  uint32_t count[2];
+  uint32_t pad[2];
+};
+
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__host__ __device__ inline int ego_sparse_out_bytes(const BcgParams& p) { return ((p.ego_w * p.ego_h + 15) & ~15) + 16; }
+
+__global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kernel(const BcgParams p, const BcgBatch b,
+                                                                                   uint8_t* __restrict__ image) {
+  extern __shared__ __align__(128) uint8_t egs_smem[];
+  constexpr int NT = BCG_EGS_THREADS;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int out_bytes = ego_sparse_out_bytes(p);
+  EgoSparseTab& T = *reinterpret_cast<EgoSparseTab*>(egs_smem + 2 * out_bytes);
+  uint8_t* const rec_s = egs_smem + 2 * out_bytes + sizeof(EgoSparseTab);
+  const uint32_t out_u32 = smem_u32(egs_smem), rec_u32 = smem_u32(rec_s);
+  const uint32_t adxy_u32 = smem_u32(T.adxy), bxy_u32 = smem_u32(T.bxy);
+  const uint8_t* const recs = reinterpret_cast<const uint8_t*>(b.ego_work);
+  const int n = b.n_envs, G = gridDim.x;
+  const int ego_w = p.ego_w, ego_h = p.ego_h, npx = ego_w * ego_h;
+  const int e0 = blockIdx.x;
+  if (e0 >= n) return;
+
+  auto fetch_record = [&](int en, int slot) {
+    if (en < n && tid < 16)
+      cp_async_16(rec_u32 + slot * BCG_EGO_WORK_BYTES + tid * 16, recs + (int64_t)en * BCG_EGO_WORK_BYTES + tid * 16, 16u);
+  };
+  constexpr int RD = 3;
+  static_assert(RD < BCG_EGT_REC_SLOTS, "record ring too small");
+#pragma unroll
+  for (int k = 0; k < RD; ++k) fetch_record(e0 + k * G, k);
+  cp_async_commit();
+  if (tid < 2) T.count[tid] = 0;
+  cp_async_wait_all();
+  __syncthreads();
+
+  int e = e0;
+  for (int it = 0; e < n; e += G, ++it) {
+    const int slot = it & (BCG_EGT_REC_SLOTS - 1), par = it & 1;
+    fetch_record(e + RD * G, (it + RD) & (BCG_EGT_REC_SLOTS - 1));
+    cp_async_commit();
+    const EgoTileWork* r = reinterpret_cast<const EgoTileWork*>(rec_s + slot * BCG_EGO_WORK_BYTES);
+    const int mode = r->mode, X0 = r->X0, Y0 = r->Y0, ntx = r->ntx, nty = r->nty;
+    uint8_t* const dst = image + (int64_t)e * npx;
+    const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u);
+    const uint32_t buf = out_u32 + (uint32_t)(par * out_bytes);       // this env's image buffer
+    const uint32_t out0 = buf + phase;                                // image byte i lives at out0 + i
+    if (mode == BCG_EGO_MODE_TILES) {
+      // ---- 1. zero the image (the bulk read of the env two iterations back has completed: see the wait below) ----
+      for (int i = tid * 16; i < out_bytes; i += NT * 16) sts_v4(buf + i, make_uint4(0u, 0u, 0u, 0u));
+      // ---- fixed-point tables of the crop (as the dense kernel) --------------------------------------------------
+      const EgoAffine A = r->aff;
+      for (int t = tid; t < ego_w; t += NT)
+        T.adxy[t] = make_int2(__double2int_rn(A.a11 * t * 1024), __double2int_rn(A.a21 * t * 1024));
+      for (int t = tid; t < ego_h; t += NT)
+        T.bxy[t] = make_int2(__double2int_rn((A.a12 * t + A.b1) * 1024) + 512 - (X0 << 10),
+                             __double2int_rn((A.a22 * t + A.b2) * 1024) + 512 - (Y0 << 10));
+      // ---- 2. occupied cells of the window: a half warp per 32 x 16 bit tile, a lane per row ---------------------
+      const BcgMapDesc* md = b.maps + r->map_id;
+      const int tiles_x = md->tiles_x, tiles_y = md->tiles_y;
+      const uint32_t* occ = b.occ_tile_arena + md->tile_off;
+      const int wx0 = X0 >> 5, nwx = ((X0 + 16 * ntx - 1) >> 5) - wx0 + 1;
+      const int by0 = Y0 >> 4, nby = ((Y0 + 8 * nty - 1) >> 4) - by0 + 1;
+      const int q = lane & 15;
+      const uint32_t span_u32 = rec_u32 + slot * BCG_EGO_WORK_BYTES + 128;
+      int j = tid >> 4, band = 0;                                      // tile (band, j) of this half warp
+      const int rounds = (nby * nwx + NT / 16 - 1) / (NT / 16);        // uniform trip count: the warp votes inside
+      for (int rd = 0; rd < rounds; ++rd, j += NT / 16) {
+        while (j >= nwx) {
+          j -= nwx;
+          ++band;
+        }
+        uint32_t bits = 0;
+        const int ty = by0 + band, tx = wx0 + j;
+        const int yr = ((ty << 4) + q) - Y0;                            // window row of this lane
+        if (band < nby && (unsigned)ty < (unsigned)tiles_y && (unsigned)tx < (unsigned)tiles_x && yr >= 0 && yr < 8 * nty) {
+          const uint32_t sp = lds_u16(span_u32 + 2 * (yr >> 3));
+          const int lo = max(X0 + 16 * (int)(sp & 0xff) - (tx << 5), 0);
+          const int hi = min(X0 + 16 * (int)(sp >> 8) + 15 - (tx << 5), 31);
+          if (lo <= hi) {
+            bits = __ldg(occ + ((((int64_t)ty * tiles_x + tx) << 4) + q));
+            bits &= (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
+          }
+        }
+        if (__any_sync(BCG_FULL, bits != 0u)) {
+          const int cnt = __popc(bits);
+          int incl = cnt;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(BCG_FULL, incl, o);
+            if (lane >= o) incl += up;
+          }
+          uint32_t base = 0;
+          if (lane == 31) base = atomicAdd(&T.count[par], (uint32_t)incl);
+          base = __shfl_sync(BCG_FULL, base, 31);
+          uint32_t pos = base + (uint32_t)(incl - cnt);
+          const int key = (yr << 16) + ((tx << 5) - X0);           // x_rel of bit 0 may be negative, of a kept bit never
+          while (bits) {
+            const int bit = __ffs(bits) - 1;
+            bits &= bits - 1;
+            if (pos < BCG_EGS_LIST) T.list[pos] = (uint32_t)(key + bit);
+            ++pos;
+          }
+        }
+      }
+    }
+    cp_async_wait_group_1();                  // the record needed next iteration has landed
+    __syncthreads();                          // zeroed image, tables, list and count are complete
+    const uint32_t count = T.count[par];
+    const bool sparse = mode == BCG_EGO_MODE_TILES && count <= BCG_EGS_LIST;
+    if (sparse) {
+      // ---- 3. scatter the listed cells ----------------------------------------------------------------------------
+      const BcgMapDesc* md = b.maps + r->map_id;
+      const bool only_lethal = (md->flags & BCG_MAP_ONLY_LETHAL) != 0;
+      const uint8_t* src = b.map_arena + md->data_off;
+      const int pitch = md->pitch;
+      const float m0 = r->fwd[0], m1 = r->fwd[1], m2 = r->fwd[2], m3 = r->fwd[3], m4 = r->fwd[4], m5 = r->fwd[5];
+      for (uint32_t i = tid; i < count; i += NT) {
+        const uint32_t key = T.list[i];
+        const int xr = (int)(key & 0xffffu), yr = (int)(key >> 16);
+        const float X = (float)(X0 + xr), Y = (float)(Y0 + yr);
+        const int fu = (int)floorf(m0 * X + m1 * Y + m2), fv = (int)floorf(m3 * X + m4 * Y + m5);
+        if (fu < -1 || fu >= ego_w || fv < -1 || fv >= ego_h) continue;     // every candidate is outside the crop
+        uint32_t val = 254u;
+        if (!only_lethal) val = __ldg(src + (int64_t)(Y0 + yr) * pitch + (X0 + xr));
+        const int u0 = max(fu, 0), u1 = min(fu + 1, ego_w - 1), v0 = max(fv, 0), v1 = min(fv + 1, ego_h - 1);
+        const uint2 a0 = lds_v2(adxy_u32 + 8u * (uint32_t)u0), a1 = lds_v2(adxy_u32 + 8u * (uint32_t)u1);
+        const uint2 b0 = lds_v2(bxy_u32 + 8u * (uint32_t)v0), b1 = lds_v2(bxy_u32 + 8u * (uint32_t)v1);
+        const bool x00 = (((int)a0.x + (int)b0.x) >> 10) == xr, x10 = (((int)a1.x + (int)b0.x) >> 10) == xr;
+        const bool x01 = (((int)a0.x + (int)b1.x) >> 10) == xr, x11 = (((int)a1.x + (int)b1.x) >> 10) == xr;
+        const bool y00 = (((int)a0.y + (int)b0.y) >> 10) == yr, y10 = (((int)a1.y + (int)b0.y) >> 10) == yr;
+        const bool y01 = (((int)a0.y + (int)b1.y) >> 10) == yr, y11 = (((int)a1.y + (int)b1.y) >> 10) == yr;
+        if (x00 && y00) sts_u8(out0 + (uint32_t)(v0 * ego_w + u0), val);
+        if (x10 && y10) sts_u8(out0 + (uint32_t)(v0 * ego_w + u1), val);
+        if (x01 && y01) sts_u8(out0 + (uint32_t)(v1 * ego_w + u0), val);
+        if (x11 && y11) sts_u8(out0 + (uint32_t)(v1 * ego_w + u1), val);
+      }
+      fence_async_smem();                       // the image bytes are visible to the bulk-copy engine
+    }
+    if (tid == 0) {
+      T.count[par ^ 1] = 0;                     // nobody reads the other counter before the next barrier
+      bulk_wait_read();                         // the store issued last iteration has read its buffer: the next
+    }                                           // iteration may zero it
+    __syncthreads();                            // the image is complete; list, tables and record `it` are free
+    if (sparse) {
+      const int head = min((int)((16u - phase) & 15u), npx), body = (npx - head) & ~15, tail = npx - head - body;
+      if (tid == 0 && body > 0) bulk_store(dst + head, out0 + head, (uint32_t)body);
+      if (warp == 1) {
+        const uint8_t* img = egs_smem + par * out_bytes + phase;
+        if (lane < head) dst[lane] = img[lane];
+        if (lane >= 16 && lane - 16 < tail) dst[head + body + lane - 16] = img[head + body + lane - 16];
+      }
+    } else if (tid == 0) {
+      const int at = atomicAdd(b.ego_list + n, 1);
+      b.ego_list[at] = e;
+    }
+  }
+  if (tid == 0) bulk_wait_all();
 }
 
 // EgoWork records and / or goal_n_state from the current state (stand-alone bcg_observe_ego): one thread per env
@@ -1460,7 +1682,7 @@ static int sm_count_of_current_device(int* out) {
 }
 
 template <int NG>
-static int launch_ego_tiles(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, cudaStream_t s) {
+static int launch_ego_tiles(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, const int* env_list, cudaStream_t s) {
   const int win = ego_window_capacity(*p);
   const int smem = win + (int)sizeof(EgoTab) + BCG_EGT_REC_SLOTS * BCG_EGO_WORK_BYTES;
   static int configured[64] = {0};    // per template instance and device: the attribute is per function and context
@@ -1473,21 +1695,54 @@ static int launch_ego_tiles(const BcgParams* p, const BcgBatch* b, uint8_t* ego_
   int sms = 0;
   if (int rc = sm_count_of_current_device(&sms)) return rc;
   const int grid = b->n_envs < BCG_EGT_CTAS * sms ? b->n_envs : BCG_EGT_CTAS * sms;
-  ego_tiles_kernel<NG><<<grid, BCG_EGT_THREADS, smem, s>>>(*p, *b, ego_image, win);
+  ego_tiles_kernel<NG><<<grid, BCG_EGT_THREADS, smem, s>>>(*p, *b, ego_image, win, env_list);
   BCG_CHECK_CUDA(cudaGetLastError());
   return BCG_OK;
 }
 
-// the image kernel; the per-env records must already be in b->ego_work
+static int launch_ego_dense(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, const int* env_list, cudaStream_t s) {
+  switch ((p->ego_w + 31) / 32) {
+    case 1: return launch_ego_tiles<1>(p, b, ego_image, env_list, s);
+    case 2: return launch_ego_tiles<2>(p, b, ego_image, env_list, s);
+    case 3: return launch_ego_tiles<3>(p, b, ego_image, env_list, s);
+    case 4: return launch_ego_tiles<4>(p, b, ego_image, env_list, s);
+    default: return launch_ego_tiles<5>(p, b, ego_image, env_list, s);
+  }
+}
+
+// sparse scatter kernel for every env, then the dense kernel for the envs it handed over (usually none)
+static int launch_ego_sparse(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, cudaStream_t s) {
+  const int smem = 2 * ego_sparse_out_bytes(*p) + (int)sizeof(EgoSparseTab) + BCG_EGT_REC_SLOTS * BCG_EGO_WORK_BYTES;
+  static int configured[64] = {0};
+  int dev = 0;
+  BCG_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || configured[dev] < smem) {
+    BCG_CHECK_CUDA(cudaFuncSetAttribute(ego_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (dev >= 0 && dev < 64) configured[dev] = smem;
+  }
+  int sms = 0;
+  if (int rc = sm_count_of_current_device(&sms)) return rc;
+  BCG_CHECK_CUDA(cudaMemsetAsync(b->ego_list + b->n_envs, 0, sizeof(int32_t), s));
+  const int grid = b->n_envs < BCG_EGS_CTAS * sms ? b->n_envs : BCG_EGS_CTAS * sms;
+  ego_sparse_kernel<<<grid, BCG_EGS_THREADS, smem, s>>>(*p, *b, ego_image);
+  BCG_CHECK_CUDA(cudaGetLastError());
+  return launch_ego_dense(p, b, ego_image, b->ego_list, s);
+}
+
+// BCG_EGO_KERNEL=dense forces the dense cell-tile kernel for every env (A/B timing of the sparse path)
+static bool ego_dense_kernel_requested() {
+  static const bool dense = [] {
+    const char* v = getenv("BCG_EGO_KERNEL");
+    return v && strcmp(v, "dense") == 0;
+  }();
+  return dense;
+}
+
+// the image kernel(s); the per-env records must already be in b->ego_work
 static int launch_ego_image(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, cudaStream_t s) {
   if (b->cell_tile_arena) {
-    switch ((p->ego_w + 31) / 32) {
-      case 1: return launch_ego_tiles<1>(p, b, ego_image, s);
-      case 2: return launch_ego_tiles<2>(p, b, ego_image, s);
-      case 3: return launch_ego_tiles<3>(p, b, ego_image, s);
-      case 4: return launch_ego_tiles<4>(p, b, ego_image, s);
-      default: return launch_ego_tiles<5>(p, b, ego_image, s);
-    }
+    if (b->occ_tile_arena && b->ego_list && !ego_dense_kernel_requested()) return launch_ego_sparse(p, b, ego_image, s);
+    return launch_ego_dense(p, b, ego_image, nullptr, s);
   }
   const int cap = ego_tile_capacity(*p, *b);
   // alignment slack + the per-row spans of the plain-load path, which live behind the tile

@@ -102,6 +102,7 @@ class VecRandomAisleTurnEnv(VecPlanEnv):
         self.map_arena = torch.zeros(n * self._slot_bytes, dtype=torch.uint8, device=dev)
         self.cell_tile_arena = torch.zeros(n * self._slot_bytes, dtype=torch.uint8, device=dev)
         self.tile_arena = torch.zeros(n * self._tile_slot_words, dtype=torch.int32, device=dev)
+        self.occ_tile_arena = torch.zeros(n * self._tile_slot_words, dtype=torch.int32, device=dev)
         self.path_arena = torch.zeros(n * path_slot, dtype=torch.float64, device=dev)
         self.map_descs = self._to_device(np.frombuffer(bytes(descs), dtype=np.uint8).copy())
         self.path_descs = self._to_device(np.frombuffer(bytes(pdescs), dtype=np.uint8).copy())

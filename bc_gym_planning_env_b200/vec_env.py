@@ -195,6 +195,7 @@ class VecPlanEnv(object):
                 raise ValueError("costmaps are limited to 32767 cells per side")
             d.height, d.width, d.pitch = h, w, _round_up(w, 32)
             d.tiles_x, d.tiles_y = d.pitch // 32, (h + 15) // 16
+            d.flags = nat.MAP_ONLY_LETHAL                   # cleared on device when a cell is neither 0 nor 254
             d.origin_x, d.origin_y = float(cm.get_origin()[0]), float(cm.get_origin()[1])
             d.ctiles_x, d.ctiles_y = d.pitch // 16, (h + 7) // 8
             d.data_off, d.tile_off, d.cell_tile_off = data_off, tile_off, ctile_off
@@ -237,9 +238,11 @@ class VecPlanEnv(object):
         widths = (C.c_int32 * len(self._tmap_widths))(*self._tmap_widths)
         tm = np.zeros(len(descs) * len(self._tmap_widths) * 128, dtype=np.uint8)
         self.tile_arena = torch.zeros(max(pool_words, 1), dtype=torch.int32, device=self.device)
-        self.cell_tile_arena = None
+        self.cell_tile_arena = self.occ_tile_arena = None
         if self.ego_staging == 'tiles':
             self.cell_tile_arena = torch.empty(max(pool_ctile_bytes, 128), dtype=torch.uint8, device=self.device)
+            # occupancy plane (cell != 0) for the sparse egocentric kernel: same layout as the lethal plane
+            self.occ_tile_arena = torch.zeros(max(pool_words, 1), dtype=torch.int32, device=self.device)
         if self.ego_staging == 'tma':
             nat.check(nat.lib().bcg_encode_map_tensor_maps(descs, len(descs), C.c_void_p(map_arena.data_ptr()), widths,
                                                            len(self._tmap_widths), self._tmap_box_h,
@@ -334,6 +337,9 @@ class VecPlanEnv(object):
         b.status, b.stats = self._status.data_ptr(), self._stats.data_ptr()
         if self.cell_tile_arena is not None:
             b.cell_tile_arena = self.cell_tile_arena.data_ptr()
+        if getattr(self, 'occ_tile_arena', None) is not None:
+            self._ego_list = torch.zeros(self.n_envs + 4, dtype=torch.int32, device=self.device)
+            b.occ_tile_arena, b.ego_list = self.occ_tile_arena.data_ptr(), self._ego_list.data_ptr()
         if self.use_tma:
             b.map_tmaps, b.tmap_n_widths, b.tmap_box_h = self.map_tmaps.data_ptr(), len(self._tmap_widths), self._tmap_box_h
             for j, w in enumerate(self._tmap_widths):

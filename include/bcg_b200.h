@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BCG_ABI_VERSION 2
+#define BCG_ABI_VERSION 3
 
 /* error codes */
 #define BCG_OK 0
@@ -116,13 +116,15 @@ typedef struct BcgParams {
  * bit-plane (collision) and the cell tiles (the same uint8 cells re-laid out as 128-byte tiles of 16 px x 8
  * rows, tile (ty, tx) at cell_tile_off + (ty * ctiles_x + tx) * 128, row r of a tile at + r * 16, zero
  * beyond the map; the egocentric kernel fetches whole HBM lines of a rotated window from it) */
+#define BCG_MAP_ONLY_LETHAL 1
 typedef struct BcgMapDesc {
   int64_t data_off;  /* byte offset of uint8 [H][pitch] in the map arena                      */
   int64_t tile_off;  /* uint32 offset of the lethal tile plane in the tile arena               */
   double origin_x, origin_y;
   int32_t height, width, pitch;
   int32_t tiles_x, tiles_y; /* 32 px x 16 rows per 64-byte tile                                */
-  int32_t reserved;
+  int32_t flags;            /* BCG_MAP_ONLY_LETHAL: every non-zero cell is 254 (set by the host before
+                               bcg_build_lethal_tiles, cleared there when another value is met)       */
   int64_t cell_tile_off;    /* byte offset of the map's cell tiles in the cell-tile arena (multiple of 128) */
   int32_t ctiles_x, ctiles_y; /* 16 px x 8 rows per 128-byte cell tile: pitch / 16, ceil(height / 8)     */
 } BcgMapDesc;
@@ -186,6 +188,12 @@ typedef struct BcgBatch {
                             egocentric kernel stages only the 128-byte tiles its rotated source window
                             touches (16-byte cp.async pieces, zero fill outside the map) and map_tmaps is
                             not used                                                                      */
+  const uint32_t* occ_tile_arena; /* optional: the occupancy plane (1 bit per cell, value != 0), laid out exactly
+                            like the lethal tile plane (same tile_off); filled by bcg_build_lethal_tiles.
+                            With it, cell_tile_arena and ego_list the egocentric observation takes the sparse
+                            path: zero the crop, then scatter only the occupied source cells of its window   */
+  int32_t* ego_list;      /* optional scratch [n_envs + 4]: envs whose window holds too many occupied cells
+                            for the sparse path, handed to the dense cell-tile kernel (count at [n_envs])   */
   uint32_t* status; /* [BCG_STATUS_WORDS] */
   double* stats;    /* [BCG_STATS_WORDS]  */
 } BcgBatch;
