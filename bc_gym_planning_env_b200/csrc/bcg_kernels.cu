@@ -1267,6 +1267,7 @@ __global__ void __launch_bounds__(BCG_EGT_THREADS, BCG_EGT_CTAS) ego_tiles_kerne
 #define BCG_EGS_THREADS 256
 #define BCG_EGS_CTAS 5
 #define BCG_EGS_LIST 2048
+#define BCG_EGS_MAX_TILES 128      // 32 x 16 bit tiles a window may span (sparse path); more -> dense kernel
 struct EgoSparseTab {
   int2 adxy[BCG_EGT_MAX_W];                     // (rint(a11 u 2^10), rint(a21 u 2^10))
   int2 bxy[BCG_EGO_MAX];                        // rint((a12 v + b1) 2^10) + 512 - (X0 << 10), same for y
@@ -1333,69 +1334,82 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
     const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u);
     const uint32_t buf = out_u32 + (uint32_t)(par * out_bytes);       // this env's image buffer
     const uint32_t out0 = buf + phase;                                // image byte i lives at out0 + i
-    if (mode == BCG_EGO_MODE_TILES) {
+    const int wx0 = X0 >> 5, nwx = ((X0 + 16 * ntx - 1) >> 5) - wx0 + 1;        // <= 9 columns of 32-cell words
+    const int by0 = Y0 >> 4, nby = ((Y0 + 8 * nty - 1) >> 4) - by0 + 1;         // bands of 16 rows
+    const int ntile = nby * nwx;
+    const bool try_sparse = mode == BCG_EGO_MODE_TILES && ntile <= BCG_EGS_MAX_TILES;
+    if (try_sparse) {
       // ---- 1. zero the image (the bulk read of the env two iterations back has completed: see the wait below) ----
       for (int i = tid * 16; i < out_bytes; i += NT * 16) sts_v4(buf + i, make_uint4(0u, 0u, 0u, 0u));
       // ---- fixed-point tables of the crop (as the dense kernel) --------------------------------------------------
       const EgoAffine A = r->aff;
-      for (int t = tid; t < ego_w; t += NT)
-        T.adxy[t] = make_int2(__double2int_rn(A.a11 * t * 1024), __double2int_rn(A.a21 * t * 1024));
-      for (int t = tid; t < ego_h; t += NT)
-        T.bxy[t] = make_int2(__double2int_rn((A.a12 * t + A.b1) * 1024) + 512 - (X0 << 10),
-                             __double2int_rn((A.a22 * t + A.b2) * 1024) + 512 - (Y0 << 10));
-      // ---- 2. occupied cells of the window: a half warp per 32 x 16 bit tile, a lane per row ---------------------
+      for (int i = tid; i < ego_w + ego_h; i += NT) {             // one pass for the usual 117 + 133 entries
+        if (i < ego_w) {
+          T.adxy[i] = make_int2(__double2int_rn(A.a11 * i * 1024), __double2int_rn(A.a21 * i * 1024));
+        } else {
+          const int t = i - ego_w;
+          T.bxy[t] = make_int2(__double2int_rn((A.a12 * t + A.b1) * 1024) + 512 - (X0 << 10),
+                               __double2int_rn((A.a22 * t + A.b2) * 1024) + 512 - (Y0 << 10));
+        }
+      }
+      // ---- 2. occupied cells of the window: a half warp per 32 x 16 bit tile, a lane per row.  All loads of a thread
+      // are issued before the first is used (one DRAM round trip per env instead of one per tile) -------------------
       const BcgMapDesc* md = b.maps + r->map_id;
       const int tiles_x = md->tiles_x, tiles_y = md->tiles_y;
       const uint32_t* occ = b.occ_tile_arena + md->tile_off;
-      const int wx0 = X0 >> 5, nwx = ((X0 + 16 * ntx - 1) >> 5) - wx0 + 1;
-      const int by0 = Y0 >> 4, nby = ((Y0 + 8 * nty - 1) >> 4) - by0 + 1;
       const int q = lane & 15;
+      const uint32_t inv = (65536u + (uint32_t)nwx - 1u) / (uint32_t)nwx;         // t / nwx == (t * inv) >> 16 for t < 4096
+      constexpr int HW = NT / 16;                                                // half warps per CTA
+      constexpr int RMAX = BCG_EGS_MAX_TILES / HW;
+      uint32_t word[RMAX];
+#pragma unroll
+      for (int rd = 0; rd < RMAX; ++rd) {
+        const int t = (tid >> 4) + rd * HW;
+        const int band = (int)(((uint32_t)t * inv) >> 16), jw = t - band * nwx;
+        const int ty = by0 + band, tx = wx0 + jw;
+        word[rd] = 0u;
+        if (t < ntile && (unsigned)ty < (unsigned)tiles_y && (unsigned)tx < (unsigned)tiles_x)
+          word[rd] = __ldg(occ + (((ty * tiles_x + tx) << 4) + q));
+      }
       const uint32_t span_u32 = rec_u32 + slot * BCG_EGO_WORK_BYTES + 128;
-      int j = tid >> 4, band = 0;                                      // tile (band, j) of this half warp
-      const int rounds = (nby * nwx + NT / 16 - 1) / (NT / 16);        // uniform trip count: the warp votes inside
-      for (int rd = 0; rd < rounds; ++rd, j += NT / 16) {
-        while (j >= nwx) {
-          j -= nwx;
-          ++band;
-        }
-        uint32_t bits = 0;
-        const int ty = by0 + band, tx = wx0 + j;
-        const int yr = ((ty << 4) + q) - Y0;                            // window row of this lane
-        if (band < nby && (unsigned)ty < (unsigned)tiles_y && (unsigned)tx < (unsigned)tiles_x && yr >= 0 && yr < 8 * nty) {
+#pragma unroll
+      for (int rd = 0; rd < RMAX; ++rd) {
+        if (!__any_sync(BCG_FULL, word[rd] != 0u)) continue;                     // the usual case: free space
+        const int t = (tid >> 4) + rd * HW;
+        const int band = (int)(((uint32_t)t * inv) >> 16), jw = t - band * nwx;
+        const int tx = wx0 + jw;
+        const int yr = (((by0 + band) << 4) + q) - Y0;                            // window row of this lane
+        uint32_t bits = 0u;
+        if (yr >= 0 && yr < 8 * nty) {                                            // clip to the tile span of that row
           const uint32_t sp = lds_u16(span_u32 + 2 * (yr >> 3));
           const int lo = max(X0 + 16 * (int)(sp & 0xff) - (tx << 5), 0);
           const int hi = min(X0 + 16 * (int)(sp >> 8) + 15 - (tx << 5), 31);
-          if (lo <= hi) {
-            bits = __ldg(occ + ((((int64_t)ty * tiles_x + tx) << 4) + q));
-            bits &= (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
-          }
+          if (lo <= hi) bits = word[rd] & (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
         }
-        if (__any_sync(BCG_FULL, bits != 0u)) {
-          const int cnt = __popc(bits);
-          int incl = cnt;
+        const int cnt = __popc(bits);
+        int incl = cnt;
 #pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int up = __shfl_up_sync(BCG_FULL, incl, o);
-            if (lane >= o) incl += up;
-          }
-          uint32_t base = 0;
-          if (lane == 31) base = atomicAdd(&T.count[par], (uint32_t)incl);
-          base = __shfl_sync(BCG_FULL, base, 31);
-          uint32_t pos = base + (uint32_t)(incl - cnt);
-          const int key = (yr << 16) + ((tx << 5) - X0);           // x_rel of bit 0 may be negative, of a kept bit never
-          while (bits) {
-            const int bit = __ffs(bits) - 1;
-            bits &= bits - 1;
-            if (pos < BCG_EGS_LIST) T.list[pos] = (uint32_t)(key + bit);
-            ++pos;
-          }
+        for (int o = 1; o < 32; o <<= 1) {
+          const int up = __shfl_up_sync(BCG_FULL, incl, o);
+          if (lane >= o) incl += up;
+        }
+        uint32_t base = 0;
+        if (lane == 31 && incl > 0) base = atomicAdd(&T.count[par], (uint32_t)incl);
+        base = __shfl_sync(BCG_FULL, base, 31);
+        uint32_t pos = base + (uint32_t)(incl - cnt);
+        const int key = (yr << 16) + ((tx << 5) - X0);           // x_rel of bit 0 may be negative, of a kept bit never
+        while (bits) {
+          const int bit = __ffs(bits) - 1;
+          bits &= bits - 1;
+          if (pos < BCG_EGS_LIST) T.list[pos] = (uint32_t)(key + bit);
+          ++pos;
         }
       }
     }
     cp_async_wait_group_1();                  // the record needed next iteration has landed
     __syncthreads();                          // zeroed image, tables, list and count are complete
     const uint32_t count = T.count[par];
-    const bool sparse = mode == BCG_EGO_MODE_TILES && count <= BCG_EGS_LIST;
+    const bool sparse = try_sparse && count <= BCG_EGS_LIST;
     if (sparse) {
       // ---- 3. scatter the listed cells ----------------------------------------------------------------------------
       const BcgMapDesc* md = b.maps + r->map_id;
