@@ -1352,41 +1352,48 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
                                __double2int_rn((A.a22 * t + A.b2) * 1024) + 512 - (Y0 << 10));
         }
       }
-      // ---- 2. occupied cells of the window: a half warp per 32 x 16 bit tile, a lane per row.  All loads of a thread
-      // are issued before the first is used (one DRAM round trip per env instead of one per tile) -------------------
+      // ---- 2. occupied cells of the window: four lanes per 32 x 16 bit tile (a 16-byte load = 4 rows each), eight
+      // tiles per warp and round.  All loads of a thread are issued before the first is used (one DRAM round trip per
+      // env instead of one per round) ---------------------------------------------------------------------------------
       const BcgMapDesc* md = b.maps + r->map_id;
       const int tiles_x = md->tiles_x, tiles_y = md->tiles_y;
-      const uint32_t* occ = b.occ_tile_arena + md->tile_off;
-      const int q = lane & 15;
+      const uint4* occ = reinterpret_cast<const uint4*>(b.occ_tile_arena + md->tile_off);
+      const int g = lane & 3;                                                     // rows 4 g .. 4 g + 3 of the tile
       const uint32_t inv = (65536u + (uint32_t)nwx - 1u) / (uint32_t)nwx;         // t / nwx == (t * inv) >> 16 for t < 4096
-      constexpr int HW = NT / 16;                                                // half warps per CTA
-      constexpr int RMAX = BCG_EGS_MAX_TILES / HW;
-      uint32_t word[RMAX];
+      constexpr int TPR = NT / 4;                                                // tiles per round
+      constexpr int RMAX = BCG_EGS_MAX_TILES / TPR;
+      uint4 word[RMAX];
 #pragma unroll
       for (int rd = 0; rd < RMAX; ++rd) {
-        const int t = (tid >> 4) + rd * HW;
+        const int t = (tid >> 2) + rd * TPR;
         const int band = (int)(((uint32_t)t * inv) >> 16), jw = t - band * nwx;
         const int ty = by0 + band, tx = wx0 + jw;
-        word[rd] = 0u;
+        word[rd] = make_uint4(0u, 0u, 0u, 0u);
         if (t < ntile && (unsigned)ty < (unsigned)tiles_y && (unsigned)tx < (unsigned)tiles_x)
-          word[rd] = __ldg(occ + (((ty * tiles_x + tx) << 4) + q));
+          word[rd] = __ldg(occ + (((ty * tiles_x + tx) << 2) + g));
       }
       const uint32_t span_u32 = rec_u32 + slot * BCG_EGO_WORK_BYTES + 128;
 #pragma unroll
       for (int rd = 0; rd < RMAX; ++rd) {
-        if (!__any_sync(BCG_FULL, word[rd] != 0u)) continue;                     // the usual case: free space
-        const int t = (tid >> 4) + rd * HW;
+        if (!__any_sync(BCG_FULL, (word[rd].x | word[rd].y | word[rd].z | word[rd].w) != 0u)) continue;   // free space
+        const int t = (tid >> 2) + rd * TPR;
         const int band = (int)(((uint32_t)t * inv) >> 16), jw = t - band * nwx;
         const int tx = wx0 + jw;
-        const int yr = (((by0 + band) << 4) + q) - Y0;                            // window row of this lane
-        uint32_t bits = 0u;
-        if (yr >= 0 && yr < 8 * nty) {                                            // clip to the tile span of that row
-          const uint32_t sp = lds_u16(span_u32 + 2 * (yr >> 3));
+        const int yr0 = (((by0 + band) << 4) + 4 * g) - Y0;                       // window row of word .x; 4 | yr0
+        uint32_t bits[4] = {word[rd].x, word[rd].y, word[rd].z, word[rd].w};
+        uint32_t keep = 0u;
+        if (yr0 >= 0 && yr0 < 8 * nty) {                                          // clip to the tile span of these rows
+          const uint32_t sp = lds_u16(span_u32 + 2 * (yr0 >> 3));
           const int lo = max(X0 + 16 * (int)(sp & 0xff) - (tx << 5), 0);
           const int hi = min(X0 + 16 * (int)(sp >> 8) + 15 - (tx << 5), 31);
-          if (lo <= hi) bits = word[rd] & (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
+          if (lo <= hi) keep = (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
         }
-        const int cnt = __popc(bits);
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          bits[k] &= keep;
+          cnt += __popc(bits[k]);
+        }
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -1397,12 +1404,16 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
         if (lane == 31 && incl > 0) base = atomicAdd(&T.count[par], (uint32_t)incl);
         base = __shfl_sync(BCG_FULL, base, 31);
         uint32_t pos = base + (uint32_t)(incl - cnt);
-        const int key = (yr << 16) + ((tx << 5) - X0);           // x_rel of bit 0 may be negative, of a kept bit never
-        while (bits) {
-          const int bit = __ffs(bits) - 1;
-          bits &= bits - 1;
-          if (pos < BCG_EGS_LIST) T.list[pos] = (uint32_t)(key + bit);
-          ++pos;
+        const int key = (yr0 << 16) + ((tx << 5) - X0);          // x_rel of bit 0 may be negative, of a kept bit never
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint32_t w = bits[k];
+          while (w) {
+            const int bit = __ffs(w) - 1;
+            w &= w - 1;
+            if (pos < BCG_EGS_LIST) T.list[pos] = (uint32_t)(key + (k << 16) + bit);
+            ++pos;
+          }
         }
       }
     }
