@@ -1276,6 +1276,14 @@ struct EgoSparseTab {
   uint32_t pad[2];
 };
 
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -1403,16 +1411,18 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
         uint32_t base = 0;
         if (lane == 31 && incl > 0) base = atomicAdd(&T.count[par], (uint32_t)incl);
         base = __shfl_sync(BCG_FULL, base, 31);
-        uint32_t pos = base + (uint32_t)(incl - cnt);
+        const uint32_t total = __shfl_sync(BCG_FULL, (uint32_t)incl, 31);
+        if (base + total > BCG_EGS_LIST) continue;               // overflow: the env goes to the dense kernel anyway
+        uint32_t at = smem_u32(T.list) + 4u * (base + (uint32_t)(incl - cnt));
         const int key = (yr0 << 16) + ((tx << 5) - X0);          // x_rel of bit 0 may be negative, of a kept bit never
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           uint32_t w = bits[k];
           while (w) {
-            const int bit = __ffs(w) - 1;
-            w &= w - 1;
-            if (pos < BCG_EGS_LIST) T.list[pos] = (uint32_t)(key + (k << 16) + bit);
-            ++pos;
+            const int bit = 31 - __clz(w);                       // order within the list is irrelevant
+            w ^= 1u << bit;
+            sts_u32(at, (uint32_t)(key + (k << 16) + bit));
+            at += 4u;
           }
         }
       }
@@ -1428,25 +1438,31 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
       const uint8_t* src = b.map_arena + md->data_off;
       const int pitch = md->pitch;
       const float m0 = r->fwd[0], m1 = r->fwd[1], m2 = r->fwd[2], m3 = r->fwd[3], m4 = r->fwd[4], m5 = r->fwd[5];
+      const uint32_t list_u32 = smem_u32(T.list);
       for (uint32_t i = tid; i < count; i += NT) {
-        const uint32_t key = T.list[i];
+        const uint32_t key = lds_u32(list_u32 + 4u * i);
         const int xr = (int)(key & 0xffffu), yr = (int)(key >> 16);
         const float X = (float)(X0 + xr), Y = (float)(Y0 + yr);
-        const int fu = (int)floorf(m0 * X + m1 * Y + m2), fv = (int)floorf(m3 * X + m4 * Y + m5);
+        // candidates only: fused multiply-adds are fine here, the fixed-point test below decides
+        const int fu = __float2int_rd(__fmaf_rn(m0, X, __fmaf_rn(m1, Y, m2)));
+        const int fv = __float2int_rd(__fmaf_rn(m3, X, __fmaf_rn(m4, Y, m5)));
         if (fu < -1 || fu >= ego_w || fv < -1 || fv >= ego_h) continue;     // every candidate is outside the crop
         uint32_t val = 254u;
         if (!only_lethal) val = __ldg(src + (int64_t)(Y0 + yr) * pitch + (X0 + xr));
         const int u0 = max(fu, 0), u1 = min(fu + 1, ego_w - 1), v0 = max(fv, 0), v1 = min(fv + 1, ego_h - 1);
         const uint2 a0 = lds_v2(adxy_u32 + 8u * (uint32_t)u0), a1 = lds_v2(adxy_u32 + 8u * (uint32_t)u1);
         const uint2 b0 = lds_v2(bxy_u32 + 8u * (uint32_t)v0), b1 = lds_v2(bxy_u32 + 8u * (uint32_t)v1);
-        const bool x00 = (((int)a0.x + (int)b0.x) >> 10) == xr, x10 = (((int)a1.x + (int)b0.x) >> 10) == xr;
-        const bool x01 = (((int)a0.x + (int)b1.x) >> 10) == xr, x11 = (((int)a1.x + (int)b1.x) >> 10) == xr;
-        const bool y00 = (((int)a0.y + (int)b0.y) >> 10) == yr, y10 = (((int)a1.y + (int)b0.y) >> 10) == yr;
-        const bool y01 = (((int)a0.y + (int)b1.y) >> 10) == yr, y11 = (((int)a1.y + (int)b1.y) >> 10) == yr;
-        if (x00 && y00) sts_u8(out0 + (uint32_t)(v0 * ego_w + u0), val);
-        if (x10 && y10) sts_u8(out0 + (uint32_t)(v0 * ego_w + u1), val);
-        if (x01 && y01) sts_u8(out0 + (uint32_t)(v1 * ego_w + u0), val);
-        if (x11 && y11) sts_u8(out0 + (uint32_t)(v1 * ego_w + u1), val);
+        // (a + b) >> 10 == r  <=>  0 <= a + b - (r << 10) < 1024
+        const int xs = xr << 10, ys = yr << 10;
+        const bool h00 = (uint32_t)((int)a0.x + (int)b0.x - xs) < 1024u && (uint32_t)((int)a0.y + (int)b0.y - ys) < 1024u;
+        const bool h10 = (uint32_t)((int)a1.x + (int)b0.x - xs) < 1024u && (uint32_t)((int)a1.y + (int)b0.y - ys) < 1024u;
+        const bool h01 = (uint32_t)((int)a0.x + (int)b1.x - xs) < 1024u && (uint32_t)((int)a0.y + (int)b1.y - ys) < 1024u;
+        const bool h11 = (uint32_t)((int)a1.x + (int)b1.x - xs) < 1024u && (uint32_t)((int)a1.y + (int)b1.y - ys) < 1024u;
+        const uint32_t row0 = out0 + (uint32_t)(v0 * ego_w), row1 = out0 + (uint32_t)(v1 * ego_w);
+        if (h00) sts_u8(row0 + (uint32_t)u0, val);
+        if (h10) sts_u8(row0 + (uint32_t)u1, val);
+        if (h01) sts_u8(row1 + (uint32_t)u0, val);
+        if (h11) sts_u8(row1 + (uint32_t)u1, val);
       }
       fence_async_smem();                       // the image bytes are visible to the bulk-copy engine
     }
