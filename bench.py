@@ -41,6 +41,10 @@ def parse_args():
     ap.add_argument("--no-ego", action="store_true", help="skip the egocentric observation kernel (not the headline)")
     ap.add_argument("--ego-staging", default="tiles", choices=["tiles", "tma", "spans"],
                     help="how the egocentric kernel stages its source window (see VecPlanEnv)")
+    ap.add_argument("--worlds", default="pool", choices=["pool", "device"],
+                    help="pool: --pool host-built maps replicated on device (default); device: every env's own world drawn "
+                         "and rasterised on the GPU (bcg_generate_aisles; about 1.2 MB of slots per env)")
+    ap.add_argument("--gen-envs", type=int, default=8192, help="envs of the device-generation (reset storm) measurement; 0 = skip")
     ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--ref-envs", type=int, default=16, help="reference arm: envs advanced per worker per step")
@@ -53,8 +57,10 @@ def workload_config(args, n_envs):
                     "auto-reset, egocentric obs %s" % (n_envs, DELAYS[0], DELAYS[1], DELAYS[2], "off" if args.no_ego else "on"),
         "envs_per_gpu": n_envs,
         "map_pool": args.pool,
-        "maps": "random aisle turns (RandomAisleTurnEnv distribution); pool of %d distinct maps generated on the host, "
-                "replicated on device so every env owns a private costmap copy in HBM" % args.pool,
+        "maps": ("random aisle turns (RandomAisleTurnEnv distribution); pool of %d distinct maps generated on the host, "
+                 "replicated on device so every env owns a private costmap copy in HBM" % args.pool) if args.worlds == "pool"
+        else "random aisle turns (RandomAisleTurnEnv distribution), one distinct world per env drawn and rasterised on the "
+             "GPU (bcg_generate_aisles, Philox)",
         "ego_staging": args.ego_staging,
         "l2": "inputs larger than L2 (per-env costmaps + egocentric output are GBs per step); no explicit flush",
     }
@@ -171,6 +177,24 @@ def cpu_baseline_sample(seconds, with_ego):
                       "host has %d cores" % (n, dt, os.cpu_count())}
 
 
+def cpu_generation_sample(seconds):
+    """Worlds per second of the host path the reference takes at every RandomAisleTurnEnv.reset (draw, geometry,
+    cv2-equivalent walls, refine_path, initial reward state), restated by the oracle, on one core."""
+    from oracle import aisle_oracle as A
+    from oracle import plan_env_oracle as O
+    rng = np.random.RandomState(5)
+    t0 = time.perf_counter()
+    n = 0
+    while time.perf_counter() - t0 < seconds:
+        coarse, costmap, origin = A.aisle_world(A.draw_turn_params(rng), 0.03)
+        path = O.refine_path(coarse, 0.05)
+        O.initial_reward_state(path, 1.0, np.pi / 2)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "worlds/s", "cores": 1, "kind": "port",
+            "sample": "%d aisle worlds of the NumPy oracle port in %.1f s on 1 core" % (n, dt)}
+
+
 def _single_threaded_math():
     """One worker per core: keep BLAS / OpenCV from spawning their own thread pools in every worker."""
     try:
@@ -248,6 +272,10 @@ def build_env(args, rank, device):
     from bc_gym_planning_env_b200.envs.synth_turn_env import random_aisle_pool
     from bc_gym_planning_env_b200.vec_env import VecPlanEnv
     params = aisle_params()
+    if args.worlds == "device":
+        from bc_gym_planning_env_b200.vec_aisle_env import VecRandomAisleTurnEnv
+        return VecRandomAisleTurnEnv(args.envs, params, seed=1234, auto_reset=True, device=device,
+                                     env_id_base=rank * args.envs, with_ego=not args.no_ego)
     costmaps, paths = random_aisle_pool(args.pool, 10000 + rank * args.pool, params)
     env = VecPlanEnv(costmaps, paths, params, n_envs=args.envs, seed=1234, auto_reset=True, device=device,
                      env_id_base=rank * args.envs, private_map_copies=True, with_ego=not args.no_ego,
@@ -369,8 +397,16 @@ def run_b200(args):
                        "algorithmic bytes (SURVEY 8d) = in-map footprint pixels x 1 B (uint8 definition; the kernel reads "
                        "the derived 1-bit lethal tile plane) + remaining path points x 24 B (the kernel skips path chunks "
                        "farther than the reach radius); collision-only share: %.1f MB" % (coll_bytes / 1e6))
-    ego_name = "ego_tiles_kernel" if args.ego_staging == "tiles" else "ego_kernel"
-    roof_ego = roof(ego_name, ego_bytes, ego_ms, "algorithmic bytes = 2 x ego_w x ego_h per env (gather + write); staging: " + args.ego_staging)
+    sparse = getattr(env, "_ego_list", None) is not None and os.environ.get("BCG_EGO_KERNEL") != "dense"
+    ego_name = "ego_sparse_kernel" if sparse else ("ego_tiles_kernel" if env.ego_staging == "tiles" else "ego_kernel")
+    dense_envs = int(env._ego_list[n].item()) if sparse else n
+    roof_ego = roof(ego_name, ego_bytes, ego_ms,
+                    "algorithmic bytes = 2 x ego_w x ego_h per env (SURVEY 8d: source read + image write).  " +
+                    ("The sparse kernel reads the 1-bit occupancy plane of the window instead of its bytes and scatters only "
+                     "occupied cells, so its physical DRAM traffic (`traffic`) is below the algorithmic bytes; the image "
+                     "write alone is %.2f GB per launch.  ms_per_launch covers ego_sparse_kernel plus the dense "
+                     "ego_tiles_kernel launch for the %d envs it handed over in the last step." % (ego_bytes / 2e9, dense_envs)
+                     if sparse else "staging: " + env.ego_staging))
     dominant = roof_ego if (not args.no_ego and ego_ms >= cr_ms) else roof_commit
 
     # ---- stand-alone collision kernels, cold L2 (flush between launches) ----------------------------
@@ -395,6 +431,31 @@ def run_b200(args):
     tiles_ms = time_kernel(lambda: nat.check(nat.lib().bcg_collision(C.byref(env._c_params), C.byref(env._batch), None, nat.ptr(flags), None, s)))
     u8_ms = time_kernel(lambda: nat.check(nat.lib().bcg_collision_u8(C.byref(env._c_params), C.byref(env._batch), None, nat.ptr(flags), s)))
     del flush
+
+    # ---- reset storm: every env of a batch gets a new world on the device -----------
+    generation = None
+    if args.gen_envs > 0 and rank == 0:
+        from bc_gym_planning_env_b200.vec_aisle_env import VecRandomAisleTurnEnv
+        genv = env if args.worlds == "device" else VecRandomAisleTurnEnv(args.gen_envs, aisle_params(), seed=99, device=device)
+        for _ in range(2):
+            genv.generate()
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        g0.record()
+        for _ in range(reps):
+            genv.generate()
+        g1.record()
+        torch.cuda.synchronize()
+        gms = g0.elapsed_time(g1) / reps
+        genv.check_status()
+        generation = {"worlds_per_sec": genv.n_envs / (gms * 1e-3), "ms_per_launch": gms, "envs": genv.n_envs,
+                      "kernel": "generate_aisles_kernel",
+                      "what": "RandomAisleTurnEnv.reset with draw_new_turn_on_reset for every env: turn draw, five walls "
+                              "(old ones erased), both tile planes, refined path, initial state"}
+        if genv is not env:
+            del genv
+            torch.cuda.empty_cache()
 
     # ---- e2e: host actions in, host results out, every step -----------------------------------------
     h_actions = [a.cpu().pin_memory() for a in actions]
@@ -423,6 +484,8 @@ def run_b200(args):
 
     if rank == 0:
         cpu = cpu_baseline_sample(args.cpu_seconds, not args.no_ego) if args.gpus == 1 else None
+        if generation is not None and args.gpus == 1:
+            generation["cpu_baseline"] = cpu_generation_sample(min(args.cpu_seconds, 3.0))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -431,7 +494,8 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "pinned-host actions in; reward f64, done u8 and the 12-float compact observation out; "
                             "egocentric images stay in HBM for a GPU-resident policy"},
-            "gpu_launches": args.steps * (3 if args.no_ego else 4) * world,
+            "gpu_launches": args.steps * (3 if args.no_ego else (5 if sparse else 4)) * world,
+            "ego_dense_fallback_envs_last_step": None if args.no_ego else dense_envs,
             "roofline": dominant,
             "roofline_collision": roof_commit,
             "roofline_ego": None if args.no_ego else roof_ego,
@@ -442,6 +506,7 @@ def run_b200(args):
                 "u8": roof("collision_kernel (uint8 rows), cold L2", coll_bytes, u8_ms, "uint8-definition bytes"),
             },
             "value_without_ego_obs": no_ego_value,
+            "generation": generation,
             "episode_stats": {k: float(v) for k, v in zip(nat.STAT_NAMES, stats.tolist())},
             "cpu_baseline": cpu,
         }
