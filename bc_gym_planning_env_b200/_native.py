@@ -160,7 +160,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build()
+    path = os.environ.get("BCG_B200_LIB") or _build.build()    # BCG_B200_LIB: a tuning variant (csrc/build.py build_variant)
     handle = C.CDLL(path)
     for name, (restype, argtypes) in SYMBOLS.items():
         fn = getattr(handle, name)  # AttributeError here = header and library disagree

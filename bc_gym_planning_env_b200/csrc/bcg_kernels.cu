@@ -1251,23 +1251,39 @@ __global__ void __launch_bounds__(BCG_EGT_THREADS, BCG_EGT_CTAS) ego_tiles_kerne
 // ---- ego_sparse_kernel: scatter instead of gather ----------------------------------------------------------------
 // A costmap is mostly free space (an aisle turn: five one-pixel walls), so almost every pixel of the crop is 0.  Instead
 // of sampling all ego_w x ego_h pixels through a staged copy of the source window (ego_tiles_kernel: 463 M warp
-// instructions and 112 M shared-memory wavefronts per launch, profiles/r1b_ncu_summary.txt), one CTA per env
-//   1. zeroes a shared-memory image,
+// instructions and 112 M shared-memory wavefronts per launch, profiles/r1b_ncu_summary.txt), one small CTA per env
+//   1. zeroes the crop in global memory: one thread hands the 16-byte aligned body to the bulk-copy engine
+//      (cp.async.bulk.global.shared::cta from a shared page of zeros), lanes store the < 16 head / tail bytes,
 //   2. reads the OCCUPANCY plane (1 bit per cell != 0, bcg_build_lethal_tiles) of the window -- 1/8 of the bytes -- and
 //      lists the occupied cells inside the tile spans the rotated crop touches (warp-aggregated compaction),
 //   3. maps every listed cell forward with cv::warpAffine's float32 matrix and tests the <= 4 crop pixels around the
 //      image point with the exact fixed-point inverse rule (the one the dense kernel applies to every pixel); a crop
-//      pixel samples cell (X, Y) iff that test holds, so the result is bit-identical,
-//   4. hands the image to the bulk-copy engine (cp.async.bulk.global.shared::cta) at the 16-byte phase of its global
-//      destination; < 16 head / tail bytes are stored by lanes.  Two image buffers: the store of env i overlaps env i+1.
+//      pixel samples cell (X, Y) iff that test holds, so the result is bit-identical.  Hits are single-byte stores on
+//      top of the zeros (the bulk stores are waited for before the barrier that precedes this phase).
 // Why <= 4 candidates: the sample of pixel (u, v) is X = floor(x + 1/2 + d), |d| <= 2^-10, with (x, y) = A (u, v) + b and A
 // a rotation, so the pixels sampling (X, Y) lie within 0.501 (|cos| + |sin|) <= 0.709 of the forward image of (X, Y).
+// No image lives in shared memory, so a CTA needs ~9 KB and many run per SM: the kernel is bound by latency (one
+// DRAM round trip for the occupancy words, two barriers) and by its ~3 k warp instructions per env, not by bytes.
 // Envs whose window holds more than BCG_EGS_LIST occupied cells (filled regions of real costmaps), or whose record is
 // in direct mode, are appended to ego_list and rendered by the dense kernel right after.
-#define BCG_EGS_THREADS 256
-#define BCG_EGS_CTAS 5
-#define BCG_EGS_LIST 2048
-#define BCG_EGS_MAX_TILES 128      // 32 x 16 bit tiles a window may span (sparse path); more -> dense kernel
+// shape chosen by measurement (profiles/probes/egs_variants.py, profiles/r1_notes.md): 64 x 16 0.292 ms, 128 x 12 0.303,
+// 256 x 6 0.371, 64 x 24 (fewer registers) 0.458, 32 x 24 0.578
+#ifndef BCG_EGS_THREADS
+#define BCG_EGS_THREADS 64
+#endif
+#ifndef BCG_EGS_CTAS
+#define BCG_EGS_CTAS 16
+#endif
+#ifndef BCG_EGS_LIST
+#define BCG_EGS_LIST 1024
+#endif
+#ifndef BCG_EGS_REC_SLOTS
+#define BCG_EGS_REC_SLOTS 4          // record ring (power of two, > the prefetch distance 3)
+#endif
+#define BCG_EGS_MAX_TILES 128        // 32 x 16 bit tiles a window may span (sparse path); more -> dense kernel
+#ifndef BCG_EGS_ZERO_BYTES
+#define BCG_EGS_ZERO_BYTES 4096      // shared page of zeros the bulk stores read
+#endif
 struct EgoSparseTab {
   int2 adxy[BCG_EGT_MAX_W];                     // (rint(a11 u 2^10), rint(a21 u 2^10))
   int2 bxy[BCG_EGO_MAX];                        // rint((a12 v + b1) 2^10) + 512 - (X0 << 10), same for y
@@ -1284,9 +1300,6 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
-  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
 __device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
   uint2 v;
   asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
@@ -1294,24 +1307,20 @@ __device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
 }
 __device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__host__ __device__ inline int ego_sparse_out_bytes(const BcgParams& p) { return ((p.ego_w * p.ego_h + 15) & ~15) + 16; }
-
 __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kernel(const BcgParams p, const BcgBatch b,
                                                                                    uint8_t* __restrict__ image) {
-  extern __shared__ __align__(128) uint8_t egs_smem[];
+  __shared__ __align__(128) uint8_t zero_s[BCG_EGS_ZERO_BYTES];
+  __shared__ __align__(16) EgoSparseTab T;
+  __shared__ __align__(128) uint8_t rec_s[BCG_EGS_REC_SLOTS * BCG_EGO_WORK_BYTES];
   constexpr int NT = BCG_EGS_THREADS;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int out_bytes = ego_sparse_out_bytes(p);
-  EgoSparseTab& T = *reinterpret_cast<EgoSparseTab*>(egs_smem + 2 * out_bytes);
-  uint8_t* const rec_s = egs_smem + 2 * out_bytes + sizeof(EgoSparseTab);
-  const uint32_t out_u32 = smem_u32(egs_smem), rec_u32 = smem_u32(rec_s);
-  const uint32_t adxy_u32 = smem_u32(T.adxy), bxy_u32 = smem_u32(T.bxy);
+  const uint32_t zero_u32 = smem_u32(zero_s), rec_u32 = smem_u32(rec_s);
+  const uint32_t adxy_u32 = smem_u32(T.adxy), bxy_u32 = smem_u32(T.bxy), list_u32 = smem_u32(T.list);
   const uint8_t* const recs = reinterpret_cast<const uint8_t*>(b.ego_work);
   const int n = b.n_envs, G = gridDim.x;
   const int ego_w = p.ego_w, ego_h = p.ego_h, npx = ego_w * ego_h;
@@ -1323,35 +1332,46 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
       cp_async_16(rec_u32 + slot * BCG_EGO_WORK_BYTES + tid * 16, recs + (int64_t)en * BCG_EGO_WORK_BYTES + tid * 16, 16u);
   };
   constexpr int RD = 3;
-  static_assert(RD < BCG_EGT_REC_SLOTS, "record ring too small");
+  static_assert(RD < BCG_EGS_REC_SLOTS, "record ring too small");
 #pragma unroll
   for (int k = 0; k < RD; ++k) fetch_record(e0 + k * G, k);
   cp_async_commit();
+  for (int i = tid * 16; i < BCG_EGS_ZERO_BYTES; i += NT * 16) *reinterpret_cast<uint4*>(zero_s + i) = make_uint4(0u, 0u, 0u, 0u);
   if (tid < 2) T.count[tid] = 0;
+  fence_async_smem();                         // the zeros are visible to the bulk-copy engine
   cp_async_wait_all();
   __syncthreads();
 
   int e = e0;
   for (int it = 0; e < n; e += G, ++it) {
-    const int slot = it & (BCG_EGT_REC_SLOTS - 1), par = it & 1;
-    fetch_record(e + RD * G, (it + RD) & (BCG_EGT_REC_SLOTS - 1));
+    const int slot = it & (BCG_EGS_REC_SLOTS - 1), par = it & 1;
+    fetch_record(e + RD * G, (it + RD) & (BCG_EGS_REC_SLOTS - 1));
     cp_async_commit();
     const EgoTileWork* r = reinterpret_cast<const EgoTileWork*>(rec_s + slot * BCG_EGO_WORK_BYTES);
     const int mode = r->mode, X0 = r->X0, Y0 = r->Y0, ntx = r->ntx, nty = r->nty;
     uint8_t* const dst = image + (int64_t)e * npx;
-    const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u);
-    const uint32_t buf = out_u32 + (uint32_t)(par * out_bytes);       // this env's image buffer
-    const uint32_t out0 = buf + phase;                                // image byte i lives at out0 + i
     const int wx0 = X0 >> 5, nwx = ((X0 + 16 * ntx - 1) >> 5) - wx0 + 1;        // <= 9 columns of 32-cell words
     const int by0 = Y0 >> 4, nby = ((Y0 + 8 * nty - 1) >> 4) - by0 + 1;         // bands of 16 rows
     const int ntile = nby * nwx;
     const bool try_sparse = mode == BCG_EGO_MODE_TILES && ntile <= BCG_EGS_MAX_TILES;
     if (try_sparse) {
-      // ---- 1. zero the image (the bulk read of the env two iterations back has completed: see the wait below) ----
-      for (int i = tid * 16; i < out_bytes; i += NT * 16) sts_v4(buf + i, make_uint4(0u, 0u, 0u, 0u));
+      // ---- 1. zero the crop in global memory ----------------------------------------------------------------------
+      {
+        const int head = min((int)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u), npx);
+        const int body = (npx - head) & ~15, tail = npx - head - body;
+        if (tid == 0) {
+          for (int o = 0; o < body; o += BCG_EGS_ZERO_BYTES)
+            bulk_store(dst + head + o, zero_u32, (uint32_t)min(body - o, BCG_EGS_ZERO_BYTES));
+          bulk_commit();
+        }
+        if (warp == NT / 32 - 1) {
+          if (lane < head) dst[lane] = 0;
+          if (lane >= 16 && lane - 16 < tail) dst[head + body + lane - 16] = 0;
+        }
+      }
       // ---- fixed-point tables of the crop (as the dense kernel) --------------------------------------------------
       const EgoAffine A = r->aff;
-      for (int i = tid; i < ego_w + ego_h; i += NT) {             // one pass for the usual 117 + 133 entries
+      for (int i = tid; i < ego_w + ego_h; i += NT) {
         if (i < ego_w) {
           T.adxy[i] = make_int2(__double2int_rn(A.a11 * i * 1024), __double2int_rn(A.a21 * i * 1024));
         } else {
@@ -1369,7 +1389,7 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
       const int g = lane & 3;                                                     // rows 4 g .. 4 g + 3 of the tile
       const uint32_t inv = (65536u + (uint32_t)nwx - 1u) / (uint32_t)nwx;         // t / nwx == (t * inv) >> 16 for t < 4096
       constexpr int TPR = NT / 4;                                                // tiles per round
-      constexpr int RMAX = BCG_EGS_MAX_TILES / TPR;
+      constexpr int RMAX = (BCG_EGS_MAX_TILES + TPR - 1) / TPR;
       uint4 word[RMAX];
 #pragma unroll
       for (int rd = 0; rd < RMAX; ++rd) {
@@ -1413,7 +1433,7 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
         base = __shfl_sync(BCG_FULL, base, 31);
         const uint32_t total = __shfl_sync(BCG_FULL, (uint32_t)incl, 31);
         if (base + total > BCG_EGS_LIST) continue;               // overflow: the env goes to the dense kernel anyway
-        uint32_t at = smem_u32(T.list) + 4u * (base + (uint32_t)(incl - cnt));
+        uint32_t at = list_u32 + 4u * (base + (uint32_t)(incl - cnt));
         const int key = (yr0 << 16) + ((tx << 5) - X0);          // x_rel of bit 0 may be negative, of a kept bit never
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -1426,9 +1446,10 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
           }
         }
       }
+      if (tid == 0) bulk_wait_all();          // the zeros have landed (they had the whole scan to do so)
     }
     cp_async_wait_group_1();                  // the record needed next iteration has landed
-    __syncthreads();                          // zeroed image, tables, list and count are complete
+    __syncthreads();                          // zeros (incl. head / tail bytes), tables, list and count are complete
     const uint32_t count = T.count[par];
     const bool sparse = try_sparse && count <= BCG_EGS_LIST;
     if (sparse) {
@@ -1438,7 +1459,6 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
       const uint8_t* src = b.map_arena + md->data_off;
       const int pitch = md->pitch;
       const float m0 = r->fwd[0], m1 = r->fwd[1], m2 = r->fwd[2], m3 = r->fwd[3], m4 = r->fwd[4], m5 = r->fwd[5];
-      const uint32_t list_u32 = smem_u32(T.list);
       for (uint32_t i = tid; i < count; i += NT) {
         const uint32_t key = lds_u32(list_u32 + 4u * i);
         const int xr = (int)(key & 0xffffu), yr = (int)(key >> 16);
@@ -1447,7 +1467,7 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
         const int fu = __float2int_rd(__fmaf_rn(m0, X, __fmaf_rn(m1, Y, m2)));
         const int fv = __float2int_rd(__fmaf_rn(m3, X, __fmaf_rn(m4, Y, m5)));
         if (fu < -1 || fu >= ego_w || fv < -1 || fv >= ego_h) continue;     // every candidate is outside the crop
-        uint32_t val = 254u;
+        uint8_t val = 254;
         if (!only_lethal) val = __ldg(src + (int64_t)(Y0 + yr) * pitch + (X0 + xr));
         const int u0 = max(fu, 0), u1 = min(fu + 1, ego_w - 1), v0 = max(fv, 0), v1 = min(fv + 1, ego_h - 1);
         const uint2 a0 = lds_v2(adxy_u32 + 8u * (uint32_t)u0), a1 = lds_v2(adxy_u32 + 8u * (uint32_t)u1);
@@ -1458,33 +1478,19 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
         const bool h10 = (uint32_t)((int)a1.x + (int)b0.x - xs) < 1024u && (uint32_t)((int)a1.y + (int)b0.y - ys) < 1024u;
         const bool h01 = (uint32_t)((int)a0.x + (int)b1.x - xs) < 1024u && (uint32_t)((int)a0.y + (int)b1.y - ys) < 1024u;
         const bool h11 = (uint32_t)((int)a1.x + (int)b1.x - xs) < 1024u && (uint32_t)((int)a1.y + (int)b1.y - ys) < 1024u;
-        const uint32_t row0 = out0 + (uint32_t)(v0 * ego_w), row1 = out0 + (uint32_t)(v1 * ego_w);
-        if (h00) sts_u8(row0 + (uint32_t)u0, val);
-        if (h10) sts_u8(row0 + (uint32_t)u1, val);
-        if (h01) sts_u8(row1 + (uint32_t)u0, val);
-        if (h11) sts_u8(row1 + (uint32_t)u1, val);
-      }
-      fence_async_smem();                       // the image bytes are visible to the bulk-copy engine
-    }
-    if (tid == 0) {
-      T.count[par ^ 1] = 0;                     // nobody reads the other counter before the next barrier
-      bulk_wait_read();                         // the store issued last iteration has read its buffer: the next
-    }                                           // iteration may zero it
-    __syncthreads();                            // the image is complete; list, tables and record `it` are free
-    if (sparse) {
-      const int head = min((int)((16u - phase) & 15u), npx), body = (npx - head) & ~15, tail = npx - head - body;
-      if (tid == 0 && body > 0) bulk_store(dst + head, out0 + head, (uint32_t)body);
-      if (warp == 1) {
-        const uint8_t* img = egs_smem + par * out_bytes + phase;
-        if (lane < head) dst[lane] = img[lane];
-        if (lane >= 16 && lane - 16 < tail) dst[head + body + lane - 16] = img[head + body + lane - 16];
+        uint8_t* const row0 = dst + v0 * ego_w, * const row1 = dst + v1 * ego_w;
+        if (h00) row0[u0] = val;
+        if (h10) row0[u1] = val;
+        if (h01) row1[u0] = val;
+        if (h11) row1[u1] = val;
       }
     } else if (tid == 0) {
       const int at = atomicAdd(b.ego_list + n, 1);
       b.ego_list[at] = e;
     }
+    if (tid == 0) T.count[par ^ 1] = 0;         // nobody reads the other counter before the next barrier
+    __syncthreads();                            // list, tables and record `it` are free
   }
-  if (tid == 0) bulk_wait_all();
 }
 
 // EgoWork records and / or goal_n_state from the current state (stand-alone bcg_observe_ego): one thread per env
@@ -1753,19 +1759,11 @@ static int launch_ego_dense(const BcgParams* p, const BcgBatch* b, uint8_t* ego_
 
 // sparse scatter kernel for every env, then the dense kernel for the envs it handed over (usually none)
 static int launch_ego_sparse(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, cudaStream_t s) {
-  const int smem = 2 * ego_sparse_out_bytes(*p) + (int)sizeof(EgoSparseTab) + BCG_EGT_REC_SLOTS * BCG_EGO_WORK_BYTES;
-  static int configured[64] = {0};
-  int dev = 0;
-  BCG_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || configured[dev] < smem) {
-    BCG_CHECK_CUDA(cudaFuncSetAttribute(ego_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    if (dev >= 0 && dev < 64) configured[dev] = smem;
-  }
   int sms = 0;
   if (int rc = sm_count_of_current_device(&sms)) return rc;
   BCG_CHECK_CUDA(cudaMemsetAsync(b->ego_list + b->n_envs, 0, sizeof(int32_t), s));
   const int grid = b->n_envs < BCG_EGS_CTAS * sms ? b->n_envs : BCG_EGS_CTAS * sms;
-  ego_sparse_kernel<<<grid, BCG_EGS_THREADS, smem, s>>>(*p, *b, ego_image);
+  ego_sparse_kernel<<<grid, BCG_EGS_THREADS, 0, s>>>(*p, *b, ego_image);
   BCG_CHECK_CUDA(cudaGetLastError());
   return launch_ego_dense(p, b, ego_image, b->ego_list, s);
 }

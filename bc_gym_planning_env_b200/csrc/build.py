@@ -18,11 +18,11 @@ HEADERS = [os.path.join(HERE, "bcg_device.cuh"), os.path.join(HERE, "bcg_generat
 TARGET = os.path.join(HERE, "libbcg_b200.so")
 
 
-def nvcc_command(verbose=False):
+def nvcc_command(verbose=False, target=None, defines=()):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false",
            "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", HERE,
-           "-o", TARGET] + SOURCES
+           "-o", target or TARGET] + ["-D" + d for d in defines] + SOURCES
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     return cmd
@@ -45,6 +45,20 @@ def build(force=False, verbose=False):
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building %s" % TARGET)
     return TARGET
+
+
+def build_variant(name, defines, verbose=False):
+    """A tuning variant of the library (-D overrides of kernel shape macros) next to the product build:
+    csrc/variants/libbcg_b200_<name>.so; load it with BCG_B200_LIB=<path> (profiles/probes/*)."""
+    os.makedirs(os.path.join(HERE, "variants"), exist_ok=True)
+    target = os.path.join(HERE, "variants", "libbcg_b200_%s.so" % name)
+    cmd = nvcc_command(verbose, target, defines)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed building %s" % target)
+    return target
 
 
 if __name__ == "__main__":
