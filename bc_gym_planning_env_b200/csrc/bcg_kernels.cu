@@ -20,6 +20,16 @@
 #include "bcg_generate.cuh"
 
 using namespace bcg;
+// block sizes of the three state kernels (tunable: csrc/build.py build_variant)
+#ifndef BCG_KIN_THREADS
+#define BCG_KIN_THREADS 128
+#endif
+#ifndef BCG_COMMIT_THREADS
+#define BCG_COMMIT_THREADS 128
+#endif
+#ifndef BCG_CR_THREADS
+#define BCG_CR_THREADS 64
+#endif
 
 namespace {
 
@@ -76,7 +86,7 @@ int check_batch(const BcgParams* p, const BcgBatch* b) {
 // robot.step for every env: envs/base/env.py:371-373 (control delay) + robot model into b.cand, plus the
 // pixel / footprint-bin reference of the proposed pose for the collision kernel.  One thread per env:
 // every load and store is a coalesced SoA row access.
-__global__ void __launch_bounds__(128) kin_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L,
+__global__ void __launch_bounds__(BCG_KIN_THREADS) kin_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L,
                                                   const void* __restrict__ actions, const int action_is_f64,
                                                   const uint64_t step_index) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -151,7 +161,7 @@ __global__ void __launch_bounds__(128) pose_prep_kernel(const BcgParams p, const
 // reward of the pose the reward provider will see (reward.py:214-259).  Reads only; its few results go
 // to the scratch rows, the thread-per-env commit kernel applies them.  No store precedes a load, so all
 // of a warp's independent loads are in flight together.
-__global__ void __launch_bounds__(256, 5) collide_reward_kernel(const BcgParams p, const BcgBatch b) {
+__global__ void __launch_bounds__(BCG_CR_THREADS, 1280 / BCG_CR_THREADS) collide_reward_kernel(const BcgParams p, const BcgBatch b) {
   const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned lane = threadIdx.x & 31;
   if (e >= b.n_envs) return;
@@ -551,7 +561,7 @@ __device__ __forceinline__ void write_ego_record(const BcgParams& p, const BcgBa
 // One thread per env: the rest of _resolve_state_transition (env.py:363-398) -- rollback, pose and
 // robot-state delay lines, time/iter, sticky collision -- then done (env.py:407-419), episode statistics,
 // auto-reset (env.py:293-303) and the compact fp32 observation.  All accesses are coalesced SoA rows.
-__global__ void __launch_bounds__(128) commit_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L,
+__global__ void __launch_bounds__(BCG_COMMIT_THREADS) commit_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L,
                                                      const BcgStepOut out, const int ego_cap) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = e < b.n_envs;
@@ -1816,13 +1826,13 @@ int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, 
   cudaStream_t s = (cudaStream_t)stream;
   const BcgStateLayout L = make_layout(*p);
   if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[0], s));
-  kin_kernel<<<blocks_for(b->n_envs, 128), 128, 0, s>>>(*p, *b, L, actions, action_is_f64, step_index);
+  kin_kernel<<<blocks_for(b->n_envs, BCG_KIN_THREADS), BCG_KIN_THREADS, 0, s>>>(*p, *b, L, actions, action_is_f64, step_index);
   BCG_CHECK_CUDA(cudaGetLastError());
   if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[1], s));
-  collide_reward_kernel<<<blocks_for((int64_t)b->n_envs * 32, 256), 256, 0, s>>>(*p, *b);
+  collide_reward_kernel<<<blocks_for((int64_t)b->n_envs * 32, BCG_CR_THREADS), BCG_CR_THREADS, 0, s>>>(*p, *b);
   BCG_CHECK_CUDA(cudaGetLastError());
   if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[2], s));
-  commit_kernel<<<blocks_for(b->n_envs, 128), 128, 0, s>>>(*p, *b, L, *out, ego ? ego_capacity(*p, *b) : 0);
+  commit_kernel<<<blocks_for(b->n_envs, BCG_COMMIT_THREADS), BCG_COMMIT_THREADS, 0, s>>>(*p, *b, L, *out, ego ? ego_capacity(*p, *b) : 0);
   BCG_CHECK_CUDA(cudaGetLastError());
   if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[3], s));
   if (out->ego_image) {

@@ -1,4 +1,4 @@
-"""A/B of ego_sparse_kernel shapes on the bench workload (run on the GPU box):
+"""A/B of kernel shapes (ego_sparse_kernel CTA shape, block sizes of the state kernels) on the bench workload (run on the GPU box):
     python profiles/probes/egs_variants.py
 Builds nothing: the variants are csrc/variants/libbcg_b200_<name>.so made by csrc/build.py build_variant and are
 selected with BCG_B200_LIB."""
@@ -18,7 +18,9 @@ for lib in [None] + sorted(glob.glob(os.path.join(ROOT, "bc_gym_planning_env_b20
     name = os.path.basename(lib) if lib else "product build"
     try:
         d = json.loads(out.stdout.strip().splitlines()[-1])
-        print("%-32s ego_ms %.4f step_ms %.4f value %.4g dense-fallback envs %s" % (
-            name, d["kernels_ms"]["ego_sparse_kernel"], d["ms_per_step"], d["value"], d["ego_dense_fallback_envs_last_step"]), flush=True)
+        k = d["kernels_ms"]
+        print("%-32s kin %.4f collide %.4f commit %.4f ego %.4f step_ms %.4f value %.4g dense-fallback envs %s" % (
+            name, k["kin_kernel"], k["collide_reward_kernel"], k["commit_kernel"], k["ego_sparse_kernel"], d["ms_per_step"],
+            d["value"], d["ego_dense_fallback_envs_last_step"]), flush=True)
     except Exception:
         print(name, "failed", out.stderr[-600:], flush=True)
