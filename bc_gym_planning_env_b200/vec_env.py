@@ -403,6 +403,40 @@ class VecPlanEnv(object):
         self._step_index += 1
         return self.observation(), self.reward, self.done, {}
 
+    def step_host(self, actions_host):
+        """One env step driven from the host: `actions_host` float32 [N, 2] in pinned memory goes to the device, and
+        reward (fp64 [N]), done (uint8 [N]) and the compact observation (float32 [N, 12]: delayed pose, delayed
+        robot state, time, target index) come back in pinned host buffers -- what a CPU-side policy or logger needs
+        every step.  The device->host copies wait only for commit_kernel and run on a side stream while the
+        egocentric kernel is still working; the images stay in HBM (`ego_image`) for a GPU-resident consumer.
+        Returns (reward, done, obs_vec) host tensors, valid when this call returns (it synchronises)."""
+        if getattr(self, '_host_io', None) is None:
+            n = self.n_envs
+            self._host_io = dict(
+                actions=torch.empty((n, 2), dtype=torch.float32, device=self.device),
+                reward=torch.empty(n, dtype=torch.float64).pin_memory(),
+                done=torch.empty(n, dtype=torch.uint8).pin_memory(),
+                obs=torch.empty((n, 12), dtype=torch.float32).pin_memory(),
+                stream=torch.cuda.Stream(device=self.device),
+                events=[torch.cuda.Event(enable_timing=False) for _ in range(5)])
+            for ev in self._host_io['events']:
+                ev.record()                                   # creates the handles bcg_step_events records into
+        io = self._host_io
+        if tuple(actions_host.shape) != (self.n_envs, 2) or actions_host.dtype != torch.float32:
+            raise ValueError("actions_host must be a float32 tensor of shape (%d, 2)" % self.n_envs)
+        main = torch.cuda.current_stream(self.device)
+        io['actions'].copy_(actions_host, non_blocking=True)
+        self.step_timed(io['actions'], io['events'])
+        side = io['stream']
+        side.wait_event(io['events'][3])                      # recorded right after commit_kernel
+        with torch.cuda.stream(side):
+            io['reward'].copy_(self.reward, non_blocking=True)
+            io['done'].copy_(self._done_u8, non_blocking=True)
+            io['obs'].copy_(self.obs_vec, non_blocking=True)
+        side.synchronize()
+        main.synchronize()
+        return io['reward'], io['done'], io['obs']
+
     def reset(self, mask=None):
         """PlanEnv.reset for all envs (mask None) or those with mask[e] true."""
         m = None

@@ -459,22 +459,14 @@ def run_b200(args):
 
     # ---- e2e: host actions in, host results out, every step -----------------------------------------
     h_actions = [a.cpu().pin_memory() for a in actions]
-    d_actions = torch.empty((n, 2), dtype=torch.float32, device=device)
-    h_reward = torch.empty(n, dtype=torch.float64).pin_memory()
-    h_done = torch.empty(n, dtype=torch.uint8).pin_memory()
-    h_obs = torch.empty((n, 12), dtype=torch.float32).pin_memory()
     h2d = h_actions[0].numel() * 4
-    d2h = h_reward.numel() * 8 + h_done.numel() + h_obs.numel() * 4
+    d2h = n * 8 + n + n * 12 * 4
+    env.step_host(h_actions[0])                               # allocates the pinned buffers and the side stream
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(args.e2e_steps):
-        d_actions.copy_(h_actions[k % n_sets], non_blocking=True)
-        env.step(d_actions)
-        h_reward.copy_(env.reward, non_blocking=True)
-        h_done.copy_(env._done_u8, non_blocking=True)
-        h_obs.copy_(env.obs_vec, non_blocking=True)
-        torch.cuda.current_stream().synchronize()          # the caller needs the result before acting again
+        env.step_host(h_actions[k % n_sets])                  # synchronises: the caller acts on the result
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
@@ -492,7 +484,8 @@ def run_b200(args):
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, n),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "note": "pinned-host actions in; reward f64, done u8 and the 12-float compact observation out; "
+                    "note": "VecPlanEnv.step_host: pinned-host actions in; reward f64, done u8 and the 12-float compact "
+                            "observation out to pinned host memory every step (copies overlap the egocentric kernel); "
                             "egocentric images stay in HBM for a GPU-resident policy"},
             "gpu_launches": args.steps * (3 if args.no_ego else (5 if sparse else 4)) * world,
             "ego_dense_fallback_envs_last_step": None if args.no_ego else dense_envs,

@@ -104,3 +104,21 @@ def test_auto_reset_and_episode_statistics():
     assert stats["length"] >= stats["episodes"]
     env.episode_stats(reset=True)
     assert float(env.episode_stats().abs().sum()) == 0.0
+
+
+def test_step_host_returns_the_step_results_in_pinned_memory():
+    """VecPlanEnv.step_host == step + copies: same rewards, dones and compact observation, images still in HBM."""
+    d = common.load("aisle_delays_211")
+    a = common.make_vec_env(d, with_ego=True)
+    b = common.make_vec_env(d, with_ego=True)
+    actions = torch.from_numpy(d["actions"])                     # [E, T, 2] float32, host
+    for t in range(40):
+        host = actions[:, t].contiguous().pin_memory()
+        reward, done, obs = a.step_host(host)
+        assert reward.is_pinned() and done.is_pinned() and obs.is_pinned()
+        _, r2, d2, _ = b.step(host.cuda())
+        assert torch.equal(reward, r2.cpu()) and torch.equal(done.bool(), d2.cpu())
+        assert torch.equal(obs, b.obs_vec.cpu())
+        assert torch.equal(a.ego_image, b.ego_image)
+    with pytest.raises(ValueError):
+        a.step_host(actions[:, 0].double())
