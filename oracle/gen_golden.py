@@ -308,6 +308,27 @@ def gen_aisle_worlds(name, n_envs):
     print(name, out["turn_params"].shape, [out["costmap_%d" % s].shape for s in range(n_envs)])
 
 
+def gen_t_junction(name):
+    """Worlds of the reference's TJunction (envs/t_junction_env.py): costmaps and the six static paths."""
+    from bc_gym_planning_env.envs.t_junction_env import TJunction
+    cases = [dict(), dict(window_height=8.0, window_width=12.5, column_width=2.1, beam_width=1.3),
+             dict(window_height=6.2, window_width=5.0, column_width=1.7, beam_width=2.9, start_noise_scale=0.1)]
+    out = {"n_cases": np.int64(len(cases)), "cases": np.array(json.dumps(cases))}
+    for i, kw in enumerate(cases):
+        tj = TJunction(**kw)
+        cm = tj.get_costmap(0.03)
+        out["costmap_%d" % i] = cm.get_data().copy()
+        out["origin_%d" % i] = np.array(cm.get_origin())
+        out["corners_%d" % i] = np.array(tj.wall_corners)
+        for a in ("left", "right", "bottom"):
+            for b in ("left", "right", "bottom"):
+                if a != b:
+                    np.random.seed(12 + i)
+                    out["path_%d_%s_%s" % (i, a, b)] = tj.get_path(a, b)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, [out["costmap_%d" % i].shape for i in range(len(cases))])
+
+
 def main():
     _ref()
     os.makedirs(OUT, exist_ok=True)
@@ -330,6 +351,7 @@ def main():
     gen_kat_collision("kat_is_robot_colliding")
     gen_diffdrive("diffdrive_steps", 6, 250)
     gen_aisle_worlds("aisle_worlds", 16)
+    gen_t_junction("t_junction")
 
 
 if __name__ == "__main__":
