@@ -84,7 +84,7 @@ class VecPlanEnv(object):
     def __init__(self, costmaps, paths, params=None, n_envs=None, map_ids=None, path_ids=None,
                  noise_parameters=DEFAULT_NOISE, seed=0, auto_reset=False, device=None, env_id_base=0,
                  private_map_copies=False, with_ego=False, footprint_scale=1.0, use_tma=True, footprint=None,
-                 ego_staging='tiles'):
+                 ego_staging='tiles', ego_sparse=True):
         """
         :param costmaps: pool of CostMap2D (uint8), one resolution
         :param paths: pool of oriented paths, array(n, 3); refined here when params.refine_path
@@ -98,12 +98,15 @@ class VecPlanEnv(object):
         :param ego_staging: how the egocentric kernel stages its source window: 'tiles' (default; a derived
             copy of every costmap in 128-byte cell tiles, only the tiles the rotated window touches are read),
             'tma' (box loads of the window's bounding box from the uint8 rows) or 'spans' (plain loads)
+        :param ego_sparse: with 'tiles' staging, render crops with the sparse scatter kernel (occupancy plane; the dense
+            cell-tile kernel only takes the envs it hands over).  False: the dense kernel renders every env
         """
         costmaps = list(costmaps)
         paths = list(paths)
         if not costmaps or not paths:
             raise ValueError("need at least one costmap and one path")
         n = int(n_envs if n_envs is not None else max(len(costmaps), len(paths)))
+        self._ego_sparse = bool(ego_sparse)
         self._configure(params, n, float(costmaps[0].get_resolution()), noise_parameters, seed, auto_reset, device,
                         env_id_base, with_ego, ego_staging if use_tma else 'spans')   # use_tma=False: older spelling
         self._map_pool = costmaps
@@ -241,6 +244,7 @@ class VecPlanEnv(object):
         self.cell_tile_arena = self.occ_tile_arena = None
         if self.ego_staging == 'tiles':
             self.cell_tile_arena = torch.empty(max(pool_ctile_bytes, 128), dtype=torch.uint8, device=self.device)
+        if self.ego_staging == 'tiles' and getattr(self, '_ego_sparse', True):
             # occupancy plane (cell != 0) for the sparse egocentric kernel: same layout as the lethal plane
             self.occ_tile_arena = torch.zeros(max(pool_words, 1), dtype=torch.int32, device=self.device)
         if self.ego_staging == 'tma':

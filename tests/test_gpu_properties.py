@@ -70,3 +70,33 @@ def test_full_size_rollout_properties(big):
         env.step(a)
     assert torch.equal(env.get_state().f, first.f) and torch.equal(env.get_state().i, first.i)
     assert float(torch.stack(rewards).sum()) > 0
+
+
+def test_sparse_and_dense_egocentric_kernels_agree_at_full_size(big):
+    """The scatter kernel (occupancy plane) and the dense gather kernel (cell tiles) render the same 65 536 crops."""
+    env, actions, costmaps, paths = big
+    dense = VecPlanEnv(costmaps, paths, env.params, n_envs=N, noise_parameters=None, with_ego=True, ego_sparse=False)
+    assert dense.occ_tile_arena is None and env.occ_tile_arena is not None
+    env.reset()
+    for a in actions[:12]:
+        env.step(a)
+        dense.step(a)
+    assert torch.equal(env.state_f, dense.state_f)
+    assert torch.equal(env.ego_image, dense.ego_image)
+    assert int((env.ego_image != 0).sum()) > 1000 * 100         # walls are in view
+    assert int(env._ego_list[N]) == 0                            # aisle windows never overflow the cell list
+    # arbitrary poses, many of them straddling the map edge or outside it
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(5)
+    jitter = torch.rand((3, N), generator=gen, device="cuda", dtype=torch.float64)
+    poses = env.state_f[nat.F_DPOSE:nat.F_DPOSE + 3].clone()
+    poses[0] += (jitter[0] - 0.5) * 30.0
+    poses[1] += (jitter[1] - 0.5) * 30.0
+    poses[2] = (jitter[2] - 0.5) * 2 * np.pi
+    for e in (env, dense):
+        e.state_f[nat.F_DPOSE:nat.F_DPOSE + 3] = poses
+    a, _ = env.observe_ego()
+    b, _ = dense.observe_ego()
+    assert torch.equal(a, b)
+    env.check_status()
+    dense.check_status()
