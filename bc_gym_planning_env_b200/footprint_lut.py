@@ -130,6 +130,20 @@ class FootprintLut(object):
         bits = (self.rows[k, :h, :, None] >> np.arange(64, dtype=np.uint64)) & np.uint64(1)
         return bits.reshape(h, -1)[:, :w].astype(bool), x0, y0
 
+    def canvas(self, angle):
+        """The reference's own return format (utilities/path_tools.py:122-162, fill=True): uint8 image
+        (2 hy + 1, 2 hx + 1) with the footprint in 255 about the centre pixel, half sizes = ceil of the largest
+        rotated coordinate.  Array-for-array equal to get_pixel_footprint (reference test_path_tools.py:453-462)."""
+        c, s = np.cos(angle), np.sin(angle)
+        m = np.array([[c, -s], [s, c]], dtype=np.float64).reshape(2, 2, 1)
+        rot = np.dot(self.fp_pix, m)[:, :, 0]
+        half = np.ceil(np.maximum(rot.max(axis=0), -rot.min(axis=0))).astype(np.int32)
+        mask, x0, y0 = self.mask(self.bin_of(angle))
+        out = np.zeros((2 * half[1] + 1, 2 * half[0] + 1), dtype=np.uint8)
+        h, w = mask.shape
+        out[y0 + half[1]:y0 + half[1] + h, x0 + half[0]:x0 + half[0] + w] = mask.astype(np.uint8) * 255
+        return out
+
     def arrays(self):
         return dict(edges=self.edges, verts=self.verts, header=self.header, rows=self.rows,
                     fp_pix=self.fp_pix.reshape(-1), bucket_first=self.bucket_first)

@@ -45,3 +45,13 @@ def test_bin_edges_sit_where_a_rounded_vertex_flips():
         below = rounded_vertices(lut.edges[k] - 1e-9, lut.fp_pix)
         above = rounded_vertices(lut.edges[k] + 1e-9, lut.fp_pix)
         assert not np.array_equal(below, above)
+
+
+def test_canvas_equals_the_reference_return_format():
+    """FootprintLut.canvas == get_pixel_footprint's array (the native-vs-Python equality of reference test_path_tools.py:453-462)."""
+    rng = np.random.RandomState(4)
+    for footprint, res in ((O.TRICYCLE_FOOTPRINT, 0.03), (RECT, 0.05), (O.DIFFDRIVE_FOOTPRINT, 0.03)):
+        lut = FootprintLut(footprint, res)
+        for a in np.concatenate([rng.uniform(-np.pi, np.pi, 120), [0., np.pi / 2, -np.pi, 7.3]]):
+            got, want = lut.canvas(a), O.pixel_footprint(a, footprint, res)
+            assert got.dtype == np.uint8 and got.shape == want.shape and np.array_equal(got, want), a
