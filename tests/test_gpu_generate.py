@@ -167,3 +167,44 @@ def test_reset_storm_draws_new_worlds_for_done_envs_only():
     assert np.array_equal(env.costmap(e).get_data(), costmap)
     np.testing.assert_allclose(path, O.refine_path(coarse, 0.05), rtol=0, atol=1e-9)
     env.check_status()
+
+
+def test_other_resolution_and_footprint_scale_step_parity():
+    """Nothing in the kernels is specialised to 0.03 m cells or the 117 x 133 crop: a 0.05 m world (70 x 80 crop)."""
+    from bc_gym_planning_env_b200.utilities.costmap_2d import CostMap2D
+    from bc_gym_planning_env_b200.vec_env import VecPlanEnv
+    res = 0.05
+    rng = np.random.RandomState(8)
+    worlds = []
+    for _ in range(6):
+        coarse, costmap, origin = A.aisle_world(A.draw_turn_params(rng), res)
+        worlds.append((CostMap2D(costmap, res, origin), coarse))
+    ep = EnvParams(control_delay=1, pose_delay=1, state_delay=0)
+    env = VecPlanEnv([c for c, _ in worlds], [p for _, p in worlds], ep, noise_parameters=None, with_ego=True)
+    assert tuple(env.ego_image.shape[1:]) == (80, 70, 1)
+    oracles = [O.OraclePlanEnv(c.get_data(), c.get_origin(), res, p, delays=(1, 1, 0)) for c, p in worlds]
+    low, high = env.action_bounds()
+    for t in range(100):
+        a = rng.uniform(low, high, size=(env.n_envs, 2)).astype(np.float32)
+        obs, r, done, _ = env.step(a)
+        pose, rew, dn = obs.pose.cpu().numpy(), r.cpu().numpy(), done.cpu().numpy()
+        for e, o in enumerate(oracles):
+            oo, r2, d2, _ = o.step(a[e])
+            np.testing.assert_allclose(pose[e], oo["pose"], rtol=0, atol=1e-9)
+            assert rew[e] == r2 and bool(dn[e]) == d2, (t, e)
+        if t % 10 == 9:
+            img = env.ego_image.cpu().numpy()[..., 0]
+            for e, o in enumerate(oracles):
+                assert np.array_equal(img[e], O.ego_costmap(o.costmap, o.pose, o.origin, res)), (t, e)
+    env.check_status()
+
+
+def test_device_worlds_at_another_resolution():
+    n, seed = 12, 77
+    env = VecRandomAisleTurnEnv(n, EnvParams(), seed=seed, noise_parameters=None, resolution=0.05)
+    for e in range(n):
+        coarse, costmap, origin = A.aisle_world(A.philox_turn_params(seed, e, 0), 0.05)
+        path = O.refine_path(coarse, 0.05)
+        target, min_dist = O.initial_reward_state(path, 1.0, np.pi / 2)
+        _check_world(env, e, costmap, origin, path, target, min_dist)
+    env.check_status()
