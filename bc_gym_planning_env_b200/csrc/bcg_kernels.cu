@@ -508,41 +508,53 @@ __device__ __forceinline__ void write_ego_tile_record(const BcgParams& p, const 
 #pragma unroll
   for (int k = 0; k < 8; ++k) dst[k] = src[k];
   if (w.mode == BCG_EGO_MODE_TILES) {
-    // x-extent of the crop rectangle within each row of tiles: clip its four edges against the band (no division
-    // in the loop: one inverse slope per edge)
+    // x-extent of the crop rectangle within each row of tiles.  The rectangle is convex, so over a band of rows its
+    // left boundary is the maximum of the lines through its left edges (a convex function of y: smallest at a band end
+    // or at the leftmost vertex) and its right boundary the minimum of the lines through its right edges.  Two line
+    // evaluations per edge and band, one inverse slope per edge, no clipping.
     const int ttx0 = w.X0 >> 4;
-    double inv[4];
+    const bool ccw = (qx[1] - qx[0]) * (qy[3] - qy[0]) - (qy[1] - qy[0]) * (qx[3] - qx[0]) > 0.0;
+    double inv[4], lsel[4], rsel[4];     // a line counts for the left (right) boundary where lsel (rsel) is 0, else +-BIG
+    double y_at_xlo = qy[0], y_at_xhi = qy[0];
+    const double BIG = 1e300;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const double dy = qy[(k + 1) & 3] - qy[k];
       inv[k] = dy != 0.0 ? (qx[(k + 1) & 3] - qx[k]) / dy : 0.0;
+      const bool is_left = ccw ? dy < 0.0 : dy > 0.0, is_right = ccw ? dy > 0.0 : dy < 0.0;   // horizontal edges: neither
+      lsel[k] = is_left ? 0.0 : -BIG;
+      rsel[k] = is_right ? 0.0 : BIG;
+      if (qx[k] == xlo) y_at_xlo = qy[k];
+      if (qx[k] == xhi) y_at_xhi = qy[k];
     }
-    for (int t = 0; t < w.nty; ++t) {
-      const double blo = (double)(w.Y0 + 8 * t) - 0.51, bhi = (double)(w.Y0 + 8 * t + 7) + 0.51;
-      double xmin = 1e300, xmax = -1e300;
+    for (int t8 = 0; t8 < w.nty; t8 += 8) {     // eight spans per 16-byte store
+      uint32_t packed[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const double xa = qx[k], ya = qy[k], xb = qx[(k + 1) & 3], yb = qy[(k + 1) & 3];
-        const double lo = fmax(blo, fmin(ya, yb)), hi = fmin(bhi, fmax(ya, yb));
-        if (lo <= hi) {
-          double x0, x1;
-          if (ya == yb) {
-            x0 = xa;
-            x1 = xb;
-          } else {               // clamp: the clipped points lie on the edge, rounding must not push them past its ends
-            x0 = fmin(fmax(xa + (lo - ya) * inv[k], fmin(xa, xb)), fmax(xa, xb));
-            x1 = fmin(fmax(xa + (hi - ya) * inv[k], fmin(xa, xb)), fmax(xa, xb));
+      for (int j = 0; j < 8; ++j) {
+        const int t = t8 + j;
+        const double y0 = fmax((double)(w.Y0 + 8 * t) - 0.51, ylo), y1 = fmin((double)(w.Y0 + 8 * t + 7) + 0.51, yhi);
+        int ts = 1, te = 0;
+        if (t < w.nty && y0 <= y1) {
+          double l0 = -BIG, l1 = -BIG, r0 = BIG, r1 = BIG;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const double v0 = qx[k] + (y0 - qy[k]) * inv[k], v1 = qx[k] + (y1 - qy[k]) * inv[k];
+            l0 = fmax(l0, lsel[k] != 0.0 ? lsel[k] : v0);
+            l1 = fmax(l1, lsel[k] != 0.0 ? lsel[k] : v1);
+            r0 = fmin(r0, rsel[k] != 0.0 ? rsel[k] : v0);
+            r1 = fmin(r1, rsel[k] != 0.0 ? rsel[k] : v1);
           }
-          xmin = fmin(xmin, fmin(x0, x1));
-          xmax = fmax(xmax, fmax(x0, x1));
+          double xmin = fmin(l0, l1), xmax = fmax(r0, r1);
+          if (y_at_xlo >= y0 && y_at_xlo <= y1) xmin = xlo;
+          if (y_at_xhi >= y0 && y_at_xhi <= y1) xmax = xhi;
+          xmin = fmax(xmin, xlo);                 // rounding of nearly horizontal edges must not leave the rectangle
+          xmax = fmin(xmax, xhi);
+          ts = max(((int)floor(xmin - 0.51) >> 4) - ttx0, 0);
+          te = min(((int)ceil(xmax + 0.51) >> 4) - ttx0, w.ntx - 1);
         }
+        packed[j >> 1] |= (uint32_t)(ts | (te << 8)) << (16 * (j & 1));
       }
-      int ts = 1, te = 0;
-      if (xmin <= xmax) {
-        ts = max(((int)floor(xmin - 0.51) >> 4) - ttx0, 0);
-        te = min(((int)ceil(xmax + 0.51) >> 4) - ttx0, w.ntx - 1);
-      }
-      *reinterpret_cast<uint16_t*>(rec->span[t]) = (uint16_t)(ts | (te << 8));
+      *reinterpret_cast<uint4*>(rec->span[t8]) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
     }
   }
 }
