@@ -389,9 +389,11 @@ def run_b200(args):
 
     def roof(kernel, alg_bytes, ms, note):
         ach = alg_bytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        tr = traffic.get(kernel.split(" ")[0])
+        phys = tr / (ms * 1e-3) / 1e9 if (tr and ms > 0) else None      # DRAM bytes ncu counted / launch time measured here
         return {"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic.get(kernel.split(" ")[0]), "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms,
-                "peak_source": peak_src, "note": note}
+                "traffic": tr, "traffic_gbs": phys, "traffic_frac": None if phys is None else phys / peak,
+                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms, "peak_source": peak_src, "note": note}
 
     roof_commit = roof("collide_reward_kernel", coll_bytes + scan_bytes, cr_ms,
                        "algorithmic bytes (SURVEY 8d) = in-map footprint pixels x 1 B (uint8 definition; the kernel reads "
@@ -403,8 +405,8 @@ def run_b200(args):
     roof_ego = roof(ego_name, ego_bytes, ego_ms,
                     "algorithmic bytes = 2 x ego_w x ego_h per env (SURVEY 8d: source read + image write).  " +
                     ("The sparse kernel reads the 1-bit occupancy plane of the window instead of its bytes and scatters only "
-                     "occupied cells, so its physical DRAM traffic (`traffic`) is below the algorithmic bytes; the image "
-                     "write alone is %.2f GB per launch.  ms_per_launch covers ego_sparse_kernel plus the dense "
+                     "occupied cells, so its physical DRAM traffic (`traffic`, `traffic_frac` of the peak) is below the "
+                     "algorithmic bytes and `frac` can exceed 1; the image write alone is %.2f GB per launch.  ms_per_launch covers ego_sparse_kernel plus the dense "
                      "ego_tiles_kernel launch for the %d envs it handed over in the last step." % (ego_bytes / 2e9, dense_envs)
                      if sparse else "staging: " + env.ego_staging))
     dominant = roof_ego if (not args.no_ego and ego_ms >= cr_ms) else roof_commit
