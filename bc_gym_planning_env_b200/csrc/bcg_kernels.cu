@@ -1444,18 +1444,10 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
           bits[k] &= keep;
           cnt += __popc(bits[k]);
         }
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int up = __shfl_up_sync(BCG_FULL, incl, o);
-          if (lane >= o) incl += up;
-        }
-        uint32_t base = 0;
-        if (lane == 31 && incl > 0) base = atomicAdd(&T.count[par], (uint32_t)incl);
-        base = __shfl_sync(BCG_FULL, base, 31);
-        const uint32_t total = __shfl_sync(BCG_FULL, (uint32_t)incl, 31);
-        if (base + total > BCG_EGS_LIST) continue;               // overflow: the env goes to the dense kernel anyway
-        uint32_t at = list_u32 + 4u * (base + (uint32_t)(incl - cnt));
+        if (cnt == 0) continue;                                  // walls are thin: a few lanes per round hold cells,
+        const uint32_t base = atomicAdd(&T.count[par], (uint32_t)cnt);   // so each reserves its own list slots
+        if (base + (uint32_t)cnt > BCG_EGS_LIST) continue;       // overflow: the env goes to the dense kernel anyway
+        uint32_t at = list_u32 + 4u * base;
         const int key = (yr0 << 16) + ((tx << 5) - X0);          // x_rel of bit 0 may be negative, of a kept bit never
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
