@@ -86,6 +86,17 @@ class BcgAisleSlots(C.Structure):
     ]
 
 
+class BcgMiniGenParams(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("inner_h", "inner_w", "mid_margin", "out_margin", "min_obstacle_angle",
+                                          "max_obstacle_angle", "lim_euc_dist", "lim_ang_dist", "angular_pose_noise_scale",
+                                          "goal_spat_dist", "goal_ang_dist")]
+
+
+class BcgMiniParams(C.Structure):
+    _fields_ = [("h", C.c_double), ("w", C.c_double), ("start", C.c_double * 3), ("end", C.c_double * 3),
+                ("a", C.c_double * 2), ("o", C.c_double * 2), ("b", C.c_double * 2)]
+
+
 class BcgStateLayout(C.Structure):
     _fields_ = [
         ("n_frows", C.c_int32), ("n_irows", C.c_int32),
@@ -101,12 +112,12 @@ class BcgStepOut(C.Structure):
 
 
 _STRUCTS = [BcgParams, BcgMapDesc, BcgPathDesc, BcgFootprintLut, BcgBatch, BcgStateLayout, BcgStepOut, BcgTurnParams,
-            BcgAisleSlots]
+            BcgAisleSlots, BcgMiniGenParams, BcgMiniParams]
 
 # fixed rows / words of include/bcg_b200.h
 F_ROBOT, F_DROBOT, F_DPOSE, F_TIME, F_MIN_DIST, F_EP_RETURN, F_FIXED = 0, 7, 14, 17, 18, 19, 20
 I_ITER, I_TARGET, I_COLLIDED, I_QC, I_QP, I_QS, I_FIXED = 0, 1, 2, 3, 4, 5, 6
-STATUS_LUT_MISS, STATUS_PATH_EXHAUSTED, STATUS_SLOT_OVERFLOW, STATUS_WORDS = 0, 1, 2, 8
+STATUS_LUT_MISS, STATUS_PATH_EXHAUSTED, STATUS_SLOT_OVERFLOW, STATUS_SAMPLER_EMPTY, STATUS_WORDS = 0, 1, 2, 3, 8
 STAT_NAMES = ("episodes", "return", "length", "collided", "goal", "timeout")
 STATS_WORDS = 8
 ROBOT_TRICYCLE, ROBOT_DIFFDRIVE = 0, 1
@@ -128,6 +139,8 @@ SYMBOLS = {
     "bcg_init_state": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgBatch), _P]),
     "bcg_generate_aisles": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgBatch), C.POINTER(BcgAisleSlots), _P, _P, C.c_uint64,
                                       C.c_double, _P]),
+    "bcg_generate_minis": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgBatch), C.POINTER(BcgAisleSlots), _P,
+                                     C.POINTER(BcgMiniGenParams), _P, _P, C.c_uint64, C.c_double, _P]),
     "bcg_reset_where": (C.c_int, [C.POINTER(BcgBatch), _P, _P]),
     "bcg_step": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgBatch), _P, C.c_int32, C.c_uint64,
                            C.POINTER(BcgStepOut), _P]),

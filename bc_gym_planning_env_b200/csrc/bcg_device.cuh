@@ -329,7 +329,9 @@ __device__ __forceinline__ uint32_t mask_window32(uint64_t mk, int rel) {
 // footprint row (two passes cover the <= 64 rows), loads the row's mask once and walks the <= 3 tiles
 // the row crosses; 16 consecutive rows of a tile are one coalesced 64-byte read.  Returns the
 // warp-uniform verdict.  If COUNT, *pixels gets the number of in-map footprint pixels.
-template <bool COUNT>
+// COHERENT: read the tile words around L1 (ld.global.cg) -- for callers that changed the plane earlier in the SAME
+// kernel (the mini-env generator); everyone else reads through the non-coherent path.
+template <bool COUNT, bool COHERENT = false>
 __device__ __forceinline__ bool collide_tiles(const BcgBatch& b, const WorkCollide& f, unsigned lane, int* pixels) {
   const int X0 = f.X0, Y0 = f.Y0;
   const int X1 = X0 + f.fwidth - 1;
@@ -348,7 +350,7 @@ __device__ __forceinline__ bool collide_tiles(const BcgBatch& b, const WorkColli
       const uint64_t* mrow = rows + (int64_t)dy * wpr;
       const uint64_t mk = __ldg(mrow);
       for (int tx = tx0; tx <= tx1; ++tx) {
-        const uint32_t word = __ldg(trow + (tx << 4));
+        const uint32_t word = COHERENT ? __ldcg(trow + (tx << 4)) : __ldg(trow + (tx << 4));
         const int rel = (tx << 5) - X0;
         const uint32_t mbits = (wpr == 1) ? mask_window32(mk, rel) : mask_bits32(mrow, wpr, rel);
         hit |= word & mbits;

@@ -186,4 +186,144 @@ __device__ __forceinline__ void refined_point(const double way[4][3], const Refi
   y = (double)k * sy + way[i][1];
 }
 
+// ---- RandomMiniEnv (envs/mini_env.py) -------------------------------------------------------------------------------
+
+// cv::clipLine(Size(w, h), pt1, pt2) (OpenCV imgproc drawing.cpp): the part of the segment inside the image, computed in
+// integers with truncation exactly like cv2.line does before it walks the pixels; false when nothing is inside
+__device__ __forceinline__ bool clip_line(int w, int h, long long& x1, long long& y1, long long& x2, long long& y2) {
+  const long long right = w - 1, bottom = h - 1;
+  if (w <= 0 || h <= 0) return false;
+  int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
+  int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
+  if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+    long long a;
+    if (c1 & 12) {
+      a = c1 < 8 ? 0 : bottom;
+      x1 += (long long)((double)(a - y1) * (double)(x2 - x1) / (double)(y2 - y1));
+      y1 = a;
+      c1 = (x1 < 0) + (x1 > right) * 2;
+    }
+    if (c2 & 12) {
+      a = c2 < 8 ? 0 : bottom;
+      x2 += (long long)((double)(a - y2) * (double)(x2 - x1) / (double)(y2 - y1));
+      y2 = a;
+      c2 = (x2 < 0) + (x2 > right) * 2;
+    }
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+      if (c1) {
+        a = c1 == 1 ? 0 : right;
+        y1 += (long long)((double)(a - x1) * (double)(y2 - y1) / (double)(x2 - x1));
+        x1 = a;
+        c1 = 0;
+      }
+      if (c2) {
+        a = c2 == 1 ? 0 : right;
+        y2 += (long long)((double)(a - x2) * (double)(y2 - y1) / (double)(x2 - x1));
+        x2 = a;
+        c2 = 0;
+      }
+    }
+  }
+  return (c1 | c2) == 0;
+}
+
+// cv2.line with end points anywhere: clip, then walk (the walker swaps to left-to-right itself)
+__device__ __forceinline__ void draw_wall_clipped(const MapLayout& m, int width, int height, int x0, int y0, int x1, int y1,
+                                                  uint8_t value, int first, int stride) {
+  long long a0 = x0, b0 = y0, a1 = x1, b1 = y1;
+  if (!clip_line(width, height, a0, b0, a1, b1)) return;
+  draw_wall(m, (int)a0, (int)b0, (int)a1, (int)b1, value, first, stride);
+}
+
+// the k-th uniform of (seed; env, draw): as philox_uniform, in a stream of its own ('MINI')
+struct MiniRng {
+  uint64_t seed, env, draw;
+  uint32_t k;
+  __device__ __forceinline__ double u01() {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)env, (uint32_t)draw, 0x4d494e49u + (k >> 1), (uint32_t)(draw >> 32)),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint64_t bits = (k & 1) ? (((uint64_t)r.z << 21) | (r.w >> 11)) : (((uint64_t)r.x << 21) | (r.y >> 11));
+    ++k;
+    return (double)bits * 0x1.0p-53;
+  }
+  __device__ __forceinline__ double uniform(double a, double b) { return a + (b - a) * u01(); }
+};
+
+// not_inside_obstacle (envs/mini_env.py:198-208): the bearing of the point seen from the corner is outside the wedge
+__device__ __forceinline__ bool mini_outside_obstacle(double x, double y, double ox, double oy, double start_angle, double angle) {
+  const double phi = wrap_angle(atan2(y - oy, x - ox));
+  if (phi >= start_angle && phi <= start_angle + angle) return false;
+  if (phi + BCG_TWO_PI >= start_angle && phi + BCG_TWO_PI <= start_angle + angle) return false;
+  return true;
+}
+
+// _sample_mini_env_params_no_final_check (envs/mini_env.py:269-320), same draw order.  Returns 1 = drawn, 0 = the
+// circle method ran out of tries (SpaceSeemsEmptyError: the caller draws again), -1 = the square method did (ValueError)
+__device__ __noinline__ int draw_mini_params(MiniRng& rng, const BcgMiniGenParams& g, BcgMiniParams& out) {
+  const double ox = rng.uniform(-g.inner_w / 2, g.inner_w / 2), oy = rng.uniform(-g.inner_h / 2, g.inner_h / 2);
+  const double start_angle = rng.uniform(0, BCG_TWO_PI);
+  const double angle = rng.uniform(g.min_obstacle_angle, g.max_obstacle_angle);
+  const double r = 3 * (g.inner_h + g.inner_w + g.mid_margin + g.out_margin);
+  double sn, cs;
+  sincos(start_angle, &sn, &cs);
+  out.a[0] = r * cs + ox;
+  out.a[1] = r * sn + oy;
+  sincos(start_angle + angle, &sn, &cs);
+  out.b[0] = r * cs + ox;
+  out.b[1] = r * sn + oy;
+  out.o[0] = ox;
+  out.o[1] = oy;
+  out.h = g.inner_h + 2 * g.mid_margin + 2 * g.out_margin;
+  out.w = g.inner_w + 2 * g.mid_margin + 2 * g.out_margin;
+  double sx = 0, sy = 0, ex = 0, ey = 0, theta = 0;
+  if (rng.u01() < 0.7) {
+    // circle method (:141-178): two opposite points of a circle, heading along the chord
+    bool found = false;
+    for (int t = 0; t < 1000 && !found; ++t) {
+      const double rc = fmin((g.inner_w + g.inner_h) / 4. + g.mid_margin, g.lim_euc_dist);
+      const double phi = rng.uniform(0, BCG_TWO_PI);
+      sincos(phi, &sn, &cs);
+      const double x = rc * cs, y = rc * sn;
+      rng.uniform(0, BCG_TWO_PI);                                    // a heading the reference draws and discards
+      if (mini_outside_obstacle(x, y, ox, oy, start_angle, angle) && mini_outside_obstacle(-x, -y, ox, oy, start_angle, angle)) {
+        sx = x; sy = y; ex = -x; ey = -y;
+        theta = wrap_angle(atan2(-y - y, -x - x));
+        found = true;
+      }
+    }
+    if (!found) return 0;
+  } else {
+    // square method (:181-240): two poses of the middle square, the second not too far in heading / distance
+    const double lx = g.inner_w / 2 + g.mid_margin, ly = g.inner_h / 2 + g.mid_margin;
+    double st = 0;
+    bool found = false;
+    for (int t = 0; t < 1000 && !found; ++t) {
+      const double x = rng.uniform(-lx, lx), y = rng.uniform(-ly, ly);
+      const double th = wrap_angle(rng.uniform(0, BCG_TWO_PI));
+      if (mini_outside_obstacle(x, y, ox, oy, start_angle, angle)) {
+        sx = x; sy = y; st = th;
+        found = true;
+      }
+    }
+    if (!found) return -1;
+    found = false;
+    for (int t = 0; t < 1000 && !found; ++t) {
+      const double x = rng.uniform(-lx, lx), y = rng.uniform(-ly, ly);
+      const double th = wrap_angle(rng.uniform(0, BCG_TWO_PI));
+      if (mini_outside_obstacle(x, y, ox, oy, start_angle, angle) && py_mod(st - th, BCG_TWO_PI) < g.lim_ang_dist &&
+          sqrt((sx - x) * (sx - x) + (sy - y) * (sy - y)) < g.lim_euc_dist) {
+        ex = x; ey = y;
+        found = true;
+      }
+    }
+    if (!found) return -1;
+    theta = wrap_angle(atan2(ey - sy, ex - sx));
+  }
+  const double n1 = rng.uniform(-g.angular_pose_noise_scale / 2.0, g.angular_pose_noise_scale / 2.0);
+  out.start[0] = sx; out.start[1] = sy; out.start[2] = wrap_angle(theta + n1);
+  const double n2 = rng.uniform(-g.angular_pose_noise_scale / 2.0, g.angular_pose_noise_scale / 2.0);
+  out.end[0] = ex; out.end[1] = ey; out.end[2] = wrap_angle(theta + n2);
+  return 1;
+}
+
 }  // namespace bcg

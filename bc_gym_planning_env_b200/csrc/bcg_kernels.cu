@@ -845,6 +845,166 @@ __global__ void __launch_bounds__(256) generate_aisles_kernel(const BcgParams p,
   }
 }
 
+// bcg_generate_minis: one CTA per env.  Thread 0 samples (the draw count depends on the data), the CTA rasterises the
+// two walls, warp 0 checks the two end poses against them; accepted parameters get their path and initial state.
+__global__ void __launch_bounds__(128) generate_minis_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L,
+                                                             const BcgAisleSlots slots, const uint8_t* __restrict__ mask,
+                                                             const BcgMiniGenParams g, const BcgMiniParams* __restrict__ explicit_params,
+                                                             BcgMiniParams* __restrict__ params_out, const uint64_t draw_index,
+                                                             const double path_delta) {
+  const int e = blockIdx.x;
+  if (mask && !mask[e]) return;
+  const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31;
+  __shared__ BcgMiniParams mp_s;
+  __shared__ int verdict_s;          // 1 drawn / accepted, 0 draw again, -1 give up
+  BcgMapDesc* md = const_cast<BcgMapDesc*>(b.maps) + e;
+  BcgPathDesc* pdsc = const_cast<BcgPathDesc*>(b.paths) + e;
+  AisleGenState* gs = reinterpret_cast<AisleGenState*>(slots.gen_state) + e;
+  MapLayout m;
+  m.data = const_cast<uint8_t*>(b.map_arena) + md->data_off;
+  m.tiles = const_cast<uint32_t*>(b.tile_arena) + md->tile_off;
+  m.occ = b.occ_tile_arena ? const_cast<uint32_t*>(b.occ_tile_arena) + md->tile_off : nullptr;
+  m.ctiles = const_cast<uint8_t*>(b.cell_tile_arena) + md->cell_tile_off;
+  MiniRng rng = {p.seed, p.env_id_base + (uint64_t)e, draw_index, 0u};
+  bool accepted = false;
+  for (int attempt = 0; attempt < 1000 && !accepted; ++attempt) {
+    if (tid == 0) {
+      int rc = 1;
+      if (explicit_params) mp_s = explicit_params[e];
+      else rc = draw_mini_params(rng, g, mp_s);
+      verdict_s = rc;
+    }
+    __syncthreads();
+    const int drawn = verdict_s;
+    __syncthreads();                              // verdict_s is rewritten below
+    if (drawn < 0) break;                         // the square method found no pose: "the sampling space looks empty"
+    if (drawn == 0) continue;                     // SpaceSeemsEmptyError of the circle method: draw again
+    // ---- CostMap2D.create_empty(world_size=(h, w), origin=(-h/2, -w/2)) and the two walls (mini_env.py:364-389) ----
+    const double origin_x = -mp_s.h / 2., origin_y = -mp_s.w / 2.;
+    const int width = world_to_pixel_1d(mp_s.h, 0.0, p.inv_resolution), height = world_to_pixel_1d(mp_s.w, 0.0, p.inv_resolution);
+    const int pitch = (width + 31) & ~31;
+    const int tiles_x = pitch >> 5, tiles_y = (height + 15) >> 4, ctiles_x = pitch >> 4, ctiles_y = (height + 7) >> 3;
+    const double dxp = mp_s.end[0] - mp_s.start[0], dyp = mp_s.end[1] - mp_s.start[1];
+    const double dist = sqrt(dxp * dxp + dyp * dyp);
+    const int n_path = dist > path_delta ? (int)(dist / path_delta) + 2 : 2;        // refine_path of a two-point path
+    const bool fits = width > 0 && height > 0 && width < 32768 && height < 32768 &&
+                      (int64_t)height * pitch <= slots.map_slot_bytes && (int64_t)ctiles_x * ctiles_y * 128 <= slots.map_slot_bytes &&
+                      (int64_t)tiles_x * tiles_y * 16 <= slots.tile_slot_words && n_path <= slots.path_pitch &&
+                      (n_path + 31) / 32 <= slots.chunk_pitch;
+    if (!fits) {
+      if (tid == 0) atomicAdd(b.status + BCG_STATUS_SLOT_OVERFLOW, 1u);
+      return;                                     // (before anything of the slot was touched in this attempt)
+    }
+    if (gs->valid) {                              // erase what the slot holds, with the layout it was drawn in
+      MapLayout old = m;
+      old.pitch = gs->pitch; old.rows = gs->rows; old.tiles_x = gs->tiles_x; old.ctiles_x = gs->ctiles_x;
+      for (int k = 0; k < 5; ++k)
+        draw_wall_clipped(old, gs->pad[0], gs->rows, gs->wall[k][0], gs->wall[k][1], gs->wall[k][2], gs->wall[k][3], 0, tid, nthr);
+    }
+    __syncthreads();
+    m.pitch = pitch; m.rows = height; m.tiles_x = tiles_x; m.ctiles_x = ctiles_x;
+    int wpx[2][4];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const double* far = k == 0 ? mp_s.a : mp_s.b;
+      wpx[k][0] = world_to_pixel_1d(mp_s.o[0], origin_x, p.inv_resolution);
+      wpx[k][1] = world_to_pixel_1d(mp_s.o[1], origin_y, p.inv_resolution);
+      wpx[k][2] = world_to_pixel_1d(far[0], origin_x, p.inv_resolution);
+      wpx[k][3] = world_to_pixel_1d(far[1], origin_y, p.inv_resolution);
+      draw_wall_clipped(m, width, height, wpx[k][0], wpx[k][1], wpx[k][2], wpx[k][3], 254, tid, nthr);
+    }
+    if (tid == 0) {
+      AisleGenState ns;
+      for (int k = 0; k < 5; ++k)
+        for (int c = 0; c < 4; ++c) ns.wall[k][c] = k < 2 ? wpx[k][c] : -1;      // (-1, -1)-(-1, -1) clips to nothing
+      ns.pitch = pitch; ns.rows = height; ns.tiles_x = tiles_x; ns.ctiles_x = ctiles_x;
+      ns.valid = 1;
+      for (int k = 0; k < 7; ++k) ns.pad[k] = 0;
+      ns.pad[0] = width;                          // the clip rectangle of the walls drawn
+      *gs = ns;
+      md->origin_x = origin_x; md->origin_y = origin_y;
+      md->height = height; md->width = width; md->pitch = pitch;
+      md->tiles_x = tiles_x; md->tiles_y = tiles_y; md->ctiles_x = ctiles_x; md->ctiles_y = ctiles_y;
+      md->flags = BCG_MAP_ONLY_LETHAL;
+    }
+    __syncthreads();                              // walls, planes and the descriptor are visible to the CTA
+    // ---- the final check of _sample_mini_env_params (:336-358): both end poses free, not within the goal tolerances ----
+    if (warp == 0) {
+      bool ok = true;
+      if (!explicit_params) {
+        const WorkCollide w0 = make_work_collide(p, b, e, e, mp_s.start[0], mp_s.start[1], mp_s.start[2]);
+        const WorkCollide w1 = make_work_collide(p, b, e, e, mp_s.end[0], mp_s.end[1], mp_s.end[2]);
+        const bool hit0 = collide_tiles<false, true>(b, w0, lane, nullptr);
+        const bool hit1 = collide_tiles<false, true>(b, w1, lane, nullptr);
+        const double cart = hypot(mp_s.start[0] - mp_s.end[0], mp_s.start[1] - mp_s.end[1]);
+        const double ang = fabs(wrap_angle(mp_s.start[2] - mp_s.end[2]));
+        const bool too_close = cart < g.goal_spat_dist && ang < g.goal_ang_dist;
+        ok = !(hit0 || hit1) && !too_close;
+      }
+      if (lane == 0) verdict_s = ok ? 1 : 0;
+    }
+    __syncthreads();
+    accepted = verdict_s == 1;
+    __syncthreads();
+    if (!accepted) continue;
+    // ---- accepted: refined path (path_tools.py:178-240 for two way points), chunk bounds, initial state ----------------
+    double* P = const_cast<double*>(b.path_arena) + pdsc->off;
+    const int pp = slots.path_pitch;
+    if (tid == 0) {
+      pdsc->n = n_path;
+      pdsc->pitch = pp;
+      pdsc->n_chunks = (n_path + 31) / 32;
+      pdsc->chunk_pitch = slots.chunk_pitch;
+      pdsc->chunk_off = pdsc->off + 5 * (int64_t)pp;
+      if (params_out) params_out[e] = mp_s;
+    }
+    {
+      const double div = (double)(n_path - 1);    // np.linspace(start, end, num)[:-1] then the end point itself
+      const double sx = dxp / div, sy = dyp / div;
+      double sn0, cs0, sn1, cs1;
+      sincos(mp_s.start[2], &sn0, &cs0);
+      sincos(mp_s.end[2], &sn1, &cs1);
+      for (int i = tid; i < n_path; i += nthr) {
+        const bool last = i == n_path - 1;
+        const bool refined = dist > path_delta;
+        const double x = last ? mp_s.end[0] : (refined ? (double)i * sx + mp_s.start[0] : mp_s.start[0]);
+        const double y = last ? mp_s.end[1] : (refined ? (double)i * sy + mp_s.start[1] : mp_s.start[1]);
+        P[i] = x; P[pp + i] = y;
+        P[2 * pp + i] = last ? mp_s.end[2] : mp_s.start[2];
+        P[3 * pp + i] = last ? cs1 : cs0;
+        P[4 * pp + i] = last ? sn1 : sn0;
+      }
+    }
+    __syncthreads();
+    double* Cb = P + 5 * (int64_t)pp;
+    const int nwarp = nthr >> 5;
+    for (int c = warp; c * 32 < n_path; c += nwarp) {
+      const int i = min(c * 32 + lane, n_path - 1);
+      const double x = P[i], y = P[pp + i];
+      double xlo = x, xhi = x, ylo = y, yhi = y;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        xlo = fmin(xlo, __shfl_xor_sync(BCG_FULL, xlo, o)); xhi = fmax(xhi, __shfl_xor_sync(BCG_FULL, xhi, o));
+        ylo = fmin(ylo, __shfl_xor_sync(BCG_FULL, ylo, o)); yhi = fmax(yhi, __shfl_xor_sync(BCG_FULL, yhi, o));
+      }
+      const double ctx = 0.5 * (xlo + xhi), cty = 0.5 * (ylo + yhi);
+      double rad = hypot(x - ctx, y - cty);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) rad = fmax(rad, __shfl_xor_sync(BCG_FULL, rad, o));
+      if (lane == 0) {
+        Cb[c] = ctx; Cb[slots.chunk_pitch + c] = cty; Cb[2 * slots.chunk_pitch + c] = rad * (1 + 1e-12) + 1e-9;
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      PathRef pr;
+      pr.P = P; pr.C = Cb; pr.n = n_path; pr.pitch = pp; pr.chunk_pitch = slots.chunk_pitch;
+      init_env_state(p, b, L, e, pr, lane);
+    }
+  }
+  if (!accepted && tid == 0) atomicAdd(b.status + BCG_STATUS_SAMPLER_EMPTY, 1u);
+}
+
 __global__ void __launch_bounds__(256) reset_kernel(const BcgBatch b, const uint8_t* __restrict__ mask) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= b.n_envs) return;
@@ -1587,6 +1747,8 @@ int64_t bcg_sizeof(int32_t which) {
     case 6: return sizeof(BcgStepOut);
     case 7: return sizeof(BcgTurnParams);
     case 8: return sizeof(BcgAisleSlots);
+    case 9: return sizeof(BcgMiniGenParams);
+    case 10: return sizeof(BcgMiniParams);
     default: return -1;
   }
 }
@@ -1690,6 +1852,29 @@ int bcg_generate_aisles(const BcgParams* p, const BcgBatch* b, const BcgAisleSlo
   BCG_REQUIRE((int)(0.05 / p->resolution) <= 1, "walls are drawn one pixel thick: resolution must be above 0.025 m");
   generate_aisles_kernel<<<b->n_envs, 256, 0, (cudaStream_t)stream>>>(*p, *b, make_layout(*p), *slots, mask, turn_params,
                                                                      draw_index, path_delta);
+  BCG_CHECK_CUDA(cudaGetLastError());
+  return BCG_OK;
+}
+
+int bcg_generate_minis(const BcgParams* p, const BcgBatch* b, const BcgAisleSlots* slots, const uint8_t* mask,
+                       const BcgMiniGenParams* gen, const BcgMiniParams* mini_params, BcgMiniParams* params_out,
+                       uint64_t draw_index, double path_delta, void* stream) {
+  if (int rc = check_batch(p, b)) return rc;
+  BCG_REQUIRE(slots && slots->gen_state, "null slots / gen_state");
+  BCG_REQUIRE(gen || mini_params, "need the sampling space (gen) or explicit MiniEnvParams");
+  BCG_REQUIRE(b->cell_tile_arena, "bcg_generate_minis needs the cell-tile arena");
+  BCG_REQUIRE(!b->map_tmaps, "bcg_generate_minis cannot re-encode TMA tensor maps; use cell-tile or plain-load staging");
+  BCG_REQUIRE(b->n_maps == b->n_envs && b->n_paths == b->n_envs, "device-generated envs own one map and one path slot each");
+  BCG_REQUIRE(slots->map_slot_bytes > 0 && slots->tile_slot_words > 0 && slots->path_pitch >= 8 && slots->path_pitch % 4 == 0 &&
+                  slots->chunk_pitch * 32 >= slots->path_pitch,
+              "bad slot sizes");
+  BCG_REQUIRE(path_delta > 0, "path_delta must be positive");
+  BCG_REQUIRE((int)(0.05 / p->resolution) <= 1, "walls are drawn one pixel thick: resolution must be above 0.025 m");
+  BcgMiniGenParams g;
+  memset(&g, 0, sizeof(g));
+  if (gen) g = *gen;
+  generate_minis_kernel<<<b->n_envs, 128, 0, (cudaStream_t)stream>>>(*p, *b, make_layout(*p), *slots, mask, g, mini_params,
+                                                                    params_out, draw_index, path_delta);
   BCG_CHECK_CUDA(cudaGetLastError());
   return BCG_OK;
 }

@@ -66,6 +66,7 @@ extern "C" {
 #define BCG_STATUS_LUT_MISS 0     /* footprint tuple not found in the angle-bin table */
 #define BCG_STATUS_PATH_EXHAUSTED 1 /* init: "Goal pose too close to initial pose" (reward.py:275-277) */
 #define BCG_STATUS_SLOT_OVERFLOW 2  /* bcg_generate_aisles: a drawn map / path did not fit its slot; env left as it was */
+#define BCG_STATUS_SAMPLER_EMPTY 3  /* bcg_generate_minis: "the sampling space looks empty" (mini_env.py:138,361)      */
 #define BCG_STATUS_WORDS 8
 
 /* episode statistics accumulated on device at episode end (fp64, length BCG_STATS_WORDS) */
@@ -220,6 +221,22 @@ typedef struct BcgAisleSlots {
   BcgTurnParams* params_out; /* optional device [n_envs]: the turn each regenerated env now has   */
 } BcgAisleSlots;
 
+/* RandomMiniEnvParams (envs/mini_env.py:30-46) + the two goal tolerances of its EnvParams the sampler's final check
+ * uses (:349-353) */
+typedef struct BcgMiniGenParams {
+  double inner_h, inner_w, mid_margin, out_margin;
+  double min_obstacle_angle, max_obstacle_angle;
+  double lim_euc_dist, lim_ang_dist, angular_pose_noise_scale;
+  double goal_spat_dist, goal_ang_dist;
+} BcgMiniGenParams;
+
+/* MiniEnvParams (envs/mini_env.py:80-92): world size, start / end poses, the corner obstacle (two walls o-a, o-b) */
+typedef struct BcgMiniParams {
+  double h, w;
+  double start[3], end[3];
+  double a[2], o[2], b[2];
+} BcgMiniParams;
+
 typedef struct BcgStateLayout {
   int32_t n_frows, n_irows;
   int32_t ring_control; /* first fp64 row of the control ring: delay_control slots x 2 rows */
@@ -242,7 +259,8 @@ int bcg_abi_version(void);
 /* copies the calling thread's last error message (NUL terminated) and returns its length */
 size_t bcg_last_error(char* buf, size_t cap);
 /* sizeof() of the ABI structs, in declaration order: 0 BcgParams, 1 BcgMapDesc, 2 BcgPathDesc,
- * 3 BcgFootprintLut, 4 BcgBatch, 5 BcgStateLayout, 6 BcgStepOut, 7 BcgTurnParams, 8 BcgAisleSlots; -1 for anything else.  Lets a
+ * 3 BcgFootprintLut, 4 BcgBatch, 5 BcgStateLayout, 6 BcgStepOut, 7 BcgTurnParams, 8 BcgAisleSlots, 9 BcgMiniGenParams,
+ * 10 BcgMiniParams; -1 for anything else.  Lets a
  * binding (ctypes, cffi, ...) verify its struct mirrors before the first call. */
 int64_t bcg_sizeof(int32_t which);
 /* number of CUDA devices visible, <0 on error; makes a missing GPU a loud failure for callers */
@@ -277,6 +295,18 @@ int bcg_reset_where(const BcgBatch* b, const uint8_t* mask, void* stream);
  * Not available together with TMA tensor maps (map_tmaps), which cannot be re-encoded on the device. */
 int bcg_generate_aisles(const BcgParams* p, const BcgBatch* b, const BcgAisleSlots* slots, const uint8_t* mask,
                         const BcgTurnParams* turn_params, uint64_t draw_index, double path_delta, void* stream);
+
+/* RandomMiniEnv's env construction (envs/mini_env.py:323-389, what its reset repeats) on the device, for envs with
+ * mask[e] != 0 (mask NULL = all), in the same per-env slots as bcg_generate_aisles: sample MiniEnvParams (:269-320,
+ * Philox keyed (p->seed; env id, draw_index) in the reference's draw order) until neither end pose collides and the
+ * two are not within the goal tolerances of each other (:336-358), rasterise the two walls like cv2.line incl. its
+ * clipping of far end points (cv::clipLine), refine the path, make the initial state.  With `mini_params` (device
+ * [n_envs]) the worlds are built from those parameters as they are, like MiniEnv(config) does.  `params_out`
+ * (optional, device [n_envs]) receives the accepted parameters.  BCG_STATUS_SLOT_OVERFLOW counts worlds that do not
+ * fit their slots, BCG_STATUS_SAMPLER_EMPTY envs whose sampling ran out of tries (both left as they were). */
+int bcg_generate_minis(const BcgParams* p, const BcgBatch* b, const BcgAisleSlots* slots, const uint8_t* mask,
+                       const BcgMiniGenParams* gen, const BcgMiniParams* mini_params, BcgMiniParams* params_out,
+                       uint64_t draw_index, double path_delta, void* stream);
 
 /* -- the hot path -------------------------------------------------------------------------------- */
 /* PlanEnv.step (env.py:334-361) for all envs.  actions: device [n][2] (wheel_v, wheel_angle) or

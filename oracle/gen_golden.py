@@ -329,6 +329,30 @@ def gen_t_junction(name):
     print(name, [out["costmap_%d" % i].shape for i in range(len(cases))])
 
 
+def gen_mini_worlds(name, n_envs):
+    """Worlds the reference samples for RandomMiniEnv (envs/mini_env.py:269-389): the accepted MiniEnvParams, the
+    costmap, the coarse and refined path and the initial reward state, for RandomState(400 + s)."""
+    from bc_gym_planning_env.envs.base.params import EnvParams
+    from bc_gym_planning_env.envs.mini_env import MiniEnv, RandomMiniEnvParams, _sample_mini_env_params
+    out = {"n_envs": np.int64(n_envs)}
+    gen = RandomMiniEnvParams(env_params=EnvParams(goal_ang_dist=np.pi / 8., goal_spat_dist=0.2))
+    for s in range(n_envs):
+        mp = _sample_mini_env_params(gen, np.random.RandomState(400 + s))
+        env = MiniEnv(mp)
+        st = env._state
+        out["params_%d" % s] = np.r_[mp.h, mp.w, mp.start_pos.as_np(), mp.end_pos.as_np(), mp.obstacle_a.as_np(),
+                                     mp.obstacle_o.as_np(), mp.obstacle_b.as_np()]
+        out["costmap_%d" % s] = st.costmap.get_data().copy()
+        out["origin_%d" % s] = np.array(st.costmap.get_origin())
+        out["path_%d" % s] = np.array(st.original_path)
+        rp = st.reward_provider_state
+        out["target_idx_%d" % s] = np.int64(rp.target_idx)
+        out["min_dist_%d" % s] = np.float64(rp.min_spat_dist_so_far)
+    out["resolution"] = np.float64(st.costmap.get_resolution())
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, [out["costmap_%d" % s].shape for s in range(n_envs)][:3], [len(out["path_%d" % s]) for s in range(n_envs)])
+
+
 def main():
     _ref()
     os.makedirs(OUT, exist_ok=True)
@@ -352,6 +376,7 @@ def main():
     gen_diffdrive("diffdrive_steps", 6, 250)
     gen_aisle_worlds("aisle_worlds", 16)
     gen_t_junction("t_junction")
+    gen_mini_worlds("mini_worlds", 24)
 
 
 if __name__ == "__main__":
