@@ -458,6 +458,22 @@ def run_b200(args):
         if genv is not env:
             del genv
             torch.cuda.empty_cache()
+        # RandomMiniEnv.reset for a configs[1]-sized batch: sample (with its collision / too-close rejection), rasterise,
+        # initial state -- the reference does ~100 of these per second on a core
+        from bc_gym_planning_env_b200.vec_aisle_env import VecRandomMiniEnv
+        menv = VecRandomMiniEnv(4096, seed=98, device=device)
+        menv.generate()
+        torch.cuda.synchronize()
+        g0.record()
+        for _ in range(reps):
+            menv.generate()
+        g1.record()
+        torch.cuda.synchronize()
+        menv.check_status()
+        generation["mini"] = {"worlds_per_sec": menv.n_envs / (g0.elapsed_time(g1) / reps * 1e-3), "envs": menv.n_envs,
+                              "ms_per_launch": g0.elapsed_time(g1) / reps, "kernel": "generate_minis_kernel"}
+        del menv
+        torch.cuda.empty_cache()
 
     # ---- e2e: host actions in, host results out, every step -----------------------------------------
     h_actions = [a.cpu().pin_memory() for a in actions]
