@@ -75,24 +75,39 @@ def aisle_params():
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler(object):
-    """nvidia-smi clocks and throttle reasons sampled DURING the timed region."""
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks and throttle reasons sampled DURING the timed region: the sampler starts before the warm-up
+    (nvidia-smi needs a few hundred ms to come up), every sample carries a timestamp, and only the samples between
+    `mark_start()` and `mark_end()` are kept (all samples under load if the region was shorter than one poll)."""
+    QUERY = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.gpu_index = gpu_index
         self.proc, self.path = None, None
+        self.t_load = self.t0 = self.t1 = None
 
     def start(self):
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "10"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+        self.t_load = time.time()
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
+    @staticmethod
+    def _stamp(text):
+        import datetime
+        return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -103,25 +118,32 @@ class ClockSampler(object):
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
+        rows = []
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
-                if len(f) < 8:
+                if len(f) < 9:
                     continue
                 try:
-                    sm.append(float(f[1]))
-                    smax.append(float(f[2]))
+                    rows.append((self._stamp(f[0]), float(f[2]), float(f[3]), f[5:9]))
                 except ValueError:
                     continue
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(np.max(smax)), reasons=sorted(reasons), samples=len(sm))
+        t0, t1 = self.t0 or self.t_load, self.t1 or time.time()
+        inside = [r for r in rows if t0 - 0.005 <= r[0] <= t1 + 0.005]
+        scope = "timed region"
+        if not inside:                       # region shorter than a poll: everything sampled since the warm-up began
+            inside, scope = [r for r in rows if self.t_load <= r[0] <= t1 + 0.005], "warm-up + timed region"
+        reasons = set()
+        for r in inside:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if inside:
+            out.update(sm_mhz=float(np.median([r[1] for r in inside])), sm_max_mhz=float(np.max([r[2] for r in inside])),
+                       reasons=sorted(reasons), samples=len(inside), scope=scope)
         return out
 
 
@@ -312,26 +334,28 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for w in range(args.warmup):
         env.step(actions[w % n_sets])
     env.episode_stats(reset=True)
     barrier()
 
     # ---- timed region: K steps, inputs resident in HBM ------------------------------------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
     for evs in ev:
         for e in evs:
             e.record()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_start()
     t_start.record()
     for k in range(args.steps):
         env.step_timed(actions[k % n_sets], ev[k])
     stats = allreduce_episode_stats(env)      # the path's only collective
     t_end.record()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop()
     elapsed_ms = t_start.elapsed_time(t_end)
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
