@@ -212,6 +212,16 @@ __device__ __forceinline__ void delay_line(double* ring, int64_t stride, int& q,
   q = head | (len << 16);
 }
 
+// What delay_line would hand back for `v`, without touching the ring
+template <int NCOMP>
+__device__ __forceinline__ void delay_peek(const double* ring, int64_t stride, int q, int d, double v[NCOMP]) {
+  if (d <= 0) return;
+  const int head = q & 0xffff, len = q >> 16;
+  if (len == 0) return;                     // warm-up with an empty queue: the element itself comes back
+#pragma unroll
+  for (int c = 0; c < NCOMP; ++c) v[c] = ring[(int64_t)(head * NCOMP + c) * stride];
+}
+
 // ---- footprint table lookup ----------------------------------------------------------------------
 // Work records: what the warp-per-env kernels need to know about one env, resolved by the thread-per-env
 // kernels (kinematics / pose-prep) and stored array-of-structures so that a warp gets everything with one

@@ -27,6 +27,9 @@ using namespace bcg;
 #ifndef BCG_COMMIT_THREADS
 #define BCG_COMMIT_THREADS 128
 #endif
+#ifndef BCG_COMMIT_MIN_BLOCKS
+#define BCG_COMMIT_MIN_BLOCKS 4      // register budget of commit_kernel: 65536 / (threads x blocks)
+#endif
 #ifndef BCG_CR_THREADS
 #define BCG_CR_THREADS 64
 #endif
@@ -280,13 +283,12 @@ __device__ __forceinline__ EgoAffine ego_affine(const BcgParams& p, const BcgMap
 }
 
 // goal_n_state (envs/egocentric.py:141-160) by one thread
+// `target` and `drobot` (the delayed robot state x, y, th, v, w, steer, wheel) are those of the state being observed
 __device__ __forceinline__ void write_goal_n_state(const BcgParams& p, const BcgBatch& b, int e, double px, double py,
-                                                   double pth, float* __restrict__ goal_n_state) {
-  const int64_t N = b.n_envs;
-  const double* sf = b.state_f + e;
+                                                   double pth, int target, const double drobot[7],
+                                                   float* __restrict__ goal_n_state) {
   float* g = goal_n_state + (int64_t)e * 9;
   const BcgPathDesc pd = b.paths[b.path_id[e]];
-  const int target = b.state_i[BCG_I_TARGET * N + e];
   if (target > pd.n - 1) {
 #pragma unroll
     for (int k = 0; k < 9; ++k) g[k] = 0.f;
@@ -312,21 +314,21 @@ __device__ __forceinline__ void write_goal_n_state(const BcgParams& p, const Bcg
     const double nrm = sqrt(nx * nx + ny * ny);
     g[0] = (float)(nx / nrm);
     g[1] = (float)(ny / nrm);
-    g[2] = (float)sf[(BCG_F_DROBOT + 3) * N];
-    g[3] = (float)sf[(BCG_F_DROBOT + 4) * N];
-    g[4] = (float)sf[(BCG_F_DROBOT + 6) * N];
+    g[2] = (float)drobot[3];
+    g[3] = (float)drobot[4];
+    g[4] = (float)drobot[6];
     g[5] = g[6] = g[7] = g[8] = 0.f;
     return;
   }
   g[0] = (float)clampd(ex / p.ego_world_w, -1.0, 1.0);
   g[1] = (float)clampd(ey / p.ego_world_h, -1.0, 1.0);
   g[2] = (float)ea;
-  g[3] = (float)sf[(BCG_F_DROBOT + 0) * N];
-  g[4] = (float)sf[(BCG_F_DROBOT + 1) * N];
-  g[5] = (float)sf[(BCG_F_DROBOT + 2) * N];
-  g[6] = (float)sf[(BCG_F_DROBOT + 3) * N];
-  g[7] = (float)sf[(BCG_F_DROBOT + 4) * N];
-  g[8] = (float)sf[(BCG_F_DROBOT + 6) * N];
+  g[3] = (float)drobot[0];
+  g[4] = (float)drobot[1];
+  g[5] = (float)drobot[2];
+  g[6] = (float)drobot[3];
+  g[7] = (float)drobot[4];
+  g[8] = (float)drobot[6];
 }
 
 // Per-env record the egocentric kernel starts from, resolved one thread per env (commit / prep kernel):
@@ -570,63 +572,93 @@ __device__ __forceinline__ void write_ego_record(const BcgParams& p, const BcgBa
   }
 }
 
-// One thread per env: the rest of _resolve_state_transition (env.py:363-398) -- rollback, pose and
-// robot-state delay lines, time/iter, sticky collision -- then done (env.py:407-419), episode statistics,
-// auto-reset (env.py:293-303) and the compact fp32 observation.  All accesses are coalesced SoA rows.
-__global__ void __launch_bounds__(BCG_COMMIT_THREADS) commit_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L,
+// Two threads per env, in different warps of one CTA (64 envs per 128-thread block).  Role 0: the rest of
+// _resolve_state_transition (env.py:363-398) -- rollback, pose and robot-state delay lines, time/iter, sticky collision
+// -- then done (env.py:407-419), episode statistics, auto-reset (env.py:293-303) and the compact fp32 observation.
+// Role 1: what the observation kernels need from the state being written -- the egocentric work record and
+// goal_n_state -- computed from the same inputs at the same time instead of after the writes: the kernel is bound by
+// the length of a thread's dependent chain, and this halves it.  Both roles read before anyone writes (one barrier).
+// All accesses are coalesced SoA rows.
+__global__ void __launch_bounds__(BCG_COMMIT_THREADS, BCG_COMMIT_MIN_BLOCKS) commit_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L,
                                                      const BcgStepOut out, const int ego_cap) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int EPB = BCG_COMMIT_THREADS / 2;              // envs per block
+  const int role = threadIdx.x / EPB;
+  const int e = blockIdx.x * EPB + (threadIdx.x - role * EPB);
   const bool active = e < b.n_envs;
   const int64_t N = b.n_envs;
   double ev_ret = 0.0, ev_len = 0.0;
   int ev = 0, ev_col = 0, ev_goal = 0, ev_to = 0;
+  // ---- phase 1 (both roles): everything that is read ------------------------------------------------------------------
+  double c[7], dpose[3], dstate[7];
+  double reward = 0.0, min_dist = 0.0, time = 0.0, ep_return = 0.0;
+  int target = 0, flags = 0, iter = 0, collided = 0, qp = 0, qs = 0;
+  double* sf = b.state_f + (active ? e : 0);
+  int32_t* si = b.state_i + (active ? e : 0);
   if (active) {
-    double* sf = b.state_f + e;
-    int32_t* si = b.state_i + e;
-    double c[7];
 #pragma unroll
     for (int r = 0; r < 7; ++r) c[r] = b.cand[r * N + e];
-    const double reward = b.cand[7 * N + e];
-    const double min_dist = b.cand[8 * N + e];
-    const int target = b.cand_i[BCG_CI_TARGET * N + e];
-    const int flags = b.cand_i[BCG_CI_FLAGS * N + e];
-    const bool hit = flags & 1, goal = flags & 2, goal_before = flags & 4;
-    int iter = si[BCG_I_ITER * N];
-    int collided = si[BCG_I_COLLIDED * N];
-    int qp = si[BCG_I_QP * N], qs = si[BCG_I_QS * N];
-    const bool done_before = goal_before || (iter >= p.iteration_timeout) || (collided != 0);
-    if (hit) {  // env.py:458-459 + tricycle_model.py:471-476: pose restored, v = w = 0, wheel/steer kept
+    target = b.cand_i[BCG_CI_TARGET * N + e];
+    flags = b.cand_i[BCG_CI_FLAGS * N + e];
+    iter = si[BCG_I_ITER * N];
+    collided = si[BCG_I_COLLIDED * N];
+    qp = si[BCG_I_QP * N];
+    qs = si[BCG_I_QS * N];
+    if (role == 0) {
+      reward = b.cand[7 * N + e];
+      min_dist = b.cand[8 * N + e];
+      time = sf[BCG_F_TIME * N] + p.dt;
+      ep_return = sf[BCG_F_EP_RETURN * N] + reward;
+    }
+    if (flags & 1) {  // env.py:458-459 + tricycle_model.py:471-476: pose restored, v = w = 0, wheel/steer kept
       c[0] = sf[(BCG_F_ROBOT + 0) * N];
       c[1] = sf[(BCG_F_ROBOT + 1) * N];
       c[2] = sf[(BCG_F_ROBOT + 2) * N];
       c[3] = 0.0;
       c[4] = 0.0;
     }
-    double dpose[3] = {c[0], c[1], c[2]};
-    double dstate[7];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) dpose[r] = c[r];
 #pragma unroll
     for (int r = 0; r < 7; ++r) dstate[r] = c[r];
+    if (role == 1) {                                       // role 0 reads the rings when it updates them
+      delay_peek<3>(sf + (int64_t)L.ring_pose * N, N, qp, p.delay_pose, dpose);
+      delay_peek<7>(sf + (int64_t)L.ring_state * N, N, qs, p.delay_state, dstate);
+    }
+  }
+  const bool hit = flags & 1, goal = flags & 2, goal_before = flags & 4;
+  const bool done_before = goal_before || (iter >= p.iteration_timeout) || (collided != 0);
+  const int iter_after = iter + 1;
+  const int collided_after = collided | (hit ? 1 : 0);
+  const bool timed_out = iter_after >= p.iteration_timeout;
+  const bool done = goal || timed_out || (collided_after != 0);
+  const bool reset_now = done && p.auto_reset;
+  if (active && role == 1 && reset_now && (out.ego_image || out.goal_n_state)) {     // the observation is the initial state's
+    target = b.init_i[(int64_t)BCG_I_TARGET * N + e];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) dpose[r] = b.init_f[(int64_t)(BCG_F_DPOSE + r) * N + e];
+#pragma unroll
+    for (int r = 0; r < 7; ++r) dstate[r] = b.init_f[(int64_t)(BCG_F_DROBOT + r) * N + e];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) c[r] = b.init_f[(int64_t)(BCG_F_ROBOT + r) * N + e];
+  }
+  __syncthreads();                                         // nothing of the state has been written yet
+  // ---- phase 2 -------------------------------------------------------------------------------------------------------
+  if (active && role == 0) {
     delay_line<3>(sf + (int64_t)L.ring_pose * N, N, qp, p.delay_pose, dpose);
     delay_line<7>(sf + (int64_t)L.ring_state * N, N, qs, p.delay_state, dstate);
-    const double time = sf[BCG_F_TIME * N] + p.dt;
-    const double ep_return = sf[BCG_F_EP_RETURN * N] + reward;
-    iter += 1;
-    collided |= hit ? 1 : 0;
-    const bool timed_out = iter >= p.iteration_timeout;
-    const bool done = goal || timed_out || (collided != 0);
     if (out.reward) out.reward[e] = reward;
     if (out.done) out.done[e] = done ? 1 : 0;
     if (out.hit) out.hit[e] = hit ? 1 : 0;
     if (done && !done_before) {
       ev = 1;
       ev_ret = ep_return;
-      ev_len = (double)iter;
-      ev_col = collided;
+      ev_len = (double)iter_after;
+      ev_col = collided_after;
       ev_goal = goal ? 1 : 0;
       ev_to = timed_out ? 1 : 0;
     }
     float ov[12];
-    if (done && p.auto_reset) {
+    if (reset_now) {
       for (int r = 0; r < L.n_frows; ++r) sf[(int64_t)r * N] = b.init_f[(int64_t)r * N + e];
       for (int r = 0; r < L.n_irows; ++r) si[(int64_t)r * N] = b.init_i[(int64_t)r * N + e];
       if (out.obs_vec) {
@@ -647,9 +679,9 @@ __global__ void __launch_bounds__(BCG_COMMIT_THREADS) commit_kernel(const BcgPar
       sf[BCG_F_TIME * N] = time;
       sf[BCG_F_MIN_DIST * N] = min_dist;
       sf[BCG_F_EP_RETURN * N] = ep_return;
-      si[BCG_I_ITER * N] = iter;
+      si[BCG_I_ITER * N] = iter_after;
       si[BCG_I_TARGET * N] = target;
-      si[BCG_I_COLLIDED * N] = collided;
+      si[BCG_I_COLLIDED * N] = collided_after;
       si[BCG_I_QP * N] = qp;
       si[BCG_I_QS * N] = qs;
 #pragma unroll
@@ -665,15 +697,14 @@ __global__ void __launch_bounds__(BCG_COMMIT_THREADS) commit_kernel(const BcgPar
       o[1] = make_float4(ov[4], ov[5], ov[6], ov[7]);
       o[2] = make_float4(ov[8], ov[9], ov[10], ov[11]);
     }
-    // the observation the egocentric kernel will render is that of the state just written: resolve its
-    // affine map, source window and goal vector here, one thread per env
-    if (out.ego_image || out.goal_n_state) {
-      const int prow = p.ego_variant == 1 ? BCG_F_ROBOT : BCG_F_DPOSE;   // true robot pose vs observed (delayed) pose
-      const double opx = sf[(prow + 0) * N], opy = sf[(prow + 1) * N], opth = sf[(prow + 2) * N];
-      if (out.ego_image)
-        write_ego_record(p, b, e, b.map_id[e], opx, opy, opth, ego_cap);
-      if (out.goal_n_state) write_goal_n_state(p, b, e, opx, opy, opth, out.goal_n_state);
-    }
+  }
+  if (active && role == 1 && (out.ego_image || out.goal_n_state)) {
+    // the observation the egocentric kernel will render is that of the state role 0 is writing: resolve its affine
+    // map, source window and goal vector from the same values
+    const bool true_pose = p.ego_variant == 1;             // true robot pose vs observed (delayed) pose
+    const double opx = true_pose ? c[0] : dpose[0], opy = true_pose ? c[1] : dpose[1], opth = true_pose ? c[2] : dpose[2];
+    if (out.ego_image) write_ego_record(p, b, e, b.map_id[e], opx, opy, opth, ego_cap);
+    if (out.goal_n_state) write_goal_n_state(p, b, e, opx, opy, opth, target, dstate, out.goal_n_state);
   }
   // episode statistics: one atomic set per warp that saw an episode end
   if (__any_sync(BCG_FULL, ev != 0)) {
@@ -1677,7 +1708,12 @@ __global__ void __launch_bounds__(128) ego_prep_kernel(const BcgParams p, const 
   const int prow = p.ego_variant == 1 ? BCG_F_ROBOT : BCG_F_DPOSE;
   const double px = sf[(prow + 0) * N], py = sf[(prow + 1) * N], pth = sf[(prow + 2) * N];
   if (want_image) write_ego_record(p, b, e, b.map_id[e], px, py, pth, ego_cap);
-  if (goal_n_state) write_goal_n_state(p, b, e, px, py, pth, goal_n_state);
+  if (goal_n_state) {
+    double drobot[7];
+#pragma unroll
+    for (int r = 0; r < 7; ++r) drobot[r] = sf[(BCG_F_DROBOT + r) * N];
+    write_goal_n_state(p, b, e, px, py, pth, b.state_i[BCG_I_TARGET * N + e], drobot, goal_n_state);
+  }
 }
 
 __global__ void __launch_bounds__(256) gather_kernel(const BcgBatch b, const int64_t* __restrict__ idx, const int k,
@@ -2021,7 +2057,7 @@ int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, 
   collide_reward_kernel<<<blocks_for((int64_t)b->n_envs * 32, BCG_CR_THREADS), BCG_CR_THREADS, 0, s>>>(*p, *b);
   BCG_CHECK_CUDA(cudaGetLastError());
   if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[2], s));
-  commit_kernel<<<blocks_for(b->n_envs, BCG_COMMIT_THREADS), BCG_COMMIT_THREADS, 0, s>>>(*p, *b, L, *out, ego ? ego_capacity(*p, *b) : 0);
+  commit_kernel<<<blocks_for(b->n_envs, BCG_COMMIT_THREADS / 2), BCG_COMMIT_THREADS, 0, s>>>(*p, *b, L, *out, ego ? ego_capacity(*p, *b) : 0);
   BCG_CHECK_CUDA(cudaGetLastError());
   if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[3], s));
   if (out->ego_image) {
