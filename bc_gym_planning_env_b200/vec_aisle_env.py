@@ -1,4 +1,4 @@
-"""VecRandomAisleTurnEnv: N `RandomAisleTurnEnv`s whose worlds are drawn and rasterised on the GPU.
+"""VecRandomAisleTurnEnv / VecRandomMiniEnv: batches whose worlds are drawn and rasterised on the GPU.
 
 The reference rebuilds a random aisle turn on the host at every `reset` (envs/synth_turn_env.py:278-291:
 draw TurnParams :317-332, path_and_costmap_from_config :110-192, cv2.line walls, refine_path, initial reward
@@ -7,6 +7,8 @@ in one launch: every env owns a fixed-size slot of the map / tile / path arenas 
 place, so a 65 536-env reset storm is a single kernel instead of a minute of host work.
 Draws come from Philox4x32-10 keyed (seed; env id, draw index) instead of the reference's MT19937; explicit
 TurnParams can be supplied instead (that is how the parity tests replay the reference's own worlds).
+`VecRandomMiniEnv` does the same for `RandomMiniEnv` (envs/mini_env.py:269-389: rejection sampler, two clipped
+walls, two-point path) through `bcg_generate_minis`.
 """
 import ctypes as C
 

@@ -311,8 +311,10 @@ int bcg_generate_minis(const BcgParams* p, const BcgBatch* b, const BcgAisleSlot
 /* -- the hot path -------------------------------------------------------------------------------- */
 /* PlanEnv.step (env.py:334-361) for all envs.  actions: device [n][2] (wheel_v, wheel_angle) or
  * (v, w) for diff-drive; action_is_f64 selects fp64 vs fp32 elements.  Launches, in order:
- * kinematics (thread/env), collision+reward (warp/env), commit (thread/env), egocentric observation
- * (CTA/env, only if out->ego_image or out->goal_n_state is set).  step_index is the caller's global step
+ * kinematics (thread/env), collision+reward (warp/env), commit (two threads/env), and -- only if
+ * out->ego_image is set -- the egocentric observation: with the occupancy plane and ego_list the sparse
+ * scatter kernel followed by the dense cell-tile kernel for the envs it hands over, else one dense kernel
+ * (CTA/env).  step_index is the caller's global step
  * counter: odometry noise is Philox4x32-10 keyed by p->seed at counter (env id, step_index, draw),
  * replacing the reference's global np.random (differential_drive.py:50). */
 int bcg_step(const BcgParams* p, const BcgBatch* b, const void* actions, int32_t action_is_f64,
