@@ -35,6 +35,7 @@ class BcgMapDesc(C.Structure):
         ("height", C.c_int32), ("width", C.c_int32), ("pitch", C.c_int32),
         ("tiles_x", C.c_int32), ("tiles_y", C.c_int32), ("flags", C.c_int32),
         ("cell_tile_off", C.c_int64), ("ctiles_x", C.c_int32), ("ctiles_y", C.c_int32),
+        ("occupied", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

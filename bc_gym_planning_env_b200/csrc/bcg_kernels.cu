@@ -455,7 +455,8 @@ struct __align__(16) EgoTileWork {   // 256 bytes
   int32_t ctiles_x, ctiles_y;        // cell-tile grid of the env's map
   int64_t ctile_off;                 // byte offset of the map's cell tiles in the cell-tile arena
   float fwd[6];                      // cv::warpAffine's forward matrix (source -> crop), for the sparse kernel
-  int32_t pad[4];
+  int32_t dense_map;                 // more than 1 cell in 20 of the map is occupied: skip the sparse kernel's scan
+  int32_t pad[3];
   uint8_t span[BCG_EGT_MAX_TILE_ROWS][2];   // first and last window tile column touched in tile row t (first > last: none)
 };
 static_assert(sizeof(EgoTileWork) == BCG_EGO_WORK_BYTES, "EgoTileWork records are 256 bytes");
@@ -478,8 +479,9 @@ __device__ __forceinline__ void write_ego_tile_record(const BcgParams& p, const 
   w.X0 = w.Y0 = w.ntx = w.nty = 0;
   w.mode = BCG_EGO_MODE_DIRECT;
   w.map_id = map_id;
+  w.dense_map = ((int64_t)m.occupied * 20 > (int64_t)m.width * m.height) ? 1 : 0;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) w.pad[k] = 0;
+  for (int k = 0; k < 3; ++k) w.pad[k] = 0;
   w.ctiles_x = m.ctiles_x;
   w.ctiles_y = m.ctiles_y;
   w.ctile_off = m.cell_tile_off;
@@ -830,6 +832,7 @@ __global__ void __launch_bounds__(256) generate_aisles_kernel(const BcgParams p,
     md->height = g.height; md->width = g.width; md->pitch = pitch;
     md->tiles_x = tiles_x; md->tiles_y = tiles_y; md->ctiles_x = ctiles_x; md->ctiles_y = ctiles_y;
     md->flags = BCG_MAP_ONLY_LETHAL;           // walls are the only occupied cells
+    md->occupied = 0;                          // (a few hundred: far below the dense threshold)
     pdsc->n = shape.n;
     pdsc->pitch = slots.path_pitch;
     pdsc->n_chunks = (shape.n + 31) / 32;
@@ -957,6 +960,7 @@ __global__ void __launch_bounds__(128) generate_minis_kernel(const BcgParams p, 
       md->height = height; md->width = width; md->pitch = pitch;
       md->tiles_x = tiles_x; md->tiles_y = tiles_y; md->ctiles_x = ctiles_x; md->ctiles_y = ctiles_y;
       md->flags = BCG_MAP_ONLY_LETHAL;
+      md->occupied = 0;
     }
     __syncthreads();                              // walls, planes and the descriptor are visible to the CTA
     // ---- the final check of _sample_mini_env_params (:336-358): both end poses free, not within the goal tolerances ----
@@ -1053,6 +1057,7 @@ __global__ void __launch_bounds__(256) tiles_kernel(const BcgBatch b, const int 
   uint32_t* occ = b.occ_tile_arena ? const_cast<uint32_t*>(b.occ_tile_arena) + m.tile_off : nullptr;
   const uint8_t* src = b.map_arena + m.data_off;
   bool other = false;                      // a cell that is neither free (0) nor lethal (254)
+  int occupied = 0;
   for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < words; w += gridDim.x * blockDim.x) {
     const int tile = w >> 4, r = w & 15;
     const int ty = tile / m.tiles_x, tx = tile - ty * m.tiles_x;
@@ -1081,12 +1086,21 @@ __global__ void __launch_bounds__(256) tiles_kernel(const BcgBatch b, const int 
         obits &= keep;
       }
       other |= (obits != bits);
+      occupied += __popc(obits);
     }
     dst[w] = bits;
     if (occ) occ[w] = obits;
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) occupied += __shfl_xor_sync(BCG_FULL, occupied, o);
+  if ((threadIdx.x & 31) == 0 && occupied) atomicAdd(&const_cast<BcgMapDesc*>(b.maps)[first + blockIdx.y].occupied, occupied);
   if (__any_sync(BCG_FULL, other) && (threadIdx.x & 31) == 0)
     atomicAnd(&const_cast<BcgMapDesc*>(b.maps)[first + blockIdx.y].flags, ~BCG_MAP_ONLY_LETHAL);
+}
+
+__global__ void __launch_bounds__(256) zero_occupied_kernel(const BcgBatch b, const int first, const int count) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < count) const_cast<BcgMapDesc*>(b.maps)[first + k].occupied = 0;
 }
 
 __global__ void __launch_bounds__(256) cell_tiles_kernel(const BcgBatch b, const int first) {
@@ -1566,7 +1580,10 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
     const int wx0 = X0 >> 5, nwx = ((X0 + 16 * ntx - 1) >> 5) - wx0 + 1;        // <= 9 columns of 32-cell words
     const int by0 = Y0 >> 4, nby = ((Y0 + 8 * nty - 1) >> 4) - by0 + 1;         // bands of 16 rows
     const int ntile = nby * nwx;
-    const bool try_sparse = mode == BCG_EGO_MODE_TILES && ntile <= BCG_EGS_MAX_TILES;
+    // maps with more than one cell in 20 occupied (filled regions, inflation gradients) overflow the cell list in
+    // almost every window: they go straight to the dense kernel instead of paying for a scan that is thrown away
+    const bool dense_map = r->dense_map != 0;           // decided by the record writer, which holds the map descriptor
+    const bool try_sparse = mode == BCG_EGO_MODE_TILES && ntile <= BCG_EGS_MAX_TILES && !dense_map;
     if (try_sparse) {
       // ---- 1. zero the crop in global memory ----------------------------------------------------------------------
       {
@@ -1810,6 +1827,7 @@ int bcg_build_lethal_tiles(const BcgBatch* b, int32_t first, int32_t count, void
   BCG_REQUIRE(b && b->maps && b->map_arena && b->tile_arena, "null map arena");
   BCG_REQUIRE(first >= 0 && count >= 0 && first + count <= b->n_maps, "map range out of bounds");
   cudaStream_t s = (cudaStream_t)stream;
+  if (count > 0) zero_occupied_kernel<<<blocks_for(count, 256), 256, 0, s>>>(*b, first, count);
   for (int32_t done = 0; done < count; done += 32768) {
     const int32_t chunk = (count - done) < 32768 ? (count - done) : 32768;
     tiles_kernel<<<dim3(8, chunk), 256, 0, s>>>(*b, first + done);

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BCG_ABI_VERSION 3
+#define BCG_ABI_VERSION 4
 
 /* error codes */
 #define BCG_OK 0
@@ -128,6 +128,9 @@ typedef struct BcgMapDesc {
                                bcg_build_lethal_tiles, cleared there when another value is met)       */
   int64_t cell_tile_off;    /* byte offset of the map's cell tiles in the cell-tile arena (multiple of 128) */
   int32_t ctiles_x, ctiles_y; /* 16 px x 8 rows per 128-byte cell tile: pitch / 16, ceil(height / 8)     */
+  int32_t occupied;         /* cells != 0, counted by bcg_build_lethal_tiles: maps with more than 1 cell in 20
+                               occupied skip the sparse egocentric kernel (their windows overflow its list) */
+  int32_t reserved;
 } BcgMapDesc;
 
 /* one refined path: fp64 SoA rows x,y,th,cos(th),sin(th), each `pitch` long, then chunk bounds */
