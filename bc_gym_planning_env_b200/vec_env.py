@@ -106,7 +106,10 @@ class VecPlanEnv(object):
         if not costmaps or not paths:
             raise ValueError("need at least one costmap and one path")
         n = int(n_envs if n_envs is not None else max(len(costmaps), len(paths)))
-        self._ego_sparse = bool(ego_sparse)
+        # the sparse kernel pays off on maps that are mostly free space; when every map of the pool is above the
+        # library's dense threshold (1 cell in 20 occupied) it would only hand every env over: leave it out
+        self._ego_sparse = bool(ego_sparse) and not all(
+            np.count_nonzero(c.get_data()) * 20 > c.get_data().size for c in costmaps)
         self._configure(params, n, float(costmaps[0].get_resolution()), noise_parameters, seed, auto_reset, device,
                         env_id_base, with_ego, ego_staging if use_tma else 'spans')   # use_tma=False: older spelling
         self._map_pool = costmaps

@@ -423,7 +423,7 @@ def run_b200(args):
                        "algorithmic bytes (SURVEY 8d) = in-map footprint pixels x 1 B (uint8 definition; the kernel reads "
                        "the derived 1-bit lethal tile plane) + remaining path points x 24 B (the kernel skips path chunks "
                        "farther than the reach radius); collision-only share: %.1f MB" % (coll_bytes / 1e6))
-    sparse = getattr(env, "_ego_list", None) is not None and os.environ.get("BCG_EGO_KERNEL") != "dense"
+    sparse = getattr(env, "occ_tile_arena", None) is not None and os.environ.get("BCG_EGO_KERNEL") != "dense"
     ego_name = "ego_sparse_kernel" if sparse else ("ego_tiles_kernel" if env.ego_staging == "tiles" else "ego_kernel")
     dense_envs = int(env._ego_list[n].item()) if sparse else n
     # Algorithmic bytes of the egocentric observation.  SURVEY 8d counts a gather: source read + image write = 2 x W x H
