@@ -1508,9 +1508,13 @@ __global__ void __launch_bounds__(BCG_EGT_THREADS, BCG_EGT_CTAS) ego_tiles_kerne
 #define BCG_EGS_REC_SLOTS 4          // record ring (power of two, > the prefetch distance 3)
 #endif
 #define BCG_EGS_MAX_TILES 128        // 32 x 16 bit tiles a window may span (sparse path); more -> dense kernel
-#ifndef BCG_EGS_ZERO_BYTES
-#define BCG_EGS_ZERO_BYTES 4096      // shared page of zeros the bulk stores read
+#ifndef BCG_EGS_QUEUE
+#define BCG_EGS_QUEUE 1              // 1: non-empty 16-byte occupancy pieces are queued per warp and expanded 32 at a time
 #endif
+#ifndef BCG_EGS_ZERO_BYTES
+#define BCG_EGS_ZERO_BYTES (BCG_EGS_QUEUE ? 2048 : 4096)      // shared page of zeros the bulk stores read
+#endif
+#define BCG_EGS_QCAP 64              // ring slots per warp: a push adds <= 32 to <= 31 left over
 struct EgoSparseTab {
   int2 adxy[BCG_EGT_MAX_W];                     // (rint(a11 u 2^10), rint(a21 u 2^10))
   int2 bxy[BCG_EGO_MAX];                        // rint((a12 v + b1) 2^10) + 512 - (X0 << 10), same for y
@@ -1525,6 +1529,11 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
 }
 __device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
@@ -1546,6 +1555,11 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
   __shared__ __align__(128) uint8_t rec_s[BCG_EGS_REC_SLOTS * BCG_EGO_WORK_BYTES];
   constexpr int NT = BCG_EGS_THREADS;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#if BCG_EGS_QUEUE
+  __shared__ __align__(16) uint4 qword_s[NT / 32][BCG_EGS_QCAP];
+  __shared__ uint32_t qtag_s[NT / 32][BCG_EGS_QCAP];
+  const uint32_t qword_u32 = smem_u32(qword_s[warp]), qtag_u32 = smem_u32(qtag_s[warp]);
+#endif
   const uint32_t zero_u32 = smem_u32(zero_s), rec_u32 = smem_u32(rec_s);
   const uint32_t adxy_u32 = smem_u32(T.adxy), bxy_u32 = smem_u32(T.bxy), list_u32 = smem_u32(T.list);
   const uint8_t* const recs = reinterpret_cast<const uint8_t*>(b.ego_work);
@@ -1589,7 +1603,11 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
       {
         const int head = min((int)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u), npx);
         const int body = (npx - head) & ~15, tail = npx - head - body;
+#ifdef BCG_EGS_EXP_NO_ZERO                  // experiment: no bulk zero stores
+        if (tid == 0 && ego_w < 0) {
+#else
         if (tid == 0) {
+#endif
           for (int o = 0; o < body; o += BCG_EGS_ZERO_BYTES)
             bulk_store(dst + head + o, zero_u32, (uint32_t)min(body - o, BCG_EGS_ZERO_BYTES));
           bulk_commit();
@@ -1631,6 +1649,88 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
           word[rd] = __ldg(occ + (((ty * tiles_x + tx) << 2) + g));
       }
       const uint32_t span_u32 = rec_u32 + slot * BCG_EGO_WORK_BYTES + 128;
+#if BCG_EGS_QUEUE
+      // Walls are thin: in a round only a few of a warp's 32 pieces hold a cell, so expanding them where they were
+      // loaded keeps most lanes idle.  Each warp queues its non-empty pieces (16 bytes + tile / row-group tag) in a
+      // shared ring and expands them 32 at a time, one piece per lane.
+      auto expand = [&](const uint32_t qhead, const int nitems) {
+        uint4 wd = make_uint4(0u, 0u, 0u, 0u);
+        uint32_t tag = 0u;
+        if (lane < nitems) {
+          const uint32_t at = (qhead + (uint32_t)lane) & (BCG_EGS_QCAP - 1);
+          wd = lds_v4(qword_u32 + 16u * at);
+          tag = lds_u32(qtag_u32 + 4u * at);
+        }
+        __syncwarp();                                                            // ring slots are free again
+        const int t = (int)(tag >> 2), gq = (int)(tag & 3u);
+        const int band = (int)(((uint32_t)t * inv) >> 16), jw = t - band * nwx;
+        const int tx = wx0 + jw;
+        const int yr0 = (((by0 + band) << 4) + 4 * gq) - Y0;                      // window row of word .x; 4 | yr0
+        uint32_t bits[4] = {wd.x, wd.y, wd.z, wd.w};
+        uint32_t keep = 0u;
+        if (yr0 >= 0 && yr0 < 8 * nty) {                                          // clip to the tile span of these rows
+          const uint32_t sp = lds_u16(span_u32 + 2 * (yr0 >> 3));
+          const int lo = max(X0 + 16 * (int)(sp & 0xff) - (tx << 5), 0);
+          const int hi = min(X0 + 16 * (int)(sp >> 8) + 15 - (tx << 5), 31);
+          if (lo <= hi) keep = (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
+        }
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          bits[k] &= keep;
+          cnt += __popc(bits[k]);
+        }
+        // list slots: inclusive warp scan of the counts, one shared-memory atomic per warp
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int v = __shfl_up_sync(BCG_FULL, incl, d);
+          if (lane >= d) incl += v;
+        }
+        const int total = __shfl_sync(BCG_FULL, incl, 31);
+        if (total == 0) return;
+        uint32_t base0 = 0u;
+        if (lane == 31) base0 = atomicAdd(&T.count[par], (uint32_t)total);
+        base0 = __shfl_sync(BCG_FULL, base0, 31);
+        const uint32_t base = base0 + (uint32_t)(incl - cnt);
+        if (cnt == 0 || base + (uint32_t)cnt > BCG_EGS_LIST) return;              // overflow: the env goes to the dense kernel
+        uint32_t at = list_u32 + 4u * base;
+        const int key = (yr0 << 16) + ((tx << 5) - X0);          // x_rel of bit 0 may be negative, of a kept bit never
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint32_t w = bits[k];
+          while (w) {
+            const int bit = 31 - __clz(w);                       // order within the list is irrelevant
+            w ^= 1u << bit;
+            sts_u32(at, (uint32_t)(key + (k << 16) + bit));
+            at += 4u;
+          }
+        }
+      };
+      const uint32_t lt_mask = (1u << lane) - 1u;
+      uint32_t qhead = 0u, qtail = 0u;
+#pragma unroll
+      for (int rd = 0; rd < RMAX; ++rd) {
+        const bool nz = (word[rd].x | word[rd].y | word[rd].z | word[rd].w) != 0u;
+        const uint32_t bal = __ballot_sync(BCG_FULL, nz);
+        if (bal == 0u) continue;                                                  // free space
+        if (nz) {
+          const uint32_t at = (qtail + (uint32_t)__popc(bal & lt_mask)) & (BCG_EGS_QCAP - 1);
+          sts_v4(qword_u32 + 16u * at, word[rd]);
+          sts_u32(qtag_u32 + 4u * at, (uint32_t)((((tid >> 2) + rd * TPR) << 2) | g));
+        }
+        qtail += (uint32_t)__popc(bal);
+        if (qtail - qhead >= 32u) {
+          __syncwarp();
+          expand(qhead, 32);
+          qhead += 32u;
+        }
+      }
+      if (qtail != qhead) {
+        __syncwarp();
+        expand(qhead, (int)(qtail - qhead));
+      }
+#else
 #pragma unroll
       for (int rd = 0; rd < RMAX; ++rd) {
         if (!__any_sync(BCG_FULL, (word[rd].x | word[rd].y | word[rd].z | word[rd].w) != 0u)) continue;   // free space
@@ -1668,6 +1768,7 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
           }
         }
       }
+#endif
       if (tid == 0) bulk_wait_all();          // the zeros have landed (they had the whole scan to do so)
     }
     cp_async_wait_group_1();                  // the record needed next iteration has landed
@@ -1701,10 +1802,16 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
         const bool h01 = (uint32_t)((int)a0.x + (int)b1.x - xs) < 1024u && (uint32_t)((int)a0.y + (int)b1.y - ys) < 1024u;
         const bool h11 = (uint32_t)((int)a1.x + (int)b1.x - xs) < 1024u && (uint32_t)((int)a1.y + (int)b1.y - ys) < 1024u;
         uint8_t* const row0 = dst + v0 * ego_w, * const row1 = dst + v1 * ego_w;
+#ifdef BCG_EGS_EXP_NO_HITS                  // experiment: everything but the hit stores (the compiler cannot drop the tests)
+        if (ego_w < 0) {
+#endif
         if (h00) row0[u0] = val;
         if (h10) row0[u1] = val;
         if (h01) row1[u0] = val;
         if (h11) row1[u1] = val;
+#ifdef BCG_EGS_EXP_NO_HITS
+        }
+#endif
       }
     } else if (tid == 0) {
       const int at = atomicAdd(b.ego_list + n, 1);
