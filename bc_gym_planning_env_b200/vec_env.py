@@ -410,13 +410,16 @@ class VecPlanEnv(object):
         self._step_index += 1
         return self.observation(), self.reward, self.done, {}
 
-    def step_host(self, actions_host):
+    def step_host(self, actions_host, images=False):
         """One env step driven from the host: `actions_host` float32 [N, 2] in pinned memory goes to the device, and
         reward (fp64 [N]), done (uint8 [N]) and the compact observation (float32 [N, 12]: delayed pose, delayed
         robot state, time, target index) come back in pinned host buffers -- what a CPU-side policy or logger needs
         every step.  The device->host copies wait only for commit_kernel and run on a side stream while the
         egocentric kernel is still working; the images stay in HBM (`ego_image`) for a GPU-resident consumer.
-        Returns (reward, done, obs_vec) host tensors, valid when this call returns (it synchronises)."""
+        With `images` the egocentric crops (uint8 [N, H, W]) and goal_n_state (float32 [N, 9]) are copied to pinned
+        host memory as well, after the egocentric kernel (N x 15.6 KB per step: the PCIe link then sets the pace).
+        Returns (reward, done, obs_vec) host tensors -- plus (ego_image, goal_n_state) with `images` --, valid when
+        this call returns (it synchronises)."""
         if getattr(self, '_host_io', None) is None:
             n = self.n_envs
             self._host_io = dict(
@@ -440,8 +443,18 @@ class VecPlanEnv(object):
             io['reward'].copy_(self.reward, non_blocking=True)
             io['done'].copy_(self._done_u8, non_blocking=True)
             io['obs'].copy_(self.obs_vec, non_blocking=True)
+        if images:
+            if self.ego_image is None:
+                raise ValueError("this batch was built without the egocentric observation (with_ego=False)")
+            if 'ego_image' not in io:
+                io['ego_image'] = torch.empty(tuple(self.ego_image.shape), dtype=torch.uint8).pin_memory()
+                io['goal_n_state'] = torch.empty(tuple(self.goal_n_state.shape), dtype=torch.float32).pin_memory()
+            io['ego_image'].copy_(self.ego_image, non_blocking=True)
+            io['goal_n_state'].copy_(self.goal_n_state, non_blocking=True)
         side.synchronize()
         main.synchronize()
+        if images:
+            return io['reward'], io['done'], io['obs'], io['ego_image'], io['goal_n_state']
         return io['reward'], io['done'], io['obs']
 
     def reset(self, mask=None):

@@ -46,6 +46,7 @@ def parse_args():
                          "and rasterised on the GPU (bcg_generate_aisles; about 1.2 MB of slots per env)")
     ap.add_argument("--gen-envs", type=int, default=8192, help="envs of the device-generation (reset storm) measurement; 0 = skip")
     ap.add_argument("--e2e-steps", type=int, default=50)
+    ap.add_argument("--e2e-image-steps", type=int, default=5, help="steps of the images-to-host e2e variant; 0 = skip")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--ref-envs", type=int, default=16, help="reference arm: envs advanced per worker per step")
     return ap.parse_args()
@@ -526,6 +527,25 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = n * world * args.e2e_steps / (float(t.item()) * 1e-3)
 
+    # same, with the egocentric crops and goal vectors copied to pinned host memory every step as well (a host-side
+    # consumer of the images): bound by the host link, reported beside the headline e2e
+    e2e_images = None
+    if not args.no_ego and args.e2e_image_steps > 0:
+        env.step_host(h_actions[0], images=True)              # allocates the pinned image buffer
+        barrier()
+        e0.record()
+        for k in range(args.e2e_image_steps):
+            env.step_host(h_actions[k % n_sets], images=True)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        img_bytes = env.ego_image.numel() + env.goal_n_state.numel() * 4
+        e2e_images = {"value": n * world * args.e2e_image_steps / (float(t.item()) * 1e-3), "unit": UNIT,
+                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h + img_bytes, "steps": args.e2e_image_steps,
+                      "d2h_gbs": (d2h + img_bytes) * args.e2e_image_steps / (float(t.item()) * 1e-3) / 1e9}
+
     if rank == 0:
         cpu = cpu_baseline_sample(args.cpu_seconds, not args.no_ego) if args.gpus == 1 else None
         if generation is not None and args.gpus == 1:
@@ -538,7 +558,9 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "VecPlanEnv.step_host: pinned-host actions in; reward f64, done u8 and the 12-float compact "
                             "observation out to pinned host memory every step (copies overlap the egocentric kernel); "
-                            "egocentric images stay in HBM for a GPU-resident policy"},
+                            "egocentric images stay in HBM for a GPU-resident policy; `with_images_to_host` = the same "
+                            "call with every crop and goal vector copied to pinned host memory too (host-link bound)",
+                    "with_images_to_host": e2e_images},
             "gpu_launches": args.steps * (3 if args.no_ego else (5 if sparse else 4)) * world,
             "ego_dense_fallback_envs_last_step": None if args.no_ego else dense_envs,
             "roofline": dominant,

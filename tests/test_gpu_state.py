@@ -120,5 +120,11 @@ def test_step_host_returns_the_step_results_in_pinned_memory():
         assert torch.equal(reward, r2.cpu()) and torch.equal(done.bool(), d2.cpu())
         assert torch.equal(obs, b.obs_vec.cpu())
         assert torch.equal(a.ego_image, b.ego_image)
+    host = actions[:, 40].contiguous().pin_memory()
+    reward, done, obs, image, goal = a.step_host(host, images=True)   # crops and goal vectors to the host as well
+    b.step(host.cuda())
+    assert image.is_pinned() and goal.is_pinned()
+    assert torch.equal(reward, b.reward.cpu()) and torch.equal(image, b.ego_image.cpu())
+    assert torch.equal(goal, b.goal_n_state.cpu())
     with pytest.raises(ValueError):
         a.step_host(actions[:, 0].double())
