@@ -35,7 +35,7 @@ class BcgMapDesc(C.Structure):
         ("height", C.c_int32), ("width", C.c_int32), ("pitch", C.c_int32),
         ("tiles_x", C.c_int32), ("tiles_y", C.c_int32), ("flags", C.c_int32),
         ("cell_tile_off", C.c_int64), ("ctiles_x", C.c_int32), ("ctiles_y", C.c_int32),
-        ("occupied", C.c_int32), ("reserved", C.c_int32),
+        ("occupied", C.c_int32), ("sum_off", C.c_int32),
     ]
 
 
@@ -67,7 +67,7 @@ class BcgBatch(C.Structure):
         ("map_tmaps", C.c_void_p), ("tmap_n_widths", C.c_int32), ("tmap_box_h", C.c_int32),
         ("tmap_box_w", C.c_int32 * 4),
         ("cell_tile_arena", C.c_void_p), ("occ_tile_arena", C.c_void_p), ("ego_list", C.c_void_p),
-        ("status", C.c_void_p), ("stats", C.c_void_p),
+        ("occ_sum_arena", C.c_void_p), ("status", C.c_void_p), ("stats", C.c_void_p),
     ]
 
 

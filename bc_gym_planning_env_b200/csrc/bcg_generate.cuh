@@ -95,6 +95,7 @@ struct MapLayout {
   uint8_t* data;       // uint8 rows
   uint32_t* tiles;     // lethal tile plane
   uint32_t* occ;       // occupancy plane (same layout; may be null)
+  uint32_t* sum;       // tile summary of the occupancy plane: [tiles_y][(tiles_x + 31) / 32] words (may be null)
   uint8_t* ctiles;     // cell tiles
   int pitch, rows, tiles_x, ctiles_x;
 };
@@ -124,12 +125,21 @@ __device__ __forceinline__ void draw_wall(const MapLayout& m, int x0, int y0, in
     m.data[(int64_t)y * m.pitch + x] = value;
     m.ctiles[(((int64_t)(y >> 3) * m.ctiles_x + (x >> 4)) << 7) + ((y & 7) << 4) + (x & 15)] = value;
     const int64_t widx = (((int64_t)(y >> 4) * m.tiles_x + (x >> 5)) << 4) + (y & 15);
+    // tile summary: walls are the only cells of a generated world and all of them are erased before any is drawn,
+    // so a tile an erased pixel lies in is empty by the time the drawing starts
+    // Only the pixel with which the line enters a tile touches the summary (x grows along the line, y moves by sy:
+    // a tile is entered through its column 0, its row 0 / 15, the map's last row, or at the line's first pixel).
+    const bool enters = j == 0 || (x & 31) == 0 || (y & 15) == (sy > 0 ? 0 : 15) || y == m.rows - 1;
+    uint32_t* const sword = (m.sum && enters) ? m.sum + (y >> 4) * ((m.tiles_x + 31) >> 5) + (x >> 10) : nullptr;
+    const uint32_t sbit = 1u << ((x >> 5) & 31);
     if (value == 254) {
       atomicOr(m.tiles + widx, 1u << (x & 31));
       if (m.occ) atomicOr(m.occ + widx, 1u << (x & 31));
+      if (sword) atomicOr(sword, sbit);                  // result unused: a fire-and-forget reduction
     } else {
       atomicAnd(m.tiles + widx, ~(1u << (x & 31)));
       if (m.occ) atomicAnd(m.occ + widx, ~(1u << (x & 31)));
+      if (sword) atomicAnd(sword, ~sbit);
     }
   }
 }

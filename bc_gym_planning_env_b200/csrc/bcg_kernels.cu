@@ -801,6 +801,7 @@ __global__ void __launch_bounds__(256) generate_aisles_kernel(const BcgParams p,
   m.data = const_cast<uint8_t*>(b.map_arena) + md->data_off;
   m.tiles = const_cast<uint32_t*>(b.tile_arena) + md->tile_off;
   m.occ = b.occ_tile_arena ? const_cast<uint32_t*>(b.occ_tile_arena) + md->tile_off : nullptr;
+  m.sum = (b.occ_tile_arena && b.occ_sum_arena) ? const_cast<uint32_t*>(b.occ_sum_arena) + md->sum_off : nullptr;
   m.ctiles = const_cast<uint8_t*>(b.cell_tile_arena) + md->cell_tile_off;
   // ---- erase what the slot holds (with the layout it was drawn in) -------------------------------------------
   if (gs->valid) {
@@ -898,6 +899,7 @@ __global__ void __launch_bounds__(128) generate_minis_kernel(const BcgParams p, 
   m.data = const_cast<uint8_t*>(b.map_arena) + md->data_off;
   m.tiles = const_cast<uint32_t*>(b.tile_arena) + md->tile_off;
   m.occ = b.occ_tile_arena ? const_cast<uint32_t*>(b.occ_tile_arena) + md->tile_off : nullptr;
+  m.sum = (b.occ_tile_arena && b.occ_sum_arena) ? const_cast<uint32_t*>(b.occ_sum_arena) + md->sum_off : nullptr;
   m.ctiles = const_cast<uint8_t*>(b.cell_tile_arena) + md->cell_tile_off;
   MiniRng rng = {p.seed, p.env_id_base + (uint64_t)e, draw_index, 0u};
   bool accepted = false;
@@ -1055,6 +1057,7 @@ __global__ void __launch_bounds__(256) tiles_kernel(const BcgBatch b, const int 
   const int words = m.tiles_x * m.tiles_y * 16;
   uint32_t* dst = const_cast<uint32_t*>(b.tile_arena) + m.tile_off;
   uint32_t* occ = b.occ_tile_arena ? const_cast<uint32_t*>(b.occ_tile_arena) + m.tile_off : nullptr;
+  uint32_t* sum = (occ && b.occ_sum_arena) ? const_cast<uint32_t*>(b.occ_sum_arena) + m.sum_off : nullptr;
   const uint8_t* src = b.map_arena + m.data_off;
   bool other = false;                      // a cell that is neither free (0) nor lethal (254)
   int occupied = 0;
@@ -1090,6 +1093,10 @@ __global__ void __launch_bounds__(256) tiles_kernel(const BcgBatch b, const int 
     }
     dst[w] = bits;
     if (occ) occ[w] = obits;
+    if (sum && obits) {                      // the tile holds a cell (rows race for the same bit: test before the atomic)
+      uint32_t* const sw = sum + ty * ((m.tiles_x + 31) >> 5) + (tx >> 5);
+      if ((*(volatile uint32_t*)sw & (1u << (tx & 31))) == 0u) atomicOr(sw, 1u << (tx & 31));
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) occupied += __shfl_xor_sync(BCG_FULL, occupied, o);
@@ -1100,7 +1107,14 @@ __global__ void __launch_bounds__(256) tiles_kernel(const BcgBatch b, const int 
 
 __global__ void __launch_bounds__(256) zero_occupied_kernel(const BcgBatch b, const int first, const int count) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < count) const_cast<BcgMapDesc*>(b.maps)[first + k].occupied = 0;
+  if (k >= count) return;
+  BcgMapDesc* m = const_cast<BcgMapDesc*>(b.maps) + first + k;
+  m->occupied = 0;
+  if (b.occ_tile_arena && b.occ_sum_arena) {            // tiles_kernel only sets summary bits
+    uint32_t* sum = const_cast<uint32_t*>(b.occ_sum_arena) + m->sum_off;
+    const int words = m->tiles_y * ((m->tiles_x + 31) >> 5);
+    for (int i = 0; i < words; ++i) sum[i] = 0u;
+  }
 }
 
 __global__ void __launch_bounds__(256) cell_tiles_kernel(const BcgBatch b, const int first) {
@@ -1508,11 +1522,11 @@ __global__ void __launch_bounds__(BCG_EGT_THREADS, BCG_EGT_CTAS) ego_tiles_kerne
 #define BCG_EGS_REC_SLOTS 4          // record ring (power of two, > the prefetch distance 3)
 #endif
 #define BCG_EGS_MAX_TILES 128        // 32 x 16 bit tiles a window may span (sparse path); more -> dense kernel
-#ifndef BCG_EGS_QUEUE
-#define BCG_EGS_QUEUE 1              // 1: non-empty 16-byte occupancy pieces are queued per warp and expanded 32 at a time
-#endif
 #ifndef BCG_EGS_ZERO_BYTES
-#define BCG_EGS_ZERO_BYTES (BCG_EGS_QUEUE ? 2048 : 4096)      // shared page of zeros the bulk stores read
+#define BCG_EGS_ZERO_BYTES 2048      // shared page of zeros the bulk stores read
+#endif
+#ifndef BCG_EGS_SUM_ROUNDS
+#define BCG_EGS_SUM_ROUNDS 4         // with the tile summary: rounds of 16 non-empty tiles loaded per pass
 #endif
 #define BCG_EGS_QCAP 64              // ring slots per warp: a push adds <= 32 to <= 31 left over
 struct EgoSparseTab {
@@ -1531,6 +1545,9 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
 __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -1548,6 +1565,7 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+template <bool SUM>
 __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kernel(const BcgParams p, const BcgBatch b,
                                                                                    uint8_t* __restrict__ image) {
   __shared__ __align__(128) uint8_t zero_s[BCG_EGS_ZERO_BYTES];
@@ -1555,11 +1573,10 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
   __shared__ __align__(128) uint8_t rec_s[BCG_EGS_REC_SLOTS * BCG_EGO_WORK_BYTES];
   constexpr int NT = BCG_EGS_THREADS;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-#if BCG_EGS_QUEUE
   __shared__ __align__(16) uint4 qword_s[NT / 32][BCG_EGS_QCAP];
   __shared__ uint32_t qtag_s[NT / 32][BCG_EGS_QCAP];
-  const uint32_t qword_u32 = smem_u32(qword_s[warp]), qtag_u32 = smem_u32(qtag_s[warp]);
-#endif
+  __shared__ uint16_t tlist_s[SUM ? BCG_EGS_MAX_TILES : 2];   // non-empty tiles of the window (every warp writes the same values)
+  const uint32_t qword_u32 = smem_u32(qword_s[warp]), qtag_u32 = smem_u32(qtag_s[warp]), tlist_u32 = smem_u32(tlist_s);
   const uint32_t zero_u32 = smem_u32(zero_s), rec_u32 = smem_u32(rec_s);
   const uint32_t adxy_u32 = smem_u32(T.adxy), bxy_u32 = smem_u32(T.bxy), list_u32 = smem_u32(T.list);
   const uint8_t* const recs = reinterpret_cast<const uint8_t*>(b.ego_work);
@@ -1597,7 +1614,7 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
     // maps with more than one cell in 20 occupied (filled regions, inflation gradients) overflow the cell list in
     // almost every window: they go straight to the dense kernel instead of paying for a scan that is thrown away
     const bool dense_map = r->dense_map != 0;           // decided by the record writer, which holds the map descriptor
-    const bool try_sparse = mode == BCG_EGO_MODE_TILES && ntile <= BCG_EGS_MAX_TILES && !dense_map;
+    const bool try_sparse = mode == BCG_EGO_MODE_TILES && ntile <= BCG_EGS_MAX_TILES && !dense_map && (!SUM || (nby <= 32 && nwx <= 32));
     if (try_sparse) {
       // ---- 1. zero the crop in global memory ----------------------------------------------------------------------
       {
@@ -1628,31 +1645,17 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
                                __double2int_rn((A.a22 * t + A.b2) * 1024) + 512 - (Y0 << 10));
         }
       }
-      // ---- 2. occupied cells of the window: four lanes per 32 x 16 bit tile (a 16-byte load = 4 rows each), eight
-      // tiles per warp and round.  All loads of a thread are issued before the first is used (one DRAM round trip per
-      // env instead of one per round) ---------------------------------------------------------------------------------
+      // ---- 2. occupied cells of the window: four lanes per 32 x 16 bit tile (a 16-byte load = 4 rows each).  All loads
+      // of a thread are issued before the first is used (one DRAM round trip per env instead of one per round).
+      // Walls are thin: only a few of a warp's 32 pieces hold a cell, so expanding them where they were loaded would
+      // keep most lanes idle.  Each warp queues its non-empty pieces (16 bytes + band / column / row-group tag) in a
+      // shared ring and expands them 32 at a time, one piece per lane. ------------------------------------------------
       const BcgMapDesc* md = b.maps + r->map_id;
       const int tiles_x = md->tiles_x, tiles_y = md->tiles_y;
       const uint4* occ = reinterpret_cast<const uint4*>(b.occ_tile_arena + md->tile_off);
       const int g = lane & 3;                                                     // rows 4 g .. 4 g + 3 of the tile
-      const uint32_t inv = (65536u + (uint32_t)nwx - 1u) / (uint32_t)nwx;         // t / nwx == (t * inv) >> 16 for t < 4096
       constexpr int TPR = NT / 4;                                                // tiles per round
-      constexpr int RMAX = (BCG_EGS_MAX_TILES + TPR - 1) / TPR;
-      uint4 word[RMAX];
-#pragma unroll
-      for (int rd = 0; rd < RMAX; ++rd) {
-        const int t = (tid >> 2) + rd * TPR;
-        const int band = (int)(((uint32_t)t * inv) >> 16), jw = t - band * nwx;
-        const int ty = by0 + band, tx = wx0 + jw;
-        word[rd] = make_uint4(0u, 0u, 0u, 0u);
-        if (t < ntile && (unsigned)ty < (unsigned)tiles_y && (unsigned)tx < (unsigned)tiles_x)
-          word[rd] = __ldg(occ + (((ty * tiles_x + tx) << 2) + g));
-      }
       const uint32_t span_u32 = rec_u32 + slot * BCG_EGO_WORK_BYTES + 128;
-#if BCG_EGS_QUEUE
-      // Walls are thin: in a round only a few of a warp's 32 pieces hold a cell, so expanding them where they were
-      // loaded keeps most lanes idle.  Each warp queues its non-empty pieces (16 bytes + tile / row-group tag) in a
-      // shared ring and expands them 32 at a time, one piece per lane.
       auto expand = [&](const uint32_t qhead, const int nitems) {
         uint4 wd = make_uint4(0u, 0u, 0u, 0u);
         uint32_t tag = 0u;
@@ -1662,8 +1665,7 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
           tag = lds_u32(qtag_u32 + 4u * at);
         }
         __syncwarp();                                                            // ring slots are free again
-        const int t = (int)(tag >> 2), gq = (int)(tag & 3u);
-        const int band = (int)(((uint32_t)t * inv) >> 16), jw = t - band * nwx;
+        const int band = (int)(tag >> 8), jw = (int)((tag >> 2) & 63u), gq = (int)(tag & 3u);
         const int tx = wx0 + jw;
         const int yr0 = (((by0 + band) << 4) + 4 * gq) - Y0;                      // window row of word .x; 4 | yr0
         uint32_t bits[4] = {wd.x, wd.y, wd.z, wd.w};
@@ -1709,15 +1711,14 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
       };
       const uint32_t lt_mask = (1u << lane) - 1u;
       uint32_t qhead = 0u, qtail = 0u;
-#pragma unroll
-      for (int rd = 0; rd < RMAX; ++rd) {
-        const bool nz = (word[rd].x | word[rd].y | word[rd].z | word[rd].w) != 0u;
+      auto push = [&](const uint4& w, const uint32_t tag) {
+        const bool nz = (w.x | w.y | w.z | w.w) != 0u;
         const uint32_t bal = __ballot_sync(BCG_FULL, nz);
-        if (bal == 0u) continue;                                                  // free space
+        if (bal == 0u) return;                                                    // free space
         if (nz) {
           const uint32_t at = (qtail + (uint32_t)__popc(bal & lt_mask)) & (BCG_EGS_QCAP - 1);
-          sts_v4(qword_u32 + 16u * at, word[rd]);
-          sts_u32(qtag_u32 + 4u * at, (uint32_t)((((tid >> 2) + rd * TPR) << 2) | g));
+          sts_v4(qword_u32 + 16u * at, w);
+          sts_u32(qtag_u32 + 4u * at, tag);
         }
         qtail += (uint32_t)__popc(bal);
         if (qtail - qhead >= 32u) {
@@ -1725,50 +1726,82 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
           expand(qhead, 32);
           qhead += 32u;
         }
+      };
+      if constexpr (SUM) {
+        // (a) which tiles of the window hold a cell at all: lane <-> band of 16 rows, one or two words of the map's tile
+        // summary each (every warp computes the same list: no barrier, and the few words hit L1 the second time)
+        const uint32_t* const sum = b.occ_sum_arena + md->sum_off;
+        const int sw = (tiles_x + 31) >> 5;
+        uint32_t tmask = 0u;
+        {
+          const int ty = by0 + lane, w0 = wx0 >> 5;                               // wx0 may be negative: w0 = -1
+          if (lane < nby && (unsigned)ty < (unsigned)tiles_y) {
+            const uint32_t lo = (unsigned)w0 < (unsigned)sw ? __ldg(sum + ty * sw + w0) : 0u;
+            const uint32_t hi = (unsigned)(w0 + 1) < (unsigned)sw ? __ldg(sum + ty * sw + w0 + 1) : 0u;
+            tmask = (uint32_t)((((uint64_t)hi << 32) | lo) >> (wx0 & 31)) & ((1u << nwx) - 1u);
+          }
+        }
+        // (b) the list of those tiles (band << 6 | column), in band order: inclusive warp scan of the per-band counts
+        int tincl = __popc(tmask);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int v = __shfl_up_sync(BCG_FULL, tincl, d);
+          if (lane >= d) tincl += v;
+        }
+        const int ntl = __shfl_sync(BCG_FULL, tincl, 31);                         // <= ntile <= BCG_EGS_MAX_TILES
+        {
+          uint32_t at = tlist_u32 + 2u * (uint32_t)(tincl - __popc(tmask));
+          uint32_t m2 = tmask;
+          while (m2) {
+            const int jw = __ffs((int)m2) - 1;
+            m2 &= m2 - 1u;
+            sts_u16(at, (uint32_t)((lane << 6) | jw));
+            at += 2u;
+          }
+        }
+        __syncwarp();
+        // (c) their pieces, BCG_EGS_SUM_ROUNDS x 16 tiles per pass (one pass unless the window is crowded)
+        constexpr int RS = BCG_EGS_SUM_ROUNDS;
+        for (int base = 0; base < ntl; base += RS * TPR) {
+          uint4 word[RS];
+          uint32_t tag[RS];
+#pragma unroll
+          for (int rd = 0; rd < RS; ++rd) {
+            const int i = base + (tid >> 2) + rd * TPR;
+            word[rd] = make_uint4(0u, 0u, 0u, 0u);
+            tag[rd] = 0u;
+            if (i < ntl) {
+              const uint32_t code = lds_u16(tlist_u32 + 2u * (uint32_t)i);
+              const int band = (int)(code >> 6), jw = (int)(code & 63u);
+              tag[rd] = (code << 2) | (uint32_t)g;
+              word[rd] = __ldg(occ + ((((by0 + band) * tiles_x + wx0 + jw) << 2) + g));
+            }
+          }
+#pragma unroll
+          for (int rd = 0; rd < RS; ++rd) push(word[rd], tag[rd]);
+        }
+      } else {
+        const uint32_t inv = (65536u + (uint32_t)nwx - 1u) / (uint32_t)nwx;       // t / nwx == (t * inv) >> 16 for t < 4096
+        constexpr int RMAX = (BCG_EGS_MAX_TILES + TPR - 1) / TPR;
+        uint4 word[RMAX];
+        uint32_t tag[RMAX];
+#pragma unroll
+        for (int rd = 0; rd < RMAX; ++rd) {
+          const int t = (tid >> 2) + rd * TPR;
+          const int band = (int)(((uint32_t)t * inv) >> 16), jw = t - band * nwx;
+          const int ty = by0 + band, tx = wx0 + jw;
+          word[rd] = make_uint4(0u, 0u, 0u, 0u);
+          tag[rd] = (uint32_t)((band << 8) | (jw << 2) | g);
+          if (t < ntile && (unsigned)ty < (unsigned)tiles_y && (unsigned)tx < (unsigned)tiles_x)
+            word[rd] = __ldg(occ + (((ty * tiles_x + tx) << 2) + g));
+        }
+#pragma unroll
+        for (int rd = 0; rd < RMAX; ++rd) push(word[rd], tag[rd]);
       }
       if (qtail != qhead) {
         __syncwarp();
         expand(qhead, (int)(qtail - qhead));
       }
-#else
-#pragma unroll
-      for (int rd = 0; rd < RMAX; ++rd) {
-        if (!__any_sync(BCG_FULL, (word[rd].x | word[rd].y | word[rd].z | word[rd].w) != 0u)) continue;   // free space
-        const int t = (tid >> 2) + rd * TPR;
-        const int band = (int)(((uint32_t)t * inv) >> 16), jw = t - band * nwx;
-        const int tx = wx0 + jw;
-        const int yr0 = (((by0 + band) << 4) + 4 * g) - Y0;                       // window row of word .x; 4 | yr0
-        uint32_t bits[4] = {word[rd].x, word[rd].y, word[rd].z, word[rd].w};
-        uint32_t keep = 0u;
-        if (yr0 >= 0 && yr0 < 8 * nty) {                                          // clip to the tile span of these rows
-          const uint32_t sp = lds_u16(span_u32 + 2 * (yr0 >> 3));
-          const int lo = max(X0 + 16 * (int)(sp & 0xff) - (tx << 5), 0);
-          const int hi = min(X0 + 16 * (int)(sp >> 8) + 15 - (tx << 5), 31);
-          if (lo <= hi) keep = (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
-        }
-        int cnt = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          bits[k] &= keep;
-          cnt += __popc(bits[k]);
-        }
-        if (cnt == 0) continue;                                  // walls are thin: a few lanes per round hold cells,
-        const uint32_t base = atomicAdd(&T.count[par], (uint32_t)cnt);   // so each reserves its own list slots
-        if (base + (uint32_t)cnt > BCG_EGS_LIST) continue;       // overflow: the env goes to the dense kernel anyway
-        uint32_t at = list_u32 + 4u * base;
-        const int key = (yr0 << 16) + ((tx << 5) - X0);          // x_rel of bit 0 may be negative, of a kept bit never
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint32_t w = bits[k];
-          while (w) {
-            const int bit = 31 - __clz(w);                       // order within the list is irrelevant
-            w ^= 1u << bit;
-            sts_u32(at, (uint32_t)(key + (k << 16) + bit));
-            at += 4u;
-          }
-        }
-      }
-#endif
       if (tid == 0) bulk_wait_all();          // the zeros have landed (they had the whole scan to do so)
     }
     cp_async_wait_group_1();                  // the record needed next iteration has landed
@@ -2123,7 +2156,8 @@ static int launch_ego_sparse(const BcgParams* p, const BcgBatch* b, uint8_t* ego
   if (int rc = sm_count_of_current_device(&sms)) return rc;
   BCG_CHECK_CUDA(cudaMemsetAsync(b->ego_list + b->n_envs, 0, sizeof(int32_t), s));
   const int grid = b->n_envs < BCG_EGS_CTAS * sms ? b->n_envs : BCG_EGS_CTAS * sms;
-  ego_sparse_kernel<<<grid, BCG_EGS_THREADS, 0, s>>>(*p, *b, ego_image);
+  if (b->occ_sum_arena) ego_sparse_kernel<true><<<grid, BCG_EGS_THREADS, 0, s>>>(*p, *b, ego_image);
+  else ego_sparse_kernel<false><<<grid, BCG_EGS_THREADS, 0, s>>>(*p, *b, ego_image);
   BCG_CHECK_CUDA(cudaGetLastError());
   return launch_ego_dense(p, b, ego_image, b->ego_list, s);
 }

@@ -84,10 +84,15 @@ class _VecSlotEnv(VecPlanEnv):
         descs = (nat.BcgMapDesc * n)()
         pdescs = (nat.BcgPathDesc * n)()
         path_slot = 5 * self._path_pitch + 3 * self._chunk_pitch
+        # tile summary of a slot: at most one word per tile row and 32 tile columns, i.e. never more words than tiles
+        sum_slot_words = self._tile_slot_words // 16
+        if n * sum_slot_words >= 2 ** 31:
+            raise ValueError("tile summaries of this batch exceed the 32-bit offsets of BcgMapDesc.sum_off")
         for e in range(n):
             descs[e].data_off = e * self._slot_bytes
             descs[e].cell_tile_off = e * self._slot_bytes
             descs[e].tile_off = e * self._tile_slot_words
+            descs[e].sum_off = e * sum_slot_words
             pdescs[e].off = e * path_slot
             pdescs[e].chunk_off = e * path_slot + 5 * self._path_pitch
             pdescs[e].pitch, pdescs[e].chunk_pitch = self._path_pitch, self._chunk_pitch
@@ -95,6 +100,7 @@ class _VecSlotEnv(VecPlanEnv):
         self.cell_tile_arena = torch.zeros(n * self._slot_bytes, dtype=torch.uint8, device=dev)
         self.tile_arena = torch.zeros(n * self._tile_slot_words, dtype=torch.int32, device=dev)
         self.occ_tile_arena = torch.zeros(n * self._tile_slot_words, dtype=torch.int32, device=dev)
+        self.occ_sum_arena = torch.zeros(n * sum_slot_words, dtype=torch.int32, device=dev)
         self.path_arena = torch.zeros(n * path_slot, dtype=torch.float64, device=dev)
         self.map_descs = self._to_device(np.frombuffer(bytes(descs), dtype=np.uint8).copy())
         self.path_descs = self._to_device(np.frombuffer(bytes(pdescs), dtype=np.uint8).copy())

@@ -7,6 +7,7 @@ include/bcg_b200.h), costmaps and refined paths in arenas with per-map / per-pat
 PyTorch is used for device memory, streams and (elsewhere) torch.distributed only.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -188,7 +189,7 @@ class VecPlanEnv(object):
 
     def _upload_maps(self, costmaps, private_copies):
         descs = (nat.BcgMapDesc * len(costmaps))()
-        data_off, tile_off, ctile_off = 0, 0, 0
+        data_off, tile_off, ctile_off, sum_off = 0, 0, 0, 0
         for k, cm in enumerate(costmaps):
             data = cm.get_data()
             if data.dtype != np.uint8 or data.ndim != 2:
@@ -204,7 +205,8 @@ class VecPlanEnv(object):
             d.flags = nat.MAP_ONLY_LETHAL                   # cleared on device when a cell is neither 0 nor 254
             d.origin_x, d.origin_y = float(cm.get_origin()[0]), float(cm.get_origin()[1])
             d.ctiles_x, d.ctiles_y = d.pitch // 16, (h + 7) // 8
-            d.data_off, d.tile_off, d.cell_tile_off = data_off, tile_off, ctile_off
+            d.data_off, d.tile_off, d.cell_tile_off, d.sum_off = data_off, tile_off, ctile_off, sum_off
+            sum_off += d.tiles_y * ((d.tiles_x + 31) // 32)
             data_off += _round_up(h * d.pitch, 128)
             tile_off += d.tiles_x * d.tiles_y * 16
             ctile_off += d.ctiles_x * d.ctiles_y * 128
@@ -213,7 +215,7 @@ class VecPlanEnv(object):
             d = descs[k]
             view = arena[d.data_off:d.data_off + d.height * d.pitch].reshape(d.height, d.pitch)
             view[:, :d.width] = cm.get_data()
-        pool_bytes, pool_words, pool_ctile_bytes = data_off, tile_off, ctile_off
+        pool_bytes, pool_words, pool_ctile_bytes, pool_sum_words = data_off, tile_off, ctile_off, sum_off
         map_arena = self._to_device(arena)
         ids = self._map_ids_host
         if private_copies:
@@ -232,10 +234,12 @@ class VecPlanEnv(object):
                 table[e].data_off += int(copy_idx[e]) * pool_bytes
                 table[e].tile_off += int(copy_idx[e]) * pool_words
                 table[e].cell_tile_off += int(copy_idx[e]) * pool_ctile_bytes
+                table[e].sum_off += int(copy_idx[e]) * pool_sum_words
             descs = table
             ids = np.arange(self.n_envs)
             pool_words *= copies
             pool_ctile_bytes *= copies
+            pool_sum_words *= copies
         self._map_descs_host = descs
         self.map_arena = map_arena
         # TMA tensor maps for the egocentric kernel's source-window staging: three box-width classes
@@ -244,12 +248,16 @@ class VecPlanEnv(object):
         widths = (C.c_int32 * len(self._tmap_widths))(*self._tmap_widths)
         tm = np.zeros(len(descs) * len(self._tmap_widths) * 128, dtype=np.uint8)
         self.tile_arena = torch.zeros(max(pool_words, 1), dtype=torch.int32, device=self.device)
-        self.cell_tile_arena = self.occ_tile_arena = None
+        self.cell_tile_arena = self.occ_tile_arena = self.occ_sum_arena = None
         if self.ego_staging == 'tiles':
             self.cell_tile_arena = torch.empty(max(pool_ctile_bytes, 128), dtype=torch.uint8, device=self.device)
         if self.ego_staging == 'tiles' and getattr(self, '_ego_sparse', True):
             # occupancy plane (cell != 0) for the sparse egocentric kernel: same layout as the lethal plane
             self.occ_tile_arena = torch.zeros(max(pool_words, 1), dtype=torch.int32, device=self.device)
+            if pool_sum_words >= 2 ** 31:
+                raise ValueError("tile summaries of this batch exceed the 32-bit offsets of BcgMapDesc.sum_off")
+            # one bit per 32 x 16 tile of the occupancy plane: the sparse kernel skips the empty tiles of a window
+            self.occ_sum_arena = torch.zeros(max(pool_sum_words, 1), dtype=torch.int32, device=self.device)
         if self.ego_staging == 'tma':
             nat.check(nat.lib().bcg_encode_map_tensor_maps(descs, len(descs), C.c_void_p(map_arena.data_ptr()), widths,
                                                            len(self._tmap_widths), self._tmap_box_h,
@@ -347,6 +355,9 @@ class VecPlanEnv(object):
         if getattr(self, 'occ_tile_arena', None) is not None:
             self._ego_list = torch.zeros(self.n_envs + 4, dtype=torch.int32, device=self.device)
             b.occ_tile_arena, b.ego_list = self.occ_tile_arena.data_ptr(), self._ego_list.data_ptr()
+            # BCG_EGO_SUMMARY=0: A/B switch, the sparse kernel then scans every tile of a window
+            if getattr(self, 'occ_sum_arena', None) is not None and os.environ.get("BCG_EGO_SUMMARY", "1") != "0":
+                b.occ_sum_arena = self.occ_sum_arena.data_ptr()
         if self.use_tma:
             b.map_tmaps, b.tmap_n_widths, b.tmap_box_h = self.map_tmaps.data_ptr(), len(self._tmap_widths), self._tmap_box_h
             for j, w in enumerate(self._tmap_widths):

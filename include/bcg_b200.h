@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BCG_ABI_VERSION 4
+#define BCG_ABI_VERSION 5
 
 /* error codes */
 #define BCG_OK 0
@@ -130,7 +130,10 @@ typedef struct BcgMapDesc {
   int32_t ctiles_x, ctiles_y; /* 16 px x 8 rows per 128-byte cell tile: pitch / 16, ceil(height / 8)     */
   int32_t occupied;         /* cells != 0, counted by bcg_build_lethal_tiles: maps with more than 1 cell in 20
                                occupied skip the sparse egocentric kernel (their windows overflow its list) */
-  int32_t reserved;
+  int32_t sum_off;          /* uint32 offset of the map's tile summary in BcgBatch.occ_sum_arena: [tiles_y][(tiles_x + 31) / 32]
+                               words, bit tx & 31 of word [ty][tx >> 5] set when tile (tx, ty) of the occupancy plane
+                               holds a cell (a clear bit promises an empty tile; set by the host, kept by the
+                               generators)                                                                          */
 } BcgMapDesc;
 
 /* one refined path: fp64 SoA rows x,y,th,cos(th),sin(th), each `pitch` long, then chunk bounds */
@@ -198,6 +201,9 @@ typedef struct BcgBatch {
                             path: zero the crop, then scatter only the occupied source cells of its window   */
   int32_t* ego_list;      /* optional scratch [n_envs + 4]: envs whose window holds too many occupied cells
                             for the sparse path, handed to the dense cell-tile kernel (count at [n_envs])   */
+  const uint32_t* occ_sum_arena; /* optional: one bit per tile of the occupancy plane (BcgMapDesc.sum_off), filled by
+                            bcg_build_lethal_tiles and kept by the generators; must start out zero.  With it the sparse
+                            egocentric kernel loads only the non-empty tiles of a window                              */
   uint32_t* status; /* [BCG_STATUS_WORDS] */
   double* stats;    /* [BCG_STATS_WORDS]  */
 } BcgBatch;

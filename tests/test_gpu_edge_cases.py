@@ -148,3 +148,41 @@ def test_malformed_calls_return_error_codes():
         env.step(np.zeros((env.n_envs + 1, 2), dtype=np.float32))
     with pytest.raises(ValueError):
         VecPlanEnv([], [], EnvParams())
+
+
+def _summary_is_exact(env, desc):
+    """Tile summary bit (tx, ty) == tile (tx, ty) of the occupancy plane holds a cell."""
+    tx, ty = desc.tiles_x, desc.tiles_y
+    occ = env.occ_tile_arena[desc.tile_off:desc.tile_off + tx * ty * 16].view(ty, tx, 16)
+    want = (occ != 0).any(dim=2).cpu().numpy()
+    sw = (tx + 31) // 32
+    words = env.occ_sum_arena[desc.sum_off:desc.sum_off + ty * sw].view(ty, sw).cpu().numpy().astype(np.uint32)
+    got = ((words[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).reshape(ty, sw * 32)
+    assert not got[:, tx:].any()
+    return np.array_equal(got[:, :tx].astype(bool), want)
+
+
+def test_tile_summary_follows_the_occupancy_plane():
+    """The one-bit-per-tile summary the sparse egocentric kernel trusts: exact for uploaded maps (shared and private
+    copies) and for device-generated worlds after repeated regeneration in place."""
+    from bc_gym_planning_env_b200.envs.synth_turn_env import random_aisle_pool
+    from bc_gym_planning_env_b200.vec_aisle_env import VecRandomAisleTurnEnv, VecRandomMiniEnv
+    ep = EnvParams()
+    costmaps, paths = random_aisle_pool(6, 77, ep)
+    costmaps = list(costmaps) + [CostMap2D(m, 0.03, o.astype(np.float64)) for m, o, _ in _tiny_worlds()]
+    paths = list(paths) + [p for _, _, p in _tiny_worlds()]
+    for private in (False, True):
+        env = VecPlanEnv(costmaps, paths, ep, n_envs=23, noise_parameters=None, with_ego=True, private_map_copies=private)
+        assert env.occ_sum_arena is not None
+        for d in env._map_descs_host:
+            assert _summary_is_exact(env, d)
+    for cls in (VecRandomAisleTurnEnv, VecRandomMiniEnv):
+        genv = cls(48, seed=11, with_ego=True) if cls is VecRandomMiniEnv else cls(48, ep, seed=11, with_ego=True)
+        for rep in range(4):
+            genv.generate()
+            mask = torch.zeros(48, dtype=torch.bool, device="cuda")
+            mask[rep::3] = True
+            genv.generate(mask)
+            for e in range(48):
+                assert _summary_is_exact(genv, genv._map_desc(e)), (cls.__name__, rep, e)
+        genv.check_status()
