@@ -1513,10 +1513,10 @@ __global__ void __launch_bounds__(BCG_EGT_THREADS, BCG_EGT_CTAS) ego_tiles_kerne
 #define BCG_EGS_THREADS 64
 #endif
 #ifndef BCG_EGS_CTAS
-#define BCG_EGS_CTAS 16
+#define BCG_EGS_CTAS 18              // register budget (launch bound); the launch asks the occupancy calculator
 #endif
 #ifndef BCG_EGS_LIST
-#define BCG_EGS_LIST 1024
+#define BCG_EGS_LIST 896             // cells of one window; with the crop's 2 KB of tables 18 CTAs share an SM
 #endif
 #ifndef BCG_EGS_REC_SLOTS
 #define BCG_EGS_REC_SLOTS 4          // record ring (power of two, > the prefetch distance 3)
@@ -1526,12 +1526,12 @@ __global__ void __launch_bounds__(BCG_EGT_THREADS, BCG_EGT_CTAS) ego_tiles_kerne
 #define BCG_EGS_ZERO_BYTES 2048      // shared page of zeros the bulk stores read
 #endif
 #ifndef BCG_EGS_SUM_ROUNDS
-#define BCG_EGS_SUM_ROUNDS 4         // with the tile summary: rounds of 16 non-empty tiles loaded per pass
+#define BCG_EGS_SUM_ROUNDS 3         // with the tile summary: rounds of 16 non-empty tiles loaded per pass (2: 0.2454 ms, 3: 0.2457, 4: 0.2488)
 #endif
 #define BCG_EGS_QCAP 64              // ring slots per warp: a push adds <= 32 to <= 31 left over
+// The fixed-point tables of the crop live in dynamic shared memory, sized by the crop: adxy[ego_w] = (rint(a11 u 2^10),
+// rint(a21 u 2^10)), then bxy[ego_h] = rint((a12 v + b1) 2^10) + 512 - (X0 << 10), same for y (2 KB for a 117 x 133 crop)
 struct EgoSparseTab {
-  int2 adxy[BCG_EGT_MAX_W];                     // (rint(a11 u 2^10), rint(a21 u 2^10))
-  int2 bxy[BCG_EGO_MAX];                        // rint((a12 v + b1) 2^10) + 512 - (X0 << 10), same for y
   uint32_t list[BCG_EGS_LIST];                  // occupied window cells: y_rel << 16 | x_rel
   uint32_t count[2];
   uint32_t pad[2];
@@ -1578,7 +1578,8 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
   __shared__ uint16_t tlist_s[SUM ? BCG_EGS_MAX_TILES : 2];   // non-empty tiles of the window (every warp writes the same values)
   const uint32_t qword_u32 = smem_u32(qword_s[warp]), qtag_u32 = smem_u32(qtag_s[warp]), tlist_u32 = smem_u32(tlist_s);
   const uint32_t zero_u32 = smem_u32(zero_s), rec_u32 = smem_u32(rec_s);
-  const uint32_t adxy_u32 = smem_u32(T.adxy), bxy_u32 = smem_u32(T.bxy), list_u32 = smem_u32(T.list);
+  extern __shared__ __align__(16) int2 egs_tab[];          // adxy[ego_w], bxy[ego_h]
+  const uint32_t adxy_u32 = smem_u32(egs_tab), bxy_u32 = adxy_u32 + 8u * (uint32_t)p.ego_w, list_u32 = smem_u32(T.list);
   const uint8_t* const recs = reinterpret_cast<const uint8_t*>(b.ego_work);
   const int n = b.n_envs, G = gridDim.x;
   const int ego_w = p.ego_w, ego_h = p.ego_h, npx = ego_w * ego_h;
@@ -1638,11 +1639,11 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
       const EgoAffine A = r->aff;
       for (int i = tid; i < ego_w + ego_h; i += NT) {
         if (i < ego_w) {
-          T.adxy[i] = make_int2(__double2int_rn(A.a11 * i * 1024), __double2int_rn(A.a21 * i * 1024));
+          egs_tab[i] = make_int2(__double2int_rn(A.a11 * i * 1024), __double2int_rn(A.a21 * i * 1024));
         } else {
           const int t = i - ego_w;
-          T.bxy[t] = make_int2(__double2int_rn((A.a12 * t + A.b1) * 1024) + 512 - (X0 << 10),
-                               __double2int_rn((A.a22 * t + A.b2) * 1024) + 512 - (Y0 << 10));
+          egs_tab[i] = make_int2(__double2int_rn((A.a12 * t + A.b1) * 1024) + 512 - (X0 << 10),
+                                 __double2int_rn((A.a22 * t + A.b2) * 1024) + 512 - (Y0 << 10));
         }
       }
       // ---- 2. occupied cells of the window: four lanes per 32 x 16 bit tile (a 16-byte load = 4 rows each).  All loads
@@ -2155,9 +2156,27 @@ static int launch_ego_sparse(const BcgParams* p, const BcgBatch* b, uint8_t* ego
   int sms = 0;
   if (int rc = sm_count_of_current_device(&sms)) return rc;
   BCG_CHECK_CUDA(cudaMemsetAsync(b->ego_list + b->n_envs, 0, sizeof(int32_t), s));
-  const int grid = b->n_envs < BCG_EGS_CTAS * sms ? b->n_envs : BCG_EGS_CTAS * sms;
-  if (b->occ_sum_arena) ego_sparse_kernel<true><<<grid, BCG_EGS_THREADS, 0, s>>>(*p, *b, ego_image);
-  else ego_sparse_kernel<false><<<grid, BCG_EGS_THREADS, 0, s>>>(*p, *b, ego_image);
+  // persistent CTAs, as many per SM as fit with this crop's tables (18 for the 117 x 133 crop)
+  const int tab_bytes = (p->ego_w + p->ego_h) * (int)sizeof(int2);
+  const bool sum = b->occ_sum_arena != nullptr;
+  static int per_sm_cache[2][64] = {{0}}, tab_cache[2][64] = {{0}};
+  int dev = 0;
+  BCG_CHECK_CUDA(cudaGetDevice(&dev));
+  int per_sm = 0;
+  if (dev >= 0 && dev < 64 && per_sm_cache[sum][dev] > 0 && tab_cache[sum][dev] == tab_bytes) {
+    per_sm = per_sm_cache[sum][dev];
+  } else {
+    if (sum) BCG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ego_sparse_kernel<true>, BCG_EGS_THREADS, tab_bytes));
+    else BCG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ego_sparse_kernel<false>, BCG_EGS_THREADS, tab_bytes));
+    BCG_REQUIRE(per_sm > 0, "the sparse egocentric kernel does not fit an SM with this crop size");
+    if (dev >= 0 && dev < 64) {
+      per_sm_cache[sum][dev] = per_sm;
+      tab_cache[sum][dev] = tab_bytes;
+    }
+  }
+  const int grid = b->n_envs < per_sm * sms ? b->n_envs : per_sm * sms;
+  if (sum) ego_sparse_kernel<true><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image);
+  else ego_sparse_kernel<false><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image);
   BCG_CHECK_CUDA(cudaGetLastError());
   return launch_ego_dense(p, b, ego_image, b->ego_list, s);
 }
