@@ -30,6 +30,9 @@ using namespace bcg;
 #ifndef BCG_COMMIT_MIN_BLOCKS
 #define BCG_COMMIT_MIN_BLOCKS 4      // register budget of commit_kernel: 65536 / (threads x blocks)
 #endif
+#ifndef BCG_CR_RESIDENT
+#define BCG_CR_RESIDENT 1280        // threads per SM the collide/reward kernel is compiled for (register budget)
+#endif
 #ifndef BCG_CR_THREADS
 #define BCG_CR_THREADS 64
 #endif
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(128) pose_prep_kernel(const BcgParams p, const
 // reward of the pose the reward provider will see (reward.py:214-259).  Reads only; its few results go
 // to the scratch rows, the thread-per-env commit kernel applies them.  No store precedes a load, so all
 // of a warp's independent loads are in flight together.
-__global__ void __launch_bounds__(BCG_CR_THREADS, 1280 / BCG_CR_THREADS) collide_reward_kernel(const BcgParams p, const BcgBatch b) {
+__global__ void __launch_bounds__(BCG_CR_THREADS, BCG_CR_RESIDENT / BCG_CR_THREADS) collide_reward_kernel(const BcgParams p, const BcgBatch b) {
   const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned lane = threadIdx.x & 31;
   if (e >= b.n_envs) return;
@@ -1495,20 +1498,24 @@ __global__ void __launch_bounds__(BCG_EGT_THREADS, BCG_EGT_CTAS) ego_tiles_kerne
 // instructions and 112 M shared-memory wavefronts per launch, profiles/r1b_ncu_summary.txt), one small CTA per env
 //   1. zeroes the crop in global memory: one thread hands the 16-byte aligned body to the bulk-copy engine
 //      (cp.async.bulk.global.shared::cta from a shared page of zeros), lanes store the < 16 head / tail bytes,
-//   2. reads the OCCUPANCY plane (1 bit per cell != 0, bcg_build_lethal_tiles) of the window -- 1/8 of the bytes -- and
-//      lists the occupied cells inside the tile spans the rotated crop touches (warp-aggregated compaction),
+//   2. reads the OCCUPANCY plane (1 bit per cell != 0, bcg_build_lethal_tiles) of the window -- 1/8 of the bytes, and with
+//      the tile summary (1 bit per 32 x 16 tile, ego_sparse_kernel<true>) only the tiles that hold a cell at all -- and
+//      lists the occupied cells inside the tile spans the rotated crop touches: each warp queues its non-empty 16-byte
+//      pieces in a shared ring and expands them 32 at a time, one piece per lane,
 //   3. maps every listed cell forward with cv::warpAffine's float32 matrix and tests the <= 4 crop pixels around the
 //      image point with the exact fixed-point inverse rule (the one the dense kernel applies to every pixel); a crop
 //      pixel samples cell (X, Y) iff that test holds, so the result is bit-identical.  Hits are single-byte stores on
 //      top of the zeros (the bulk stores are waited for before the barrier that precedes this phase).
 // Why <= 4 candidates: the sample of pixel (u, v) is X = floor(x + 1/2 + d), |d| <= 2^-10, with (x, y) = A (u, v) + b and A
 // a rotation, so the pixels sampling (X, Y) lie within 0.501 (|cos| + |sin|) <= 0.709 of the forward image of (X, Y).
-// No image lives in shared memory, so a CTA needs ~9 KB and many run per SM: the kernel is bound by latency (one
-// DRAM round trip for the occupancy words, two barriers) and by its ~3 k warp instructions per env, not by bytes.
+// No image lives in shared memory, so a CTA needs ~11.6 KB (2 KB of them the crop's tables, in dynamic shared memory) and
+// 18 run per SM: the kernel is bound by its ~2.3 k warp instructions per env and by latency (two dependent DRAM round
+// trips -- summary, occupancy words -- and two barriers), then by the image write (profiles/r1_notes.md has the
+// ablations).
 // Envs whose window holds more than BCG_EGS_LIST occupied cells (filled regions of real costmaps), or whose record is
 // in direct mode, are appended to ego_list and rendered by the dense kernel right after.
-// shape chosen by measurement (profiles/probes/egs_variants.py, profiles/r1_notes.md): 64 x 16 0.292 ms, 128 x 12 0.303,
-// 256 x 6 0.371, 64 x 24 (fewer registers) 0.458, 32 x 24 0.578
+// shape chosen by measurement (profiles/probes/egs_variants.py, profiles/r1_notes.md): 64 threads x 16 CTAs 0.292 ms,
+// 128 x 12 0.303, 256 x 6 0.371, 32 x 24 0.578; with today's 48 registers 64 x 18 0.237 against 0.246 for 64 x 16
 #ifndef BCG_EGS_THREADS
 #define BCG_EGS_THREADS 64
 #endif

@@ -99,11 +99,49 @@ class ClockSampler(object):
             self.proc = None
         self.t_load = time.time()
 
+    def wait_first_sample(self, timeout=15.0):
+        """Block until nvidia-smi has written its first line (bounded), so that short runs are sampled too."""
+        t = time.time()
+        ok = False
+        while self.proc is not None and time.time() - t < timeout:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    ok = True
+                    break
+            except OSError:
+                pass
+            time.sleep(0.02)
+        self.t_load = time.time()            # the load (warm-up, then the timed region) starts now
+        return ok
+
     def mark_start(self):
         self.t0 = time.time()
 
     def mark_end(self):
         self.t1 = time.time()
+        self.extended = False
+
+    def extend_end(self):
+        """The same load kept running after the timed region (see run_b200): samples up to now count."""
+        self.t1 = time.time()
+        self.extended = True
+
+    def samples_since_start(self):
+        """Lines nvidia-smi has written since mark_start (cheap estimate: the file is only read, never parsed twice)."""
+        if self.proc is None or self.t0 is None:
+            return 1 << 30
+        n = 0
+        try:
+            for line in open(self.path):
+                f = line.split(",")
+                try:
+                    if len(f) >= 9 and self._stamp(f[0]) >= self.t0 - 0.005:
+                        n += 1
+                except ValueError:
+                    continue
+        except OSError:
+            return 1 << 30
+        return n
 
     @staticmethod
     def _stamp(text):
@@ -134,7 +172,7 @@ class ClockSampler(object):
             pass
         t0, t1 = self.t0 or self.t_load, self.t1 or time.time()
         inside = [r for r in rows if t0 - 0.005 <= r[0] <= t1 + 0.005]
-        scope = "timed region"
+        scope = "timed region + the same load kept running right after it" if getattr(self, "extended", False) else "timed region"
         if not inside:                       # region shorter than a poll: everything sampled since the warm-up began
             inside, scope = [r for r in rows if self.t_load <= r[0] <= t1 + 0.005], "warm-up + timed region"
         reasons = set()
@@ -321,6 +359,8 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()                           # nvidia-smi needs a few hundred ms to come up: start it before the set-up
     env = build_env(args, rank, device)
     n = env.n_envs
     low, high = env.action_bounds()
@@ -335,8 +375,7 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.wait_first_sample()
     for w in range(args.warmup):
         env.step(actions[w % n_sets])
     env.episode_stats(reset=True)
@@ -357,8 +396,16 @@ def run_b200(args):
     t_end.record()
     barrier()
     sampler.mark_end()
-    clocks = sampler.stop()
     elapsed_ms = t_start.elapsed_time(t_end)
+    # a timed region shorter than a few polls of nvidia-smi: keep the identical load running (untimed) until the sampler
+    # has seen it, so that the clocks line always describes this workload under load
+    t_roll = time.time()
+    while sampler.samples_since_start() < 5 and time.time() - t_roll < 3.0:
+        for k in range(20):
+            env.step(actions[k % n_sets])
+        torch.cuda.synchronize()
+        sampler.extend_end()
+    clocks = sampler.stop()
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
