@@ -1535,6 +1535,9 @@ __global__ void __launch_bounds__(BCG_EGT_THREADS, BCG_EGT_CTAS) ego_tiles_kerne
 #ifndef BCG_EGS_SUM_ROUNDS
 #define BCG_EGS_SUM_ROUNDS 3         // with the tile summary: rounds of 16 non-empty tiles loaded per pass (2: 0.2454 ms, 3: 0.2457, 4: 0.2488)
 #endif
+#ifndef BCG_EGS_DYNAMIC
+#define BCG_EGS_DYNAMIC 1            // 1: envs beyond a CTA's first four are drawn from a global counter
+#endif
 #define BCG_EGS_QCAP 64              // ring slots per warp: a push adds <= 32 to <= 31 left over
 // The fixed-point tables of the crop live in dynamic shared memory, sized by the crop: adxy[ego_w] = (rint(a11 u 2^10),
 // rint(a21 u 2^10)), then bxy[ego_h] = rint((a12 v + b1) 2^10) + 512 - (X0 << 10), same for y (2 KB for a 117 x 133 crop)
@@ -1604,15 +1607,33 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
   cp_async_commit();
   for (int i = tid * 16; i < BCG_EGS_ZERO_BYTES; i += NT * 16) *reinterpret_cast<uint4*>(zero_s + i) = make_uint4(0u, 0u, 0u, 0u);
   if (tid < 2) T.count[tid] = 0;
+#if BCG_EGS_DYNAMIC
+  // Which envs a CTA renders: its first RD + 1 are blockIdx.x + k G; the later ones come from a global counter
+  // (ego_list[n + 1], zeroed with the hand-over count), drawn RD + 1 iterations ahead so that the record can be
+  // prefetched -- CTAs whose windows are light take more envs, and the 24-or-25 envs per CTA quantisation goes away.
+  __shared__ int ids_s[8];
+  if (tid <= RD) ids_s[tid] = e0 + tid * G;
+#endif
   fence_async_smem();                         // the zeros are visible to the bulk-copy engine
   cp_async_wait_all();
   __syncthreads();
 
+#if BCG_EGS_DYNAMIC
+  for (int it = 0;; ++it) {
+    const int e = ids_s[it & 7];
+    if (e >= n) break;
+    int drawn = 0;
+    if (tid == 0) drawn = (RD + 1) * G + atomicAdd(b.ego_list + n + 1, 1);       // stored at the end of the iteration
+    const int slot = it & (BCG_EGS_REC_SLOTS - 1), par = it & 1;
+    fetch_record(ids_s[(it + RD) & 7], (it + RD) & (BCG_EGS_REC_SLOTS - 1));
+    cp_async_commit();
+#else
   int e = e0;
   for (int it = 0; e < n; e += G, ++it) {
     const int slot = it & (BCG_EGS_REC_SLOTS - 1), par = it & 1;
     fetch_record(e + RD * G, (it + RD) & (BCG_EGS_REC_SLOTS - 1));
     cp_async_commit();
+#endif
     const EgoTileWork* r = reinterpret_cast<const EgoTileWork*>(rec_s + slot * BCG_EGO_WORK_BYTES);
     const int mode = r->mode, X0 = r->X0, Y0 = r->Y0, ntx = r->ntx, nty = r->nty;
     uint8_t* const dst = image + (int64_t)e * npx;
@@ -1859,6 +1880,9 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
       b.ego_list[at] = e;
     }
     if (tid == 0) T.count[par ^ 1] = 0;         // nobody reads the other counter before the next barrier
+#if BCG_EGS_DYNAMIC
+    if (tid == 0) ids_s[(it + RD + 1) & 7] = drawn;
+#endif
     __syncthreads();                            // list, tables and record `it` are free
   }
 }
@@ -2162,7 +2186,7 @@ static int launch_ego_dense(const BcgParams* p, const BcgBatch* b, uint8_t* ego_
 static int launch_ego_sparse(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, cudaStream_t s) {
   int sms = 0;
   if (int rc = sm_count_of_current_device(&sms)) return rc;
-  BCG_CHECK_CUDA(cudaMemsetAsync(b->ego_list + b->n_envs, 0, sizeof(int32_t), s));
+  BCG_CHECK_CUDA(cudaMemsetAsync(b->ego_list + b->n_envs, 0, 2 * sizeof(int32_t), s));   // hand-over count, env counter
   // persistent CTAs, as many per SM as fit with this crop's tables (18 for the 117 x 133 crop)
   const int tab_bytes = (p->ego_w + p->ego_h) * (int)sizeof(int2);
   const bool sum = b->occ_sum_arena != nullptr;

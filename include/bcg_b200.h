@@ -200,7 +200,8 @@ typedef struct BcgBatch {
                             With it, cell_tile_arena and ego_list the egocentric observation takes the sparse
                             path: zero the crop, then scatter only the occupied source cells of its window   */
   int32_t* ego_list;      /* optional scratch [n_envs + 4]: envs whose window holds too many occupied cells
-                            for the sparse path, handed to the dense cell-tile kernel (count at [n_envs])   */
+                            for the sparse path, handed to the dense cell-tile kernel (count at [n_envs]; [n_envs + 1] is
+                            the sparse kernel's env counter)                                                 */
   const uint32_t* occ_sum_arena; /* optional: one bit per tile of the occupancy plane (BcgMapDesc.sum_off), filled by
                             bcg_build_lethal_tiles and kept by the generators; must start out zero.  With it the sparse
                             egocentric kernel loads only the non-empty tiles of a window                              */
