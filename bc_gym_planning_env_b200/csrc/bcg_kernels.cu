@@ -458,8 +458,12 @@ struct __align__(16) EgoTileWork {   // 256 bytes
   int32_t ctiles_x, ctiles_y;        // cell-tile grid of the env's map
   int64_t ctile_off;                 // byte offset of the map's cell tiles in the cell-tile arena
   float fwd[6];                      // cv::warpAffine's forward matrix (source -> crop), for the sparse kernel
-  int32_t dense_map;                 // more than 1 cell in 20 of the map is occupied: skip the sparse kernel's scan
-  int32_t pad[3];
+  int32_t dense_map;                 // bit 0: more than 1 cell in 20 of the map is occupied (skip the sparse kernel's
+                                     // scan); bit 1: every occupied cell is 254 (BCG_MAP_ONLY_LETHAL)
+  // what the sparse kernel needs of the map descriptor, so that its loads start from the record alone
+  int32_t sum_off;                   // BcgMapDesc.sum_off
+  uint32_t tiles_xy;                 // tiles_x | tiles_y << 16
+  uint32_t tile_off16;               // BcgMapDesc.tile_off / 16 (a plane is a whole number of 16-word tiles)
   uint8_t span[BCG_EGT_MAX_TILE_ROWS][2];   // first and last window tile column touched in tile row t (first > last: none)
 };
 static_assert(sizeof(EgoTileWork) == BCG_EGO_WORK_BYTES, "EgoTileWork records are 256 bytes");
@@ -482,9 +486,10 @@ __device__ __forceinline__ void write_ego_tile_record(const BcgParams& p, const 
   w.X0 = w.Y0 = w.ntx = w.nty = 0;
   w.mode = BCG_EGO_MODE_DIRECT;
   w.map_id = map_id;
-  w.dense_map = ((int64_t)m.occupied * 20 > (int64_t)m.width * m.height) ? 1 : 0;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) w.pad[k] = 0;
+  w.dense_map = (((int64_t)m.occupied * 20 > (int64_t)m.width * m.height) ? 1 : 0) | ((m.flags & BCG_MAP_ONLY_LETHAL) ? 2 : 0);
+  w.sum_off = m.sum_off;
+  w.tiles_xy = (uint32_t)m.tiles_x | ((uint32_t)m.tiles_y << 16);
+  w.tile_off16 = (uint32_t)(m.tile_off >> 4);
   w.ctiles_x = m.ctiles_x;
   w.ctiles_y = m.ctiles_y;
   w.ctile_off = m.cell_tile_off;
@@ -1600,6 +1605,21 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
     if (en < n && tid < 16)
       cp_async_16(rec_u32 + slot * BCG_EGO_WORK_BYTES + tid * 16, recs + (int64_t)en * BCG_EGO_WORK_BYTES + tid * 16, 16u);
   };
+  // Tile-summary words of the window of record `q`, lane <-> band of 16 rows (zero where the band or the word lies
+  // outside the map, or the env will not take the sparse path).  Loaded one env ahead of their use, so that an env's
+  // chain of dependent DRAM round trips is the occupancy words alone.
+  auto summary_words = [&](const EgoTileWork* q, uint32_t& lo, uint32_t& hi) {
+    lo = hi = 0u;
+    if (q->mode != BCG_EGO_MODE_TILES || (q->dense_map & 1)) return;
+    const int qby0 = q->Y0 >> 4, qnby = ((q->Y0 + 8 * q->nty - 1) >> 4) - qby0 + 1;
+    const int qtx = (int)(q->tiles_xy & 0xffffu), qty = (int)(q->tiles_xy >> 16), sw = (qtx + 31) >> 5;
+    const int ty = qby0 + lane, w0 = q->X0 >> 10;                            // X0 >> 5 may be negative: w0 = -1
+    if (lane < qnby && (unsigned)ty < (unsigned)qty) {
+      const uint32_t* const srow = b.occ_sum_arena + q->sum_off + ty * sw;
+      if ((unsigned)w0 < (unsigned)sw) lo = __ldg(srow + w0);
+      if ((unsigned)(w0 + 1) < (unsigned)sw) hi = __ldg(srow + w0 + 1);
+    }
+  };
   constexpr int RD = 3;
   static_assert(RD < BCG_EGS_REC_SLOTS, "record ring too small");
 #pragma unroll
@@ -1618,6 +1638,8 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
   cp_async_wait_all();
   __syncthreads();
 
+  uint32_t pf_lo = 0u, pf_hi = 0u;              // summary words of the env about to be rendered
+  if (SUM) summary_words(reinterpret_cast<const EgoTileWork*>(rec_s), pf_lo, pf_hi);
 #if BCG_EGS_DYNAMIC
   for (int it = 0;; ++it) {
     const int e = ids_s[it & 7];
@@ -1627,13 +1649,19 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
     const int slot = it & (BCG_EGS_REC_SLOTS - 1), par = it & 1;
     fetch_record(ids_s[(it + RD) & 7], (it + RD) & (BCG_EGS_REC_SLOTS - 1));
     cp_async_commit();
+    const int e_next = ids_s[(it + 1) & 7];
 #else
   int e = e0;
   for (int it = 0; e < n; e += G, ++it) {
     const int slot = it & (BCG_EGS_REC_SLOTS - 1), par = it & 1;
     fetch_record(e + RD * G, (it + RD) & (BCG_EGS_REC_SLOTS - 1));
     cp_async_commit();
+    const int e_next = e + G;
 #endif
+    // record it + 1 has landed (only the newest fetch may still be in flight): start its summary loads now
+    const uint32_t cur_lo = pf_lo, cur_hi = pf_hi;
+    if (SUM && e_next < n)
+      summary_words(reinterpret_cast<const EgoTileWork*>(rec_s + ((it + 1) & (BCG_EGS_REC_SLOTS - 1)) * BCG_EGO_WORK_BYTES), pf_lo, pf_hi);
     const EgoTileWork* r = reinterpret_cast<const EgoTileWork*>(rec_s + slot * BCG_EGO_WORK_BYTES);
     const int mode = r->mode, X0 = r->X0, Y0 = r->Y0, ntx = r->ntx, nty = r->nty;
     uint8_t* const dst = image + (int64_t)e * npx;
@@ -1642,7 +1670,7 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
     const int ntile = nby * nwx;
     // maps with more than one cell in 20 occupied (filled regions, inflation gradients) overflow the cell list in
     // almost every window: they go straight to the dense kernel instead of paying for a scan that is thrown away
-    const bool dense_map = r->dense_map != 0;           // decided by the record writer, which holds the map descriptor
+    const bool dense_map = (r->dense_map & 1) != 0;     // decided by the record writer, which holds the map descriptor
     const bool try_sparse = mode == BCG_EGO_MODE_TILES && ntile <= BCG_EGS_MAX_TILES && !dense_map && (!SUM || (nby <= 32 && nwx <= 32));
     if (try_sparse) {
       // ---- 1. zero the crop in global memory ----------------------------------------------------------------------
@@ -1679,9 +1707,8 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
       // Walls are thin: only a few of a warp's 32 pieces hold a cell, so expanding them where they were loaded would
       // keep most lanes idle.  Each warp queues its non-empty pieces (16 bytes + band / column / row-group tag) in a
       // shared ring and expands them 32 at a time, one piece per lane. ------------------------------------------------
-      const BcgMapDesc* md = b.maps + r->map_id;
-      const int tiles_x = md->tiles_x, tiles_y = md->tiles_y;
-      const uint4* occ = reinterpret_cast<const uint4*>(b.occ_tile_arena + md->tile_off);
+      const int tiles_x = (int)(r->tiles_xy & 0xffffu), tiles_y = (int)(r->tiles_xy >> 16);
+      const uint4* occ = reinterpret_cast<const uint4*>(b.occ_tile_arena + ((int64_t)r->tile_off16 << 4));
       const int g = lane & 3;                                                     // rows 4 g .. 4 g + 3 of the tile
       constexpr int TPR = NT / 4;                                                // tiles per round
       const uint32_t span_u32 = rec_u32 + slot * BCG_EGO_WORK_BYTES + 128;
@@ -1758,18 +1785,8 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
       };
       if constexpr (SUM) {
         // (a) which tiles of the window hold a cell at all: lane <-> band of 16 rows, one or two words of the map's tile
-        // summary each (every warp computes the same list: no barrier, and the few words hit L1 the second time)
-        const uint32_t* const sum = b.occ_sum_arena + md->sum_off;
-        const int sw = (tiles_x + 31) >> 5;
-        uint32_t tmask = 0u;
-        {
-          const int ty = by0 + lane, w0 = wx0 >> 5;                               // wx0 may be negative: w0 = -1
-          if (lane < nby && (unsigned)ty < (unsigned)tiles_y) {
-            const uint32_t lo = (unsigned)w0 < (unsigned)sw ? __ldg(sum + ty * sw + w0) : 0u;
-            const uint32_t hi = (unsigned)(w0 + 1) < (unsigned)sw ? __ldg(sum + ty * sw + w0 + 1) : 0u;
-            tmask = (uint32_t)((((uint64_t)hi << 32) | lo) >> (wx0 & 31)) & ((1u << nwx) - 1u);
-          }
-        }
+        // summary each, loaded one env ahead (`summary_words`; every warp holds the same words: no barrier)
+        const uint32_t tmask = (uint32_t)((((uint64_t)cur_hi << 32) | cur_lo) >> (wx0 & 31)) & ((1u << nwx) - 1u);
         // (b) the list of those tiles (band << 6 | column), in band order: inclusive warp scan of the per-band counts
         int tincl = __popc(tmask);
 #pragma unroll
@@ -1839,10 +1856,14 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
     const bool sparse = try_sparse && count <= BCG_EGS_LIST;
     if (sparse) {
       // ---- 3. scatter the listed cells ----------------------------------------------------------------------------
-      const BcgMapDesc* md = b.maps + r->map_id;
-      const bool only_lethal = (md->flags & BCG_MAP_ONLY_LETHAL) != 0;
-      const uint8_t* src = b.map_arena + md->data_off;
-      const int pitch = md->pitch;
+      const bool only_lethal = (r->dense_map & 2) != 0;
+      const uint8_t* src = nullptr;
+      int pitch = 0;
+      if (!only_lethal) {                               // other cost values: they are read from the map's uint8 rows
+        const BcgMapDesc* md = b.maps + r->map_id;
+        src = b.map_arena + md->data_off;
+        pitch = md->pitch;
+      }
       const float m0 = r->fwd[0], m1 = r->fwd[1], m2 = r->fwd[2], m3 = r->fwd[3], m4 = r->fwd[4], m5 = r->fwd[5];
       for (uint32_t i = tid; i < count; i += NT) {
         const uint32_t key = lds_u32(list_u32 + 4u * i);
