@@ -36,3 +36,33 @@ def test_reference_arm_prints_the_contract_line():
 def test_reference_arm_runs_on_rank_0_only():
     res = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert res.returncode == 0 and res.stdout.strip() == ""
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_b200_arm_prints_the_contract_line():
+    """A small run of the CUDA arm: every key of the measurement contract is there and self-consistent."""
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--envs", "2048", "--pool", "32", "--steps", "5",
+                          "--warmup", "3", "--e2e-steps", "2", "--e2e-image-steps", "1", "--cpu-seconds", "0.5",
+                          "--gen-envs", "0"], capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stderr[-800:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in d, key
+    assert "impl" not in d and d["metric"] == "env_steps_per_sec" and d["steps"] == 5 and d["warmup"] == 3
+    assert abs(d["value"] - 2048 * 5 / (d["ms_per_step"] * 5e-3)) < 1e-6 * d["value"]
+    assert d["gpu_launches"] == 5 * 5                      # kin, collide/reward, commit, sparse ego, dense ego per step
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] > 0
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["traffic"] is None      # ncu traffic is for 65 536 envs
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 2048 * 2 * 4 and e["d2h_bytes_per_step"] == 2048 * (8 + 1 + 48)
+    assert e["with_images_to_host"]["d2h_bytes_per_step"] > 2048 * 117 * 133
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] > 0 and cb["sample"]
+    assert d["clocks"]["samples"] >= 1 and d["clocks"]["sm_mhz"] is not None
