@@ -353,6 +353,54 @@ def gen_mini_worlds(name, n_envs):
     print(name, [out["costmap_%d" % s].shape for s in range(n_envs)][:3], [len(out["path_%d" % s]) for s in range(n_envs)])
 
 
+def gen_edge_worlds(name, n_steps, every):
+    """The reference's PlanEnv + EgocentricCostmap on the tiny worlds of tests/common.py (robots that leave their map,
+    a map smaller than the footprint, an all-lethal map): rollout records plus crops / goal vectors every `every` steps."""
+    from bc_gym_planning_env.envs.base.action import Action
+    from bc_gym_planning_env.envs.base.env import PlanEnv
+    from bc_gym_planning_env.envs.base.params import EnvParams
+    from bc_gym_planning_env.envs.egocentric import EgocentricCostmap
+    from bc_gym_planning_env.utilities.costmap_2d import CostMap2D
+    sys.path.insert(0, os.path.dirname(HERE))
+    from tests.common import tiny_worlds
+    ep = EnvParams(control_delay=1, pose_delay=1, state_delay=2)
+    envs, records, actions, images, vectors = [], [], [], [], []
+    rng = np.random.RandomState(7)
+    worlds = tiny_worlds()
+    per_step = []
+    for t in range(n_steps):                     # the action stream of tests/test_gpu_edge_cases.py
+        a = rng.uniform([np.pi / 30, -np.pi / 2], [np.pi / 6, np.pi / 2], size=(len(worlds), 2)).astype(np.float32)
+        a[:, 1] = rng.uniform(-0.15, 0.15, size=len(worlds))
+        per_step.append(a)
+    per_step = np.array(per_step)                # [T, E, 2]
+    for e, (m, origin, path) in enumerate(worlds):
+        pe = PlanEnv(CostMap2D(m.copy(), 0.03, origin.astype(np.float64)), path, ep)
+        pe._robot.set_noise_parameters(None)
+        env = EgocentricCostmap(pe)
+        envs.append(pe)
+        recs, ei, ev = [], [], []
+        for t in range(n_steps):
+            obs, r, d, _ = env.step(Action(command=per_step[t, e]))
+            plain = pe._extract_obs()
+            recs.append(_record_step(pe, plain, r, d))
+            if t % every == every - 1:
+                ei.append(obs["env"][..., 0].copy())
+                ev.append(obs["goal_n_state"][:, 0].copy())
+        records.append(recs)
+        images.append(ei)
+        vectors.append(ev)
+    out = _pack_envs(envs)
+    out.update({"ref_" + k: v for k, v in _stack(records).items()})
+    out["actions"] = np.ascontiguousarray(per_step.transpose(1, 0, 2))
+    out["every"] = np.int64(every)
+    out["ref_ego_image"] = np.array(images)
+    out["ref_goal_n_state"] = np.array(vectors)
+    out["params"] = np.array(_params_json(ep, False))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, out["ref_pose"].shape, out["ref_ego_image"].shape, "collided", out["ref_collided"][:, -1],
+          "done", out["ref_done"][:, -1])
+
+
 def main():
     _ref()
     os.makedirs(OUT, exist_ok=True)
@@ -377,6 +425,7 @@ def main():
     gen_aisle_worlds("aisle_worlds", 16)
     gen_t_junction("t_junction")
     gen_mini_worlds("mini_worlds", 24)
+    gen_edge_worlds("edge_worlds", 260, 13)
 
 
 if __name__ == "__main__":

@@ -60,3 +60,25 @@ def make_vec_env(d, **kw):
         params = env_params(d["params"]) if "params" in d else None
     kw.setdefault("noise_parameters", None)
     return VecPlanEnv(costmaps, paths, params, **kw)
+
+
+def tiny_worlds():
+    """Edge-case worlds (costmap uint8, origin, coarse path): maps far smaller than an aisle, which the robot leaves;
+    one is smaller than the tricycle's footprint, one is all lethal and driven into from outside.  Shared by
+    oracle/gen_golden.py (fixture edge_worlds: the reference stepped on them) and the GPU edge-case tests."""
+    worlds = []
+    m = np.zeros((50, 40), dtype=np.uint8)             # 1.5 m x 1.2 m: a lethal post in a corner the footprint misses,
+    m[0:3, 0:3] = 254                                  # non-lethal costs under the robot
+    m[20:24, 15:19] = 253
+    m[30, :] = 255
+    worlds.append((m, np.array([-0.3, -0.6]), np.array([[0., 0., 0.], [4., 0.5, 0.2]])))
+    m = np.zeros((20, 20), dtype=np.uint8)             # 0.6 m square, smaller than the footprint that passes over it
+    m[0, :] = 253
+    m[5:9, 5:9] = 100
+    m[:, 19] = 255
+    worlds.append((m, np.array([0.4, -0.3]), np.array([[-1., 0., 0.], [3., 0., 0.]])))
+    m = np.full((33, 47), 254, dtype=np.uint8)         # all lethal, the robot starts outside and drives in
+    worlds.append((m, np.array([1.5, -0.5]), np.array([[0., 0., 0.], [4., 0., 0.]])))
+    m = np.zeros((64, 64), dtype=np.uint8)             # empty map, path leaves through a corner
+    worlds.append((m, np.array([-1., -1.]), np.array([[0., 0., np.pi / 4], [3., 3., np.pi / 4]])))
+    return worlds

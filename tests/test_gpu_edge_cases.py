@@ -14,29 +14,12 @@ from bc_gym_planning_env_b200.envs.base.params import EnvParams
 from bc_gym_planning_env_b200.utilities.costmap_2d import CostMap2D
 from bc_gym_planning_env_b200.vec_env import VecPlanEnv
 from oracle import plan_env_oracle as O
+from tests import common
 
 pytestmark = pytest.mark.gpu
 
 
-def _tiny_worlds():
-    """Maps far smaller than an aisle: (costmap, origin, coarse path).  The robot starts inside or beside them and is
-    driven well outside; one map is smaller than the tricycle's footprint."""
-    worlds = []
-    m = np.zeros((50, 40), dtype=np.uint8)             # 1.5 m x 1.2 m: a lethal post in a corner the footprint misses,
-    m[0:3, 0:3] = 254                                  # non-lethal costs under the robot
-    m[20:24, 15:19] = 253
-    m[30, :] = 255
-    worlds.append((m, np.array([-0.3, -0.6]), np.array([[0., 0., 0.], [4., 0.5, 0.2]])))
-    m = np.zeros((20, 20), dtype=np.uint8)             # 0.6 m square, smaller than the footprint that passes over it
-    m[0, :] = 253
-    m[5:9, 5:9] = 100
-    m[:, 19] = 255
-    worlds.append((m, np.array([0.4, -0.3]), np.array([[-1., 0., 0.], [3., 0., 0.]])))
-    m = np.full((33, 47), 254, dtype=np.uint8)         # all lethal, the robot starts outside and drives in
-    worlds.append((m, np.array([1.5, -0.5]), np.array([[0., 0., 0.], [4., 0., 0.]])))
-    m = np.zeros((64, 64), dtype=np.uint8)             # empty map, path leaves through a corner
-    worlds.append((m, np.array([-1., -1.]), np.array([[0., 0., np.pi / 4], [3., 3., np.pi / 4]])))
-    return worlds
+_tiny_worlds = common.tiny_worlds
 
 
 def _build(worlds, n_envs=None, **kw):

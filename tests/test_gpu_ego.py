@@ -9,10 +9,12 @@ from tests import common
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("staging", ["tiles", "tma", "spans"])
-def test_ego_observation_matches_reference(staging):
-    """All ways of staging the source window (cell tiles via cp.async, TMA box loads, plain span loads) against cv2."""
-    d = common.load("aisle_ego")
+@pytest.mark.parametrize("staging,name", [("tiles", "aisle_ego"), ("tma", "aisle_ego"), ("spans", "aisle_ego"),
+                                          ("tiles", "edge_worlds"), ("spans", "edge_worlds")])
+def test_ego_observation_matches_reference(staging, name):
+    """All ways of staging the source window (cell tiles via cp.async, TMA box loads, plain span loads) against cv2;
+    `edge_worlds`: crops that lie partly or wholly outside tiny maps (the reference pads with zeros)."""
+    d = common.load(name)
     env = common.make_vec_env(d, with_ego=True, ego_staging=staging)
     actions = torch.from_numpy(d["actions"]).cuda()
     every = int(d["every"])

@@ -31,7 +31,7 @@ def _rollout(d, **kw):
     return {k: np.swapaxes(np.array(v), 0, 1) for k, v in rec.items()}
 
 
-@pytest.mark.parametrize("name", ["mini_noise_off", "aisle_delays_211", "aisle_delays_120", "aisle_pure_pursuit"])
+@pytest.mark.parametrize("name", ["mini_noise_off", "aisle_delays_211", "aisle_delays_120", "aisle_pure_pursuit", "edge_worlds"])
 def test_step_matches_reference(name):
     d = common.load(name)
     got = _rollout(d)

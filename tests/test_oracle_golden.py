@@ -22,7 +22,7 @@ def _replay(d, oracles):
             assert len(obs["path"]) == d["ref_path_len"][e, t]
 
 
-@pytest.mark.parametrize("name", ["mini_noise_off", "aisle_delays_211", "aisle_delays_120", "aisle_pure_pursuit"])
+@pytest.mark.parametrize("name", ["mini_noise_off", "aisle_delays_211", "aisle_delays_120", "aisle_pure_pursuit", "edge_worlds"])
 def test_oracle_matches_reference_rollouts(name):
     d = common.load(name)
     _replay(d, common.make_oracles(d))
@@ -53,10 +53,11 @@ def test_oracle_collision_and_pixel_counts():
             assert O.footprint_pixels_in_map(x, y, th, O.TRICYCLE_FOOTPRINT, cm.shape, origin, res) == d["ref_pixels"][e, k]
 
 
-def test_oracle_ego_observation():
+@pytest.mark.parametrize("name", ["aisle_ego", "edge_worlds"])
+def test_oracle_ego_observation(name):
     """Closed form of cv2.warpAffine and the literal cv2 call, both against the reference's
-    EgocentricCostmap wrapper."""
-    d = common.load("aisle_ego")
+    EgocentricCostmap wrapper -- on aisles, and on the tiny worlds whose crops lie partly or wholly outside the map."""
+    d = common.load(name)
     oracles = common.make_oracles(d)
     every = int(d["every"])
     for e, o in enumerate(oracles):
