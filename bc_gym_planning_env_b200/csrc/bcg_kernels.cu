@@ -1,10 +1,18 @@
 // Kernels + C-ABI of the batched PlanEnv.step path for B200 (sm_100a).  See include/bcg_b200.h.
 //
-// Launch shapes (DESIGN.md has the rooflines):
-//   kin_kernel      1 thread / env   -- delay ring + robot model + Philox noise, coalesced SoA fp64
-//   commit_kernel   1 warp   / env   -- footprint-vs-lethal-tile collision, rollback, delay rings,
-//                                       chunk-culled reached-index scan, reward, done, auto-reset
-//   ego_kernel      1 CTA    / env   -- cv2.warpAffine(INTER_NEAREST)-exact egocentric gather
+// One step = five launches on one stream (DESIGN.md has the rooflines and the measurements):
+//   kin_kernel             1 thread / env    -- control delay ring, robot model, Philox noise; writes the proposed state
+//                                               and the env's 192-byte work record (footprint bin, tile / path references)
+//   collide_reward_kernel  1 warp / env      -- footprint vs the 1-bit lethal tile plane (lane <-> footprint row), the pose
+//                                               the reward sees, chunk-culled reached-index scan, reward; read-only
+//   commit_kernel          2 threads / env   -- rollback, pose / state delay rings, done, episode statistics, auto-reset,
+//                                               compact observation, goal vector, the 256-byte egocentric record
+//   ego_sparse_kernel      persistent, 64-thread CTAs x 18 per SM -- cv2.warpAffine(INTER_NEAREST)-exact egocentric crop as a
+//                                               scatter of the occupied cells of the source window
+//   ego_tiles_kernel       persistent, 256-thread CTAs -- the dense per-pixel gather, for the envs the sparse kernel hands
+//                                               over (filled regions) and for pools of dense maps
+// plus the set-up kernels (tile planes and summary, cell tiles, initial state), the device-side world generators and
+// the stand-alone entry points of the hook seam.
 // No tensor cores: nothing here is a dense contraction.
 #include <cuda.h>
 #include <cudaTypedefs.h>
