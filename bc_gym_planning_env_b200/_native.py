@@ -58,7 +58,7 @@ class BcgFootprintLut(C.Structure):
 class BcgBatch(C.Structure):
     _fields_ = [
         ("n_envs", C.c_int32), ("n_frows", C.c_int32), ("n_irows", C.c_int32),
-        ("n_maps", C.c_int32), ("n_paths", C.c_int32), ("reserved", C.c_int32),
+        ("n_maps", C.c_int32), ("n_paths", C.c_int32), ("flags", C.c_int32),
         ("state_f", C.c_void_p), ("state_i", C.c_void_p), ("init_f", C.c_void_p), ("init_i", C.c_void_p),
         ("cand", C.c_void_p), ("cand_i", C.c_void_p), ("ego_work", C.c_void_p), ("work", C.c_void_p), ("map_id", C.c_void_p), ("path_id", C.c_void_p),
         ("maps", C.c_void_p), ("paths", C.c_void_p),
@@ -67,7 +67,7 @@ class BcgBatch(C.Structure):
         ("map_tmaps", C.c_void_p), ("tmap_n_widths", C.c_int32), ("tmap_box_h", C.c_int32),
         ("tmap_box_w", C.c_int32 * 4),
         ("cell_tile_arena", C.c_void_p), ("occ_tile_arena", C.c_void_p), ("ego_list", C.c_void_p),
-        ("occ_sum_arena", C.c_void_p), ("status", C.c_void_p), ("stats", C.c_void_p),
+        ("occ_sum_arena", C.c_void_p), ("status", C.c_void_p), ("stats", C.c_void_p), ("step_counter", C.c_void_p),
     ]
 
 
@@ -123,6 +123,7 @@ STAT_NAMES = ("episodes", "return", "length", "collided", "goal", "timeout")
 STATS_WORDS = 8
 ROBOT_TRICYCLE, ROBOT_DIFFDRIVE = 0, 1
 MAP_ONLY_LETHAL = 1
+BATCH_SPARSE_EGO_ONLY = 1
 REWARD_CONTINUOUS, REWARD_PURE_PURSUIT = 0, 1
 
 # every symbol include/bcg_b200.h declares: name -> (restype, argtypes)
@@ -150,6 +151,7 @@ SYMBOLS = {
     "bcg_kinematic_step": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgBatch), _P, C.c_int32, C.c_uint64, _P]),
     "bcg_collision": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgBatch), _P, _P, _P, _P]),
     "bcg_collision_u8": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgBatch), _P, _P, _P]),
+    "bcg_collision_recheck": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgBatch), _P, C.c_int32, _P]),
     "bcg_observe_ego": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgBatch), _P, _P, _P]),
     "bcg_gather_state": (C.c_int, [C.POINTER(BcgBatch), _P, C.c_int32, _P, _P, _P]),
     "bcg_scatter_state": (C.c_int, [C.POINTER(BcgBatch), _P, C.c_int32, _P, _P, C.c_int32, _P]),

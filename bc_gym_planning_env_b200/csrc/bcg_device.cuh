@@ -226,7 +226,7 @@ __device__ __forceinline__ void delay_peek(const double* ring, int64_t stride, i
 // Work records: what the warp-per-env kernels need to know about one env, resolved by the thread-per-env
 // kernels (kinematics / pose-prep) and stored array-of-structures so that a warp gets everything with one
 // round of 16-byte loads instead of chasing map_id -> map descriptor -> tile address through memory.
-struct __align__(16) WorkCollide {   // 64 bytes
+struct __align__(16) WorkCollide {   // 80 bytes
   int64_t tile_off;                  // lethal tile plane of the env's map (uint32 offset in the tile arena)
   int64_t data_off;                  // uint8 cells of the env's map (byte offset in the map arena)
   int32_t tiles_x, map_pitch;
@@ -237,7 +237,10 @@ struct __align__(16) WorkCollide {   // 64 bytes
   int32_t path_n;
   int64_t path_off;                  // fp64 offset of the env's path rows in the path arena
   int32_t path_pitch, chunk_pitch;   // chunk rows start at path_off + 5 * path_pitch
+  int32_t sum_off;                   // tile summary of the env's map (BcgMapDesc.sum_off)
+  int32_t pad[3];
 };
+static_assert(sizeof(WorkCollide) == 80, "WorkCollide is 80 bytes");
 
 struct __align__(16) WorkReward {    // 96 bytes
   double cand[3];                    // pose proposed by the kinematic step
@@ -249,13 +252,13 @@ struct __align__(16) WorkReward {    // 96 bytes
   int32_t goal_before;               // pure pursuit: was the observed pose already within 1 m of the goal
 };
 
-#define BCG_WORK_BYTES 192           // WorkCollide at +0, WorkReward at +64
+#define BCG_WORK_BYTES 192           // WorkCollide at +0, WorkReward at +80
 
 __device__ __forceinline__ const WorkCollide* work_collide(const void* work, int e) {
   return reinterpret_cast<const WorkCollide*>(reinterpret_cast<const uint8_t*>(work) + (int64_t)e * BCG_WORK_BYTES);
 }
 __device__ __forceinline__ const WorkReward* work_reward(const void* work, int e) {
-  return reinterpret_cast<const WorkReward*>(reinterpret_cast<const uint8_t*>(work) + (int64_t)e * BCG_WORK_BYTES + 64);
+  return reinterpret_cast<const WorkReward*>(reinterpret_cast<const uint8_t*>(work) + (int64_t)e * BCG_WORK_BYTES + 80);
 }
 
 // Per-thread.  Picks the angle bin whose stored rounded-vertex tuple equals
@@ -312,6 +315,8 @@ __device__ __forceinline__ WorkCollide make_work_collide(const BcgParams& p, con
   w.path_off = pd.off;
   w.path_pitch = pd.pitch;
   w.chunk_pitch = pd.chunk_pitch;
+  w.sum_off = m.sum_off;
+  w.pad[0] = w.pad[1] = w.pad[2] = 0;
   return w;
 }
 
@@ -380,6 +385,72 @@ __device__ __forceinline__ bool collide_tiles(const BcgBatch& b, const WorkColli
   return __any_sync(BCG_FULL, hit != 0u);
 }
 
+// pose_collides (envs/base/env.py:464-489) by ONE thread, for the thread-per-env state kernel.  The footprint box
+// spans <= 5 bands of 16 rows x <= 3 tiles of 32 columns; a tile is four 16-byte quarters of four rows.  With the tile
+// summary (`sum`: 1 bit per tile of the occupancy plane, a superset of the lethal plane) only tiles that hold a cell at
+// all are loaded -- an aisle is mostly free space, so most checks read one or two summary words per band and nothing
+// else.  All of a thread's loads for a quarter are independent of each other.  Same verdict as collide_tiles.
+struct FootBox {
+  int X0, Y0;          // map pixel of the mask's top-left corner
+  int nrows, fwidth;   // mask bounding box
+  int bin;
+};
+
+__device__ __forceinline__ bool collide_thread(const BcgFootprintLut& lut, const uint32_t* __restrict__ tiles,
+                                               const uint32_t* __restrict__ sum, int tiles_x, int map_w, int map_h,
+                                               const FootBox& f) {
+  const int X0 = f.X0, Y0 = f.Y0;
+  const int X1 = X0 + f.fwidth - 1, Y1 = Y0 + f.nrows - 1;
+  if (X1 < 0 || X0 >= map_w || Y1 < 0 || Y0 >= map_h) return false;
+  const int tx0 = max(X0, 0) >> 5, tx1 = min(X1, map_w - 1) >> 5;
+  const int ty0 = max(Y0, 0) >> 4, ty1 = min(Y1, map_h - 1) >> 4;
+  const int wpr = lut.wpr;
+  const uint64_t* rows = lut.rows + (int64_t)f.bin * lut.max_rows * wpr;
+  const int sw = (tiles_x + 31) >> 5;
+  uint32_t hit = 0u;
+  for (int ty = ty0; ty <= ty1 && hit == 0u; ++ty) {
+    uint32_t tmask = 0xffffffffu;                      // bit j <-> tile column tx0 + j
+    if (sum) {
+      const uint32_t* srow = sum + ty * sw;
+      const int w0 = tx0 >> 5;
+      uint64_t two = __ldg(srow + w0);
+      if ((tx1 >> 5) != w0) two |= (uint64_t)__ldg(srow + w0 + 1) << 32;
+      tmask = (uint32_t)(two >> (tx0 & 31));
+    }
+    tmask &= (2u << (tx1 - tx0)) - 1u;
+    if (tmask == 0u) continue;
+    const uint32_t* trow = tiles + (((int64_t)ty * tiles_x) << 4);
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+      const int dy0 = (ty << 4) + 4 * q - Y0;           // mask row of this quarter's first tile row
+      if (dy0 + 3 < 0 || dy0 >= f.nrows) continue;
+      if (wpr == 1) {
+        uint64_t mk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mk[k] = ((unsigned)(dy0 + k) < (unsigned)f.nrows) ? __ldg(rows + dy0 + k) : 0ull;
+        for (int tx = tx0; tx <= tx1; ++tx) {
+          if (((tmask >> (tx - tx0)) & 1u) == 0u) continue;
+          const uint4 w = __ldg(reinterpret_cast<const uint4*>(trow + (tx << 4) + 4 * q));
+          const int rel = (tx << 5) - X0;
+          hit |= (w.x & mask_window32(mk[0], rel)) | (w.y & mask_window32(mk[1], rel)) |
+                 (w.z & mask_window32(mk[2], rel)) | (w.w & mask_window32(mk[3], rel));
+        }
+      } else {
+        for (int tx = tx0; tx <= tx1; ++tx) {
+          if (((tmask >> (tx - tx0)) & 1u) == 0u) continue;
+          const uint4 w = __ldg(reinterpret_cast<const uint4*>(trow + (tx << 4) + 4 * q));
+          const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+          const int rel = (tx << 5) - X0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if ((unsigned)(dy0 + k) < (unsigned)f.nrows) hit |= ws[k] & mask_bits32(rows + (int64_t)(dy0 + k) * wpr, wpr, rel);
+        }
+      }
+    }
+  }
+  return hit != 0u;
+}
+
 // The same verdict read straight from the uint8 costmap rows: each half-warp owns one footprint row
 // per pass, each lane one aligned 4-byte word of it.
 __device__ __forceinline__ bool collide_u8(const BcgBatch& b, const WorkCollide& f, unsigned lane) {
@@ -413,6 +484,9 @@ __device__ __forceinline__ bool collide_u8(const BcgBatch& b, const WorkCollide&
 // max i with hypot < sp, |wrap(dth)| < ap, parallel distance >= -sp/9.  Chunks of 32 points whose
 // bounding circle is farther than sp from the pose cannot contain a reached point and are skipped.
 // Warp-cooperative; returns -1 when nothing is reached.
+template <bool COHERENT>
+__device__ __forceinline__ double ldro(const double* q) { return COHERENT ? *q : __ldg(q); }
+
 struct PathRef {
   const double* P;   // 5 rows x, y, th, cos th, sin th, each `pitch` long
   const double* C;   // 3 chunk rows cx, cy, radius, each `chunk_pitch` long
@@ -429,6 +503,9 @@ __device__ __forceinline__ PathRef path_ref(const BcgBatch& b, const BcgPathDesc
   return r;
 }
 
+// COHERENT: plain loads instead of ld.global.nc -- for callers whose path rows were written earlier in the SAME launch (the
+// device generators); the read-only path is only defined for data that is constant for the whole kernel.
+template <bool COHERENT = false>
 __device__ __forceinline__ int last_reached_from(const BcgParams& p, const PathRef& pd, int lo, double px, double py,
                                                  double pth, unsigned lane) {
   if (lo >= pd.n) return -1;
@@ -441,8 +518,8 @@ __device__ __forceinline__ int last_reached_from(const BcgParams& p, const PathR
     const int c = (g << 5) + lane;
     bool near = false;
     if (c >= c_lo && c <= c_hi) {
-      const double cx = __ldg(C + c) - px, cy = __ldg(C + pd.chunk_pitch + c) - py;
-      const double reach = p.spatial_precision + __ldg(C + 2 * pd.chunk_pitch + c);
+      const double cx = ldro<COHERENT>(C + c) - px, cy = ldro<COHERENT>(C + pd.chunk_pitch + c) - py;
+      const double reach = p.spatial_precision + ldro<COHERENT>(C + 2 * pd.chunk_pitch + c);
       near = (cx * cx + cy * cy) < reach * reach * (1.0 + 1e-12);     // conservative: never drops a reachable chunk
     }
     unsigned bits = __ballot_sync(BCG_FULL, near);
@@ -452,8 +529,8 @@ __device__ __forceinline__ int last_reached_from(const BcgParams& p, const PathR
       const int i = (((g << 5) + cl) << 5) + lane;
       bool reached = false;
       if (i >= lo && i < pd.n) {
-        const double xi = __ldg(P + i), yi = __ldg(P + pd.pitch + i), ti = __ldg(P + 2 * pd.pitch + i);
-        const double ci = __ldg(P + 3 * pd.pitch + i), si = __ldg(P + 4 * pd.pitch + i);
+        const double xi = ldro<COHERENT>(P + i), yi = ldro<COHERENT>(P + pd.pitch + i), ti = ldro<COHERENT>(P + 2 * pd.pitch + i);
+        const double ci = ldro<COHERENT>(P + 3 * pd.pitch + i), si = ldro<COHERENT>(P + 4 * pd.pitch + i);
         // hypot(dx, dy) < sp, decided from the squared distance unless it is within 1e-12 of the threshold
         const double dx = xi - px, dy = yi - py, d2 = dx * dx + dy * dy;
         bool close = d2 < sp2 * (1.0 - 1e-12);
@@ -469,6 +546,59 @@ __device__ __forceinline__ int last_reached_from(const BcgParams& p, const PathR
     }
   }
   return -1;
+}
+
+// The same scan by ONE thread (state kernel): chunks from the far end down, culled by their bounding circles; the points of
+// a candidate chunk from the top down, two per 16-byte load, cheapest test (squared distance) first.  The first reached
+// point met is the largest reached index.  Same arithmetic as last_reached_from, so the same verdicts.
+__device__ __forceinline__ bool point_reached(const BcgParams& p, const double* __restrict__ P, int pitch, int i, double xi,
+                                              double yi, double px, double py, double pth, double sp2, double par_thr) {
+  const double dx = xi - px, dy = yi - py, d2 = dx * dx + dy * dy;
+  bool close = d2 < sp2 * (1.0 - 1e-12);
+  if (!close && d2 <= sp2 * (1.0 + 1e-12)) close = hypot(dx, dy) < p.spatial_precision;
+  if (!close) return false;
+  const double ti = __ldg(P + 2 * pitch + i), ci = __ldg(P + 3 * pitch + i), si = __ldg(P + 4 * pitch + i);
+  const double ang = fabs(wrap_angle(pth - ti));
+  const double par = ci * (px - xi) + si * (py - yi);
+  return (ang < p.angular_precision) && (par >= par_thr);
+}
+
+__device__ __forceinline__ int last_reached_thread(const BcgParams& p, const PathRef& pd, int lo, double px, double py,
+                                                   double pth) {
+  if (lo >= pd.n) return -1;
+  const double* __restrict__ P = pd.P;
+  const double* __restrict__ C = pd.C;
+  const double par_thr = -p.spatial_precision / 9;
+  const double sp2 = p.spatial_precision * p.spatial_precision;
+  const bool pairs = ((reinterpret_cast<uintptr_t>(P) & 15) == 0) && ((pd.pitch & 1) == 0);   // rows 16-byte aligned
+  for (int c = (pd.n - 1) >> 5; c >= (lo >> 5); --c) {
+    const double cx = __ldg(C + c) - px, cy = __ldg(C + pd.chunk_pitch + c) - py;
+    const double reach = p.spatial_precision + __ldg(C + 2 * pd.chunk_pitch + c);
+    if (!((cx * cx + cy * cy) < reach * reach * (1.0 + 1e-12))) continue;
+    const int i_hi = min(pd.n - 1, (c << 5) + 31), i_lo = max(lo, c << 5);
+    if (pairs) {
+      for (int j = i_hi >> 1; j >= (i_lo >> 1); --j) {
+        const double2 x2 = __ldg(reinterpret_cast<const double2*>(P) + j);
+        const double2 y2 = __ldg(reinterpret_cast<const double2*>(P + pd.pitch) + j);
+        const int i1 = 2 * j + 1, i0 = 2 * j;
+        if (i1 <= i_hi && point_reached(p, P, pd.pitch, i1, x2.y, y2.y, px, py, pth, sp2, par_thr)) return i1;
+        if (i0 >= i_lo && point_reached(p, P, pd.pitch, i0, x2.x, y2.x, px, py, pth, sp2, par_thr)) return i0;
+      }
+    } else {
+      for (int i = i_hi; i >= i_lo; --i)
+        if (point_reached(p, P, pd.pitch, i, __ldg(P + i), __ldg(P + pd.pitch + i), px, py, pth, sp2, par_thr)) return i;
+    }
+  }
+  return -1;
+}
+
+// first_beyond_radius by one thread
+__device__ __forceinline__ int first_beyond_radius_thread(const PathRef& pd, int lo, double px, double py, double radius) {
+  for (int i = max(lo, 0); i < pd.n; ++i) {
+    const double dx = __ldg(pd.P + i) - px, dy = __ldg(pd.P + pd.pitch + i) - py;
+    if (sqrt(fma(dy, dy, dx * dx)) > radius) return i;
+  }
+  return pd.n - 1;
 }
 
 // ContinuousRewardPurePursuitProviderState.update_goal (envs/base/reward.py:126-137): the first way point from

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(BCG_KIN_THREADS) kin_kernel(const BcgParams p,
   for (int r = 0; r < 3; ++r) wr.cand[r] = s[r];
   uint8_t* rec = reinterpret_cast<uint8_t*>(b.work) + (int64_t)e * BCG_WORK_BYTES;
   *reinterpret_cast<WorkCollide*>(rec) = make_work_collide(p, b, map_id, path_id, s[0], s[1], s[2]);
-  *reinterpret_cast<WorkReward*>(rec + 64) = wr;
+  *reinterpret_cast<WorkReward*>(rec + 80) = wr;
 }
 
 // work records of arbitrary poses [3][n] (stand-alone collision entry points)
@@ -295,11 +295,10 @@ __device__ __forceinline__ EgoAffine ego_affine(const BcgParams& p, const BcgMap
 
 // goal_n_state (envs/egocentric.py:141-160) by one thread
 // `target` and `drobot` (the delayed robot state x, y, th, v, w, steer, wheel) are those of the state being observed
-__device__ __forceinline__ void write_goal_n_state(const BcgParams& p, const BcgBatch& b, int e, double px, double py,
-                                                   double pth, int target, const double drobot[7],
+__device__ __forceinline__ void write_goal_n_state(const BcgParams& p, const BcgBatch& b, int e, const BcgPathDesc& pd,
+                                                   double px, double py, double pth, int target, const double drobot[7],
                                                    float* __restrict__ goal_n_state) {
   float* g = goal_n_state + (int64_t)e * 9;
-  const BcgPathDesc pd = b.paths[b.path_id[e]];
   if (target > pd.n - 1) {
 #pragma unroll
     for (int k = 0; k < 9; ++k) g[k] = 0.f;
@@ -357,11 +356,10 @@ static_assert(sizeof(EgoWork) == 128, "EgoWork records are 128 bytes");
 #define BCG_EGO_MODE_TMA 1
 #define BCG_EGO_MODE_SPANS 2
 #define BCG_EGO_MODE_TILES 3
-#define BCG_EGO_WORK_BYTES 256        // stride of the per-env records in BcgBatch.ego_work (EgoWork uses the first 128)
+#define BCG_EGO_WORK_BYTES 128        // stride of the per-env records in BcgBatch.ego_work (EgoWork / EgoTileWork)
 
-__device__ __forceinline__ EgoWork make_ego_work(const BcgParams& p, const BcgBatch& b, int map_id, double px, double py,
-                                                 double pth, int tile_capacity) {
-  const BcgMapDesc m = b.maps[map_id];
+__device__ __forceinline__ EgoWork make_ego_work(const BcgParams& p, const BcgBatch& b, int map_id, const BcgMapDesc& m,
+                                                 double px, double py, double pth, int tile_capacity) {
   EgoWork w;
   w.aff = ego_affine(p, m, px, py, pth);
   w.data_off = m.data_off;
@@ -458,7 +456,7 @@ __device__ __forceinline__ void quad_band_extent(const double qx[4], const doubl
 // rectangle touches.  Doing the clipping here (32 envs per warp) instead of in the image kernel (one env per
 // CTA) is ~50x cheaper in issued instructions.
 #define BCG_EGT_MAX_TILE_ROWS 64
-struct __align__(16) EgoTileWork {   // 256 bytes
+struct __align__(16) EgoTileWork {   // 128 bytes
   EgoAffine aff;                     // 48
   int32_t X0, Y0;                    // window origin in map pixels, multiples of (16, 8); 0 in direct mode
   int32_t ntx, nty;                  // window size in cell tiles
@@ -472,9 +470,8 @@ struct __align__(16) EgoTileWork {   // 256 bytes
   int32_t sum_off;                   // BcgMapDesc.sum_off
   uint32_t tiles_xy;                 // tiles_x | tiles_y << 16
   uint32_t tile_off16;               // BcgMapDesc.tile_off / 16 (a plane is a whole number of 16-word tiles)
-  uint8_t span[BCG_EGT_MAX_TILE_ROWS][2];   // first and last window tile column touched in tile row t (first > last: none)
 };
-static_assert(sizeof(EgoTileWork) == BCG_EGO_WORK_BYTES, "EgoTileWork records are 256 bytes");
+static_assert(sizeof(EgoTileWork) == BCG_EGO_WORK_BYTES, "EgoTileWork records are 128 bytes");
 
 // shared-memory bytes of one window buffer of ego_tiles_kernel: worst-case tile-aligned window of the crop
 __host__ __device__ inline int ego_window_capacity(const BcgParams& p) {
@@ -485,9 +482,24 @@ __host__ __device__ inline int ego_window_capacity(const BcgParams& p) {
   return (int)cap;
 }
 
-__device__ __forceinline__ void write_ego_tile_record(const BcgParams& p, const BcgBatch& b, int e, int map_id, double px,
-                                                      double py, double pth, int win_capacity) {
-  const BcgMapDesc m = b.maps[map_id];
+// corners of the crop rectangle in source pixels (the image of the crop's corner pixels under the inverted map)
+struct EgoQuad {
+  double qx[4], qy[4], xlo, xhi, ylo, yhi;
+};
+__device__ __forceinline__ EgoQuad ego_quad(const EgoAffine& A, int ego_w, int ego_h) {
+  EgoQuad q;
+  const double uw = (double)(ego_w - 1), vh = (double)(ego_h - 1);
+  q.qx[0] = A.b1; q.qx[1] = A.a11 * uw + A.b1; q.qx[2] = A.a11 * uw + A.a12 * vh + A.b1; q.qx[3] = A.a12 * vh + A.b1;
+  q.qy[0] = A.b2; q.qy[1] = A.a21 * uw + A.b2; q.qy[2] = A.a21 * uw + A.a22 * vh + A.b2; q.qy[3] = A.a22 * vh + A.b2;
+  q.xlo = fmin(fmin(q.qx[0], q.qx[1]), fmin(q.qx[2], q.qx[3]));
+  q.xhi = fmax(fmax(q.qx[0], q.qx[1]), fmax(q.qx[2], q.qx[3]));
+  q.ylo = fmin(fmin(q.qy[0], q.qy[1]), fmin(q.qy[2], q.qy[3]));
+  q.yhi = fmax(fmax(q.qy[0], q.qy[1]), fmax(q.qy[2], q.qy[3]));
+  return q;
+}
+
+__device__ __forceinline__ void write_ego_tile_record(const BcgParams& p, const BcgBatch& b, int e, int map_id,
+                                                      const BcgMapDesc& m, double px, double py, double pth, int win_capacity) {
   EgoTileWork* rec = reinterpret_cast<EgoTileWork*>(reinterpret_cast<uint8_t*>(b.ego_work) + (int64_t)e * BCG_EGO_WORK_BYTES);
   EgoTileWork w;
   w.aff = ego_affine(p, m, px, py, pth, w.fwd);
@@ -503,17 +515,12 @@ __device__ __forceinline__ void write_ego_tile_record(const BcgParams& p, const 
   w.ctile_off = m.cell_tile_off;
   // every sample is X = floor(x + 0.5 + d), |d| <= 2^-10, of a point x of the rotated crop rectangle: the
   // rectangle grown by 0.51 px bounds all samples
-  const EgoAffine& A = w.aff;
-  const double uw = (double)(p.ego_w - 1), vh = (double)(p.ego_h - 1);
-  const double qx[4] = {A.b1, A.a11 * uw + A.b1, A.a11 * uw + A.a12 * vh + A.b1, A.a12 * vh + A.b1};
-  const double qy[4] = {A.b2, A.a21 * uw + A.b2, A.a21 * uw + A.a22 * vh + A.b2, A.a22 * vh + A.b2};
+  const EgoQuad q = ego_quad(w.aff, p.ego_w, p.ego_h);
   const double lim = 1048576.0;
-  const double xlo = fmin(fmin(qx[0], qx[1]), fmin(qx[2], qx[3])), xhi = fmax(fmax(qx[0], qx[1]), fmax(qx[2], qx[3]));
-  const double ylo = fmin(fmin(qy[0], qy[1]), fmin(qy[2], qy[3])), yhi = fmax(fmax(qy[0], qy[1]), fmax(qy[2], qy[3]));
-  const bool sane = xlo > -lim && xhi < lim && ylo > -lim && yhi < lim;   // false for NaN too
+  const bool sane = q.xlo > -lim && q.xhi < lim && q.ylo > -lim && q.yhi < lim;   // false for NaN too
   if (sane) {
-    const int x0 = (int)floor(xlo - 0.51) & ~15, y0 = (int)floor(ylo - 0.51) & ~7;
-    const int x1 = (int)ceil(xhi + 0.51), y1 = (int)ceil(yhi + 0.51);
+    const int x0 = (int)floor(q.xlo - 0.51) & ~15, y0 = (int)floor(q.ylo - 0.51) & ~7;
+    const int x1 = (int)ceil(q.xhi + 0.51), y1 = (int)ceil(q.yhi + 0.51);
     const int ntx = (x1 >> 4) - (x0 >> 4) + 1, nty = (y1 >> 3) - (y0 >> 3) + 1;
     if (ntx <= 16 && nty <= BCG_EGT_MAX_TILE_ROWS && nty * 128 * (ntx | 1) <= win_capacity) {   // 16: one staging pass per tile row
       w.mode = BCG_EGO_MODE_TILES;
@@ -527,66 +534,61 @@ __device__ __forceinline__ void write_ego_tile_record(const BcgParams& p, const 
   const uint4* src = reinterpret_cast<const uint4*>(&w);
 #pragma unroll
   for (int k = 0; k < 8; ++k) dst[k] = src[k];
-  if (w.mode == BCG_EGO_MODE_TILES) {
-    // x-extent of the crop rectangle within each row of tiles.  The rectangle is convex, so over a band of rows its
-    // left boundary is the maximum of the lines through its left edges (a convex function of y: smallest at a band end
-    // or at the leftmost vertex) and its right boundary the minimum of the lines through its right edges.  Two line
-    // evaluations per edge and band, one inverse slope per edge, no clipping.
-    const int ttx0 = w.X0 >> 4;
-    const bool ccw = (qx[1] - qx[0]) * (qy[3] - qy[0]) - (qy[1] - qy[0]) * (qx[3] - qx[0]) > 0.0;
-    double inv[4], lsel[4], rsel[4];     // a line counts for the left (right) boundary where lsel (rsel) is 0, else +-BIG
-    double y_at_xlo = qy[0], y_at_xhi = qy[0];
-    const double BIG = 1e300;
+}
+
+// Which cell tiles of row t of the window (8 source rows) the rotated crop rectangle touches: first | last << 8 window
+// tile column (first > last: none).  Evaluated by the egocentric kernels themselves, lane <-> tile row, one env ahead
+// of its use: for a thread-per-env kernel this loop was 4 k serial fp64 instructions per env, for a warp with one band
+// per lane it is ~100.  The rectangle is convex, so over a band of rows its left boundary is the maximum of the lines
+// through its left edges (a convex function of y: smallest at a band end or at the leftmost vertex) and its right
+// boundary the minimum of the lines through its right edges.  A span only has to COVER the samples (the exact
+// fixed-point rule decides every pixel later), so it is worked out in float32 on window-relative coordinates (< 1024,
+// rounding errors ~1e-4 px) with the 0.51 px sample margin widened to 0.53.
+__device__ __forceinline__ uint32_t ego_band_span(const EgoAffine& A, int ego_w, int ego_h, int X0, int Y0, int ntx, int nty,
+                                                  int t) {
+  const double uw = (double)(ego_w - 1), vh = (double)(ego_h - 1);
+  const double bx = A.b1 - (double)X0, by = A.b2 - (double)Y0;
+  const float qx[4] = {(float)bx, (float)(A.a11 * uw + bx), (float)(A.a11 * uw + A.a12 * vh + bx), (float)(A.a12 * vh + bx)};
+  const float qy[4] = {(float)by, (float)(A.a21 * uw + by), (float)(A.a21 * uw + A.a22 * vh + by), (float)(A.a22 * vh + by)};
+  const float xlo = fminf(fminf(qx[0], qx[1]), fminf(qx[2], qx[3])), xhi = fmaxf(fmaxf(qx[0], qx[1]), fmaxf(qx[2], qx[3]));
+  const float ylo = fminf(fminf(qy[0], qy[1]), fminf(qy[2], qy[3])), yhi = fmaxf(fmaxf(qy[0], qy[1]), fmaxf(qy[2], qy[3]));
+  const bool ccw = (qx[1] - qx[0]) * (qy[3] - qy[0]) - (qy[1] - qy[0]) * (qx[3] - qx[0]) > 0.f;
+  const float BIG = 1e30f, M = 0.53f;
+  const float y0 = fmaxf((float)(8 * t) - M, ylo), y1 = fminf((float)(8 * t + 7) + M, yhi);
+  int ts = 1, te = 0;
+  if (t < nty && y0 <= y1) {
+    float l0 = -BIG, l1 = -BIG, r0 = BIG, r1 = BIG;
+    float y_at_xlo = qy[0], y_at_xhi = qy[0];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const double dy = qy[(k + 1) & 3] - qy[k];
-      inv[k] = dy != 0.0 ? (qx[(k + 1) & 3] - qx[k]) / dy : 0.0;
-      const bool is_left = ccw ? dy < 0.0 : dy > 0.0, is_right = ccw ? dy > 0.0 : dy < 0.0;   // horizontal edges: neither
-      lsel[k] = is_left ? 0.0 : -BIG;
-      rsel[k] = is_right ? 0.0 : BIG;
+      const float dy = qy[(k + 1) & 3] - qy[k];
+      const float inv = dy != 0.f ? (qx[(k + 1) & 3] - qx[k]) / dy : 0.f;
+      const bool is_left = ccw ? dy < 0.f : dy > 0.f, is_right = ccw ? dy > 0.f : dy < 0.f;   // horizontal edges: neither
+      const float v0 = qx[k] + (y0 - qy[k]) * inv, v1 = qx[k] + (y1 - qy[k]) * inv;
+      if (is_left) { l0 = fmaxf(l0, v0); l1 = fmaxf(l1, v1); }
+      if (is_right) { r0 = fminf(r0, v0); r1 = fminf(r1, v1); }
       if (qx[k] == xlo) y_at_xlo = qy[k];
       if (qx[k] == xhi) y_at_xhi = qy[k];
     }
-    for (int t8 = 0; t8 < w.nty; t8 += 8) {     // eight spans per 16-byte store
-      uint32_t packed[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int t = t8 + j;
-        const double y0 = fmax((double)(w.Y0 + 8 * t) - 0.51, ylo), y1 = fmin((double)(w.Y0 + 8 * t + 7) + 0.51, yhi);
-        int ts = 1, te = 0;
-        if (t < w.nty && y0 <= y1) {
-          double l0 = -BIG, l1 = -BIG, r0 = BIG, r1 = BIG;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const double v0 = qx[k] + (y0 - qy[k]) * inv[k], v1 = qx[k] + (y1 - qy[k]) * inv[k];
-            l0 = fmax(l0, lsel[k] != 0.0 ? lsel[k] : v0);
-            l1 = fmax(l1, lsel[k] != 0.0 ? lsel[k] : v1);
-            r0 = fmin(r0, rsel[k] != 0.0 ? rsel[k] : v0);
-            r1 = fmin(r1, rsel[k] != 0.0 ? rsel[k] : v1);
-          }
-          double xmin = fmin(l0, l1), xmax = fmax(r0, r1);
-          if (y_at_xlo >= y0 && y_at_xlo <= y1) xmin = xlo;
-          if (y_at_xhi >= y0 && y_at_xhi <= y1) xmax = xhi;
-          xmin = fmax(xmin, xlo);                 // rounding of nearly horizontal edges must not leave the rectangle
-          xmax = fmin(xmax, xhi);
-          ts = max(((int)floor(xmin - 0.51) >> 4) - ttx0, 0);
-          te = min(((int)ceil(xmax + 0.51) >> 4) - ttx0, w.ntx - 1);
-        }
-        packed[j >> 1] |= (uint32_t)(ts | (te << 8)) << (16 * (j & 1));
-      }
-      *reinterpret_cast<uint4*>(rec->span[t8]) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-    }
+    float xmin = fminf(l0, l1), xmax = fmaxf(r0, r1);
+    if (y_at_xlo >= y0 && y_at_xlo <= y1) xmin = xlo;
+    if (y_at_xhi >= y0 && y_at_xhi <= y1) xmax = xhi;
+    xmin = fmaxf(xmin, xlo);                // rounding of nearly horizontal edges must not leave the rectangle
+    xmax = fminf(xmax, xhi);
+    ts = max((int)floorf(xmin - M) >> 4, 0);
+    te = min((int)ceilf(xmax + M) >> 4, ntx - 1);
   }
+  return (uint32_t)(ts | (te << 8));
 }
 
 // the per-env record of whichever egocentric kernel the batch is set up for
-__device__ __forceinline__ void write_ego_record(const BcgParams& p, const BcgBatch& b, int e, int map_id, double px,
-                                                 double py, double pth, int cap) {
+__device__ __forceinline__ void write_ego_record(const BcgParams& p, const BcgBatch& b, int e, int map_id,
+                                                 const BcgMapDesc& m, double px, double py, double pth, int cap) {
   if (b.cell_tile_arena) {
-    write_ego_tile_record(p, b, e, map_id, px, py, pth, cap);
+    write_ego_tile_record(p, b, e, map_id, m, px, py, pth, cap);
   } else {
     *reinterpret_cast<EgoWork*>(reinterpret_cast<uint8_t*>(b.ego_work) + (int64_t)e * BCG_EGO_WORK_BYTES) =
-        make_ego_work(p, b, map_id, px, py, pth, cap);
+        make_ego_work(p, b, map_id, m, px, py, pth, cap);
   }
 }
 
@@ -662,6 +664,7 @@ __global__ void __launch_bounds__(BCG_COMMIT_THREADS, BCG_COMMIT_MIN_BLOCKS) com
   __syncthreads();                                         // nothing of the state has been written yet
   // ---- phase 2 -------------------------------------------------------------------------------------------------------
   if (active && role == 0) {
+    if (e == 0 && b.ego_list) b.ego_list[N] = b.ego_list[N + 1] = 0;     // hand-over count, env counter of the sparse kernel
     delay_line<3>(sf + (int64_t)L.ring_pose * N, N, qp, p.delay_pose, dpose);
     delay_line<7>(sf + (int64_t)L.ring_state * N, N, qs, p.delay_state, dstate);
     if (out.reward) out.reward[e] = reward;
@@ -721,8 +724,11 @@ __global__ void __launch_bounds__(BCG_COMMIT_THREADS, BCG_COMMIT_MIN_BLOCKS) com
     // map, source window and goal vector from the same values
     const bool true_pose = p.ego_variant == 1;             // true robot pose vs observed (delayed) pose
     const double opx = true_pose ? c[0] : dpose[0], opy = true_pose ? c[1] : dpose[1], opth = true_pose ? c[2] : dpose[2];
-    if (out.ego_image) write_ego_record(p, b, e, b.map_id[e], opx, opy, opth, ego_cap);
-    if (out.goal_n_state) write_goal_n_state(p, b, e, opx, opy, opth, target, dstate, out.goal_n_state);
+    if (out.ego_image) {
+      const int map_id = b.map_id[e];
+      write_ego_record(p, b, e, map_id, b.maps[map_id], opx, opy, opth, ego_cap);
+    }
+    if (out.goal_n_state) write_goal_n_state(p, b, e, b.paths[b.path_id[e]], opx, opy, opth, target, dstate, out.goal_n_state);
   }
   // episode statistics: one atomic set per warp that saw an episode end
   if (__any_sync(BCG_FULL, ev != 0)) {
@@ -743,6 +749,233 @@ __global__ void __launch_bounds__(BCG_COMMIT_THREADS, BCG_COMMIT_MIN_BLOCKS) com
   }
 }
 
+// ---- state_kernel: the whole of _resolve_state_transition + reward + done for one env per thread -----------------------
+// PlanEnv.step (envs/base/env.py:334-361) up to the observation, fused: control delay (:371-373), robot model
+// (tricycle_model.py:478-538 / differential_drive.py:236-265) with Philox noise, footprint lookup, pose_collides
+// (env.py:464-489) on the lethal tile plane, rollback (:458-459), pose / robot-state delay lines (:377-389), time / iter /
+// sticky collision (:383-393), reward (reward.py:214-259 or :331-350), done (env.py:407-419), episode statistics,
+// auto-reset (:293-303), the compact observation, goal_n_state (egocentric.py:152-159) and the 128-byte record the
+// egocentric kernel starts from.
+// One thread owns one env from the first load to the last store, so nothing passes through scratch rows or work
+// records between launches (round 1: three kernels, 0.158 ms per 65 536 envs, each a single wave bound by one thread's
+// dependent chain; here one chain and one launch).  Every state access is a coalesced SoA row.  The two gathers are
+// thread-serial: collide_thread reads 16-byte quarters of only the non-empty tiles under the footprint,
+// last_reached_thread scans candidate chunks from the top with 16-byte point pairs.
+#ifndef BCG_STATE_THREADS
+#define BCG_STATE_THREADS 64
+#endif
+#ifndef BCG_STATE_MIN_BLOCKS
+#define BCG_STATE_MIN_BLOCKS 8        // register budget: 65536 / (threads x blocks) = 128
+#endif
+__global__ void __launch_bounds__(BCG_STATE_THREADS, BCG_STATE_MIN_BLOCKS)
+state_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L, const void* __restrict__ actions,
+             const int action_is_f64, const uint64_t step_index_arg, const BcgStepOut out, const int ego_cap) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = e < b.n_envs;
+  const int64_t N = b.n_envs;
+  const uint64_t step_index = b.step_counter ? *reinterpret_cast<const volatile uint64_t*>(b.step_counter) : step_index_arg;
+  double ev_ret = 0.0, ev_len = 0.0;
+  int ev = 0, ev_col = 0, ev_goal = 0, ev_to = 0;
+  if (e == 0 && b.ego_list) b.ego_list[N] = b.ego_list[N + 1] = 0;       // hand-over count, env counter of the sparse kernel
+  if (active) {
+    double* const sf = b.state_f + e;
+    int32_t* const si = b.state_i + e;
+    // ---- everything that is read from rows (independent loads, issued together) --------------------------------------
+    double u[2];
+    if (action_is_f64) {
+      const double2 a = reinterpret_cast<const double2*>(actions)[e];
+      u[0] = a.x;
+      u[1] = a.y;
+    } else {
+      const float2 a = reinterpret_cast<const float2*>(actions)[e];
+      u[0] = (double)a.x;
+      u[1] = (double)a.y;
+    }
+    double s[7];
+#pragma unroll
+    for (int r = 0; r < 7; ++r) s[r] = sf[(BCG_F_ROBOT + r) * N];
+    const int map_id = b.map_id[e], path_id = b.path_id[e];
+    double min_dist = sf[BCG_F_MIN_DIST * N];
+    const double time = sf[BCG_F_TIME * N] + p.dt;
+    double ep_return = sf[BCG_F_EP_RETURN * N];
+    int target = si[BCG_I_TARGET * N];
+    const int collided = si[BCG_I_COLLIDED * N], iter = si[BCG_I_ITER * N];
+    int qp = si[BCG_I_QP * N], qs = si[BCG_I_QS * N];
+    const BcgMapDesc m = b.maps[map_id];
+    const BcgPathDesc pdsc = b.paths[path_id];
+    const PathRef pd = path_ref(b, pdsc);
+    const bool pursuit = p.reward_kind == BCG_REWARD_PURE_PURSUIT;
+    double gx = 0.0, gy = 0.0;
+    bool goal_before = target > pd.n - 1;
+    if (pursuit) {                                       // reward.py:139-149 on the pose observed before this step
+      gx = __ldg(pd.P + pd.n - 1);
+      gy = __ldg(pd.P + pd.pitch + pd.n - 1);
+      goal_before = hypot(gx - sf[(BCG_F_DPOSE + 0) * N], gy - sf[(BCG_F_DPOSE + 1) * N]) < 1.0;
+    }
+    const double old_pose[3] = {s[0], s[1], s[2]};
+    // ---- env.py:371-373 control delay, then the robot model ----------------------------------------------------------------
+    if (p.delay_control > 0) {
+      int q = si[BCG_I_QC * N];
+      delay_line<2>(sf + (int64_t)L.ring_control * N, N, q, p.delay_control, u);
+      si[BCG_I_QC * N] = q;
+    }
+    robot_step(s, u[0], u[1], p, p.env_id_base + (uint64_t)e, step_index);
+    if (b.cand) {                                        // the proposed pose, for the stand-alone collision entry points
+#pragma unroll
+      for (int r = 0; r < 3; ++r) b.cand[r * N + e] = s[r];
+    }
+    // ---- env.py:455 pose_collides of the proposed pose ------------------------------------------------------------------------
+    FootBox fb;
+    fb.bin = find_foot_bin(b.lut, s[2], b.status);
+    {
+      const short4 h = __ldg(reinterpret_cast<const short4*>(b.lut.header) + fb.bin);     // xmin, ymin, nrows, width
+      fb.X0 = world_to_pixel_1d(s[0], m.origin_x, p.inv_resolution) + h.x;
+      fb.Y0 = world_to_pixel_1d(s[1], m.origin_y, p.inv_resolution) + h.y;
+      fb.nrows = h.z;
+      fb.fwidth = h.w;
+    }
+    const bool hit = collide_thread(b.lut, b.tile_arena + m.tile_off, b.occ_sum_arena ? b.occ_sum_arena + m.sum_off : nullptr,
+                                    m.tiles_x, m.width, m.height, fb);
+    if (hit) {  // env.py:458-459 + tricycle_model.py:471-476: pose restored, v = w = 0, wheel / steer command kept
+      s[0] = old_pose[0];
+      s[1] = old_pose[1];
+      s[2] = old_pose[2];
+      s[3] = 0.0;
+      s[4] = 0.0;
+    }
+    // ---- env.py:377-389 pose and robot-state delay lines ----------------------------------------------------------------------
+    double dpose[3] = {s[0], s[1], s[2]};
+    double dstate[7];
+#pragma unroll
+    for (int r = 0; r < 7; ++r) dstate[r] = s[r];
+    delay_line<3>(sf + (int64_t)L.ring_pose * N, N, qp, p.delay_pose, dpose);
+    delay_line<7>(sf + (int64_t)L.ring_state * N, N, qs, p.delay_state, dstate);
+    // ---- reward of the pose State.pose now holds (reward.py:214-259 / :331-350) ---------------------------------------------
+    double reward = 0.0;
+    bool goal;
+    if (pursuit) {
+      target = first_beyond_radius_thread(pd, target, dpose[0], dpose[1], 2.0);
+      const double d = hypot(gx - dpose[0], gy - dpose[1]);
+      reward = -0.05;
+      reward += min_dist - d;
+      if (collided || hit) reward -= 100;
+      min_dist = d;
+      goal = d < 1.0;
+    } else {
+      if (!goal_before) {
+        const double tx = __ldg(pd.P + target), ty = __ldg(pd.P + pd.pitch + target);   // issued before the scan needs them
+        const int last = last_reached_thread(p, pd, target, dpose[0], dpose[1], dpose[2]);
+        if (last >= target) {
+          target = last + 1;
+          if (target > pd.n - 1) {
+            min_dist = 0.0;
+          } else {
+            min_dist = hypot(__ldg(pd.P + target) - dpose[0], __ldg(pd.P + pd.pitch + target) - dpose[1]);
+          }
+          reward = 1.0;
+        } else {
+          const double d = hypot(tx - dpose[0], ty - dpose[1]);
+          if (d < min_dist) {
+            reward = (min_dist - d) * p.progress_multiplier;
+            min_dist = d;
+          }
+        }
+      }
+      goal = target > pd.n - 1;
+    }
+    ep_return += reward;
+    // ---- env.py:383-393, :407-419 ------------------------------------------------------------------------------------------------
+    const bool done_before = goal_before || (iter >= p.iteration_timeout) || (collided != 0);
+    const int iter_after = iter + 1;
+    const int collided_after = collided | (hit ? 1 : 0);
+    const bool timed_out = iter_after >= p.iteration_timeout;
+    const bool done = goal || timed_out || (collided_after != 0);
+    const bool reset_now = done && p.auto_reset;
+    if (out.reward) out.reward[e] = reward;
+    if (out.done) out.done[e] = done ? 1 : 0;
+    if (out.hit) out.hit[e] = hit ? 1 : 0;
+    if (done && !done_before) {
+      ev = 1;
+      ev_ret = ep_return;
+      ev_len = (double)iter_after;
+      ev_col = collided_after;
+      ev_goal = goal ? 1 : 0;
+      ev_to = timed_out ? 1 : 0;
+    }
+    double otime = time;
+    if (reset_now) {                                     // env.py:293-303: the state (and the observation) is the initial one
+      for (int r = 0; r < L.n_frows; ++r) sf[(int64_t)r * N] = b.init_f[(int64_t)r * N + e];
+      for (int r = 0; r < L.n_irows; ++r) si[(int64_t)r * N] = b.init_i[(int64_t)r * N + e];
+      target = b.init_i[(int64_t)BCG_I_TARGET * N + e];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) dpose[r] = b.init_f[(int64_t)(BCG_F_DPOSE + r) * N + e];
+#pragma unroll
+      for (int r = 0; r < 7; ++r) dstate[r] = b.init_f[(int64_t)(BCG_F_DROBOT + r) * N + e];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) s[r] = b.init_f[(int64_t)(BCG_F_ROBOT + r) * N + e];
+      otime = b.init_f[(int64_t)BCG_F_TIME * N + e];
+    } else {
+#pragma unroll
+      for (int r = 0; r < 7; ++r) sf[(BCG_F_ROBOT + r) * N] = s[r];
+#pragma unroll
+      for (int r = 0; r < 7; ++r) sf[(BCG_F_DROBOT + r) * N] = dstate[r];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) sf[(BCG_F_DPOSE + r) * N] = dpose[r];
+      sf[BCG_F_TIME * N] = time;
+      sf[BCG_F_MIN_DIST * N] = min_dist;
+      sf[BCG_F_EP_RETURN * N] = ep_return;
+      si[BCG_I_ITER * N] = iter_after;
+      si[BCG_I_TARGET * N] = target;
+      si[BCG_I_COLLIDED * N] = collided_after;
+      si[BCG_I_QP * N] = qp;
+      si[BCG_I_QS * N] = qs;
+    }
+    if (out.obs_vec) {
+      float4* o = reinterpret_cast<float4*>(out.obs_vec + (int64_t)e * 12);
+      o[0] = make_float4((float)dpose[0], (float)dpose[1], (float)dpose[2], (float)dstate[0]);
+      o[1] = make_float4((float)dstate[1], (float)dstate[2], (float)dstate[3], (float)dstate[4]);
+      o[2] = make_float4((float)dstate[5], (float)dstate[6], (float)otime, (float)target);
+    }
+    if (out.ego_image || out.goal_n_state) {
+      // the observation the egocentric kernel will render is that of the state just written
+      const bool true_pose = p.ego_variant == 1;         // true robot pose vs observed (delayed) pose
+      const double opx = true_pose ? s[0] : dpose[0], opy = true_pose ? s[1] : dpose[1], opth = true_pose ? s[2] : dpose[2];
+      if (out.ego_image) write_ego_record(p, b, e, map_id, m, opx, opy, opth, ego_cap);
+      if (out.goal_n_state) write_goal_n_state(p, b, e, pdsc, opx, opy, opth, target, dstate, out.goal_n_state);
+    }
+  }
+  // episode statistics: one atomic set per warp that saw an episode end
+  if (__any_sync(BCG_FULL, ev != 0)) {
+    double v[6] = {(double)ev, ev_ret, ev_len, (double)ev_col, (double)ev_goal, (double)ev_to};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(BCG_FULL, v[k], o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(b.stats + BCG_STAT_EPISODES, v[0]);
+      atomicAdd(b.stats + BCG_STAT_RETURN, v[1]);
+      atomicAdd(b.stats + BCG_STAT_LENGTH, v[2]);
+      atomicAdd(b.stats + BCG_STAT_COLLIDED, v[3]);
+      atomicAdd(b.stats + BCG_STAT_GOAL, v[4]);
+      atomicAdd(b.stats + BCG_STAT_TIMEOUT, v[5]);
+    }
+  }
+  // device-side step counter (CUDA-graph replays cannot change a kernel argument): the last CTA to finish bumps it
+  if (b.step_counter) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      unsigned long long* const ctr = reinterpret_cast<unsigned long long*>(b.step_counter);
+      const unsigned long long ticket = atomicAdd(ctr + 1, 1ull);
+      if (ticket == (unsigned long long)gridDim.x - 1ull) {
+        ctr[1] = 0ull;
+        ctr[0] = step_index + 1ull;
+      }
+    }
+  }
+}
+
 // make_initial_state (env.py:179-214) + generate_initial_state (reward.py:261-288) of env e by one warp
 __device__ __forceinline__ void init_env_state(const BcgParams& p, const BcgBatch& b, const BcgStateLayout& L, int e,
                                                const PathRef& pd, unsigned lane) {
@@ -755,7 +988,7 @@ __device__ __forceinline__ void init_env_state(const BcgParams& p, const BcgBatc
     target = 1;
     min_dist = hypot(P[pd.n - 1] - x0, P[pd.pitch + pd.n - 1] - y0);
   } else {
-    const int last = last_reached_from(p, pd, 0, x0, y0, t0, lane);
+    const int last = last_reached_from<true>(p, pd, 0, x0, y0, t0, lane);   // the generators wrote the rows in this launch
     target = last + 1;
     if (target > pd.n - 1) {
       if (lane == 0) atomicAdd(b.status + BCG_STATUS_PATH_EXHAUSTED, 1u);
@@ -1168,6 +1401,27 @@ __global__ void __launch_bounds__(256, 6) collision_kernel(const BcgBatch b, uin
   }
 }
 
+// pose_collides of the poses whose work records are in b.work, one THREAD per env (collide_thread): the form the state
+// kernel uses, and the one the collision roofline is measured on.  Per env it reads the 64-byte record, one or two tile
+// summary words per 16-row band and 16-byte quarters of the non-empty tiles under the footprint only.
+__global__ void __launch_bounds__(128) collision_thread_kernel(const BcgBatch b, uint8_t* __restrict__ flags) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= b.n_envs) return;
+  const uint4* rec = reinterpret_cast<const uint4*>(work_collide(b.work, e));
+  WorkCollide f;
+  uint4* fw = reinterpret_cast<uint4*>(&f);
+#pragma unroll
+  for (int k = 0; k < 5; ++k) fw[k] = __ldg(rec + k);
+  FootBox fb;
+  fb.X0 = f.X0;
+  fb.Y0 = f.Y0;
+  fb.nrows = f.nrows;
+  fb.fwidth = f.fwidth;
+  fb.bin = f.bin;
+  const uint32_t* sum = b.occ_sum_arena ? b.occ_sum_arena + f.sum_off : nullptr;
+  flags[e] = collide_thread(b.lut, b.tile_arena + f.tile_off, sum, f.tiles_x, f.map_w, f.map_h, fb) ? 1 : 0;
+}
+
 // ---- TMA / mbarrier primitives (sm_90+ PTX; SASS: UTMALDG, SYNCS) ------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -1411,12 +1665,24 @@ __global__ void __launch_bounds__(BCG_EGT_THREADS, BCG_EGT_CTAS) ego_tiles_kerne
   cp_async_commit();
   cp_async_wait_all();
   __syncthreads();
+  // tile spans of the window rows (ego_band_span), thread <-> tile row, computed one env ahead of their use
+  __shared__ uint16_t span_s[2][BCG_EGT_MAX_TILE_ROWS];
+  auto make_spans = [&](int slot, int buf) {
+    const int t = tid - (NT - BCG_EGT_MAX_TILE_ROWS);          // the last two warps
+    if (t < 0) return;
+    const EgoTileWork* q = reinterpret_cast<const EgoTileWork*>(rec_s + slot * BCG_EGO_WORK_BYTES);
+    if (q->mode != BCG_EGO_MODE_TILES || t >= q->nty) return;
+    span_s[buf][t] = (uint16_t)ego_band_span(q->aff, ego_w, ego_h, q->X0, q->Y0, q->ntx, q->nty, t);
+  };
+  make_spans(0, 0);
+  __syncthreads();
 
   int e = e0;
   for (int it = 0; e < n; e += G, ++it) {
     const int slot = it & (BCG_EGT_REC_SLOTS - 1);
     fetch_record(e + RD * G, (it + RD) & (BCG_EGT_REC_SLOTS - 1));
     cp_async_commit();
+    if (e + G < n) make_spans((it + 1) & (BCG_EGT_REC_SLOTS - 1), (it + 1) & 1);   // its record landed an iteration ago
     const EgoTileWork* r = reinterpret_cast<const EgoTileWork*>(rec_s + slot * BCG_EGO_WORK_BYTES);
     const int mode = r->mode, X0 = r->X0, Y0 = r->Y0, ntx = r->ntx, nty = r->nty;
     const int pitch_b = 16 * (ntx | 1);          // 16 * odd: staging writes and rotated reads spread over the banks
@@ -1429,7 +1695,7 @@ __global__ void __launch_bounds__(BCG_EGT_THREADS, BCG_EGT_CTAS) ego_tiles_kerne
       const uint8_t* const src_lane = b.cell_tile_arena + r->ctile_off + piece * 16 + ((int64_t)ttx0 + sub) * 128;
       const uint32_t dst_lane = win_u32 + piece * pitch_b + sub * 16;
       const int lo_map = -ttx0, hi_map = ctx - 1 - ttx0;       // window tile columns that exist in the map
-      const uint32_t span_u32 = rec_u32 + slot * BCG_EGO_WORK_BYTES + 128;
+      const uint32_t span_u32 = smem_u32(span_s[it & 1]);
       for (int t = warp; t < nty; t += NW) {
         const uint32_t sp = lds_u16(span_u32 + 2 * t);
         const int ts = sp & 0xff, te = sp >> 8;
@@ -1646,6 +1912,17 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
   cp_async_wait_all();
   __syncthreads();
 
+  // tile spans of the window rows (ego_band_span), lane <-> tile row, computed by the last warp one env ahead of their use
+  __shared__ uint16_t span_s[2][BCG_EGT_MAX_TILE_ROWS];
+  auto make_spans = [&](int slot, int buf) {
+    if (warp != NT / 32 - 1) return;
+    const EgoTileWork* q = reinterpret_cast<const EgoTileWork*>(rec_s + slot * BCG_EGO_WORK_BYTES);
+    if (q->mode != BCG_EGO_MODE_TILES || (q->dense_map & 1)) return;
+    for (int t = lane; t < q->nty; t += 32)
+      span_s[buf][t] = (uint16_t)ego_band_span(q->aff, ego_w, ego_h, q->X0, q->Y0, q->ntx, q->nty, t);
+  };
+  make_spans(0, 0);
+  __syncthreads();
   uint32_t pf_lo = 0u, pf_hi = 0u;              // summary words of the env about to be rendered
   if (SUM) summary_words(reinterpret_cast<const EgoTileWork*>(rec_s), pf_lo, pf_hi);
 #if BCG_EGS_DYNAMIC
@@ -1670,6 +1947,7 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
     const uint32_t cur_lo = pf_lo, cur_hi = pf_hi;
     if (SUM && e_next < n)
       summary_words(reinterpret_cast<const EgoTileWork*>(rec_s + ((it + 1) & (BCG_EGS_REC_SLOTS - 1)) * BCG_EGO_WORK_BYTES), pf_lo, pf_hi);
+    if (e_next < n) make_spans((it + 1) & (BCG_EGS_REC_SLOTS - 1), (it + 1) & 1);
     const EgoTileWork* r = reinterpret_cast<const EgoTileWork*>(rec_s + slot * BCG_EGO_WORK_BYTES);
     const int mode = r->mode, X0 = r->X0, Y0 = r->Y0, ntx = r->ntx, nty = r->nty;
     uint8_t* const dst = image + (int64_t)e * npx;
@@ -1719,7 +1997,7 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
       const uint4* occ = reinterpret_cast<const uint4*>(b.occ_tile_arena + ((int64_t)r->tile_off16 << 4));
       const int g = lane & 3;                                                     // rows 4 g .. 4 g + 3 of the tile
       constexpr int TPR = NT / 4;                                                // tiles per round
-      const uint32_t span_u32 = rec_u32 + slot * BCG_EGO_WORK_BYTES + 128;
+      const uint32_t span_u32 = smem_u32(span_s[par]);
       auto expand = [&](const uint32_t qhead, const int nitems) {
         uint4 wd = make_uint4(0u, 0u, 0u, 0u);
         uint32_t tag = 0u;
@@ -1904,6 +2182,30 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
         }
 #endif
       }
+    } else if (b.flags & BCG_BATCH_SPARSE_EGO_ONLY) {
+      // No dense pass follows this kernel (the host knows that no map of the batch is dense): the rare window that
+      // overflows the cell list, or lies outside any sane range, is rendered here by the bounds-checked per-pixel gather.
+      const EgoAffine A = r->aff;
+      for (int i = tid; i < ego_w + ego_h; i += NT) {
+        if (i < ego_w) {
+          egs_tab[i] = make_int2(__double2int_rn(A.a11 * i * 1024), __double2int_rn(A.a21 * i * 1024));
+        } else {
+          const int t = i - ego_w;
+          egs_tab[i] = make_int2(__double2int_rn((A.a12 * t + A.b1) * 1024) + 512, __double2int_rn((A.a22 * t + A.b2) * 1024) + 512);
+        }
+      }
+      __syncthreads();
+      const BcgMapDesc* md = b.maps + r->map_id;
+      const uint8_t* src = b.map_arena + md->data_off;
+      const int mw = md->width, mh = md->height, mpitch = md->pitch;
+      for (int i = tid; i < npx; i += NT) {
+        const int vv = i / ego_w, uu = i - vv * ego_w;
+        const int2 aa = egs_tab[uu], bb = egs_tab[ego_w + vv];
+        const long long X = ((long long)aa.x + bb.x) >> 10, Y = ((long long)aa.y + bb.y) >> 10;
+        uint8_t val = 0;
+        if (X >= 0 && X < mw && Y >= 0 && Y < mh) val = __ldg(src + Y * mpitch + X);
+        dst[i] = val;
+      }
     } else if (tid == 0) {
       const int at = atomicAdd(b.ego_list + n, 1);
       b.ego_list[at] = e;
@@ -1925,12 +2227,16 @@ __global__ void __launch_bounds__(128) ego_prep_kernel(const BcgParams p, const 
   const double* sf = b.state_f + e;
   const int prow = p.ego_variant == 1 ? BCG_F_ROBOT : BCG_F_DPOSE;
   const double px = sf[(prow + 0) * N], py = sf[(prow + 1) * N], pth = sf[(prow + 2) * N];
-  if (want_image) write_ego_record(p, b, e, b.map_id[e], px, py, pth, ego_cap);
+  if (want_image) {
+    const int map_id = b.map_id[e];
+    write_ego_record(p, b, e, map_id, b.maps[map_id], px, py, pth, ego_cap);
+  }
+  if (e == 0 && b.ego_list) b.ego_list[N] = b.ego_list[N + 1] = 0;       // hand-over count, env counter of the sparse kernel
   if (goal_n_state) {
     double drobot[7];
 #pragma unroll
     for (int r = 0; r < 7; ++r) drobot[r] = sf[(BCG_F_DROBOT + r) * N];
-    write_goal_n_state(p, b, e, px, py, pth, b.state_i[BCG_I_TARGET * N + e], drobot, goal_n_state);
+    write_goal_n_state(p, b, e, b.paths[b.path_id[e]], px, py, pth, b.state_i[BCG_I_TARGET * N + e], drobot, goal_n_state);
   }
 }
 
@@ -2145,8 +2451,8 @@ int bcg_kinematic_step(const BcgParams* p, const BcgBatch* b, const void* action
                        uint64_t step_index, void* stream) {
   if (int rc = check_batch(p, b)) return rc;
   BCG_REQUIRE(actions, "null actions");
-  kin_kernel<<<blocks_for(b->n_envs, 128), 128, 0, (cudaStream_t)stream>>>(*p, *b, make_layout(*p), actions,
-                                                                          action_is_f64, step_index);
+  kin_kernel<<<blocks_for(b->n_envs, BCG_KIN_THREADS), BCG_KIN_THREADS, 0, (cudaStream_t)stream>>>(*p, *b, make_layout(*p), actions,
+                                                                                              action_is_f64, step_index);
   BCG_CHECK_CUDA(cudaGetLastError());
   return BCG_OK;
 }
@@ -2215,7 +2521,7 @@ static int launch_ego_dense(const BcgParams* p, const BcgBatch* b, uint8_t* ego_
 static int launch_ego_sparse(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, cudaStream_t s) {
   int sms = 0;
   if (int rc = sm_count_of_current_device(&sms)) return rc;
-  BCG_CHECK_CUDA(cudaMemsetAsync(b->ego_list + b->n_envs, 0, 2 * sizeof(int32_t), s));   // hand-over count, env counter
+  // (the hand-over count and the env counter in ego_list[n_envs ..] were zeroed by the state / prep kernel)
   // persistent CTAs, as many per SM as fit with this crop's tables (18 for the 117 x 133 crop)
   const int tab_bytes = (p->ego_w + p->ego_h) * (int)sizeof(int2);
   const bool sum = b->occ_sum_arena != nullptr;
@@ -2238,7 +2544,17 @@ static int launch_ego_sparse(const BcgParams* p, const BcgBatch* b, uint8_t* ego
   if (sum) ego_sparse_kernel<true><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image);
   else ego_sparse_kernel<false><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image);
   BCG_CHECK_CUDA(cudaGetLastError());
+  if (b->flags & BCG_BATCH_SPARSE_EGO_ONLY) return BCG_OK;     // the sparse kernel rendered every env itself
   return launch_ego_dense(p, b, ego_image, b->ego_list, s);
+}
+
+// BCG_STEP_KERNELS=split runs kin_kernel + collide_reward_kernel + commit_kernel instead of the fused state_kernel
+static bool split_state_kernels_requested() {
+  static const bool split = [] {
+    const char* v = getenv("BCG_STEP_KERNELS");
+    return v && strcmp(v, "split") == 0;
+  }();
+  return split;
 }
 
 // BCG_EGO_KERNEL=dense forces the dense cell-tile kernel for every env (A/B timing of the sparse path)
@@ -2282,6 +2598,7 @@ int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, 
                     uint64_t step_index, const BcgStepOut* out, void* const* events, void* stream) {
   if (int rc = check_batch(p, b)) return rc;
   BCG_REQUIRE(actions && out, "null actions/out");
+  BCG_REQUIRE(!(b->step_counter && split_state_kernels_requested()), "BCG_STEP_KERNELS=split has no device-side step counter");
   const bool ego = out->ego_image || out->goal_n_state;
   if (ego) {
     if (int rc = check_ego(p, b, out->ego_image)) return rc;
@@ -2289,14 +2606,25 @@ int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, 
   cudaStream_t s = (cudaStream_t)stream;
   const BcgStateLayout L = make_layout(*p);
   if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[0], s));
-  kin_kernel<<<blocks_for(b->n_envs, BCG_KIN_THREADS), BCG_KIN_THREADS, 0, s>>>(*p, *b, L, actions, action_is_f64, step_index);
-  BCG_CHECK_CUDA(cudaGetLastError());
-  if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[1], s));
-  collide_reward_kernel<<<blocks_for((int64_t)b->n_envs * 32, BCG_CR_THREADS), BCG_CR_THREADS, 0, s>>>(*p, *b);
-  BCG_CHECK_CUDA(cudaGetLastError());
-  if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[2], s));
-  commit_kernel<<<blocks_for(b->n_envs, BCG_COMMIT_THREADS / 2), BCG_COMMIT_THREADS, 0, s>>>(*p, *b, L, *out, ego ? ego_capacity(*p, *b) : 0);
-  BCG_CHECK_CUDA(cudaGetLastError());
+  if (split_state_kernels_requested()) {
+    // round 1's three state kernels (BCG_STEP_KERNELS=split): kept as the A/B and bit-equality reference of state_kernel
+    kin_kernel<<<blocks_for(b->n_envs, BCG_KIN_THREADS), BCG_KIN_THREADS, 0, s>>>(*p, *b, L, actions, action_is_f64, step_index);
+    BCG_CHECK_CUDA(cudaGetLastError());
+    if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[1], s));
+    collide_reward_kernel<<<blocks_for((int64_t)b->n_envs * 32, BCG_CR_THREADS), BCG_CR_THREADS, 0, s>>>(*p, *b);
+    BCG_CHECK_CUDA(cudaGetLastError());
+    if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[2], s));
+    commit_kernel<<<blocks_for(b->n_envs, BCG_COMMIT_THREADS / 2), BCG_COMMIT_THREADS, 0, s>>>(*p, *b, L, *out, ego ? ego_capacity(*p, *b) : 0);
+    BCG_CHECK_CUDA(cudaGetLastError());
+  } else {
+    if (events) {
+      BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[1], s));
+      BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[2], s));
+    }
+    state_kernel<<<blocks_for(b->n_envs, BCG_STATE_THREADS), BCG_STATE_THREADS, 0, s>>>(*p, *b, L, actions, action_is_f64, step_index,
+                                                                                       *out, ego ? ego_capacity(*p, *b) : 0);
+    BCG_CHECK_CUDA(cudaGetLastError());
+  }
   if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[3], s));
   if (out->ego_image) {
     if (int rc = launch_ego_image(p, b, out->ego_image, s)) return rc;
@@ -2310,18 +2638,21 @@ int bcg_step(const BcgParams* p, const BcgBatch* b, const void* actions, int32_t
   return bcg_step_events(p, b, actions, action_is_f64, step_index, out, nullptr, stream);
 }
 
-static int launch_collision(const BcgParams* p, const BcgBatch* b, const double* poses, uint8_t* flags_out,
-                            int32_t* pixels_out, int use_u8, cudaStream_t s) {
-  if (poses) {   // NULL: check the poses the last kinematic step proposed (their work records are still in b->work)
-    pose_prep_kernel<<<blocks_for(b->n_envs, 128), 128, 0, s>>>(*p, *b, poses);
-    BCG_CHECK_CUDA(cudaGetLastError());
-  }
+static int launch_collision_kernel(const BcgBatch* b, uint8_t* flags_out, int32_t* pixels_out, int use_u8, cudaStream_t s) {
   const int grid = blocks_for((int64_t)b->n_envs * 32, 256);
   if (use_u8) collision_kernel<2><<<grid, 256, 0, s>>>(*b, flags_out, nullptr);
   else if (pixels_out) collision_kernel<1><<<grid, 256, 0, s>>>(*b, flags_out, pixels_out);
-  else collision_kernel<0><<<grid, 256, 0, s>>>(*b, flags_out, nullptr);
+  else collision_thread_kernel<<<blocks_for(b->n_envs, 128), 128, 0, s>>>(*b, flags_out);
   BCG_CHECK_CUDA(cudaGetLastError());
   return BCG_OK;
+}
+
+static int launch_collision(const BcgParams* p, const BcgBatch* b, const double* poses, uint8_t* flags_out,
+                            int32_t* pixels_out, int use_u8, cudaStream_t s) {
+  // NULL: the poses the last step proposed (rows 0..2 of b->cand have the [3][n] layout of `poses`)
+  pose_prep_kernel<<<blocks_for(b->n_envs, 128), 128, 0, s>>>(*p, *b, poses ? poses : b->cand);
+  BCG_CHECK_CUDA(cudaGetLastError());
+  return launch_collision_kernel(b, flags_out, pixels_out, use_u8, s);
 }
 
 int bcg_collision(const BcgParams* p, const BcgBatch* b, const double* poses, uint8_t* flags_out, int32_t* pixels_out,
@@ -2335,6 +2666,12 @@ int bcg_collision_u8(const BcgParams* p, const BcgBatch* b, const double* poses,
   if (int rc = check_batch(p, b)) return rc;
   BCG_REQUIRE(flags_out, "null flags");
   return launch_collision(p, b, poses, flags_out, nullptr, 1, (cudaStream_t)stream);
+}
+
+int bcg_collision_recheck(const BcgParams* p, const BcgBatch* b, uint8_t* flags_out, int32_t use_u8, void* stream) {
+  if (int rc = check_batch(p, b)) return rc;
+  BCG_REQUIRE(flags_out, "null flags");
+  return launch_collision_kernel(b, flags_out, nullptr, use_u8, (cudaStream_t)stream);
 }
 
 int bcg_gather_state(const BcgBatch* b, const int64_t* idx, int32_t k, double* out_f, int32_t* out_i, void* stream) {

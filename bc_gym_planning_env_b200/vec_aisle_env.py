@@ -78,24 +78,26 @@ class _VecSlotEnv(VecPlanEnv):
         self._upload_lut(footprint_lut_for(self.params.robot_name, self.resolution, footprint_scale, footprint))
         self._alloc_state()
         self._make_batch()
+        # generated worlds are thin walls (BcgMapDesc.occupied stays 0): no env ever needs the dense egocentric kernel
+        self._batch.flags |= nat.BATCH_SPARSE_EGO_ONLY
 
     def _alloc_slots(self, record_bytes):
         n, dev = self.n_envs, self.device
-        descs = (nat.BcgMapDesc * n)()
-        pdescs = (nat.BcgPathDesc * n)()
         path_slot = 5 * self._path_pitch + 3 * self._chunk_pitch
         # tile summary of a slot: at most one word per tile row and 32 tile columns, i.e. never more words than tiles
         sum_slot_words = self._tile_slot_words // 16
         if n * sum_slot_words >= 2 ** 31:
             raise ValueError("tile summaries of this batch exceed the 32-bit offsets of BcgMapDesc.sum_off")
-        for e in range(n):
-            descs[e].data_off = e * self._slot_bytes
-            descs[e].cell_tile_off = e * self._slot_bytes
-            descs[e].tile_off = e * self._tile_slot_words
-            descs[e].sum_off = e * sum_slot_words
-            pdescs[e].off = e * path_slot
-            pdescs[e].chunk_off = e * path_slot + 5 * self._path_pitch
-            pdescs[e].pitch, pdescs[e].chunk_pitch = self._path_pitch, self._chunk_pitch
+        ids = np.arange(n, dtype=np.int64)
+        md = np.zeros(n, dtype=np.dtype(nat.BcgMapDesc))
+        md['data_off'] = md['cell_tile_off'] = ids * self._slot_bytes
+        md['tile_off'] = ids * self._tile_slot_words
+        md['sum_off'] = ids * sum_slot_words
+        pdd = np.zeros(n, dtype=np.dtype(nat.BcgPathDesc))
+        pdd['off'] = ids * path_slot
+        pdd['chunk_off'] = ids * path_slot + 5 * self._path_pitch
+        pdd['pitch'], pdd['chunk_pitch'] = self._path_pitch, self._chunk_pitch
+        descs, pdescs = md.tobytes(), pdd.tobytes()
         self.map_arena = torch.zeros(n * self._slot_bytes, dtype=torch.uint8, device=dev)
         self.cell_tile_arena = torch.zeros(n * self._slot_bytes, dtype=torch.uint8, device=dev)
         self.tile_arena = torch.zeros(n * self._tile_slot_words, dtype=torch.int32, device=dev)

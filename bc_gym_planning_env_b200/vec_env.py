@@ -128,6 +128,13 @@ class VecPlanEnv(object):
             nat.check(nat.lib().bcg_build_cell_tiles(C.byref(self._batch), 0, self._batch.n_maps, s))
         nat.check(nat.lib().bcg_init_state(C.byref(self._c_params), C.byref(self._batch), s))
         self.check_status()
+        if self._ego_list is not None:
+            # bcg_build_lethal_tiles counted the occupied cells of every map: when none is above the library's dense
+            # threshold (1 cell in 20) no env is ever handed to the dense egocentric kernel, so it is not launched
+            d = np.frombuffer(self.map_descs.cpu().numpy().tobytes(), dtype=np.dtype(nat.BcgMapDesc))
+            dense = d['occupied'].astype(np.int64) * 20 > d['width'].astype(np.int64) * d['height'].astype(np.int64)
+            if not dense.any():
+                self._batch.flags |= nat.BATCH_SPARSE_EGO_ONLY
 
     def _configure(self, params, n_envs, resolution, noise_parameters, seed, auto_reset, device, env_id_base, with_ego,
                    ego_staging):
@@ -148,6 +155,7 @@ class VecPlanEnv(object):
         self.ego_staging = ego_staging
         self.use_tma = ego_staging == 'tma'
         self._step_index = 0
+        self._graph = None
         self._c_params = self._make_params(noise_parameters, seed, env_id_base)
         self.layout = nat.state_layout(self._c_params)
 
@@ -228,13 +236,16 @@ class VecPlanEnv(object):
             copy_idx[order] = np.arange(len(ids)) - run_start
             copies = int(copy_idx.max()) + 1
             map_arena = map_arena.repeat(copies)
-            table = (nat.BcgMapDesc * self.n_envs)()
-            for e in range(self.n_envs):
-                C.memmove(C.byref(table[e]), C.byref(descs[int(ids[e])]), C.sizeof(nat.BcgMapDesc))
-                table[e].data_off += int(copy_idx[e]) * pool_bytes
-                table[e].tile_off += int(copy_idx[e]) * pool_words
-                table[e].cell_tile_off += int(copy_idx[e]) * pool_ctile_bytes
-                table[e].sum_off += int(copy_idx[e]) * pool_sum_words
+            # one descriptor per env: its pool entry's, with the offsets moved into the env's own copy of the pool
+            pool = np.frombuffer(bytes(descs), dtype=np.dtype(nat.BcgMapDesc))
+            rows = pool[ids].copy()
+            rows['data_off'] += copy_idx * pool_bytes
+            rows['tile_off'] += copy_idx * pool_words
+            rows['cell_tile_off'] += copy_idx * pool_ctile_bytes
+            if int((rows['sum_off'] + copy_idx * pool_sum_words).max()) >= 2 ** 31:
+                raise ValueError("tile summaries of this batch exceed the 32-bit offsets of BcgMapDesc.sum_off")
+            rows['sum_off'] += (copy_idx * pool_sum_words).astype(np.int32)
+            table = (nat.BcgMapDesc * self.n_envs).from_buffer_copy(rows.tobytes())
             descs = table
             ids = np.arange(self.n_envs)
             pool_words *= copies
@@ -248,16 +259,15 @@ class VecPlanEnv(object):
         widths = (C.c_int32 * len(self._tmap_widths))(*self._tmap_widths)
         tm = np.zeros(len(descs) * len(self._tmap_widths) * 128, dtype=np.uint8)
         self.tile_arena = torch.zeros(max(pool_words, 1), dtype=torch.int32, device=self.device)
-        self.cell_tile_arena = self.occ_tile_arena = self.occ_sum_arena = None
+        self.cell_tile_arena = None
         if self.ego_staging == 'tiles':
             self.cell_tile_arena = torch.empty(max(pool_ctile_bytes, 128), dtype=torch.uint8, device=self.device)
-        if self.ego_staging == 'tiles' and getattr(self, '_ego_sparse', True):
-            # occupancy plane (cell != 0) for the sparse egocentric kernel: same layout as the lethal plane
-            self.occ_tile_arena = torch.zeros(max(pool_words, 1), dtype=torch.int32, device=self.device)
-            if pool_sum_words >= 2 ** 31:
-                raise ValueError("tile summaries of this batch exceed the 32-bit offsets of BcgMapDesc.sum_off")
-            # one bit per 32 x 16 tile of the occupancy plane: the sparse kernel skips the empty tiles of a window
-            self.occ_sum_arena = torch.zeros(max(pool_sum_words, 1), dtype=torch.int32, device=self.device)
+        # occupancy plane (cell != 0; same layout as the lethal plane) and its tile summary (one bit per 32 x 16 tile):
+        # the sparse egocentric kernel scans them, and the collision check uses the summary to skip empty tiles
+        self.occ_tile_arena = torch.zeros(max(pool_words, 1), dtype=torch.int32, device=self.device)
+        if pool_sum_words >= 2 ** 31:
+            raise ValueError("tile summaries of this batch exceed the 32-bit offsets of BcgMapDesc.sum_off")
+        self.occ_sum_arena = torch.zeros(max(pool_sum_words, 1), dtype=torch.int32, device=self.device)
         if self.ego_staging == 'tma':
             nat.check(nat.lib().bcg_encode_map_tensor_maps(descs, len(descs), C.c_void_p(map_arena.data_ptr()), widths,
                                                            len(self._tmap_widths), self._tmap_box_h,
@@ -318,7 +328,8 @@ class VecPlanEnv(object):
         self._cand = torch.zeros((9, n), dtype=torch.float64, device=dev)
         self._cand_i = torch.zeros((2, n), dtype=torch.int32, device=dev)
         self._work = torch.zeros((n, 192), dtype=torch.uint8, device=dev)
-        self._ego_work = torch.zeros((n, 256), dtype=torch.uint8, device=dev)
+        self._ego_work = torch.zeros((n, 128), dtype=torch.uint8, device=dev)
+        self._step_counter = torch.zeros(2, dtype=torch.int64, device=dev)
         self._status = torch.zeros(nat.STATUS_WORDS, dtype=torch.int32, device=dev)
         self._stats = torch.zeros(nat.STATS_WORDS, dtype=torch.float64, device=dev)
         self.reward = torch.zeros(n, dtype=torch.float64, device=dev)
@@ -352,12 +363,15 @@ class VecPlanEnv(object):
         b.status, b.stats = self._status.data_ptr(), self._stats.data_ptr()
         if self.cell_tile_arena is not None:
             b.cell_tile_arena = self.cell_tile_arena.data_ptr()
-        if getattr(self, 'occ_tile_arena', None) is not None:
+        b.occ_tile_arena = self.occ_tile_arena.data_ptr()
+        # BCG_EGO_SUMMARY=0: A/B switch, the sparse kernel then scans every tile of a window (and the collision check
+        # loads every tile under the footprint)
+        if os.environ.get("BCG_EGO_SUMMARY", "1") != "0":
+            b.occ_sum_arena = self.occ_sum_arena.data_ptr()
+        self._ego_list = None
+        if self.cell_tile_arena is not None and getattr(self, '_ego_sparse', True):
             self._ego_list = torch.zeros(self.n_envs + 4, dtype=torch.int32, device=self.device)
-            b.occ_tile_arena, b.ego_list = self.occ_tile_arena.data_ptr(), self._ego_list.data_ptr()
-            # BCG_EGO_SUMMARY=0: A/B switch, the sparse kernel then scans every tile of a window
-            if getattr(self, 'occ_sum_arena', None) is not None and os.environ.get("BCG_EGO_SUMMARY", "1") != "0":
-                b.occ_sum_arena = self.occ_sum_arena.data_ptr()
+            b.ego_list = self._ego_list.data_ptr()
         if self.use_tma:
             b.map_tmaps, b.tmap_n_widths, b.tmap_box_h = self.map_tmaps.data_ptr(), len(self._tmap_widths), self._tmap_box_h
             for j, w in enumerate(self._tmap_widths):
@@ -407,6 +421,35 @@ class VecPlanEnv(object):
         nat.check(nat.lib().bcg_step(C.byref(self._c_params), C.byref(self._batch), nat.ptr(a),
                                      1 if a.dtype == torch.float64 else 0, self._step_index,
                                      C.byref(self._out), self._stream()))
+        self._step_index += 1
+        return self.observation(), self.reward, self.done, {}
+
+    def step_graph(self, actions=None):
+        """`step` as ONE CUDA-graph launch: the first call captures the step's kernels (reading `self.actions`, a
+        persistent float32 [N, 2] device buffer, and the device-side step counter) and every call replays them --
+        one driver call per step instead of one per kernel plus the argument marshalling, which is what a small
+        batch spends its time on.  `actions` (optional) is copied into `self.actions` first; a GPU-resident policy
+        writes into `self.actions` itself and calls step_graph().  From the first call on the step index lives on the
+        device (BcgBatch.step_counter); `step` keeps working and uses it too."""
+        if self._graph is None:
+            self.actions = torch.zeros((self.n_envs, 2), dtype=torch.float32, device=self.device)
+            if actions is not None:
+                self.actions.copy_(self._as_actions(actions))
+            self._step_counter[0] = self._step_index
+            self._step_counter[1] = 0
+            self._batch.step_counter = self._step_counter.data_ptr()
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g, stream=side):
+                    nat.check(nat.lib().bcg_step(C.byref(self._c_params), C.byref(self._batch), nat.ptr(self.actions), 0, 0,
+                                                 C.byref(self._out), C.c_void_p(side.cuda_stream)))
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            self._graph = g
+        elif actions is not None:
+            self.actions.copy_(self._as_actions(actions), non_blocking=True)
+        self._graph.replay()
         self._step_index += 1
         return self.observation(), self.reward, self.done, {}
 

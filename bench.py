@@ -412,9 +412,10 @@ def run_b200(args):
     elapsed_ms = float(t.item())
     env.check_status()
     value = n * world * args.steps / (elapsed_ms * 1e-3)
+    split = os.environ.get("BCG_STEP_KERNELS") == "split"      # round 1's three state kernels (A/B)
     kin_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
     cr_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
-    commit_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in ev]))
+    commit_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in ev]))      # fused build: the state kernel
     ego_ms = float(np.mean([e[3].elapsed_time(e[4]) for e in ev]))
 
     # ---- same loop without the egocentric kernel (reported beside the headline, not instead of it) -----
@@ -471,7 +472,7 @@ def run_b200(args):
                        "algorithmic bytes (SURVEY 8d) = in-map footprint pixels x 1 B (uint8 definition; the kernel reads "
                        "the derived 1-bit lethal tile plane) + remaining path points x 24 B (the kernel skips path chunks "
                        "farther than the reach radius); collision-only share: %.1f MB" % (coll_bytes / 1e6))
-    sparse = getattr(env, "occ_tile_arena", None) is not None and os.environ.get("BCG_EGO_KERNEL") != "dense"
+    sparse = getattr(env, "_ego_list", None) is not None and os.environ.get("BCG_EGO_KERNEL") != "dense"
     ego_name = "ego_sparse_kernel" if sparse else ("ego_tiles_kernel" if env.ego_staging == "tiles" else "ego_kernel")
     dense_envs = int(env._ego_list[n].item()) if sparse else n
     # Algorithmic bytes of the egocentric observation.  SURVEY 8d counts a gather: source read + image write = 2 x W x H
@@ -512,8 +513,10 @@ def run_b200(args):
     import ctypes as C
     flags = torch.empty(n, dtype=torch.uint8, device=device)
     s = env._stream()
-    tiles_ms = time_kernel(lambda: nat.check(nat.lib().bcg_collision(C.byref(env._c_params), C.byref(env._batch), None, nat.ptr(flags), None, s)))
-    u8_ms = time_kernel(lambda: nat.check(nat.lib().bcg_collision_u8(C.byref(env._c_params), C.byref(env._batch), None, nat.ptr(flags), s)))
+    # work records of the poses the last step proposed (one prep launch), then only the collision kernel is timed
+    nat.check(nat.lib().bcg_collision(C.byref(env._c_params), C.byref(env._batch), None, nat.ptr(flags), None, s))
+    tiles_ms = time_kernel(lambda: nat.check(nat.lib().bcg_collision_recheck(C.byref(env._c_params), C.byref(env._batch), nat.ptr(flags), 0, s)))
+    u8_ms = time_kernel(lambda: nat.check(nat.lib().bcg_collision_recheck(C.byref(env._c_params), C.byref(env._batch), nat.ptr(flags), 1, s)))
     del flush
 
     # ---- reset storm: every env of a batch gets a new world on the device -----------
@@ -608,13 +611,14 @@ def run_b200(args):
                             "egocentric images stay in HBM for a GPU-resident policy; `with_images_to_host` = the same "
                             "call with every crop and goal vector copied to pinned host memory too (host-link bound)",
                     "with_images_to_host": e2e_images},
-            "gpu_launches": args.steps * (3 if args.no_ego else (5 if sparse else 4)) * world,
+            "gpu_launches": args.steps * ((3 if split else 1) + (0 if args.no_ego else (1 if (sparse and env._batch.flags & 1) else (2 if sparse else 1)))) * world,
             "ego_dense_fallback_envs_last_step": None if args.no_ego else dense_envs,
             "roofline": dominant,
             "roofline_collision": roof_commit,
             "roofline_ego": None if args.no_ego else roof_ego,
-            "kernels_ms": {"kin_kernel": kin_ms, "collide_reward_kernel": cr_ms, "commit_kernel": commit_ms, ego_name: ego_ms,
-                           "collision_tiles_cold_l2": tiles_ms, "collision_u8_cold_l2": u8_ms},
+            "kernels_ms": dict({"kin_kernel": kin_ms, "collide_reward_kernel": cr_ms, "commit_kernel": commit_ms} if split
+                               else {"state_kernel": commit_ms},
+                               **{ego_name: ego_ms, "collision_tiles_cold_l2": tiles_ms, "collision_u8_cold_l2": u8_ms}),
             "collision_standalone": {
                 "tiles": roof("collision_kernel (lethal tile plane), cold L2", coll_bytes, tiles_ms, "uint8-definition bytes"),
                 "u8": roof("collision_kernel (uint8 rows), cold L2", coll_bytes, u8_ms, "uint8-definition bytes"),

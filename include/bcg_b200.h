@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BCG_ABI_VERSION 5
+#define BCG_ABI_VERSION 6
 
 /* error codes */
 #define BCG_OK 0
@@ -159,24 +159,30 @@ typedef struct BcgFootprintLut {
   int32_t n_buckets, reserved;
 } BcgFootprintLut;
 
+/* BcgBatch.flags */
+#define BCG_BATCH_SPARSE_EGO_ONLY 1 /* no map of the batch is dense (BcgMapDesc.occupied below 1 cell in 20, read back by the
+                                       host after bcg_build_lethal_tiles; always true for device-generated worlds): the
+                                       sparse egocentric kernel renders the rare window that overflows its cell list
+                                       itself and the dense kernel is not launched behind it */
+
 /* everything a step touches; all pointers are device pointers */
 typedef struct BcgBatch {
   int32_t n_envs;
   int32_t n_frows, n_irows; /* must equal bcg_state_layout() for the params in use */
   int32_t n_maps, n_paths;
-  int32_t reserved;
+  int32_t flags;            /* BCG_BATCH_* */
   double* state_f;
   int32_t* state_i;
   double* init_f;  /* the state reset() restores (env.py:247,302) */
   int32_t* init_i;
-  double* cand;    /* scratch [9][n_envs]: robot state proposed by the kinematic kernel (7 rows), then
-                      this step's reward and new min_dist from the collide/reward kernel            */
-  int32_t* cand_i; /* scratch [2][n_envs]: new target_idx and verdict flags from the collide/reward kernel */
-  void* ego_work;  /* scratch [n_envs][256 bytes]: per-env affine map + source window of the egocentric crop,
-                      written by the commit kernel (or bcg_observe_ego) for the egocentric kernel; may be
+  double* cand;    /* scratch [9][n_envs]: rows 0..2 = the pose the last step proposed (before the collision
+                      verdict); the split kernels (bcg_kinematic_step, BCG_STEP_KERNELS=split) use all nine   */
+  int32_t* cand_i; /* scratch [2][n_envs] of the split kernels                                              */
+  void* ego_work;  /* scratch [n_envs][128 bytes]: per-env affine map + source window of the egocentric crop,
+                      written by the state kernel (or bcg_observe_ego) for the egocentric kernel; may be
                       NULL when no egocentric image is ever requested                                      */
-  void* work;      /* scratch [n_envs][192 bytes]: per-env work records (map / path / footprint references and
-                      reward inputs) written by the kinematic kernel for the warp-per-env kernels         */
+  void* work;      /* scratch [n_envs][192 bytes]: per-env work records (map / path / footprint references) of the
+                      stand-alone collision entry points and the split kernels                            */
   const int32_t* map_id;  /* [n_envs] index into maps  */
   const int32_t* path_id; /* [n_envs] index into paths */
   const BcgMapDesc* maps;
@@ -207,6 +213,10 @@ typedef struct BcgBatch {
                             egocentric kernel loads only the non-empty tiles of a window                              */
   uint32_t* status; /* [BCG_STATUS_WORDS] */
   double* stats;    /* [BCG_STATS_WORDS]  */
+  uint64_t* step_counter; /* optional device [2], zero at start: when set, bcg_step ignores its step_index argument,
+                            takes the step index from word 0 and increments it on the device when the step is done
+                            (word 1 is its scratch) -- so that a captured CUDA graph of a step can be replayed
+                            without changing a kernel argument                                                    */
 } BcgBatch;
 
 /* TurnParams (envs/synth_turn_env.py:18-31): geometry of one aisle turn */
@@ -320,19 +330,20 @@ int bcg_generate_minis(const BcgParams* p, const BcgBatch* b, const BcgAisleSlot
 
 /* -- the hot path -------------------------------------------------------------------------------- */
 /* PlanEnv.step (env.py:334-361) for all envs.  actions: device [n][2] (wheel_v, wheel_angle) or
- * (v, w) for diff-drive; action_is_f64 selects fp64 vs fp32 elements.  Launches, in order:
- * kinematics (thread/env), collision+reward (warp/env), commit (two threads/env), and -- only if
- * out->ego_image is set -- the egocentric observation: with the occupancy plane and ego_list the sparse
- * scatter kernel followed by the dense cell-tile kernel for the envs it hands over, else one dense kernel
- * (CTA/env).  step_index is the caller's global step
+ * (v, w) for diff-drive; action_is_f64 selects fp64 vs fp32 elements.  Launches the state kernel (one thread per
+ * env: control delay, robot model, collision, rollback, delay lines, reward, done, statistics, auto-reset, compact
+ * observation, goal vector, egocentric record) and -- only if out->ego_image is set -- the egocentric observation:
+ * with the occupancy plane and ego_list the sparse scatter kernel, followed by the dense cell-tile kernel for the
+ * envs it hands over unless BCG_BATCH_SPARSE_EGO_ONLY, else one dense kernel.  step_index is the caller's global step
  * counter: odometry noise is Philox4x32-10 keyed by p->seed at counter (env id, step_index, draw),
  * replacing the reference's global np.random (differential_drive.py:50). */
 int bcg_step(const BcgParams* p, const BcgBatch* b, const void* actions, int32_t action_is_f64,
              uint64_t step_index, const BcgStepOut* out, void* stream);
 
 /* bcg_step with per-kernel timing hooks: events[0..4] are caller-created cudaEvent_t handles (timing
- * enabled) recorded on `stream` before the kinematic kernel and after each of the kinematic,
- * collide/reward, commit and egocentric kernels.  events == NULL behaves exactly like bcg_step. */
+ * enabled) recorded on `stream`: [2] before and [3] after the state kernel, [4] after the egocentric kernels
+ * ([0], [1] coincide with [2]; with BCG_STEP_KERNELS=split they bracket the kinematic and collide/reward
+ * kernels of round 1).  events == NULL behaves exactly like bcg_step. */
 int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, int32_t action_is_f64,
                     uint64_t step_index, const BcgStepOut* out, void* const* events, void* stream);
 
@@ -341,14 +352,18 @@ int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, 
 int bcg_kinematic_step(const BcgParams* p, const BcgBatch* b, const void* actions,
                        int32_t action_is_f64, uint64_t step_index, void* stream);
 /* pose_collides (env.py:464-489) of poses [3][n] (rows x,y,th) against each env's map, using the
- * lethal tile plane; flags_out [n].  pixels_out (optional, [n]) = in-map footprint pixel count.
- * poses == NULL re-checks the poses the last bcg_kinematic_step / bcg_step proposed (only the
- * warp-per-env collision kernel is launched -- this is the form the roofline is measured on). */
+ * lethal tile plane; flags_out [n].  pixels_out (optional, [n]) = in-map footprint pixel count (warp-per-env
+ * kernel; without it the thread-per-env kernel the step itself uses).  poses == NULL checks the poses the last
+ * bcg_step / bcg_kinematic_step proposed (rows 0..2 of b->cand).  Two launches: per-env work records (footprint
+ * angle bin, mask box, map references) into b->work, then the collision kernel. */
 int bcg_collision(const BcgParams* p, const BcgBatch* b, const double* poses, uint8_t* flags_out,
                   int32_t* pixels_out, void* stream);
 /* same verdicts read straight from the uint8 costmap rows (no derived plane) */
 int bcg_collision_u8(const BcgParams* p, const BcgBatch* b, const double* poses, uint8_t* flags_out,
                      void* stream);
+/* only the collision kernel, on the work records the last bcg_collision / bcg_collision_u8 call left in b->work
+ * (use_u8: the uint8-row kernel) -- the form the collision roofline is measured on */
+int bcg_collision_recheck(const BcgParams* p, const BcgBatch* b, uint8_t* flags_out, int32_t use_u8, void* stream);
 /* EgocentricCostmap.observation (egocentric.py:125-160) from the current state */
 int bcg_observe_ego(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, float* goal_n_state,
                     void* stream);

@@ -34,7 +34,7 @@ for sparse in (True, False):
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / 200
-    handed = int(env._ego_list[n]) if env.occ_tile_arena is not None else n
+    handed = int(env._ego_list[n]) if env._ego_list is not None else n
     print("ego_sparse=%s: %.4f ms/step, %.3g env-steps/s, %d of %d envs rendered by the dense kernel in the last step"
           % (sparse, ms, n / ms * 1e3, handed, n))
     env.check_status()

@@ -86,7 +86,7 @@ def test_sparse_and_dense_paths_carry_every_cost_value(fill):
         img, _ = env.observe_ego()
         img = img.cpu().numpy()[..., 0]
         # (a pool in which every map is dense is built without the sparse kernel: all envs go through the dense one)
-        handed_over = int(env._ego_list[n]) if env.occ_tile_arena is not None else n
+        handed_over = int(env._ego_list[n]) if env._ego_list is not None else n
         seen.add(handed_over > 0)
         for e, (c, _) in enumerate(worlds):
             want = O.ego_costmap(c.get_data(), poses[e], c.get_origin(), res)

@@ -76,7 +76,7 @@ def test_sparse_and_dense_egocentric_kernels_agree_at_full_size(big):
     """The scatter kernel (occupancy plane) and the dense gather kernel (cell tiles) render the same 65 536 crops."""
     env, actions, costmaps, paths = big
     dense = VecPlanEnv(costmaps, paths, env.params, n_envs=N, noise_parameters=None, with_ego=True, ego_sparse=False)
-    assert dense.occ_tile_arena is None and env.occ_tile_arena is not None
+    assert dense._ego_list is None and env._ego_list is not None
     env.reset()
     for a in actions[:12]:
         env.step(a)
