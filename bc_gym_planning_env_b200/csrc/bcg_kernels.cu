@@ -1653,7 +1653,7 @@ __global__ void __launch_bounds__(BCG_EGT_THREADS, BCG_EGT_CTAS) ego_tiles_kerne
 
   // record of env `en` -> ring slot `slot` (the first 16 threads move 16 bytes each)
   auto fetch_record = [&](int en, int slot) {
-    if (en < n && tid < 16)
+    if (en < n && tid < BCG_EGO_WORK_BYTES / 16)
       cp_async_16(rec_u32 + slot * BCG_EGO_WORK_BYTES + tid * 16, recs + (int64_t)env_of(en) * BCG_EGO_WORK_BYTES + tid * 16, 16u);
   };
 
@@ -1876,7 +1876,7 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
   if (e0 >= n) return;
 
   auto fetch_record = [&](int en, int slot) {
-    if (en < n && tid < 16)
+    if (en < n && tid < BCG_EGO_WORK_BYTES / 16)
       cp_async_16(rec_u32 + slot * BCG_EGO_WORK_BYTES + tid * 16, recs + (int64_t)en * BCG_EGO_WORK_BYTES + tid * 16, 16u);
   };
   // Tile-summary words of the window of record `q`, lane <-> band of 16 rows (zero where the band or the word lies

@@ -50,12 +50,12 @@ def _stack(records):
     return {k: np.array([[r[k] for r in env_recs] for env_recs in records]) for k in keys}
 
 
-def _params_json(ep, noise):
+def _params_json(ep, noise, footprint_scale=1.0):
     rp = ep.reward_provider_params
     return json.dumps(dict(dt=ep.dt, sp=rp.spatial_precision, ap=rp.angular_precision,
                            multiplier=rp.spatial_progress_multiplier, timeout=ep.iteration_timeout,
                            delays=[ep.control_delay, ep.pose_delay, ep.state_delay], robot=ep.robot_name,
-                           noise=noise, reward_provider=ep.reward_provider_name))
+                           noise=noise, reward_provider=ep.reward_provider_name, footprint_scale=footprint_scale))
 
 
 def gen_rollouts(name, make_env, n_envs, n_steps, noise=False, sample_from_space=False):
@@ -100,7 +100,7 @@ def gen_rollouts(name, make_env, n_envs, n_steps, noise=False, sample_from_space
     out = _pack_envs(envs)
     out.update({"ref_" + k: v for k, v in _stack(records).items()})
     out["actions"] = np.array(actions, dtype=np.float32)
-    out["params"] = np.array(_params_json(envs[0]._params, noise))
+    out["params"] = np.array(_params_json(envs[0]._params, noise, float(envs[0]._robot.get_footprint_scale())))
     if noise:
         out["normal_draws"] = np.array(draws)     # [E, T, 3] in draw order; NaN = not drawn
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
@@ -401,6 +401,66 @@ def gen_edge_worlds(name, n_steps, every):
           "done", out["ref_done"][:, -1])
 
 
+def gen_goal_reached(name, n_envs, extra, every):
+    """PlanEnv + EgocentricCostmap on SHORT paths (the first 2-3 m of an aisle) followed by a simple pursuit controller,
+    delays (2, 1, 1): the envs reach the end of their path (reward.py:223-246: reward 1 for the last way point,
+    min_dist 0, then reward 0 for ever; egocentric.py:143-150: goal_n_state all zeros once the path is empty) and
+    are stepped `extra` steps past done.  Records every step, goal_n_state every step, crops every `every` steps."""
+    from bc_gym_planning_env.envs.base.action import Action
+    from bc_gym_planning_env.envs.base.env import PlanEnv
+    from bc_gym_planning_env.envs.base.params import EnvParams
+    from bc_gym_planning_env.envs.egocentric import EgocentricCostmap
+    from bc_gym_planning_env.envs.synth_turn_env import RandomAisleTurnEnv
+    from bc_gym_planning_env.utilities.coordinate_transformations import normalize_angle
+    ep = EnvParams(control_delay=2, pose_delay=1, state_delay=1)
+    envs, records, actions, images, vectors = [], [], [], [], []
+    n_steps = None
+    runs = []
+    for s in range(n_envs):
+        world = RandomAisleTurnEnv(seed=600 + s)._env._state
+        full = np.array(world.original_path)
+        n_pts = 40 + 6 * s                               # 2.0 .. 3.5 m of the aisle's own (refined) path
+        pe = PlanEnv(world.costmap, full[:n_pts + 1:8].copy(), ep)
+        pe._robot.set_noise_parameters(None)
+        env = EgocentricCostmap(pe)
+        recs, ea, ei, ev = [], [], [], []
+        done_at = None
+        t = 0
+        while done_at is None or t < done_at + extra:
+            plain = pe._extract_obs()
+            if len(plain.path):
+                tgt = plain.path[min(len(plain.path) - 1, 6)]
+                err = normalize_angle(np.arctan2(tgt[1] - plain.pose[1], tgt[0] - plain.pose[0]) - plain.pose[2])
+            else:
+                err = 0.3 * np.sin(0.2 * t)              # past the goal: keep moving
+            a = np.array([0.5, np.clip(1.5 * err, -np.pi / 2, np.pi / 2)], dtype=np.float32)
+            obs, r, d, _ = env.step(Action(command=a))
+            recs.append(_record_step(pe, pe._extract_obs(), r, d))
+            ea.append(a)
+            ev.append(obs["goal_n_state"][:, 0].copy())
+            if t % every == every - 1:
+                ei.append(obs["env"][..., 0].copy())
+            if d and done_at is None:
+                done_at = t
+            t += 1
+            assert t < 1000
+        envs.append(pe)
+        runs.append((recs, ea, ei, ev, done_at))
+    n_steps = min(len(r[0]) for r in runs) // every * every      # common length (all envs are past done by then)
+    assert all(r[4] + 10 < n_steps for r in runs)
+    out = _pack_envs(envs)
+    out.update({"ref_" + k: v for k, v in _stack([r[0][:n_steps] for r in runs]).items()})
+    out["actions"] = np.array([r[1][:n_steps] for r in runs], dtype=np.float32)
+    out["every"] = np.int64(every)
+    out["ref_ego_image"] = np.array([r[2][:n_steps // every] for r in runs])
+    out["ref_goal_n_state_all"] = np.array([r[3][:n_steps] for r in runs])
+    out["ref_goal_n_state"] = out["ref_goal_n_state_all"][:, every - 1::every]
+    out["params"] = np.array(_params_json(ep, False))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, out["ref_pose"].shape, "done at", [r[4] for r in runs], "goal reached", (out["ref_path_len"][:, -1] == 0),
+          "collided", out["ref_collided"][:, -1])
+
+
 def main():
     _ref()
     os.makedirs(OUT, exist_ok=True)
@@ -426,8 +486,28 @@ def main():
     gen_t_junction("t_junction")
     gen_mini_worlds("mini_worlds", 24)
     gen_edge_worlds("edge_worlds", 260, 13)
+    gen_new_round2()
+
+
+def _scaled(env, scale):
+    env._env._robot._footprint_scale = scale          # TricycleRobot.get_footprint reads it (tricycle_model.py:371)
+    return env
+
+
+def gen_new_round2():
+    from bc_gym_planning_env.envs.base.params import EnvParams
+    from bc_gym_planning_env.envs.synth_turn_env import RandomAisleTurnEnv
+    gen_goal_reached("aisle_goal_reached", 6, 50, 3)
+    # another resolution and a scaled footprint (robot_models/tricycle_model.py:297,371): both change the footprint table
+    gen_rollouts("aisle_res005_scale125", lambda s: _scaled(RandomAisleTurnEnv(
+        params=EnvParams(resolution=0.05, control_delay=1, pose_delay=1, state_delay=0, iteration_timeout=240), seed=120 + s),
+        1.25), 6, 260)
 
 
 if __name__ == "__main__":
     sys.path.insert(0, os.path.dirname(HERE))
-    main()
+    if "--round2" in sys.argv:               # only the fixtures added in round 2 (the others stay byte-identical)
+        _ref()
+        gen_new_round2()
+    else:
+        main()

@@ -482,11 +482,13 @@ class OraclePlanEnv(object):
     def __init__(self, costmap, origin, resolution, path, robot="industrial_tricycle_v1", dt=0.05,
                  sp=1.0, ap=np.pi / 2, multiplier=0.0, timeout=1200, delays=(0, 0, 0), alphas=None,
                  normal_source=None, refine=True, path_delta=0.05, initial_wheel_angle=0.0,
-                 reward_provider="continuous_reward"):
+                 reward_provider="continuous_reward", footprint_scale=1.0):
         self.costmap = np.ascontiguousarray(costmap)
         self.origin = np.asarray(origin, dtype=np.float64)
         self.resolution = float(resolution)
-        self.robot = ROBOTS[robot]
+        self.robot = dict(ROBOTS[robot])
+        if footprint_scale != 1.0:          # robot_models/tricycle_model.py:371: dimensions.footprint() * footprint_scale
+            self.robot["footprint"] = np.asarray(self.robot["footprint"]) * footprint_scale
         self.dt, self.sp, self.ap, self.multiplier = dt, sp, ap, multiplier
         self.timeout = int(timeout)
         self.delays = tuple(int(d) for d in delays)

@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE ONLY -- loader for the *unmodified* upstream reference.
 
 Imports braincorp/bc-gym-planning-env read-only from /root/reference (present in the
-build container, absent on the GPU box) so that
+build container, absent on the GPU box) or from the install oracle/make_ref.py leaves in oracle/_ref/
+(git-ignored; it travels to the GPU box) so that
 
   * the oracle restatement in this directory can be validated against the real thing, and
   * golden fixtures under tests/golden/ can be (re)generated (oracle/gen_golden.py).
@@ -16,11 +17,22 @@ which cv2 4.13 rejects).
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get("BCG_REFERENCE_ROOT", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+# where the reference may live, in order: an explicit override, the build container's read-only mount, the driver's
+# `pip install --target baseline/_ref`, and this repo's own install (oracle/make_ref.py) -- the one that travels to the GPU box
+CANDIDATE_ROOTS = [r for r in (os.environ.get("BCG_REFERENCE_ROOT"), "/root/reference",
+                               os.path.join(os.path.dirname(HERE), "baseline", "_ref"), os.path.join(HERE, "_ref")) if r]
+
+
+def reference_root():
+    for root in CANDIDATE_ROOTS:
+        if os.path.isfile(os.path.join(root, "bc_gym_planning_env", "envs", "base", "env.py")):
+            return root
+    return None
 
 
 def reference_available():
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "bc_gym_planning_env"))
+    return reference_root() is not None
 
 
 _loaded = False
@@ -31,8 +43,9 @@ def load_reference():
     global _loaded
     if _loaded:
         return
-    if not reference_available():
-        raise RuntimeError("reference tree not found at %s" % REFERENCE_ROOT)
+    root = reference_root()
+    if root is None:
+        raise RuntimeError("reference package not found in any of %s" % CANDIDATE_ROOTS)
     import numpy as np
     import cv2
 
@@ -50,6 +63,6 @@ def load_reference():
         cv2.getRotationMatrix2D = _get_rotation_matrix_2d
 
     sys.dont_write_bytecode = True  # the reference mount is read-only
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     _loaded = True

@@ -33,7 +33,8 @@ def make_oracles(d, alphas=None, normal_sources=None):
         out.append(O.OraclePlanEnv(cm, origin, float(d["resolution"]), path, robot=p["robot"], dt=p["dt"], sp=p["sp"],
                                    ap=p["ap"], multiplier=p["multiplier"], timeout=p["timeout"], delays=p["delays"],
                                    alphas=alphas, normal_source=None if normal_sources is None else normal_sources[i],
-                                   refine=False, reward_provider=p.get("reward_provider", "continuous_reward")))
+                                   refine=False, reward_provider=p.get("reward_provider", "continuous_reward"),
+                                   footprint_scale=p.get("footprint_scale", 1.0)))
     return out
 
 
@@ -59,6 +60,8 @@ def make_vec_env(d, **kw):
     if params is None:
         params = env_params(d["params"]) if "params" in d else None
     kw.setdefault("noise_parameters", None)
+    if "params" in d:
+        kw.setdefault("footprint_scale", d["params"].get("footprint_scale", 1.0))
     return VecPlanEnv(costmaps, paths, params, **kw)
 
 

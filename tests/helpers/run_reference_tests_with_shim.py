@@ -8,7 +8,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
-from oracle.ref_loader import REFERENCE_ROOT, load_reference  # noqa: E402
+from oracle.ref_loader import load_reference, reference_root  # noqa: E402
 
 load_reference()
 from bc_gym_planning_env_b200 import shim  # noqa: E402
@@ -22,4 +22,4 @@ import pytest  # noqa: E402
 
 # the reference's pytest.ini turns numpy's deprecation warnings into errors; its tests are run as they are otherwise
 sys.exit(pytest.main(['-q', '-p', 'no:cacheprovider', '-c', os.devnull, '--rootdir', '/tmp', '-W', 'ignore::DeprecationWarning',
-                      os.path.join(REFERENCE_ROOT, sys.argv[1]), '-k', sys.argv[2]]))
+                      os.path.join(reference_root(), sys.argv[1]), '-k', sys.argv[2]]))
