@@ -385,11 +385,13 @@ __device__ __forceinline__ bool collide_tiles(const BcgBatch& b, const WorkColli
   return __any_sync(BCG_FULL, hit != 0u);
 }
 
-// pose_collides (envs/base/env.py:464-489) by ONE thread, for the thread-per-env state kernel.  The footprint box
-// spans <= 5 bands of 16 rows x <= 3 tiles of 32 columns; a tile is four 16-byte quarters of four rows.  With the tile
-// summary (`sum`: 1 bit per tile of the occupancy plane, a superset of the lethal plane) only tiles that hold a cell at
-// all are loaded -- an aisle is mostly free space, so most checks read one or two summary words per band and nothing
-// else.  All of a thread's loads for a quarter are independent of each other.  Same verdict as collide_tiles.
+// pose_collides (envs/base/env.py:464-489) by ONE thread, for the thread-per-env kinematics + collision kernel.  The
+// footprint box spans a few bands of 16 rows x <= 3 tiles of 32 columns.  A thread-serial gather pays a full memory
+// round trip per dependent load, so the loads are batched: (1) the tile-summary words of ALL bands (`sum`: 1 bit per
+// tile of the occupancy plane, a superset of the lethal plane), one round trip; (2) per non-empty tile under the
+// footprint -- a corridor is mostly free space: typically 0..3 of the 15 -- its four 16-byte quarters and the 16
+// footprint-mask rows of its band, 20 independent loads, one round trip; early exit on the first hit.
+// Same verdict as collide_tiles.
 struct FootBox {
   int X0, Y0;          // map pixel of the mask's top-left corner
   int nrows, fwidth;   // mask bounding box
@@ -405,50 +407,57 @@ __device__ __forceinline__ bool collide_thread(const BcgFootprintLut& lut, const
   const int tx0 = max(X0, 0) >> 5, tx1 = min(X1, map_w - 1) >> 5;
   const int ty0 = max(Y0, 0) >> 4, ty1 = min(Y1, map_h - 1) >> 4;
   const int wpr = lut.wpr;
-  const uint64_t* rows = lut.rows + (int64_t)f.bin * lut.max_rows * wpr;
+  const uint64_t* __restrict__ rows = lut.rows + (int64_t)f.bin * lut.max_rows * wpr;
   const int sw = (tiles_x + 31) >> 5;
-  uint32_t hit = 0u;
-  for (int ty = ty0; ty <= ty1 && hit == 0u; ++ty) {
-    uint32_t tmask = 0xffffffffu;                      // bit j <-> tile column tx0 + j
-    if (sum) {
-      const uint32_t* srow = sum + ty * sw;
-      const int w0 = tx0 >> 5;
-      uint64_t two = __ldg(srow + w0);
-      if ((tx1 >> 5) != w0) two |= (uint64_t)__ldg(srow + w0 + 1) << 32;
-      tmask = (uint32_t)(two >> (tx0 & 31));
-    }
-    tmask &= (2u << (tx1 - tx0)) - 1u;
-    if (tmask == 0u) continue;
-    const uint32_t* trow = tiles + (((int64_t)ty * tiles_x) << 4);
-#pragma unroll 1
-    for (int q = 0; q < 4; ++q) {
-      const int dy0 = (ty << 4) + 4 * q - Y0;           // mask row of this quarter's first tile row
-      if (dy0 + 3 < 0 || dy0 >= f.nrows) continue;
-      if (wpr == 1) {
-        uint64_t mk[4];
+  const uint32_t colmask = (2u << (tx1 - tx0)) - 1u;     // bit j <-> tile column tx0 + j
+  constexpr int MAXB = 6;                                // bands per batch (a 64-row mask spans <= 5)
+  for (int tyb = ty0; tyb <= ty1; tyb += MAXB) {
+    uint32_t tm[MAXB];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) mk[k] = ((unsigned)(dy0 + k) < (unsigned)f.nrows) ? __ldg(rows + dy0 + k) : 0ull;
-        for (int tx = tx0; tx <= tx1; ++tx) {
-          if (((tmask >> (tx - tx0)) & 1u) == 0u) continue;
-          const uint4 w = __ldg(reinterpret_cast<const uint4*>(trow + (tx << 4) + 4 * q));
-          const int rel = (tx << 5) - X0;
-          hit |= (w.x & mask_window32(mk[0], rel)) | (w.y & mask_window32(mk[1], rel)) |
-                 (w.z & mask_window32(mk[2], rel)) | (w.w & mask_window32(mk[3], rel));
-        }
-      } else {
-        for (int tx = tx0; tx <= tx1; ++tx) {
-          if (((tmask >> (tx - tx0)) & 1u) == 0u) continue;
-          const uint4 w = __ldg(reinterpret_cast<const uint4*>(trow + (tx << 4) + 4 * q));
-          const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-          const int rel = (tx << 5) - X0;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if ((unsigned)(dy0 + k) < (unsigned)f.nrows) hit |= ws[k] & mask_bits32(rows + (int64_t)(dy0 + k) * wpr, wpr, rel);
+    for (int k = 0; k < MAXB; ++k) {
+      tm[k] = 0u;
+      if (tyb + k <= ty1) {
+        tm[k] = colmask;
+        if (sum) {
+          const uint32_t* srow = sum + (tyb + k) * sw;
+          const int w0 = tx0 >> 5;
+          uint64_t two = __ldg(srow + w0);
+          if ((tx1 >> 5) != w0) two |= (uint64_t)__ldg(srow + w0 + 1) << 32;
+          tm[k] = (uint32_t)(two >> (tx0 & 31)) & colmask;
         }
       }
     }
+#pragma unroll 1
+    for (int k = 0; k < MAXB; ++k) {
+      uint32_t m = tm[k];
+      if (m == 0u) continue;
+      const int ty = tyb + k;
+      const int dy0 = (ty << 4) - Y0;                      // mask row of the band's first tile row
+      const uint32_t* trow = tiles + (((int64_t)ty * tiles_x) << 4);
+      while (m) {
+        const int tx = tx0 + __ffs((int)m) - 1;
+        m &= m - 1u;
+        const uint4* tq = reinterpret_cast<const uint4*>(trow + (tx << 4));
+        const uint4 w0 = __ldg(tq), w1 = __ldg(tq + 1), w2 = __ldg(tq + 2), w3 = __ldg(tq + 3);
+        const uint32_t ws[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+        const int rel = (tx << 5) - X0;
+        uint32_t hit = 0u;
+        if (wpr == 1) {
+          uint64_t mk[16];
+#pragma unroll
+          for (int r = 0; r < 16; ++r) mk[r] = ((unsigned)(dy0 + r) < (unsigned)f.nrows) ? __ldg(rows + dy0 + r) : 0ull;
+#pragma unroll
+          for (int r = 0; r < 16; ++r) hit |= ws[r] & mask_window32(mk[r], rel);
+        } else {
+#pragma unroll 1
+          for (int r = 0; r < 16; ++r)
+            if (ws[r] != 0u && (unsigned)(dy0 + r) < (unsigned)f.nrows) hit |= ws[r] & mask_bits32(rows + (int64_t)(dy0 + r) * wpr, wpr, rel);
+        }
+        if (hit) return true;
+      }
+    }
   }
-  return hit != 0u;
+  return false;
 }
 
 // The same verdict read straight from the uint8 costmap rows: each half-warp owns one footprint row

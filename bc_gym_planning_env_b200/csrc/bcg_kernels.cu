@@ -749,132 +749,314 @@ __global__ void __launch_bounds__(BCG_COMMIT_THREADS, BCG_COMMIT_MIN_BLOCKS) com
   }
 }
 
-// ---- state_kernel: the whole of _resolve_state_transition + reward + done for one env per thread -----------------------
-// PlanEnv.step (envs/base/env.py:334-361) up to the observation, fused: control delay (:371-373), robot model
-// (tricycle_model.py:478-538 / differential_drive.py:236-265) with Philox noise, footprint lookup, pose_collides
-// (env.py:464-489) on the lethal tile plane, rollback (:458-459), pose / robot-state delay lines (:377-389), time / iter /
-// sticky collision (:383-393), reward (reward.py:214-259 or :331-350), done (env.py:407-419), episode statistics,
-// auto-reset (:293-303), the compact observation, goal_n_state (egocentric.py:152-159) and the 128-byte record the
-// egocentric kernel starts from.
-// One thread owns one env from the first load to the last store, so nothing passes through scratch rows or work
-// records between launches (round 1: three kernels, 0.158 ms per 65 536 envs, each a single wave bound by one thread's
-// dependent chain; here one chain and one launch).  Every state access is a coalesced SoA row.  The two gathers are
-// thread-serial: collide_thread reads 16-byte quarters of only the non-empty tiles under the footprint,
-// last_reached_thread scans candidate chunks from the top with 16-byte point pairs.
-#ifndef BCG_STATE_THREADS
-#define BCG_STATE_THREADS 64
+// ---- the two state kernels of a step --------------------------------------------------------------------------------
+// PlanEnv.step (envs/base/env.py:334-361) up to the observation is two launches, split by the shape of the work:
+//
+//   move_kernel    one THREAD per env.  Everything that is scalar per env and one long dependent chain: control delay
+//                  (:371-373), robot model (tricycle_model.py:478-538 / differential_drive.py:236-265) with Philox
+//                  noise, footprint lookup, pose_collides (env.py:464-489; collide_thread: batched loads of the
+//                  non-empty lethal tiles under the footprint only), rollback (:458-459), pose / robot-state delay lines
+//                  (:377-389), time / iter / sticky collision (:383-393), the compact observation and the 128-byte
+//                  record of the egocentric kernel.  Every state access is a coalesced SoA row.  It leaves a 144-byte
+//                  StepRecord per env for
+//   reward_kernel  one WARP per env.  The one gather that wants a warp: find_last_reached (path_tools.py:408-448) over
+//                  the remaining path, lanes <-> points, chunk-culled; then lane 0 finishes the step: reward
+//                  (reward.py:214-259 / :331-350), done (env.py:407-419), episode statistics, goal_n_state
+//                  (egocentric.py:152-159; the pose's inverse transform comes precomputed in the record), and the rare
+//                  auto-reset (env.py:293-303), which rewrites the env's rows and its egocentric record from the
+//                  initial state.
+//
+// Round 1 ran three kernels (kin: thread, collide + reward: warp, commit: two threads per env; 0.158 ms per 65 536
+// envs): the collision gather sat in the warp kernel (617 warp instructions per env at 49 % issue), and the commit
+// kernel repeated the loads of the first.  A fully fused thread-per-env kernel was built and measured first
+// (profiles/r2_notes.md): bit-identical, but its thread-serial reached-index scan pays one memory round trip per
+// loop iteration -- 0.090 ms at 256 envs against 0.037 for the three kernels.
+struct __align__(16) StepRecord {     // 144 bytes, at the start of the env's slot in BcgBatch.work
+  double pose[3];                    // State.pose after this step: the pose the reward sees
+  double min_dist;                   // ContinuousRewardProviderState.min_spat_dist_so_far before this step
+  double ep_return;                  // before this step's reward
+  double ct, st, tx, ty, tt;         // inverse transform of the observed pose (coordinate_transformations.py:57-84)
+  int64_t path_off;                  // fp64 offset of the env's path rows
+  int32_t path_n, path_pitch, chunk_pitch, target;
+  int32_t flags, iter_after;
+  float drobot[6];                   // delayed robot state x, y, th, v, w, wheel (goal_n_state's tail)
+};
+static_assert(sizeof(StepRecord) == 144 && sizeof(StepRecord) <= BCG_WORK_BYTES, "StepRecord is 144 bytes");
+#define BCG_SR_HIT 1
+#define BCG_SR_COLLIDED_AFTER 2
+#define BCG_SR_TIMED_OUT 4
+#define BCG_SR_DONE_BEFORE 8
+#define BCG_SR_GOAL_BEFORE 16
+
+#ifndef BCG_MOVE_THREADS
+#define BCG_MOVE_THREADS 64
 #endif
-#ifndef BCG_STATE_MIN_BLOCKS
-#define BCG_STATE_MIN_BLOCKS 8        // register budget: 65536 / (threads x blocks) = 128
+#ifndef BCG_MOVE_MIN_BLOCKS
+#define BCG_MOVE_MIN_BLOCKS 8         // register budget: 65536 / (threads x blocks) = 128
 #endif
-__global__ void __launch_bounds__(BCG_STATE_THREADS, BCG_STATE_MIN_BLOCKS)
-state_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L, const void* __restrict__ actions,
-             const int action_is_f64, const uint64_t step_index_arg, const BcgStepOut out, const int ego_cap) {
+#ifndef BCG_REWARD_THREADS
+#define BCG_REWARD_THREADS 64
+#endif
+#ifndef BCG_REWARD_RESIDENT
+#define BCG_REWARD_RESIDENT 1280      // threads per SM the reward kernel is compiled for (register budget 48)
+#endif
+
+// the inverse transform of pose (px, py, pth), as write_goal_n_state evaluates it
+__device__ __forceinline__ void inverse_transform(double px, double py, double pth, double& ct, double& st, double& tx,
+                                                  double& ty, double& tt) {
+  double sn, cs;
+  sincos(pth, &sn, &cs);
+  tx = -px * cs - py * sn;
+  ty = px * sn - py * cs;
+  tt = wrap_angle(-pth);
+  sincos(tt, &st, &ct);
+}
+
+// goal_n_state (envs/egocentric.py:141-160) from the precomputed inverse transform; same arithmetic as write_goal_n_state
+__device__ __forceinline__ void write_goal_from_transform(const BcgParams& p, const double* __restrict__ P, int pitch, int n,
+                                                          int target, double ct, double st, double tx, double ty, double tt,
+                                                          const float drobot[6], float* __restrict__ g) {
+  if (target > n - 1) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) g[k] = 0.f;
+    return;
+  }
+  const int gi = p.ego_variant == 1 ? n - 1 : target;      // last path point vs next way point
+  const double gx = P[gi], gy = P[pitch + gi], gt = P[2 * pitch + gi];
+  const double ex = ct * gx - st * gy + tx;
+  const double ey = st * gx + ct * gy + ty;
+  const double ea = wrap_angle(gt + tt);
+  if (p.ego_variant == 1) {
+    const double nx = ex / p.ego_world_w, ny = ey / p.ego_world_h;
+    const double nrm = sqrt(nx * nx + ny * ny);
+    g[0] = (float)(nx / nrm);
+    g[1] = (float)(ny / nrm);
+    g[2] = drobot[3];
+    g[3] = drobot[4];
+    g[4] = drobot[5];
+    g[5] = g[6] = g[7] = g[8] = 0.f;
+    return;
+  }
+  g[0] = (float)clampd(ex / p.ego_world_w, -1.0, 1.0);
+  g[1] = (float)clampd(ey / p.ego_world_h, -1.0, 1.0);
+  g[2] = (float)ea;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) g[3 + k] = drobot[k];
+}
+
+__global__ void __launch_bounds__(BCG_MOVE_THREADS, BCG_MOVE_MIN_BLOCKS)
+move_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L, const void* __restrict__ actions,
+            const int action_is_f64, const uint64_t step_index_arg, const BcgStepOut out, const int ego_cap) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = e < b.n_envs;
+  if (e >= b.n_envs) return;
   const int64_t N = b.n_envs;
   const uint64_t step_index = b.step_counter ? *reinterpret_cast<const volatile uint64_t*>(b.step_counter) : step_index_arg;
-  double ev_ret = 0.0, ev_len = 0.0;
-  int ev = 0, ev_col = 0, ev_goal = 0, ev_to = 0;
   if (e == 0 && b.ego_list) b.ego_list[N] = b.ego_list[N + 1] = 0;       // hand-over count, env counter of the sparse kernel
-  if (active) {
-    double* const sf = b.state_f + e;
-    int32_t* const si = b.state_i + e;
-    // ---- everything that is read from rows (independent loads, issued together) --------------------------------------
-    double u[2];
-    if (action_is_f64) {
-      const double2 a = reinterpret_cast<const double2*>(actions)[e];
-      u[0] = a.x;
-      u[1] = a.y;
-    } else {
-      const float2 a = reinterpret_cast<const float2*>(actions)[e];
-      u[0] = (double)a.x;
-      u[1] = (double)a.y;
-    }
-    double s[7];
+  double* const sf = b.state_f + e;
+  int32_t* const si = b.state_i + e;
+  // ---- everything that is read from rows (independent loads, issued together) ----------------------------------------
+  double u[2];
+  if (action_is_f64) {
+    const double2 a = reinterpret_cast<const double2*>(actions)[e];
+    u[0] = a.x;
+    u[1] = a.y;
+  } else {
+    const float2 a = reinterpret_cast<const float2*>(actions)[e];
+    u[0] = (double)a.x;
+    u[1] = (double)a.y;
+  }
+  double s[7];
 #pragma unroll
-    for (int r = 0; r < 7; ++r) s[r] = sf[(BCG_F_ROBOT + r) * N];
-    const int map_id = b.map_id[e], path_id = b.path_id[e];
-    double min_dist = sf[BCG_F_MIN_DIST * N];
-    const double time = sf[BCG_F_TIME * N] + p.dt;
-    double ep_return = sf[BCG_F_EP_RETURN * N];
-    int target = si[BCG_I_TARGET * N];
-    const int collided = si[BCG_I_COLLIDED * N], iter = si[BCG_I_ITER * N];
-    int qp = si[BCG_I_QP * N], qs = si[BCG_I_QS * N];
-    const BcgMapDesc m = b.maps[map_id];
-    const BcgPathDesc pdsc = b.paths[path_id];
-    const PathRef pd = path_ref(b, pdsc);
+  for (int r = 0; r < 7; ++r) s[r] = sf[(BCG_F_ROBOT + r) * N];
+  const int map_id = b.map_id[e], path_id = b.path_id[e];
+  const double time = sf[BCG_F_TIME * N] + p.dt;
+  const int target = si[BCG_I_TARGET * N];
+  const int collided = si[BCG_I_COLLIDED * N], iter = si[BCG_I_ITER * N];
+  int qp = si[BCG_I_QP * N], qs = si[BCG_I_QS * N];
+  StepRecord rec;
+  rec.min_dist = sf[BCG_F_MIN_DIST * N];
+  rec.ep_return = sf[BCG_F_EP_RETURN * N];
+  const BcgMapDesc m = b.maps[map_id];
+  const BcgPathDesc pdsc = b.paths[path_id];
+  bool goal_before = target > pdsc.n - 1;
+  if (p.reward_kind == BCG_REWARD_PURE_PURSUIT) {        // reward.py:139-149 on the pose observed before this step
+    const double* P = b.path_arena + pdsc.off;
+    const double gx = __ldg(P + pdsc.n - 1), gy = __ldg(P + pdsc.pitch + pdsc.n - 1);
+    goal_before = hypot(gx - sf[(BCG_F_DPOSE + 0) * N], gy - sf[(BCG_F_DPOSE + 1) * N]) < 1.0;
+  }
+  const double old_pose[3] = {s[0], s[1], s[2]};
+  // ---- env.py:371-373 control delay, then the robot model ------------------------------------------------------------------
+  if (p.delay_control > 0) {
+    int q = si[BCG_I_QC * N];
+    delay_line<2>(sf + (int64_t)L.ring_control * N, N, q, p.delay_control, u);
+    si[BCG_I_QC * N] = q;
+  }
+  robot_step(s, u[0], u[1], p, p.env_id_base + (uint64_t)e, step_index);
+  if (b.cand) {                                          // the proposed pose, for the stand-alone collision entry points
+#pragma unroll
+    for (int r = 0; r < 3; ++r) b.cand[r * N + e] = s[r];
+  }
+  // ---- env.py:455 pose_collides of the proposed pose --------------------------------------------------------------------------
+  FootBox fb;
+  fb.bin = find_foot_bin(b.lut, s[2], b.status);
+  {
+    const short4 h = __ldg(reinterpret_cast<const short4*>(b.lut.header) + fb.bin);     // xmin, ymin, nrows, width
+    fb.X0 = world_to_pixel_1d(s[0], m.origin_x, p.inv_resolution) + h.x;
+    fb.Y0 = world_to_pixel_1d(s[1], m.origin_y, p.inv_resolution) + h.y;
+    fb.nrows = h.z;
+    fb.fwidth = h.w;
+  }
+  const bool hit = collide_thread(b.lut, b.tile_arena + m.tile_off, b.occ_sum_arena ? b.occ_sum_arena + m.sum_off : nullptr,
+                                  m.tiles_x, m.width, m.height, fb);
+  if (hit) {  // env.py:458-459 + tricycle_model.py:471-476: pose restored, v = w = 0, wheel / steer command kept
+    s[0] = old_pose[0];
+    s[1] = old_pose[1];
+    s[2] = old_pose[2];
+    s[3] = 0.0;
+    s[4] = 0.0;
+  }
+  // ---- env.py:377-389 pose and robot-state delay lines ------------------------------------------------------------------------
+  double dpose[3] = {s[0], s[1], s[2]};
+  double dstate[7];
+#pragma unroll
+  for (int r = 0; r < 7; ++r) dstate[r] = s[r];
+  delay_line<3>(sf + (int64_t)L.ring_pose * N, N, qp, p.delay_pose, dpose);
+  delay_line<7>(sf + (int64_t)L.ring_state * N, N, qs, p.delay_state, dstate);
+  // ---- env.py:383-393: the state rows that do not depend on the reward (reward_kernel writes target, min_dist, return) ---
+  const int iter_after = iter + 1;
+  const int collided_after = collided | (hit ? 1 : 0);
+#pragma unroll
+  for (int r = 0; r < 7; ++r) sf[(BCG_F_ROBOT + r) * N] = s[r];
+#pragma unroll
+  for (int r = 0; r < 7; ++r) sf[(BCG_F_DROBOT + r) * N] = dstate[r];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) sf[(BCG_F_DPOSE + r) * N] = dpose[r];
+  sf[BCG_F_TIME * N] = time;
+  si[BCG_I_ITER * N] = iter_after;
+  si[BCG_I_COLLIDED * N] = collided_after;
+  si[BCG_I_QP * N] = qp;
+  si[BCG_I_QS * N] = qs;
+  if (out.hit) out.hit[e] = hit ? 1 : 0;
+  if (out.obs_vec) {                                     // [11] = target index: reward_kernel
+    float* o = out.obs_vec + (int64_t)e * 12;
+    reinterpret_cast<float4*>(o)[0] = make_float4((float)dpose[0], (float)dpose[1], (float)dpose[2], (float)dstate[0]);
+    reinterpret_cast<float4*>(o)[1] = make_float4((float)dstate[1], (float)dstate[2], (float)dstate[3], (float)dstate[4]);
+    o[8] = (float)dstate[5];
+    o[9] = (float)dstate[6];
+    o[10] = (float)time;
+  }
+  // ---- what reward_kernel starts from ----------------------------------------------------------------------------------------
+  const bool true_pose = p.ego_variant == 1;             // observation about the true robot pose vs the observed (delayed) pose
+  const double opx = true_pose ? s[0] : dpose[0], opy = true_pose ? s[1] : dpose[1], opth = true_pose ? s[2] : dpose[2];
+  if (out.ego_image) write_ego_record(p, b, e, map_id, m, opx, opy, opth, ego_cap);
+  rec.ct = rec.st = rec.tx = rec.ty = rec.tt = 0.0;
+  if (out.goal_n_state) inverse_transform(opx, opy, opth, rec.ct, rec.st, rec.tx, rec.ty, rec.tt);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) rec.pose[r] = dpose[r];
+  rec.path_off = pdsc.off;
+  rec.path_n = pdsc.n;
+  rec.path_pitch = pdsc.pitch;
+  rec.chunk_pitch = pdsc.chunk_pitch;
+  rec.target = target;
+  rec.iter_after = iter_after;
+  const bool done_before = goal_before || (iter >= p.iteration_timeout) || (collided != 0);
+  rec.flags = (hit ? BCG_SR_HIT : 0) | (collided_after ? BCG_SR_COLLIDED_AFTER : 0) |
+              (iter_after >= p.iteration_timeout ? BCG_SR_TIMED_OUT : 0) | (done_before ? BCG_SR_DONE_BEFORE : 0) |
+              (goal_before ? BCG_SR_GOAL_BEFORE : 0);
+  rec.drobot[0] = (float)dstate[0];
+  rec.drobot[1] = (float)dstate[1];
+  rec.drobot[2] = (float)dstate[2];
+  rec.drobot[3] = (float)dstate[3];
+  rec.drobot[4] = (float)dstate[4];
+  rec.drobot[5] = (float)dstate[6];
+  uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(b.work) + (int64_t)e * BCG_WORK_BYTES);
+  const uint4* src = reinterpret_cast<const uint4*>(&rec);
+#pragma unroll
+  for (int k = 0; k < (int)(sizeof(StepRecord) / 16); ++k) dst[k] = src[k];
+}
+
+// auto-reset of env e (env.py:293-303) by its warp: the rows, the observation and the egocentric record of the initial state
+__device__ __noinline__ void reset_env_rows(const BcgParams& p, const BcgBatch& b, const BcgStepOut& out, int e, int ego_cap,
+                                            unsigned lane) {
+  const int64_t N = b.n_envs;
+  for (int r = lane; r < b.n_frows; r += 32) b.state_f[(int64_t)r * N + e] = b.init_f[(int64_t)r * N + e];
+  for (int r = lane; r < b.n_irows; r += 32) b.state_i[(int64_t)r * N + e] = b.init_i[(int64_t)r * N + e];
+  if (lane != 0) return;
+  double dpose[3], dstate[7], c[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) dpose[r] = b.init_f[(int64_t)(BCG_F_DPOSE + r) * N + e];
+#pragma unroll
+  for (int r = 0; r < 7; ++r) dstate[r] = b.init_f[(int64_t)(BCG_F_DROBOT + r) * N + e];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) c[r] = b.init_f[(int64_t)(BCG_F_ROBOT + r) * N + e];
+  const int target = b.init_i[(int64_t)BCG_I_TARGET * N + e];
+  if (out.obs_vec) {
+    float4* o = reinterpret_cast<float4*>(out.obs_vec + (int64_t)e * 12);
+    o[0] = make_float4((float)dpose[0], (float)dpose[1], (float)dpose[2], (float)dstate[0]);
+    o[1] = make_float4((float)dstate[1], (float)dstate[2], (float)dstate[3], (float)dstate[4]);
+    o[2] = make_float4((float)dstate[5], (float)dstate[6], (float)b.init_f[(int64_t)BCG_F_TIME * N + e], (float)target);
+  }
+  if (out.ego_image || out.goal_n_state) {
+    const bool true_pose = p.ego_variant == 1;
+    const double opx = true_pose ? c[0] : dpose[0], opy = true_pose ? c[1] : dpose[1], opth = true_pose ? c[2] : dpose[2];
+    if (out.ego_image) {
+      const int map_id = b.map_id[e];
+      write_ego_record(p, b, e, map_id, b.maps[map_id], opx, opy, opth, ego_cap);
+    }
+    if (out.goal_n_state) write_goal_n_state(p, b, e, b.paths[b.path_id[e]], opx, opy, opth, target, dstate, out.goal_n_state);
+  }
+}
+
+__global__ void __launch_bounds__(BCG_REWARD_THREADS, BCG_REWARD_RESIDENT / BCG_REWARD_THREADS)
+reward_kernel(const BcgParams p, const BcgBatch b, const BcgStepOut out, const int ego_cap) {
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  if (e < b.n_envs) {
+    const int64_t N = b.n_envs;
+    // the env's record: a warp-uniform 144-byte read
+    const StepRecord rec = *reinterpret_cast<const StepRecord*>(reinterpret_cast<const uint8_t*>(b.work) + (int64_t)e * BCG_WORK_BYTES);
+    PathRef pd;
+    pd.P = b.path_arena + rec.path_off;
+    pd.C = pd.P + 5 * (int64_t)rec.path_pitch;
+    pd.n = rec.path_n;
+    pd.pitch = rec.path_pitch;
+    pd.chunk_pitch = rec.chunk_pitch;
+    int target = rec.target;
+    double min_dist = rec.min_dist;
     const bool pursuit = p.reward_kind == BCG_REWARD_PURE_PURSUIT;
+    const bool goal_before = (rec.flags & BCG_SR_GOAL_BEFORE) != 0;
+    const bool hit = (rec.flags & BCG_SR_HIT) != 0;
+    // issued before the scan needs them: the goal point the reward most likely uses
     double gx = 0.0, gy = 0.0;
-    bool goal_before = target > pd.n - 1;
-    if (pursuit) {                                       // reward.py:139-149 on the pose observed before this step
-      gx = __ldg(pd.P + pd.n - 1);
-      gy = __ldg(pd.P + pd.pitch + pd.n - 1);
-      goal_before = hypot(gx - sf[(BCG_F_DPOSE + 0) * N], gy - sf[(BCG_F_DPOSE + 1) * N]) < 1.0;
+    if (pursuit || !goal_before) {
+      const int gi = pursuit ? pd.n - 1 : target;
+      gx = __ldg(pd.P + gi);
+      gy = __ldg(pd.P + pd.pitch + gi);
     }
-    const double old_pose[3] = {s[0], s[1], s[2]};
-    // ---- env.py:371-373 control delay, then the robot model ----------------------------------------------------------------
-    if (p.delay_control > 0) {
-      int q = si[BCG_I_QC * N];
-      delay_line<2>(sf + (int64_t)L.ring_control * N, N, q, p.delay_control, u);
-      si[BCG_I_QC * N] = q;
-    }
-    robot_step(s, u[0], u[1], p, p.env_id_base + (uint64_t)e, step_index);
-    if (b.cand) {                                        // the proposed pose, for the stand-alone collision entry points
-#pragma unroll
-      for (int r = 0; r < 3; ++r) b.cand[r * N + e] = s[r];
-    }
-    // ---- env.py:455 pose_collides of the proposed pose ------------------------------------------------------------------------
-    FootBox fb;
-    fb.bin = find_foot_bin(b.lut, s[2], b.status);
-    {
-      const short4 h = __ldg(reinterpret_cast<const short4*>(b.lut.header) + fb.bin);     // xmin, ymin, nrows, width
-      fb.X0 = world_to_pixel_1d(s[0], m.origin_x, p.inv_resolution) + h.x;
-      fb.Y0 = world_to_pixel_1d(s[1], m.origin_y, p.inv_resolution) + h.y;
-      fb.nrows = h.z;
-      fb.fwidth = h.w;
-    }
-    const bool hit = collide_thread(b.lut, b.tile_arena + m.tile_off, b.occ_sum_arena ? b.occ_sum_arena + m.sum_off : nullptr,
-                                    m.tiles_x, m.width, m.height, fb);
-    if (hit) {  // env.py:458-459 + tricycle_model.py:471-476: pose restored, v = w = 0, wheel / steer command kept
-      s[0] = old_pose[0];
-      s[1] = old_pose[1];
-      s[2] = old_pose[2];
-      s[3] = 0.0;
-      s[4] = 0.0;
-    }
-    // ---- env.py:377-389 pose and robot-state delay lines ----------------------------------------------------------------------
-    double dpose[3] = {s[0], s[1], s[2]};
-    double dstate[7];
-#pragma unroll
-    for (int r = 0; r < 7; ++r) dstate[r] = s[r];
-    delay_line<3>(sf + (int64_t)L.ring_pose * N, N, qp, p.delay_pose, dpose);
-    delay_line<7>(sf + (int64_t)L.ring_state * N, N, qs, p.delay_state, dstate);
-    // ---- reward of the pose State.pose now holds (reward.py:214-259 / :331-350) ---------------------------------------------
     double reward = 0.0;
     bool goal;
     if (pursuit) {
-      target = first_beyond_radius_thread(pd, target, dpose[0], dpose[1], 2.0);
-      const double d = hypot(gx - dpose[0], gy - dpose[1]);
+      // ContinuousRewardPurePursuitProvider.reward (reward.py:331-350)
+      target = first_beyond_radius(pd, target, rec.pose[0], rec.pose[1], 2.0, lane);
+      const double d = hypot(gx - rec.pose[0], gy - rec.pose[1]);
       reward = -0.05;
       reward += min_dist - d;
-      if (collided || hit) reward -= 100;
+      if (rec.flags & BCG_SR_COLLIDED_AFTER) reward -= 100;
       min_dist = d;
       goal = d < 1.0;
     } else {
       if (!goal_before) {
-        const double tx = __ldg(pd.P + target), ty = __ldg(pd.P + pd.pitch + target);   // issued before the scan needs them
-        const int last = last_reached_thread(p, pd, target, dpose[0], dpose[1], dpose[2]);
+        const int last = last_reached_from(p, pd, target, rec.pose[0], rec.pose[1], rec.pose[2], lane);
         if (last >= target) {
           target = last + 1;
           if (target > pd.n - 1) {
             min_dist = 0.0;
           } else {
-            min_dist = hypot(__ldg(pd.P + target) - dpose[0], __ldg(pd.P + pd.pitch + target) - dpose[1]);
+            min_dist = hypot(__ldg(pd.P + target) - rec.pose[0], __ldg(pd.P + pd.pitch + target) - rec.pose[1]);
           }
           reward = 1.0;
         } else {
-          const double d = hypot(tx - dpose[0], ty - dpose[1]);
+          const double d = hypot(gx - rec.pose[0], gy - rec.pose[1]);
           if (d < min_dist) {
             reward = (min_dist - d) * p.progress_multiplier;
             min_dist = d;
@@ -883,82 +1065,32 @@ state_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L, const 
       }
       goal = target > pd.n - 1;
     }
-    ep_return += reward;
-    // ---- env.py:383-393, :407-419 ------------------------------------------------------------------------------------------------
-    const bool done_before = goal_before || (iter >= p.iteration_timeout) || (collided != 0);
-    const int iter_after = iter + 1;
-    const int collided_after = collided | (hit ? 1 : 0);
-    const bool timed_out = iter_after >= p.iteration_timeout;
-    const bool done = goal || timed_out || (collided_after != 0);
-    const bool reset_now = done && p.auto_reset;
-    if (out.reward) out.reward[e] = reward;
-    if (out.done) out.done[e] = done ? 1 : 0;
-    if (out.hit) out.hit[e] = hit ? 1 : 0;
-    if (done && !done_before) {
-      ev = 1;
-      ev_ret = ep_return;
-      ev_len = (double)iter_after;
-      ev_col = collided_after;
-      ev_goal = goal ? 1 : 0;
-      ev_to = timed_out ? 1 : 0;
+    // ---- env.py:407-419 done, statistics, outputs ---------------------------------------------------------------------------
+    const bool timed_out = (rec.flags & BCG_SR_TIMED_OUT) != 0, collided_after = (rec.flags & BCG_SR_COLLIDED_AFTER) != 0;
+    const bool done = goal || timed_out || collided_after;
+    const double ep_return = rec.ep_return + reward;
+    if (lane == 0) {
+      if (out.reward) out.reward[e] = reward;
+      if (out.done) out.done[e] = done ? 1 : 0;
+      if (done && !(rec.flags & BCG_SR_DONE_BEFORE)) {
+        atomicAdd(b.stats + BCG_STAT_EPISODES, 1.0);
+        atomicAdd(b.stats + BCG_STAT_RETURN, ep_return);
+        atomicAdd(b.stats + BCG_STAT_LENGTH, (double)rec.iter_after);
+        if (collided_after) atomicAdd(b.stats + BCG_STAT_COLLIDED, 1.0);
+        if (goal) atomicAdd(b.stats + BCG_STAT_GOAL, 1.0);
+        if (timed_out) atomicAdd(b.stats + BCG_STAT_TIMEOUT, 1.0);
+      }
     }
-    double otime = time;
-    if (reset_now) {                                     // env.py:293-303: the state (and the observation) is the initial one
-      for (int r = 0; r < L.n_frows; ++r) sf[(int64_t)r * N] = b.init_f[(int64_t)r * N + e];
-      for (int r = 0; r < L.n_irows; ++r) si[(int64_t)r * N] = b.init_i[(int64_t)r * N + e];
-      target = b.init_i[(int64_t)BCG_I_TARGET * N + e];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) dpose[r] = b.init_f[(int64_t)(BCG_F_DPOSE + r) * N + e];
-#pragma unroll
-      for (int r = 0; r < 7; ++r) dstate[r] = b.init_f[(int64_t)(BCG_F_DROBOT + r) * N + e];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) s[r] = b.init_f[(int64_t)(BCG_F_ROBOT + r) * N + e];
-      otime = b.init_f[(int64_t)BCG_F_TIME * N + e];
-    } else {
-#pragma unroll
-      for (int r = 0; r < 7; ++r) sf[(BCG_F_ROBOT + r) * N] = s[r];
-#pragma unroll
-      for (int r = 0; r < 7; ++r) sf[(BCG_F_DROBOT + r) * N] = dstate[r];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) sf[(BCG_F_DPOSE + r) * N] = dpose[r];
-      sf[BCG_F_TIME * N] = time;
-      sf[BCG_F_MIN_DIST * N] = min_dist;
-      sf[BCG_F_EP_RETURN * N] = ep_return;
-      si[BCG_I_ITER * N] = iter_after;
-      si[BCG_I_TARGET * N] = target;
-      si[BCG_I_COLLIDED * N] = collided_after;
-      si[BCG_I_QP * N] = qp;
-      si[BCG_I_QS * N] = qs;
-    }
-    if (out.obs_vec) {
-      float4* o = reinterpret_cast<float4*>(out.obs_vec + (int64_t)e * 12);
-      o[0] = make_float4((float)dpose[0], (float)dpose[1], (float)dpose[2], (float)dstate[0]);
-      o[1] = make_float4((float)dstate[1], (float)dstate[2], (float)dstate[3], (float)dstate[4]);
-      o[2] = make_float4((float)dstate[5], (float)dstate[6], (float)otime, (float)target);
-    }
-    if (out.ego_image || out.goal_n_state) {
-      // the observation the egocentric kernel will render is that of the state just written
-      const bool true_pose = p.ego_variant == 1;         // true robot pose vs observed (delayed) pose
-      const double opx = true_pose ? s[0] : dpose[0], opy = true_pose ? s[1] : dpose[1], opth = true_pose ? s[2] : dpose[2];
-      if (out.ego_image) write_ego_record(p, b, e, map_id, m, opx, opy, opth, ego_cap);
-      if (out.goal_n_state) write_goal_n_state(p, b, e, pdsc, opx, opy, opth, target, dstate, out.goal_n_state);
-    }
-  }
-  // episode statistics: one atomic set per warp that saw an episode end
-  if (__any_sync(BCG_FULL, ev != 0)) {
-    double v[6] = {(double)ev, ev_ret, ev_len, (double)ev_col, (double)ev_goal, (double)ev_to};
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(BCG_FULL, v[k], o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-      atomicAdd(b.stats + BCG_STAT_EPISODES, v[0]);
-      atomicAdd(b.stats + BCG_STAT_RETURN, v[1]);
-      atomicAdd(b.stats + BCG_STAT_LENGTH, v[2]);
-      atomicAdd(b.stats + BCG_STAT_COLLIDED, v[3]);
-      atomicAdd(b.stats + BCG_STAT_GOAL, v[4]);
-      atomicAdd(b.stats + BCG_STAT_TIMEOUT, v[5]);
+    if (done && p.auto_reset) {
+      reset_env_rows(p, b, out, e, ego_cap, lane);
+    } else if (lane == 0) {
+      b.state_f[BCG_F_MIN_DIST * N + e] = min_dist;
+      b.state_f[BCG_F_EP_RETURN * N + e] = ep_return;
+      b.state_i[BCG_I_TARGET * N + e] = target;
+      if (out.obs_vec) out.obs_vec[(int64_t)e * 12 + 11] = (float)target;
+      if (out.goal_n_state)
+        write_goal_from_transform(p, pd.P, pd.pitch, pd.n, target, rec.ct, rec.st, rec.tx, rec.ty, rec.tt, rec.drobot,
+                                  out.goal_n_state + (int64_t)e * 9);
     }
   }
   // device-side step counter (CUDA-graph replays cannot change a kernel argument): the last CTA to finish bumps it
@@ -970,7 +1102,7 @@ state_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L, const 
       const unsigned long long ticket = atomicAdd(ctr + 1, 1ull);
       if (ticket == (unsigned long long)gridDim.x - 1ull) {
         ctr[1] = 0ull;
-        ctr[0] = step_index + 1ull;
+        ctr[0] = ctr[0] + 1ull;
       }
     }
   }
@@ -2607,7 +2739,7 @@ int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, 
   const BcgStateLayout L = make_layout(*p);
   if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[0], s));
   if (split_state_kernels_requested()) {
-    // round 1's three state kernels (BCG_STEP_KERNELS=split): kept as the A/B and bit-equality reference of state_kernel
+    // round 1's three state kernels (BCG_STEP_KERNELS=split): kept as the A/B and bit-equality reference of move_kernel + reward_kernel
     kin_kernel<<<blocks_for(b->n_envs, BCG_KIN_THREADS), BCG_KIN_THREADS, 0, s>>>(*p, *b, L, actions, action_is_f64, step_index);
     BCG_CHECK_CUDA(cudaGetLastError());
     if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[1], s));
@@ -2617,12 +2749,13 @@ int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, 
     commit_kernel<<<blocks_for(b->n_envs, BCG_COMMIT_THREADS / 2), BCG_COMMIT_THREADS, 0, s>>>(*p, *b, L, *out, ego ? ego_capacity(*p, *b) : 0);
     BCG_CHECK_CUDA(cudaGetLastError());
   } else {
-    if (events) {
-      BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[1], s));
-      BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[2], s));
-    }
-    state_kernel<<<blocks_for(b->n_envs, BCG_STATE_THREADS), BCG_STATE_THREADS, 0, s>>>(*p, *b, L, actions, action_is_f64, step_index,
-                                                                                       *out, ego ? ego_capacity(*p, *b) : 0);
+    if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[1], s));
+    const int cap = ego ? ego_capacity(*p, *b) : 0;
+    move_kernel<<<blocks_for(b->n_envs, BCG_MOVE_THREADS), BCG_MOVE_THREADS, 0, s>>>(*p, *b, L, actions, action_is_f64, step_index,
+                                                                                    *out, cap);
+    BCG_CHECK_CUDA(cudaGetLastError());
+    if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[2], s));
+    reward_kernel<<<blocks_for((int64_t)b->n_envs * 32, BCG_REWARD_THREADS), BCG_REWARD_THREADS, 0, s>>>(*p, *b, *out, cap);
     BCG_CHECK_CUDA(cudaGetLastError());
   }
   if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[3], s));

@@ -414,7 +414,7 @@ def gen_goal_reached(name, n_envs, extra, every):
     from bc_gym_planning_env.utilities.coordinate_transformations import normalize_angle
     ep = EnvParams(control_delay=2, pose_delay=1, state_delay=1)
     envs, records, actions, images, vectors = [], [], [], [], []
-    n_steps = None
+    n_total = 240
     runs = []
     for s in range(n_envs):
         world = RandomAisleTurnEnv(seed=600 + s)._env._state
@@ -426,7 +426,7 @@ def gen_goal_reached(name, n_envs, extra, every):
         recs, ea, ei, ev = [], [], [], []
         done_at = None
         t = 0
-        while done_at is None or t < done_at + extra:
+        while t < n_total:
             plain = pe._extract_obs()
             if len(plain.path):
                 tgt = plain.path[min(len(plain.path) - 1, 6)]
@@ -443,11 +443,10 @@ def gen_goal_reached(name, n_envs, extra, every):
             if d and done_at is None:
                 done_at = t
             t += 1
-            assert t < 1000
         envs.append(pe)
         runs.append((recs, ea, ei, ev, done_at))
-    n_steps = min(len(r[0]) for r in runs) // every * every      # common length (all envs are past done by then)
-    assert all(r[4] + 10 < n_steps for r in runs)
+    n_steps = n_total // every * every
+    assert all(r[4] is not None and r[4] + extra <= n_steps for r in runs), [r[4] for r in runs]
     out = _pack_envs(envs)
     out.update({"ref_" + k: v for k, v in _stack([r[0][:n_steps] for r in runs]).items()})
     out["actions"] = np.array([r[1][:n_steps] for r in runs], dtype=np.float32)

@@ -393,16 +393,22 @@ def ego_costmap_cv2(costmap, pose, origin, resolution):
 
 
 def ego_path(path, pose):
-    """utilities/coordinate_transformations.py:341-362 -> :57-84 -> :310-328: the path in the
-    robot frame, R(-th)(p - t), angles wrapped."""
+    """utilities/coordinate_transformations.py:341-362 -> :57-84 (inverse_transform) -> :310-328 (project_poses): the
+    path in the robot frame, R(-th)(p - t), angles wrapped.  Like the reference, the points go through ONE
+    np.dot(3x3 homogeneous matrix, [x; y; 1] columns) (:322-324): BLAS evaluates that 3-term dot product with fused
+    multiply-adds, so it must be the same call on the same shapes to give the same last bits (a way point dead ahead
+    of the robot has y ~ 1e-17 by cancellation)."""
+    path = np.asarray(path, dtype=np.float64)
     c, s = np.cos(pose[2]), np.sin(pose[2])
     tx = -pose[0] * c - pose[1] * s
     ty = pose[0] * s - pose[1] * c
     tt = float(normalize_angle(-pose[2]))
     ct, st = np.cos(tt), np.sin(tt)
-    out = np.empty_like(path)
-    out[:, 0] = ct * path[:, 0] - st * path[:, 1] + tx
-    out[:, 1] = st * path[:, 0] + ct * path[:, 1] + ty
+    h = np.identity(3)
+    h[:2, :2] = np.array([[ct, -st], [st, ct]])
+    h[:2, 2] = (tx, ty)
+    ph = np.hstack((path[:, :2], np.ones((path.shape[0], 1))))
+    out = np.dot(h, ph.T).T
     out[:, 2] = normalize_angle(path[:, 2] + tt)
     return out
 
@@ -415,7 +421,7 @@ def goal_n_state(remaining_path, pose, robot_state, resolution=0.03):
     w, h = ego_crop_size(resolution)
     ox, oy = EGO_X_BOUNDS[0], EGO_Y_BOUNDS[0]
     world = np.array([(ox + resolution * w) - ox, (oy + resolution * h) - oy])  # costmap_2d.py:106-121
-    g = ego_path(np.asarray(remaining_path[:1], dtype=np.float64), pose)[0]
+    g = ego_path(np.asarray(remaining_path, dtype=np.float64), pose)[0]      # the whole remaining path, like the reference
     ng = np.clip(g[:2] / world, (-1., -1.), (1., 1.))
     x, y, th, v, w_, _, wheel = robot_state
     return np.hstack([ng, g[2], [x, y, th, v, w_, wheel]]).astype(np.float32)

@@ -10,7 +10,8 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("staging,name", [("tiles", "aisle_ego"), ("tma", "aisle_ego"), ("spans", "aisle_ego"),
-                                          ("tiles", "edge_worlds"), ("spans", "edge_worlds")])
+                                          ("tiles", "edge_worlds"), ("spans", "edge_worlds"),
+                                          ("tiles", "aisle_goal_reached")])
 def test_ego_observation_matches_reference(staging, name):
     """All ways of staging the source window (cell tiles via cp.async, TMA box loads, plain span loads) against cv2;
     `edge_worlds`: crops that lie partly or wholly outside tiny maps (the reference pads with zeros)."""
@@ -21,6 +22,11 @@ def test_ego_observation_matches_reference(staging, name):
     k = 0
     for t in range(actions.shape[1]):
         env.step(actions[:, t].contiguous())
+        if "ref_goal_n_state_all" in d:              # the goal vector at every step, across the goal-reached transition
+            vec = env.goal_n_state.cpu().numpy()[..., 0]
+            ref = d["ref_goal_n_state_all"][:, t]
+            assert np.all(np.abs(vec - ref) <= np.spacing(np.abs(ref).astype(np.float32)) + 1e-12), t
+            assert np.array_equal((vec == 0).all(axis=1), (ref == 0).all(axis=1)), t    # all zeros once the path is finished
         if t % every == every - 1:
             img = env.ego_image.cpu().numpy()[..., 0]
             vec = env.goal_n_state.cpu().numpy()[..., 0]

@@ -31,7 +31,8 @@ def _rollout(d, **kw):
     return {k: np.swapaxes(np.array(v), 0, 1) for k, v in rec.items()}
 
 
-@pytest.mark.parametrize("name", ["mini_noise_off", "aisle_delays_211", "aisle_delays_120", "aisle_pure_pursuit", "edge_worlds"])
+@pytest.mark.parametrize("name", ["mini_noise_off", "aisle_delays_211", "aisle_delays_120", "aisle_pure_pursuit", "edge_worlds",
+                                  "aisle_goal_reached", "aisle_res005_scale125"])
 def test_step_matches_reference(name):
     d = common.load(name)
     got = _rollout(d)
@@ -43,6 +44,8 @@ def test_step_matches_reference(name):
         np.testing.assert_allclose(got[k], ref, rtol=0, atol=common.TIGHT_ATOL, err_msg=k)
     assert d["ref_collided"].any() and d["ref_done"].any()
     assert (d["ref_reward"] == 1.0).any() or (d["ref_reward"] < -99).any()
+    if name == "aisle_goal_reached":          # every env finishes its path and is stepped on past done (reward.py:223-224)
+        assert (d["ref_path_len"][:, -1] == 0).all() and (got["reward"][:, -40:] == 0).all()
 
 
 def test_f64_actions_and_shared_pools_agree():

@@ -22,7 +22,8 @@ def _replay(d, oracles):
             assert len(obs["path"]) == d["ref_path_len"][e, t]
 
 
-@pytest.mark.parametrize("name", ["mini_noise_off", "aisle_delays_211", "aisle_delays_120", "aisle_pure_pursuit", "edge_worlds"])
+@pytest.mark.parametrize("name", ["mini_noise_off", "aisle_delays_211", "aisle_delays_120", "aisle_pure_pursuit", "edge_worlds",
+                                  "aisle_goal_reached", "aisle_res005_scale125"])
 def test_oracle_matches_reference_rollouts(name):
     d = common.load(name)
     _replay(d, common.make_oracles(d))
@@ -53,7 +54,7 @@ def test_oracle_collision_and_pixel_counts():
             assert O.footprint_pixels_in_map(x, y, th, O.TRICYCLE_FOOTPRINT, cm.shape, origin, res) == d["ref_pixels"][e, k]
 
 
-@pytest.mark.parametrize("name", ["aisle_ego", "edge_worlds"])
+@pytest.mark.parametrize("name", ["aisle_ego", "edge_worlds", "aisle_goal_reached"])
 def test_oracle_ego_observation(name):
     """Closed form of cv2.warpAffine and the literal cv2 call, both against the reference's
     EgocentricCostmap wrapper -- on aisles, and on the tiny worlds whose crops lie partly or wholly outside the map."""
@@ -64,6 +65,9 @@ def test_oracle_ego_observation(name):
         k = 0
         for t in range(d["actions"].shape[1]):
             obs, _, _, _ = o.step(d["actions"][e, t])
+            if "ref_goal_n_state_all" in d:          # the goal vector at every step, across the goal-reached transition
+                g = O.goal_n_state(obs["path"], obs["pose"], obs["robot_state"], o.resolution)
+                assert np.array_equal(g, d["ref_goal_n_state_all"][e, t]), (e, t)
             if t % every == every - 1:
                 want = d["ref_ego_image"][e, k]
                 assert np.array_equal(O.ego_costmap(o.costmap, obs["pose"], o.origin, o.resolution), want)
