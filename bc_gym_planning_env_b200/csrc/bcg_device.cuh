@@ -282,11 +282,29 @@ __device__ __forceinline__ int find_foot_bin(const BcgFootprintLut& lut, double 
     if (kk >= lut.n_bins) kk -= lut.n_bins;
     const int16_t* v = lut.verts + (int64_t)kk * 2 * lut.n_verts;
     bool ok = true;
-    for (int i = 0; i < lut.n_verts && ok; ++i) {
-      const double fx = __ldg(lut.fp_pix + 2 * i), fy = __ldg(lut.fp_pix + 2 * i + 1);
-      const int vx = (int)rint(fma(fy, -sn, fx * cs));   // np.dot's fused form, see oracle
-      const int vy = (int)rint(fma(fy, cs, fx * sn));
-      ok = (v[2 * i] == vx) && (v[2 * i + 1] == vy);
+    if ((lut.n_verts & 3) == 0) {
+      // four vertices per 16-byte load (a tuple row is n_verts * 4 bytes, rows of a table with n_verts % 4 == 0 are
+      // 16-byte aligned): per-lane bins make every load a separate line, so the tuple is fetched in as few loads as possible
+      const uint4* v4 = reinterpret_cast<const uint4*>(v);
+      for (int i4 = 0; i4 < lut.n_verts / 4 && ok; ++i4) {
+        const uint4 q = __ldg(v4 + i4);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = 4 * i4 + j;
+          const double fx = __ldg(lut.fp_pix + 2 * i), fy = __ldg(lut.fp_pix + 2 * i + 1);
+          const int vx = (int)rint(fma(fy, -sn, fx * cs));   // np.dot's fused form, see oracle
+          const int vy = (int)rint(fma(fy, cs, fx * sn));
+          ok = ok && ((int)(int16_t)(w[j] & 0xffffu) == vx) && ((int)(int16_t)(w[j] >> 16) == vy);
+        }
+      }
+    } else {
+      for (int i = 0; i < lut.n_verts && ok; ++i) {
+        const double fx = __ldg(lut.fp_pix + 2 * i), fy = __ldg(lut.fp_pix + 2 * i + 1);
+        const int vx = (int)rint(fma(fy, -sn, fx * cs));   // np.dot's fused form, see oracle
+        const int vy = (int)rint(fma(fy, cs, fx * sn));
+        ok = (v[2 * i] == vx) && (v[2 * i + 1] == vy);
+      }
     }
     if (ok) return kk;
   }
@@ -410,6 +428,7 @@ __device__ __forceinline__ bool collide_thread(const BcgFootprintLut& lut, const
   const uint64_t* __restrict__ rows = lut.rows + (int64_t)f.bin * lut.max_rows * wpr;
   const int sw = (tiles_x + 31) >> 5;
   const uint32_t colmask = (2u << (tx1 - tx0)) - 1u;     // bit j <-> tile column tx0 + j
+  const bool pair_rows = (lut.max_rows & 1) == 0 && (reinterpret_cast<uintptr_t>(lut.rows) & 15) == 0;   // rows of a bin start 16-byte aligned
   constexpr int MAXB = 6;                                // bands per batch (a 64-row mask spans <= 5)
   for (int tyb = ty0; tyb <= ty1; tyb += MAXB) {
     uint32_t tm[MAXB];
@@ -442,7 +461,22 @@ __device__ __forceinline__ bool collide_thread(const BcgFootprintLut& lut, const
         const uint32_t ws[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
         const int rel = (tx << 5) - X0;
         uint32_t hit = 0u;
-        if (wpr == 1) {
+        if (wpr == 1 && pair_rows) {
+          // the band's 16 mask rows as nine aligned 16-byte pairs starting at the even row at or below dy0 (rows beyond
+          // the mask are zero in the table; pairs outside the bin's max_rows rows are not loaded)
+          const int base = dy0 & ~1, odd = dy0 & 1;
+          uint64_t v[18];
+#pragma unroll
+          for (int j = 0; j < 9; ++j) {
+            const int r0 = base + 2 * j;
+            ulonglong2 q = make_ulonglong2(0ull, 0ull);
+            if ((unsigned)r0 < (unsigned)lut.max_rows) q = __ldg(reinterpret_cast<const ulonglong2*>(rows + r0));
+            v[2 * j] = q.x;
+            v[2 * j + 1] = q.y;
+          }
+#pragma unroll
+          for (int r = 0; r < 16; ++r) hit |= ws[r] & mask_window32(odd ? v[r + 1] : v[r], rel);
+        } else if (wpr == 1) {
           uint64_t mk[16];
 #pragma unroll
           for (int r = 0; r < 16; ++r) mk[r] = ((unsigned)(dy0 + r) < (unsigned)f.nrows) ? __ldg(rows + dy0 + r) : 0ull;

@@ -18,6 +18,7 @@
 #include <cudaTypedefs.h>
 #include <cuda_runtime.h>
 
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -782,6 +783,8 @@ struct __align__(16) StepRecord {     // 144 bytes, at the start of the env's sl
   float drobot[6];                   // delayed robot state x, y, th, v, w, wheel (goal_n_state's tail)
 };
 static_assert(sizeof(StepRecord) == 144 && sizeof(StepRecord) <= BCG_WORK_BYTES, "StepRecord is 144 bytes");
+static_assert(offsetof(StepRecord, path_off) == 80 && offsetof(StepRecord, chunk_pitch) == 96 && offsetof(StepRecord, drobot) == 112,
+              "move_kernel stores the record field by field");
 #define BCG_SR_HIT 1
 #define BCG_SR_COLLIDED_AFTER 2
 #define BCG_SR_TIMED_OUT 4
@@ -969,14 +972,22 @@ move_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L, const v
   rec.drobot[3] = (float)dstate[3];
   rec.drobot[4] = (float)dstate[4];
   rec.drobot[5] = (float)dstate[6];
-  uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(b.work) + (int64_t)e * BCG_WORK_BYTES);
-  const uint4* src = reinterpret_cast<const uint4*>(&rec);
-#pragma unroll
-  for (int k = 0; k < (int)(sizeof(StepRecord) / 16); ++k) dst[k] = src[k];
+  // (field by field: copying the struct through a uint4 pointer would force it into local memory)
+  uint8_t* const dst = reinterpret_cast<uint8_t*>(b.work) + (int64_t)e * BCG_WORK_BYTES;
+  double2* d2 = reinterpret_cast<double2*>(dst);
+  d2[0] = make_double2(rec.pose[0], rec.pose[1]);
+  d2[1] = make_double2(rec.pose[2], rec.min_dist);
+  d2[2] = make_double2(rec.ep_return, rec.ct);
+  d2[3] = make_double2(rec.st, rec.tx);
+  d2[4] = make_double2(rec.ty, rec.tt);
+  reinterpret_cast<int4*>(dst + 80)[0] = make_int4((int)(rec.path_off & 0xffffffffll), (int)(rec.path_off >> 32), rec.path_n, rec.path_pitch);
+  reinterpret_cast<int4*>(dst + 96)[0] = make_int4(rec.chunk_pitch, rec.target, rec.flags, rec.iter_after);
+  reinterpret_cast<float4*>(dst + 112)[0] = make_float4(rec.drobot[0], rec.drobot[1], rec.drobot[2], rec.drobot[3]);
+  reinterpret_cast<float2*>(dst + 128)[0] = make_float2(rec.drobot[4], rec.drobot[5]);
 }
 
 // auto-reset of env e (env.py:293-303) by its warp: the rows, the observation and the egocentric record of the initial state
-__device__ __noinline__ void reset_env_rows(const BcgParams& p, const BcgBatch& b, const BcgStepOut& out, int e, int ego_cap,
+__device__ __forceinline__ void reset_env_rows(const BcgParams& p, const BcgBatch& b, const BcgStepOut& out, int e, int ego_cap,
                                             unsigned lane) {
   const int64_t N = b.n_envs;
   for (int r = lane; r < b.n_frows; r += 32) b.state_f[(int64_t)r * N + e] = b.init_f[(int64_t)r * N + e];

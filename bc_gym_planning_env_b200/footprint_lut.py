@@ -90,7 +90,7 @@ class FootprintLut(object):
             if key not in cache:
                 cache[key] = fill_polygon_mask(t)
             masks.append(cache[key])
-        self.max_rows = max(m.shape[0] for m, _, _ in masks)
+        self.max_rows = (max(m.shape[0] for m, _, _ in masks) + 1) // 2 * 2     # even: the device loads rows in 16-byte pairs
         width = max(m.shape[1] for m, _, _ in masks)
         self.wpr = (width + 63) // 64
         self.header = np.zeros((self.n_bins, 4), dtype=np.int16)

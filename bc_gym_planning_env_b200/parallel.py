@@ -47,40 +47,45 @@ def broadcast_snapshot(f, i, src=0):
     return f, i
 
 
-def fan_out_columns(k_states, n_local):
-    """Which snapshot column each local env starts from when k_states start states are replicated
-    over all envs of all ranks: global env g takes state g % k_states."""
-    rank, ws = world()
-    g0 = rank * n_local
-    return (torch.arange(n_local, dtype=torch.int64) + g0) % int(k_states)
+def fan_out_columns(k_states, n_local, first_global_env=None):
+    """Which snapshot column each local env starts from when k_states start states are replicated over all envs of
+    all ranks: global env g takes state g % k_states.  `first_global_env` is the global id of this rank's env 0
+    (VecPlanEnv's env_id_base, or shard_range(...)[0]); default: every rank holds n_local envs."""
+    if first_global_env is None:
+        first_global_env = world()[0] * int(n_local)
+    return (torch.arange(n_local, dtype=torch.int64) + int(first_global_env)) % int(k_states)
 
 
-def monte_carlo_rollouts(env, start, actions, reduce=True):
+def monte_carlo_rollouts(env, start, actions, reduce=True, cols=None):
     """Monte-Carlo evaluation of `start` states (README.md:45-61 of the reference, batched).
 
-    env: a VecPlanEnv whose envs all share the map/path of the start states they are assigned;
+    env: a VecPlanEnv (auto_reset off) whose env e has the map and path of the start state it is assigned;
     start: VecState with k columns (already identical on every rank, e.g. via broadcast_snapshot);
-    actions: [H, k, 2] fixed action sequence per start state.  Every local env e is loaded with column
-    fan_out_columns()[e] and stepped H times with its own Philox stream.
-    Returns fp64 [k, 4]: (sum of returns, collisions, goals reached, rollouts) per start state, summed
-    over ranks when reduce."""
-    from bc_gym_planning_env_b200 import _native as nat
+    actions: [H, k, 2] fixed action sequence per start state.  Local env e is loaded with column cols[e] (default:
+    fan_out_columns from the env's env_id_base, i.e. global env g takes state g % k) and stepped H times with its own
+    Philox stream.
+    Returns fp64 [k, 4]: (sum of returns, rollouts that collided, rollouts that finished their path, rollouts) per
+    start state, summed over ranks when reduce."""
+    if env.auto_reset:
+        raise ValueError("Monte-Carlo rollouts need auto_reset off: a reset rollout would restart from the initial state")
     k = start.f.shape[1]
-    cols = fan_out_columns(k, env.n_envs).to(env.device)
+    if cols is None:
+        cols = fan_out_columns(k, env.n_envs, int(env._c_params.env_id_base))
+    cols = cols.to(env.device)
+    if tuple(cols.shape) != (env.n_envs,) or int(cols.min()) < 0 or int(cols.max()) >= k:
+        raise ValueError("cols must assign one of the %d start states to each of the %d envs" % (k, env.n_envs))
+    if tuple(actions.shape[1:]) != (k, 2):
+        raise ValueError("actions must have shape [H, %d, 2]" % k)
     env.set_state(type(start)(start.f.to(env.device)[:, cols].contiguous(), start.i.to(env.device)[:, cols].contiguous()))
     ret = torch.zeros(env.n_envs, dtype=torch.float64, device=env.device)
-    acts = actions.to(env.device)
+    acts = actions.to(env.device)[:, cols].contiguous()          # [H, n, 2]: one gather for the whole horizon
     for h in range(acts.shape[0]):
-        _, r, _, _ = env.step(acts[h][cols].contiguous())
+        _, r, _, _ = env.step(acts[h])
         ret += r
+    from bc_gym_planning_env_b200 import _native as nat
     out = torch.zeros((k, 4), dtype=torch.float64, device=env.device)
-    target = env.state_i[nat.I_TARGET].to(torch.int64)
-    n_path = torch.as_tensor([len(env.full_path(e)) for e in range(env.n_envs)], device=env.device) \
-        if env.n_envs <= 4096 else None
-    collided = env.state_i[nat.I_COLLIDED].to(torch.float64)
     out[:, 0].index_add_(0, cols, ret)
-    out[:, 1].index_add_(0, cols, collided)
-    if n_path is not None:
-        out[:, 2].index_add_(0, cols, (target > n_path - 1).to(torch.float64))
+    out[:, 1].index_add_(0, cols, env.state_i[nat.I_COLLIDED].to(torch.float64))
+    out[:, 2].index_add_(0, cols, env.goal_reached().to(torch.float64))
     out[:, 3].index_add_(0, cols, torch.ones_like(ret))
     return allreduce_sum_(out) if reduce else out

@@ -118,14 +118,6 @@ class _VecSlotEnv(VecPlanEnv):
         slots.gen_state = self._gen_state.data_ptr()
         self._slots = slots
 
-    def _mask(self, mask):
-        if mask is None:
-            return None
-        m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
-        if tuple(m.shape) != (self.n_envs,):
-            raise ValueError("mask must have shape (%d,)" % self.n_envs)
-        return m
-
     # ---- accessors: the worlds live on the device ----------------------------------------------------
     def _map_desc(self, e):
         sz = C.sizeof(nat.BcgMapDesc)

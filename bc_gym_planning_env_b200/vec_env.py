@@ -513,11 +513,18 @@ class VecPlanEnv(object):
 
     def reset(self, mask=None):
         """PlanEnv.reset for all envs (mask None) or those with mask[e] true."""
-        m = None
-        if mask is not None:
-            m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        m = self._mask(mask)
         nat.check(nat.lib().bcg_reset_where(C.byref(self._batch), nat.ptr(m), self._stream()))
         return self.observation()
+
+    def _mask(self, mask):
+        """uint8 [N] device tensor of a per-env mask (None stays None); the kernels index it by env id unchecked"""
+        if mask is None:
+            return None
+        m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        if tuple(m.shape) != (self.n_envs,):
+            raise ValueError("mask must have shape (%d,)" % self.n_envs)
+        return m
 
     def observation(self):
         return VecObservation(self)
@@ -610,6 +617,7 @@ class VecPlanEnv(object):
             self._status.zero_()
             raise ValueError("Goal pose too close to initial pose")   # reference envs/base/reward.py:275-277
         if st[nat.STATUS_LUT_MISS]:
+            self._status.zero_()
             raise nat.BcgError("%d footprint lookups fell outside the angle-bin table" % st[nat.STATUS_LUT_MISS])
         if st[nat.STATUS_SLOT_OVERFLOW]:
             self._status.zero_()
@@ -622,6 +630,25 @@ class VecPlanEnv(object):
         if reset:
             self._stats.zero_()
         return out
+
+    def path_lengths(self):
+        """Refined path length of every env, int64 [N] on the device -- read from the path descriptors where they live
+        (device-generated worlds rewrite them), no host round trip."""
+        n_of_path = self.path_descs.view(torch.int32).view(-1, C.sizeof(nat.BcgPathDesc) // 4)[:, nat.BcgPathDesc.n.offset // 4]
+        return n_of_path[self.path_id.to(torch.int64)].to(torch.int64)
+
+    def goal_reached(self):
+        """bool [N]: has env e finished its path?  ContinuousRewardProvider: target_idx past the last way point
+        (reference envs/base/reward.py:66-69); pure pursuit: observed pose within 1 m of the last point (:139-149)."""
+        n = self.path_lengths()
+        if self.params.reward_provider_name != CONTINUOUS_REWARD_PURE_PURSUIT:
+            return self.state_i[nat.I_TARGET].to(torch.int64) > n - 1
+        d = self.path_descs.view(torch.int64).view(-1, C.sizeof(nat.BcgPathDesc) // 8)
+        pid = self.path_id.to(torch.int64)
+        off = d[:, nat.BcgPathDesc.off.offset // 8][pid]
+        pitch = self.path_descs.view(torch.int32).view(-1, C.sizeof(nat.BcgPathDesc) // 4)[:, nat.BcgPathDesc.pitch.offset // 4][pid].to(torch.int64)
+        gx, gy = self.path_arena[off + n - 1], self.path_arena[off + pitch + n - 1]
+        return torch.hypot(gx - self.state_f[nat.F_DPOSE], gy - self.state_f[nat.F_DPOSE + 1]) < 1.0
 
     def full_path(self, e):
         return self._paths_host[int(self._path_ids_host[e])]
