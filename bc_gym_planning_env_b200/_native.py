@@ -109,6 +109,7 @@ class BcgStepOut(C.Structure):
     _fields_ = [
         ("reward", C.c_void_p), ("done", C.c_void_p), ("hit", C.c_void_p),
         ("ego_image", C.c_void_p), ("goal_n_state", C.c_void_p), ("obs_vec", C.c_void_p),
+        ("ego_hits", C.c_void_p), ("ego_hit_count", C.c_void_p), ("ego_hit_cap", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -446,49 +446,59 @@ __device__ __forceinline__ bool collide_thread(const BcgFootprintLut& lut, const
         }
       }
     }
-#pragma unroll 1
-    for (int k = 0; k < MAXB; ++k) {
-      uint32_t m = tm[k];
-      if (m == 0u) continue;
-      const int ty = tyb + k;
-      const int dy0 = (ty << 4) - Y0;                      // mask row of the band's first tile row
-      const uint32_t* trow = tiles + (((int64_t)ty * tiles_x) << 4);
-      while (m) {
-        const int tx = tx0 + __ffs((int)m) - 1;
-        m &= m - 1u;
-        const uint4* tq = reinterpret_cast<const uint4*>(trow + (tx << 4));
-        const uint4 w0 = __ldg(tq), w1 = __ldg(tq + 1), w2 = __ldg(tq + 2), w3 = __ldg(tq + 3);
-        const uint32_t ws[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
-        const int rel = (tx << 5) - X0;
-        uint32_t hit = 0u;
-        if (wpr == 1 && pair_rows) {
-          // the band's 16 mask rows as nine aligned 16-byte pairs starting at the even row at or below dy0 (rows beyond
-          // the mask are zero in the table; pairs outside the bin's max_rows rows are not loaded)
-          const int base = dy0 & ~1, odd = dy0 & 1;
-          uint64_t v[18];
+    // Non-empty tiles of all bands as ONE per-thread list (4 bits per band: a 64-column mask spans <= 3 tiles), so that
+    // a warp iterates max-over-lanes(tiles of a lane) times, not sum-over-bands(max-over-lanes(tiles of the band)).
+    uint32_t todo = 0u;
+    const bool flat = (tx1 - tx0) < 4;
 #pragma unroll
-          for (int j = 0; j < 9; ++j) {
-            const int r0 = base + 2 * j;
-            ulonglong2 q = make_ulonglong2(0ull, 0ull);
-            if ((unsigned)r0 < (unsigned)lut.max_rows) q = __ldg(reinterpret_cast<const ulonglong2*>(rows + r0));
-            v[2 * j] = q.x;
-            v[2 * j + 1] = q.y;
-          }
+    for (int k = 0; k < MAXB; ++k) todo |= flat ? (tm[k] << (4 * k)) : 0u;
+    int kb = 0;                                            // wide footprints: band by band
+    while (flat ? (todo != 0u) : (kb < MAXB)) {
+      int k, j;
+      if (flat) {
+        const int bit = __ffs((int)todo) - 1;
+        todo &= todo - 1u;
+        k = bit >> 2;
+        j = bit & 3;
+      } else {
+        uint32_t mk = 0u;
 #pragma unroll
-          for (int r = 0; r < 16; ++r) hit |= ws[r] & mask_window32(odd ? v[r + 1] : v[r], rel);
-        } else if (wpr == 1) {
-          uint64_t mk[16];
+        for (int q = 0; q < MAXB; ++q) mk = (q == kb) ? tm[q] : mk;
+        if (mk == 0u) { ++kb; continue; }
+        k = kb;
+        j = __ffs((int)mk) - 1;
 #pragma unroll
-          for (int r = 0; r < 16; ++r) mk[r] = ((unsigned)(dy0 + r) < (unsigned)f.nrows) ? __ldg(rows + dy0 + r) : 0ull;
-#pragma unroll
-          for (int r = 0; r < 16; ++r) hit |= ws[r] & mask_window32(mk[r], rel);
-        } else {
-#pragma unroll 1
-          for (int r = 0; r < 16; ++r)
-            if (ws[r] != 0u && (unsigned)(dy0 + r) < (unsigned)f.nrows) hit |= ws[r] & mask_bits32(rows + (int64_t)(dy0 + r) * wpr, wpr, rel);
-        }
-        if (hit) return true;
+        for (int q = 0; q < MAXB; ++q) if (q == kb) tm[q] &= tm[q] - 1u;
       }
+      const int ty = tyb + k, tx = tx0 + j;
+      const int dy0 = (ty << 4) - Y0;                      // mask row of the band's first tile row
+      const uint4* tq = reinterpret_cast<const uint4*>(tiles + ((((int64_t)ty * tiles_x) + tx) << 4));
+      const uint4 w0 = __ldg(tq), w1 = __ldg(tq + 1), w2 = __ldg(tq + 2), w3 = __ldg(tq + 3);
+      const int rel = (tx << 5) - X0;
+      uint32_t hit = 0u;
+      if (wpr == 1 && pair_rows) {
+        // the band's 16 mask rows as nine aligned 16-byte pairs starting at the even row at or below dy0 (rows beyond
+        // the mask are zero in the table; pairs outside the bin's max_rows rows are not loaded)
+        const int base = dy0 & ~1, odd = dy0 & 1;
+        uint64_t v[18];
+#pragma unroll
+        for (int jj = 0; jj < 9; ++jj) {
+          const int r0 = base + 2 * jj;
+          ulonglong2 q = make_ulonglong2(0ull, 0ull);
+          if ((unsigned)r0 < (unsigned)lut.max_rows) q = __ldg(reinterpret_cast<const ulonglong2*>(rows + r0));
+          v[2 * jj] = q.x;
+          v[2 * jj + 1] = q.y;
+        }
+        const uint32_t ws[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+#pragma unroll
+        for (int r = 0; r < 16; ++r) hit |= ws[r] & mask_window32(odd ? v[r + 1] : v[r], rel);
+      } else {
+        const uint32_t ws[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+#pragma unroll
+        for (int r = 0; r < 16; ++r)                       // (unrolled: a dynamic index would put the tile words in local memory)
+          if (ws[r] != 0u && (unsigned)(dy0 + r) < (unsigned)f.nrows) hit |= ws[r] & mask_bits32(rows + (int64_t)(dy0 + r) * wpr, wpr, rel);
+      }
+      if (hit) return true;
     }
   }
   return false;
@@ -589,6 +599,98 @@ __device__ __forceinline__ int last_reached_from(const BcgParams& p, const PathR
     }
   }
   return -1;
+}
+
+// The same scan by a GROUP of G lanes (G = 8: four envs per warp; reward_kernel).  With a whole warp per env the ~370
+// straight-line instructions around the scan (record unpack, chunk test, reward, done, outputs) are paid per env; a group
+// of 8 lanes pays a quarter of that and tests a 32-point chunk in four rounds.  Lane gl of a group takes the gl-th highest
+// index of a round, so the lowest set ballot bit is the largest index.  Every loop is warp-uniform (exit when all groups
+// are done): the ballots are full-warp ballots, each group reads its own G bits.
+template <int G>
+__device__ __forceinline__ int last_reached_group(const BcgParams& p, const PathRef& pd, int lo, double px, double py,
+                                                  double pth, unsigned lane, bool active) {
+  const unsigned gl = lane & (G - 1), gbase = lane & ~(unsigned)(G - 1);
+  const uint32_t gmask = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
+  const double* __restrict__ P = pd.P;
+  const double* __restrict__ C = pd.C;
+  const double par_thr = -p.spatial_precision / 9;
+  const double sp2 = p.spatial_precision * p.spatial_precision;
+  bool done = !active || lo >= pd.n;
+  const int c_lo = lo >> 5;
+  int ctop = (pd.n - 1) >> 5;
+  int result = -1;
+  while (!__all_sync(BCG_FULL, done)) {
+    const int c = ctop - (int)gl;
+    bool near = false;
+    if (!done && c >= c_lo) {
+      const double cx = __ldg(C + c) - px, cy = __ldg(C + pd.chunk_pitch + c) - py;
+      const double reach = p.spatial_precision + __ldg(C + 2 * pd.chunk_pitch + c);
+      near = (cx * cx + cy * cy) < reach * reach * (1.0 + 1e-12);     // conservative: never drops a reachable chunk
+    }
+    uint32_t bits = (__ballot_sync(BCG_FULL, near) >> gbase) & gmask;   // bit j <-> chunk ctop - j
+    while (true) {
+      const bool has = !done && bits != 0u;
+      if (!__any_sync(BCG_FULL, has)) break;
+      int cc = 0;
+      if (has) {
+        cc = ctop - (__ffs((int)bits) - 1);
+        bits &= bits - 1u;
+      }
+#pragma unroll 1
+      for (int r = 0; r < 32 / G; ++r) {
+        const int i = (cc << 5) + 31 - r * G - (int)gl;
+        bool reached = false;
+        if (has && !done && i >= lo && i < pd.n) {
+          const double xi = __ldg(P + i), yi = __ldg(P + pd.pitch + i);
+          // hypot(dx, dy) < sp, decided from the squared distance unless it is within 1e-12 of the threshold
+          const double dx = xi - px, dy = yi - py, d2 = dx * dx + dy * dy;
+          bool close = d2 < sp2 * (1.0 - 1e-12);
+          if (!close && d2 <= sp2 * (1.0 + 1e-12)) close = hypot(dx, dy) < p.spatial_precision;
+          if (close) {
+            const double ti = __ldg(P + 2 * pd.pitch + i), ci = __ldg(P + 3 * pd.pitch + i), si = __ldg(P + 4 * pd.pitch + i);
+            const double ang = fabs(wrap_angle(pth - ti));
+            const double par = ci * (px - xi) + si * (py - yi);
+            reached = (ang < p.angular_precision) && (par >= par_thr);
+          }
+        }
+        const uint32_t rb = (__ballot_sync(BCG_FULL, reached) >> gbase) & gmask;
+        if (rb != 0u && !done) {
+          result = (cc << 5) + 31 - r * G - (__ffs((int)rb) - 1);
+          done = true;
+        }
+      }
+    }
+    ctop -= G;
+    if (ctop < c_lo) done = true;
+  }
+  return result;
+}
+
+// first_beyond_radius by a group of G lanes (see last_reached_group)
+template <int G>
+__device__ __forceinline__ int first_beyond_radius_group(const PathRef& pd, int lo, double px, double py, double radius,
+                                                         unsigned lane, bool active) {
+  const unsigned gl = lane & (G - 1), gbase = lane & ~(unsigned)(G - 1);
+  const uint32_t gmask = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
+  int base = max(lo, 0);
+  int result = pd.n - 1;
+  bool done = !active || base >= pd.n;
+  while (!__all_sync(BCG_FULL, done)) {
+    const int i = base + (int)gl;
+    bool far = false;
+    if (!done && i < pd.n) {
+      const double dx = __ldg(pd.P + i) - px, dy = __ldg(pd.P + pd.pitch + i) - py;
+      far = sqrt(fma(dy, dy, dx * dx)) > radius;        // np.linalg.norm of a 2-vector = sqrt(ddot), fused like the BLAS
+    }
+    const uint32_t bits = (__ballot_sync(BCG_FULL, far) >> gbase) & gmask;
+    if (!done && bits != 0u) {
+      result = base + __ffs((int)bits) - 1;
+      done = true;
+    }
+    base += G;
+    if (base >= pd.n) done = true;
+  }
+  return result;
 }
 
 // The same scan by ONE thread (state kernel): chunks from the far end down, culled by their bounding circles; the points of

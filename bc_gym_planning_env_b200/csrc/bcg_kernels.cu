@@ -760,8 +760,8 @@ __global__ void __launch_bounds__(BCG_COMMIT_THREADS, BCG_COMMIT_MIN_BLOCKS) com
 //                  (:377-389), time / iter / sticky collision (:383-393), the compact observation and the 128-byte
 //                  record of the egocentric kernel.  Every state access is a coalesced SoA row.  It leaves a 144-byte
 //                  StepRecord per env for
-//   reward_kernel  one WARP per env.  The one gather that wants a warp: find_last_reached (path_tools.py:408-448) over
-//                  the remaining path, lanes <-> points, chunk-culled; then lane 0 finishes the step: reward
+//   reward_kernel  eight LANES per env.  The one gather that wants lanes: find_last_reached (path_tools.py:408-448) over
+//                  the remaining path, lanes <-> points, chunk-culled; then the group's first lane finishes the step: reward
 //                  (reward.py:214-259 / :331-350), done (env.py:407-419), episode statistics, goal_n_state
 //                  (egocentric.py:152-159; the pose's inverse transform comes precomputed in the record), and the rare
 //                  auto-reset (env.py:293-303), which rewrites the env's rows and its egocentric record from the
@@ -801,7 +801,7 @@ static_assert(offsetof(StepRecord, path_off) == 80 && offsetof(StepRecord, chunk
 #define BCG_REWARD_THREADS 64
 #endif
 #ifndef BCG_REWARD_RESIDENT
-#define BCG_REWARD_RESIDENT 1280      // threads per SM the reward kernel is compiled for (register budget 48)
+#define BCG_REWARD_RESIDENT 1024      // threads per SM the reward kernel is compiled for (register budget 64)
 #endif
 
 // the inverse transform of pose (px, py, pth), as write_goal_n_state evaluates it
@@ -986,13 +986,15 @@ move_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L, const v
   reinterpret_cast<float2*>(dst + 128)[0] = make_float2(rec.drobot[4], rec.drobot[5]);
 }
 
-// auto-reset of env e (env.py:293-303) by its warp: the rows, the observation and the egocentric record of the initial state
+// auto-reset of env e (env.py:293-303) by its lane group: the rows, the observation and the egocentric record of the
+// initial state
+template <int G>
 __device__ __forceinline__ void reset_env_rows(const BcgParams& p, const BcgBatch& b, const BcgStepOut& out, int e, int ego_cap,
-                                            unsigned lane) {
+                                               unsigned gl) {
   const int64_t N = b.n_envs;
-  for (int r = lane; r < b.n_frows; r += 32) b.state_f[(int64_t)r * N + e] = b.init_f[(int64_t)r * N + e];
-  for (int r = lane; r < b.n_irows; r += 32) b.state_i[(int64_t)r * N + e] = b.init_i[(int64_t)r * N + e];
-  if (lane != 0) return;
+  for (int r = gl; r < b.n_frows; r += G) b.state_f[(int64_t)r * N + e] = b.init_f[(int64_t)r * N + e];
+  for (int r = gl; r < b.n_irows; r += G) b.state_i[(int64_t)r * N + e] = b.init_i[(int64_t)r * N + e];
+  if (gl != 0) return;
   double dpose[3], dstate[7], c[3];
 #pragma unroll
   for (int r = 0; r < 3; ++r) dpose[r] = b.init_f[(int64_t)(BCG_F_DPOSE + r) * N + e];
@@ -1018,14 +1020,19 @@ __device__ __forceinline__ void reset_env_rows(const BcgParams& p, const BcgBatc
   }
 }
 
+#ifndef BCG_REWARD_LANES
+#define BCG_REWARD_LANES 8            // lanes per env (power of two, 1 < G <= 32): 32 / G envs per warp
+#endif
 __global__ void __launch_bounds__(BCG_REWARD_THREADS, BCG_REWARD_RESIDENT / BCG_REWARD_THREADS)
 reward_kernel(const BcgParams p, const BcgBatch b, const BcgStepOut out, const int ego_cap) {
-  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const unsigned lane = threadIdx.x & 31;
-  if (e < b.n_envs) {
-    const int64_t N = b.n_envs;
-    // the env's record: a warp-uniform 144-byte read
-    const StepRecord rec = *reinterpret_cast<const StepRecord*>(reinterpret_cast<const uint8_t*>(b.work) + (int64_t)e * BCG_WORK_BYTES);
+  constexpr int G = BCG_REWARD_LANES;
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const unsigned lane = threadIdx.x & 31, gl = lane & (G - 1);
+  const bool active = e < b.n_envs;
+  const int64_t N = b.n_envs;
+  {
+    // the env's record: a group-uniform 144-byte read (env 0's for the idle groups of the last warp)
+    const StepRecord rec = *reinterpret_cast<const StepRecord*>(reinterpret_cast<const uint8_t*>(b.work) + (int64_t)(active ? e : 0) * BCG_WORK_BYTES);
     PathRef pd;
     pd.P = b.path_arena + rec.path_off;
     pd.C = pd.P + 5 * (int64_t)rec.path_pitch;
@@ -1036,7 +1043,6 @@ reward_kernel(const BcgParams p, const BcgBatch b, const BcgStepOut out, const i
     double min_dist = rec.min_dist;
     const bool pursuit = p.reward_kind == BCG_REWARD_PURE_PURSUIT;
     const bool goal_before = (rec.flags & BCG_SR_GOAL_BEFORE) != 0;
-    const bool hit = (rec.flags & BCG_SR_HIT) != 0;
     // issued before the scan needs them: the goal point the reward most likely uses
     double gx = 0.0, gy = 0.0;
     if (pursuit || !goal_before) {
@@ -1048,7 +1054,7 @@ reward_kernel(const BcgParams p, const BcgBatch b, const BcgStepOut out, const i
     bool goal;
     if (pursuit) {
       // ContinuousRewardPurePursuitProvider.reward (reward.py:331-350)
-      target = first_beyond_radius(pd, target, rec.pose[0], rec.pose[1], 2.0, lane);
+      target = first_beyond_radius_group<G>(pd, target, rec.pose[0], rec.pose[1], 2.0, lane, active);
       const double d = hypot(gx - rec.pose[0], gy - rec.pose[1]);
       reward = -0.05;
       reward += min_dist - d;
@@ -1056,8 +1062,9 @@ reward_kernel(const BcgParams p, const BcgBatch b, const BcgStepOut out, const i
       min_dist = d;
       goal = d < 1.0;
     } else {
+      // (every group of the warp calls the scan: its loops and ballots are warp-uniform)
+      const int last = last_reached_group<G>(p, pd, target, rec.pose[0], rec.pose[1], rec.pose[2], lane, active && !goal_before);
       if (!goal_before) {
-        const int last = last_reached_from(p, pd, target, rec.pose[0], rec.pose[1], rec.pose[2], lane);
         if (last >= target) {
           target = last + 1;
           if (target > pd.n - 1) {
@@ -1080,7 +1087,7 @@ reward_kernel(const BcgParams p, const BcgBatch b, const BcgStepOut out, const i
     const bool timed_out = (rec.flags & BCG_SR_TIMED_OUT) != 0, collided_after = (rec.flags & BCG_SR_COLLIDED_AFTER) != 0;
     const bool done = goal || timed_out || collided_after;
     const double ep_return = rec.ep_return + reward;
-    if (lane == 0) {
+    if (active && gl == 0) {
       if (out.reward) out.reward[e] = reward;
       if (out.done) out.done[e] = done ? 1 : 0;
       if (done && !(rec.flags & BCG_SR_DONE_BEFORE)) {
@@ -1092,9 +1099,9 @@ reward_kernel(const BcgParams p, const BcgBatch b, const BcgStepOut out, const i
         if (timed_out) atomicAdd(b.stats + BCG_STAT_TIMEOUT, 1.0);
       }
     }
-    if (done && p.auto_reset) {
-      reset_env_rows(p, b, out, e, ego_cap, lane);
-    } else if (lane == 0) {
+    if (active && done && p.auto_reset) {
+      reset_env_rows<G>(p, b, out, e, ego_cap, gl);
+    } else if (active && gl == 0) {
       b.state_f[BCG_F_MIN_DIST * N + e] = min_dist;
       b.state_f[BCG_F_EP_RETURN * N + e] = ep_return;
       b.state_i[BCG_I_TARGET * N + e] = target;
@@ -1961,12 +1968,15 @@ __global__ void __launch_bounds__(BCG_EGT_THREADS, BCG_EGT_CTAS) ego_tiles_kerne
 #define BCG_EGS_DYNAMIC 1            // 1: envs beyond a CTA's first four are drawn from a global counter
 #endif
 #define BCG_EGS_QCAP 64              // ring slots per warp: a push adds <= 32 to <= 31 left over
+#ifndef BCG_EGS_SPANS
+#define BCG_EGS_SPANS 1              // clip the listed cells to the tile spans of the rotated crop (0: to its bounding box)
+#endif
 // The fixed-point tables of the crop live in dynamic shared memory, sized by the crop: adxy[ego_w] = (rint(a11 u 2^10),
 // rint(a21 u 2^10)), then bxy[ego_h] = rint((a12 v + b1) 2^10) + 512 - (X0 << 10), same for y (2 KB for a 117 x 133 crop)
 struct EgoSparseTab {
   uint32_t list[BCG_EGS_LIST];                  // occupied window cells: y_rel << 16 | x_rel
   uint32_t count[2];
-  uint32_t pad[2];
+  uint32_t hits[2];                             // compact output: non-zero crop pixels recorded so far (same parity scheme)
 };
 
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
@@ -1999,7 +2009,10 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 template <bool SUM>
 __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kernel(const BcgParams p, const BcgBatch b,
-                                                                                   uint8_t* __restrict__ image) {
+                                                                                   uint8_t* __restrict__ image,
+                                                                                   uint32_t* __restrict__ hit_list,
+                                                                                   int32_t* __restrict__ hit_count,
+                                                                                   const int hit_cap) {
   __shared__ __align__(128) uint8_t zero_s[BCG_EGS_ZERO_BYTES];
   __shared__ __align__(16) EgoSparseTab T;
   __shared__ __align__(128) uint8_t rec_s[BCG_EGS_REC_SLOTS * BCG_EGO_WORK_BYTES];
@@ -2043,7 +2056,7 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
   for (int k = 0; k < RD; ++k) fetch_record(e0 + k * G, k);
   cp_async_commit();
   for (int i = tid * 16; i < BCG_EGS_ZERO_BYTES; i += NT * 16) *reinterpret_cast<uint4*>(zero_s + i) = make_uint4(0u, 0u, 0u, 0u);
-  if (tid < 2) T.count[tid] = 0;
+  if (tid < 2) T.count[tid] = T.hits[tid] = 0;
 #if BCG_EGS_DYNAMIC
   // Which envs a CTA renders: its first RD + 1 are blockIdx.x + k G; the later ones come from a global counter
   // (ego_list[n + 1], zeroed with the hand-over count), drawn RD + 1 iterations ahead so that the record can be
@@ -2058,7 +2071,7 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
   // tile spans of the window rows (ego_band_span), lane <-> tile row, computed by the last warp one env ahead of their use
   __shared__ uint16_t span_s[2][BCG_EGT_MAX_TILE_ROWS];
   auto make_spans = [&](int slot, int buf) {
-    if (warp != NT / 32 - 1) return;
+    if (!BCG_EGS_SPANS || warp != NT / 32 - 1) return;
     const EgoTileWork* q = reinterpret_cast<const EgoTileWork*>(rec_s + slot * BCG_EGO_WORK_BYTES);
     if (q->mode != BCG_EGO_MODE_TILES || (q->dense_map & 1)) return;
     for (int t = lane; t < q->nty; t += 32)
@@ -2156,7 +2169,11 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
         uint32_t bits[4] = {wd.x, wd.y, wd.z, wd.w};
         uint32_t keep = 0u;
         if (yr0 >= 0 && yr0 < 8 * nty) {                                          // clip to the tile span of these rows
+#if BCG_EGS_SPANS
           const uint32_t sp = lds_u16(span_u32 + 2 * (yr0 >> 3));
+#else
+          const uint32_t sp = (uint32_t)(ntx - 1) << 8;                          // experiment: the window's bounding box only
+#endif
           const int lo = max(X0 + 16 * (int)(sp & 0xff) - (tx << 5), 0);
           const int hi = min(X0 + 16 * (int)(sp >> 8) + 15 - (tx << 5), 31);
           if (lo <= hi) keep = (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
@@ -2324,6 +2341,20 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
 #ifdef BCG_EGS_EXP_NO_HITS
         }
 #endif
+        if (hit_list) {
+          // compact observation (BcgStepOut.ego_hits): pixel offset | value << 16 of every non-zero crop pixel.  A crop
+          // pixel samples exactly one cell, so the entries of an env are distinct.
+          const int nh = (int)h00 + (int)h10 + (int)h01 + (int)h11;
+          if (nh) {
+            uint32_t at = atomicAdd(&T.hits[par], (uint32_t)nh);
+            uint32_t* const out = hit_list + (int64_t)e * hit_cap;
+            const uint32_t tagged = (uint32_t)val << 16;
+            if (h00) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(v0 * ego_w + u0); ++at; }
+            if (h10) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(v0 * ego_w + u1); ++at; }
+            if (h01) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(v1 * ego_w + u0); ++at; }
+            if (h11) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(v1 * ego_w + u1); ++at; }
+          }
+        }
       }
     } else if (b.flags & BCG_BATCH_SPARSE_EGO_ONLY) {
       // No dense pass follows this kernel (the host knows that no map of the batch is dense): the rare window that
@@ -2354,6 +2385,12 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
       b.ego_list[at] = e;
     }
     if (tid == 0) T.count[par ^ 1] = 0;         // nobody reads the other counter before the next barrier
+    if (hit_count) {                            // (the hit counter of this env is complete after the barrier below)
+      if (!sparse && tid == 0) hit_count[e] = -1;       // rendered densely: the consumer reads the image itself
+      __syncthreads();
+      if (sparse && tid == 0) hit_count[e] = (int32_t)T.hits[par];      // > hit_cap: the list overflowed, read the image
+      if (tid == 0) T.hits[par ^ 1] = 0;
+    }
 #if BCG_EGS_DYNAMIC
     if (tid == 0) ids_s[(it + RD + 1) & 7] = drawn;
 #endif
@@ -2661,7 +2698,13 @@ static int launch_ego_dense(const BcgParams* p, const BcgBatch* b, uint8_t* ego_
 }
 
 // sparse scatter kernel for every env, then the dense kernel for the envs it handed over (usually none)
-static int launch_ego_sparse(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, cudaStream_t s) {
+struct EgoHits {       // BcgStepOut.ego_hits / ego_hit_count / ego_hit_cap (all zero: no compact output)
+  uint32_t* list;
+  int32_t* count;
+  int cap;
+};
+
+static int launch_ego_sparse(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, const EgoHits& hits, cudaStream_t s) {
   int sms = 0;
   if (int rc = sm_count_of_current_device(&sms)) return rc;
   // (the hand-over count and the env counter in ego_list[n_envs ..] were zeroed by the state / prep kernel)
@@ -2684,8 +2727,8 @@ static int launch_ego_sparse(const BcgParams* p, const BcgBatch* b, uint8_t* ego
     }
   }
   const int grid = b->n_envs < per_sm * sms ? b->n_envs : per_sm * sms;
-  if (sum) ego_sparse_kernel<true><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image);
-  else ego_sparse_kernel<false><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image);
+  if (sum) ego_sparse_kernel<true><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image, hits.list, hits.count, hits.cap);
+  else ego_sparse_kernel<false><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image, hits.list, hits.count, hits.cap);
   BCG_CHECK_CUDA(cudaGetLastError());
   if (b->flags & BCG_BATCH_SPARSE_EGO_ONLY) return BCG_OK;     // the sparse kernel rendered every env itself
   return launch_ego_dense(p, b, ego_image, b->ego_list, s);
@@ -2710,11 +2753,13 @@ static bool ego_dense_kernel_requested() {
 }
 
 // the image kernel(s); the per-env records must already be in b->ego_work
-static int launch_ego_image(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, cudaStream_t s) {
+static int launch_ego_image(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, const EgoHits& hits, cudaStream_t s) {
   if (b->cell_tile_arena) {
-    if (b->occ_tile_arena && b->ego_list && !ego_dense_kernel_requested()) return launch_ego_sparse(p, b, ego_image, s);
+    if (b->occ_tile_arena && b->ego_list && !ego_dense_kernel_requested()) return launch_ego_sparse(p, b, ego_image, hits, s);
+    BCG_REQUIRE(!hits.list, "the compact egocentric output (BcgStepOut.ego_hits) comes from the sparse kernel: ego_list is needed");
     return launch_ego_dense(p, b, ego_image, nullptr, s);
   }
+  BCG_REQUIRE(!hits.list, "the compact egocentric output (BcgStepOut.ego_hits) needs the cell-tile / occupancy planes");
   const int cap = ego_tile_capacity(*p, *b);
   // alignment slack + the per-row spans of the plain-load path, which live behind the tile
   const int extra = 128 + BCG_EGO_MAX_TILE_ROWS * (int)sizeof(short2);
@@ -2733,7 +2778,7 @@ int bcg_observe_ego(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, f
   ego_prep_kernel<<<blocks_for(b->n_envs, 128), 128, 0, s>>>(*p, *b, ego_image ? 1 : 0, goal_n_state,
                                                             ego_capacity(*p, *b));
   BCG_CHECK_CUDA(cudaGetLastError());
-  if (ego_image) return launch_ego_image(p, b, ego_image, s);
+  if (ego_image) return launch_ego_image(p, b, ego_image, EgoHits{nullptr, nullptr, 0}, s);
   return BCG_OK;
 }
 
@@ -2766,12 +2811,14 @@ int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, 
                                                                                     *out, cap);
     BCG_CHECK_CUDA(cudaGetLastError());
     if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[2], s));
-    reward_kernel<<<blocks_for((int64_t)b->n_envs * 32, BCG_REWARD_THREADS), BCG_REWARD_THREADS, 0, s>>>(*p, *b, *out, cap);
+    reward_kernel<<<blocks_for((int64_t)b->n_envs * BCG_REWARD_LANES, BCG_REWARD_THREADS), BCG_REWARD_THREADS, 0, s>>>(*p, *b, *out, cap);
     BCG_CHECK_CUDA(cudaGetLastError());
   }
   if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[3], s));
   if (out->ego_image) {
-    if (int rc = launch_ego_image(p, b, out->ego_image, s)) return rc;
+    BCG_REQUIRE((out->ego_hits != nullptr) == (out->ego_hit_count != nullptr) && (!out->ego_hits || out->ego_hit_cap > 0),
+                "ego_hits, ego_hit_count and ego_hit_cap go together");
+    if (int rc = launch_ego_image(p, b, out->ego_image, EgoHits{out->ego_hits, out->ego_hit_count, out->ego_hit_cap}, s)) return rc;
   }
   if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[4], s));
   return BCG_OK;

@@ -453,6 +453,15 @@ class VecPlanEnv(object):
         self._step_index += 1
         return self.observation(), self.reward, self.done, {}
 
+    def launches_per_step(self):
+        """Kernels one `step` launches: move + reward (three with BCG_STEP_KERNELS=split), then the egocentric kernel(s)."""
+        n = 3 if os.environ.get("BCG_STEP_KERNELS") == "split" else 2
+        if not self.with_ego:
+            return n
+        if self._ego_list is None or os.environ.get("BCG_EGO_KERNEL") == "dense":
+            return n + 1                                   # one dense kernel
+        return n + (1 if self._batch.flags & nat.BATCH_SPARSE_EGO_ONLY else 2)
+
     def step_timed(self, actions, events):
         """`step` with five torch.cuda.Event (enable_timing=True, already recorded once so that their
         handles exist) recorded around the four kernels; see bcg_step_events."""

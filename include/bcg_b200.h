@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BCG_ABI_VERSION 6
+#define BCG_ABI_VERSION 7
 
 /* error codes */
 #define BCG_OK 0
@@ -272,6 +272,15 @@ typedef struct BcgStepOut {
   uint8_t* ego_image;  /* [n][ego_h][ego_w] egocentric crop (egocentric.py:125-160 'env')        */
   float* goal_n_state; /* [n][9] egocentric.py:152-159                                          */
   float* obs_vec;      /* [n][12] fp32 copy of delayed pose(3), delayed robot state(7), time, target_idx */
+  /* compact form of ego_image for consumers behind a narrow link (optional; needs ego_image and the sparse kernel): per
+   * env the list of its non-zero crop pixels, entry = pixel offset (v * ego_w + u) | cost value << 16, in no particular
+   * order.  ego_hit_count[e] = number of entries (only the first ego_hit_cap are stored: a larger count means "read
+   * ego_image[e]"), or -1 when the env was rendered by the dense kernel.  A crop is ~1 % walls, so this is ~0.8 KB per
+   * env instead of 15.6 KB. */
+  uint32_t* ego_hits;      /* [n][ego_hit_cap] */
+  int32_t* ego_hit_count;  /* [n]              */
+  int32_t ego_hit_cap;
+  int32_t reserved;
 } BcgStepOut;
 
 /* -- library ------------------------------------------------------------------------------------ */

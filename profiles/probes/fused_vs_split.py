@@ -123,5 +123,17 @@ def times():
     print(json.dumps({"mode": os.environ.get("BCG_STEP_KERNELS", "fused"), "times": res}))
 
 
+def profile():
+    """a short run for ncu: python profiles/probes/fused_vs_split.py profile [--envs N] [--steps K]"""
+    import torch
+    n, steps = arg("--envs", 65536), arg("--steps", 12)
+    env, actions = make_env(n)
+    for k in range(steps):
+        env.step(actions[k % 16])
+    torch.cuda.synchronize()
+    env.check_status()
+    print("profiled run done")
+
+
 if __name__ == "__main__":
-    {"run": run, "compare": compare, "times": times}[sys.argv[1]]()
+    {"run": run, "compare": compare, "times": times, "profile": profile}[sys.argv[1]]()
