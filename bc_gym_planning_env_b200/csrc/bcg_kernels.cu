@@ -2007,7 +2007,7 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <bool SUM>
+template <bool SUM, bool HITS>
 __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kernel(const BcgParams p, const BcgBatch b,
                                                                                    uint8_t* __restrict__ image,
                                                                                    uint32_t* __restrict__ hit_list,
@@ -2341,7 +2341,7 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
 #ifdef BCG_EGS_EXP_NO_HITS
         }
 #endif
-        if (hit_list) {
+        if (HITS) {
           // compact observation (BcgStepOut.ego_hits): pixel offset | value << 16 of every non-zero crop pixel.  A crop
           // pixel samples exactly one cell, so the entries of an env are distinct.
           const int nh = (int)h00 + (int)h10 + (int)h01 + (int)h11;
@@ -2385,7 +2385,7 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
       b.ego_list[at] = e;
     }
     if (tid == 0) T.count[par ^ 1] = 0;         // nobody reads the other counter before the next barrier
-    if (hit_count) {                            // (the hit counter of this env is complete after the barrier below)
+    if (HITS) {                                 // (the hit counter of this env is complete after the barrier below)
       if (!sparse && tid == 0) hit_count[e] = -1;       // rendered densely: the consumer reads the image itself
       __syncthreads();
       if (sparse && tid == 0) hit_count[e] = (int32_t)T.hits[par];      // > hit_cap: the list overflowed, read the image
@@ -2443,6 +2443,20 @@ __global__ void __launch_bounds__(256) scatter_kernel(const BcgBatch b, const in
     b.state_f[(int64_t)r * N + e] = in_f[(int64_t)src * k + j];
   }
   for (int r = 0; r < b.n_irows; ++r) b.state_i[(int64_t)r * N + e] = in_i[(int64_t)r * k + j];
+}
+
+// ego_hits lists of all envs, fixed stride -> one contiguous array (offsets: exclusive prefix sum of the clamped counts);
+// eight lanes per env
+__global__ void __launch_bounds__(256) pack_hits_kernel(const uint32_t* __restrict__ hits, const int32_t* __restrict__ counts,
+                                                        const int cap, const int n, const int64_t* __restrict__ offsets,
+                                                        uint32_t* __restrict__ packed) {
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, gl = threadIdx.x & 7;
+  if (e >= n) return;
+  const int c = counts[e];
+  if (c <= 0 || c > cap) return;                 // rendered densely / list overflowed: the consumer reads the image
+  const uint32_t* src = hits + (int64_t)e * cap;
+  uint32_t* dst = packed + offsets[e];
+  for (int i = gl; i < c; i += 8) dst[i] = src[i];
 }
 
 __global__ void w2p_kernel(const double* __restrict__ xy, const int64_t n, const double ox, const double oy,
@@ -2718,8 +2732,8 @@ static int launch_ego_sparse(const BcgParams* p, const BcgBatch* b, uint8_t* ego
   if (dev >= 0 && dev < 64 && per_sm_cache[sum][dev] > 0 && tab_cache[sum][dev] == tab_bytes) {
     per_sm = per_sm_cache[sum][dev];
   } else {
-    if (sum) BCG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ego_sparse_kernel<true>, BCG_EGS_THREADS, tab_bytes));
-    else BCG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ego_sparse_kernel<false>, BCG_EGS_THREADS, tab_bytes));
+    if (sum) BCG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ego_sparse_kernel<true, false>, BCG_EGS_THREADS, tab_bytes));
+    else BCG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ego_sparse_kernel<false, false>, BCG_EGS_THREADS, tab_bytes));
     BCG_REQUIRE(per_sm > 0, "the sparse egocentric kernel does not fit an SM with this crop size");
     if (dev >= 0 && dev < 64) {
       per_sm_cache[sum][dev] = per_sm;
@@ -2727,8 +2741,14 @@ static int launch_ego_sparse(const BcgParams* p, const BcgBatch* b, uint8_t* ego
     }
   }
   const int grid = b->n_envs < per_sm * sms ? b->n_envs : per_sm * sms;
-  if (sum) ego_sparse_kernel<true><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image, hits.list, hits.count, hits.cap);
-  else ego_sparse_kernel<false><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image, hits.list, hits.count, hits.cap);
+  // (the variant that also records the compact hit lists has the same shared-memory footprint and register budget)
+  if (hits.list) {
+    if (sum) ego_sparse_kernel<true, true><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image, hits.list, hits.count, hits.cap);
+    else ego_sparse_kernel<false, true><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image, hits.list, hits.count, hits.cap);
+  } else {
+    if (sum) ego_sparse_kernel<true, false><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image, nullptr, nullptr, 0);
+    else ego_sparse_kernel<false, false><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image, nullptr, nullptr, 0);
+  }
   BCG_CHECK_CUDA(cudaGetLastError());
   if (b->flags & BCG_BATCH_SPARSE_EGO_ONLY) return BCG_OK;     // the sparse kernel rendered every env itself
   return launch_ego_dense(p, b, ego_image, b->ego_list, s);
@@ -2878,6 +2898,15 @@ int bcg_scatter_state(const BcgBatch* b, const int64_t* idx, int32_t k, const do
   BCG_REQUIRE(b && idx && in_f && in_i && k >= 0, "bad scatter arguments");
   if (k == 0) return BCG_OK;
   scatter_kernel<<<blocks_for(k, 256), 256, 0, (cudaStream_t)stream>>>(*b, idx, k, in_f, in_i, load_delayed_robot);
+  BCG_CHECK_CUDA(cudaGetLastError());
+  return BCG_OK;
+}
+
+int bcg_pack_ego_hits(const uint32_t* hits, const int32_t* counts, int32_t cap, int32_t n, const int64_t* offsets,
+                      uint32_t* packed, void* stream) {
+  BCG_REQUIRE(hits && counts && offsets && packed && cap > 0 && n >= 0, "bad pack arguments");
+  if (n == 0) return BCG_OK;
+  pack_hits_kernel<<<blocks_for((int64_t)n * 8, 256), 256, 0, (cudaStream_t)stream>>>(hits, counts, cap, n, offsets, packed);
   BCG_CHECK_CUDA(cudaGetLastError());
   return BCG_OK;
 }

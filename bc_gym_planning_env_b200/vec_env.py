@@ -85,7 +85,7 @@ class VecPlanEnv(object):
     def __init__(self, costmaps, paths, params=None, n_envs=None, map_ids=None, path_ids=None,
                  noise_parameters=DEFAULT_NOISE, seed=0, auto_reset=False, device=None, env_id_base=0,
                  private_map_copies=False, with_ego=False, footprint_scale=1.0, use_tma=True, footprint=None,
-                 ego_staging='tiles', ego_sparse=True):
+                 ego_staging='tiles', ego_sparse=True, compact_ego=False):
         """
         :param costmaps: pool of CostMap2D (uint8), one resolution
         :param paths: pool of oriented paths, array(n, 3); refined here when params.refine_path
@@ -99,6 +99,8 @@ class VecPlanEnv(object):
         :param ego_staging: how the egocentric kernel stages its source window: 'tiles' (default; a derived
             copy of every costmap in 128-byte cell tiles, only the tiles the rotated window touches are read),
             'tma' (box loads of the window's bounding box from the uint8 rows) or 'spans' (plain loads)
+        :param compact_ego: also keep, per env, the list of non-zero crop pixels (BcgStepOut.ego_hits): what
+            `step_host(images='compact')` sends to the host instead of whole crops (needs with_ego and the sparse kernel)
         :param ego_sparse: with 'tiles' staging, render crops with the sparse scatter kernel (occupancy plane; the dense
             cell-tile kernel only takes the envs it hands over).  False: the dense kernel renders every env
         """
@@ -111,6 +113,7 @@ class VecPlanEnv(object):
         # library's dense threshold (1 cell in 20 occupied) it would only hand every env over: leave it out
         self._ego_sparse = bool(ego_sparse) and not all(
             np.count_nonzero(c.get_data()) * 20 > c.get_data().size for c in costmaps)
+        self._compact_ego = bool(compact_ego)
         self._configure(params, n, float(costmaps[0].get_resolution()), noise_parameters, seed, auto_reset, device,
                         env_id_base, with_ego, ego_staging if use_tma else 'spans')   # use_tma=False: older spelling
         self._map_pool = costmaps
@@ -382,6 +385,14 @@ class VecPlanEnv(object):
         out.obs_vec = self.obs_vec.data_ptr()
         if self.with_ego:
             out.ego_image, out.goal_n_state = self.ego_image.data_ptr(), self.goal_n_state.data_ptr()
+        self._ego_hits = self._ego_hit_count = None
+        if getattr(self, '_compact_ego', False):
+            if not self.with_ego or self._ego_list is None:
+                raise ValueError("compact_ego needs with_ego=True and the sparse egocentric kernel (ego_staging='tiles', sparse maps)")
+            self.EGO_HIT_CAP = 1024
+            self._ego_hits = torch.zeros((self.n_envs, self.EGO_HIT_CAP), dtype=torch.int32, device=self.device)
+            self._ego_hit_count = torch.zeros(self.n_envs, dtype=torch.int32, device=self.device)
+            out.ego_hits, out.ego_hit_count, out.ego_hit_cap = self._ego_hits.data_ptr(), self._ego_hit_count.data_ptr(), self.EGO_HIT_CAP
         self._out = out
 
     def _stream(self):
@@ -506,6 +517,10 @@ class VecPlanEnv(object):
             io['reward'].copy_(self.reward, non_blocking=True)
             io['done'].copy_(self._done_u8, non_blocking=True)
             io['obs'].copy_(self.obs_vec, non_blocking=True)
+        compact = None
+        if images == 'compact':
+            compact = self._compact_to_host(io, side)
+            images = False
         if images:
             if self.ego_image is None:
                 raise ValueError("this batch was built without the egocentric observation (with_ego=False)")
@@ -516,9 +531,62 @@ class VecPlanEnv(object):
             io['goal_n_state'].copy_(self.goal_n_state, non_blocking=True)
         side.synchronize()
         main.synchronize()
+        if compact is not None:
+            return io['reward'], io['done'], io['obs'], compact, io['goal_n_state']
         if images:
             return io['reward'], io['done'], io['obs'], io['ego_image'], io['goal_n_state']
         return io['reward'], io['done'], io['obs']
+
+    def _compact_to_host(self, io, side):
+        """The egocentric observation of the step just launched as per-env lists of non-zero pixels, packed on the
+        device and copied to pinned host memory: dict(counts int32 [N] (-1 / > cap: see dense_envs), offsets int64 [N],
+        packed uint32 [total] (pixel offset | value << 16), dense_envs int64 [k], dense_images uint8 [k, H, W],
+        bytes = bytes that crossed the link for the images).  Expand with `expand_compact`."""
+        if self._ego_hits is None:
+            raise ValueError("this batch was built without compact_ego=True")
+        n, cap = self.n_envs, self.EGO_HIT_CAP
+        counts = self._ego_hit_count
+        listed = (counts > 0) & (counts <= cap)
+        c = torch.where(listed, counts, torch.zeros_like(counts)).to(torch.int64)
+        ends = torch.cumsum(c, 0)
+        offsets = (ends - c).contiguous()
+        dense = torch.nonzero((counts < 0) | (counts > cap)).reshape(-1)
+        total = int(ends[-1])                                    # (synchronises: the size of the copy is data)
+        if 'packed_dev' not in io or io['packed_dev'].numel() < total:
+            size = max(total * 5 // 4, n * 64)
+            io['packed_dev'] = torch.empty(size, dtype=torch.int32, device=self.device)
+            io['packed'] = torch.empty(size, dtype=torch.int32).pin_memory()
+            io['counts'] = torch.empty(n, dtype=torch.int32).pin_memory()
+            io['offsets'] = torch.empty(n, dtype=torch.int64).pin_memory()
+            io['goal_n_state'] = torch.empty(tuple(self.goal_n_state.shape), dtype=torch.float32).pin_memory()
+        nat.check(nat.lib().bcg_pack_ego_hits(nat.ptr(self._ego_hits), nat.ptr(counts), cap, n, nat.ptr(offsets),
+                                              nat.ptr(io['packed_dev']), self._stream()))
+        io['packed'][:total].copy_(io['packed_dev'][:total], non_blocking=True)
+        io['counts'].copy_(counts, non_blocking=True)
+        io['offsets'].copy_(offsets, non_blocking=True)
+        io['goal_n_state'].copy_(self.goal_n_state, non_blocking=True)
+        dense_images = None
+        if dense.numel():
+            dense_images = self.ego_image[dense].reshape(dense.numel(), self.ego_image.shape[1], self.ego_image.shape[2]).cpu()
+        return dict(counts=io['counts'], offsets=io['offsets'], packed=io['packed'][:total], dense_envs=dense.cpu(),
+                    dense_images=dense_images, cap=cap,
+                    bytes=total * 4 + n * 12 + (0 if dense_images is None else dense_images.numel()))
+
+    @staticmethod
+    def expand_compact(compact, height, width):
+        """Host-side expander of `step_host(images='compact')`: uint8 [N, H, W] equal to `ego_image` byte for byte."""
+        counts = compact['counts'].numpy()
+        n = len(counts)
+        out = np.zeros((n, height * width), dtype=np.uint8)
+        listed = (counts > 0) & (counts <= compact['cap'])
+        c = np.where(listed, counts, 0).astype(np.int64)
+        env = np.repeat(np.arange(n), c)
+        words = compact['packed'].numpy().view(np.uint32)
+        out[env, words & 0xffff] = (words >> 16).astype(np.uint8)
+        out = out.reshape(n, height, width)
+        if compact['dense_images'] is not None:
+            out[compact['dense_envs'].numpy()] = compact['dense_images'].numpy()
+        return out
 
     def reset(self, mask=None):
         """PlanEnv.reset for all envs (mask None) or those with mask[e] true."""

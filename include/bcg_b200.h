@@ -385,6 +385,14 @@ int bcg_gather_state(const BcgBatch* b, const int64_t* idx, int32_t k, double* o
 int bcg_scatter_state(const BcgBatch* b, const int64_t* idx, int32_t k, const double* in_f,
                       const int32_t* in_i, int32_t load_delayed_robot, void* stream);
 
+/* -- compact observation ------------------------------------------------------------------------------ */
+/* Packs the per-env hit lists a step left in BcgStepOut.ego_hits (fixed stride `cap`) into one contiguous array:
+ * env e's min(count, cap) entries go to packed[offsets[e] ..], offsets = exclusive prefix sum of the counts with
+ * dense / overflowed envs (count < 0 or > cap) counted as 0 -- what a host consumer copies over the link instead
+ * of n crops of ego_w x ego_h bytes. */
+int bcg_pack_ego_hits(const uint32_t* hits, const int32_t* counts, int32_t cap, int32_t n, const int64_t* offsets,
+                      uint32_t* packed, void* stream);
+
 /* -- hook-seam helpers (batched forms of the brain.shining_utils.* scalars) --------------------- */
 /* world_to_pixel (coordinate_transformations.py:185-205): xy [n][2] fp64 -> int32 [n][2] */
 int bcg_world_to_pixel(const double* xy, int64_t n, double origin_x, double origin_y,

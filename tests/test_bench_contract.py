@@ -28,7 +28,9 @@ def test_reference_arm_prints_the_contract_line():
     assert d["dtype"] == "f64" and d["data"] == "synthetic" and "AisleTurnEnv" in d["config"]["workload"]
     assert d["value"] > 0 and d["ms_per_step"] > 0
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and cb["sample"]
+    from oracle.ref_loader import reference_available
+    assert cb["kind"] == ("reference" if reference_available() else "port")      # the unmodified reference when importable
+    assert cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and cb["sample"] and cb["port_value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
 
@@ -56,13 +58,19 @@ def test_b200_arm_prints_the_contract_line():
         assert key in d, key
     assert "impl" not in d and d["metric"] == "env_steps_per_sec" and d["steps"] == 5 and d["warmup"] == 3
     assert abs(d["value"] - 2048 * 5 / (d["ms_per_step"] * 5e-3)) < 1e-6 * d["value"]
-    assert d["gpu_launches"] == 5 * 2                      # state kernel + sparse egocentric kernel per step
+    assert d["gpu_launches"] == 5 * 3                      # move_kernel, reward_kernel, sparse egocentric kernel per step
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] > 0
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["traffic"] is None      # ncu traffic is for 65 536 envs
+    assert d["roofline_collision"]["kernel"].startswith("collision_thread_kernel") and d["roofline_collision"]["frac"] > 0
+    for name in ("move_kernel", "reward_kernel", "ego_sparse_kernel"):
+        assert d["kernels_ms"][name] > 0
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 2048 * 2 * 4 and e["d2h_bytes_per_step"] == 2048 * (8 + 1 + 48)
-    assert e["with_images_to_host"]["d2h_bytes_per_step"] > 2048 * 117 * 133
+    im = d["e2e_images_to_host"]
+    assert im["dense"]["d2h_bytes_per_step"] > 2048 * 117 * 133 > 4 * im["compact"]["d2h_bytes_per_step"] and im["compact"]["value"] > 0
+    assert d["value_graph"]["value"] > 0 and d["value_200_steps"]["steps"] == 200 and d["strong"] is None     # (2048 envs: not the strong workload)
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] > 0 and cb["sample"]
+    from oracle.ref_loader import reference_available
+    assert cb["kind"] == ("reference" if reference_available() else "port") and cb["cores"] == 1 and cb["value"] > 0 and cb["sample"]
     assert d["clocks"]["samples"] >= 1 and d["clocks"]["sm_mhz"] is not None
