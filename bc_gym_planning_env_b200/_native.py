@@ -159,6 +159,10 @@ SYMBOLS = {
     "bcg_pack_ego_hits": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     "bcg_world_to_pixel": (C.c_int, [_P, C.c_int64, C.c_double, C.c_double, C.c_double, _P, _P]),
     "bcg_normalize_angle": (C.c_int, [_P, C.c_int64, _P, _P]),
+    "bcg_masked_any_equal": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P]),
+    "bcg_inverse_transform": (C.c_int, [_P, C.c_int64, _P, _P]),
+    "bcg_project_poses": (C.c_int, [C.POINTER(C.c_double), _P, C.c_int64, _P, _P]),
+    "bcg_observe_ego_path": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgBatch), C.c_int32, _P, _P, _P]),
 }
 
 

@@ -2344,15 +2344,18 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
         if (HITS) {
           // compact observation (BcgStepOut.ego_hits): pixel offset | value << 16 of every non-zero crop pixel.  A crop
           // pixel samples exactly one cell, so the entries of an env are distinct.
-          const int nh = (int)h00 + (int)h10 + (int)h01 + (int)h11;
+          // (at the crop's border two candidates can be the same pixel: u0 == u1 or v0 == v1 after clamping)
+          const bool du = u1 != u0, dv = v1 != v0;
+          const bool r00 = h00, r10 = h10 && du, r01 = h01 && dv, r11 = h11 && du && dv;
+          const int nh = (int)r00 + (int)r10 + (int)r01 + (int)r11;
           if (nh) {
             uint32_t at = atomicAdd(&T.hits[par], (uint32_t)nh);
             uint32_t* const out = hit_list + (int64_t)e * hit_cap;
             const uint32_t tagged = (uint32_t)val << 16;
-            if (h00) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(v0 * ego_w + u0); ++at; }
-            if (h10) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(v0 * ego_w + u1); ++at; }
-            if (h01) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(v1 * ego_w + u0); ++at; }
-            if (h11) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(v1 * ego_w + u1); ++at; }
+            if (r00) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(v0 * ego_w + u0); ++at; }
+            if (r10) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(v0 * ego_w + u1); ++at; }
+            if (r01) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(v1 * ego_w + u0); ++at; }
+            if (r11) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(v1 * ego_w + u1); ++at; }
           }
         }
       }
@@ -2457,6 +2460,74 @@ __global__ void __launch_bounds__(256) pack_hits_kernel(const uint32_t* __restri
   const uint32_t* src = hits + (int64_t)e * cap;
   uint32_t* dst = packed + offsets[e];
   for (int i = gl; i < c; i += 8) dst[i] = src[i];
+}
+
+// is_footprint_colliding_impl: any(values[mask] == value) over flattened arrays
+__global__ void __launch_bounds__(256) masked_any_equal_kernel(const uint8_t* __restrict__ values, const uint8_t* __restrict__ mask,
+                                                               const int64_t n, const uint8_t value, int32_t* __restrict__ flag) {
+  bool hit = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    hit |= (mask[i] != 0) && (values[i] == value);
+  if (__any_sync(BCG_FULL, hit) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+// inverse_transform (utilities/coordinate_transformations.py:57-84) of n transforms [n][3]
+__global__ void __launch_bounds__(256) inverse_transform_kernel(const double* __restrict__ in, const int64_t n, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = in[3 * i], y = in[3 * i + 1], th = in[3 * i + 2];
+  double sn, cs;
+  sincos(th, &sn, &cs);
+  out[3 * i] = -x * cs - y * sn;
+  out[3 * i + 1] = x * sn - y * cs;
+  out[3 * i + 2] = wrap_angle(-th);
+}
+
+// project_poses (utilities/coordinate_transformations.py:289-328): rotate by the transform's angle, translate, wrap the angle
+__global__ void __launch_bounds__(256) project_poses_kernel(const double tx, const double ty, const double tt,
+                                                            const double* __restrict__ poses, const int64_t n, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double sn, cs;
+  sincos(tt, &sn, &cs);
+  const double x = poses[3 * i], y = poses[3 * i + 1];
+  out[3 * i] = cs * x - sn * y + tx;
+  out[3 * i + 1] = sn * x + cs * y + ty;
+  out[3 * i + 2] = wrap_angle(poses[3 * i + 2] + tt);
+}
+
+// Observation.path (envs/base/env.py:421-433: path[target_idx:]) of every env as a device tensor, in the robot frame
+// (from_global_to_egocentric, utilities/coordinate_transformations.py:341-362): out [n][max_points][3], zero padded;
+// len_out[e] = number of remaining way points (may exceed max_points).  One warp per env, lanes <-> points.
+__global__ void __launch_bounds__(256) ego_path_kernel(const BcgParams p, const BcgBatch b, const int max_points,
+                                                       double* __restrict__ out, int32_t* __restrict__ len_out) {
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  if (e >= b.n_envs) return;
+  const int64_t N = b.n_envs;
+  const BcgPathDesc pd = b.paths[b.path_id[e]];
+  const double* P = b.path_arena + pd.off;
+  const int target = b.state_i[BCG_I_TARGET * N + e];
+  const bool pursuit = p.reward_kind == BCG_REWARD_PURE_PURSUIT;      // reward.py:120-124: path[:target_idx + 1]
+  const int first = pursuit ? 0 : min(max(target, 0), pd.n);
+  const int count = pursuit ? min(target + 1, pd.n) : pd.n - first;
+  const int prow = p.ego_variant == 1 ? BCG_F_ROBOT : BCG_F_DPOSE;
+  double ct, st, tx, ty, tt;
+  inverse_transform(b.state_f[(prow + 0) * N + e], b.state_f[(prow + 1) * N + e], b.state_f[(prow + 2) * N + e], ct, st, tx, ty, tt);
+  double* o = out + (int64_t)e * max_points * 3;
+  for (int j = lane; j < max_points; j += 32) {
+    double ex = 0.0, ey = 0.0, ea = 0.0;
+    if (j < count) {
+      const double gx = P[first + j], gy = P[pd.pitch + first + j], gt = P[2 * pd.pitch + first + j];
+      ex = ct * gx - st * gy + tx;
+      ey = st * gx + ct * gy + ty;
+      ea = wrap_angle(gt + tt);
+    }
+    o[3 * j] = ex;
+    o[3 * j + 1] = ey;
+    o[3 * j + 2] = ea;
+  }
+  if (lane == 0 && len_out) len_out[e] = count;
 }
 
 __global__ void w2p_kernel(const double* __restrict__ xy, const int64_t n, const double ox, const double oy,
@@ -2907,6 +2978,42 @@ int bcg_pack_ego_hits(const uint32_t* hits, const int32_t* counts, int32_t cap, 
   BCG_REQUIRE(hits && counts && offsets && packed && cap > 0 && n >= 0, "bad pack arguments");
   if (n == 0) return BCG_OK;
   pack_hits_kernel<<<blocks_for((int64_t)n * 8, 256), 256, 0, (cudaStream_t)stream>>>(hits, counts, cap, n, offsets, packed);
+  BCG_CHECK_CUDA(cudaGetLastError());
+  return BCG_OK;
+}
+
+int bcg_masked_any_equal(const uint8_t* values, const uint8_t* mask, int64_t n, int32_t value, int32_t* flag_out, void* stream) {
+  BCG_REQUIRE(values && mask && flag_out && n >= 0 && value >= 0 && value <= 255, "bad masked_any_equal arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  BCG_CHECK_CUDA(cudaMemsetAsync(flag_out, 0, sizeof(int32_t), s));
+  if (n == 0) return BCG_OK;
+  const int grid = (int)(n < 256 * 1024 ? blocks_for(n, 256) : 1024);
+  masked_any_equal_kernel<<<grid, 256, 0, s>>>(values, mask, n, (uint8_t)value, flag_out);
+  BCG_CHECK_CUDA(cudaGetLastError());
+  return BCG_OK;
+}
+
+int bcg_inverse_transform(const double* transforms, int64_t n, double* out, void* stream) {
+  BCG_REQUIRE(transforms && out && n >= 0, "bad inverse_transform arguments");
+  if (n == 0) return BCG_OK;
+  inverse_transform_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(transforms, n, out);
+  BCG_CHECK_CUDA(cudaGetLastError());
+  return BCG_OK;
+}
+
+int bcg_project_poses(const double* transform_host, const double* poses, int64_t n, double* out, void* stream) {
+  BCG_REQUIRE(transform_host && poses && out && n >= 0, "bad project_poses arguments");
+  if (n == 0) return BCG_OK;
+  project_poses_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(transform_host[0], transform_host[1], transform_host[2],
+                                                                           poses, n, out);
+  BCG_CHECK_CUDA(cudaGetLastError());
+  return BCG_OK;
+}
+
+int bcg_observe_ego_path(const BcgParams* p, const BcgBatch* b, int32_t max_points, double* out, int32_t* len_out, void* stream) {
+  if (int rc = check_batch(p, b)) return rc;
+  BCG_REQUIRE(out && max_points > 0, "bad ego path arguments");
+  ego_path_kernel<<<blocks_for((int64_t)b->n_envs * 32, 256), 256, 0, (cudaStream_t)stream>>>(*p, *b, max_points, out, len_out);
   BCG_CHECK_CUDA(cudaGetLastError());
   return BCG_OK;
 }

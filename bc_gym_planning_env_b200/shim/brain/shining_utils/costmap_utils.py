@@ -1,4 +1,4 @@
-"""world_to_pixel_impl and get_pixel_footprint_impl backed by libbcg_b200 / the exact footprint table."""
+"""world_to_pixel_impl, get_pixel_footprint_impl and is_footprint_colliding_impl backed by libbcg_b200 / the exact footprint table."""
 import ctypes as C
 
 import numpy as np
@@ -43,3 +43,19 @@ def get_pixel_footprint_impl(angle, robot_footprint, map_resolution, fill=True):
     if key not in _LUTS:
         _LUTS[key] = FootprintLut(footprint, float(map_resolution))
     return _LUTS[key].canvas(float(angle))
+
+
+def is_footprint_colliding_impl(image_slice, blit_mask, lethal_value):
+    """replaces the native hook of utilities/costmap_utils.py:106-136 (contract: test_costmap_utils.py:251-325): does any
+    costmap cell under the blitted footprint equal `lethal_value`?  image_slice: the costmap view get_blit_mask cut out,
+    blit_mask: the footprint's boolean mask over it."""
+    image_slice, blit_mask = np.asarray(image_slice), np.asarray(blit_mask)
+    if image_slice.shape[:2] != blit_mask.shape[:2] or image_slice.dtype != np.uint8:
+        raise TypeError("is_footprint_colliding_impl takes a uint8 image slice and a mask of the same shape")
+    nat.require_cuda()
+    vals = torch.from_numpy(np.ascontiguousarray(image_slice).reshape(-1)).cuda()
+    mask = torch.from_numpy(np.ascontiguousarray(blit_mask, dtype=np.uint8).reshape(-1)).cuda()
+    flag = torch.zeros(1, dtype=torch.int32, device=vals.device)
+    nat.check(nat.lib().bcg_masked_any_equal(nat.ptr(vals), nat.ptr(mask), vals.numel(), int(lethal_value), nat.ptr(flag),
+                                             C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return bool(flag.item())

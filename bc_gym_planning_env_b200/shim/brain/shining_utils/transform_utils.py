@@ -1,4 +1,5 @@
-"""normalize_angle_impl backed by bcg_normalize_angle (replaces utilities/coordinate_transformations.py:28-36)."""
+"""normalize_angle_impl (replaces utilities/coordinate_transformations.py:28-36) and inverse_transform_2d_impl (:39-84)
+backed by libbcg_b200."""
 import ctypes as C
 
 import numpy as np
@@ -25,3 +26,17 @@ def normalize_angle_impl(z):
                                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     res = out.cpu().numpy()
     return float(res[0]) if scalar else res
+
+
+def inverse_transform_2d_impl(transform):
+    """replaces the native hook of utilities/coordinate_transformations.py:39-84 (contract:
+    test_coordinate_transformations.py:105-178): (x, y, angle) or array(N, 3) of them -> the inverse transform(s)."""
+    t = np.asarray(transform, dtype=np.float64)
+    if t.ndim not in (1, 2) or t.shape[-1] != 3:
+        raise TypeError("inverse_transform takes an (x, y, angle) transform or an array(N, 3) of them")
+    nat.require_cuda()
+    dev = torch.from_numpy(np.ascontiguousarray(t).reshape(-1, 3)).cuda()
+    out = torch.empty_like(dev)
+    nat.check(nat.lib().bcg_inverse_transform(nat.ptr(dev), dev.shape[0], nat.ptr(out),
+                                              C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return out.cpu().numpy().reshape(t.shape)

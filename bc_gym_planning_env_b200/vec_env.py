@@ -392,7 +392,7 @@ class VecPlanEnv(object):
             self.EGO_HIT_CAP = 1024
             self._ego_hits = torch.zeros((self.n_envs, self.EGO_HIT_CAP), dtype=torch.int32, device=self.device)
             self._ego_hit_count = torch.zeros(self.n_envs, dtype=torch.int32, device=self.device)
-            out.ego_hits, out.ego_hit_count, out.ego_hit_cap = self._ego_hits.data_ptr(), self._ego_hit_count.data_ptr(), self.EGO_HIT_CAP
+            # (BcgStepOut.ego_hits is only set for the steps whose lists are wanted: step_host(images='compact'))
         self._out = out
 
     def _stream(self):
@@ -510,7 +510,16 @@ class VecPlanEnv(object):
             raise ValueError("actions_host must be a float32 tensor of shape (%d, 2)" % self.n_envs)
         main = torch.cuda.current_stream(self.device)
         io['actions'].copy_(actions_host, non_blocking=True)
-        self.step_timed(io['actions'], io['events'])
+        if images == 'compact':
+            if self._ego_hits is None:
+                raise ValueError("this batch was built without compact_ego=True")
+            self._out.ego_hits, self._out.ego_hit_count = self._ego_hits.data_ptr(), self._ego_hit_count.data_ptr()
+            self._out.ego_hit_cap = self.EGO_HIT_CAP
+        try:
+            self.step_timed(io['actions'], io['events'])
+        finally:
+            self._out.ego_hits = self._out.ego_hit_count = None
+            self._out.ego_hit_cap = 0
         side = io['stream']
         side.wait_event(io['events'][3])                      # recorded right after commit_kernel
         with torch.cuda.stream(side):
@@ -638,6 +647,18 @@ class VecPlanEnv(object):
         nat.check(nat.lib().bcg_observe_ego(C.byref(self._c_params), C.byref(self._batch), nat.ptr(self.ego_image),
                                             nat.ptr(self.goal_n_state), self._stream()))
         return self.ego_image, self.goal_n_state
+
+    def observe_ego_path(self, max_points=64):
+        """Observation.path of every env as device tensors (reference envs/base/env.py:421-433: `path[target_idx:]`, with
+        the pure-pursuit provider `path[:target_idx + 1]`), in the robot frame like the egocentric wrapper sees it
+        (from_global_to_egocentric, utilities/coordinate_transformations.py:341-362): (fp64 [N, max_points, 3] zero
+        padded, int32 [N] way points left) -- what a GPU-resident policy consumes instead of the ragged per-env slices
+        of `VecObservation.path`."""
+        out = torch.empty((self.n_envs, int(max_points), 3), dtype=torch.float64, device=self.device)
+        left = torch.empty(self.n_envs, dtype=torch.int32, device=self.device)
+        nat.check(nat.lib().bcg_observe_ego_path(C.byref(self._c_params), C.byref(self._batch), int(max_points), nat.ptr(out),
+                                                 nat.ptr(left), self._stream()))
+        return out, left
 
     def get_state(self, indices=None):
         idx = self._indices(indices)

@@ -672,11 +672,11 @@ def run_aisle(args, D):
     # ---- same loop without the egocentric kernel (reported beside the headline, not instead of it) -----
     no_ego_value = None
     if not args.no_ego:
-        saved = (env._out.ego_image, env._out.goal_n_state, env._out.ego_hits, env._out.ego_hit_count)
-        env._out.ego_image = env._out.goal_n_state = env._out.ego_hits = env._out.ego_hit_count = None
+        saved = (env._out.ego_image, env._out.goal_n_state)
+        env._out.ego_image = env._out.goal_n_state = None
         ms = plain_steps(env, actions, args.steps, D)
         no_ego_value = n * world * args.steps / (ms * 1e-3)
-        env._out.ego_image, env._out.goal_n_state, env._out.ego_hits, env._out.ego_hit_count = saved
+        env._out.ego_image, env._out.goal_n_state = saved
 
     # ---- algorithmic bytes -----------------------------------------------------------
     cand_pose = env._cand[:3].t().contiguous()

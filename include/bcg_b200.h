@@ -399,6 +399,19 @@ int bcg_world_to_pixel(const double* xy, int64_t n, double origin_x, double orig
                        double resolution, int32_t* out, void* stream);
 /* normalize_angle (coordinate_transformations.py:28-36) */
 int bcg_normalize_angle(const double* in, int64_t n, double* out, void* stream);
+/* is_footprint_colliding_impl (costmap_utils.py:106-136; contract test_costmap_utils.py:251-325): does any cell of the
+ * blitted footprint equal `value`?  values, mask: device [n] (the image slice and the blit mask, flattened);
+ * flag_out: device int32, 1 when any(values[mask != 0] == value) */
+int bcg_masked_any_equal(const uint8_t* values, const uint8_t* mask, int64_t n, int32_t value, int32_t* flag_out, void* stream);
+/* inverse_transform_2d_impl (coordinate_transformations.py:39-84): device [n][3] (x, y, angle) -> [n][3] */
+int bcg_inverse_transform(const double* transforms, int64_t n, double* out, void* stream);
+/* native_project_poses (coordinate_transformations.py:289-328): poses device [n][3] moved by the HOST transform
+ * (x, y, angle): rotate, translate, wrap the angle */
+int bcg_project_poses(const double* transform_host, const double* poses, int64_t n, double* out, void* stream);
+/* Observation.path of every env (env.py:421-433: path[target_idx:]; pure pursuit: path[:target_idx + 1]) as a device
+ * tensor in the robot frame (from_global_to_egocentric, coordinate_transformations.py:341-362, about the observed pose):
+ * out device [n][max_points][3] zero padded, len_out (optional) device [n] = way points left (may exceed max_points) */
+int bcg_observe_ego_path(const BcgParams* p, const BcgBatch* b, int32_t max_points, double* out, int32_t* len_out, void* stream);
 
 #ifdef __cplusplus
 }

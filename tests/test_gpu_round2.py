@@ -74,7 +74,7 @@ def _blob_world():
     m = np.zeros((500, 500), dtype=np.uint8)
     m[230:290, 300:360] = 254
     m[100, 50:450] = 253
-    return CostMap2D(m, 0.03, np.array([0., 0.])), np.array([[2.0, 7.2, 0.0], [12.0, 7.2, 0.0]])
+    return CostMap2D(m, 0.03, np.array([0., 0.])), np.array([[7.4, 7.8, 0.0], [14.0, 7.8, 0.0]])     # starts 1.6 m before the block
 
 
 def test_sparse_kernel_renders_overflowing_windows_itself():

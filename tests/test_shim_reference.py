@@ -30,4 +30,5 @@ def test_shim_modules_resolve_without_touching_the_gpu():
     cu = importlib.import_module("brain.shining_utils.costmap_utils")
     tu = importlib.import_module("brain.shining_utils.transform_utils")
     assert callable(cu.world_to_pixel_impl) and callable(cu.get_pixel_footprint_impl) and callable(tu.normalize_angle_impl)
-    assert not hasattr(cu, "is_footprint_colliding_impl")          # left to the reference's own Python
+    eu = importlib.import_module("brain.shining_utils.env_utils")
+    assert callable(cu.is_footprint_colliding_impl) and callable(tu.inverse_transform_2d_impl) and callable(eu.native_project_poses)
