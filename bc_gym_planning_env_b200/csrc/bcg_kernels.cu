@@ -2401,6 +2401,384 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
   }
 }
 
+// ---- ego_warp_kernel: the same scatter, one WARP per env ------------------------------------------------------------
+// ego_sparse_kernel gives an env to a 64-thread CTA: per env its two warps meet at two barriers (8 % of the stall samples),
+// both build the window's tile list, and ~950 of its 2 700 warp instructions per env are per-env fixed cost that is paid
+// per warp (profiles/r2_notes.md).  Here a warp owns an env from the record to the last byte: no barrier (only
+// __syncwarp), nothing computed twice, its own shared-memory context (cell list as 16-bit entries, piece queue, tile
+// list, tile spans, record ring, crop tables), its own draws from the global env counter.  A CTA is just a container of
+// BCG_EGW_WARPS such warps that share one page of zeros for the bulk stores.
+#ifndef BCG_EGW_WARPS
+#define BCG_EGW_WARPS 4
+#endif
+#ifndef BCG_EGW_CTAS
+#define BCG_EGW_CTAS 8               // register budget (launch bound): 65536 / (128 x 8) = 64; the launch asks the occupancy calculator
+#endif
+#ifndef BCG_EGW_ROUNDS
+#define BCG_EGW_ROUNDS 4             // rounds of 8 non-empty tiles whose occupancy words a warp loads per pass
+#endif
+struct __align__(16) EgwCtx {
+  uint4 qword[BCG_EGS_QCAP];                    // queued non-empty 16-byte occupancy pieces
+  uint8_t rec[BCG_EGS_REC_SLOTS * BCG_EGO_WORK_BYTES];   // record ring
+  uint32_t qtag[BCG_EGS_QCAP];
+  uint16_t list[BCG_EGS_LIST];                  // occupied window cells: y_rel << 8 | x_rel (windows of <= 256 x 256 cells)
+  uint16_t tlist[BCG_EGS_MAX_TILES];            // non-empty tiles of the window
+  uint16_t span[BCG_EGT_MAX_TILE_ROWS];         // tile spans of the window's rows (ego_band_span)
+  uint32_t count, hits;
+  int32_t ids[8];                               // envs drawn from the global counter, RD + 1 iterations ahead
+};
+
+template <bool SUM, bool HITS>
+__global__ void __launch_bounds__(BCG_EGW_WARPS * 32, BCG_EGW_CTAS) ego_warp_kernel(const BcgParams p, const BcgBatch b,
+                                                                                   uint8_t* __restrict__ image,
+                                                                                   uint32_t* __restrict__ hit_list,
+                                                                                   int32_t* __restrict__ hit_count,
+                                                                                   const int hit_cap) {
+  __shared__ __align__(128) uint8_t zero_s[BCG_EGS_ZERO_BYTES];
+  __shared__ EgwCtx ctx_s[BCG_EGW_WARPS];
+  extern __shared__ __align__(16) int2 egw_tab[];          // per warp: adxy[ego_w], bxy[ego_h]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ego_w = p.ego_w, ego_h = p.ego_h, npx = ego_w * ego_h;
+  EgwCtx& T = ctx_s[warp];
+  int2* const tab = egw_tab + warp * (ego_w + ego_h);
+  const uint32_t qword_u32 = smem_u32(T.qword), qtag_u32 = smem_u32(T.qtag), tlist_u32 = smem_u32(T.tlist);
+  const uint32_t zero_u32 = smem_u32(zero_s), rec_u32 = smem_u32(T.rec), list_u32 = smem_u32(T.list), span_u32 = smem_u32(T.span);
+  const uint32_t adxy_u32 = smem_u32(tab), bxy_u32 = adxy_u32 + 8u * (uint32_t)ego_w;
+  const uint8_t* const recs = reinterpret_cast<const uint8_t*>(b.ego_work);
+  const int n = b.n_envs;
+  constexpr int RD = 3;
+  static_assert(RD < BCG_EGS_REC_SLOTS, "record ring too small");
+
+  for (int i = tid * 16; i < BCG_EGS_ZERO_BYTES; i += BCG_EGW_WARPS * 32 * 16) *reinterpret_cast<uint4*>(zero_s + i) = make_uint4(0u, 0u, 0u, 0u);
+  fence_async_smem();                         // the zeros are visible to the bulk-copy engine
+  __syncthreads();                            // (the only CTA-wide barrier: from here on the warps are on their own)
+
+  auto fetch_record = [&](int en, int slot) {
+    if (en < n && lane < BCG_EGO_WORK_BYTES / 16)
+      cp_async_16(rec_u32 + slot * BCG_EGO_WORK_BYTES + lane * 16, recs + (int64_t)en * BCG_EGO_WORK_BYTES + lane * 16, 16u);
+  };
+  auto summary_words = [&](const EgoTileWork* q, uint32_t& lo, uint32_t& hi) {
+    lo = hi = 0u;
+    if (q->mode != BCG_EGO_MODE_TILES || (q->dense_map & 1)) return;
+    const int qby0 = q->Y0 >> 4, qnby = ((q->Y0 + 8 * q->nty - 1) >> 4) - qby0 + 1;
+    const int qtx = (int)(q->tiles_xy & 0xffffu), qty = (int)(q->tiles_xy >> 16), sw = (qtx + 31) >> 5;
+    const int ty = qby0 + lane, w0 = q->X0 >> 10;                            // X0 >> 5 may be negative: w0 = -1
+    if (lane < qnby && (unsigned)ty < (unsigned)qty) {
+      const uint32_t* const srow = b.occ_sum_arena + q->sum_off + ty * sw;
+      if ((unsigned)w0 < (unsigned)sw) lo = __ldg(srow + w0);
+      if ((unsigned)(w0 + 1) < (unsigned)sw) hi = __ldg(srow + w0 + 1);
+    }
+  };
+  // the warp's first RD + 1 envs, drawn from the global counter (ego_list[n + 1], zeroed by the state / prep kernel)
+  {
+    int first = 0;
+    if (lane == 0) first = atomicAdd(b.ego_list + n + 1, RD + 1);
+    first = __shfl_sync(BCG_FULL, first, 0);
+    if (lane <= RD) T.ids[lane] = first + lane;
+    if (first >= n) return;
+#pragma unroll
+    for (int k = 0; k < RD; ++k) fetch_record(first + k, k);
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncwarp();
+  }
+  uint32_t pf_lo = 0u, pf_hi = 0u;              // summary words of the env about to be rendered
+  if (SUM) summary_words(reinterpret_cast<const EgoTileWork*>(T.rec), pf_lo, pf_hi);
+  for (int it = 0;; ++it) {
+    const int e = T.ids[it & 7];
+    if (e >= n) break;
+    int drawn = 0;
+    if (lane == 0) {
+      drawn = atomicAdd(b.ego_list + n + 1, 1);           // stored at the end of the iteration
+      T.count = 0u;
+      T.hits = 0u;
+    }
+    const int slot = it & (BCG_EGS_REC_SLOTS - 1);
+    fetch_record(T.ids[(it + RD) & 7], (it + RD) & (BCG_EGS_REC_SLOTS - 1));
+    cp_async_commit();
+    const int e_next = T.ids[(it + 1) & 7];
+    // record it + 1 has landed (only the newest fetch may still be in flight): start its summary loads now
+    const uint32_t cur_lo = pf_lo, cur_hi = pf_hi;
+    if (SUM && e_next < n)
+      summary_words(reinterpret_cast<const EgoTileWork*>(T.rec + ((it + 1) & (BCG_EGS_REC_SLOTS - 1)) * BCG_EGO_WORK_BYTES), pf_lo, pf_hi);
+    const EgoTileWork* r = reinterpret_cast<const EgoTileWork*>(T.rec + slot * BCG_EGO_WORK_BYTES);
+    const int mode = r->mode, X0 = r->X0, Y0 = r->Y0, ntx = r->ntx, nty = r->nty;
+    uint8_t* const dst = image + (int64_t)e * npx;
+    const int wx0 = X0 >> 5, nwx = ((X0 + 16 * ntx - 1) >> 5) - wx0 + 1;        // <= 9 columns of 32-cell words
+    const int by0 = Y0 >> 4, nby = ((Y0 + 8 * nty - 1) >> 4) - by0 + 1;         // bands of 16 rows
+    const int ntile = nby * nwx;
+    const bool dense_map = (r->dense_map & 1) != 0;     // decided by the record writer, which holds the map descriptor
+    // (nty <= 32: window rows fit the 8 bits of a list entry, and one lane per tile row)
+    const bool try_sparse = mode == BCG_EGO_MODE_TILES && ntile <= BCG_EGS_MAX_TILES && !dense_map && nty <= 32 &&
+                            (!SUM || (nby <= 32 && nwx <= 32));
+    __syncwarp();                               // the counters are zero for everyone
+    if (try_sparse) {
+      // ---- 1. zero the crop in global memory ----------------------------------------------------------------------
+      {
+        const int head = min((int)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u), npx);
+        const int body = (npx - head) & ~15, tail = npx - head - body;
+        if (lane == 0) {
+          for (int o = 0; o < body; o += BCG_EGS_ZERO_BYTES)
+            bulk_store(dst + head + o, zero_u32, (uint32_t)min(body - o, BCG_EGS_ZERO_BYTES));
+          bulk_commit();
+        }
+        if (lane < head) dst[lane] = 0;
+        if (lane >= 16 && lane - 16 < tail) dst[head + body + lane - 16] = 0;
+      }
+      const int tiles_x = (int)(r->tiles_xy & 0xffffu), tiles_y = (int)(r->tiles_xy >> 16);
+      const uint4* occ = reinterpret_cast<const uint4*>(b.occ_tile_arena + ((int64_t)r->tile_off16 << 4));
+      const int g = lane & 3;                                                     // rows 4 g .. 4 g + 3 of the tile
+      constexpr int TPR = 8;                                                      // tiles per round
+      auto expand = [&](const uint32_t qhead, const int nitems) {
+        uint4 wd = make_uint4(0u, 0u, 0u, 0u);
+        uint32_t tag = 0u;
+        if (lane < nitems) {
+          const uint32_t at = (qhead + (uint32_t)lane) & (BCG_EGS_QCAP - 1);
+          wd = lds_v4(qword_u32 + 16u * at);
+          tag = lds_u32(qtag_u32 + 4u * at);
+        }
+        __syncwarp();                                                            // ring slots are free again
+        const int band = (int)(tag >> 8), jw = (int)((tag >> 2) & 63u), gq = (int)(tag & 3u);
+        const int tx = wx0 + jw;
+        const int yr0 = (((by0 + band) << 4) + 4 * gq) - Y0;                      // window row of word .x; 4 | yr0
+        uint32_t bits[4] = {wd.x, wd.y, wd.z, wd.w};
+        uint32_t keep = 0u;
+        if (yr0 >= 0 && yr0 < 8 * nty) {                                          // clip to the tile span of these rows
+          const uint32_t sp = lds_u16(span_u32 + 2 * (yr0 >> 3));
+          const int lo = max(X0 + 16 * (int)(sp & 0xff) - (tx << 5), 0);
+          const int hi = min(X0 + 16 * (int)(sp >> 8) + 15 - (tx << 5), 31);
+          if (lo <= hi) keep = (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
+        }
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          bits[k] &= keep;
+          cnt += __popc(bits[k]);
+        }
+        // list slots: inclusive warp scan of the counts (the warp owns the list: no atomic)
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int v = __shfl_up_sync(BCG_FULL, incl, d);
+          if (lane >= d) incl += v;
+        }
+        const int total = __shfl_sync(BCG_FULL, incl, 31);
+        if (total == 0) return;
+        const uint32_t base0 = T.count;
+        __syncwarp();
+        if (lane == 31) T.count = base0 + (uint32_t)total;
+        const uint32_t base = base0 + (uint32_t)(incl - cnt);
+        if (cnt == 0 || base + (uint32_t)cnt > BCG_EGS_LIST) return;              // overflow: see below
+        uint32_t at = list_u32 + 2u * base;
+        const int key = (yr0 << 8) + ((tx << 5) - X0);           // x_rel of bit 0 may be negative, of a kept bit never
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint32_t w = bits[k];
+          while (w) {
+            const int bit = 31 - __clz(w);                       // order within the list is irrelevant
+            w ^= 1u << bit;
+            sts_u16(at, (uint32_t)(key + (k << 8) + bit));
+            at += 2u;
+          }
+        }
+      };
+      const uint32_t lt_mask = (1u << lane) - 1u;
+      uint32_t qhead = 0u, qtail = 0u;
+      auto push = [&](const uint4& w, const uint32_t tag) {
+        const bool nz = (w.x | w.y | w.z | w.w) != 0u;
+        const uint32_t bal = __ballot_sync(BCG_FULL, nz);
+        if (bal == 0u) return;                                                    // free space
+        if (nz) {
+          const uint32_t at = (qtail + (uint32_t)__popc(bal & lt_mask)) & (BCG_EGS_QCAP - 1);
+          sts_v4(qword_u32 + 16u * at, w);
+          sts_u32(qtag_u32 + 4u * at, tag);
+        }
+        qtail += (uint32_t)__popc(bal);
+        if (qtail - qhead >= 32u) {
+          __syncwarp();
+          expand(qhead, 32);
+          qhead += 32u;
+        }
+      };
+      // the crop's tile spans (lane <-> tile row) and fixed-point tables: worked out while the first occupancy loads fly
+      auto spans_and_tables = [&]() {
+        if (lane < nty) sts_u16(span_u32 + 2u * (uint32_t)lane, ego_band_span(r->aff, ego_w, ego_h, X0, Y0, ntx, nty, lane));
+        const EgoAffine A = r->aff;
+        for (int i = lane; i < ego_w + ego_h; i += 32) {
+          if (i < ego_w) {
+            tab[i] = make_int2(__double2int_rn(A.a11 * i * 1024), __double2int_rn(A.a21 * i * 1024));
+          } else {
+            const int t = i - ego_w;
+            tab[i] = make_int2(__double2int_rn((A.a12 * t + A.b1) * 1024) + 512 - (X0 << 10),
+                               __double2int_rn((A.a22 * t + A.b2) * 1024) + 512 - (Y0 << 10));
+          }
+        }
+        __syncwarp();
+      };
+      if constexpr (SUM) {
+        // (a) which tiles of the window hold a cell at all: lane <-> band of 16 rows (summary words loaded one env ahead)
+        const uint32_t tmask = (uint32_t)((((uint64_t)cur_hi << 32) | cur_lo) >> (wx0 & 31)) & ((1u << nwx) - 1u);
+        // (b) the list of those tiles (band << 6 | column), in band order: inclusive warp scan of the per-band counts
+        int tincl = __popc(tmask);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int v = __shfl_up_sync(BCG_FULL, tincl, d);
+          if (lane >= d) tincl += v;
+        }
+        const int ntl = __shfl_sync(BCG_FULL, tincl, 31);                         // <= ntile <= BCG_EGS_MAX_TILES
+        {
+          uint32_t at = tlist_u32 + 2u * (uint32_t)(tincl - __popc(tmask));
+          uint32_t m2 = tmask;
+          while (m2) {
+            const int jw = __ffs((int)m2) - 1;
+            m2 &= m2 - 1u;
+            sts_u16(at, (uint32_t)((lane << 6) | jw));
+            at += 2u;
+          }
+        }
+        __syncwarp();
+        // (c) their pieces, BCG_EGW_ROUNDS x 8 tiles per pass
+        constexpr int RS = BCG_EGW_ROUNDS;
+        bool first_pass = true;
+        for (int base = 0; base < ntl || first_pass; base += RS * TPR) {
+          uint4 word[RS];
+          uint32_t tag[RS];
+#pragma unroll
+          for (int rd = 0; rd < RS; ++rd) {
+            const int i = base + (lane >> 2) + rd * TPR;
+            word[rd] = make_uint4(0u, 0u, 0u, 0u);
+            tag[rd] = 0u;
+            if (i < ntl) {
+              const uint32_t code = lds_u16(tlist_u32 + 2u * (uint32_t)i);
+              const int band = (int)(code >> 6), jw = (int)(code & 63u);
+              tag[rd] = (code << 2) | (uint32_t)g;
+              word[rd] = __ldg(occ + ((((by0 + band) * tiles_x + wx0 + jw) << 2) + g));
+            }
+          }
+          if (first_pass) spans_and_tables();
+          first_pass = false;
+#pragma unroll
+          for (int rd = 0; rd < RS; ++rd) push(word[rd], tag[rd]);
+        }
+      } else {
+        spans_and_tables();
+        const uint32_t inv = (65536u + (uint32_t)nwx - 1u) / (uint32_t)nwx;       // t / nwx == (t * inv) >> 16 for t < 4096
+        for (int base = 0; base < ntile; base += 4 * TPR) {
+          uint4 word[4];
+          uint32_t tag[4];
+#pragma unroll
+          for (int rd = 0; rd < 4; ++rd) {
+            const int t = base + (lane >> 2) + rd * TPR;
+            const int band = (int)(((uint32_t)t * inv) >> 16), jw = t - band * nwx;
+            const int ty = by0 + band, tx = wx0 + jw;
+            word[rd] = make_uint4(0u, 0u, 0u, 0u);
+            tag[rd] = (uint32_t)((band << 8) | (jw << 2) | g);
+            if (t < ntile && (unsigned)ty < (unsigned)tiles_y && (unsigned)tx < (unsigned)tiles_x)
+              word[rd] = __ldg(occ + (((ty * tiles_x + tx) << 2) + g));
+          }
+#pragma unroll
+          for (int rd = 0; rd < 4; ++rd) push(word[rd], tag[rd]);
+        }
+      }
+      if (qtail != qhead) {
+        __syncwarp();
+        expand(qhead, (int)(qtail - qhead));
+      }
+      if (lane == 0) bulk_wait_all();         // the zeros have landed (they had the whole scan to do so)
+    }
+    cp_async_wait_group_1();                  // the record needed next iteration has landed
+    __syncwarp();                             // zeros (incl. head / tail bytes), tables, list and count are complete
+    const uint32_t count = T.count;
+    const bool sparse = try_sparse && count <= BCG_EGS_LIST;
+    if (sparse) {
+      // ---- 3. scatter the listed cells ----------------------------------------------------------------------------
+      const bool only_lethal = (r->dense_map & 2) != 0;
+      const uint8_t* src = nullptr;
+      int pitch = 0;
+      if (!only_lethal) {                               // other cost values: they are read from the map's uint8 rows
+        const BcgMapDesc* md = b.maps + r->map_id;
+        src = b.map_arena + md->data_off;
+        pitch = md->pitch;
+      }
+      const float m0 = r->fwd[0], m1 = r->fwd[1], m2 = r->fwd[2], m3 = r->fwd[3], m4 = r->fwd[4], m5 = r->fwd[5];
+      for (uint32_t i = lane; i < count; i += 32) {
+        const uint32_t key = lds_u16(list_u32 + 2u * i);
+        const int xr = (int)(key & 0xffu), yr = (int)(key >> 8);
+        const float X = (float)(X0 + xr), Y = (float)(Y0 + yr);
+        // candidates only: fused multiply-adds are fine here, the fixed-point test below decides
+        const int fu = __float2int_rd(__fmaf_rn(m0, X, __fmaf_rn(m1, Y, m2)));
+        const int fv = __float2int_rd(__fmaf_rn(m3, X, __fmaf_rn(m4, Y, m5)));
+        if (fu < -1 || fu >= ego_w || fv < -1 || fv >= ego_h) continue;     // every candidate is outside the crop
+        uint8_t val = 254;
+        if (!only_lethal) val = __ldg(src + (int64_t)(Y0 + yr) * pitch + (X0 + xr));
+        const int u0 = max(fu, 0), u1 = min(fu + 1, ego_w - 1), v0 = max(fv, 0), v1 = min(fv + 1, ego_h - 1);
+        const uint2 a0 = lds_v2(adxy_u32 + 8u * (uint32_t)u0), a1 = lds_v2(adxy_u32 + 8u * (uint32_t)u1);
+        const uint2 b0 = lds_v2(bxy_u32 + 8u * (uint32_t)v0), b1 = lds_v2(bxy_u32 + 8u * (uint32_t)v1);
+        // (a + b) >> 10 == r  <=>  0 <= a + b - (r << 10) < 1024
+        const int xs = xr << 10, ys = yr << 10;
+        const bool h00 = (uint32_t)((int)a0.x + (int)b0.x - xs) < 1024u && (uint32_t)((int)a0.y + (int)b0.y - ys) < 1024u;
+        const bool h10 = (uint32_t)((int)a1.x + (int)b0.x - xs) < 1024u && (uint32_t)((int)a1.y + (int)b0.y - ys) < 1024u;
+        const bool h01 = (uint32_t)((int)a0.x + (int)b1.x - xs) < 1024u && (uint32_t)((int)a0.y + (int)b1.y - ys) < 1024u;
+        const bool h11 = (uint32_t)((int)a1.x + (int)b1.x - xs) < 1024u && (uint32_t)((int)a1.y + (int)b1.y - ys) < 1024u;
+        uint8_t* const row0 = dst + v0 * ego_w, * const row1 = dst + v1 * ego_w;
+        if (h00) row0[u0] = val;
+        if (h10) row0[u1] = val;
+        if (h01) row1[u0] = val;
+        if (h11) row1[u1] = val;
+        if (HITS) {
+          // compact observation (BcgStepOut.ego_hits): pixel offset | value << 16 of every non-zero crop pixel (at the
+          // crop's border two candidates can be the same pixel: u0 == u1 or v0 == v1 after clamping)
+          const bool du = u1 != u0, dv = v1 != v0;
+          const bool r00 = h00, r10 = h10 && du, r01 = h01 && dv, r11 = h11 && du && dv;
+          const int nh = (int)r00 + (int)r10 + (int)r01 + (int)r11;
+          if (nh) {
+            uint32_t at = atomicAdd(&T.hits, (uint32_t)nh);
+            uint32_t* const out = hit_list + (int64_t)e * hit_cap;
+            const uint32_t tagged = (uint32_t)val << 16;
+            if (r00) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(v0 * ego_w + u0); ++at; }
+            if (r10) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(v0 * ego_w + u1); ++at; }
+            if (r01) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(v1 * ego_w + u0); ++at; }
+            if (r11) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(v1 * ego_w + u1); ++at; }
+          }
+        }
+      }
+    } else if (b.flags & BCG_BATCH_SPARSE_EGO_ONLY) {
+      // No dense pass follows this kernel (the host knows that no map of the batch is dense): the rare window that
+      // overflows the cell list, or lies outside any sane range, is rendered here by the bounds-checked per-pixel gather.
+      const EgoAffine A = r->aff;
+      for (int i = lane; i < ego_w + ego_h; i += 32) {
+        if (i < ego_w) {
+          tab[i] = make_int2(__double2int_rn(A.a11 * i * 1024), __double2int_rn(A.a21 * i * 1024));
+        } else {
+          const int t = i - ego_w;
+          tab[i] = make_int2(__double2int_rn((A.a12 * t + A.b1) * 1024) + 512, __double2int_rn((A.a22 * t + A.b2) * 1024) + 512);
+        }
+      }
+      __syncwarp();
+      const BcgMapDesc* md = b.maps + r->map_id;
+      const uint8_t* src = b.map_arena + md->data_off;
+      const int mw = md->width, mh = md->height, mpitch = md->pitch;
+      for (int i = lane; i < npx; i += 32) {
+        const int vv = i / ego_w, uu = i - vv * ego_w;
+        const int2 aa = tab[uu], bb = tab[ego_w + vv];
+        const long long X = ((long long)aa.x + bb.x) >> 10, Y = ((long long)aa.y + bb.y) >> 10;
+        uint8_t val = 0;
+        if (X >= 0 && X < mw && Y >= 0 && Y < mh) val = __ldg(src + Y * mpitch + X);
+        dst[i] = val;
+      }
+    } else if (lane == 0) {
+      const int at = atomicAdd(b.ego_list + n, 1);
+      b.ego_list[at] = e;
+    }
+    __syncwarp();                               // every lane is done with the list, the tables, the hit counter and record `it`
+    if (lane == 0) {
+      if (HITS) hit_count[e] = sparse ? (int32_t)T.hits : -1;     // > hit_cap: the list overflowed; -1: rendered densely
+      T.ids[(it + RD + 1) & 7] = drawn;
+    }
+    __syncwarp();
+  }
+}
+
 // EgoWork records and / or goal_n_state from the current state (stand-alone bcg_observe_ego): one thread per env
 __global__ void __launch_bounds__(128) ego_prep_kernel(const BcgParams p, const BcgBatch b, const int want_image,
                                                        float* __restrict__ goal_n_state, const int ego_cap) {
