@@ -93,10 +93,28 @@ __device__ __forceinline__ void pose_motion_step(double& x, double& y, double& t
 
 // kinematic_body_pose_motion_step_with_noise, robot_models/differential_drive.py:43-74.
 // Normal slots: block 0 = (angular, final rotation), block 1 first half = linear.
+// the normals of Philox block 0 (angular velocity, final rotation), drawn ahead of their use: they depend on nothing but
+// (seed, env, step), so a caller can take them off the dependent chain of the kinematics
+struct NoiseDraws {
+  bool have0;
+  double n_w, n_g;
+};
+__device__ __forceinline__ NoiseDraws draw_noise_ahead(const BcgParams& p, uint64_t env, uint64_t step) {
+  NoiseDraws nd;
+  nd.have0 = false;
+  nd.n_w = nd.n_g = 0.0;
+  if (p.noise_on && (p.alpha[2] > 0.0 || p.alpha[3] > 0.0 || p.alpha[4] > 0.0 || p.alpha[5] > 0.0)) {
+    philox_normals(p.seed, env, step, 0u, nd.n_w, nd.n_g);
+    nd.have0 = true;
+  }
+  return nd;
+}
+
 __device__ __forceinline__ void noisy_pose_motion_step(double& x, double& y, double& th, double v, double w,
-                                                       const BcgParams& p, uint64_t env, uint64_t step) {
-  double n_w = 0.0, n_g = 0.0;
-  bool have0 = false;
+                                                       const BcgParams& p, uint64_t env, uint64_t step,
+                                                       NoiseDraws nd = NoiseDraws{false, 0.0, 0.0}) {
+  double n_w = nd.n_w, n_g = nd.n_g;
+  bool have0 = nd.have0;
   double var = p.alpha[0] * (v * v) + p.alpha[1] * (w * w);
   if (var > 0.0) {
     double n_v, unused;
@@ -105,7 +123,7 @@ __device__ __forceinline__ void noisy_pose_motion_step(double& x, double& y, dou
   }
   var = p.alpha[2] * (v * v) + p.alpha[3] * (w * w);
   if (var > 0.0) {
-    philox_normals(p.seed, env, step, 0u, n_w, n_g);
+    if (!have0) philox_normals(p.seed, env, step, 0u, n_w, n_g);
     have0 = true;
     w = w + sqrt(var) * n_w;
   }
@@ -142,7 +160,7 @@ __device__ __forceinline__ void measured_velocity(double x0, double y0, double t
 // TricycleRobot.step (robot_models/tricycle_model.py:478-538) / DiffDriveRobot.step
 // (robot_models/differential_drive.py:236-265).  s[7] = x,y,th,v,w,steer_cmd,wheel, updated in place.
 __device__ __forceinline__ void robot_step(double s[7], double u0, double u1, const BcgParams& p, uint64_t env,
-                                           uint64_t step) {
+                                           uint64_t step, NoiseDraws nd = NoiseDraws{false, 0.0, 0.0}) {
   const double x0 = s[0], y0 = s[1], th0 = s[2];
   double v_new, w_new;
   if (p.robot_kind == BCG_ROBOT_TRICYCLE) {
@@ -169,7 +187,7 @@ __device__ __forceinline__ void robot_step(double s[7], double u0, double u1, co
   }
   double x = x0, y = y0, th = th0;
   if (p.noise_on)
-    noisy_pose_motion_step(x, y, th, v_new, w_new, p, env, step);
+    noisy_pose_motion_step(x, y, th, v_new, w_new, p, env, step, nd);
   else
     pose_motion_step(x, y, th, v_new, w_new, p.dt);
   measured_velocity(x0, y0, th0, x, y, th, p.dt, s[3], s[4]);

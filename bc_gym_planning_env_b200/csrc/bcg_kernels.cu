@@ -872,6 +872,9 @@ move_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L, const v
 #pragma unroll
   for (int r = 0; r < 7; ++r) s[r] = sf[(BCG_F_ROBOT + r) * N];
   const int map_id = b.map_id[e], path_id = b.path_id[e];
+  // the step's normal draws depend on (seed, env, step) alone: Philox + Box-Muller run under the loads above instead of in
+  // the middle of the kinematic chain
+  const NoiseDraws noise = draw_noise_ahead(p, p.env_id_base + (uint64_t)e, step_index);
   const double time = sf[BCG_F_TIME * N] + p.dt;
   const int target = si[BCG_I_TARGET * N];
   const int collided = si[BCG_I_COLLIDED * N], iter = si[BCG_I_ITER * N];
@@ -894,7 +897,7 @@ move_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L, const v
     delay_line<2>(sf + (int64_t)L.ring_control * N, N, q, p.delay_control, u);
     si[BCG_I_QC * N] = q;
   }
-  robot_step(s, u[0], u[1], p, p.env_id_base + (uint64_t)e, step_index);
+  robot_step(s, u[0], u[1], p, p.env_id_base + (uint64_t)e, step_index, noise);
   if (b.cand) {                                          // the proposed pose, for the stand-alone collision entry points
 #pragma unroll
     for (int r = 0; r < 3; ++r) b.cand[r * N + e] = s[r];
@@ -3161,15 +3164,58 @@ static int launch_ego_dense(const BcgParams* p, const BcgBatch* b, uint8_t* ego_
 }
 
 // sparse scatter kernel for every env, then the dense kernel for the envs it handed over (usually none)
+// BCG_EGO_KERNEL=cta renders with round 1's CTA-per-env scatter kernel (ego_sparse_kernel) instead of ego_warp_kernel (A/B)
+static bool ego_cta_kernel_requested() {
+  static const bool cta = [] {
+    const char* v = getenv("BCG_EGO_KERNEL");
+    return v && strcmp(v, "cta") == 0;
+  }();
+  return cta;
+}
+
 struct EgoHits {       // BcgStepOut.ego_hits / ego_hit_count / ego_hit_cap (all zero: no compact output)
   uint32_t* list;
   int32_t* count;
   int cap;
 };
 
+template <bool SUM, bool HITS>
+static int launch_ego_warp_t(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, const EgoHits& hits, int sms, cudaStream_t s) {
+  const int tab_bytes = BCG_EGW_WARPS * (p->ego_w + p->ego_h) * (int)sizeof(int2);
+  static int per_sm_cache[64] = {0}, tab_cache[64] = {0};      // per template instance and device
+  int dev = 0;
+  BCG_CHECK_CUDA(cudaGetDevice(&dev));
+  int per_sm = 0;
+  if (dev >= 0 && dev < 64 && per_sm_cache[dev] > 0 && tab_cache[dev] == tab_bytes) {
+    per_sm = per_sm_cache[dev];
+  } else {
+    BCG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ego_warp_kernel<SUM, HITS>, BCG_EGW_WARPS * 32, tab_bytes));
+    BCG_REQUIRE(per_sm > 0, "the egocentric scatter kernel does not fit an SM with this crop size");
+    if (dev >= 0 && dev < 64) {
+      per_sm_cache[dev] = per_sm;
+      tab_cache[dev] = tab_bytes;
+    }
+  }
+  // persistent warps, each drawing envs from the global counter: no more warps than envs (a warp's first draw is 4 envs)
+  const int want = (b->n_envs + 4 * BCG_EGW_WARPS - 1) / (4 * BCG_EGW_WARPS);
+  const int grid = want < per_sm * sms ? (want > 0 ? want : 1) : per_sm * sms;
+  ego_warp_kernel<SUM, HITS><<<grid, BCG_EGW_WARPS * 32, tab_bytes, s>>>(*p, *b, ego_image, hits.list, hits.count, hits.cap);
+  BCG_CHECK_CUDA(cudaGetLastError());
+  return BCG_OK;
+}
+
 static int launch_ego_sparse(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, const EgoHits& hits, cudaStream_t s) {
   int sms = 0;
   if (int rc = sm_count_of_current_device(&sms)) return rc;
+  if (!ego_cta_kernel_requested()) {
+    const bool sum = b->occ_sum_arena != nullptr;
+    int rc;
+    if (hits.list) rc = sum ? launch_ego_warp_t<true, true>(p, b, ego_image, hits, sms, s) : launch_ego_warp_t<false, true>(p, b, ego_image, hits, sms, s);
+    else rc = sum ? launch_ego_warp_t<true, false>(p, b, ego_image, hits, sms, s) : launch_ego_warp_t<false, false>(p, b, ego_image, hits, sms, s);
+    if (rc) return rc;
+    if (b->flags & BCG_BATCH_SPARSE_EGO_ONLY) return BCG_OK;     // the scatter kernel rendered every env itself
+    return launch_ego_dense(p, b, ego_image, b->ego_list, s);
+  }
   // (the hand-over count and the env counter in ego_list[n_envs ..] were zeroed by the state / prep kernel)
   // persistent CTAs, as many per SM as fit with this crop's tables (18 for the 117 x 133 crop)
   const int tab_bytes = (p->ego_w + p->ego_h) * (int)sizeof(int2);
