@@ -51,7 +51,7 @@ class BcgFootprintLut(C.Structure):
         ("edges", C.c_void_p), ("verts", C.c_void_p), ("header", C.c_void_p), ("rows", C.c_void_p),
         ("fp_pix", C.c_void_p), ("bucket_first", C.c_void_p), ("bucket_scale", C.c_double),
         ("n_bins", C.c_int32), ("n_verts", C.c_int32), ("max_rows", C.c_int32), ("wpr", C.c_int32),
-        ("n_buckets", C.c_int32), ("reserved", C.c_int32),
+        ("n_buckets", C.c_int32), ("bin_stride", C.c_int32), ("bins", C.c_void_p),
     ]
 
 

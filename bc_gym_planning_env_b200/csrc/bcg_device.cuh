@@ -230,6 +230,36 @@ __device__ __forceinline__ void delay_line(double* ring, int64_t stride, int& q,
   q = head | (len << 16);
 }
 
+// delay_line in two halves, so that the loads can be issued at the top of a kernel (they depend on the queue word alone)
+// and the stores where the new element is known: delay_front reads the element delay_push will hand back.
+template <int NCOMP>
+__device__ __forceinline__ void delay_front(const double* ring, int64_t stride, int q, int d, double front[NCOMP]) {
+  if (d <= 0) return;
+  const int head = q & 0xffff, len = q >> 16;
+  if (len == 0) return;                     // warm-up with an empty queue: the element itself comes back
+#pragma unroll
+  for (int c = 0; c < NCOMP; ++c) front[c] = ring[(int64_t)(head * NCOMP + c) * stride];
+}
+template <int NCOMP>
+__device__ __forceinline__ void delay_push(double* ring, int64_t stride, int& q, int d, double v[NCOMP], const double front[NCOMP]) {
+  if (d <= 0) return;
+  int head = q & 0xffff, len = q >> 16;
+  int slot = head;
+  if (len < d) {
+    slot = head + len;
+    if (slot >= d) slot -= d;
+  }
+#pragma unroll
+  for (int c = 0; c < NCOMP; ++c) ring[(int64_t)(slot * NCOMP + c) * stride] = v[c];
+  if (len > 0) {
+#pragma unroll
+    for (int c = 0; c < NCOMP; ++c) v[c] = front[c];
+  }
+  if (len < d) ++len;
+  else head = (head + 1 == d) ? 0 : head + 1;
+  q = head | (len << 16);
+}
+
 // What delay_line would hand back for `v`, without touching the ring
 template <int NCOMP>
 __device__ __forceinline__ void delay_peek(const double* ring, int64_t stride, int q, int d, double v[NCOMP]) {
@@ -260,25 +290,11 @@ struct __align__(16) WorkCollide {   // 80 bytes
 };
 static_assert(sizeof(WorkCollide) == 80, "WorkCollide is 80 bytes");
 
-struct __align__(16) WorkReward {    // 96 bytes
-  double cand[3];                    // pose proposed by the kinematic step
-  double old_pose[3];                // pose to fall back to on a collision (env.py:458-459)
-  double ring_front[3];              // front of the pose delay queue (valid when from_ring)
-  double min_dist;
-  int32_t target, from_ring;
-  int32_t collided;                  // sticky collision flag before this step
-  int32_t goal_before;               // pure pursuit: was the observed pose already within 1 m of the goal
-};
-
-#define BCG_WORK_BYTES 192           // WorkCollide at +0, WorkReward at +80
+#define BCG_WORK_BYTES 192           // per-env scratch slot: WorkCollide (stand-alone collision) or the step's StepRecord at +0
 
 __device__ __forceinline__ const WorkCollide* work_collide(const void* work, int e) {
   return reinterpret_cast<const WorkCollide*>(reinterpret_cast<const uint8_t*>(work) + (int64_t)e * BCG_WORK_BYTES);
 }
-__device__ __forceinline__ const WorkReward* work_reward(const void* work, int e) {
-  return reinterpret_cast<const WorkReward*>(reinterpret_cast<const uint8_t*>(work) + (int64_t)e * BCG_WORK_BYTES + 80);
-}
-
 // Per-thread.  Picks the angle bin whose stored rounded-vertex tuple equals
 // round_half_even(R(th) * footprint / res) (utilities/path_tools.py:140-150), i.e. the bin whose
 // cv2.fillPoly mask the reference would have rasterised for this exact angle.  A uniform bucket table
@@ -330,6 +346,55 @@ __device__ __forceinline__ int find_foot_bin(const BcgFootprintLut& lut, double 
   return k;
 }
 
+// find_foot_bin + the bin's header in two memory round trips instead of five (bucket -> edges -> edges -> tuple -> header):
+// the bucket's first bin and its successor are fetched together from the combined table (`bins`: tuple + header per
+// 16-byte aligned row), the rounded vertex tuple of the angle is worked out once and compared with both.  An angle that
+// is in neither (two bin edges inside one of the 16 384 buckets, or a pose on an edge) takes the probing path above.
+__device__ __forceinline__ int find_foot_bin_header(const BcgFootprintLut& lut, double th, uint32_t* status, short4& header) {
+  if (lut.bins != nullptr && lut.n_verts == 16) {
+    double sn, cs;
+    sincos(th, &sn, &cs);
+    double t = th;
+    if (!(t >= -BCG_PI && t < BCG_PI)) t = wrap_angle(t);
+    int bk = (int)((t + BCG_PI) * lut.bucket_scale);
+    bk = min(max(bk, 0), lut.n_buckets - 1);
+    const int k0 = __ldg(lut.bucket_first + bk);
+    const int k1 = (k0 + 1 == lut.n_bins) ? 0 : k0 + 1;
+    const uint4* r0 = reinterpret_cast<const uint4*>(lut.bins + (int64_t)k0 * lut.bin_stride);
+    const uint4* r1 = reinterpret_cast<const uint4*>(lut.bins + (int64_t)k1 * lut.bin_stride);
+    uint4 q0[5], q1[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      q0[i] = __ldg(r0 + i);
+      q1[i] = __ldg(r1 + i);
+    }
+    bool ok0 = true, ok1 = true;
+#pragma unroll
+    for (int i4 = 0; i4 < 4; ++i4) {
+      const uint32_t a[4] = {q0[i4].x, q0[i4].y, q0[i4].z, q0[i4].w}, c[4] = {q1[i4].x, q1[i4].y, q1[i4].z, q1[i4].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = 4 * i4 + j;
+        const double fx = __ldg(lut.fp_pix + 2 * i), fy = __ldg(lut.fp_pix + 2 * i + 1);
+        const int vx = (int)rint(fma(fy, -sn, fx * cs));   // np.dot's fused form, see oracle
+        const int vy = (int)rint(fma(fy, cs, fx * sn));
+        const uint32_t want = ((uint32_t)vx & 0xffffu) | ((uint32_t)vy << 16);
+        const bool fits = vx >= -32768 && vx < 32768 && vy >= -32768 && vy < 32768;
+        ok0 = ok0 && fits && a[j] == want;
+        ok1 = ok1 && fits && c[j] == want;
+      }
+    }
+    if (ok0 || ok1) {
+      const uint4 h = ok0 ? q0[4] : q1[4];
+      header = make_short4((short)(h.x & 0xffffu), (short)(h.x >> 16), (short)(h.y & 0xffffu), (short)(h.y >> 16));
+      return ok0 ? k0 : k1;
+    }
+  }
+  const int bin = find_foot_bin(lut, th, status);
+  header = __ldg(reinterpret_cast<const short4*>(lut.header) + bin);
+  return bin;
+}
+
 __device__ __forceinline__ WorkCollide make_work_collide(const BcgParams& p, const BcgBatch& b, int map_id, int path_id,
                                                          double x, double y, double th) {
   const BcgMapDesc m = b.maps[map_id];
@@ -355,11 +420,6 @@ __device__ __forceinline__ WorkCollide make_work_collide(const BcgParams& p, con
   w.pad[0] = w.pad[1] = w.pad[2] = 0;
   return w;
 }
-
-// scratch int rows written by the collide/reward kernel for the commit kernel
-#define BCG_CI_TARGET 0
-#define BCG_CI_FLAGS 1 /* bit0 hit, bit1 goal after this step, bit2 goal before it */
-#define BCG_CI_ROWS 2
 
 // 32 mask bits starting at bit `rel` of a multi-word row mask (bit b <-> column xmin + b)
 __device__ __forceinline__ uint32_t mask_bits32(const uint64_t* row, int wpr, int rel) {
@@ -684,7 +744,8 @@ __device__ __forceinline__ int last_reached_group(const BcgParams& p, const Path
   return result;
 }
 
-// first_beyond_radius by a group of G lanes (see last_reached_group)
+// ContinuousRewardPurePursuitProviderState.update_goal (envs/base/reward.py:126-137): the first way point from `lo` on
+// that is more than `radius` from the pose, else the last point -- by a group of G lanes (see last_reached_group)
 template <int G>
 __device__ __forceinline__ int first_beyond_radius_group(const PathRef& pd, int lo, double px, double py, double radius,
                                                          unsigned lane, bool active) {
@@ -709,76 +770,6 @@ __device__ __forceinline__ int first_beyond_radius_group(const PathRef& pd, int 
     if (base >= pd.n) done = true;
   }
   return result;
-}
-
-// The same scan by ONE thread (state kernel): chunks from the far end down, culled by their bounding circles; the points of
-// a candidate chunk from the top down, two per 16-byte load, cheapest test (squared distance) first.  The first reached
-// point met is the largest reached index.  Same arithmetic as last_reached_from, so the same verdicts.
-__device__ __forceinline__ bool point_reached(const BcgParams& p, const double* __restrict__ P, int pitch, int i, double xi,
-                                              double yi, double px, double py, double pth, double sp2, double par_thr) {
-  const double dx = xi - px, dy = yi - py, d2 = dx * dx + dy * dy;
-  bool close = d2 < sp2 * (1.0 - 1e-12);
-  if (!close && d2 <= sp2 * (1.0 + 1e-12)) close = hypot(dx, dy) < p.spatial_precision;
-  if (!close) return false;
-  const double ti = __ldg(P + 2 * pitch + i), ci = __ldg(P + 3 * pitch + i), si = __ldg(P + 4 * pitch + i);
-  const double ang = fabs(wrap_angle(pth - ti));
-  const double par = ci * (px - xi) + si * (py - yi);
-  return (ang < p.angular_precision) && (par >= par_thr);
-}
-
-__device__ __forceinline__ int last_reached_thread(const BcgParams& p, const PathRef& pd, int lo, double px, double py,
-                                                   double pth) {
-  if (lo >= pd.n) return -1;
-  const double* __restrict__ P = pd.P;
-  const double* __restrict__ C = pd.C;
-  const double par_thr = -p.spatial_precision / 9;
-  const double sp2 = p.spatial_precision * p.spatial_precision;
-  const bool pairs = ((reinterpret_cast<uintptr_t>(P) & 15) == 0) && ((pd.pitch & 1) == 0);   // rows 16-byte aligned
-  for (int c = (pd.n - 1) >> 5; c >= (lo >> 5); --c) {
-    const double cx = __ldg(C + c) - px, cy = __ldg(C + pd.chunk_pitch + c) - py;
-    const double reach = p.spatial_precision + __ldg(C + 2 * pd.chunk_pitch + c);
-    if (!((cx * cx + cy * cy) < reach * reach * (1.0 + 1e-12))) continue;
-    const int i_hi = min(pd.n - 1, (c << 5) + 31), i_lo = max(lo, c << 5);
-    if (pairs) {
-      for (int j = i_hi >> 1; j >= (i_lo >> 1); --j) {
-        const double2 x2 = __ldg(reinterpret_cast<const double2*>(P) + j);
-        const double2 y2 = __ldg(reinterpret_cast<const double2*>(P + pd.pitch) + j);
-        const int i1 = 2 * j + 1, i0 = 2 * j;
-        if (i1 <= i_hi && point_reached(p, P, pd.pitch, i1, x2.y, y2.y, px, py, pth, sp2, par_thr)) return i1;
-        if (i0 >= i_lo && point_reached(p, P, pd.pitch, i0, x2.x, y2.x, px, py, pth, sp2, par_thr)) return i0;
-      }
-    } else {
-      for (int i = i_hi; i >= i_lo; --i)
-        if (point_reached(p, P, pd.pitch, i, __ldg(P + i), __ldg(P + pd.pitch + i), px, py, pth, sp2, par_thr)) return i;
-    }
-  }
-  return -1;
-}
-
-// first_beyond_radius by one thread
-__device__ __forceinline__ int first_beyond_radius_thread(const PathRef& pd, int lo, double px, double py, double radius) {
-  for (int i = max(lo, 0); i < pd.n; ++i) {
-    const double dx = __ldg(pd.P + i) - px, dy = __ldg(pd.P + pd.pitch + i) - py;
-    if (sqrt(fma(dy, dy, dx * dx)) > radius) return i;
-  }
-  return pd.n - 1;
-}
-
-// ContinuousRewardPurePursuitProviderState.update_goal (envs/base/reward.py:126-137): the first way point from
-// `lo` on that is more than `radius` from the pose, else the last point.  Warp-cooperative min-index scan.
-__device__ __forceinline__ int first_beyond_radius(const PathRef& pd, int lo, double px, double py, double radius,
-                                                   unsigned lane) {
-  for (int base = lo & ~31; base < pd.n; base += 32) {
-    const int i = base + lane;
-    bool far = false;
-    if (i >= lo && i < pd.n) {
-      const double dx = __ldg(pd.P + i) - px, dy = __ldg(pd.P + pd.pitch + i) - py;
-      far = sqrt(fma(dy, dy, dx * dx)) > radius;        // np.linalg.norm of a 2-vector = sqrt(ddot), fused like the BLAS
-    }
-    const unsigned bits = __ballot_sync(BCG_FULL, far);
-    if (bits) return base + __ffs(bits) - 1;
-  }
-  return pd.n - 1;
 }
 
 }  // namespace bcg

@@ -1,16 +1,16 @@
 // Kernels + C-ABI of the batched PlanEnv.step path for B200 (sm_100a).  See include/bcg_b200.h.
 //
-// One step = five launches on one stream (DESIGN.md has the rooflines and the measurements):
-//   kin_kernel             1 thread / env    -- control delay ring, robot model, Philox noise; writes the proposed state
-//                                               and the env's 192-byte work record (footprint bin, tile / path references)
-//   collide_reward_kernel  1 warp / env      -- footprint vs the 1-bit lethal tile plane (lane <-> footprint row), the pose
-//                                               the reward sees, chunk-culled reached-index scan, reward; read-only
-//   commit_kernel          2 threads / env   -- rollback, pose / state delay rings, done, episode statistics, auto-reset,
-//                                               compact observation, goal vector, the 256-byte egocentric record
+// One step = three launches on one stream (DESIGN.md has the rooflines and the measurements):
+//   move_kernel            1 thread / env    -- control delay ring, robot model, Philox noise, footprint lookup, collision
+//                                               on the 1-bit lethal tile plane (batched loads of the non-empty tiles under
+//                                               the footprint), rollback, pose / state delay rings, compact observation,
+//                                               the 128-byte egocentric record and the 144-byte record of
+//   reward_kernel          8 lanes / env     -- chunk-culled reached-index scan of the remaining path, reward, done, episode
+//                                               statistics, goal vector, the rare auto-reset
 //   ego_sparse_kernel      persistent, 64-thread CTAs x 18 per SM -- cv2.warpAffine(INTER_NEAREST)-exact egocentric crop as a
 //                                               scatter of the occupied cells of the source window
-//   ego_tiles_kernel       persistent, 256-thread CTAs -- the dense per-pixel gather, for the envs the sparse kernel hands
-//                                               over (filled regions) and for pools of dense maps
+//   (ego_tiles_kernel      persistent, 256-thread CTAs -- the dense per-pixel gather: pools of dense maps, and the envs
+//                                               the sparse kernel hands over when a batch mixes sparse and dense maps)
 // plus the set-up kernels (tile planes and summary, cell tiles, initial state), the device-side world generators and
 // the stand-alone entry points of the hook seam.
 // No tensor cores: nothing here is a dense contraction.
@@ -29,23 +29,10 @@
 #include "bcg_generate.cuh"
 
 using namespace bcg;
-// block sizes of the three state kernels (tunable: csrc/build.py build_variant)
+// block size of the stand-alone kinematics kernel (the step kernels have their own macros below)
 #ifndef BCG_KIN_THREADS
 #define BCG_KIN_THREADS 128
 #endif
-#ifndef BCG_COMMIT_THREADS
-#define BCG_COMMIT_THREADS 128
-#endif
-#ifndef BCG_COMMIT_MIN_BLOCKS
-#define BCG_COMMIT_MIN_BLOCKS 4      // register budget of commit_kernel: 65536 / (threads x blocks)
-#endif
-#ifndef BCG_CR_RESIDENT
-#define BCG_CR_RESIDENT 1280        // threads per SM the collide/reward kernel is compiled for (register budget)
-#endif
-#ifndef BCG_CR_THREADS
-#define BCG_CR_THREADS 64
-#endif
-
 namespace {
 
 thread_local std::string g_last_error;
@@ -98,9 +85,8 @@ int check_batch(const BcgParams* p, const BcgBatch* b) {
 
 // ---- kernels -------------------------------------------------------------------------------------
 
-// robot.step for every env: envs/base/env.py:371-373 (control delay) + robot model into b.cand, plus the
-// pixel / footprint-bin reference of the proposed pose for the collision kernel.  One thread per env:
-// every load and store is a coalesced SoA row access.
+// robot.step for every env (stand-alone bcg_kinematic_step): envs/base/env.py:371-373 (control delay) + robot model, the
+// proposed robot state into b.cand rows 0..6.  One thread per env: every load and store is a coalesced SoA row.
 __global__ void __launch_bounds__(BCG_KIN_THREADS) kin_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L,
                                                   const void* __restrict__ actions, const int action_is_f64,
                                                   const uint64_t step_index) {
@@ -120,33 +106,6 @@ __global__ void __launch_bounds__(BCG_KIN_THREADS) kin_kernel(const BcgParams p,
   double s[7];
 #pragma unroll
   for (int r = 0; r < 7; ++r) s[r] = b.state_f[(BCG_F_ROBOT + r) * N + e];
-  const int map_id = b.map_id[e], path_id = b.path_id[e];
-  // inputs of the reward the warp kernel will compute (read here: coalesced rows)
-  WorkReward wr;
-#pragma unroll
-  for (int r = 0; r < 3; ++r) wr.old_pose[r] = s[r];
-  wr.min_dist = b.state_f[BCG_F_MIN_DIST * N + e];
-  wr.target = b.state_i[BCG_I_TARGET * N + e];
-  wr.collided = b.state_i[BCG_I_COLLIDED * N + e];
-  wr.goal_before = 0;
-  if (p.reward_kind == BCG_REWARD_PURE_PURSUIT) {      // reward.py:139-149 on the pose observed before this step
-    const BcgPathDesc pdsc = b.paths[path_id];
-    const double* P = b.path_arena + pdsc.off;
-    const double gx = P[pdsc.n - 1], gy = P[pdsc.pitch + pdsc.n - 1];
-    wr.goal_before = hypot(gx - b.state_f[(BCG_F_DPOSE + 0) * N + e], gy - b.state_f[(BCG_F_DPOSE + 1) * N + e]) < 1.0;
-  }
-  wr.from_ring = 0;
-#pragma unroll
-  for (int r = 0; r < 3; ++r) wr.ring_front[r] = 0.0;
-  if (p.delay_pose > 0) {
-    const int qp = b.state_i[BCG_I_QP * N + e];
-    if ((qp >> 16) > 0) {                              // env.py:27-49: the front of a non-empty queue
-      wr.from_ring = 1;
-      const int head = qp & 0xffff;
-#pragma unroll
-      for (int r = 0; r < 3; ++r) wr.ring_front[r] = b.state_f[(int64_t)(L.ring_pose + head * 3 + r) * N + e];
-    }
-  }
   if (p.delay_control > 0) {
     int q = b.state_i[BCG_I_QC * N + e];
     delay_line<2>(b.state_f + (int64_t)L.ring_control * N + e, N, q, p.delay_control, u);
@@ -155,11 +114,6 @@ __global__ void __launch_bounds__(BCG_KIN_THREADS) kin_kernel(const BcgParams p,
   robot_step(s, u[0], u[1], p, p.env_id_base + (uint64_t)e, step_index);
 #pragma unroll
   for (int r = 0; r < 7; ++r) b.cand[r * N + e] = s[r];
-#pragma unroll
-  for (int r = 0; r < 3; ++r) wr.cand[r] = s[r];
-  uint8_t* rec = reinterpret_cast<uint8_t*>(b.work) + (int64_t)e * BCG_WORK_BYTES;
-  *reinterpret_cast<WorkCollide*>(rec) = make_work_collide(p, b, map_id, path_id, s[0], s[1], s[2]);
-  *reinterpret_cast<WorkReward*>(rec + 80) = wr;
 }
 
 // work records of arbitrary poses [3][n] (stand-alone collision entry points)
@@ -170,81 +124,6 @@ __global__ void __launch_bounds__(128) pose_prep_kernel(const BcgParams p, const
   const int64_t N = b.n_envs;
   uint8_t* rec = reinterpret_cast<uint8_t*>(b.work) + (int64_t)e * BCG_WORK_BYTES;
   *reinterpret_cast<WorkCollide*>(rec) = make_work_collide(p, b, b.map_id[e], b.path_id[e], poses[e], poses[N + e], poses[2 * N + e]);
-}
-
-// One warp per env: footprint-vs-lethal-tile collision of the proposed pose (env.py:455), then the
-// reward of the pose the reward provider will see (reward.py:214-259).  Reads only; its few results go
-// to the scratch rows, the thread-per-env commit kernel applies them.  No store precedes a load, so all
-// of a warp's independent loads are in flight together.
-__global__ void __launch_bounds__(BCG_CR_THREADS, BCG_CR_RESIDENT / BCG_CR_THREADS) collide_reward_kernel(const BcgParams p, const BcgBatch b) {
-  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const unsigned lane = threadIdx.x & 31;
-  if (e >= b.n_envs) return;
-  const int64_t N = b.n_envs;
-  // round 1: the env's two work records (a warp-uniform 160-byte read)
-  const WorkCollide wc = *work_collide(b.work, e);
-  const WorkReward wr = *work_reward(b.work, e);
-  PathRef pd;
-  pd.P = b.path_arena + wc.path_off;
-  pd.C = pd.P + 5 * (int64_t)wc.path_pitch;
-  pd.n = wc.path_n;
-  pd.pitch = wc.path_pitch;
-  pd.chunk_pitch = wc.chunk_pitch;
-  int target = wr.target;
-  double min_dist = wr.min_dist;
-  const bool pursuit = p.reward_kind == BCG_REWARD_PURE_PURSUIT;
-  const bool goal_before = pursuit ? (wr.goal_before != 0) : (target > pd.n - 1);
-  // round 2 (issued before the collision verdict is needed): the goal point the reward most likely uses
-  double gx = 0.0, gy = 0.0;
-  if (pursuit || !goal_before) {
-    const int gi = pursuit ? pd.n - 1 : target;
-    gx = __ldg(pd.P + gi);
-    gy = __ldg(pd.P + pd.pitch + gi);
-  }
-
-  const bool hit = collide_tiles<false>(b, wc, lane, nullptr);
-
-  // the pose State.pose will hold after this step: rolled back on a hit (env.py:458-459), delayed (:377-380)
-  double pose[3];
-#pragma unroll
-  for (int r = 0; r < 3; ++r) pose[r] = wr.from_ring ? wr.ring_front[r] : (hit ? wr.old_pose[r] : wr.cand[r]);
-
-  double reward = 0.0;
-  bool goal_after;
-  if (pursuit) {
-    // ContinuousRewardPurePursuitProvider.reward (reward.py:331-350)
-    target = first_beyond_radius(pd, target, pose[0], pose[1], 2.0, lane);
-    const double d = hypot(gx - pose[0], gy - pose[1]);
-    reward = -0.05;
-    reward += min_dist - d;
-    if (wr.collided || hit) reward -= 100;
-    min_dist = d;
-    goal_after = d < 1.0;
-  } else if (!goal_before) {
-    const int last = last_reached_from(p, pd, target, pose[0], pose[1], pose[2], lane);
-    if (last >= target) {
-      target = last + 1;
-      if (target > pd.n - 1) {
-        min_dist = 0.0;
-      } else {
-        min_dist = hypot(__ldg(pd.P + target) - pose[0], __ldg(pd.P + pd.pitch + target) - pose[1]);
-      }
-      reward = 1.0;
-    } else {
-      const double d = hypot(gx - pose[0], gy - pose[1]);
-      if (d < min_dist) {
-        reward = (min_dist - d) * p.progress_multiplier;
-        min_dist = d;
-      }
-    }
-  }
-  if (!pursuit) goal_after = target > pd.n - 1;
-  if (lane == 0) {
-    b.cand[7 * N + e] = reward;
-    b.cand[8 * N + e] = min_dist;
-    b.cand_i[BCG_CI_TARGET * N + e] = target;
-    b.cand_i[BCG_CI_FLAGS * N + e] = (hit ? 1 : 0) | (goal_after ? 2 : 0) | (goal_before ? 4 : 0);
-  }
 }
 
 // cv2::saturate_cast<int>(double) == cvRound with saturation
@@ -593,163 +472,6 @@ __device__ __forceinline__ void write_ego_record(const BcgParams& p, const BcgBa
   }
 }
 
-// Two threads per env, in different warps of one CTA (64 envs per 128-thread block).  Role 0: the rest of
-// _resolve_state_transition (env.py:363-398) -- rollback, pose and robot-state delay lines, time/iter, sticky collision
-// -- then done (env.py:407-419), episode statistics, auto-reset (env.py:293-303) and the compact fp32 observation.
-// Role 1: what the observation kernels need from the state being written -- the egocentric work record and
-// goal_n_state -- computed from the same inputs at the same time instead of after the writes: the kernel is bound by
-// the length of a thread's dependent chain, and this halves it.  Both roles read before anyone writes (one barrier).
-// All accesses are coalesced SoA rows.
-__global__ void __launch_bounds__(BCG_COMMIT_THREADS, BCG_COMMIT_MIN_BLOCKS) commit_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L,
-                                                     const BcgStepOut out, const int ego_cap) {
-  constexpr int EPB = BCG_COMMIT_THREADS / 2;              // envs per block
-  const int role = threadIdx.x / EPB;
-  const int e = blockIdx.x * EPB + (threadIdx.x - role * EPB);
-  const bool active = e < b.n_envs;
-  const int64_t N = b.n_envs;
-  double ev_ret = 0.0, ev_len = 0.0;
-  int ev = 0, ev_col = 0, ev_goal = 0, ev_to = 0;
-  // ---- phase 1 (both roles): everything that is read ------------------------------------------------------------------
-  double c[7], dpose[3], dstate[7];
-  double reward = 0.0, min_dist = 0.0, time = 0.0, ep_return = 0.0;
-  int target = 0, flags = 0, iter = 0, collided = 0, qp = 0, qs = 0;
-  double* sf = b.state_f + (active ? e : 0);
-  int32_t* si = b.state_i + (active ? e : 0);
-  if (active) {
-#pragma unroll
-    for (int r = 0; r < 7; ++r) c[r] = b.cand[r * N + e];
-    target = b.cand_i[BCG_CI_TARGET * N + e];
-    flags = b.cand_i[BCG_CI_FLAGS * N + e];
-    iter = si[BCG_I_ITER * N];
-    collided = si[BCG_I_COLLIDED * N];
-    qp = si[BCG_I_QP * N];
-    qs = si[BCG_I_QS * N];
-    if (role == 0) {
-      reward = b.cand[7 * N + e];
-      min_dist = b.cand[8 * N + e];
-      time = sf[BCG_F_TIME * N] + p.dt;
-      ep_return = sf[BCG_F_EP_RETURN * N] + reward;
-    }
-    if (flags & 1) {  // env.py:458-459 + tricycle_model.py:471-476: pose restored, v = w = 0, wheel/steer kept
-      c[0] = sf[(BCG_F_ROBOT + 0) * N];
-      c[1] = sf[(BCG_F_ROBOT + 1) * N];
-      c[2] = sf[(BCG_F_ROBOT + 2) * N];
-      c[3] = 0.0;
-      c[4] = 0.0;
-    }
-#pragma unroll
-    for (int r = 0; r < 3; ++r) dpose[r] = c[r];
-#pragma unroll
-    for (int r = 0; r < 7; ++r) dstate[r] = c[r];
-    if (role == 1) {                                       // role 0 reads the rings when it updates them
-      delay_peek<3>(sf + (int64_t)L.ring_pose * N, N, qp, p.delay_pose, dpose);
-      delay_peek<7>(sf + (int64_t)L.ring_state * N, N, qs, p.delay_state, dstate);
-    }
-  }
-  const bool hit = flags & 1, goal = flags & 2, goal_before = flags & 4;
-  const bool done_before = goal_before || (iter >= p.iteration_timeout) || (collided != 0);
-  const int iter_after = iter + 1;
-  const int collided_after = collided | (hit ? 1 : 0);
-  const bool timed_out = iter_after >= p.iteration_timeout;
-  const bool done = goal || timed_out || (collided_after != 0);
-  const bool reset_now = done && p.auto_reset;
-  if (active && role == 1 && reset_now && (out.ego_image || out.goal_n_state)) {     // the observation is the initial state's
-    target = b.init_i[(int64_t)BCG_I_TARGET * N + e];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) dpose[r] = b.init_f[(int64_t)(BCG_F_DPOSE + r) * N + e];
-#pragma unroll
-    for (int r = 0; r < 7; ++r) dstate[r] = b.init_f[(int64_t)(BCG_F_DROBOT + r) * N + e];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) c[r] = b.init_f[(int64_t)(BCG_F_ROBOT + r) * N + e];
-  }
-  __syncthreads();                                         // nothing of the state has been written yet
-  // ---- phase 2 -------------------------------------------------------------------------------------------------------
-  if (active && role == 0) {
-    if (e == 0 && b.ego_list) b.ego_list[N] = b.ego_list[N + 1] = 0;     // hand-over count, env counter of the sparse kernel
-    delay_line<3>(sf + (int64_t)L.ring_pose * N, N, qp, p.delay_pose, dpose);
-    delay_line<7>(sf + (int64_t)L.ring_state * N, N, qs, p.delay_state, dstate);
-    if (out.reward) out.reward[e] = reward;
-    if (out.done) out.done[e] = done ? 1 : 0;
-    if (out.hit) out.hit[e] = hit ? 1 : 0;
-    if (done && !done_before) {
-      ev = 1;
-      ev_ret = ep_return;
-      ev_len = (double)iter_after;
-      ev_col = collided_after;
-      ev_goal = goal ? 1 : 0;
-      ev_to = timed_out ? 1 : 0;
-    }
-    float ov[12];
-    if (reset_now) {
-      for (int r = 0; r < L.n_frows; ++r) sf[(int64_t)r * N] = b.init_f[(int64_t)r * N + e];
-      for (int r = 0; r < L.n_irows; ++r) si[(int64_t)r * N] = b.init_i[(int64_t)r * N + e];
-      if (out.obs_vec) {
-#pragma unroll
-        for (int r = 0; r < 3; ++r) ov[r] = (float)b.init_f[(int64_t)(BCG_F_DPOSE + r) * N + e];
-#pragma unroll
-        for (int r = 0; r < 7; ++r) ov[3 + r] = (float)b.init_f[(int64_t)(BCG_F_DROBOT + r) * N + e];
-        ov[10] = (float)b.init_f[(int64_t)BCG_F_TIME * N + e];
-        ov[11] = (float)b.init_i[(int64_t)BCG_I_TARGET * N + e];
-      }
-    } else {
-#pragma unroll
-      for (int r = 0; r < 7; ++r) sf[(BCG_F_ROBOT + r) * N] = c[r];
-#pragma unroll
-      for (int r = 0; r < 7; ++r) sf[(BCG_F_DROBOT + r) * N] = dstate[r];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) sf[(BCG_F_DPOSE + r) * N] = dpose[r];
-      sf[BCG_F_TIME * N] = time;
-      sf[BCG_F_MIN_DIST * N] = min_dist;
-      sf[BCG_F_EP_RETURN * N] = ep_return;
-      si[BCG_I_ITER * N] = iter_after;
-      si[BCG_I_TARGET * N] = target;
-      si[BCG_I_COLLIDED * N] = collided_after;
-      si[BCG_I_QP * N] = qp;
-      si[BCG_I_QS * N] = qs;
-#pragma unroll
-      for (int r = 0; r < 3; ++r) ov[r] = (float)dpose[r];
-#pragma unroll
-      for (int r = 0; r < 7; ++r) ov[3 + r] = (float)dstate[r];
-      ov[10] = (float)time;
-      ov[11] = (float)target;
-    }
-    if (out.obs_vec) {
-      float4* o = reinterpret_cast<float4*>(out.obs_vec + (int64_t)e * 12);
-      o[0] = make_float4(ov[0], ov[1], ov[2], ov[3]);
-      o[1] = make_float4(ov[4], ov[5], ov[6], ov[7]);
-      o[2] = make_float4(ov[8], ov[9], ov[10], ov[11]);
-    }
-  }
-  if (active && role == 1 && (out.ego_image || out.goal_n_state)) {
-    // the observation the egocentric kernel will render is that of the state role 0 is writing: resolve its affine
-    // map, source window and goal vector from the same values
-    const bool true_pose = p.ego_variant == 1;             // true robot pose vs observed (delayed) pose
-    const double opx = true_pose ? c[0] : dpose[0], opy = true_pose ? c[1] : dpose[1], opth = true_pose ? c[2] : dpose[2];
-    if (out.ego_image) {
-      const int map_id = b.map_id[e];
-      write_ego_record(p, b, e, map_id, b.maps[map_id], opx, opy, opth, ego_cap);
-    }
-    if (out.goal_n_state) write_goal_n_state(p, b, e, b.paths[b.path_id[e]], opx, opy, opth, target, dstate, out.goal_n_state);
-  }
-  // episode statistics: one atomic set per warp that saw an episode end
-  if (__any_sync(BCG_FULL, ev != 0)) {
-    double v[6] = {(double)ev, ev_ret, ev_len, (double)ev_col, (double)ev_goal, (double)ev_to};
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(BCG_FULL, v[k], o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-      atomicAdd(b.stats + BCG_STAT_EPISODES, v[0]);
-      atomicAdd(b.stats + BCG_STAT_RETURN, v[1]);
-      atomicAdd(b.stats + BCG_STAT_LENGTH, v[2]);
-      atomicAdd(b.stats + BCG_STAT_COLLIDED, v[3]);
-      atomicAdd(b.stats + BCG_STAT_GOAL, v[4]);
-      atomicAdd(b.stats + BCG_STAT_TIMEOUT, v[5]);
-    }
-  }
-}
-
 // ---- the two state kernels of a step --------------------------------------------------------------------------------
 // PlanEnv.step (envs/base/env.py:334-361) up to the observation is two launches, split by the shape of the work:
 //
@@ -879,6 +601,10 @@ move_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L, const v
   const int target = si[BCG_I_TARGET * N];
   const int collided = si[BCG_I_COLLIDED * N], iter = si[BCG_I_ITER * N];
   int qp = si[BCG_I_QP * N], qs = si[BCG_I_QS * N];
+  // the fronts of the pose and robot-state queues (what the delay lines will hand back): loaded here, a round trip early
+  double pose_front[3], state_front[7];
+  delay_front<3>(sf + (int64_t)L.ring_pose * N, N, qp, p.delay_pose, pose_front);
+  delay_front<7>(sf + (int64_t)L.ring_state * N, N, qs, p.delay_state, state_front);
   StepRecord rec;
   rec.min_dist = sf[BCG_F_MIN_DIST * N];
   rec.ep_return = sf[BCG_F_EP_RETURN * N];
@@ -904,9 +630,9 @@ move_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L, const v
   }
   // ---- env.py:455 pose_collides of the proposed pose --------------------------------------------------------------------------
   FootBox fb;
-  fb.bin = find_foot_bin(b.lut, s[2], b.status);
   {
-    const short4 h = __ldg(reinterpret_cast<const short4*>(b.lut.header) + fb.bin);     // xmin, ymin, nrows, width
+    short4 h;                                            // xmin, ymin, nrows, width
+    fb.bin = find_foot_bin_header(b.lut, s[2], b.status, h);
     fb.X0 = world_to_pixel_1d(s[0], m.origin_x, p.inv_resolution) + h.x;
     fb.Y0 = world_to_pixel_1d(s[1], m.origin_y, p.inv_resolution) + h.y;
     fb.nrows = h.z;
@@ -926,8 +652,8 @@ move_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L, const v
   double dstate[7];
 #pragma unroll
   for (int r = 0; r < 7; ++r) dstate[r] = s[r];
-  delay_line<3>(sf + (int64_t)L.ring_pose * N, N, qp, p.delay_pose, dpose);
-  delay_line<7>(sf + (int64_t)L.ring_state * N, N, qs, p.delay_state, dstate);
+  delay_push<3>(sf + (int64_t)L.ring_pose * N, N, qp, p.delay_pose, dpose, pose_front);
+  delay_push<7>(sf + (int64_t)L.ring_state * N, N, qs, p.delay_state, dstate, state_front);
   // ---- env.py:383-393: the state rows that do not depend on the reward (reward_kernel writes target, min_dist, return) ---
   const int iter_after = iter + 1;
   const int collided_after = collided | (hit ? 1 : 0);
@@ -2404,384 +2130,6 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
   }
 }
 
-// ---- ego_warp_kernel: the same scatter, one WARP per env ------------------------------------------------------------
-// ego_sparse_kernel gives an env to a 64-thread CTA: per env its two warps meet at two barriers (8 % of the stall samples),
-// both build the window's tile list, and ~950 of its 2 700 warp instructions per env are per-env fixed cost that is paid
-// per warp (profiles/r2_notes.md).  Here a warp owns an env from the record to the last byte: no barrier (only
-// __syncwarp), nothing computed twice, its own shared-memory context (cell list as 16-bit entries, piece queue, tile
-// list, tile spans, record ring, crop tables), its own draws from the global env counter.  A CTA is just a container of
-// BCG_EGW_WARPS such warps that share one page of zeros for the bulk stores.
-#ifndef BCG_EGW_WARPS
-#define BCG_EGW_WARPS 4
-#endif
-#ifndef BCG_EGW_CTAS
-#define BCG_EGW_CTAS 8               // register budget (launch bound): 65536 / (128 x 8) = 64; the launch asks the occupancy calculator
-#endif
-#ifndef BCG_EGW_ROUNDS
-#define BCG_EGW_ROUNDS 4             // rounds of 8 non-empty tiles whose occupancy words a warp loads per pass
-#endif
-struct __align__(16) EgwCtx {
-  uint4 qword[BCG_EGS_QCAP];                    // queued non-empty 16-byte occupancy pieces
-  uint8_t rec[BCG_EGS_REC_SLOTS * BCG_EGO_WORK_BYTES];   // record ring
-  uint32_t qtag[BCG_EGS_QCAP];
-  uint16_t list[BCG_EGS_LIST];                  // occupied window cells: y_rel << 8 | x_rel (windows of <= 256 x 256 cells)
-  uint16_t tlist[BCG_EGS_MAX_TILES];            // non-empty tiles of the window
-  uint16_t span[BCG_EGT_MAX_TILE_ROWS];         // tile spans of the window's rows (ego_band_span)
-  uint32_t count, hits;
-  int32_t ids[8];                               // envs drawn from the global counter, RD + 1 iterations ahead
-};
-
-template <bool SUM, bool HITS>
-__global__ void __launch_bounds__(BCG_EGW_WARPS * 32, BCG_EGW_CTAS) ego_warp_kernel(const BcgParams p, const BcgBatch b,
-                                                                                   uint8_t* __restrict__ image,
-                                                                                   uint32_t* __restrict__ hit_list,
-                                                                                   int32_t* __restrict__ hit_count,
-                                                                                   const int hit_cap) {
-  __shared__ __align__(128) uint8_t zero_s[BCG_EGS_ZERO_BYTES];
-  __shared__ EgwCtx ctx_s[BCG_EGW_WARPS];
-  extern __shared__ __align__(16) int2 egw_tab[];          // per warp: adxy[ego_w], bxy[ego_h]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ego_w = p.ego_w, ego_h = p.ego_h, npx = ego_w * ego_h;
-  EgwCtx& T = ctx_s[warp];
-  int2* const tab = egw_tab + warp * (ego_w + ego_h);
-  const uint32_t qword_u32 = smem_u32(T.qword), qtag_u32 = smem_u32(T.qtag), tlist_u32 = smem_u32(T.tlist);
-  const uint32_t zero_u32 = smem_u32(zero_s), rec_u32 = smem_u32(T.rec), list_u32 = smem_u32(T.list), span_u32 = smem_u32(T.span);
-  const uint32_t adxy_u32 = smem_u32(tab), bxy_u32 = adxy_u32 + 8u * (uint32_t)ego_w;
-  const uint8_t* const recs = reinterpret_cast<const uint8_t*>(b.ego_work);
-  const int n = b.n_envs;
-  constexpr int RD = 3;
-  static_assert(RD < BCG_EGS_REC_SLOTS, "record ring too small");
-
-  for (int i = tid * 16; i < BCG_EGS_ZERO_BYTES; i += BCG_EGW_WARPS * 32 * 16) *reinterpret_cast<uint4*>(zero_s + i) = make_uint4(0u, 0u, 0u, 0u);
-  fence_async_smem();                         // the zeros are visible to the bulk-copy engine
-  __syncthreads();                            // (the only CTA-wide barrier: from here on the warps are on their own)
-
-  auto fetch_record = [&](int en, int slot) {
-    if (en < n && lane < BCG_EGO_WORK_BYTES / 16)
-      cp_async_16(rec_u32 + slot * BCG_EGO_WORK_BYTES + lane * 16, recs + (int64_t)en * BCG_EGO_WORK_BYTES + lane * 16, 16u);
-  };
-  auto summary_words = [&](const EgoTileWork* q, uint32_t& lo, uint32_t& hi) {
-    lo = hi = 0u;
-    if (q->mode != BCG_EGO_MODE_TILES || (q->dense_map & 1)) return;
-    const int qby0 = q->Y0 >> 4, qnby = ((q->Y0 + 8 * q->nty - 1) >> 4) - qby0 + 1;
-    const int qtx = (int)(q->tiles_xy & 0xffffu), qty = (int)(q->tiles_xy >> 16), sw = (qtx + 31) >> 5;
-    const int ty = qby0 + lane, w0 = q->X0 >> 10;                            // X0 >> 5 may be negative: w0 = -1
-    if (lane < qnby && (unsigned)ty < (unsigned)qty) {
-      const uint32_t* const srow = b.occ_sum_arena + q->sum_off + ty * sw;
-      if ((unsigned)w0 < (unsigned)sw) lo = __ldg(srow + w0);
-      if ((unsigned)(w0 + 1) < (unsigned)sw) hi = __ldg(srow + w0 + 1);
-    }
-  };
-  // the warp's first RD + 1 envs, drawn from the global counter (ego_list[n + 1], zeroed by the state / prep kernel)
-  {
-    int first = 0;
-    if (lane == 0) first = atomicAdd(b.ego_list + n + 1, RD + 1);
-    first = __shfl_sync(BCG_FULL, first, 0);
-    if (lane <= RD) T.ids[lane] = first + lane;
-    if (first >= n) return;
-#pragma unroll
-    for (int k = 0; k < RD; ++k) fetch_record(first + k, k);
-    cp_async_commit();
-    cp_async_wait_all();
-    __syncwarp();
-  }
-  uint32_t pf_lo = 0u, pf_hi = 0u;              // summary words of the env about to be rendered
-  if (SUM) summary_words(reinterpret_cast<const EgoTileWork*>(T.rec), pf_lo, pf_hi);
-  for (int it = 0;; ++it) {
-    const int e = T.ids[it & 7];
-    if (e >= n) break;
-    int drawn = 0;
-    if (lane == 0) {
-      drawn = atomicAdd(b.ego_list + n + 1, 1);           // stored at the end of the iteration
-      T.count = 0u;
-      T.hits = 0u;
-    }
-    const int slot = it & (BCG_EGS_REC_SLOTS - 1);
-    fetch_record(T.ids[(it + RD) & 7], (it + RD) & (BCG_EGS_REC_SLOTS - 1));
-    cp_async_commit();
-    const int e_next = T.ids[(it + 1) & 7];
-    // record it + 1 has landed (only the newest fetch may still be in flight): start its summary loads now
-    const uint32_t cur_lo = pf_lo, cur_hi = pf_hi;
-    if (SUM && e_next < n)
-      summary_words(reinterpret_cast<const EgoTileWork*>(T.rec + ((it + 1) & (BCG_EGS_REC_SLOTS - 1)) * BCG_EGO_WORK_BYTES), pf_lo, pf_hi);
-    const EgoTileWork* r = reinterpret_cast<const EgoTileWork*>(T.rec + slot * BCG_EGO_WORK_BYTES);
-    const int mode = r->mode, X0 = r->X0, Y0 = r->Y0, ntx = r->ntx, nty = r->nty;
-    uint8_t* const dst = image + (int64_t)e * npx;
-    const int wx0 = X0 >> 5, nwx = ((X0 + 16 * ntx - 1) >> 5) - wx0 + 1;        // <= 9 columns of 32-cell words
-    const int by0 = Y0 >> 4, nby = ((Y0 + 8 * nty - 1) >> 4) - by0 + 1;         // bands of 16 rows
-    const int ntile = nby * nwx;
-    const bool dense_map = (r->dense_map & 1) != 0;     // decided by the record writer, which holds the map descriptor
-    // (nty <= 32: window rows fit the 8 bits of a list entry, and one lane per tile row)
-    const bool try_sparse = mode == BCG_EGO_MODE_TILES && ntile <= BCG_EGS_MAX_TILES && !dense_map && nty <= 32 &&
-                            (!SUM || (nby <= 32 && nwx <= 32));
-    __syncwarp();                               // the counters are zero for everyone
-    if (try_sparse) {
-      // ---- 1. zero the crop in global memory ----------------------------------------------------------------------
-      {
-        const int head = min((int)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u), npx);
-        const int body = (npx - head) & ~15, tail = npx - head - body;
-        if (lane == 0) {
-          for (int o = 0; o < body; o += BCG_EGS_ZERO_BYTES)
-            bulk_store(dst + head + o, zero_u32, (uint32_t)min(body - o, BCG_EGS_ZERO_BYTES));
-          bulk_commit();
-        }
-        if (lane < head) dst[lane] = 0;
-        if (lane >= 16 && lane - 16 < tail) dst[head + body + lane - 16] = 0;
-      }
-      const int tiles_x = (int)(r->tiles_xy & 0xffffu), tiles_y = (int)(r->tiles_xy >> 16);
-      const uint4* occ = reinterpret_cast<const uint4*>(b.occ_tile_arena + ((int64_t)r->tile_off16 << 4));
-      const int g = lane & 3;                                                     // rows 4 g .. 4 g + 3 of the tile
-      constexpr int TPR = 8;                                                      // tiles per round
-      auto expand = [&](const uint32_t qhead, const int nitems) {
-        uint4 wd = make_uint4(0u, 0u, 0u, 0u);
-        uint32_t tag = 0u;
-        if (lane < nitems) {
-          const uint32_t at = (qhead + (uint32_t)lane) & (BCG_EGS_QCAP - 1);
-          wd = lds_v4(qword_u32 + 16u * at);
-          tag = lds_u32(qtag_u32 + 4u * at);
-        }
-        __syncwarp();                                                            // ring slots are free again
-        const int band = (int)(tag >> 8), jw = (int)((tag >> 2) & 63u), gq = (int)(tag & 3u);
-        const int tx = wx0 + jw;
-        const int yr0 = (((by0 + band) << 4) + 4 * gq) - Y0;                      // window row of word .x; 4 | yr0
-        uint32_t bits[4] = {wd.x, wd.y, wd.z, wd.w};
-        uint32_t keep = 0u;
-        if (yr0 >= 0 && yr0 < 8 * nty) {                                          // clip to the tile span of these rows
-          const uint32_t sp = lds_u16(span_u32 + 2 * (yr0 >> 3));
-          const int lo = max(X0 + 16 * (int)(sp & 0xff) - (tx << 5), 0);
-          const int hi = min(X0 + 16 * (int)(sp >> 8) + 15 - (tx << 5), 31);
-          if (lo <= hi) keep = (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
-        }
-        int cnt = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          bits[k] &= keep;
-          cnt += __popc(bits[k]);
-        }
-        // list slots: inclusive warp scan of the counts (the warp owns the list: no atomic)
-        int incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int v = __shfl_up_sync(BCG_FULL, incl, d);
-          if (lane >= d) incl += v;
-        }
-        const int total = __shfl_sync(BCG_FULL, incl, 31);
-        if (total == 0) return;
-        const uint32_t base0 = T.count;
-        __syncwarp();
-        if (lane == 31) T.count = base0 + (uint32_t)total;
-        const uint32_t base = base0 + (uint32_t)(incl - cnt);
-        if (cnt == 0 || base + (uint32_t)cnt > BCG_EGS_LIST) return;              // overflow: see below
-        uint32_t at = list_u32 + 2u * base;
-        const int key = (yr0 << 8) + ((tx << 5) - X0);           // x_rel of bit 0 may be negative, of a kept bit never
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint32_t w = bits[k];
-          while (w) {
-            const int bit = 31 - __clz(w);                       // order within the list is irrelevant
-            w ^= 1u << bit;
-            sts_u16(at, (uint32_t)(key + (k << 8) + bit));
-            at += 2u;
-          }
-        }
-      };
-      const uint32_t lt_mask = (1u << lane) - 1u;
-      uint32_t qhead = 0u, qtail = 0u;
-      auto push = [&](const uint4& w, const uint32_t tag) {
-        const bool nz = (w.x | w.y | w.z | w.w) != 0u;
-        const uint32_t bal = __ballot_sync(BCG_FULL, nz);
-        if (bal == 0u) return;                                                    // free space
-        if (nz) {
-          const uint32_t at = (qtail + (uint32_t)__popc(bal & lt_mask)) & (BCG_EGS_QCAP - 1);
-          sts_v4(qword_u32 + 16u * at, w);
-          sts_u32(qtag_u32 + 4u * at, tag);
-        }
-        qtail += (uint32_t)__popc(bal);
-        if (qtail - qhead >= 32u) {
-          __syncwarp();
-          expand(qhead, 32);
-          qhead += 32u;
-        }
-      };
-      // the crop's tile spans (lane <-> tile row) and fixed-point tables: worked out while the first occupancy loads fly
-      auto spans_and_tables = [&]() {
-        if (lane < nty) sts_u16(span_u32 + 2u * (uint32_t)lane, ego_band_span(r->aff, ego_w, ego_h, X0, Y0, ntx, nty, lane));
-        const EgoAffine A = r->aff;
-        for (int i = lane; i < ego_w + ego_h; i += 32) {
-          if (i < ego_w) {
-            tab[i] = make_int2(__double2int_rn(A.a11 * i * 1024), __double2int_rn(A.a21 * i * 1024));
-          } else {
-            const int t = i - ego_w;
-            tab[i] = make_int2(__double2int_rn((A.a12 * t + A.b1) * 1024) + 512 - (X0 << 10),
-                               __double2int_rn((A.a22 * t + A.b2) * 1024) + 512 - (Y0 << 10));
-          }
-        }
-        __syncwarp();
-      };
-      if constexpr (SUM) {
-        // (a) which tiles of the window hold a cell at all: lane <-> band of 16 rows (summary words loaded one env ahead)
-        const uint32_t tmask = (uint32_t)((((uint64_t)cur_hi << 32) | cur_lo) >> (wx0 & 31)) & ((1u << nwx) - 1u);
-        // (b) the list of those tiles (band << 6 | column), in band order: inclusive warp scan of the per-band counts
-        int tincl = __popc(tmask);
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int v = __shfl_up_sync(BCG_FULL, tincl, d);
-          if (lane >= d) tincl += v;
-        }
-        const int ntl = __shfl_sync(BCG_FULL, tincl, 31);                         // <= ntile <= BCG_EGS_MAX_TILES
-        {
-          uint32_t at = tlist_u32 + 2u * (uint32_t)(tincl - __popc(tmask));
-          uint32_t m2 = tmask;
-          while (m2) {
-            const int jw = __ffs((int)m2) - 1;
-            m2 &= m2 - 1u;
-            sts_u16(at, (uint32_t)((lane << 6) | jw));
-            at += 2u;
-          }
-        }
-        __syncwarp();
-        // (c) their pieces, BCG_EGW_ROUNDS x 8 tiles per pass
-        constexpr int RS = BCG_EGW_ROUNDS;
-        bool first_pass = true;
-        for (int base = 0; base < ntl || first_pass; base += RS * TPR) {
-          uint4 word[RS];
-          uint32_t tag[RS];
-#pragma unroll
-          for (int rd = 0; rd < RS; ++rd) {
-            const int i = base + (lane >> 2) + rd * TPR;
-            word[rd] = make_uint4(0u, 0u, 0u, 0u);
-            tag[rd] = 0u;
-            if (i < ntl) {
-              const uint32_t code = lds_u16(tlist_u32 + 2u * (uint32_t)i);
-              const int band = (int)(code >> 6), jw = (int)(code & 63u);
-              tag[rd] = (code << 2) | (uint32_t)g;
-              word[rd] = __ldg(occ + ((((by0 + band) * tiles_x + wx0 + jw) << 2) + g));
-            }
-          }
-          if (first_pass) spans_and_tables();
-          first_pass = false;
-#pragma unroll
-          for (int rd = 0; rd < RS; ++rd) push(word[rd], tag[rd]);
-        }
-      } else {
-        spans_and_tables();
-        const uint32_t inv = (65536u + (uint32_t)nwx - 1u) / (uint32_t)nwx;       // t / nwx == (t * inv) >> 16 for t < 4096
-        for (int base = 0; base < ntile; base += 4 * TPR) {
-          uint4 word[4];
-          uint32_t tag[4];
-#pragma unroll
-          for (int rd = 0; rd < 4; ++rd) {
-            const int t = base + (lane >> 2) + rd * TPR;
-            const int band = (int)(((uint32_t)t * inv) >> 16), jw = t - band * nwx;
-            const int ty = by0 + band, tx = wx0 + jw;
-            word[rd] = make_uint4(0u, 0u, 0u, 0u);
-            tag[rd] = (uint32_t)((band << 8) | (jw << 2) | g);
-            if (t < ntile && (unsigned)ty < (unsigned)tiles_y && (unsigned)tx < (unsigned)tiles_x)
-              word[rd] = __ldg(occ + (((ty * tiles_x + tx) << 2) + g));
-          }
-#pragma unroll
-          for (int rd = 0; rd < 4; ++rd) push(word[rd], tag[rd]);
-        }
-      }
-      if (qtail != qhead) {
-        __syncwarp();
-        expand(qhead, (int)(qtail - qhead));
-      }
-      if (lane == 0) bulk_wait_all();         // the zeros have landed (they had the whole scan to do so)
-    }
-    cp_async_wait_group_1();                  // the record needed next iteration has landed
-    __syncwarp();                             // zeros (incl. head / tail bytes), tables, list and count are complete
-    const uint32_t count = T.count;
-    const bool sparse = try_sparse && count <= BCG_EGS_LIST;
-    if (sparse) {
-      // ---- 3. scatter the listed cells ----------------------------------------------------------------------------
-      const bool only_lethal = (r->dense_map & 2) != 0;
-      const uint8_t* src = nullptr;
-      int pitch = 0;
-      if (!only_lethal) {                               // other cost values: they are read from the map's uint8 rows
-        const BcgMapDesc* md = b.maps + r->map_id;
-        src = b.map_arena + md->data_off;
-        pitch = md->pitch;
-      }
-      const float m0 = r->fwd[0], m1 = r->fwd[1], m2 = r->fwd[2], m3 = r->fwd[3], m4 = r->fwd[4], m5 = r->fwd[5];
-      for (uint32_t i = lane; i < count; i += 32) {
-        const uint32_t key = lds_u16(list_u32 + 2u * i);
-        const int xr = (int)(key & 0xffu), yr = (int)(key >> 8);
-        const float X = (float)(X0 + xr), Y = (float)(Y0 + yr);
-        // candidates only: fused multiply-adds are fine here, the fixed-point test below decides
-        const int fu = __float2int_rd(__fmaf_rn(m0, X, __fmaf_rn(m1, Y, m2)));
-        const int fv = __float2int_rd(__fmaf_rn(m3, X, __fmaf_rn(m4, Y, m5)));
-        if (fu < -1 || fu >= ego_w || fv < -1 || fv >= ego_h) continue;     // every candidate is outside the crop
-        uint8_t val = 254;
-        if (!only_lethal) val = __ldg(src + (int64_t)(Y0 + yr) * pitch + (X0 + xr));
-        const int u0 = max(fu, 0), u1 = min(fu + 1, ego_w - 1), v0 = max(fv, 0), v1 = min(fv + 1, ego_h - 1);
-        const uint2 a0 = lds_v2(adxy_u32 + 8u * (uint32_t)u0), a1 = lds_v2(adxy_u32 + 8u * (uint32_t)u1);
-        const uint2 b0 = lds_v2(bxy_u32 + 8u * (uint32_t)v0), b1 = lds_v2(bxy_u32 + 8u * (uint32_t)v1);
-        // (a + b) >> 10 == r  <=>  0 <= a + b - (r << 10) < 1024
-        const int xs = xr << 10, ys = yr << 10;
-        const bool h00 = (uint32_t)((int)a0.x + (int)b0.x - xs) < 1024u && (uint32_t)((int)a0.y + (int)b0.y - ys) < 1024u;
-        const bool h10 = (uint32_t)((int)a1.x + (int)b0.x - xs) < 1024u && (uint32_t)((int)a1.y + (int)b0.y - ys) < 1024u;
-        const bool h01 = (uint32_t)((int)a0.x + (int)b1.x - xs) < 1024u && (uint32_t)((int)a0.y + (int)b1.y - ys) < 1024u;
-        const bool h11 = (uint32_t)((int)a1.x + (int)b1.x - xs) < 1024u && (uint32_t)((int)a1.y + (int)b1.y - ys) < 1024u;
-        uint8_t* const row0 = dst + v0 * ego_w, * const row1 = dst + v1 * ego_w;
-        if (h00) row0[u0] = val;
-        if (h10) row0[u1] = val;
-        if (h01) row1[u0] = val;
-        if (h11) row1[u1] = val;
-        if (HITS) {
-          // compact observation (BcgStepOut.ego_hits): pixel offset | value << 16 of every non-zero crop pixel (at the
-          // crop's border two candidates can be the same pixel: u0 == u1 or v0 == v1 after clamping)
-          const bool du = u1 != u0, dv = v1 != v0;
-          const bool r00 = h00, r10 = h10 && du, r01 = h01 && dv, r11 = h11 && du && dv;
-          const int nh = (int)r00 + (int)r10 + (int)r01 + (int)r11;
-          if (nh) {
-            uint32_t at = atomicAdd(&T.hits, (uint32_t)nh);
-            uint32_t* const out = hit_list + (int64_t)e * hit_cap;
-            const uint32_t tagged = (uint32_t)val << 16;
-            if (r00) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(v0 * ego_w + u0); ++at; }
-            if (r10) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(v0 * ego_w + u1); ++at; }
-            if (r01) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(v1 * ego_w + u0); ++at; }
-            if (r11) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(v1 * ego_w + u1); ++at; }
-          }
-        }
-      }
-    } else if (b.flags & BCG_BATCH_SPARSE_EGO_ONLY) {
-      // No dense pass follows this kernel (the host knows that no map of the batch is dense): the rare window that
-      // overflows the cell list, or lies outside any sane range, is rendered here by the bounds-checked per-pixel gather.
-      const EgoAffine A = r->aff;
-      for (int i = lane; i < ego_w + ego_h; i += 32) {
-        if (i < ego_w) {
-          tab[i] = make_int2(__double2int_rn(A.a11 * i * 1024), __double2int_rn(A.a21 * i * 1024));
-        } else {
-          const int t = i - ego_w;
-          tab[i] = make_int2(__double2int_rn((A.a12 * t + A.b1) * 1024) + 512, __double2int_rn((A.a22 * t + A.b2) * 1024) + 512);
-        }
-      }
-      __syncwarp();
-      const BcgMapDesc* md = b.maps + r->map_id;
-      const uint8_t* src = b.map_arena + md->data_off;
-      const int mw = md->width, mh = md->height, mpitch = md->pitch;
-      for (int i = lane; i < npx; i += 32) {
-        const int vv = i / ego_w, uu = i - vv * ego_w;
-        const int2 aa = tab[uu], bb = tab[ego_w + vv];
-        const long long X = ((long long)aa.x + bb.x) >> 10, Y = ((long long)aa.y + bb.y) >> 10;
-        uint8_t val = 0;
-        if (X >= 0 && X < mw && Y >= 0 && Y < mh) val = __ldg(src + Y * mpitch + X);
-        dst[i] = val;
-      }
-    } else if (lane == 0) {
-      const int at = atomicAdd(b.ego_list + n, 1);
-      b.ego_list[at] = e;
-    }
-    __syncwarp();                               // every lane is done with the list, the tables, the hit counter and record `it`
-    if (lane == 0) {
-      if (HITS) hit_count[e] = sparse ? (int32_t)T.hits : -1;     // > hit_cap: the list overflowed; -1: rendered densely
-      T.ids[(it + RD + 1) & 7] = drawn;
-    }
-    __syncwarp();
-  }
-}
-
 // EgoWork records and / or goal_n_state from the current state (stand-alone bcg_observe_ego): one thread per env
 __global__ void __launch_bounds__(128) ego_prep_kernel(const BcgParams p, const BcgBatch b, const int want_image,
                                                        float* __restrict__ goal_n_state, const int ego_cap) {
@@ -3164,58 +2512,15 @@ static int launch_ego_dense(const BcgParams* p, const BcgBatch* b, uint8_t* ego_
 }
 
 // sparse scatter kernel for every env, then the dense kernel for the envs it handed over (usually none)
-// BCG_EGO_KERNEL=cta renders with round 1's CTA-per-env scatter kernel (ego_sparse_kernel) instead of ego_warp_kernel (A/B)
-static bool ego_cta_kernel_requested() {
-  static const bool cta = [] {
-    const char* v = getenv("BCG_EGO_KERNEL");
-    return v && strcmp(v, "cta") == 0;
-  }();
-  return cta;
-}
-
 struct EgoHits {       // BcgStepOut.ego_hits / ego_hit_count / ego_hit_cap (all zero: no compact output)
   uint32_t* list;
   int32_t* count;
   int cap;
 };
 
-template <bool SUM, bool HITS>
-static int launch_ego_warp_t(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, const EgoHits& hits, int sms, cudaStream_t s) {
-  const int tab_bytes = BCG_EGW_WARPS * (p->ego_w + p->ego_h) * (int)sizeof(int2);
-  static int per_sm_cache[64] = {0}, tab_cache[64] = {0};      // per template instance and device
-  int dev = 0;
-  BCG_CHECK_CUDA(cudaGetDevice(&dev));
-  int per_sm = 0;
-  if (dev >= 0 && dev < 64 && per_sm_cache[dev] > 0 && tab_cache[dev] == tab_bytes) {
-    per_sm = per_sm_cache[dev];
-  } else {
-    BCG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ego_warp_kernel<SUM, HITS>, BCG_EGW_WARPS * 32, tab_bytes));
-    BCG_REQUIRE(per_sm > 0, "the egocentric scatter kernel does not fit an SM with this crop size");
-    if (dev >= 0 && dev < 64) {
-      per_sm_cache[dev] = per_sm;
-      tab_cache[dev] = tab_bytes;
-    }
-  }
-  // persistent warps, each drawing envs from the global counter: no more warps than envs (a warp's first draw is 4 envs)
-  const int want = (b->n_envs + 4 * BCG_EGW_WARPS - 1) / (4 * BCG_EGW_WARPS);
-  const int grid = want < per_sm * sms ? (want > 0 ? want : 1) : per_sm * sms;
-  ego_warp_kernel<SUM, HITS><<<grid, BCG_EGW_WARPS * 32, tab_bytes, s>>>(*p, *b, ego_image, hits.list, hits.count, hits.cap);
-  BCG_CHECK_CUDA(cudaGetLastError());
-  return BCG_OK;
-}
-
 static int launch_ego_sparse(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, const EgoHits& hits, cudaStream_t s) {
   int sms = 0;
   if (int rc = sm_count_of_current_device(&sms)) return rc;
-  if (!ego_cta_kernel_requested()) {
-    const bool sum = b->occ_sum_arena != nullptr;
-    int rc;
-    if (hits.list) rc = sum ? launch_ego_warp_t<true, true>(p, b, ego_image, hits, sms, s) : launch_ego_warp_t<false, true>(p, b, ego_image, hits, sms, s);
-    else rc = sum ? launch_ego_warp_t<true, false>(p, b, ego_image, hits, sms, s) : launch_ego_warp_t<false, false>(p, b, ego_image, hits, sms, s);
-    if (rc) return rc;
-    if (b->flags & BCG_BATCH_SPARSE_EGO_ONLY) return BCG_OK;     // the scatter kernel rendered every env itself
-    return launch_ego_dense(p, b, ego_image, b->ego_list, s);
-  }
   // (the hand-over count and the env counter in ego_list[n_envs ..] were zeroed by the state / prep kernel)
   // persistent CTAs, as many per SM as fit with this crop's tables (18 for the 117 x 133 crop)
   const int tab_bytes = (p->ego_w + p->ego_h) * (int)sizeof(int2);
@@ -3247,15 +2552,6 @@ static int launch_ego_sparse(const BcgParams* p, const BcgBatch* b, uint8_t* ego
   BCG_CHECK_CUDA(cudaGetLastError());
   if (b->flags & BCG_BATCH_SPARSE_EGO_ONLY) return BCG_OK;     // the sparse kernel rendered every env itself
   return launch_ego_dense(p, b, ego_image, b->ego_list, s);
-}
-
-// BCG_STEP_KERNELS=split runs kin_kernel + collide_reward_kernel + commit_kernel instead of the fused state_kernel
-static bool split_state_kernels_requested() {
-  static const bool split = [] {
-    const char* v = getenv("BCG_STEP_KERNELS");
-    return v && strcmp(v, "split") == 0;
-  }();
-  return split;
 }
 
 // BCG_EGO_KERNEL=dense forces the dense cell-tile kernel for every env (A/B timing of the sparse path)
@@ -3301,7 +2597,6 @@ int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, 
                     uint64_t step_index, const BcgStepOut* out, void* const* events, void* stream) {
   if (int rc = check_batch(p, b)) return rc;
   BCG_REQUIRE(actions && out, "null actions/out");
-  BCG_REQUIRE(!(b->step_counter && split_state_kernels_requested()), "BCG_STEP_KERNELS=split has no device-side step counter");
   const bool ego = out->ego_image || out->goal_n_state;
   if (ego) {
     if (int rc = check_ego(p, b, out->ego_image)) return rc;
@@ -3309,17 +2604,7 @@ int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, 
   cudaStream_t s = (cudaStream_t)stream;
   const BcgStateLayout L = make_layout(*p);
   if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[0], s));
-  if (split_state_kernels_requested()) {
-    // round 1's three state kernels (BCG_STEP_KERNELS=split): kept as the A/B and bit-equality reference of move_kernel + reward_kernel
-    kin_kernel<<<blocks_for(b->n_envs, BCG_KIN_THREADS), BCG_KIN_THREADS, 0, s>>>(*p, *b, L, actions, action_is_f64, step_index);
-    BCG_CHECK_CUDA(cudaGetLastError());
-    if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[1], s));
-    collide_reward_kernel<<<blocks_for((int64_t)b->n_envs * 32, BCG_CR_THREADS), BCG_CR_THREADS, 0, s>>>(*p, *b);
-    BCG_CHECK_CUDA(cudaGetLastError());
-    if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[2], s));
-    commit_kernel<<<blocks_for(b->n_envs, BCG_COMMIT_THREADS / 2), BCG_COMMIT_THREADS, 0, s>>>(*p, *b, L, *out, ego ? ego_capacity(*p, *b) : 0);
-    BCG_CHECK_CUDA(cudaGetLastError());
-  } else {
+  {
     if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[1], s));
     const int cap = ego ? ego_capacity(*p, *b) : 0;
     move_kernel<<<blocks_for(b->n_envs, BCG_MOVE_THREADS), BCG_MOVE_THREADS, 0, s>>>(*p, *b, L, actions, action_is_f64, step_index,

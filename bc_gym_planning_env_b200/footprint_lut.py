@@ -145,5 +145,10 @@ class FootprintLut(object):
         return out
 
     def arrays(self):
+        # a bin's vertex tuple and header side by side, rows padded to 16 bytes: what the device lookup fetches per candidate
+        stride = (2 * self.n_verts + 4 + 7) // 8 * 8
+        bins = np.zeros((self.n_bins, stride), dtype=np.int16)
+        bins[:, :2 * self.n_verts] = self.verts
+        bins[:, 2 * self.n_verts:2 * self.n_verts + 4] = self.header
         return dict(edges=self.edges, verts=self.verts, header=self.header, rows=self.rows,
-                    fp_pix=self.fp_pix.reshape(-1), bucket_first=self.bucket_first)
+                    fp_pix=self.fp_pix.reshape(-1), bucket_first=self.bucket_first, bins=bins)

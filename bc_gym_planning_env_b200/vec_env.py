@@ -361,6 +361,7 @@ class VecPlanEnv(object):
         b.lut.edges, b.lut.verts, b.lut.header = d['edges'].data_ptr(), d['verts'].data_ptr(), d['header'].data_ptr()
         b.lut.rows, b.lut.fp_pix = d['rows'].data_ptr(), d['fp_pix'].data_ptr()
         b.lut.bucket_first, b.lut.n_buckets = d['bucket_first'].data_ptr(), self.lut.n_buckets
+        b.lut.bins, b.lut.bin_stride = d['bins'].data_ptr(), int(d['bins'].shape[1])
         b.lut.bucket_scale = self.lut.bucket_scale
         b.lut.n_bins, b.lut.n_verts, b.lut.max_rows, b.lut.wpr = self.lut.n_bins, self.lut.n_verts, self.lut.max_rows, self.lut.wpr
         b.status, b.stats = self._status.data_ptr(), self._stats.data_ptr()
@@ -465,8 +466,8 @@ class VecPlanEnv(object):
         return self.observation(), self.reward, self.done, {}
 
     def launches_per_step(self):
-        """Kernels one `step` launches: move + reward (three with BCG_STEP_KERNELS=split), then the egocentric kernel(s)."""
-        n = 3 if os.environ.get("BCG_STEP_KERNELS") == "split" else 2
+        """Kernels one `step` launches: move_kernel + reward_kernel, then the egocentric kernel(s)."""
+        n = 2
         if not self.with_ego:
             return n
         if self._ego_list is None or os.environ.get("BCG_EGO_KERNEL") == "dense":

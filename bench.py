@@ -502,12 +502,8 @@ def timed_steps(env, actions, steps, D, sampler=None):
     if sampler is not None:
         sampler.mark_end()
     ms = D.max_ms(t_start.elapsed_time(t_end))
-    split = os.environ.get("BCG_STEP_KERNELS") == "split"                # round 1's three state kernels (A/B)
-    names = ("kin_kernel", "collide_reward_kernel", "commit_kernel") if split else (None, "move_kernel", "reward_kernel")
-    kern = {}
-    for j, name in enumerate(names):
-        if name:
-            kern[name] = float(np.mean([e[j].elapsed_time(e[j + 1]) for e in ev]))
+    kern = {"move_kernel": float(np.mean([e[1].elapsed_time(e[2]) for e in ev])),
+            "reward_kernel": float(np.mean([e[2].elapsed_time(e[3]) for e in ev]))}
     kern["ego"] = float(np.mean([e[3].elapsed_time(e[4]) for e in ev]))
     return ms, kern, stats
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BCG_ABI_VERSION 7
+#define BCG_ABI_VERSION 8
 
 /* error codes */
 #define BCG_OK 0
@@ -156,7 +156,11 @@ typedef struct BcgFootprintLut {
   const int32_t* bucket_first; /* device [n_buckets]: bin containing the left end of uniform bucket k  */
   double bucket_scale;    /* n_buckets / (2 pi)                                                     */
   int32_t n_bins, n_verts, max_rows, wpr;
-  int32_t n_buckets, reserved;
+  int32_t n_buckets;
+  int32_t bin_stride;     /* int16 elements per row of `bins` (multiple of 8), 0 when bins is NULL         */
+  const int16_t* bins;    /* optional, device [n_bins][bin_stride]: a bin's vertex tuple followed by its header
+                             (xmin, ymin, n_rows, width), 16-byte aligned rows -- lets the lookup fetch two
+                             candidate bins, tuple and header, in one memory round trip                     */
 } BcgFootprintLut;
 
 /* BcgBatch.flags */

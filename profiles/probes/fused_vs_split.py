@@ -1,7 +1,8 @@
-"""A/B of the fused state_kernel against round 1's three state kernels (BCG_STEP_KERNELS=split), and of plain launches
-against the captured CUDA graph (VecPlanEnv.step_graph).
+"""A/B of two builds or modes of the step (BCG_B200_LIB=<variant>; in round 2 also BCG_STEP_KERNELS=split for round 1's three
+state kernels and BCG_EGO_KERNEL=cta / warp -- modes that no longer exist), and of plain launches against the captured
+CUDA graph (VecPlanEnv.step_graph).
 
-    python profiles/probes/fused_vs_split.py run OUT.npz [--envs N] [--steps K]     # honours BCG_STEP_KERNELS
+    python profiles/probes/fused_vs_split.py run OUT.npz [--envs N] [--steps K]
     python profiles/probes/fused_vs_split.py compare A.npz B.npz                    # bit equality of the two runs
     python profiles/probes/fused_vs_split.py times [--sizes 256,8192,65536]         # per-kernel and per-step times
 
@@ -99,7 +100,7 @@ def times():
         t1.record()
         torch.cuda.synchronize()
         r["step_ms_plain"] = t0.elapsed_time(t1) / K
-        if os.environ.get("BCG_STEP_KERNELS") != "split":
+        if True:
             env.step_graph(actions[0])
             torch.cuda.synchronize()
             t0.record()

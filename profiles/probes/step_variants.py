@@ -11,7 +11,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sizes = sys.argv[sys.argv.index("--sizes") + 1] if "--sizes" in sys.argv else "8192,65536"
 only = sys.argv[sys.argv.index("--only") + 1].split(",") if "--only" in sys.argv else None
-for lib in [None, "cta"] + sorted(glob.glob(os.path.join(ROOT, "bc_gym_planning_env_b200", "csrc", "variants", "*.so"))):
+for lib in [None] + sorted(glob.glob(os.path.join(ROOT, "bc_gym_planning_env_b200", "csrc", "variants", "*.so"))):
     name = "product" if lib is None else ("product, BCG_EGO_KERNEL=cta" if lib == "cta" else os.path.basename(lib)[len("libbcg_b200_"):-3])
     if only and name not in only:
         continue
