@@ -530,6 +530,13 @@ __device__ __forceinline__ bool collide_thread(const BcgFootprintLut& lut, const
     const bool flat = (tx1 - tx0) < 4;
 #pragma unroll
     for (int k = 0; k < MAXB; ++k) todo |= flat ? (tm[k] << (4 * k)) : 0u;
+    // every listed tile is asked into L2 right away (no register, no wait): the loop below then pays one DRAM round trip
+    // in all instead of one per tile
+    for (uint32_t ahead = todo; ahead != 0u; ahead &= ahead - 1u) {
+      const int bit = __ffs((int)ahead) - 1;
+      const uint32_t* tp = tiles + ((((int64_t)(tyb + (bit >> 2)) * tiles_x) + tx0 + (bit & 3)) << 4);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(tp));
+    }
     int kb = 0;                                            // wide footprints: band by band
     while (flat ? (todo != 0u) : (kb < MAXB)) {
       int k, j;

@@ -749,12 +749,12 @@ __device__ __forceinline__ void reset_env_rows(const BcgParams& p, const BcgBatc
   }
 }
 
-#ifndef BCG_REWARD_LANES
-#define BCG_REWARD_LANES 8            // lanes per env (power of two, 1 < G <= 32): 32 / G envs per warp
-#endif
+// G lanes per env (power of two, 1 < G <= 32): 32 / G envs per warp.  Measured (profiles/r2_notes.md): 65 536 envs G = 8
+// 0.045 ms, 16: 0.050, 32: 0.065; 8 192 envs 0.022 / 0.018 / 0.019; 256 envs 0.0147 / 0.0121 / 0.0108 -- a large batch
+// wants few warps (the straight-line code is paid per warp), a small one a short chain (a chunk in one round).
+template <int G>
 __global__ void __launch_bounds__(BCG_REWARD_THREADS, BCG_REWARD_RESIDENT / BCG_REWARD_THREADS)
 reward_kernel(const BcgParams p, const BcgBatch b, const BcgStepOut out, const int ego_cap) {
-  constexpr int G = BCG_REWARD_LANES;
   const int e = (blockIdx.x * blockDim.x + threadIdx.x) / G;
   const unsigned lane = threadIdx.x & 31, gl = lane & (G - 1);
   const bool active = e < b.n_envs;
@@ -2611,7 +2611,9 @@ int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, 
                                                                                     *out, cap);
     BCG_CHECK_CUDA(cudaGetLastError());
     if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[2], s));
-    reward_kernel<<<blocks_for((int64_t)b->n_envs * BCG_REWARD_LANES, BCG_REWARD_THREADS), BCG_REWARD_THREADS, 0, s>>>(*p, *b, *out, cap);
+    if (b->n_envs > 16384) reward_kernel<8><<<blocks_for((int64_t)b->n_envs * 8, BCG_REWARD_THREADS), BCG_REWARD_THREADS, 0, s>>>(*p, *b, *out, cap);
+    else if (b->n_envs > 2048) reward_kernel<16><<<blocks_for((int64_t)b->n_envs * 16, BCG_REWARD_THREADS), BCG_REWARD_THREADS, 0, s>>>(*p, *b, *out, cap);
+    else reward_kernel<32><<<blocks_for((int64_t)b->n_envs * 32, BCG_REWARD_THREADS), BCG_REWARD_THREADS, 0, s>>>(*p, *b, *out, cap);
     BCG_CHECK_CUDA(cudaGetLastError());
   }
   if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[3], s));
