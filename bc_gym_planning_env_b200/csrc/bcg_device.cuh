@@ -274,7 +274,7 @@ __device__ __forceinline__ void delay_peek(const double* ring, int64_t stride, i
 // Work records: what the warp-per-env kernels need to know about one env, resolved by the thread-per-env
 // kernels (kinematics / pose-prep) and stored array-of-structures so that a warp gets everything with one
 // round of 16-byte loads instead of chasing map_id -> map descriptor -> tile address through memory.
-struct __align__(16) WorkCollide {   // 80 bytes
+struct __align__(16) WorkCollide {   // 48 bytes
   int64_t tile_off;                  // lethal tile plane of the env's map (uint32 offset in the tile arena)
   int64_t data_off;                  // uint8 cells of the env's map (byte offset in the map arena)
   int32_t tiles_x, map_pitch;
@@ -282,13 +282,9 @@ struct __align__(16) WorkCollide {   // 80 bytes
   int16_t nrows, fwidth;             // mask bounding box
   int16_t map_w, map_h;
   int32_t bin;                       // footprint angle bin
-  int32_t path_n;
-  int64_t path_off;                  // fp64 offset of the env's path rows in the path arena
-  int32_t path_pitch, chunk_pitch;   // chunk rows start at path_off + 5 * path_pitch
   int32_t sum_off;                   // tile summary of the env's map (BcgMapDesc.sum_off)
-  int32_t pad[3];
 };
-static_assert(sizeof(WorkCollide) == 80, "WorkCollide is 80 bytes");
+static_assert(sizeof(WorkCollide) == 48, "WorkCollide is 48 bytes");
 
 #define BCG_WORK_BYTES 192           // per-env scratch slot: WorkCollide (stand-alone collision) or the step's StepRecord at +0
 
@@ -395,13 +391,12 @@ __device__ __forceinline__ int find_foot_bin_header(const BcgFootprintLut& lut, 
   return bin;
 }
 
-__device__ __forceinline__ WorkCollide make_work_collide(const BcgParams& p, const BcgBatch& b, int map_id, int path_id,
-                                                         double x, double y, double th) {
+__device__ __forceinline__ WorkCollide make_work_collide(const BcgParams& p, const BcgBatch& b, int map_id, double x, double y,
+                                                         double th) {
   const BcgMapDesc m = b.maps[map_id];
-  const BcgPathDesc pd = b.paths[path_id];
   WorkCollide w;
-  w.bin = find_foot_bin(b.lut, th, b.status);
-  const short4 h = __ldg(reinterpret_cast<const short4*>(b.lut.header) + w.bin);     // xmin, ymin, nrows, width
+  short4 h;                                                                          // xmin, ymin, nrows, width
+  w.bin = find_foot_bin_header(b.lut, th, b.status, h);
   w.X0 = world_to_pixel_1d(x, m.origin_x, p.inv_resolution) + h.x;
   w.Y0 = world_to_pixel_1d(y, m.origin_y, p.inv_resolution) + h.y;
   w.nrows = h.z;
@@ -412,12 +407,7 @@ __device__ __forceinline__ WorkCollide make_work_collide(const BcgParams& p, con
   w.map_pitch = m.pitch;
   w.map_w = (int16_t)m.width;
   w.map_h = (int16_t)m.height;
-  w.path_n = pd.n;
-  w.path_off = pd.off;
-  w.path_pitch = pd.pitch;
-  w.chunk_pitch = pd.chunk_pitch;
   w.sum_off = m.sum_off;
-  w.pad[0] = w.pad[1] = w.pad[2] = 0;
   return w;
 }
 

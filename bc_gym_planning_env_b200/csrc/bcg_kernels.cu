@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(128) pose_prep_kernel(const BcgParams p, const
   if (e >= b.n_envs) return;
   const int64_t N = b.n_envs;
   uint8_t* rec = reinterpret_cast<uint8_t*>(b.work) + (int64_t)e * BCG_WORK_BYTES;
-  *reinterpret_cast<WorkCollide*>(rec) = make_work_collide(p, b, b.map_id[e], b.path_id[e], poses[e], poses[N + e], poses[2 * N + e]);
+  *reinterpret_cast<WorkCollide*>(rec) = make_work_collide(p, b, b.map_id[e], poses[e], poses[N + e], poses[2 * N + e]);
 }
 
 // cv2::saturate_cast<int>(double) == cvRound with saturation
@@ -1097,8 +1097,8 @@ __global__ void __launch_bounds__(128) generate_minis_kernel(const BcgParams p, 
     if (warp == 0) {
       bool ok = true;
       if (!explicit_params) {
-        const WorkCollide w0 = make_work_collide(p, b, e, e, mp_s.start[0], mp_s.start[1], mp_s.start[2]);
-        const WorkCollide w1 = make_work_collide(p, b, e, e, mp_s.end[0], mp_s.end[1], mp_s.end[2]);
+        const WorkCollide w0 = make_work_collide(p, b, e, mp_s.start[0], mp_s.start[1], mp_s.start[2]);
+        const WorkCollide w1 = make_work_collide(p, b, e, mp_s.end[0], mp_s.end[1], mp_s.end[2]);
         const bool hit0 = collide_tiles<false, true>(b, w0, lane, nullptr);
         const bool hit1 = collide_tiles<false, true>(b, w1, lane, nullptr);
         const double cart = hypot(mp_s.start[0] - mp_s.end[0], mp_s.start[1] - mp_s.end[1]);
@@ -1281,16 +1281,16 @@ __global__ void __launch_bounds__(256, 6) collision_kernel(const BcgBatch b, uin
 }
 
 // pose_collides of the poses whose work records are in b.work, one THREAD per env (collide_thread): the form the state
-// kernel uses, and the one the collision roofline is measured on.  Per env it reads the 64-byte record, one or two tile
+// kernel uses, and the one the collision roofline is measured on.  Per env it reads the 48-byte record, one or two tile
 // summary words per 16-row band and 16-byte quarters of the non-empty tiles under the footprint only.
-__global__ void __launch_bounds__(128) collision_thread_kernel(const BcgBatch b, uint8_t* __restrict__ flags) {
+__global__ void __launch_bounds__(64) collision_thread_kernel(const BcgBatch b, uint8_t* __restrict__ flags) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= b.n_envs) return;
   const uint4* rec = reinterpret_cast<const uint4*>(work_collide(b.work, e));
   WorkCollide f;
   uint4* fw = reinterpret_cast<uint4*>(&f);
 #pragma unroll
-  for (int k = 0; k < 5; ++k) fw[k] = __ldg(rec + k);
+  for (int k = 0; k < 3; ++k) fw[k] = __ldg(rec + k);
   FootBox fb;
   fb.X0 = f.X0;
   fb.Y0 = f.Y0;
@@ -2635,7 +2635,7 @@ static int launch_collision_kernel(const BcgBatch* b, uint8_t* flags_out, int32_
   const int grid = blocks_for((int64_t)b->n_envs * 32, 256);
   if (use_u8) collision_kernel<2><<<grid, 256, 0, s>>>(*b, flags_out, nullptr);
   else if (pixels_out) collision_kernel<1><<<grid, 256, 0, s>>>(*b, flags_out, pixels_out);
-  else collision_thread_kernel<<<blocks_for(b->n_envs, 128), 128, 0, s>>>(*b, flags_out);
+  else collision_thread_kernel<<<blocks_for(b->n_envs, 64), 64, 0, s>>>(*b, flags_out);
   BCG_CHECK_CUDA(cudaGetLastError());
   return BCG_OK;
 }
