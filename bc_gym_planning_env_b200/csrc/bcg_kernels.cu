@@ -2594,11 +2594,8 @@ static int launch_ego_sparse(const BcgParams* p, const BcgBatch* b, uint8_t* ego
       tab_cache[sum][dev] = tab_bytes;
     }
   }
-  // With the reward kernel and the second pass beside it, the first pass leaves one CTA slot per SM free: the reward
-  // kernel's CTAs need 4 K registers each and 18 resident CTAs of this kernel leave 5.6 K per SM.
-  const int slots = (pass == 0 && b->ego_fix && per_sm > 2) ? per_sm - 1 : per_sm;
-  int grid = b->n_envs < slots * sms ? b->n_envs : slots * sms;
-  if (pass == 1 && grid > 4 * sms) grid = 4 * sms;             // the second pass renders the few listed envs
+  int grid = b->n_envs < per_sm * sms ? b->n_envs : per_sm * sms;
+  if (pass == 1 && grid > 2 * sms) grid = 2 * sms;             // the second pass renders the few listed envs
   // (the variant that also records the compact hit lists has the same shared-memory footprint and register budget)
   if (hits.list) {
     if (sum) ego_sparse_kernel<true, true><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image, hits.list, hits.count, hits.cap, pass, done);
@@ -2684,19 +2681,16 @@ int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, 
       cudaStream_t side = (cudaStream_t)b->side_stream;
       BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)b->ev_fork, s));
       BCG_CHECK_CUDA(cudaStreamWaitEvent(side, (cudaEvent_t)b->ev_fork, 0));
-      BCG_REQUIRE((out->ego_hits != nullptr) == (out->ego_hit_count != nullptr) && (!out->ego_hits || out->ego_hit_cap > 0),
-                  "ego_hits, ego_hit_count and ego_hit_cap go together");
-      const EgoHits hits{out->ego_hits, out->ego_hit_count, out->ego_hit_cap};
-      // side stream: reward kernel, then the second egocentric pass (the envs the verdict may have reset) -- both beside
-      // the first pass, which the main stream runs; a dependent launch AFTER the first pass would add its own ~25 us
-      // chain to every step (measured: profiles/r2_notes.md r2m)
       launch_reward(p, b, out, cap, side);
       BCG_CHECK_CUDA(cudaGetLastError());
       if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[3], side));
-      if (int rc = launch_ego_sparse(p, b, out->ego_image, hits, side, 1, out->done)) return rc;
       BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)b->ev_join, side));
+      BCG_REQUIRE((out->ego_hits != nullptr) == (out->ego_hit_count != nullptr) && (!out->ego_hits || out->ego_hit_cap > 0),
+                  "ego_hits, ego_hit_count and ego_hit_cap go together");
+      const EgoHits hits{out->ego_hits, out->ego_hit_count, out->ego_hit_cap};
       if (int rc = launch_ego_sparse(p, b, out->ego_image, hits, s, 0, nullptr)) return rc;
       BCG_CHECK_CUDA(cudaStreamWaitEvent(s, (cudaEvent_t)b->ev_join, 0));
+      if (int rc = launch_ego_sparse(p, b, out->ego_image, hits, s, 1, out->done)) return rc;
       if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[4], s));
       return BCG_OK;
     }
