@@ -67,9 +67,7 @@ class BcgBatch(C.Structure):
         ("map_tmaps", C.c_void_p), ("tmap_n_widths", C.c_int32), ("tmap_box_h", C.c_int32),
         ("tmap_box_w", C.c_int32 * 4),
         ("cell_tile_arena", C.c_void_p), ("occ_tile_arena", C.c_void_p), ("ego_list", C.c_void_p),
-        ("occ_sum_arena", C.c_void_p), ("status", C.c_void_p), ("stats", C.c_void_p),
-        ("ego_init", C.c_void_p), ("ego_fix", C.c_void_p), ("side_stream", C.c_void_p), ("ev_fork", C.c_void_p), ("ev_join", C.c_void_p),
-        ("step_counter", C.c_void_p),
+        ("occ_sum_arena", C.c_void_p), ("status", C.c_void_p), ("stats", C.c_void_p), ("step_counter", C.c_void_p),
     ]
 
 

@@ -135,7 +135,6 @@ __device__ __forceinline__ int cv_round_sat(double v) {
 }
 
 #define BCG_EGO_MAX 256
-#define BCG_EGT_MAX_W 160
 #define BCG_EGO_THREADS 256
 #define BCG_EGO_MAX_TILE_ROWS 384
 
@@ -379,17 +378,15 @@ __device__ __forceinline__ EgoQuad ego_quad(const EgoAffine& A, int ego_w, int e
   return q;
 }
 
-#define BCG_EGO_DEFERRED 4              // EgoTileWork.dense_map bit 2: rendered by the egocentric kernel's second pass
 __device__ __forceinline__ void write_ego_tile_record(const BcgParams& p, const BcgBatch& b, int e, int map_id,
-                                                      const BcgMapDesc& m, double px, double py, double pth, int win_capacity,
-                                                      void* records = nullptr, int extra_flags = 0) {
-  EgoTileWork* rec = reinterpret_cast<EgoTileWork*>(reinterpret_cast<uint8_t*>(records ? records : b.ego_work) + (int64_t)e * BCG_EGO_WORK_BYTES);
+                                                      const BcgMapDesc& m, double px, double py, double pth, int win_capacity) {
+  EgoTileWork* rec = reinterpret_cast<EgoTileWork*>(reinterpret_cast<uint8_t*>(b.ego_work) + (int64_t)e * BCG_EGO_WORK_BYTES);
   EgoTileWork w;
   w.aff = ego_affine(p, m, px, py, pth, w.fwd);
   w.X0 = w.Y0 = w.ntx = w.nty = 0;
   w.mode = BCG_EGO_MODE_DIRECT;
   w.map_id = map_id;
-  w.dense_map = (((int64_t)m.occupied * 20 > (int64_t)m.width * m.height) ? 1 : 0) | ((m.flags & BCG_MAP_ONLY_LETHAL) ? 2 : 0) | extra_flags;
+  w.dense_map = (((int64_t)m.occupied * 20 > (int64_t)m.width * m.height) ? 1 : 0) | ((m.flags & BCG_MAP_ONLY_LETHAL) ? 2 : 0);
   w.sum_off = m.sum_off;
   w.tiles_xy = (uint32_t)m.tiles_x | ((uint32_t)m.tiles_y << 16);
   w.tile_off16 = (uint32_t)(m.tile_off >> 4);
@@ -466,10 +463,9 @@ __device__ __forceinline__ uint32_t ego_band_span(const EgoAffine& A, int ego_w,
 
 // the per-env record of whichever egocentric kernel the batch is set up for
 __device__ __forceinline__ void write_ego_record(const BcgParams& p, const BcgBatch& b, int e, int map_id,
-                                                 const BcgMapDesc& m, double px, double py, double pth, int cap,
-                                                 int extra_flags = 0) {
+                                                 const BcgMapDesc& m, double px, double py, double pth, int cap) {
   if (b.cell_tile_arena) {
-    write_ego_tile_record(p, b, e, map_id, m, px, py, pth, cap, nullptr, extra_flags);
+    write_ego_tile_record(p, b, e, map_id, m, px, py, pth, cap);
   } else {
     *reinterpret_cast<EgoWork*>(reinterpret_cast<uint8_t*>(b.ego_work) + (int64_t)e * BCG_EGO_WORK_BYTES) =
         make_ego_work(p, b, map_id, m, px, py, pth, cap);
@@ -684,23 +680,7 @@ move_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L, const v
   // ---- what reward_kernel starts from ----------------------------------------------------------------------------------------
   const bool true_pose = p.ego_variant == 1;             // observation about the true robot pose vs the observed (delayed) pose
   const double opx = true_pose ? s[0] : dpose[0], opy = true_pose ? s[1] : dpose[1], opth = true_pose ? s[2] : dpose[2];
-  // With the reward kernel running BESIDE the egocentric kernel (BcgBatch.ego_fix set), an env that may be reset by this
-  // step's verdict -- collided, timed out, or close enough to its last way point to finish the path -- is not rendered
-  // by the first egocentric pass: it is listed for the second pass, which runs after the reward kernel and picks the
-  // initial state's record when the env was reset.  Conservative: a listed env that does not reset is rendered from this
-  // record all the same.
-  int ego_flags = 0;
-  if (out.ego_image && b.ego_fix && p.auto_reset) {
-    const double* P = b.path_arena + pdsc.off;
-    const double gx = __ldg(P + pdsc.n - 1) - dpose[0], gy = __ldg(P + pdsc.pitch + pdsc.n - 1) - dpose[1];
-    const double reach = (p.reward_kind == BCG_REWARD_PURE_PURSUIT) ? 1.0 : p.spatial_precision;
-    const bool maybe_goal = goal_before || (gx * gx + gy * gy) < reach * reach * (1.0 + 1e-9);
-    if (maybe_goal || collided_after != 0 || iter_after >= p.iteration_timeout) {
-      ego_flags = BCG_EGO_DEFERRED;
-      b.ego_fix[atomicAdd(b.ego_fix + N, 1)] = e;
-    }
-  }
-  if (out.ego_image) write_ego_record(p, b, e, map_id, m, opx, opy, opth, ego_cap, ego_flags);
+  if (out.ego_image) write_ego_record(p, b, e, map_id, m, opx, opy, opth, ego_cap);
   rec.ct = rec.st = rec.tx = rec.ty = rec.tt = 0.0;
   if (out.goal_n_state) inverse_transform(opx, opy, opth, rec.ct, rec.st, rec.tx, rec.ty, rec.tt);
 #pragma unroll
@@ -761,7 +741,7 @@ __device__ __forceinline__ void reset_env_rows(const BcgParams& p, const BcgBatc
   if (out.ego_image || out.goal_n_state) {
     const bool true_pose = p.ego_variant == 1;
     const double opx = true_pose ? c[0] : dpose[0], opy = true_pose ? c[1] : dpose[1], opth = true_pose ? c[2] : dpose[2];
-    if (out.ego_image && !b.ego_fix) {                   // (with the second egocentric pass: it takes the initial state's record)
+    if (out.ego_image) {
       const int map_id = b.map_id[e];
       write_ego_record(p, b, e, map_id, b.maps[map_id], opx, opy, opth, ego_cap);
     }
@@ -908,12 +888,6 @@ __device__ __forceinline__ void init_env_state(const BcgParams& p, const BcgBatc
     const int v = (r == BCG_I_TARGET) ? target : 0;
     b.init_i[(int64_t)r * N + e] = v;
     b.state_i[(int64_t)r * N + e] = v;
-  }
-  // the egocentric record of the initial state (what an auto-reset env is observed with): written once here, so that the
-  // step's reward kernel never has to touch a record the egocentric kernel may be reading beside it
-  if (lane == 0 && b.ego_init && b.cell_tile_arena && p.ego_w > 0 && p.ego_w <= BCG_EGT_MAX_W) {
-    const int map_id = b.map_id[e];
-    write_ego_tile_record(p, b, e, map_id, b.maps[map_id], x0, y0, t0, ego_window_capacity(p), b.ego_init);
   }
 }
 
@@ -1520,6 +1494,7 @@ __global__ void __launch_bounds__(BCG_EGO_THREADS, 5) ego_kernel(const BcgParams
 // not HBM; cp.async staging, TMA boxes of the tile view, double-buffered windows and L2 prefetch were all slower.
 #define BCG_EGT_THREADS 256
 #define BCG_EGT_CTAS 5
+#define BCG_EGT_MAX_W 160
 #define BCG_EGT_REC_SLOTS 8
 struct EgoTab {
   int adx[BCG_EGT_MAX_W], ady[BCG_EGT_MAX_W];   // rint(a11 u 2^10), rint(a21 u 2^10)
@@ -1766,11 +1741,7 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
                                                                                    uint8_t* __restrict__ image,
                                                                                    uint32_t* __restrict__ hit_list,
                                                                                    int32_t* __restrict__ hit_count,
-                                                                                   const int hit_cap, const int pass,
-                                                                                   const uint8_t* __restrict__ done) {
-  // pass 0: every env of the batch (those whose record is marked BCG_EGO_DEFERRED are left out when the batch runs the
-  // reward kernel beside this one).  pass 1 (after the reward kernel): the envs move_kernel listed in BcgBatch.ego_fix,
-  // each from its step record or -- when it was reset (done[e] with auto-reset) -- from the initial state's record.
+                                                                                   const int hit_cap) {
   __shared__ __align__(128) uint8_t zero_s[BCG_EGS_ZERO_BYTES];
   __shared__ __align__(16) EgoSparseTab T;
   __shared__ __align__(128) uint8_t rec_s[BCG_EGS_REC_SLOTS * BCG_EGO_WORK_BYTES];
@@ -1784,21 +1755,14 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
   extern __shared__ __align__(16) int2 egs_tab[];          // adxy[ego_w], bxy[ego_h]
   const uint32_t adxy_u32 = smem_u32(egs_tab), bxy_u32 = adxy_u32 + 8u * (uint32_t)p.ego_w, list_u32 = smem_u32(T.list);
   const uint8_t* const recs = reinterpret_cast<const uint8_t*>(b.ego_work);
-  const int32_t* const fix = b.ego_fix;
-  const int n = pass == 1 ? fix[b.n_envs] : b.n_envs, G = gridDim.x;          // jobs of this pass
-  int32_t* const counter = pass == 1 ? b.ego_fix + b.n_envs + 1 : b.ego_list + b.n_envs + 1;
+  const int n = b.n_envs, G = gridDim.x;
   const int ego_w = p.ego_w, ego_h = p.ego_h, npx = ego_w * ego_h;
   const int e0 = blockIdx.x;
-  auto env_of = [&](int j) { return pass == 1 ? fix[j] : j; };
-  if (e0 < n) {                                 // (no early return: the second pass ends with a ticket every CTA takes)
+  if (e0 >= n) return;
 
-  auto fetch_record = [&](int j, int slot) {
-    if (j < n && tid < BCG_EGO_WORK_BYTES / 16) {
-      const int en = env_of(j);
-      const uint8_t* src = recs;
-      if (pass == 1 && p.auto_reset && done[en]) src = reinterpret_cast<const uint8_t*>(b.ego_init);
-      cp_async_16(rec_u32 + slot * BCG_EGO_WORK_BYTES + tid * 16, src + (int64_t)en * BCG_EGO_WORK_BYTES + tid * 16, 16u);
-    }
+  auto fetch_record = [&](int en, int slot) {
+    if (en < n && tid < BCG_EGO_WORK_BYTES / 16)
+      cp_async_16(rec_u32 + slot * BCG_EGO_WORK_BYTES + tid * 16, recs + (int64_t)en * BCG_EGO_WORK_BYTES + tid * 16, 16u);
   };
   // Tile-summary words of the window of record `q`, lane <-> band of 16 rows (zero where the band or the word lies
   // outside the map, or the env will not take the sparse path).  Loaded one env ahead of their use, so that an env's
@@ -1848,23 +1812,21 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
   if (SUM) summary_words(reinterpret_cast<const EgoTileWork*>(rec_s), pf_lo, pf_hi);
 #if BCG_EGS_DYNAMIC
   for (int it = 0;; ++it) {
-    const int job = ids_s[it & 7];
-    if (job >= n) break;
-    const int e = env_of(job);
+    const int e = ids_s[it & 7];
+    if (e >= n) break;
     int drawn = 0;
-    if (tid == 0) drawn = (RD + 1) * G + atomicAdd(counter, 1);                  // stored at the end of the iteration
+    if (tid == 0) drawn = (RD + 1) * G + atomicAdd(b.ego_list + n + 1, 1);       // stored at the end of the iteration
     const int slot = it & (BCG_EGS_REC_SLOTS - 1), par = it & 1;
     fetch_record(ids_s[(it + RD) & 7], (it + RD) & (BCG_EGS_REC_SLOTS - 1));
     cp_async_commit();
     const int e_next = ids_s[(it + 1) & 7];
 #else
-  int job = e0;
-  for (int it = 0; job < n; job += G, ++it) {
-    const int e = env_of(job);
+  int e = e0;
+  for (int it = 0; e < n; e += G, ++it) {
     const int slot = it & (BCG_EGS_REC_SLOTS - 1), par = it & 1;
-    fetch_record(job + RD * G, (it + RD) & (BCG_EGS_REC_SLOTS - 1));
+    fetch_record(e + RD * G, (it + RD) & (BCG_EGS_REC_SLOTS - 1));
     cp_async_commit();
-    const int e_next = job + G;
+    const int e_next = e + G;
 #endif
     // record it + 1 has landed (only the newest fetch may still be in flight): start its summary loads now
     const uint32_t cur_lo = pf_lo, cur_hi = pf_hi;
@@ -1880,9 +1842,7 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
     // maps with more than one cell in 20 occupied (filled regions, inflation gradients) overflow the cell list in
     // almost every window: they go straight to the dense kernel instead of paying for a scan that is thrown away
     const bool dense_map = (r->dense_map & 1) != 0;     // decided by the record writer, which holds the map descriptor
-    const bool skip = pass == 0 && fix != nullptr && (r->dense_map & BCG_EGO_DEFERRED) != 0;     // the second pass renders it
-    const bool try_sparse = !skip && mode == BCG_EGO_MODE_TILES && ntile <= BCG_EGS_MAX_TILES && !dense_map &&
-                            (!SUM || (nby <= 32 && nwx <= 32));
+    const bool try_sparse = mode == BCG_EGO_MODE_TILES && ntile <= BCG_EGS_MAX_TILES && !dense_map && (!SUM || (nby <= 32 && nwx <= 32));
     if (try_sparse) {
       // ---- 1. zero the crop in global memory ----------------------------------------------------------------------
       {
@@ -2128,8 +2088,6 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
           }
         }
       }
-    } else if (skip) {
-      // (nothing: rendered by the second pass)
     } else if (b.flags & BCG_BATCH_SPARSE_EGO_ONLY) {
       // No dense pass follows this kernel (the host knows that no map of the batch is dense): the rare window that
       // overflows the cell list, or lies outside any sane range, is rendered here by the bounds-checked per-pixel gather.
@@ -2160,7 +2118,7 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
     }
     if (tid == 0) T.count[par ^ 1] = 0;         // nobody reads the other counter before the next barrier
     if (HITS) {                                 // (the hit counter of this env is complete after the barrier below)
-      if (!sparse && !skip && tid == 0) hit_count[e] = -1;       // rendered densely: the consumer reads the image itself
+      if (!sparse && tid == 0) hit_count[e] = -1;       // rendered densely: the consumer reads the image itself
       __syncthreads();
       if (sparse && tid == 0) hit_count[e] = (int32_t)T.hits[par];      // > hit_cap: the list overflowed, read the image
       if (tid == 0) T.hits[par ^ 1] = 0;
@@ -2169,17 +2127,6 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
     if (tid == 0) ids_s[(it + RD + 1) & 7] = drawn;
 #endif
     __syncthreads();                            // list, tables and record `it` are free
-  }
-  }   // e0 < n
-  if (pass == 1 && tid == 0) {
-    // the last CTA of the second pass empties the list for the next step (count, env counter, this ticket)
-    int32_t* const fx = b.ego_fix + b.n_envs;
-    __threadfence();
-    if (atomicAdd(fx + 2, 1) == (int)gridDim.x - 1) {
-      fx[0] = 0;
-      fx[1] = 0;
-      fx[2] = 0;
-    }
   }
 }
 
@@ -2571,8 +2518,7 @@ struct EgoHits {       // BcgStepOut.ego_hits / ego_hit_count / ego_hit_cap (all
   int cap;
 };
 
-static int launch_ego_sparse(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, const EgoHits& hits, cudaStream_t s,
-                             int pass = 0, const uint8_t* done = nullptr) {
+static int launch_ego_sparse(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, const EgoHits& hits, cudaStream_t s) {
   int sms = 0;
   if (int rc = sm_count_of_current_device(&sms)) return rc;
   // (the hand-over count and the env counter in ego_list[n_envs ..] were zeroed by the state / prep kernel)
@@ -2594,15 +2540,14 @@ static int launch_ego_sparse(const BcgParams* p, const BcgBatch* b, uint8_t* ego
       tab_cache[sum][dev] = tab_bytes;
     }
   }
-  int grid = b->n_envs < per_sm * sms ? b->n_envs : per_sm * sms;
-  if (pass == 1 && grid > 2 * sms) grid = 2 * sms;             // the second pass renders the few listed envs
+  const int grid = b->n_envs < per_sm * sms ? b->n_envs : per_sm * sms;
   // (the variant that also records the compact hit lists has the same shared-memory footprint and register budget)
   if (hits.list) {
-    if (sum) ego_sparse_kernel<true, true><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image, hits.list, hits.count, hits.cap, pass, done);
-    else ego_sparse_kernel<false, true><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image, hits.list, hits.count, hits.cap, pass, done);
+    if (sum) ego_sparse_kernel<true, true><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image, hits.list, hits.count, hits.cap);
+    else ego_sparse_kernel<false, true><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image, hits.list, hits.count, hits.cap);
   } else {
-    if (sum) ego_sparse_kernel<true, false><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image, nullptr, nullptr, 0, pass, done);
-    else ego_sparse_kernel<false, false><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image, nullptr, nullptr, 0, pass, done);
+    if (sum) ego_sparse_kernel<true, false><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image, nullptr, nullptr, 0);
+    else ego_sparse_kernel<false, false><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image, nullptr, nullptr, 0);
   }
   BCG_CHECK_CUDA(cudaGetLastError());
   if (b->flags & BCG_BATCH_SPARSE_EGO_ONLY) return BCG_OK;     // the sparse kernel rendered every env itself
@@ -2632,12 +2577,6 @@ static int launch_ego_image(const BcgParams* p, const BcgBatch* b, uint8_t* ego_
   ego_kernel<<<b->n_envs, BCG_EGO_THREADS, cap + extra, s>>>(*p, *b, ego_image, cap);
   BCG_CHECK_CUDA(cudaGetLastError());
   return BCG_OK;
-}
-
-static void launch_reward(const BcgParams* p, const BcgBatch* b, const BcgStepOut* out, int cap, cudaStream_t s) {
-  if (b->n_envs > 16384) reward_kernel<8><<<blocks_for((int64_t)b->n_envs * 8, BCG_REWARD_THREADS), BCG_REWARD_THREADS, 0, s>>>(*p, *b, *out, cap);
-  else if (b->n_envs > 2048) reward_kernel<16><<<blocks_for((int64_t)b->n_envs * 16, BCG_REWARD_THREADS), BCG_REWARD_THREADS, 0, s>>>(*p, *b, *out, cap);
-  else reward_kernel<32><<<blocks_for((int64_t)b->n_envs * 32, BCG_REWARD_THREADS), BCG_REWARD_THREADS, 0, s>>>(*p, *b, *out, cap);
 }
 
 extern "C" {
@@ -2672,29 +2611,9 @@ int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, 
                                                                                     *out, cap);
     BCG_CHECK_CUDA(cudaGetLastError());
     if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[2], s));
-    if (b->ego_fix && out->ego_image) {
-      // The reward kernel BESIDE the egocentric kernel: fork after move_kernel, reward on the caller's side stream, first
-      // egocentric pass on the main stream (envs that may be reset are left out), join, second pass for those.
-      BCG_REQUIRE(b->side_stream && b->ev_fork && b->ev_join && b->ego_init && out->done && b->ego_list && b->cell_tile_arena &&
-                      b->occ_tile_arena && (b->flags & BCG_BATCH_SPARSE_EGO_ONLY) && !ego_dense_kernel_requested(),
-                  "BcgBatch.ego_fix needs side_stream, ev_fork, ev_join, ego_init, BcgStepOut.done and a batch of sparse maps");
-      cudaStream_t side = (cudaStream_t)b->side_stream;
-      BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)b->ev_fork, s));
-      BCG_CHECK_CUDA(cudaStreamWaitEvent(side, (cudaEvent_t)b->ev_fork, 0));
-      launch_reward(p, b, out, cap, side);
-      BCG_CHECK_CUDA(cudaGetLastError());
-      if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[3], side));
-      BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)b->ev_join, side));
-      BCG_REQUIRE((out->ego_hits != nullptr) == (out->ego_hit_count != nullptr) && (!out->ego_hits || out->ego_hit_cap > 0),
-                  "ego_hits, ego_hit_count and ego_hit_cap go together");
-      const EgoHits hits{out->ego_hits, out->ego_hit_count, out->ego_hit_cap};
-      if (int rc = launch_ego_sparse(p, b, out->ego_image, hits, s, 0, nullptr)) return rc;
-      BCG_CHECK_CUDA(cudaStreamWaitEvent(s, (cudaEvent_t)b->ev_join, 0));
-      if (int rc = launch_ego_sparse(p, b, out->ego_image, hits, s, 1, out->done)) return rc;
-      if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[4], s));
-      return BCG_OK;
-    }
-    launch_reward(p, b, out, cap, s);
+    if (b->n_envs > 16384) reward_kernel<8><<<blocks_for((int64_t)b->n_envs * 8, BCG_REWARD_THREADS), BCG_REWARD_THREADS, 0, s>>>(*p, *b, *out, cap);
+    else if (b->n_envs > 2048) reward_kernel<16><<<blocks_for((int64_t)b->n_envs * 16, BCG_REWARD_THREADS), BCG_REWARD_THREADS, 0, s>>>(*p, *b, *out, cap);
+    else reward_kernel<32><<<blocks_for((int64_t)b->n_envs * 32, BCG_REWARD_THREADS), BCG_REWARD_THREADS, 0, s>>>(*p, *b, *out, cap);
     BCG_CHECK_CUDA(cudaGetLastError());
   }
   if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[3], s));

@@ -80,7 +80,6 @@ class _VecSlotEnv(VecPlanEnv):
         self._make_batch()
         # generated worlds are thin walls (BcgMapDesc.occupied stays 0): no env ever needs the dense egocentric kernel
         self._batch.flags |= nat.BATCH_SPARSE_EGO_ONLY
-        self._enable_reward_overlap()
 
     def _alloc_slots(self, record_bytes):
         n, dev = self.n_envs, self.device

@@ -85,7 +85,7 @@ class VecPlanEnv(object):
     def __init__(self, costmaps, paths, params=None, n_envs=None, map_ids=None, path_ids=None,
                  noise_parameters=DEFAULT_NOISE, seed=0, auto_reset=False, device=None, env_id_base=0,
                  private_map_copies=False, with_ego=False, footprint_scale=1.0, use_tma=True, footprint=None,
-                 ego_staging='tiles', ego_sparse=True, compact_ego=False, overlap_reward=True):
+                 ego_staging='tiles', ego_sparse=True, compact_ego=False):
         """
         :param costmaps: pool of CostMap2D (uint8), one resolution
         :param paths: pool of oriented paths, array(n, 3); refined here when params.refine_path
@@ -101,9 +101,6 @@ class VecPlanEnv(object):
             'tma' (box loads of the window's bounding box from the uint8 rows) or 'spans' (plain loads)
         :param compact_ego: also keep, per env, the list of non-zero crop pixels (BcgStepOut.ego_hits): what
             `step_host(images='compact')` sends to the host instead of whole crops (needs with_ego and the sparse kernel)
-        :param overlap_reward: run the step's reward kernel BESIDE the egocentric kernel on a side stream instead of before
-            it (batches of sparse maps with the egocentric observation on; envs the step may reset are rendered by a
-            short second pass).  False: the three kernels run one after the other
         :param ego_sparse: with 'tiles' staging, render crops with the sparse scatter kernel (occupancy plane; the dense
             cell-tile kernel only takes the envs it hands over).  False: the dense kernel renders every env
         """
@@ -117,7 +114,6 @@ class VecPlanEnv(object):
         self._ego_sparse = bool(ego_sparse) and not all(
             np.count_nonzero(c.get_data()) * 20 > c.get_data().size for c in costmaps)
         self._compact_ego = bool(compact_ego)
-        self._overlap_reward = bool(overlap_reward)
         self._configure(params, n, float(costmaps[0].get_resolution()), noise_parameters, seed, auto_reset, device,
                         env_id_base, with_ego, ego_staging if use_tma else 'spans')   # use_tma=False: older spelling
         self._map_pool = costmaps
@@ -142,7 +138,6 @@ class VecPlanEnv(object):
             dense = d['occupied'].astype(np.int64) * 20 > d['width'].astype(np.int64) * d['height'].astype(np.int64)
             if not dense.any():
                 self._batch.flags |= nat.BATCH_SPARSE_EGO_ONLY
-        self._enable_reward_overlap()
 
     def _configure(self, params, n_envs, resolution, noise_parameters, seed, auto_reset, device, env_id_base, with_ego,
                    ego_staging):
@@ -337,8 +332,6 @@ class VecPlanEnv(object):
         self._cand_i = torch.zeros((2, n), dtype=torch.int32, device=dev)
         self._work = torch.zeros((n, 192), dtype=torch.uint8, device=dev)
         self._ego_work = torch.zeros((n, 128), dtype=torch.uint8, device=dev)
-        self._ego_init = torch.zeros((n, 128), dtype=torch.uint8, device=dev)      # egocentric records of the initial states
-        self._ego_fix = torch.zeros(n + 4, dtype=torch.int32, device=dev)           # envs of the second egocentric pass
         self._step_counter = torch.zeros(2, dtype=torch.int64, device=dev)
         self._status = torch.zeros(nat.STATUS_WORDS, dtype=torch.int32, device=dev)
         self._stats = torch.zeros(nat.STATS_WORDS, dtype=torch.float64, device=dev)
@@ -361,8 +354,6 @@ class VecPlanEnv(object):
         b.init_f, b.init_i = self.init_f.data_ptr(), self.init_i.data_ptr()
         b.cand, b.cand_i, b.work = self._cand.data_ptr(), self._cand_i.data_ptr(), self._work.data_ptr()
         b.ego_work = self._ego_work.data_ptr()
-        if self.with_ego:
-            b.ego_init = self._ego_init.data_ptr()           # written by bcg_init_state / the generators
         b.map_id, b.path_id = self.map_id.data_ptr(), self.path_id.data_ptr()
         b.maps, b.paths = self.map_descs.data_ptr(), self.path_descs.data_ptr()
         b.map_arena, b.tile_arena, b.path_arena = self.map_arena.data_ptr(), self.tile_arena.data_ptr(), self.path_arena.data_ptr()
@@ -407,24 +398,6 @@ class VecPlanEnv(object):
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-
-    def _enable_reward_overlap(self):
-        """The reward kernel beside the egocentric kernel (BcgBatch.ego_fix): for batches of sparse maps whose step
-        assembles the egocentric observation."""
-        self._side = None
-        if not (getattr(self, '_overlap_reward', True) and self.with_ego and self._ego_list is not None
-                and self._batch.flags & nat.BATCH_SPARSE_EGO_ONLY and os.environ.get("BCG_EGO_KERNEL") != "dense"
-                and os.environ.get("BCG_OVERLAP_REWARD", "1") != "0"):
-            return
-        self._side = torch.cuda.Stream(device=self.device, priority=-1)
-        self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
-        cur = torch.cuda.current_stream(self.device)
-        self._ev_fork.record(cur)                            # (creates the handles)
-        self._ev_join.record(cur)
-        b = self._batch
-        b.ego_fix = self._ego_fix.data_ptr()
-        b.side_stream = self._side.cuda_stream
-        b.ev_fork, b.ev_join = self._ev_fork.cuda_event, self._ev_join.cuda_event
 
     # ---- the env API ---------------------------------------------------------------------------
     @property
@@ -499,8 +472,6 @@ class VecPlanEnv(object):
             return n
         if self._ego_list is None or os.environ.get("BCG_EGO_KERNEL") == "dense":
             return n + 1                                   # one dense kernel
-        if getattr(self, '_side', None) is not None:
-            return n + 2                                   # two passes of the sparse kernel, the reward kernel beside the first
         return n + (1 if self._batch.flags & nat.BATCH_SPARSE_EGO_ONLY else 2)
 
     def step_timed(self, actions, events):

@@ -504,13 +504,7 @@ def timed_steps(env, actions, steps, D, sampler=None):
     ms = D.max_ms(t_start.elapsed_time(t_end))
     kern = {"move_kernel": float(np.mean([e[1].elapsed_time(e[2]) for e in ev])),
             "reward_kernel": float(np.mean([e[2].elapsed_time(e[3]) for e in ev]))}
-    if getattr(env, "_side", None) is not None:
-        # the reward kernel runs on a side stream BESIDE the egocentric kernel: its span and the span of the two egocentric
-        # passes both start at the end of move_kernel and overlap
-        kern["reward_kernel_runs_beside_ego"] = True
-        kern["ego"] = float(np.mean([e[2].elapsed_time(e[4]) for e in ev]))
-    else:
-        kern["ego"] = float(np.mean([e[3].elapsed_time(e[4]) for e in ev]))
+    kern["ego"] = float(np.mean([e[3].elapsed_time(e[4]) for e in ev]))
     return ms, kern, stats
 
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BCG_ABI_VERSION 9
+#define BCG_ABI_VERSION 8
 
 /* error codes */
 #define BCG_OK 0
@@ -217,16 +217,6 @@ typedef struct BcgBatch {
                             egocentric kernel loads only the non-empty tiles of a window                              */
   uint32_t* status; /* [BCG_STATUS_WORDS] */
   double* stats;    /* [BCG_STATS_WORDS]  */
-  /* optional, all or none: the reward kernel runs BESIDE the egocentric kernel (on side_stream) instead of before it.
-   * Needs BCG_BATCH_SPARSE_EGO_ONLY, ego_list and BcgStepOut.done.  Envs that this step's verdict may reset are listed in
-   * ego_fix by the move kernel, left out by the first egocentric pass and rendered by a second pass after the join --
-   * from the step's record, or from ego_init when the env was reset. */
-  void* ego_init;         /* device [n_envs][128 bytes]: the egocentric record of every env's INITIAL state, written by
-                            bcg_init_state / bcg_generate_* when set                                                */
-  int32_t* ego_fix;       /* device scratch [n_envs + 4], zero at start                                             */
-  void* side_stream;      /* cudaStream_t, ideally of higher priority than the caller's                              */
-  void* ev_fork;          /* cudaEvent_t (timing not needed)                                                         */
-  void* ev_join;          /* cudaEvent_t                                                                             */
   uint64_t* step_counter; /* optional device [2], zero at start: when set, bcg_step ignores its step_index argument,
                             takes the step index from word 0 and increments it on the device when the step is done
                             (word 1 is its scratch) -- so that a captured CUDA graph of a step can be replayed
@@ -364,9 +354,9 @@ int bcg_step(const BcgParams* p, const BcgBatch* b, const void* actions, int32_t
              uint64_t step_index, const BcgStepOut* out, void* stream);
 
 /* bcg_step with per-kernel timing hooks: events[0..4] are caller-created cudaEvent_t handles (timing
- * enabled): [1] before and [2] after the move kernel, [3] after the reward kernel, [4] after the egocentric kernels
- * ([0] coincides with [1]).  All on `stream` -- except that with BcgBatch.ego_fix [3] is recorded on side_stream, where
- * the reward kernel then runs, and [2]..[4] spans both egocentric passes.  events == NULL behaves exactly like bcg_step. */
+ * enabled) recorded on `stream`: [2] before and [3] after the state kernel, [4] after the egocentric kernels
+ * ([0], [1] coincide with [2]; with BCG_STEP_KERNELS=split they bracket the kinematic and collide/reward
+ * kernels of round 1).  events == NULL behaves exactly like bcg_step. */
 int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, int32_t action_is_f64,
                     uint64_t step_index, const BcgStepOut* out, void* const* events, void* stream);
 

@@ -93,7 +93,7 @@ def times():
              "kin": float(np.mean([e[0].elapsed_time(e[1]) for e in ev])),
              "cr": float(np.mean([e[1].elapsed_time(e[2]) for e in ev])),
              "state_or_commit": float(np.mean([e[2].elapsed_time(e[3]) for e in ev])),
-             "ego": float(np.mean([e[2 if getattr(env, "_side", None) is not None else 3].elapsed_time(e[4]) for e in ev]))}
+             "ego": float(np.mean([e[3].elapsed_time(e[4]) for e in ev]))}
         t0.record()
         for k in range(K):
             env.step(actions[k % 16])

@@ -58,7 +58,7 @@ def test_b200_arm_prints_the_contract_line():
         assert key in d, key
     assert "impl" not in d and d["metric"] == "env_steps_per_sec" and d["steps"] == 5 and d["warmup"] == 3
     assert abs(d["value"] - 2048 * 5 / (d["ms_per_step"] * 5e-3)) < 1e-6 * d["value"]
-    assert d["gpu_launches"] == 5 * 4                      # move_kernel, reward_kernel beside the first egocentric pass, second pass
+    assert d["gpu_launches"] == 5 * 3                      # move_kernel, reward_kernel, sparse egocentric kernel per step
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] > 0
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["traffic"] is None      # ncu traffic is for 65 536 envs

@@ -81,7 +81,7 @@ def test_sparse_kernel_renders_overflowing_windows_itself():
     cm, path = _blob_world()
     assert np.count_nonzero(cm.get_data()) * 20 < cm.get_data().size
     env = VecPlanEnv([cm], [path], EnvParams(), n_envs=64, noise_parameters=None, with_ego=True, compact_ego=True)
-    assert env._batch.flags & nat.BATCH_SPARSE_EGO_ONLY and env.launches_per_step() == 4
+    assert env._batch.flags & nat.BATCH_SPARSE_EGO_ONLY and env.launches_per_step() == 3
     rng = np.random.RandomState(0)
     poses = np.stack([rng.uniform(5.0, 12.0, 64), rng.uniform(5.5, 9.5, 64), rng.uniform(-np.pi, np.pi, 64)], axis=1)
     env.state_f[nat.F_DPOSE:nat.F_DPOSE + 3] = torch.from_numpy(poses.T.copy()).cuda()
