@@ -307,6 +307,20 @@ class PlanEnv(object):
     def _from_state(self, state):
         v = self._vec
         L = v.layout
+        # The reference's set_state adopts the State wholesale, map and path included (envs/base/env.py:278-285).  Here the
+        # map and the path live in device arenas that a snapshot does not carry, so a State taken from ANOTHER world is
+        # refused instead of being applied to this env's map and path silently.
+        full = v.full_path(0)
+        if state.original_path is not None and (np.shape(state.original_path) != np.shape(full) or
+                                                not np.array_equal(np.asarray(state.original_path), full)):
+            raise ValueError("set_state: the State belongs to an env with another path; build a new env for it")
+        if state.costmap is not None and (state.costmap.get_data().shape != self._costmap.get_data().shape or
+                                          not np.array_equal(state.costmap.get_data(), self._costmap.get_data()) or
+                                          not np.array_equal(state.costmap.get_origin(), self._costmap.get_origin())):
+            raise ValueError("set_state: the State belongs to an env with another costmap; build a new env for it")
+        if state.iter_timeout is not None and int(state.iter_timeout) != int(self._params.iteration_timeout):
+            raise ValueError("set_state: the State was taken with iteration_timeout %s, this env has %s"
+                             % (state.iter_timeout, self._params.iteration_timeout))
         f = np.zeros(L.n_frows, dtype=np.float64)
         i = np.zeros(L.n_irows, dtype=np.int32)
         row = state.robot_state.as_row()
