@@ -156,7 +156,7 @@ SYMBOLS = {
     "bcg_observe_ego": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgBatch), _P, _P, _P]),
     "bcg_gather_state": (C.c_int, [C.POINTER(BcgBatch), _P, C.c_int32, _P, _P, _P]),
     "bcg_scatter_state": (C.c_int, [C.POINTER(BcgBatch), _P, C.c_int32, _P, _P, C.c_int32, _P]),
-    "bcg_pack_ego_hits": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
+    "bcg_pack_ego_hits": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P]),
     "bcg_world_to_pixel": (C.c_int, [_P, C.c_int64, C.c_double, C.c_double, C.c_double, _P, _P]),
     "bcg_normalize_angle": (C.c_int, [_P, C.c_int64, _P, _P]),
     "bcg_masked_any_equal": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P]),

@@ -528,6 +528,8 @@ __device__ __forceinline__ bool collide_thread(const BcgFootprintLut& lut, const
       asm volatile("prefetch.global.L2 [%0];" ::"l"(tp));
     }
     int kb = 0;                                            // wide footprints: band by band
+    int vband = -1;                                        // band whose mask rows v[] holds
+    uint64_t v[18];
     while (flat ? (todo != 0u) : (kb < MAXB)) {
       int k, j;
       if (flat) {
@@ -553,16 +555,19 @@ __device__ __forceinline__ bool collide_thread(const BcgFootprintLut& lut, const
       uint32_t hit = 0u;
       if (wpr == 1 && pair_rows) {
         // the band's 16 mask rows as nine aligned 16-byte pairs starting at the even row at or below dy0 (rows beyond
-        // the mask are zero in the table; pairs outside the bin's max_rows rows are not loaded)
+        // the mask are zero in the table; pairs outside the bin's max_rows rows are not loaded).  The tiles of a thread's
+        // list come band by band, so the rows are kept for the next tile of the same band
         const int base = dy0 & ~1, odd = dy0 & 1;
-        uint64_t v[18];
+        if (k != vband) {
+          vband = k;
 #pragma unroll
-        for (int jj = 0; jj < 9; ++jj) {
-          const int r0 = base + 2 * jj;
-          ulonglong2 q = make_ulonglong2(0ull, 0ull);
-          if ((unsigned)r0 < (unsigned)lut.max_rows) q = __ldg(reinterpret_cast<const ulonglong2*>(rows + r0));
-          v[2 * jj] = q.x;
-          v[2 * jj + 1] = q.y;
+          for (int jj = 0; jj < 9; ++jj) {
+            const int r0 = base + 2 * jj;
+            ulonglong2 q = make_ulonglong2(0ull, 0ull);
+            if ((unsigned)r0 < (unsigned)lut.max_rows) q = __ldg(reinterpret_cast<const ulonglong2*>(rows + r0));
+            v[2 * jj] = q.x;
+            v[2 * jj + 1] = q.y;
+          }
         }
         const uint32_t ws[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
 #pragma unroll

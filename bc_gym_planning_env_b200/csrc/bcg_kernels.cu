@@ -2178,17 +2178,24 @@ __global__ void __launch_bounds__(256) scatter_kernel(const BcgBatch b, const in
 }
 
 // ego_hits lists of all envs, fixed stride -> one contiguous array (offsets: exclusive prefix sum of the clamped counts);
-// eight lanes per env
+// eight lanes per env.  OFFSETS_ONLY: 16-bit pixel offsets without the cost values (batches whose maps hold no cost value
+// but 254: the value is implied)
+template <bool OFFSETS_ONLY>
 __global__ void __launch_bounds__(256) pack_hits_kernel(const uint32_t* __restrict__ hits, const int32_t* __restrict__ counts,
                                                         const int cap, const int n, const int64_t* __restrict__ offsets,
-                                                        uint32_t* __restrict__ packed) {
+                                                        void* __restrict__ packed) {
   const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, gl = threadIdx.x & 7;
   if (e >= n) return;
   const int c = counts[e];
   if (c <= 0 || c > cap) return;                 // rendered densely / list overflowed: the consumer reads the image
   const uint32_t* src = hits + (int64_t)e * cap;
-  uint32_t* dst = packed + offsets[e];
-  for (int i = gl; i < c; i += 8) dst[i] = src[i];
+  if (OFFSETS_ONLY) {
+    uint16_t* dst = reinterpret_cast<uint16_t*>(packed) + offsets[e];
+    for (int i = gl; i < c; i += 8) dst[i] = (uint16_t)(src[i] & 0xffffu);
+  } else {
+    uint32_t* dst = reinterpret_cast<uint32_t*>(packed) + offsets[e];
+    for (int i = gl; i < c; i += 8) dst[i] = src[i];
+  }
 }
 
 // is_footprint_colliding_impl: any(values[mask] == value) over flattened arrays
@@ -2685,10 +2692,11 @@ int bcg_scatter_state(const BcgBatch* b, const int64_t* idx, int32_t k, const do
 }
 
 int bcg_pack_ego_hits(const uint32_t* hits, const int32_t* counts, int32_t cap, int32_t n, const int64_t* offsets,
-                      uint32_t* packed, void* stream) {
+                      void* packed, int32_t offsets_only, void* stream) {
   BCG_REQUIRE(hits && counts && offsets && packed && cap > 0 && n >= 0, "bad pack arguments");
   if (n == 0) return BCG_OK;
-  pack_hits_kernel<<<blocks_for((int64_t)n * 8, 256), 256, 0, (cudaStream_t)stream>>>(hits, counts, cap, n, offsets, packed);
+  if (offsets_only) pack_hits_kernel<true><<<blocks_for((int64_t)n * 8, 256), 256, 0, (cudaStream_t)stream>>>(hits, counts, cap, n, offsets, packed);
+  else pack_hits_kernel<false><<<blocks_for((int64_t)n * 8, 256), 256, 0, (cudaStream_t)stream>>>(hits, counts, cap, n, offsets, packed);
   BCG_CHECK_CUDA(cudaGetLastError());
   return BCG_OK;
 }

@@ -46,6 +46,12 @@ def footprint_lut_for(robot_name, resolution, footprint_scale=1.0, footprint=Non
     return _LUT_CACHE[key]
 
 
+def _device_world_types():
+    """batch classes whose maps are rewritten on the device (their descriptors' flags can change after a reset)"""
+    from bc_gym_planning_env_b200 import vec_aisle_env
+    return (vec_aisle_env._VecSlotEnv,)
+
+
 class VecObservation(object):
     """Batched Observation (reference envs/base/obs.py:14-23): views into the live state tensors --
     like the reference's Observation they alias env state and change on the next step."""
@@ -550,11 +556,16 @@ class VecPlanEnv(object):
     def _compact_to_host(self, io, side):
         """The egocentric observation of the step just launched as per-env lists of non-zero pixels, packed on the
         device and copied to pinned host memory: dict(counts int32 [N] (-1 / > cap: see dense_envs), offsets int64 [N],
-        packed uint32 [total] (pixel offset | value << 16), dense_envs int64 [k], dense_images uint8 [k, H, W],
+        packed (uint32 [total]: pixel offset | value << 16 -- or, when every map of the batch holds no cost value but 254,
+        uint16 [total]: the pixel offsets alone, `value` = 254), dense_envs int64 [k], dense_images uint8 [k, H, W],
         bytes = bytes that crossed the link for the images).  Expand with `expand_compact`."""
         if self._ego_hits is None:
             raise ValueError("this batch was built without compact_ego=True")
         n, cap = self.n_envs, self.EGO_HIT_CAP
+        if getattr(self, '_only_lethal', None) is None:          # (read once: do all maps hold nothing but 0 and 254?)
+            d = np.frombuffer(self.map_descs.cpu().numpy().tobytes(), dtype=np.dtype(nat.BcgMapDesc))
+            self._only_lethal = bool(np.all(d['flags'] & nat.MAP_ONLY_LETHAL)) and not isinstance(self, _device_world_types())
+        short = self._only_lethal
         counts = self._ego_hit_count
         listed = (counts > 0) & (counts <= cap)
         c = torch.where(listed, counts, torch.zeros_like(counts)).to(torch.int64)
@@ -564,13 +575,14 @@ class VecPlanEnv(object):
         total = int(ends[-1])                                    # (synchronises: the size of the copy is data)
         if 'packed_dev' not in io or io['packed_dev'].numel() < total:
             size = max(total * 5 // 4, n * 64)
-            io['packed_dev'] = torch.empty(size, dtype=torch.int32, device=self.device)
-            io['packed'] = torch.empty(size, dtype=torch.int32).pin_memory()
+            dt = torch.int16 if short else torch.int32
+            io['packed_dev'] = torch.empty(size, dtype=dt, device=self.device)
+            io['packed'] = torch.empty(size, dtype=dt).pin_memory()
             io['counts'] = torch.empty(n, dtype=torch.int32).pin_memory()
             io['offsets'] = torch.empty(n, dtype=torch.int64).pin_memory()
             io['goal_n_state'] = torch.empty(tuple(self.goal_n_state.shape), dtype=torch.float32).pin_memory()
         nat.check(nat.lib().bcg_pack_ego_hits(nat.ptr(self._ego_hits), nat.ptr(counts), cap, n, nat.ptr(offsets),
-                                              nat.ptr(io['packed_dev']), self._stream()))
+                                              nat.ptr(io['packed_dev']), 1 if short else 0, self._stream()))
         io['packed'][:total].copy_(io['packed_dev'][:total], non_blocking=True)
         io['counts'].copy_(counts, non_blocking=True)
         io['offsets'].copy_(offsets, non_blocking=True)
@@ -579,8 +591,8 @@ class VecPlanEnv(object):
         if dense.numel():
             dense_images = self.ego_image[dense].reshape(dense.numel(), self.ego_image.shape[1], self.ego_image.shape[2]).cpu()
         return dict(counts=io['counts'], offsets=io['offsets'], packed=io['packed'][:total], dense_envs=dense.cpu(),
-                    dense_images=dense_images, cap=cap,
-                    bytes=total * 4 + n * 12 + (0 if dense_images is None else dense_images.numel()))
+                    dense_images=dense_images, cap=cap, value=254 if short else None,
+                    bytes=total * (2 if short else 4) + n * 12 + (0 if dense_images is None else dense_images.numel()))
 
     @staticmethod
     def expand_compact(compact, height, width):
@@ -591,8 +603,11 @@ class VecPlanEnv(object):
         listed = (counts > 0) & (counts <= compact['cap'])
         c = np.where(listed, counts, 0).astype(np.int64)
         env = np.repeat(np.arange(n), c)
-        words = compact['packed'].numpy().view(np.uint32)
-        out[env, words & 0xffff] = (words >> 16).astype(np.uint8)
+        if compact['value'] is not None:                         # 16-bit offsets, one implied cost value
+            out[env, compact['packed'].numpy().view(np.uint16)] = compact['value']
+        else:
+            words = compact['packed'].numpy().view(np.uint32)
+            out[env, words & 0xffff] = (words >> 16).astype(np.uint8)
         out = out.reshape(n, height, width)
         if compact['dense_images'] is not None:
             out[compact['dense_envs'].numpy()] = compact['dense_images'].numpy()

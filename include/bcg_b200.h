@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BCG_ABI_VERSION 8
+#define BCG_ABI_VERSION 9
 
 /* error codes */
 #define BCG_OK 0
@@ -393,9 +393,11 @@ int bcg_scatter_state(const BcgBatch* b, const int64_t* idx, int32_t k, const do
 /* Packs the per-env hit lists a step left in BcgStepOut.ego_hits (fixed stride `cap`) into one contiguous array:
  * env e's min(count, cap) entries go to packed[offsets[e] ..], offsets = exclusive prefix sum of the counts with
  * dense / overflowed envs (count < 0 or > cap) counted as 0 -- what a host consumer copies over the link instead
- * of n crops of ego_w x ego_h bytes. */
+ * of n crops of ego_w x ego_h bytes.  offsets_only == 0: packed is uint32 (pixel offset | value << 16);
+ * offsets_only != 0: packed is uint16, the pixel offsets alone (for batches whose maps hold no cost value but 254,
+ * BCG_MAP_ONLY_LETHAL: the value is implied). */
 int bcg_pack_ego_hits(const uint32_t* hits, const int32_t* counts, int32_t cap, int32_t n, const int64_t* offsets,
-                      uint32_t* packed, void* stream);
+                      void* packed, int32_t offsets_only, void* stream);
 
 /* -- hook-seam helpers (batched forms of the brain.shining_utils.* scalars) --------------------- */
 /* world_to_pixel (coordinate_transformations.py:185-205): xy [n][2] fp64 -> int32 [n][2] */
