@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 
 #include "bcg_b200.h"
 #include "bcg_device.cuh"
@@ -426,13 +427,18 @@ __device__ __forceinline__ void write_ego_tile_record(const BcgParams& p, const 
 // rounding errors ~1e-4 px) with the 0.51 px sample margin widened to 0.53.
 __device__ __forceinline__ uint32_t ego_band_span(const EgoAffine& A, int ego_w, int ego_h, int X0, int Y0, int ntx, int nty,
                                                   int t) {
-  const double uw = (double)(ego_w - 1), vh = (double)(ego_h - 1);
-  const double bx = A.b1 - (double)X0, by = A.b2 - (double)Y0;
-  const float qx[4] = {(float)bx, (float)(A.a11 * uw + bx), (float)(A.a11 * uw + A.a12 * vh + bx), (float)(A.a12 * vh + bx)};
-  const float qy[4] = {(float)by, (float)(A.a21 * uw + by), (float)(A.a21 * uw + A.a22 * vh + by), (float)(A.a22 * vh + by)};
+  // corners q0 = b, q1 = q0 + U, q2 = q1 + V, q3 = q0 + V with U = (w - 1)(a11, a21), V = (h - 1)(a12, a22); the edges
+  // q0q1 and q2q3 share the slope U.x / U.y, the other two V.x / V.y: two approximate divisions (2 ulp) per env
+  const float bx = (float)(A.b1 - (double)X0), by = (float)(A.b2 - (double)Y0);
+  const float uwf = (float)(ego_w - 1), vhf = (float)(ego_h - 1);
+  const float ux = (float)A.a11 * uwf, uy = (float)A.a21 * uwf, vx = (float)A.a12 * vhf, vy = (float)A.a22 * vhf;
+  const float qx[4] = {bx, bx + ux, bx + ux + vx, bx + vx};
+  const float qy[4] = {by, by + uy, by + uy + vy, by + vy};
+  const float edy[4] = {uy, vy, -uy, -vy};
+  const float inv_u = uy != 0.f ? __fdividef(ux, uy) : 0.f, inv_v = vy != 0.f ? __fdividef(vx, vy) : 0.f;
   const float xlo = fminf(fminf(qx[0], qx[1]), fminf(qx[2], qx[3])), xhi = fmaxf(fmaxf(qx[0], qx[1]), fmaxf(qx[2], qx[3]));
   const float ylo = fminf(fminf(qy[0], qy[1]), fminf(qy[2], qy[3])), yhi = fmaxf(fmaxf(qy[0], qy[1]), fmaxf(qy[2], qy[3]));
-  const bool ccw = (qx[1] - qx[0]) * (qy[3] - qy[0]) - (qy[1] - qy[0]) * (qx[3] - qx[0]) > 0.f;
+  const bool ccw = ux * vy - uy * vx > 0.f;
   const float BIG = 1e30f, M = 0.53f;
   const float y0 = fmaxf((float)(8 * t) - M, ylo), y1 = fminf((float)(8 * t + 7) + M, yhi);
   int ts = 1, te = 0;
@@ -441,8 +447,8 @@ __device__ __forceinline__ uint32_t ego_band_span(const EgoAffine& A, int ego_w,
     float y_at_xlo = qy[0], y_at_xhi = qy[0];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float dy = qy[(k + 1) & 3] - qy[k];
-      const float inv = dy != 0.f ? (qx[(k + 1) & 3] - qx[k]) / dy : 0.f;
+      const float dy = edy[k];
+      const float inv = (k & 1) ? inv_v : inv_u;
       const bool is_left = ccw ? dy < 0.f : dy > 0.f, is_right = ccw ? dy > 0.f : dy < 0.f;   // horizontal edges: neither
       const float v0 = qx[k] + (y0 - qy[k]) * inv, v1 = qx[k] + (y1 - qy[k]) * inv;
       if (is_left) { l0 = fmaxf(l0, v0); l1 = fmaxf(l1, v1); }
@@ -519,6 +525,12 @@ static_assert(offsetof(StepRecord, path_off) == 80 && offsetof(StepRecord, chunk
 #ifndef BCG_MOVE_MIN_BLOCKS
 #define BCG_MOVE_MIN_BLOCKS 8         // register budget: 65536 / (threads x blocks) = 128
 #endif
+#ifndef BCG_MOVE_FEW_BLOCKS
+#define BCG_MOVE_FEW_BLOCKS 6         // the build used when the batch fits one wave of it: 168 registers
+#endif
+#ifndef BCG_MOVE_FEWER_BLOCKS
+#define BCG_MOVE_FEWER_BLOCKS 4       // ... and when it fits one wave of 256 per SM: 230 registers, nothing spilled
+#endif
 #ifndef BCG_REWARD_THREADS
 #define BCG_REWARD_THREADS 64
 #endif
@@ -569,7 +581,14 @@ __device__ __forceinline__ void write_goal_from_transform(const BcgParams& p, co
   for (int k = 0; k < 6; ++k) g[3 + k] = drobot[k];
 }
 
-__global__ void __launch_bounds__(BCG_MOVE_THREADS, BCG_MOVE_MIN_BLOCKS)
+// MIN_BLOCKS is the register budget: 8 CTAs per SM = 128 registers (1 024 envs in flight per SM: the large batch needs
+// the warps), 6 = 168 registers (no spills; ~3.5 us less on the chain when the whole batch fits one wave of 384 per SM).
+template <int MIN_BLOCKS>
+#ifdef BCG_MOVE_MAXNREG
+__global__ void __maxnreg__(MIN_BLOCKS == BCG_MOVE_MIN_BLOCKS ? BCG_MOVE_MAXNREG : (MIN_BLOCKS == 6 ? 168 : 232))
+#else
+__global__ void __launch_bounds__(BCG_MOVE_THREADS, MIN_BLOCKS)
+#endif
 move_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L, const void* __restrict__ actions,
             const int action_is_f64, const uint64_t step_index_arg, const BcgStepOut out, const int ego_cap) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1848,12 +1867,14 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
       {
         const int head = min((int)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u), npx);
         const int body = (npx - head) & ~15, tail = npx - head - body;
+        // one bulk store of the zero page per lane of warp 0 (a loop in one thread was 16 instructions per store; a
+        // bulk group belongs to the thread that committed it, so the same lanes wait for theirs below)
 #ifdef BCG_EGS_EXP_NO_ZERO                  // experiment: no bulk zero stores
-        if (tid == 0 && ego_w < 0) {
+        if (warp == 0 && ego_w < 0) {
 #else
-        if (tid == 0) {
+        if (warp == 0) {
 #endif
-          for (int o = 0; o < body; o += BCG_EGS_ZERO_BYTES)
+          for (int o = lane * BCG_EGS_ZERO_BYTES; o < body; o += 32 * BCG_EGS_ZERO_BYTES)
             bulk_store(dst + head + o, zero_u32, (uint32_t)min(body - o, BCG_EGS_ZERO_BYTES));
           bulk_commit();
         }
@@ -1863,14 +1884,20 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
         }
       }
       // ---- fixed-point tables of the crop (as the dense kernel) --------------------------------------------------
-      const EgoAffine A = r->aff;
-      for (int i = tid; i < ego_w + ego_h; i += NT) {
-        if (i < ego_w) {
-          egs_tab[i] = make_int2(__double2int_rn(A.a11 * i * 1024), __double2int_rn(A.a21 * i * 1024));
-        } else {
-          const int t = i - ego_w;
-          egs_tab[i] = make_int2(__double2int_rn((A.a12 * t + A.b1) * 1024) + 512 - (X0 << 10),
-                                 __double2int_rn((A.a22 * t + A.b2) * 1024) + 512 - (Y0 << 10));
+      // (a i) 1024 == (1024 a) i and (a t + b) 1024 == (1024 a) t + 1024 b bit for bit (a power of two commutes with
+      // every rounding), so the scale is folded into the coefficients: one multiplication less per table value
+      {
+        const EgoAffine A = r->aff;
+        const double a11 = A.a11 * 1024, a21 = A.a21 * 1024, a12 = A.a12 * 1024, a22 = A.a22 * 1024;
+        const double b1 = A.b1 * 1024, b2 = A.b2 * 1024;
+        const int ox = 512 - (X0 << 10), oy = 512 - (Y0 << 10);
+        for (int i = tid; i < ego_w + ego_h; i += NT) {
+          if (i < ego_w) {
+            egs_tab[i] = make_int2(__double2int_rn(a11 * i), __double2int_rn(a21 * i));
+          } else {
+            const int t = i - ego_w;
+            egs_tab[i] = make_int2(__double2int_rn(a12 * t + b1) + ox, __double2int_rn(a22 * t + b2) + oy);
+          }
         }
       }
       // ---- 2. occupied cells of the window: four lanes per 32 x 16 bit tile (a 16-byte load = 4 rows each).  All loads
@@ -1913,20 +1940,11 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
           bits[k] &= keep;
           cnt += __popc(bits[k]);
         }
-        // list slots: inclusive warp scan of the counts, one shared-memory atomic per warp
-        int incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int v = __shfl_up_sync(BCG_FULL, incl, d);
-          if (lane >= d) incl += v;
-        }
-        const int total = __shfl_sync(BCG_FULL, incl, 31);
-        if (total == 0) return;
-        uint32_t base0 = 0u;
-        if (lane == 31) base0 = atomicAdd(&T.count[par], (uint32_t)total);
-        base0 = __shfl_sync(BCG_FULL, base0, 31);
-        const uint32_t base = base0 + (uint32_t)(incl - cnt);
-        if (cnt == 0 || base + (uint32_t)cnt > BCG_EGS_LIST) return;              // overflow: the env goes to the dense kernel
+        // list slots: one shared-memory atomic per lane that holds a cell (the kernel is bound by issue slots: a warp
+        // scan of the counts was ~25 instructions per call, the atomic is one; the order of the list is irrelevant)
+        if (cnt == 0) return;
+        const uint32_t base = atomicAdd(&T.count[par], (uint32_t)cnt);
+        if (base + (uint32_t)cnt > BCG_EGS_LIST) return;                          // overflow: the env goes to the dense kernel
         uint32_t at = list_u32 + 4u * base;
         const int key = (yr0 << 16) + ((tx << 5) - X0);          // x_rel of bit 0 may be negative, of a kept bit never
 #pragma unroll
@@ -2023,7 +2041,7 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
         __syncwarp();
         expand(qhead, (int)(qtail - qhead));
       }
-      if (tid == 0) bulk_wait_all();          // the zeros have landed (they had the whole scan to do so)
+      if (warp == 0) bulk_wait_all();         // the zeros have landed (they had the whole scan to do so)
     }
     cp_async_wait_group_1();                  // the record needed next iteration has landed
     __syncthreads();                          // zeros (incl. head / tail bytes), tables, list and count are complete
@@ -2040,6 +2058,10 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
         pitch = md->pitch;
       }
       const float m0 = r->fwd[0], m1 = r->fwd[1], m2 = r->fwd[2], m3 = r->fwd[3], m4 = r->fwd[4], m5 = r->fwd[5];
+      // the loop is instantiated per kind of map: with every occupied cell lethal the value is a constant and the address
+      // arithmetic of the cost-byte load (predicated off, but issued) is gone
+      auto scatter = [&](auto lethal_tag) {
+      constexpr bool LETHAL = decltype(lethal_tag)::value;
       for (uint32_t i = tid; i < count; i += NT) {
         const uint32_t key = lds_u32(list_u32 + 4u * i);
         const int xr = (int)(key & 0xffffu), yr = (int)(key >> 16);
@@ -2049,7 +2071,7 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
         const int fv = __float2int_rd(__fmaf_rn(m3, X, __fmaf_rn(m4, Y, m5)));
         if (fu < -1 || fu >= ego_w || fv < -1 || fv >= ego_h) continue;     // every candidate is outside the crop
         uint8_t val = 254;
-        if (!only_lethal) val = __ldg(src + (int64_t)(Y0 + yr) * pitch + (X0 + xr));
+        if (!LETHAL) val = __ldg(src + (int64_t)(Y0 + yr) * pitch + (X0 + xr));
         const int u0 = max(fu, 0), u1 = min(fu + 1, ego_w - 1), v0 = max(fv, 0), v1 = min(fv + 1, ego_h - 1);
         const uint2 a0 = lds_v2(adxy_u32 + 8u * (uint32_t)u0), a1 = lds_v2(adxy_u32 + 8u * (uint32_t)u1);
         const uint2 b0 = lds_v2(bxy_u32 + 8u * (uint32_t)v0), b1 = lds_v2(bxy_u32 + 8u * (uint32_t)v1);
@@ -2088,6 +2110,9 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
           }
         }
       }
+      };
+      if (only_lethal) scatter(std::true_type{});
+      else scatter(std::false_type{});
     } else if (b.flags & BCG_BATCH_SPARSE_EGO_ONLY) {
       // No dense pass follows this kernel (the host knows that no map of the batch is dense): the rare window that
       // overflows the cell list, or lies outside any sane range, is rendered here by the bounds-checked per-pixel gather.
@@ -2614,8 +2639,15 @@ int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, 
   {
     if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[1], s));
     const int cap = ego ? ego_capacity(*p, *b) : 0;
-    move_kernel<<<blocks_for(b->n_envs, BCG_MOVE_THREADS), BCG_MOVE_THREADS, 0, s>>>(*p, *b, L, actions, action_is_f64, step_index,
-                                                                                    *out, cap);
+    int sms = 0;
+    if (int rc = sm_count_of_current_device(&sms)) return rc;
+    const int move_blocks = (int)blocks_for(b->n_envs, BCG_MOVE_THREADS);
+    if (move_blocks <= sms * BCG_MOVE_FEWER_BLOCKS)
+      move_kernel<BCG_MOVE_FEWER_BLOCKS><<<move_blocks, BCG_MOVE_THREADS, 0, s>>>(*p, *b, L, actions, action_is_f64, step_index, *out, cap);
+    else if (move_blocks <= sms * BCG_MOVE_FEW_BLOCKS)
+      move_kernel<BCG_MOVE_FEW_BLOCKS><<<move_blocks, BCG_MOVE_THREADS, 0, s>>>(*p, *b, L, actions, action_is_f64, step_index, *out, cap);
+    else
+      move_kernel<BCG_MOVE_MIN_BLOCKS><<<move_blocks, BCG_MOVE_THREADS, 0, s>>>(*p, *b, L, actions, action_is_f64, step_index, *out, cap);
     BCG_CHECK_CUDA(cudaGetLastError());
     if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[2], s));
     if (b->n_envs > 16384) reward_kernel<8><<<blocks_for((int64_t)b->n_envs * 8, BCG_REWARD_THREADS), BCG_REWARD_THREADS, 0, s>>>(*p, *b, *out, cap);

@@ -576,7 +576,37 @@ def ego_roofline(env, ego_ms, n, sparse, traffic):
     peak = r["peak"]
     r["image_write_frac"] = image_bytes / (ego_ms * 1e-3) / 1e9 / peak
     r["survey_8d"] = {"algorithmic_bytes_per_launch": gather_bytes, "frac": gather_bytes / (ego_ms * 1e-3) / 1e9 / peak}
+    r["image_fill"] = image_fill_floor(env, ego_ms)
     return name, r
+
+
+def image_fill_floor(env, ego_ms):
+    """Context for the scatter kernel's time: plain fills (library calls, not the product) of a buffer of the images' size,
+    timed like the kernels (CUDA events, mean of 20 back-to-back launches, buffer far larger than L2): torch's `zero_`
+    (the driver's memset) and `fill_` of the same bytes viewed as int64 and as uint8."""
+    import torch
+    nbytes = env.ego_image.numel()
+    scratch = torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=env.ego_image.device)
+    u8 = scratch.view(torch.uint8)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 20
+
+    ms = {"memset": timed(scratch.zero_), "fill_int64": timed(lambda: scratch.fill_(1)), "fill_uint8": timed(lambda: u8.fill_(1))}
+    best = min(ms.values())
+    del scratch, u8
+    return {"ms": ms, "best_ms": best, "best_gbs": nbytes / (best * 1e-3) / 1e9,
+            "kernel_ms_over_best_fill_ms": ego_ms / best if best > 0 else None,
+            "what": "write-only floor of the observation on this GPU: plain fills of a buffer of the crops' size"}
 
 
 def measure_e2e(env, actions, args, D, n):
