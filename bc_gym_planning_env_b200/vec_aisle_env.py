@@ -154,6 +154,11 @@ class VecRandomAisleTurnEnv(_VecSlotEnv):
         """
         :param n_envs: batch size; env e draws from the Philox stream (seed; env_id_base + e, draw index)
         :param draw_new_turn_on_reset: `reset` draws a new turn for the envs it resets (reference default)
+        :param auto_reset: the step's own in-kernel reset.  It restores the initial state of the env's CURRENT world
+            (no launch, no host round trip) and does NOT draw a new turn, whatever draw_new_turn_on_reset says: an
+            episode that ends is replayed on the same aisle.  For the reference's behaviour -- a new turn for every
+            episode (synth_turn_env.py:278-291) -- keep auto_reset=False and call `env.reset(done)` after the step:
+            one generation launch for the envs that finished.
         :param turn_params: optional list of n_envs TurnParams for the first worlds (default: drawn on device)
         :param max_map_cells, max_path_points: slot capacities per env (default: worst case of the distribution)
         """
@@ -237,6 +242,9 @@ class VecRandomMiniEnv(_VecSlotEnv):
             goal tolerances 0.2 m / pi/8)
         :param mini_params: optional list of n_envs MiniEnvParams for the first worlds (built as they are, like
             MiniEnv(config)); default: sampled on the device
+        :param auto_reset: in-kernel reset to the initial state of the env's CURRENT world; it never samples a new
+            world (see VecRandomAisleTurnEnv).  The reference builds a new env per episode (mini_env.py:447-470):
+            auto_reset=False + `env.reset(done)` does that here.
         """
         from bc_gym_planning_env_b200.envs.base.params import EnvParams
         from bc_gym_planning_env_b200.envs.mini_env import RandomMiniEnvParams

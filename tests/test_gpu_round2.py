@@ -164,3 +164,28 @@ def test_live_reference_beside_the_cuda_batch():
             seen_hit += int(base._env._state.robot_collided)
     assert seen_done > 0 and seen_hit > 0
     env.check_status()
+
+
+def test_move_kernel_register_tiers_give_the_same_bits():
+    """move_kernel is built three times (230 / 168 / 128 registers) and the launch picks one by batch size.  The same
+    envs stepped as the head of a 4 096-, a 30 000- and a 60 000-env batch (one tier each on a 148-SM B200) agree bit
+    for bit: state, rewards, done flags, compact observation, with noise, delays and auto-reset on."""
+    params = EnvParams(control_delay=2, pose_delay=1, state_delay=1)
+    costmaps, paths = random_aisle_pool(16, 31, params)
+    head = 4096
+    envs = [VecPlanEnv(costmaps, paths, params, n_envs=n, seed=9, auto_reset=True, with_ego=False, noise_parameters=DEFAULT_NOISE)
+            for n in (head, 30000, 60000)]
+    acts = _actions(envs[0], 120, 11)
+    for t, act in enumerate(acts):
+        for env in envs:
+            full = act if env.n_envs == head else act.repeat((env.n_envs + head - 1) // head, 1)[:env.n_envs].contiguous()
+            env.step(full)
+        if t % 20 == 19:
+            ref = envs[0]
+            for env in envs[1:]:
+                assert torch.equal(ref.state_f, env.state_f[:, :head]) and torch.equal(ref.state_i, env.state_i[:, :head]), (t, env.n_envs)
+                assert torch.equal(ref.reward, env.reward[:head]) and torch.equal(ref.done, env.done[:head]), (t, env.n_envs)
+                assert torch.equal(ref.obs_vec, env.obs_vec[:head]), (t, env.n_envs)
+    assert float(envs[0].episode_stats()[0]) > 0
+    for env in envs:
+        env.check_status()
