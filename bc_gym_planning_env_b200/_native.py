@@ -163,6 +163,8 @@ SYMBOLS = {
     "bcg_inverse_transform": (C.c_int, [_P, C.c_int64, _P, _P]),
     "bcg_project_poses": (C.c_int, [C.POINTER(C.c_double), _P, C.c_int64, _P, _P]),
     "bcg_observe_ego_path": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgBatch), C.c_int32, _P, _P, _P]),
+    "bcg_alloc_image_memory": (C.c_int, [C.c_int64, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "bcg_free_image_memory": (C.c_int, [_P, C.c_int64]),
 }
 
 
@@ -221,6 +223,36 @@ def state_layout(params):
     out = BcgStateLayout()
     check(lib().bcg_state_layout(C.byref(params), C.byref(out)))
     return out
+
+
+class ImageMemory(object):
+    """A device block from bcg_alloc_image_memory (compute-data compression when the device has it), exposed through
+    the CUDA array interface so that torch can view it; unmapped when the last view is gone."""
+
+    def __init__(self, nbytes, want_compression=True):
+        dptr, mapped, compressed = C.c_void_p(), C.c_int64(), C.c_int32()
+        check(lib().bcg_alloc_image_memory(int(nbytes), 1 if want_compression else 0, C.byref(dptr), C.byref(mapped),
+                                           C.byref(compressed)))
+        self.ptr, self.mapped_bytes, self.compressed, self.nbytes = int(dptr.value), int(mapped.value), bool(compressed.value), int(nbytes)
+        self.__cuda_array_interface__ = {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 3,
+                                         "strides": None}
+
+    def tensor(self, shape):
+        """uint8 torch tensor of `shape` on this block, zero filled; it keeps the block alive"""
+        import torch
+        t = torch.as_tensor(self, device="cuda").view(shape)
+        t.zero_()
+        return t
+
+    def __del__(self):
+        ptr_, self.ptr = getattr(self, "ptr", 0), 0
+        if ptr_ and _lib is not None:
+            try:
+                import torch
+                torch.cuda.synchronize()
+            except Exception:
+                pass
+            _lib.bcg_free_image_memory(C.c_void_p(ptr_), self.mapped_bytes)
 
 
 def ptr(t):

@@ -50,6 +50,23 @@ int fail(int code, const std::string& msg) {
       return fail(BCG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err__));       \
   } while (0)
 
+// driver entry points without linking libcuda (the library must load on a box without a driver: tests -m "not gpu")
+template <class F>
+static int driver_fn(const char* name, F* out) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  BCG_CHECK_CUDA(cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) return fail(BCG_ERR_CUDA, "driver entry point not available");
+  *out = reinterpret_cast<F>(fn);
+  return BCG_OK;
+}
+#define BCG_CHECK_CU(x)                                                         \
+  do {                                                                          \
+    const CUresult r_ = (x);                                                    \
+    if (r_ != CUDA_SUCCESS) return fail(BCG_ERR_CUDA, #x " failed");            \
+  } while (0)
+
+
 #define BCG_REQUIRE(cond, msg) \
   do {                         \
     if (!(cond)) return fail(BCG_ERR_INVALID, msg); \
@@ -2378,6 +2395,79 @@ int bcg_build_cell_tiles(const BcgBatch* b, int32_t first, int32_t count, void* 
     cell_tiles_kernel<<<dim3(8, chunk), 256, 0, s>>>(*b, first + done);
     BCG_CHECK_CUDA(cudaGetLastError());
   }
+  return BCG_OK;
+}
+
+int bcg_alloc_image_memory(int64_t bytes, int32_t want_compression, void** dptr, int64_t* mapped_bytes, int32_t* compressed) {
+  BCG_REQUIRE(bytes > 0 && dptr && mapped_bytes && compressed, "bad argument");
+  decltype(&cuMemGetAllocationGranularity) get_gran = nullptr;
+  decltype(&cuMemCreate) create = nullptr;
+  decltype(&cuMemGetAllocationPropertiesFromHandle) get_prop = nullptr;
+  decltype(&cuMemAddressReserve) reserve = nullptr;
+  decltype(&cuMemMap) map = nullptr;
+  decltype(&cuMemSetAccess) set_access = nullptr;
+  decltype(&cuMemRelease) release = nullptr;
+  decltype(&cuMemAddressFree) address_free = nullptr;
+  decltype(&cuDeviceGetAttribute) get_attr = nullptr;
+  if (int rc = driver_fn("cuMemGetAllocationGranularity", &get_gran)) return rc;
+  if (int rc = driver_fn("cuMemCreate", &create)) return rc;
+  if (int rc = driver_fn("cuMemGetAllocationPropertiesFromHandle", &get_prop)) return rc;
+  if (int rc = driver_fn("cuMemAddressReserve", &reserve)) return rc;
+  if (int rc = driver_fn("cuMemMap", &map)) return rc;
+  if (int rc = driver_fn("cuMemSetAccess", &set_access)) return rc;
+  if (int rc = driver_fn("cuMemRelease", &release)) return rc;
+  if (int rc = driver_fn("cuMemAddressFree", &address_free)) return rc;
+  if (int rc = driver_fn("cuDeviceGetAttribute", &get_attr)) return rc;
+  int dev = 0;
+  BCG_CHECK_CUDA(cudaGetDevice(&dev));
+  BCG_CHECK_CUDA(cudaFree(nullptr));                        // the primary context exists
+  int supported = 0;
+  BCG_CHECK_CU(get_attr(&supported, CU_DEVICE_ATTRIBUTE_GENERIC_COMPRESSION_SUPPORTED, dev));
+  CUmemAllocationProp prop = {};
+  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  prop.location.id = dev;
+  if (want_compression && supported) prop.allocFlags.compressionType = CU_MEM_ALLOCATION_COMP_GENERIC;
+  size_t gran = 0;
+  BCG_CHECK_CU(get_gran(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
+  BCG_REQUIRE(gran > 0, "zero allocation granularity");
+  const size_t size = ((size_t)bytes + gran - 1) / gran * gran;
+  CUmemGenericAllocationHandle h;
+  BCG_CHECK_CU(create(&h, size, &prop, 0));
+  CUmemAllocationProp got = {};
+  if (get_prop(&got, h) != CUDA_SUCCESS) got = prop;
+  CUdeviceptr p = 0;
+  if (reserve(&p, size, 0, 0, 0) != CUDA_SUCCESS) {
+    release(h);
+    return fail(BCG_ERR_CUDA, "cuMemAddressReserve failed");
+  }
+  if (map(p, size, 0, h, 0) != CUDA_SUCCESS) {
+    address_free(p, size);
+    release(h);
+    return fail(BCG_ERR_CUDA, "cuMemMap failed");
+  }
+  release(h);                                                // the mapping keeps the memory until it is unmapped
+  CUmemAccessDesc acc = {};
+  acc.location = prop.location;
+  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  if (set_access(p, size, &acc, 1) != CUDA_SUCCESS) {
+    bcg_free_image_memory(reinterpret_cast<void*>(p), (int64_t)size);
+    return fail(BCG_ERR_CUDA, "cuMemSetAccess failed");
+  }
+  *dptr = reinterpret_cast<void*>(p);
+  *mapped_bytes = (int64_t)size;
+  *compressed = got.allocFlags.compressionType == CU_MEM_ALLOCATION_COMP_GENERIC ? 1 : 0;
+  return BCG_OK;
+}
+
+int bcg_free_image_memory(void* dptr, int64_t mapped_bytes) {
+  BCG_REQUIRE(dptr && mapped_bytes > 0, "bad argument");
+  decltype(&cuMemUnmap) unmap = nullptr;
+  decltype(&cuMemAddressFree) address_free = nullptr;
+  if (int rc = driver_fn("cuMemUnmap", &unmap)) return rc;
+  if (int rc = driver_fn("cuMemAddressFree", &address_free)) return rc;
+  BCG_CHECK_CU(unmap(reinterpret_cast<CUdeviceptr>(dptr), (size_t)mapped_bytes));
+  BCG_CHECK_CU(address_free(reinterpret_cast<CUdeviceptr>(dptr), (size_t)mapped_bytes));
   return BCG_OK;
 }
 

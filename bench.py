@@ -562,19 +562,21 @@ def ego_roofline(env, ego_ms, n, sparse, traffic):
         name = "ego_tiles_kernel" if env.ego_staging == "tiles" else "ego_kernel"
         return name, roof(name, gather_bytes, ego_ms, "algorithmic bytes = 2 x ego_w x ego_h per env (SURVEY 8d: source read + "
                           "image write); staging: " + env.ego_staging, traffic.get(name))
-    # The sparse kernel is a scatter: it never reads the source bytes, so SURVEY 8d's gather bytes give "fractions" above 1.
-    # `frac` is therefore on the bytes the hardware moved (ncu DRAM bytes per launch from the committed capture) when the
-    # capture matches this batch size, else on the irreducible image write; the other definitions are kept beside it by name.
+    # The sparse kernel is a scatter: it never reads the source bytes, so SURVEY 8d's gather bytes (2 x W x H per env)
+    # are not what it moves and give "fractions" above 1 (kept under `survey_8d`).  Its algorithmic bytes are the crop it
+    # must produce, W x H per env; `traffic` is what ncu counted in DRAM for one launch (profiles/ncu_traffic.json) -- less
+    # than the crops' bytes, because VecPlanEnv keeps them in memory with compute-data compression.
     name = "ego_sparse_kernel"
     image_bytes = float(cp.ego_w * cp.ego_h) * n
-    tr = traffic.get(name)
-    r = roof(name, tr if tr else image_bytes, ego_ms,
-             "scatter kernel: `frac` = physical DRAM bytes per launch (ncu, profiles/ncu_traffic.json) / launch time when the "
-             "capture matches this batch size, else the image write alone; `image_write_frac` = W x H written per env; "
-             "`survey_8d` = the gather definition of SURVEY 8d (2 x W x H per env), which this kernel does not move and which "
-             "can exceed 1", tr)
+    compressed = bool(getattr(env, "image_memory_compressed", False))
+    tr = traffic.get(name if compressed else name + "_plain_memory")
+    r = roof(name, image_bytes, ego_ms,
+             "scatter kernel: algorithmic bytes = the crops it writes (ego_w x ego_h per env); `traffic` = DRAM bytes per "
+             "launch from the committed ncu capture (crops in %s memory); `survey_8d` = the gather definition of SURVEY 8d "
+             "(2 x W x H per env), which a scatter does not move and which can exceed 1; `image_fill` = plain fills of the "
+             "same bytes (the write-only floor)" % ("compressible" if compressed else "plain"), tr)
     peak = r["peak"]
-    r["image_write_frac"] = image_bytes / (ego_ms * 1e-3) / 1e9 / peak
+    r["image_memory_compressed"] = compressed
     r["survey_8d"] = {"algorithmic_bytes_per_launch": gather_bytes, "frac": gather_bytes / (ego_ms * 1e-3) / 1e9 / peak}
     r["image_fill"] = image_fill_floor(env, ego_ms)
     return name, r

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BCG_ABI_VERSION 9
+#define BCG_ABI_VERSION 10
 
 /* error codes */
 #define BCG_OK 0
@@ -418,6 +418,17 @@ int bcg_project_poses(const double* transform_host, const double* poses, int64_t
  * tensor in the robot frame (from_global_to_egocentric, coordinate_transformations.py:341-362, about the observed pose):
  * out device [n][max_points][3] zero padded, len_out (optional) device [n] = way points left (may exceed max_points) */
 int bcg_observe_ego_path(const BcgParams* p, const BcgBatch* b, int32_t max_points, double* out, int32_t* len_out, void* stream);
+
+/* -- image memory --------------------------------------------------------------------------------
+ * Egocentric crops are mostly zeros.  A device allocation with compute-data compression (CUDA virtual memory
+ * management, CU_MEM_ALLOCATION_COMP_GENERIC) makes the hardware write and read such lines at a fraction of their DRAM
+ * cost; contents and addressing are unchanged for kernels and copies.  The one place where this library allocates: the
+ * caller owns the block and returns it with bcg_free_image_memory.  (Nothing in the reference corresponds: its images
+ * are NumPy arrays, egocentric.py:125-160.)
+ * bytes: wanted size; *dptr: device address; *mapped_bytes: size actually mapped (granularity rounded), to be passed
+ * back on free; *compressed: 1 when the allocation got compression, 0 when the device / driver gave a plain one. */
+int bcg_alloc_image_memory(int64_t bytes, int32_t want_compression, void** dptr, int64_t* mapped_bytes, int32_t* compressed);
+int bcg_free_image_memory(void* dptr, int64_t mapped_bytes);
 
 #ifdef __cplusplus
 }
