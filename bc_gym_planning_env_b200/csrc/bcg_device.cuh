@@ -584,6 +584,120 @@ __device__ __forceinline__ bool collide_thread(const BcgFootprintLut& lut, const
   return false;
 }
 
+// collide_thread with the tiles of a WARP's 32 envs dealt out evenly.  In collide_thread a warp walks its tile loop as often
+// as its busiest lane has non-empty tiles under the footprint (~9 times for ~3 tiles per lane on the aisle workload), and
+// that loop was three quarters of move_kernel's instructions.  Here every lane still reads its own env's summary words and
+// lists its tiles (4 bits per band), then the warp's (env, tile) pairs are numbered by a prefix sum and lane l takes pair
+// (lanes present) r + l of round r: it finds the owner by binary search over the inclusive counts, gets the owner's box by shuffles,
+// loads the tile's four 16-byte quarters and the band's mask rows, and a hit travels back to its owner through a ballot.
+// ~3 rounds instead of ~9, no lane idles while another works.  `act` = the lanes of the warp that hold an env (all callers
+// are thread-per-env kernels whose tail warp is partly empty; those lanes are contiguous from 0).  Boxes that do not fit the
+// fast shape (multi-word mask rows, > 4 tile columns, > 6 bands) are checked by collide_thread afterwards.  Same verdict.
+__device__ __forceinline__ bool collide_warp_balanced(const BcgFootprintLut& lut, const uint32_t* __restrict__ tile_arena,
+                                                      int64_t tile_off, const uint32_t* __restrict__ sum, int tiles_x,
+                                                      int map_w, int map_h, const FootBox& f, unsigned act, unsigned lane) {
+  const int X0 = f.X0, Y0 = f.Y0;
+  const int X1 = X0 + f.fwidth - 1, Y1 = Y0 + f.nrows - 1;
+  const bool inside = !(X1 < 0 || X0 >= map_w || Y1 < 0 || Y0 >= map_h);
+  const int tx0 = max(X0, 0) >> 5, tx1 = min(X1, map_w - 1) >> 5;
+  const int ty0 = max(Y0, 0) >> 4, ty1 = min(Y1, map_h - 1) >> 4;
+  constexpr int MAXB = 6;
+  const bool pair_rows = lut.wpr == 1 && (lut.max_rows & 1) == 0 && (reinterpret_cast<uintptr_t>(lut.rows) & 15) == 0;
+  const bool fast = inside && pair_rows && (tx1 - tx0) < 4 && (ty1 - ty0) < MAXB && tiles_x < 2048 && ty0 < 2048 && tx0 < 1024 &&
+                    X0 > -32768 && Y0 > -32768;
+  uint32_t todo = 0u;
+  if (fast) {
+    const int sw = (tiles_x + 31) >> 5;
+    const uint32_t colmask = (2u << (tx1 - tx0)) - 1u;
+    uint32_t tm[MAXB];
+#pragma unroll
+    for (int k = 0; k < MAXB; ++k) {
+      tm[k] = 0u;
+      if (ty0 + k <= ty1) {
+        tm[k] = colmask;
+        if (sum) {
+          const uint32_t* srow = sum + (ty0 + k) * sw;
+          const int w0 = tx0 >> 5;
+          uint64_t two = __ldg(srow + w0);
+          if ((tx1 >> 5) != w0) two |= (uint64_t)__ldg(srow + w0 + 1) << 32;
+          tm[k] = (uint32_t)(two >> (tx0 & 31)) & colmask;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < MAXB; ++k) todo |= tm[k] << (4 * k);
+  }
+  const int cnt = __popc(todo);
+  int incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(act, incl, d);
+    if ((int)lane >= d) incl += v;
+  }
+  const int last = 31 - __clz((int)act);
+  const int total = __shfl_sync(act, incl, last);
+  // what a lane needs of a pair's owner, packed for the shuffles
+  const uint32_t pk_xy = ((uint32_t)X0 & 0xffffu) | ((uint32_t)Y0 << 16);
+  const uint32_t pk_t = (uint32_t)ty0 | ((uint32_t)tx0 << 11) | ((uint32_t)tiles_x << 21);
+  const int excl = incl - cnt;
+  bool myhit = false;
+  for (int base = 0; base < total; base += last + 1) {     // a round deals one pair to each lane that is there
+    const int i = base + (int)lane;
+    const bool has = i < total;
+    int o = 0;                                             // owner = the first lane whose inclusive count exceeds i
+#pragma unroll
+    for (int st = 16; st >= 1; st >>= 1) {
+      const int probe = o + st - 1;
+      const int t = __shfl_sync(act, incl, min(probe, last));
+      if (probe <= last && t <= i) o += st;
+    }
+    o = min(o, last);
+    const uint32_t otodo = __shfl_sync(act, todo, o);
+    const int r = i - __shfl_sync(act, excl, o);
+    const uint32_t oxy = __shfl_sync(act, pk_xy, o), ot = __shfl_sync(act, pk_t, o);
+    const int obin = __shfl_sync(act, f.bin, o);
+    const unsigned long long ooff = __shfl_sync(act, (unsigned long long)tile_off, o);
+    uint32_t hit = 0u;
+    if (has) {
+      uint32_t m = otodo;                                  // the pair's tile: set bit number r of the owner's list
+      for (int q = 0; q < r; ++q) m &= m - 1u;
+      const int bit = __ffs((int)m) - 1;
+      const int ty = (int)(ot & 2047u) + (bit >> 2), tx = (int)((ot >> 11) & 1023u) + (bit & 3);
+      const int oX0 = (int)(short)(oxy & 0xffffu), oY0 = (int)(short)(oxy >> 16);
+      const uint4* tq = reinterpret_cast<const uint4*>(tile_arena + (int64_t)ooff + ((((int64_t)ty * (int)(ot >> 21)) + tx) << 4));
+      const uint4 w0 = __ldg(tq), w1 = __ldg(tq + 1), w2 = __ldg(tq + 2), w3 = __ldg(tq + 3);
+      const int dy0 = (ty << 4) - oY0, rel = (tx << 5) - oX0;
+      const uint64_t* __restrict__ rows = lut.rows + (int64_t)obin * lut.max_rows;
+      const int rbase = dy0 & ~1, odd = dy0 & 1;
+      uint64_t v[18];
+#pragma unroll
+      for (int jj = 0; jj < 9; ++jj) {
+        const int r0 = rbase + 2 * jj;
+        ulonglong2 q = make_ulonglong2(0ull, 0ull);
+        if ((unsigned)r0 < (unsigned)lut.max_rows) q = __ldg(reinterpret_cast<const ulonglong2*>(rows + r0));
+        v[2 * jj] = q.x;
+        v[2 * jj + 1] = q.y;
+      }
+      const uint32_t ws[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr) hit |= ws[rr] & mask_window32(odd ? v[rr + 1] : v[rr], rel);
+    }
+    const uint32_t hb = __ballot_sync(act, hit != 0u);
+    for (uint32_t h2 = hb; h2 != 0u; h2 &= h2 - 1u) {      // rare: a collision ends the episode
+      const int l = __ffs((int)h2) - 1;
+      if (__shfl_sync(act, o, l) == (int)lane) myhit = true;
+    }
+  }
+  if (inside && !fast) myhit = collide_thread(lut, tile_arena + tile_off, sum, tiles_x, map_w, map_h, f);
+  return myhit;
+}
+
+// the lanes of this warp that hold one of the n items of a thread-per-item kernel (item = global thread index)
+__device__ __forceinline__ unsigned warp_item_mask(int first_item_of_warp, int n) {
+  const int left = n - first_item_of_warp;
+  return left >= 32 ? BCG_FULL : ((1u << left) - 1u);
+}
+
 // The same verdict read straight from the uint8 costmap rows: each half-warp owns one footprint row
 // per pass, each lane one aligned 4-byte word of it.
 __device__ __forceinline__ bool collide_u8(const BcgBatch& b, const WorkCollide& f, unsigned lane) {

@@ -536,6 +536,9 @@ static_assert(offsetof(StepRecord, path_off) == 80 && offsetof(StepRecord, chunk
 #define BCG_SR_DONE_BEFORE 8
 #define BCG_SR_GOAL_BEFORE 16
 
+#ifndef BCG_COLLIDE_BALANCED
+#define BCG_COLLIDE_BALANCED 1        // the tiles under a warp's 32 footprints dealt out evenly (collide_warp_balanced)
+#endif
 #ifndef BCG_MOVE_THREADS
 #define BCG_MOVE_THREADS 64
 #endif
@@ -674,8 +677,14 @@ move_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L, const v
     fb.nrows = h.z;
     fb.fwidth = h.w;
   }
+#if BCG_COLLIDE_BALANCED
+  const bool hit = collide_warp_balanced(b.lut, b.tile_arena, m.tile_off, b.occ_sum_arena ? b.occ_sum_arena + m.sum_off : nullptr,
+                                         m.tiles_x, m.width, m.height, fb, warp_item_mask(e - (int)(threadIdx.x & 31), b.n_envs),
+                                         threadIdx.x & 31);
+#else
   const bool hit = collide_thread(b.lut, b.tile_arena + m.tile_off, b.occ_sum_arena ? b.occ_sum_arena + m.sum_off : nullptr,
                                   m.tiles_x, m.width, m.height, fb);
+#endif
   if (hit) {  // env.py:458-459 + tricycle_model.py:471-476: pose restored, v = w = 0, wheel / steer command kept
     s[0] = old_pose[0];
     s[1] = old_pose[1];
@@ -1334,7 +1343,12 @@ __global__ void __launch_bounds__(64) collision_thread_kernel(const BcgBatch b, 
   fb.fwidth = f.fwidth;
   fb.bin = f.bin;
   const uint32_t* sum = b.occ_sum_arena ? b.occ_sum_arena + f.sum_off : nullptr;
+#if BCG_COLLIDE_BALANCED
+  flags[e] = collide_warp_balanced(b.lut, b.tile_arena, f.tile_off, sum, f.tiles_x, f.map_w, f.map_h, fb,
+                                   warp_item_mask(e - (int)(threadIdx.x & 31), b.n_envs), threadIdx.x & 31) ? 1 : 0;
+#else
   flags[e] = collide_thread(b.lut, b.tile_arena + f.tile_off, sum, f.tiles_x, f.map_w, f.map_h, fb) ? 1 : 0;
+#endif
 }
 
 // ---- TMA / mbarrier primitives (sm_90+ PTX; SASS: UTMALDG, SYNCS) ------------------------------------
