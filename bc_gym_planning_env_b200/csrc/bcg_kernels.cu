@@ -1797,7 +1797,7 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
                                                                                    uint8_t* __restrict__ image,
                                                                                    uint32_t* __restrict__ hit_list,
                                                                                    int32_t* __restrict__ hit_count,
-                                                                                   const int hit_cap, const int evict_first) {
+                                                                                   const int hit_cap, const int evict_from) {
   __shared__ __align__(128) uint8_t zero_s[BCG_EGS_ZERO_BYTES];
   __shared__ __align__(16) EgoSparseTab T;
   __shared__ __align__(128) uint8_t rec_s[BCG_EGS_REC_SLOTS * BCG_EGO_WORK_BYTES];
@@ -1912,7 +1912,7 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
         if (warp == 0) {
 #endif
           for (int o = lane * BCG_EGS_ZERO_BYTES; o < body; o += 32 * BCG_EGS_ZERO_BYTES) {
-            if (evict_first) bulk_store_evict_first(dst + head + o, zero_u32, (uint32_t)min(body - o, BCG_EGS_ZERO_BYTES));
+            if (e >= evict_from) bulk_store_evict_first(dst + head + o, zero_u32, (uint32_t)min(body - o, BCG_EGS_ZERO_BYTES));
             else bulk_store(dst + head + o, zero_u32, (uint32_t)min(body - o, BCG_EGS_ZERO_BYTES));
           }
           bulk_commit();
@@ -2686,15 +2686,16 @@ static int launch_ego_sparse(const BcgParams* p, const BcgBatch* b, uint8_t* ego
   }
   const int grid = b->n_envs < per_sm * sms ? b->n_envs : per_sm * sms;
   // (the variant that also records the compact hit lists has the same shared-memory footprint and register budget)
-  // When the batch's crops are about as large as L2 they linger there as dirty lines and the next step's first kernels
-  // start against their write-back: zero-filled with an evict-first policy they leave early (8 192 envs: move_kernel
-  // 0.029 -> 0.025 ms, reward_kernel 0.018 -> 0.017).  Large batches stream through L2 anyway, and there the policy only
-  // makes the hit bytes miss the lines just written (65 536 envs: 0.209 -> 0.225 ms): off above the threshold.
+  // When the batch's crops are about as large as L2 they linger there as dirty lines, and the next step's first kernels
+  // start against their write-back: zero-filled with an L2 evict-first policy they leave early (8 192 envs: move_kernel
+  // 0.029 -> 0.025 ms, reward_kernel 0.018 -> 0.017; profiles/r2ze_evict_first_by_batch.txt).  Larger batches stream
+  // through L2 anyway; there the policy only makes the hit bytes miss the lines just written (65 536 envs: 0.209 ->
+  // 0.225 ms), also when it is applied to the last crops alone (r2zf): off above the threshold.
   static const long long evict_bytes = [] {
     const char* v = getenv("BCG_EGO_EVICT_FIRST_BYTES");
     return v ? atoll(v) : 160ll << 20;
   }();
-  const int evict = (long long)b->n_envs * p->ego_w * p->ego_h <= evict_bytes ? 1 : 0;
+  const int evict = (long long)b->n_envs * p->ego_w * p->ego_h <= evict_bytes ? 0 : b->n_envs;   // evict_from: envs >= it use the policy
   if (hits.list) {
     if (sum) ego_sparse_kernel<true, true><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image, hits.list, hits.count, hits.cap, evict);
     else ego_sparse_kernel<false, true><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image, hits.list, hits.count, hits.cap, evict);
