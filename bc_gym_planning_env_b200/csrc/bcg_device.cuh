@@ -584,6 +584,43 @@ __device__ __forceinline__ bool collide_thread(const BcgFootprintLut& lut, const
   return false;
 }
 
+// The tile loop of collide_thread for a box in the fast shape (one-word mask rows in aligned pairs, <= 4 tile columns,
+// <= 6 bands) whose non-empty tiles are already listed in `todo` (4 bits per band from band ty0, bit j <-> column tx0 + j):
+// per tile its four 16-byte quarters + the band's mask rows, which are kept for the next tile of the same band.
+__device__ __forceinline__ bool collide_thread_listed(const BcgFootprintLut& lut, const uint32_t* __restrict__ tiles,
+                                                      int tiles_x, const FootBox& f, int ty0, int tx0, uint32_t todo) {
+  const uint64_t* __restrict__ rows = lut.rows + (int64_t)f.bin * lut.max_rows;
+  int vband = -1;
+  uint64_t v[18];
+  while (todo != 0u) {
+    const int bit = __ffs((int)todo) - 1;
+    todo &= todo - 1u;
+    const int k = bit >> 2, ty = ty0 + k, tx = tx0 + (bit & 3);
+    const int dy0 = (ty << 4) - f.Y0;
+    const uint4* tq = reinterpret_cast<const uint4*>(tiles + ((((int64_t)ty * tiles_x) + tx) << 4));
+    const uint4 w0 = __ldg(tq), w1 = __ldg(tq + 1), w2 = __ldg(tq + 2), w3 = __ldg(tq + 3);
+    const int rel = (tx << 5) - f.X0;
+    const int base = dy0 & ~1, odd = dy0 & 1;
+    if (k != vband) {
+      vband = k;
+#pragma unroll
+      for (int jj = 0; jj < 9; ++jj) {
+        const int r0 = base + 2 * jj;
+        ulonglong2 q = make_ulonglong2(0ull, 0ull);
+        if ((unsigned)r0 < (unsigned)lut.max_rows) q = __ldg(reinterpret_cast<const ulonglong2*>(rows + r0));
+        v[2 * jj] = q.x;
+        v[2 * jj + 1] = q.y;
+      }
+    }
+    const uint32_t ws[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+    uint32_t hit = 0u;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) hit |= ws[r] & mask_window32(odd ? v[r + 1] : v[r], rel);
+    if (hit) return true;
+  }
+  return false;
+}
+
 // collide_thread with the tiles of a WARP's 32 envs dealt out evenly.  In collide_thread a warp walks its tile loop as often
 // as its busiest lane has non-empty tiles under the footprint (~9 times for ~3 tiles per lane on the aisle workload), and
 // that loop was three quarters of move_kernel's instructions.  Here every lane still reads its own env's summary words and
@@ -636,6 +673,17 @@ __device__ __forceinline__ bool collide_warp_balanced(const BcgFootprintLut& lut
   }
   const int last = 31 - __clz((int)act);
   const int total = __shfl_sync(act, incl, last);
+  // Dealing pays when the lanes' lists differ in length.  When they do not (Monte-Carlo fan-outs: the rollouts of one
+  // start state share a pose for many steps) the per-thread loop is as short and keeps a band's mask rows across its
+  // tiles: a dealt round costs about 1.5 of its iterations.
+  const int longest = (int)__reduce_max_sync(act, (unsigned)cnt);
+  const int rounds = (total + last) / (last + 1);
+  if (3 * rounds >= 2 * longest) {
+    bool h = false;
+    if (fast) h = collide_thread_listed(lut, tile_arena + tile_off, tiles_x, f, ty0, tx0, todo);
+    else if (inside) h = collide_thread(lut, tile_arena + tile_off, sum, tiles_x, map_w, map_h, f);
+    return h;
+  }
   // what a lane needs of a pair's owner, packed for the shuffles
   const uint32_t pk_xy = ((uint32_t)X0 & 0xffffu) | ((uint32_t)Y0 << 16);
   const uint32_t pk_t = (uint32_t)ty0 | ((uint32_t)tx0 << 11) | ((uint32_t)tiles_x << 21);
