@@ -77,12 +77,13 @@ def monte_carlo_rollouts(env, start, actions, reduce=True, cols=None):
     if tuple(actions.shape[1:]) != (k, 2):
         raise ValueError("actions must have shape [H, %d, 2]" % k)
     env.set_state(type(start)(start.f.to(env.device)[:, cols].contiguous(), start.i.to(env.device)[:, cols].contiguous()))
-    ret = torch.zeros(env.n_envs, dtype=torch.float64, device=env.device)
-    acts = actions.to(env.device)[:, cols].contiguous()          # [H, n, 2]: one gather for the whole horizon
-    for h in range(acts.shape[0]):
-        _, r, _, _ = env.step(acts[h])
-        ret += r
     from bc_gym_planning_env_b200 import _native as nat
+    acts = actions.to(env.device)[:, cols].contiguous()          # [H, n, 2]: one gather for the whole horizon
+    # the rollout's return accumulates on the device in the episode-return row, started from zero (the same additions in
+    # the same order as summing the step rewards); the H steps are one CUDA-graph launch
+    env.state_f[nat.F_EP_RETURN].zero_()
+    env.rollout_graph(acts)
+    ret = env.state_f[nat.F_EP_RETURN]
     out = torch.zeros((k, 4), dtype=torch.float64, device=env.device)
     out[:, 0].index_add_(0, cols, ret)
     out[:, 1].index_add_(0, cols, env.state_i[nat.I_COLLIDED].to(torch.float64))

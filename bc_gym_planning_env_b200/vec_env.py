@@ -165,6 +165,7 @@ class VecPlanEnv(object):
         self.use_tma = ego_staging == 'tma'
         self._step_index = 0
         self._graph = None
+        self._plan_graph = None
         self._c_params = self._make_params(noise_parameters, seed, env_id_base)
         self.layout = nat.state_layout(self._c_params)
 
@@ -488,6 +489,38 @@ class VecPlanEnv(object):
         self._graph.replay()
         self._step_index += 1
         return self.observation(), self.reward, self.done, {}
+
+    def rollout_graph(self, plan):
+        """H steps of a fixed action plan as ONE CUDA-graph launch (Monte-Carlo fan-outs: README.md:45-61 of the
+        reference steps a copied env through a candidate plan).  plan: float [H, N, 2]; it is copied into a persistent
+        device buffer whose H slices the captured steps read, the Philox step index comes from the device-side counter.
+        The graph is captured on the first call for a given H and replayed afterwards.  Returns nothing: read
+        `state_f` / `reward` (last step) / `done` afterwards; the episode return accumulates in row F_EP_RETURN."""
+        plan = plan.to(self.device)
+        if plan.dim() != 3 or tuple(plan.shape[1:]) != (self.n_envs, 2):
+            raise ValueError("plan must have shape [H, %d, 2]" % self.n_envs)
+        horizon = int(plan.shape[0])
+        if self._plan_graph is None or self._plan_graph[0] != horizon:
+            buf = torch.zeros((horizon, self.n_envs, 2), dtype=torch.float32, device=self.device)
+            buf.copy_(plan)
+            if self._batch.step_counter == 0 or self._batch.step_counter is None:
+                self._step_counter[0] = self._step_index
+                self._step_counter[1] = 0
+                self._batch.step_counter = self._step_counter.data_ptr()
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g, stream=side):
+                    for h in range(horizon):
+                        nat.check(nat.lib().bcg_step(C.byref(self._c_params), C.byref(self._batch), nat.ptr(buf[h]), 0, 0,
+                                                     C.byref(self._out), C.c_void_p(side.cuda_stream)))
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            self._plan_graph = (horizon, g, buf)
+        else:
+            self._plan_graph[2].copy_(plan, non_blocking=True)
+        self._plan_graph[1].replay()
+        self._step_index += horizon
 
     def launches_per_step(self):
         """Kernels one `step` launches: move_kernel + reward_kernel, then the egocentric kernel(s)."""
