@@ -361,7 +361,8 @@ struct __align__(16) EgoTileWork {   // 128 bytes
   int32_t mode, map_id;              // BCG_EGO_MODE_TILES or BCG_EGO_MODE_DIRECT
   int32_t ctiles_x, ctiles_y;        // cell-tile grid of the env's map
   int64_t ctile_off;                 // byte offset of the map's cell tiles in the cell-tile arena
-  float fwd[6];                      // cv::warpAffine's forward matrix (source -> crop), for the sparse kernel
+  int32_t fwd[6];                    // cv::warpAffine's forward matrix (source -> crop) in 16.16 fixed point, translation
+                                     // relative to the window origin (X0, Y0): the sparse kernel's candidate pixels
   int32_t dense_map;                 // bit 0: more than 1 cell in 20 of the map is occupied (skip the sparse kernel's
                                      // scan); bit 1: every occupied cell is 254 (BCG_MAP_ONLY_LETHAL)
   // what the sparse kernel needs of the map descriptor, so that its loads start from the record alone
@@ -400,7 +401,10 @@ __device__ __forceinline__ void write_ego_tile_record(const BcgParams& p, const 
                                                       const BcgMapDesc& m, double px, double py, double pth, int win_capacity) {
   EgoTileWork* rec = reinterpret_cast<EgoTileWork*>(reinterpret_cast<uint8_t*>(b.ego_work) + (int64_t)e * BCG_EGO_WORK_BYTES);
   EgoTileWork w;
-  w.aff = ego_affine(p, m, px, py, pth, w.fwd);
+  float fwd[6];
+  w.aff = ego_affine(p, m, px, py, pth, fwd);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) w.fwd[k] = 0;
   w.X0 = w.Y0 = w.ntx = w.nty = 0;
   w.mode = BCG_EGO_MODE_DIRECT;
   w.map_id = map_id;
@@ -426,6 +430,16 @@ __device__ __forceinline__ void write_ego_tile_record(const BcgParams& p, const 
       w.Y0 = y0;
       w.ntx = ntx;
       w.nty = nty;
+      // crop pixel of window cell (xr, yr): floor((fwd0 xr + fwd1 yr + fwd2) >> 16), same for v.  Candidates only (the
+      // exact fixed-point rule decides): 2^-17 per coefficient x 255 cells is far inside the 0.29 px the rule leaves
+      const double c0 = (double)fwd[0] * x0 + (double)fwd[1] * y0 + (double)fwd[2];
+      const double c1 = (double)fwd[3] * x0 + (double)fwd[4] * y0 + (double)fwd[5];
+      w.fwd[0] = __double2int_rn((double)fwd[0] * 65536.0);
+      w.fwd[1] = __double2int_rn((double)fwd[1] * 65536.0);
+      w.fwd[2] = __double2int_rn(fmin(fmax(c0, -16000.0), 16000.0) * 65536.0);
+      w.fwd[3] = __double2int_rn((double)fwd[3] * 65536.0);
+      w.fwd[4] = __double2int_rn((double)fwd[4] * 65536.0);
+      w.fwd[5] = __double2int_rn(fmin(fmax(c1, -16000.0), 16000.0) * 65536.0);
     }
   }
   uint4* dst = reinterpret_cast<uint4*>(rec);
@@ -2096,7 +2110,7 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
         src = b.map_arena + md->data_off;
         pitch = md->pitch;
       }
-      const float m0 = r->fwd[0], m1 = r->fwd[1], m2 = r->fwd[2], m3 = r->fwd[3], m4 = r->fwd[4], m5 = r->fwd[5];
+      const int m0 = r->fwd[0], m1 = r->fwd[1], m2 = r->fwd[2], m3 = r->fwd[3], m4 = r->fwd[4], m5 = r->fwd[5];
       // the loop is instantiated per kind of map: with every occupied cell lethal the value is a constant and the address
       // arithmetic of the cost-byte load (predicated off, but issued) is gone
       auto scatter = [&](auto lethal_tag) {
@@ -2104,10 +2118,10 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
       for (uint32_t i = tid; i < count; i += NT) {
         const uint32_t key = lds_u32(list_u32 + 4u * i);
         const int xr = (int)(key & 0xffffu), yr = (int)(key >> 16);
-        const float X = (float)(X0 + xr), Y = (float)(Y0 + yr);
-        // candidates only: fused multiply-adds are fine here, the fixed-point test below decides
-        const int fu = __float2int_rd(__fmaf_rn(m0, X, __fmaf_rn(m1, Y, m2)));
-        const int fv = __float2int_rd(__fmaf_rn(m3, X, __fmaf_rn(m4, Y, m5)));
+        // candidates only, in 16.16 integers (no conversions: they run on the quarter-rate unit); the fixed-point test
+        // below decides
+        const int fu = (m0 * xr + m1 * yr + m2) >> 16;
+        const int fv = (m3 * xr + m4 * yr + m5) >> 16;
         if (fu < -1 || fu >= ego_w || fv < -1 || fv >= ego_h) continue;     // every candidate is outside the crop
         uint8_t val = 254;
         if (!LETHAL) val = __ldg(src + (int64_t)(Y0 + yr) * pitch + (X0 + xr));

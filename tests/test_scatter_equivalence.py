@@ -1,7 +1,7 @@
 """CPU: the claim ego_sparse_kernel rests on, checked in NumPy against the oracle's gather (= cv2.warpAffine).
 
 The kernel renders the egocentric crop as a scatter: every occupied source cell (X, Y) is mapped forward with the
-float32 matrix cv2 is given, and only the <= 4 crop pixels around its image are tested with the exact fixed-point
+float32 matrix cv2 is given (in 16.16 fixed point, relative to the window origin), and only the <= 4 crop pixels around its image are tested with the exact fixed-point
 inverse rule `X == (adx[u] + bx[v]) >> 10 and Y == (ady[u] + by[v]) >> 10`.  That is bit-identical to
 the gather iff every pixel that samples (X, Y) is among those four candidates.  Here: random maps, random poses (on
 the map, at its border, outside it), every cost value -- scatter == gather."""
@@ -31,10 +31,19 @@ def _scatter(costmap, pose, origin, resolution):
     ys, xs = np.nonzero(costmap)
     if len(xs) == 0:
         return out, 0
-    X, Y = xs.astype(np.float32), ys.astype(np.float32)
-    # the kernel's candidates: floor of the float32 forward image, and the next pixel, per axis
-    fu = np.floor(m32[0, 0] * X + (m32[0, 1] * Y + m32[0, 2])).astype(np.int64)
-    fv = np.floor(m32[1, 0] * X + (m32[1, 1] * Y + m32[1, 2])).astype(np.int64)
+    # the kernel's candidates: the forward image in 16.16 fixed point relative to the window origin (the tile-aligned
+    # corner of the rotated crop's bounding box, write_ego_tile_record), floored, and the next pixel, per axis
+    qx = np.array([b1, a11 * (w - 1) + b1, a11 * (w - 1) + a12 * (h - 1) + b1, a12 * (h - 1) + b1])
+    qy = np.array([b2, a21 * (w - 1) + b2, a21 * (w - 1) + a22 * (h - 1) + b2, a22 * (h - 1) + b2])
+    x0 = int(np.floor(qx.min() - 0.51)) & ~15
+    y0 = int(np.floor(qy.min() - 0.51)) & ~7
+    fx = [int(np.rint(m[0, 0] * 65536)), int(np.rint(m[0, 1] * 65536)),
+          int(np.rint(np.clip(m[0, 0] * x0 + m[0, 1] * y0 + m[0, 2], -16000, 16000) * 65536))]
+    fy = [int(np.rint(m[1, 0] * 65536)), int(np.rint(m[1, 1] * 65536)),
+          int(np.rint(np.clip(m[1, 0] * x0 + m[1, 1] * y0 + m[1, 2], -16000, 16000) * 65536))]
+    xr, yr = xs.astype(np.int64) - x0, ys.astype(np.int64) - y0
+    fu = (fx[0] * xr + fx[1] * yr + fx[2]) >> 16
+    fv = (fy[0] * xr + fy[1] * yr + fy[2]) >> 16
     inside = (fu >= -1) & (fu < w) & (fv >= -1) & (fv < h)
     xs, ys, fu, fv = xs[inside], ys[inside], fu[inside], fv[inside]
     vals = costmap[ys, xs]
