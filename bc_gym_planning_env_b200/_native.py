@@ -163,6 +163,7 @@ SYMBOLS = {
     "bcg_inverse_transform": (C.c_int, [_P, C.c_int64, _P, _P]),
     "bcg_project_poses": (C.c_int, [C.POINTER(C.c_double), _P, C.c_int64, _P, _P]),
     "bcg_observe_ego_path": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgBatch), C.c_int32, _P, _P, _P]),
+    "bcg_rollout": (C.c_int, [C.POINTER(BcgParams), C.POINTER(BcgBatch), _P, C.c_int32, C.c_uint64, C.POINTER(BcgStepOut), _P]),
     "bcg_alloc_image_memory": (C.c_int, [C.c_int64, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "bcg_free_image_memory": (C.c_int, [_P, C.c_int64]),
 }

@@ -72,6 +72,44 @@ static int driver_fn(const char* name, F* out) {
     if (!(cond)) return fail(BCG_ERR_INVALID, msg); \
   } while (0)
 
+// Programmatic dependent launch: a step kernel launched with the attribute may start while its predecessor in the stream
+// is still draining (launch latency and its own prologue overlap that tail); it calls pdl_wait() before it touches
+// anything the predecessor wrote -- the wait returns when the predecessor grid has completed and its writes are visible.
+// Kernels that call pdl_launch_next() let their successor's CTAs be scheduled once every CTA of theirs has started.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_next() {
+#if BCG_PDL_EARLY_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
+#ifndef BCG_PDL_EARLY_TRIGGER
+#define BCG_PDL_EARLY_TRIGGER 0
+#endif
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("BCG_PDL");
+    return !(v && v[0] == '0');
+  }();
+  return on;
+}
+
+template <class... KArgs, class... Args>
+cudaError_t launch_step_kernel(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 BcgStateLayout make_layout(const BcgParams& p) {
   BcgStateLayout L;
   L.ring_control = BCG_F_FIXED;
@@ -625,6 +663,8 @@ __global__ void __launch_bounds__(BCG_MOVE_THREADS, MIN_BLOCKS)
 #endif
 move_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L, const void* __restrict__ actions,
             const int action_is_f64, const uint64_t step_index_arg, const BcgStepOut out, const int ego_cap) {
+  pdl_wait();                                            // the previous step's kernels are done with the records and rows
+  pdl_launch_next();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= b.n_envs) return;
   const int64_t N = b.n_envs;
@@ -814,6 +854,8 @@ __device__ __forceinline__ void reset_env_rows(const BcgParams& p, const BcgBatc
 template <int G>
 __global__ void __launch_bounds__(BCG_REWARD_THREADS, BCG_REWARD_RESIDENT / BCG_REWARD_THREADS)
 reward_kernel(const BcgParams p, const BcgBatch b, const BcgStepOut out, const int ego_cap) {
+  pdl_wait();                                            // move_kernel's records
+  pdl_launch_next();
   const int e = (blockIdx.x * blockDim.x + threadIdx.x) / G;
   const unsigned lane = threadIdx.x & 31, gl = lane & (G - 1);
   const bool active = e < b.n_envs;
@@ -1851,11 +1893,13 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
   };
   constexpr int RD = 3;
   static_assert(RD < BCG_EGS_REC_SLOTS, "record ring too small");
+  for (int i = tid * 16; i < BCG_EGS_ZERO_BYTES; i += NT * 16) *reinterpret_cast<uint4*>(zero_s + i) = make_uint4(0u, 0u, 0u, 0u);
+  if (tid < 2) T.count[tid] = T.hits[tid] = 0;
+  pdl_wait();                                 // the records (and, on a reset, the state) are reward_kernel's
+  pdl_launch_next();
 #pragma unroll
   for (int k = 0; k < RD; ++k) fetch_record(e0 + k * G, k);
   cp_async_commit();
-  for (int i = tid * 16; i < BCG_EGS_ZERO_BYTES; i += NT * 16) *reinterpret_cast<uint4*>(zero_s + i) = make_uint4(0u, 0u, 0u, 0u);
-  if (tid < 2) T.count[tid] = T.hits[tid] = 0;
 #if BCG_EGS_DYNAMIC
   // Which envs a CTA renders: its first RD + 1 are blockIdx.x + k G; the later ones come from a global counter
   // (ego_list[n + 1], zeroed with the hand-over count), drawn RD + 1 iterations ahead so that the record can be
@@ -2674,6 +2718,7 @@ struct EgoHits {       // BcgStepOut.ego_hits / ego_hit_count / ego_hit_cap (all
   uint32_t* list;
   int32_t* count;
   int cap;
+  bool pdl;            // launch the sparse kernel as a programmatic dependent of the kernel before it (the step path)
 };
 
 static int launch_ego_sparse(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, const EgoHits& hits, cudaStream_t s) {
@@ -2710,12 +2755,14 @@ static int launch_ego_sparse(const BcgParams* p, const BcgBatch* b, uint8_t* ego
     return v ? atoll(v) : 160ll << 20;
   }();
   const int evict = (long long)b->n_envs * p->ego_w * p->ego_h <= evict_bytes ? 0 : b->n_envs;   // evict_from: envs >= it use the policy
+  uint32_t* const no_list = nullptr;
+  int32_t* const no_count = nullptr;
   if (hits.list) {
-    if (sum) ego_sparse_kernel<true, true><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image, hits.list, hits.count, hits.cap, evict);
-    else ego_sparse_kernel<false, true><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image, hits.list, hits.count, hits.cap, evict);
+    if (sum) BCG_CHECK_CUDA(launch_step_kernel(ego_sparse_kernel<true, true>, grid, BCG_EGS_THREADS, tab_bytes, s, hits.pdl, *p, *b, ego_image, hits.list, hits.count, hits.cap, evict));
+    else BCG_CHECK_CUDA(launch_step_kernel(ego_sparse_kernel<false, true>, grid, BCG_EGS_THREADS, tab_bytes, s, hits.pdl, *p, *b, ego_image, hits.list, hits.count, hits.cap, evict));
   } else {
-    if (sum) ego_sparse_kernel<true, false><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image, nullptr, nullptr, 0, evict);
-    else ego_sparse_kernel<false, false><<<grid, BCG_EGS_THREADS, tab_bytes, s>>>(*p, *b, ego_image, nullptr, nullptr, 0, evict);
+    if (sum) BCG_CHECK_CUDA(launch_step_kernel(ego_sparse_kernel<true, false>, grid, BCG_EGS_THREADS, tab_bytes, s, hits.pdl, *p, *b, ego_image, no_list, no_count, 0, evict));
+    else BCG_CHECK_CUDA(launch_step_kernel(ego_sparse_kernel<false, false>, grid, BCG_EGS_THREADS, tab_bytes, s, hits.pdl, *p, *b, ego_image, no_list, no_count, 0, evict));
   }
   BCG_CHECK_CUDA(cudaGetLastError());
   if (b->flags & BCG_BATCH_SPARSE_EGO_ONLY) return BCG_OK;     // the sparse kernel rendered every env itself
@@ -2757,7 +2804,7 @@ int bcg_observe_ego(const BcgParams* p, const BcgBatch* b, uint8_t* ego_image, f
   ego_prep_kernel<<<blocks_for(b->n_envs, 128), 128, 0, s>>>(*p, *b, ego_image ? 1 : 0, goal_n_state,
                                                             ego_capacity(*p, *b));
   BCG_CHECK_CUDA(cudaGetLastError());
-  if (ego_image) return launch_ego_image(p, b, ego_image, EgoHits{nullptr, nullptr, 0}, s);
+  if (ego_image) return launch_ego_image(p, b, ego_image, EgoHits{nullptr, nullptr, 0, false}, s);
   return BCG_OK;
 }
 
@@ -2778,24 +2825,26 @@ int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, 
     int sms = 0;
     if (int rc = sm_count_of_current_device(&sms)) return rc;
     const int move_blocks = (int)blocks_for(b->n_envs, BCG_MOVE_THREADS);
+    // (event records between the kernels are stream operations of their own: the timed form runs without the overlap)
+    const bool pdl = events == nullptr;
+    const int64_t ns = b->n_envs;
     if (move_blocks <= sms * BCG_MOVE_FEWER_BLOCKS)
-      move_kernel<BCG_MOVE_FEWER_BLOCKS><<<move_blocks, BCG_MOVE_THREADS, 0, s>>>(*p, *b, L, actions, action_is_f64, step_index, *out, cap);
+      BCG_CHECK_CUDA(launch_step_kernel(move_kernel<BCG_MOVE_FEWER_BLOCKS>, move_blocks, BCG_MOVE_THREADS, 0, s, pdl, *p, *b, L, actions, (int)action_is_f64, step_index, *out, cap));
     else if (move_blocks <= sms * BCG_MOVE_FEW_BLOCKS)
-      move_kernel<BCG_MOVE_FEW_BLOCKS><<<move_blocks, BCG_MOVE_THREADS, 0, s>>>(*p, *b, L, actions, action_is_f64, step_index, *out, cap);
+      BCG_CHECK_CUDA(launch_step_kernel(move_kernel<BCG_MOVE_FEW_BLOCKS>, move_blocks, BCG_MOVE_THREADS, 0, s, pdl, *p, *b, L, actions, (int)action_is_f64, step_index, *out, cap));
     else
-      move_kernel<BCG_MOVE_MIN_BLOCKS><<<move_blocks, BCG_MOVE_THREADS, 0, s>>>(*p, *b, L, actions, action_is_f64, step_index, *out, cap);
-    BCG_CHECK_CUDA(cudaGetLastError());
+      BCG_CHECK_CUDA(launch_step_kernel(move_kernel<BCG_MOVE_MIN_BLOCKS>, move_blocks, BCG_MOVE_THREADS, 0, s, pdl, *p, *b, L, actions, (int)action_is_f64, step_index, *out, cap));
     if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[2], s));
-    if (b->n_envs > 16384) reward_kernel<8><<<blocks_for((int64_t)b->n_envs * 8, BCG_REWARD_THREADS), BCG_REWARD_THREADS, 0, s>>>(*p, *b, *out, cap);
-    else if (b->n_envs > 2048) reward_kernel<16><<<blocks_for((int64_t)b->n_envs * 16, BCG_REWARD_THREADS), BCG_REWARD_THREADS, 0, s>>>(*p, *b, *out, cap);
-    else reward_kernel<32><<<blocks_for((int64_t)b->n_envs * 32, BCG_REWARD_THREADS), BCG_REWARD_THREADS, 0, s>>>(*p, *b, *out, cap);
+    if (ns > 16384) BCG_CHECK_CUDA(launch_step_kernel(reward_kernel<8>, blocks_for(ns * 8, BCG_REWARD_THREADS), BCG_REWARD_THREADS, 0, s, pdl, *p, *b, *out, cap));
+    else if (ns > 2048) BCG_CHECK_CUDA(launch_step_kernel(reward_kernel<16>, blocks_for(ns * 16, BCG_REWARD_THREADS), BCG_REWARD_THREADS, 0, s, pdl, *p, *b, *out, cap));
+    else BCG_CHECK_CUDA(launch_step_kernel(reward_kernel<32>, blocks_for(ns * 32, BCG_REWARD_THREADS), BCG_REWARD_THREADS, 0, s, pdl, *p, *b, *out, cap));
     BCG_CHECK_CUDA(cudaGetLastError());
   }
   if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[3], s));
   if (out->ego_image) {
     BCG_REQUIRE((out->ego_hits != nullptr) == (out->ego_hit_count != nullptr) && (!out->ego_hits || out->ego_hit_cap > 0),
                 "ego_hits, ego_hit_count and ego_hit_cap go together");
-    if (int rc = launch_ego_image(p, b, out->ego_image, EgoHits{out->ego_hits, out->ego_hit_count, out->ego_hit_cap}, s)) return rc;
+    if (int rc = launch_ego_image(p, b, out->ego_image, EgoHits{out->ego_hits, out->ego_hit_count, out->ego_hit_cap, events == nullptr}, s)) return rc;
   }
   if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[4], s));
   return BCG_OK;
@@ -2804,6 +2853,14 @@ int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, 
 int bcg_step(const BcgParams* p, const BcgBatch* b, const void* actions, int32_t action_is_f64, uint64_t step_index,
              const BcgStepOut* out, void* stream) {
   return bcg_step_events(p, b, actions, action_is_f64, step_index, out, nullptr, stream);
+}
+
+int bcg_rollout(const BcgParams* p, const BcgBatch* b, const float* plan, int32_t horizon, uint64_t step_index,
+                const BcgStepOut* out, void* stream) {
+  BCG_REQUIRE(plan && horizon >= 0, "null plan / negative horizon");
+  for (int32_t h = 0; h < horizon; ++h)
+    if (int rc = bcg_step(p, b, plan + (int64_t)h * b->n_envs * 2, 0, step_index + (uint64_t)h, out, stream)) return rc;
+  return BCG_OK;
 }
 
 static int launch_collision_kernel(const BcgBatch* b, uint8_t* flags_out, int32_t* pixels_out, int use_u8, cudaStream_t s) {

@@ -80,9 +80,9 @@ def monte_carlo_rollouts(env, start, actions, reduce=True, cols=None):
     from bc_gym_planning_env_b200 import _native as nat
     acts = actions.to(env.device)[:, cols].contiguous()          # [H, n, 2]: one gather for the whole horizon
     # the rollout's return accumulates on the device in the episode-return row, started from zero (the same additions in
-    # the same order as summing the step rewards); the H steps are one CUDA-graph launch
+    # the same order as summing the step rewards); the H steps are launched from one library call
     env.state_f[nat.F_EP_RETURN].zero_()
-    env.rollout_graph(acts)
+    env.rollout(acts)
     ret = env.state_f[nat.F_EP_RETURN]
     out = torch.zeros((k, 4), dtype=torch.float64, device=env.device)
     out[:, 0].index_add_(0, cols, ret)

@@ -490,6 +490,20 @@ class VecPlanEnv(object):
         self._step_index += 1
         return self.observation(), self.reward, self.done, {}
 
+    def rollout(self, plan):
+        """H steps of a fixed action plan from ONE library call (bcg_rollout): the 2-3 kernels of every step are launched
+        back to back, each a programmatic dependent of the one before -- no Python between the steps.  plan: float
+        [H, N, 2] on the device.  Read `state_f` / `reward` (last step) / `done` afterwards; the episode return
+        accumulates in row F_EP_RETURN."""
+        plan = plan.to(self.device)
+        if plan.dim() != 3 or tuple(plan.shape[1:]) != (self.n_envs, 2):
+            raise ValueError("plan must have shape [H, %d, 2]" % self.n_envs)
+        plan = plan.to(torch.float32).contiguous()
+        horizon = int(plan.shape[0])
+        nat.check(nat.lib().bcg_rollout(C.byref(self._c_params), C.byref(self._batch), nat.ptr(plan), horizon, self._step_index,
+                                        C.byref(self._out), self._stream()))
+        self._step_index += horizon
+
     def rollout_graph(self, plan):
         """H steps of a fixed action plan as ONE CUDA-graph launch (Monte-Carlo fan-outs: README.md:45-61 of the
         reference steps a copied env through a candidate plan).  plan: float [H, N, 2]; it is copied into a persistent

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BCG_ABI_VERSION 10
+#define BCG_ABI_VERSION 11
 
 /* error codes */
 #define BCG_OK 0
@@ -418,6 +418,13 @@ int bcg_project_poses(const double* transform_host, const double* poses, int64_t
  * tensor in the robot frame (from_global_to_egocentric, coordinate_transformations.py:341-362, about the observed pose):
  * out device [n][max_points][3] zero padded, len_out (optional) device [n] = way points left (may exceed max_points) */
 int bcg_observe_ego_path(const BcgParams* p, const BcgBatch* b, int32_t max_points, double* out, int32_t* len_out, void* stream);
+
+/* H steps of a fixed action plan (Monte-Carlo fan-outs: the reference steps a copied env through a candidate plan,
+ * README.md:45-61): bcg_step for plan[h], h = 0 .. horizon - 1, launched back to back from one call -- every kernel a
+ * programmatic dependent of the one before, no host work in between.  plan: device float32 [horizon][n_envs][2];
+ * step h uses the Philox step index step_index + h (or the device-side counter when BcgBatch.step_counter is set). */
+int bcg_rollout(const BcgParams* p, const BcgBatch* b, const float* plan, int32_t horizon, uint64_t step_index,
+                const BcgStepOut* out, void* stream);
 
 /* -- image memory --------------------------------------------------------------------------------
  * Egocentric crops are mostly zeros.  A device allocation with compute-data compression (CUDA virtual memory

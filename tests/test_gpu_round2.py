@@ -191,22 +191,27 @@ def test_move_kernel_register_tiers_give_the_same_bits():
         env.check_status()
 
 
-def test_rollout_graph_equals_plain_steps():
-    """rollout_graph runs the H steps of a plan as one captured graph (device-side step counter); the state, the last
-    rewards and the accumulated returns equal H plain steps, also when the graph is replayed with another plan."""
+def test_rollout_and_rollout_graph_equal_plain_steps():
+    """rollout (one library call launching the H steps back to back) and rollout_graph (the H steps as one captured
+    graph, device-side step counter): state, last rewards and accumulated returns equal H plain steps, also on a second
+    plan."""
     params = EnvParams(control_delay=2, pose_delay=1, state_delay=1)
     costmaps, paths = random_aisle_pool(12, 5, params)
     kw = dict(n_envs=300, seed=21, auto_reset=False, with_ego=False, noise_parameters=DEFAULT_NOISE)
-    a, b = VecPlanEnv(costmaps, paths, params, **kw), VecPlanEnv(costmaps, paths, params, **kw)
+    a, b, c = (VecPlanEnv(costmaps, paths, params, **kw) for _ in range(3))
     H = 40
     for rep in range(2):
         plan = torch.stack(_actions(a, H, 100 + rep))
         for h in range(H):
             a.step(plan[h])
         b.rollout_graph(plan)
-        assert torch.equal(a.state_f, b.state_f) and torch.equal(a.state_i, b.state_i), rep
-        assert torch.equal(a.reward, b.reward) and torch.equal(a.done, b.done), rep
+        c.rollout(plan)
+        for other in (b, c):
+            assert torch.equal(a.state_f, other.state_f) and torch.equal(a.state_i, other.state_i), rep
+            assert torch.equal(a.reward, other.reward) and torch.equal(a.done, other.done), rep
     with pytest.raises(ValueError):
         b.rollout_graph(plan[:, :10])
-    a.check_status()
-    b.check_status()
+    with pytest.raises(ValueError):
+        c.rollout(plan[:, :10])
+    for env in (a, b, c):
+        env.check_status()

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "libbcg_b200.so does not export %s" % name
     assert sorted(nat.SYMBOLS) == declared, "ctypes binding and header disagree"
-    assert lib.bcg_abi_version() == 10
+    assert lib.bcg_abi_version() == 11
 
 
 def test_struct_mirrors_match_library():
