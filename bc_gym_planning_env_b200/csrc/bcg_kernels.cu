@@ -2818,15 +2818,16 @@ int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, 
   }
   cudaStream_t s = (cudaStream_t)stream;
   const BcgStateLayout L = make_layout(*p);
-  if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[0], s));
+  if (events && events[0]) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[0], s));
   {
-    if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[1], s));
+    if (events && events[1]) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[1], s));
     const int cap = ego ? ego_capacity(*p, *b) : 0;
     int sms = 0;
     if (int rc = sm_count_of_current_device(&sms)) return rc;
     const int move_blocks = (int)blocks_for(b->n_envs, BCG_MOVE_THREADS);
     // (event records between the kernels are stream operations of their own: the timed form runs without the overlap)
-    const bool pdl = events == nullptr;
+    const bool pdl = !(events && (events[0] || events[1]));          // an event right before a kernel: no overlap for it
+    const bool pdl_reward = !(events && events[2]);
     const int64_t ns = b->n_envs;
     if (move_blocks <= sms * BCG_MOVE_FEWER_BLOCKS)
       BCG_CHECK_CUDA(launch_step_kernel(move_kernel<BCG_MOVE_FEWER_BLOCKS>, move_blocks, BCG_MOVE_THREADS, 0, s, pdl, *p, *b, L, actions, (int)action_is_f64, step_index, *out, cap));
@@ -2834,19 +2835,19 @@ int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, 
       BCG_CHECK_CUDA(launch_step_kernel(move_kernel<BCG_MOVE_FEW_BLOCKS>, move_blocks, BCG_MOVE_THREADS, 0, s, pdl, *p, *b, L, actions, (int)action_is_f64, step_index, *out, cap));
     else
       BCG_CHECK_CUDA(launch_step_kernel(move_kernel<BCG_MOVE_MIN_BLOCKS>, move_blocks, BCG_MOVE_THREADS, 0, s, pdl, *p, *b, L, actions, (int)action_is_f64, step_index, *out, cap));
-    if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[2], s));
-    if (ns > 16384) BCG_CHECK_CUDA(launch_step_kernel(reward_kernel<8>, blocks_for(ns * 8, BCG_REWARD_THREADS), BCG_REWARD_THREADS, 0, s, pdl, *p, *b, *out, cap));
-    else if (ns > 2048) BCG_CHECK_CUDA(launch_step_kernel(reward_kernel<16>, blocks_for(ns * 16, BCG_REWARD_THREADS), BCG_REWARD_THREADS, 0, s, pdl, *p, *b, *out, cap));
-    else BCG_CHECK_CUDA(launch_step_kernel(reward_kernel<32>, blocks_for(ns * 32, BCG_REWARD_THREADS), BCG_REWARD_THREADS, 0, s, pdl, *p, *b, *out, cap));
+    if (events && events[2]) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[2], s));
+    if (ns > 16384) BCG_CHECK_CUDA(launch_step_kernel(reward_kernel<8>, blocks_for(ns * 8, BCG_REWARD_THREADS), BCG_REWARD_THREADS, 0, s, pdl_reward, *p, *b, *out, cap));
+    else if (ns > 2048) BCG_CHECK_CUDA(launch_step_kernel(reward_kernel<16>, blocks_for(ns * 16, BCG_REWARD_THREADS), BCG_REWARD_THREADS, 0, s, pdl_reward, *p, *b, *out, cap));
+    else BCG_CHECK_CUDA(launch_step_kernel(reward_kernel<32>, blocks_for(ns * 32, BCG_REWARD_THREADS), BCG_REWARD_THREADS, 0, s, pdl_reward, *p, *b, *out, cap));
     BCG_CHECK_CUDA(cudaGetLastError());
   }
-  if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[3], s));
+  if (events && events[3]) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[3], s));
   if (out->ego_image) {
     BCG_REQUIRE((out->ego_hits != nullptr) == (out->ego_hit_count != nullptr) && (!out->ego_hits || out->ego_hit_cap > 0),
                 "ego_hits, ego_hit_count and ego_hit_cap go together");
-    if (int rc = launch_ego_image(p, b, out->ego_image, EgoHits{out->ego_hits, out->ego_hit_count, out->ego_hit_cap, events == nullptr}, s)) return rc;
+    if (int rc = launch_ego_image(p, b, out->ego_image, EgoHits{out->ego_hits, out->ego_hit_count, out->ego_hit_cap, !(events && events[3])}, s)) return rc;
   }
-  if (events) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[4], s));
+  if (events && events[4]) BCG_CHECK_CUDA(cudaEventRecord((cudaEvent_t)events[4], s));
   return BCG_OK;
 }
 

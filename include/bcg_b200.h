@@ -353,10 +353,11 @@ int bcg_generate_minis(const BcgParams* p, const BcgBatch* b, const BcgAisleSlot
 int bcg_step(const BcgParams* p, const BcgBatch* b, const void* actions, int32_t action_is_f64,
              uint64_t step_index, const BcgStepOut* out, void* stream);
 
-/* bcg_step with per-kernel timing hooks: events[0..4] are caller-created cudaEvent_t handles (timing
- * enabled) recorded on `stream`: [2] before and [3] after the state kernel, [4] after the egocentric kernels
- * ([0], [1] coincide with [2]; with BCG_STEP_KERNELS=split they bracket the kinematic and collide/reward
- * kernels of round 1).  events == NULL behaves exactly like bcg_step. */
+/* bcg_step with per-kernel hooks: events[0..4] are caller-created cudaEvent_t handles recorded on `stream`: [0], [1]
+ * before move_kernel, [2] between move_kernel and reward_kernel, [3] after reward_kernel (reward / done / compact
+ * observation are final: a host consumer's copies can start here while the egocentric kernel runs), [4] after the
+ * egocentric kernels.  Any entry may be NULL (not recorded).  A kernel with an event recorded right before it is not
+ * launched as a programmatic dependent of its predecessor.  events == NULL behaves exactly like bcg_step. */
 int bcg_step_events(const BcgParams* p, const BcgBatch* b, const void* actions, int32_t action_is_f64,
                     uint64_t step_index, const BcgStepOut* out, void* const* events, void* stream);
 
