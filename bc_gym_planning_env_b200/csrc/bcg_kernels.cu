@@ -656,11 +656,7 @@ __device__ __forceinline__ void write_goal_from_transform(const BcgParams& p, co
 // MIN_BLOCKS is the register budget: 8 CTAs per SM = 128 registers (1 024 envs in flight per SM: the large batch needs
 // the warps), 6 = 168 registers (no spills; ~3.5 us less on the chain when the whole batch fits one wave of 384 per SM).
 template <int MIN_BLOCKS>
-#ifdef BCG_MOVE_MAXNREG
-__global__ void __maxnreg__(MIN_BLOCKS == BCG_MOVE_MIN_BLOCKS ? BCG_MOVE_MAXNREG : (MIN_BLOCKS == 6 ? 168 : 232))
-#else
 __global__ void __launch_bounds__(BCG_MOVE_THREADS, MIN_BLOCKS)
-#endif
 move_kernel(const BcgParams p, const BcgBatch b, const BcgStateLayout L, const void* __restrict__ actions,
             const int action_is_f64, const uint64_t step_index_arg, const BcgStepOut out, const int ego_cap) {
   pdl_wait();                                            // the previous step's kernels are done with the records and rows

@@ -1,3 +1,7 @@
+"""The three collision kernels against one another on random poses near the walls (run on the GPU box):
+    python profiles/probes/collide_check.py
+thread-per-env kernel (collide_warp_balanced, the code move_kernel inlines), warp-per-env tile kernel and the uint8
+kernel must agree for full warps and for batches that end in a partly filled warp (37 and 5 envs)."""
 import sys, os
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch
