@@ -87,12 +87,13 @@ __device__ __forceinline__ void pdl_launch_next() {
 #define BCG_PDL_EARLY_TRIGGER 0
 #endif
 
+bool g_pdl_refused = false;       // the driver turned a dependent launch down once: classic launches from then on
 bool pdl_enabled() {
   static const bool on = [] {
     const char* v = getenv("BCG_PDL");
     return !(v && v[0] == '0');
   }();
-  return on;
+  return on && !g_pdl_refused;
 }
 
 template <class... KArgs, class... Args>
@@ -107,7 +108,14 @@ cudaError_t launch_step_kernel(void (*kernel)(KArgs...), int grid, int block, si
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+  cudaError_t err = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+  if (err != cudaSuccess && cfg.numAttrs == 1 && (err == cudaErrorNotSupported || err == cudaErrorInvalidValue)) {
+    (void)cudaGetLastError();           // a driver without programmatic dependent launch: same kernel, ordinary launch
+    g_pdl_refused = true;
+    cfg.numAttrs = 0;
+    err = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+  }
+  return err;
 }
 
 BcgStateLayout make_layout(const BcgParams& p) {

@@ -364,8 +364,13 @@ class VecPlanEnv(object):
         self.image_memory_compressed = False
         if mode != "plain" and int(np.prod(shape)) >= (1 << 20):      # small batches: not worth a 2 MB mapping of their own
             with torch.cuda.device(self.device):
-                block = nat.ImageMemory(int(np.prod(shape)), want_compression=(mode == "compressed"))
-                if block.compressed or mode == "vmm":
+                try:
+                    block = nat.ImageMemory(int(np.prod(shape)), want_compression=(mode == "compressed"))
+                except nat.BcgError:
+                    if mode == "vmm":
+                        raise
+                    block = None                           # no virtual-memory API on this device / driver: torch's pool
+                if block is not None and (block.compressed or mode == "vmm"):
                     self.image_memory_compressed = block.compressed
                     return block.tensor(shape)
                 del block                                  # no compression on this device: nothing gained over torch's pool
