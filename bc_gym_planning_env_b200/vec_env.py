@@ -570,7 +570,8 @@ class VecPlanEnv(object):
         With `images` the egocentric crops (uint8 [N, H, W]) and goal_n_state (float32 [N, 9]) are copied to pinned
         host memory as well, after the egocentric kernel (N x 15.6 KB per step: the PCIe link then sets the pace).
         Returns (reward, done, obs_vec) host tensors -- plus (ego_image, goal_n_state) with `images` --, valid when
-        this call returns (it synchronises)."""
+        this call returns.  It waits for exactly what it returns: without `images` that is the copies of reward / done /
+        obs, not the egocentric kernel, which finishes in stream order behind them."""
         if getattr(self, '_host_io', None) is None:
             n = self.n_envs
             self._host_io = dict(
@@ -579,6 +580,7 @@ class VecPlanEnv(object):
                 done=torch.empty(n, dtype=torch.uint8).pin_memory(),
                 obs=torch.empty((n, 12), dtype=torch.float32).pin_memory(),
                 stream=torch.cuda.Stream(device=self.device),
+                upload=torch.cuda.Stream(device=self.device), uploaded=torch.cuda.Event(enable_timing=False),
                 events=[torch.cuda.Event(enable_timing=False) for _ in range(5)])
             for ev in self._host_io['events']:
                 ev.record()                                   # creates the handles bcg_step_events records into
@@ -586,7 +588,12 @@ class VecPlanEnv(object):
         if tuple(actions_host.shape) != (self.n_envs, 2) or actions_host.dtype != torch.float32:
             raise ValueError("actions_host must be a float32 tensor of shape (%d, 2)" % self.n_envs)
         main = torch.cuda.current_stream(self.device)
-        io['actions'].copy_(actions_host, non_blocking=True)
+        # the actions go up on a stream of their own: the previous step's egocentric kernel may still be running on the
+        # main stream (see below), and its move_kernel -- the reader of this buffer -- finished before that step returned
+        with torch.cuda.stream(io['upload']):
+            io['actions'].copy_(actions_host, non_blocking=True)
+            io['uploaded'].record()
+        main.wait_event(io['uploaded'])
         if images == 'compact':
             if self._ego_hits is None:
                 raise ValueError("this batch was built without compact_ego=True")
@@ -617,7 +624,11 @@ class VecPlanEnv(object):
             io['ego_image'].copy_(self.ego_image, non_blocking=True)
             io['goal_n_state'].copy_(self.goal_n_state, non_blocking=True)
         side.synchronize()
-        main.synchronize()
+        if compact is not None or images:
+            main.synchronize()                                # the crops were asked for: wait for the egocentric kernel too
+        # (without `images` the call returns when reward / done / obs are on the host.  The egocentric kernel may still be
+        # running: `ego_image` is valid for whatever is enqueued on the current stream next, and the next step_host call
+        # queues behind it -- the host prepares the next actions meanwhile instead of leaving the GPU idle)
         if compact is not None:
             return io['reward'], io['done'], io['obs'], compact, io['goal_n_state']
         if images:

@@ -651,9 +651,12 @@ def measure_e2e(env, actions, args, D, n):
     ms, _ = loop(args.e2e_steps)
     out["resident"] = {"value": n * world * args.e2e_steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": d2h,
-                       "note": "VecPlanEnv.step_host: pinned-host actions in; reward f64, done u8 and the 12-float compact "
-                               "observation out to pinned host memory every step (copies overlap the egocentric kernel); "
-                               "egocentric images stay in HBM for a GPU-resident policy (e2e_images_to_host has the rest)"}
+                       "note": "VecPlanEnv.step_host: pinned-host actions in (upload stream); reward f64, done u8 and the "
+                               "12-float compact observation out to pinned host memory every step (copies on a side stream "
+                               "right after reward_kernel); the call returns when those are on the host, so the host "
+                               "prepares and uploads the next actions while the egocentric kernel of this step still runs -- "
+                               "that is why this figure is close to `value`; egocentric images stay in HBM for a GPU-resident "
+                               "consumer (e2e_images_to_host has the variants that wait for them)"}
     out["compact"] = out["dense"] = None
     if getattr(env, "_ego_hits", None) is not None and args.e2e_image_steps > 0:
         steps = args.e2e_image_steps * 4
