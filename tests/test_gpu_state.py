@@ -107,16 +107,19 @@ def test_auto_reset_and_episode_statistics():
 
 
 def test_step_host_returns_the_step_results_in_pinned_memory():
-    """VecPlanEnv.step_host == step + copies: same rewards, dones and compact observation, images still in HBM."""
+    """VecPlanEnv.step_host == step + copies: same rewards, dones and compact observation; the call returns when those are
+    on the host (the egocentric kernel may still run), and the images in HBM are valid for what is enqueued next."""
     d = common.load("aisle_delays_211")
     a = common.make_vec_env(d, with_ego=True)
     b = common.make_vec_env(d, with_ego=True)
     actions = torch.from_numpy(d["actions"])                     # [E, T, 2] float32, host
     for t in range(40):
         host = actions[:, t].contiguous().pin_memory()
+        dev_copy = host.cuda()
         reward, done, obs = a.step_host(host)
+        host.zero_()                                             # the upload is over when the call returns: the buffer is the caller's again
         assert reward.is_pinned() and done.is_pinned() and obs.is_pinned()
-        _, r2, d2, _ = b.step(host.cuda())
+        _, r2, d2, _ = b.step(dev_copy)
         assert torch.equal(reward, r2.cpu()) and torch.equal(done.bool(), d2.cpu())
         assert torch.equal(obs, b.obs_vec.cpu())
         assert torch.equal(a.ego_image, b.ego_image)
