@@ -10,9 +10,12 @@ Headline workload (`config.workload`): AisleTurnEnv, tricycle robot, EnvParams(c
 state_delay=1), PlanEnv's odometry noise on (Philox4x32-10), auto-reset on done, egocentric observation assembled every
 step.  A "step" is one `VecPlanEnv.step` over all envs of the rank.  Envs shard across ranks with no data-path
 collective; the only collective is one all-reduce of the episode statistics at the end of the timed region.
-  * `value` (scaling "weak"): 65 536 envs PER GPU;
+  * `value` (scaling "weak"): 65 536 envs PER GPU.  The timed region is K calls of the user's `VecPlanEnv.step`; every
+    4th of them records CUDA events between its kernels (the per-kernel times of the roofline objects);
+  * `e2e`: the same through `VecPlanEnv.step_host`: pinned-host actions up, reward / done / observation vector down to
+    pinned host memory every step, the caller waiting for them before it submits the next actions;
   * `strong` (N > 1): BASELINE's literal "65 536 envs at 1/2/4/8 B200": 65 536 envs in TOTAL, 65 536 / N per GPU,
-    stepped through the captured CUDA graph of a step.
+    stepped the faster of two ways (`step`: dependent launches; `step_graph`: one captured graph per step).
 One JSON line is printed by rank 0.
 """
 import argparse
