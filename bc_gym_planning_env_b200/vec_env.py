@@ -565,7 +565,7 @@ class VecPlanEnv(object):
         """One env step driven from the host: `actions_host` float32 [N, 2] in pinned memory goes to the device, and
         reward (fp64 [N]), done (uint8 [N]) and the compact observation (float32 [N, 12]: delayed pose, delayed
         robot state, time, target index) come back in pinned host buffers -- what a CPU-side policy or logger needs
-        every step.  The device->host copies wait only for commit_kernel and run on a side stream while the
+        every step.  The device->host copies wait only for reward_kernel and run on a side stream while the
         egocentric kernel is still working; the images stay in HBM (`ego_image`) for a GPU-resident consumer.
         With `images` the egocentric crops (uint8 [N, H, W]) and goal_n_state (float32 [N, 9]) are copied to pinned
         host memory as well, after the egocentric kernel (N x 15.6 KB per step: the PCIe link then sets the pace).
@@ -606,7 +606,7 @@ class VecPlanEnv(object):
             self._out.ego_hits = self._out.ego_hit_count = None
             self._out.ego_hit_cap = 0
         side = io['stream']
-        side.wait_event(io['events'][3])                      # recorded right after commit_kernel
+        side.wait_event(io['events'][3])                      # recorded right after reward_kernel
         with torch.cuda.stream(side):
             io['reward'].copy_(self.reward, non_blocking=True)
             io['done'].copy_(self._done_u8, non_blocking=True)

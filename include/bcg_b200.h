@@ -180,13 +180,13 @@ typedef struct BcgBatch {
   double* init_f;  /* the state reset() restores (env.py:247,302) */
   int32_t* init_i;
   double* cand;    /* scratch [9][n_envs]: rows 0..2 = the pose the last step proposed (before the collision
-                      verdict); the split kernels (bcg_kinematic_step, BCG_STEP_KERNELS=split) use all nine   */
-  int32_t* cand_i; /* scratch [2][n_envs] of the split kernels                                              */
+                      verdict); bcg_kinematic_step writes rows 0..6 (the proposed robot state)              */
+  int32_t* cand_i; /* scratch [2][n_envs] (reserved; must be allocated)                                      */
   void* ego_work;  /* scratch [n_envs][128 bytes]: per-env affine map + source window of the egocentric crop,
-                      written by the state kernel (or bcg_observe_ego) for the egocentric kernel; may be
-                      NULL when no egocentric image is ever requested                                      */
-  void* work;      /* scratch [n_envs][192 bytes]: per-env work records (map / path / footprint references) of the
-                      stand-alone collision entry points and the split kernels                            */
+                      written by move_kernel / reward_kernel (or bcg_observe_ego) for the egocentric kernel; may
+                      be NULL when no egocentric image is ever requested                                    */
+  void* work;      /* scratch [n_envs][192 bytes]: the per-env record move_kernel leaves for reward_kernel, and the
+                      work records (map / path / footprint references) of the stand-alone collision entry points */
   const int32_t* map_id;  /* [n_envs] index into maps  */
   const int32_t* path_id; /* [n_envs] index into paths */
   const BcgMapDesc* maps;
