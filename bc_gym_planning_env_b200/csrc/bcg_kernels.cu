@@ -1868,8 +1868,11 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
   __shared__ uint16_t tlist_s[SUM ? BCG_EGS_MAX_TILES : 2];   // non-empty tiles of the window (every warp writes the same values)
   const uint32_t qword_u32 = smem_u32(qword_s[warp]), qtag_u32 = smem_u32(qtag_s[warp]), tlist_u32 = smem_u32(tlist_s);
   const uint32_t zero_u32 = smem_u32(zero_s), rec_u32 = smem_u32(rec_s);
-  extern __shared__ __align__(16) int2 egs_tab[];          // adxy[ego_w], bxy[ego_h]
-  const uint32_t adxy_u32 = smem_u32(egs_tab), bxy_u32 = adxy_u32 + 8u * (uint32_t)p.ego_w, list_u32 = smem_u32(T.list);
+  // fixed-point tables of the crop with one sentinel entry before and after each: adxy[-1 .. ego_w], bxy[-1 .. ego_h].  A
+  // candidate pixel one step outside the crop reads a sentinel, fails the test and is never stored: no clamping, and the
+  // four candidates of a cell are the table entries / image bytes at fixed offsets from the first
+  extern __shared__ __align__(16) int2 egs_tab[];
+  const uint32_t adxy_u32 = smem_u32(egs_tab) + 8u, bxy_u32 = adxy_u32 + 8u * (uint32_t)(p.ego_w + 2), list_u32 = smem_u32(T.list);
   const uint8_t* const recs = reinterpret_cast<const uint8_t*>(b.ego_work);
   const int n = b.n_envs, G = gridDim.x;
   const int ego_w = p.ego_w, ego_h = p.ego_h, npx = ego_w * ego_h;
@@ -1992,12 +1995,15 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
         const double a11 = A.a11 * 1024, a21 = A.a21 * 1024, a12 = A.a12 * 1024, a22 = A.a22 * 1024;
         const double b1 = A.b1 * 1024, b2 = A.b2 * 1024;
         const int ox = 512 - (X0 << 10), oy = 512 - (Y0 << 10);
-        for (int i = tid; i < ego_w + ego_h; i += NT) {
-          if (i < ego_w) {
-            egs_tab[i] = make_int2(__double2int_rn(a11 * i), __double2int_rn(a21 * i));
+        const int2 never = make_int2(0x40000000, 0x40000000);      // a + b - (r << 10) stays far above 1023 (mod 2^32)
+        for (int i = tid; i < ego_w + ego_h + 4; i += NT) {
+          if (i < ego_w + 2) {
+            const int u = i - 1;
+            egs_tab[i] = (u < 0 || u >= ego_w) ? never : make_int2(__double2int_rn(a11 * u), __double2int_rn(a21 * u));
           } else {
-            const int t = i - ego_w;
-            egs_tab[i] = make_int2(__double2int_rn(a12 * t + b1) + ox, __double2int_rn(a22 * t + b2) + oy);
+            const int t = i - (ego_w + 2) - 1;
+            egs_tab[i] = (t < 0 || t >= ego_h) ? never
+                                               : make_int2(__double2int_rn(a12 * t + b1) + ox, __double2int_rn(a22 * t + b2) + oy);
           }
         }
       }
@@ -2173,41 +2179,41 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
         if (fu < -1 || fu >= ego_w || fv < -1 || fv >= ego_h) continue;     // every candidate is outside the crop
         uint8_t val = 254;
         if (!LETHAL) val = __ldg(src + (int64_t)(Y0 + yr) * pitch + (X0 + xr));
-        const int u0 = max(fu, 0), u1 = min(fu + 1, ego_w - 1), v0 = max(fv, 0), v1 = min(fv + 1, ego_h - 1);
-        const uint2 a0 = lds_v2(adxy_u32 + 8u * (uint32_t)u0), a1 = lds_v2(adxy_u32 + 8u * (uint32_t)u1);
-        const uint2 b0 = lds_v2(bxy_u32 + 8u * (uint32_t)v0), b1 = lds_v2(bxy_u32 + 8u * (uint32_t)v1);
-        // (a + b) >> 10 == r  <=>  0 <= a + b - (r << 10) < 1024
-        const int xs = xr << 10, ys = yr << 10;
-        const bool h00 = (uint32_t)((int)a0.x + (int)b0.x - xs) < 1024u && (uint32_t)((int)a0.y + (int)b0.y - ys) < 1024u;
-        const bool h10 = (uint32_t)((int)a1.x + (int)b0.x - xs) < 1024u && (uint32_t)((int)a1.y + (int)b0.y - ys) < 1024u;
-        const bool h01 = (uint32_t)((int)a0.x + (int)b1.x - xs) < 1024u && (uint32_t)((int)a0.y + (int)b1.y - ys) < 1024u;
-        const bool h11 = (uint32_t)((int)a1.x + (int)b1.x - xs) < 1024u && (uint32_t)((int)a1.y + (int)b1.y - ys) < 1024u;
-        uint8_t* const row0 = dst + v0 * ego_w, * const row1 = dst + v1 * ego_w;
+        // candidates (fu | fu + 1, fv | fv + 1); fu in [-1, ego_w - 1], fv in [-1, ego_h - 1]: the outer ones are sentinels
+        const uint32_t ta = adxy_u32 + 8u * (uint32_t)fu, tb = bxy_u32 + 8u * (uint32_t)fv;
+        const uint2 a0 = lds_v2(ta), a1 = lds_v2(ta + 8u);
+        const uint2 b0 = lds_v2(tb), b1 = lds_v2(tb + 8u);
+        // (a + b) >> 10 == r  <=>  0 <= a + b - (r << 10) < 1024   (unsigned arithmetic: the sentinels may wrap)
+        const uint32_t xs = (uint32_t)xr << 10, ys = (uint32_t)yr << 10;
+        const uint32_t ax0 = a0.x - xs, ax1 = a1.x - xs, ay0 = a0.y - ys, ay1 = a1.y - ys;
+        const bool h00 = (ax0 + b0.x) < 1024u && (ay0 + b0.y) < 1024u;
+        const bool h10 = (ax1 + b0.x) < 1024u && (ay1 + b0.y) < 1024u;
+        const bool h01 = (ax0 + b1.x) < 1024u && (ay0 + b1.y) < 1024u;
+        const bool h11 = (ax1 + b1.x) < 1024u && (ay1 + b1.y) < 1024u;
+        const int o00 = fv * ego_w + fu;                                      // may lie outside the crop; only hits are stored
+        uint8_t* const p0 = dst + o00, * const p1 = p0 + ego_w;
 #ifdef BCG_EGS_EXP_NO_HITS                  // experiment: everything but the hit stores (the compiler cannot drop the tests)
         if (ego_w < 0) {
 #endif
-        if (h00) row0[u0] = val;
-        if (h10) row0[u1] = val;
-        if (h01) row1[u0] = val;
-        if (h11) row1[u1] = val;
+        if (h00) p0[0] = val;
+        if (h10) p0[1] = val;
+        if (h01) p1[0] = val;
+        if (h11) p1[1] = val;
 #ifdef BCG_EGS_EXP_NO_HITS
         }
 #endif
         if (HITS) {
           // compact observation (BcgStepOut.ego_hits): pixel offset | value << 16 of every non-zero crop pixel.  A crop
-          // pixel samples exactly one cell, so the entries of an env are distinct.
-          // (at the crop's border two candidates can be the same pixel: u0 == u1 or v0 == v1 after clamping)
-          const bool du = u1 != u0, dv = v1 != v0;
-          const bool r00 = h00, r10 = h10 && du, r01 = h01 && dv, r11 = h11 && du && dv;
-          const int nh = (int)r00 + (int)r10 + (int)r01 + (int)r11;
+          // pixel samples exactly one cell and the four candidates of a cell are distinct pixels: no duplicates.
+          const int nh = (int)h00 + (int)h10 + (int)h01 + (int)h11;
           if (nh) {
             uint32_t at = atomicAdd(&T.hits[par], (uint32_t)nh);
             uint32_t* const out = hit_list + (int64_t)e * hit_cap;
             const uint32_t tagged = (uint32_t)val << 16;
-            if (r00) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(v0 * ego_w + u0); ++at; }
-            if (r10) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(v0 * ego_w + u1); ++at; }
-            if (r01) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(v1 * ego_w + u0); ++at; }
-            if (r11) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(v1 * ego_w + u1); ++at; }
+            if (h00) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)o00; ++at; }
+            if (h10) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(o00 + 1); ++at; }
+            if (h01) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(o00 + ego_w); ++at; }
+            if (h11) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(o00 + ego_w + 1); ++at; }
           }
         }
       }
@@ -2730,7 +2736,7 @@ static int launch_ego_sparse(const BcgParams* p, const BcgBatch* b, uint8_t* ego
   if (int rc = sm_count_of_current_device(&sms)) return rc;
   // (the hand-over count and the env counter in ego_list[n_envs ..] were zeroed by the state / prep kernel)
   // persistent CTAs, as many per SM as fit with this crop's tables (18 for the 117 x 133 crop)
-  const int tab_bytes = (p->ego_w + p->ego_h) * (int)sizeof(int2);
+  const int tab_bytes = (p->ego_w + p->ego_h + 4) * (int)sizeof(int2);     // + a sentinel before and after each table
   const bool sum = b->occ_sum_arena != nullptr;
   static int per_sm_cache[2][64] = {{0}}, tab_cache[2][64] = {{0}};
   int dev = 0;

@@ -50,9 +50,10 @@ def _scatter(costmap, pose, origin, resolution):
     tested = 0
     for du in (0, 1):
         for dv in (0, 1):
-            cu = np.clip(fu + du, 0, w - 1)
-            cv = np.clip(fv + dv, 0, h - 1)
-            hit = (((adx[cu] + bdx[cv]) >> 10) == xs) & (((ady[cu] + bdy[cv]) >> 10) == ys)
+            cu, cv = fu + du, fv + dv
+            ok = (cu >= 0) & (cu < w) & (cv >= 0) & (cv < h)     # one step outside the crop: the kernel reads a sentinel that never hits
+            cu, cv = np.clip(cu, 0, w - 1), np.clip(cv, 0, h - 1)
+            hit = ok & (((adx[cu] + bdx[cv]) >> 10) == xs) & (((ady[cu] + bdy[cv]) >> 10) == ys)
             out[cv[hit], cu[hit]] = vals[hit]
             tested += len(cu)
     return out, tested
