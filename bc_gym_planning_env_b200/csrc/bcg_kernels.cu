@@ -2167,6 +2167,10 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
       const int m0 = r->fwd[0], m1 = r->fwd[1], m2 = r->fwd[2], m3 = r->fwd[3], m4 = r->fwd[4], m5 = r->fwd[5];
       // the loop is instantiated per kind of map: with every occupied cell lethal the value is a constant and the address
       // arithmetic of the cost-byte load (predicated off, but issued) is gone
+      // (the table bases and the constant go through an empty asm: the compiler otherwise re-derives the shared-memory
+      // addresses from the CTA's window and re-materialises 254 once per store, inside the loop)
+      uint32_t abase = adxy_u32, bbase = bxy_u32, lethal_value = 254u + ((uint32_t)hit_cap >> 31);   // hit_cap >= 0
+      asm volatile("" : "+r"(abase), "+r"(bbase), "+r"(lethal_value));
       auto scatter = [&](auto lethal_tag) {
       constexpr bool LETHAL = decltype(lethal_tag)::value;
       for (uint32_t i = tid; i < count; i += NT) {
@@ -2177,10 +2181,10 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
         const int fu = (m0 * xr + m1 * yr + m2) >> 16;
         const int fv = (m3 * xr + m4 * yr + m5) >> 16;
         if (fu < -1 || fu >= ego_w || fv < -1 || fv >= ego_h) continue;     // every candidate is outside the crop
-        uint8_t val = 254;
+        uint32_t val = lethal_value;
         if (!LETHAL) val = __ldg(src + (int64_t)(Y0 + yr) * pitch + (X0 + xr));
         // candidates (fu | fu + 1, fv | fv + 1); fu in [-1, ego_w - 1], fv in [-1, ego_h - 1]: the outer ones are sentinels
-        const uint32_t ta = adxy_u32 + 8u * (uint32_t)fu, tb = bxy_u32 + 8u * (uint32_t)fv;
+        const uint32_t ta = abase + 8u * (uint32_t)fu, tb = bbase + 8u * (uint32_t)fv;
         const uint2 a0 = lds_v2(ta), a1 = lds_v2(ta + 8u);
         const uint2 b0 = lds_v2(tb), b1 = lds_v2(tb + 8u);
         // (a + b) >> 10 == r  <=>  0 <= a + b - (r << 10) < 1024   (unsigned arithmetic: the sentinels may wrap)
@@ -2195,10 +2199,10 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
 #ifdef BCG_EGS_EXP_NO_HITS                  // experiment: everything but the hit stores (the compiler cannot drop the tests)
         if (ego_w < 0) {
 #endif
-        if (h00) p0[0] = val;
-        if (h10) p0[1] = val;
-        if (h01) p1[0] = val;
-        if (h11) p1[1] = val;
+        if (h00) p0[0] = (uint8_t)val;
+        if (h10) p0[1] = (uint8_t)val;
+        if (h01) p1[0] = (uint8_t)val;
+        if (h11) p1[1] = (uint8_t)val;
 #ifdef BCG_EGS_EXP_NO_HITS
         }
 #endif
@@ -2209,7 +2213,7 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
           if (nh) {
             uint32_t at = atomicAdd(&T.hits[par], (uint32_t)nh);
             uint32_t* const out = hit_list + (int64_t)e * hit_cap;
-            const uint32_t tagged = (uint32_t)val << 16;
+            const uint32_t tagged = (val & 0xffu) << 16;
             if (h00) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)o00; ++at; }
             if (h10) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(o00 + 1); ++at; }
             if (h01) { if (at < (uint32_t)hit_cap) out[at] = tagged | (uint32_t)(o00 + ego_w); ++at; }
