@@ -304,7 +304,8 @@ int bcg_state_layout(const BcgParams* p, BcgStateLayout* out);
 /* -- setup (at reset time, not per step) ------------------------------------------------------------ */
 /* derive the lethal bit-plane (cell == 254, costmap_2d.py:21) of maps [first, first+count) */
 int bcg_build_lethal_tiles(const BcgBatch* b, int32_t first, int32_t count, void* stream);
-/* derive the cell tiles (see BcgMapDesc) of maps [first, first+count) from the uint8 rows */
+/* derive the cell tiles (see BcgMapDesc) of maps [first, first+count) from the uint8 rows (CostMap2D.get_data,
+ * costmap_2d.py:91-96: the bytes extract_egocentric_costmap samples, costmap_utils.py:25-75) */
 int bcg_build_cell_tiles(const BcgBatch* b, int32_t first, int32_t count, void* stream);
 /* Host-side: encode n_widths CUtensorMaps (128 B each, cuTensorMapEncodeTiled) per costmap -- uint8
  * [H][pitch] tensor, boxes (box_w[j], box_h), zero fill outside the map (= cv2.warpAffine's
@@ -343,12 +344,15 @@ int bcg_generate_minis(const BcgParams* p, const BcgBatch* b, const BcgAisleSlot
 
 /* -- the hot path -------------------------------------------------------------------------------- */
 /* PlanEnv.step (env.py:334-361) for all envs.  actions: device [n][2] (wheel_v, wheel_angle) or
- * (v, w) for diff-drive; action_is_f64 selects fp64 vs fp32 elements.  Launches the state kernel (one thread per
- * env: control delay, robot model, collision, rollback, delay lines, reward, done, statistics, auto-reset, compact
- * observation, goal vector, egocentric record) and -- only if out->ego_image is set -- the egocentric observation:
+ * (v, w) for diff-drive; action_is_f64 selects fp64 vs fp32 elements.  Launches move_kernel (one thread per env:
+ * control delay env.py:371-373, robot model tricycle_model.py:478-538 / differential_drive.py:236-265, pose_collides
+ * env.py:464-489, rollback :452-461, delay lines :377-389, compact observation, egocentric record), reward_kernel (a
+ * group of lanes per env: reward.py:214-259, done env.py:400-419, statistics, goal vector egocentric.py:152-159,
+ * auto-reset env.py:293-303) and -- only if out->ego_image is set -- the egocentric observation (egocentric.py:125-160):
  * with the occupancy plane and ego_list the sparse scatter kernel, followed by the dense cell-tile kernel for the
- * envs it hands over unless BCG_BATCH_SPARSE_EGO_ONLY, else one dense kernel.  step_index is the caller's global step
- * counter: odometry noise is Philox4x32-10 keyed by p->seed at counter (env id, step_index, draw),
+ * envs it hands over unless BCG_BATCH_SPARSE_EGO_ONLY, else one dense kernel.  Each kernel is launched as a programmatic
+ * dependent of the one before it on `stream`.  step_index is the caller's global step counter (ignored when
+ * BcgBatch.step_counter is set): odometry noise is Philox4x32-10 keyed by p->seed at counter (env id, step_index, draw),
  * replacing the reference's global np.random (differential_drive.py:50). */
 int bcg_step(const BcgParams* p, const BcgBatch* b, const void* actions, int32_t action_is_f64,
              uint64_t step_index, const BcgStepOut* out, void* stream);
