@@ -1858,21 +1858,40 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
                                                                                    uint32_t* __restrict__ hit_list,
                                                                                    int32_t* __restrict__ hit_count,
                                                                                    const int hit_cap, const int evict_from) {
-  __shared__ __align__(128) uint8_t zero_s[BCG_EGS_ZERO_BYTES];
-  __shared__ __align__(16) EgoSparseTab T;
-  __shared__ __align__(128) uint8_t rec_s[BCG_EGS_REC_SLOTS * BCG_EGO_WORK_BYTES];
   constexpr int NT = BCG_EGS_THREADS;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  __shared__ __align__(16) uint4 qword_s[NT / 32][BCG_EGS_QCAP];
-  __shared__ uint32_t qtag_s[NT / 32][BCG_EGS_QCAP];
-  __shared__ uint16_t tlist_s[SUM ? BCG_EGS_MAX_TILES : 2];   // non-empty tiles of the window (every warp writes the same values)
-  const uint32_t qword_u32 = smem_u32(qword_s[warp]), qtag_u32 = smem_u32(qtag_s[warp]), tlist_u32 = smem_u32(tlist_s);
-  const uint32_t zero_u32 = smem_u32(zero_s), rec_u32 = smem_u32(rec_s);
+  // All static shared memory is ONE struct, and its shared-window address is kept in one register (the empty asm hides
+  // where it came from): every other address is that register plus a compile-time offset, i.e. an immediate of the
+  // load / store.  With separate __shared__ arrays the compiler re-derived each address from the CTA's window (four
+  // uniform instructions) at ~20 places of the scan and expand phases instead of spending registers on them.
+  struct EgsShared {
+    alignas(128) uint8_t zero[BCG_EGS_ZERO_BYTES];
+    alignas(128) uint8_t rec[BCG_EGS_REC_SLOTS * BCG_EGO_WORK_BYTES];
+    alignas(16) EgoSparseTab T;
+    alignas(16) uint4 qword[NT / 32][BCG_EGS_QCAP];
+    uint32_t qtag[NT / 32][BCG_EGS_QCAP];
+    uint16_t tlist[SUM ? BCG_EGS_MAX_TILES : 2];                // non-empty tiles of the window (every warp writes the same values)
+    uint16_t span[2][BCG_EGT_MAX_TILE_ROWS];                    // tile spans of the window rows, double buffered
+    int ids[8];                                                 // envs this CTA renders next
+  };
+  __shared__ EgsShared S;
+  auto& zero_s = S.zero;
+  auto& rec_s = S.rec;
+  EgoSparseTab& T = S.T;
+  auto& span_s = S.span;
+  auto& ids_s = S.ids;
+  uint32_t sbase = smem_u32(&S);
+  asm volatile("" : "+r"(sbase));
+  const uint32_t qword_u32 = sbase + (uint32_t)offsetof(EgsShared, qword) + (uint32_t)warp * (uint32_t)sizeof(S.qword[0]);
+  const uint32_t qtag_u32 = sbase + (uint32_t)offsetof(EgsShared, qtag) + (uint32_t)warp * (uint32_t)sizeof(S.qtag[0]);
+  const uint32_t tlist_u32 = sbase + (uint32_t)offsetof(EgsShared, tlist);
+  const uint32_t zero_u32 = sbase + (uint32_t)offsetof(EgsShared, zero), rec_u32 = sbase + (uint32_t)offsetof(EgsShared, rec);
   // fixed-point tables of the crop with one sentinel entry before and after each: adxy[-1 .. ego_w], bxy[-1 .. ego_h].  A
   // candidate pixel one step outside the crop reads a sentinel, fails the test and is never stored: no clamping, and the
   // four candidates of a cell are the table entries / image bytes at fixed offsets from the first
   extern __shared__ __align__(16) int2 egs_tab[];
-  const uint32_t adxy_u32 = smem_u32(egs_tab) + 8u, bxy_u32 = adxy_u32 + 8u * (uint32_t)(p.ego_w + 2), list_u32 = smem_u32(T.list);
+  const uint32_t adxy_u32 = smem_u32(egs_tab) + 8u, bxy_u32 = adxy_u32 + 8u * (uint32_t)(p.ego_w + 2);
+  const uint32_t list_u32 = sbase + (uint32_t)(offsetof(EgsShared, T) + offsetof(EgoSparseTab, list));
   const uint8_t* const recs = reinterpret_cast<const uint8_t*>(b.ego_work);
   const int n = b.n_envs, G = gridDim.x;
   const int ego_w = p.ego_w, ego_h = p.ego_h, npx = ego_w * ego_h;
@@ -1911,7 +1930,6 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
   // Which envs a CTA renders: its first RD + 1 are blockIdx.x + k G; the later ones come from a global counter
   // (ego_list[n + 1], zeroed with the hand-over count), drawn RD + 1 iterations ahead so that the record can be
   // prefetched -- CTAs whose windows are light take more envs, and the 24-or-25 envs per CTA quantisation goes away.
-  __shared__ int ids_s[8];
   if (tid <= RD) ids_s[tid] = e0 + tid * G;
 #endif
   fence_async_smem();                         // the zeros are visible to the bulk-copy engine
@@ -1919,7 +1937,6 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
   __syncthreads();
 
   // tile spans of the window rows (ego_band_span), lane <-> tile row, computed by the last warp one env ahead of their use
-  __shared__ uint16_t span_s[2][BCG_EGT_MAX_TILE_ROWS];
   auto make_spans = [&](int slot, int buf) {
     if (!BCG_EGS_SPANS || warp != NT / 32 - 1) return;
     const EgoTileWork* q = reinterpret_cast<const EgoTileWork*>(rec_s + slot * BCG_EGO_WORK_BYTES);
@@ -2016,7 +2033,7 @@ __global__ void __launch_bounds__(BCG_EGS_THREADS, BCG_EGS_CTAS) ego_sparse_kern
       const uint4* occ = reinterpret_cast<const uint4*>(b.occ_tile_arena + ((int64_t)r->tile_off16 << 4));
       const int g = lane & 3;                                                     // rows 4 g .. 4 g + 3 of the tile
       constexpr int TPR = NT / 4;                                                // tiles per round
-      const uint32_t span_u32 = smem_u32(span_s[par]);
+      const uint32_t span_u32 = sbase + (uint32_t)offsetof(EgsShared, span) + (uint32_t)par * (uint32_t)sizeof(S.span[0]);
       auto expand = [&](const uint32_t qhead, const int nitems) {
         uint4 wd = make_uint4(0u, 0u, 0u, 0u);
         uint32_t tag = 0u;
